@@ -1,0 +1,131 @@
+/* lqt_b200.h -- C-ABI of the B200-native Qwen3-TTS hot path.
+ *
+ * Drop-in boundary: these entry points are exactly what the reference's host code
+ * (leaxer-ai/leaxer-qwen3-tts, src/tts_onnx.cpp) would bind in place of its seven (+1)
+ * Ort::Session::Run call sites. Each function cites the reference interface it replaces.
+ * Plain C types only; caller-owned HOST buffers; int status (0 = ok, non-zero = error, message
+ * via lqt_last_error). One handle = one GPU = one host thread at a time (same threading contract
+ * as the reference's TTSEngine, which is not re-entrant: src/tts_onnx.h:167-190).
+ *
+ * There is no CPU fallback: lqt_create fails if no sm_100 device is present.
+ */
+#ifndef LQT_B200_H
+#define LQT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lqt_engine lqt_engine;
+
+/* src/tts_onnx.h:99-105 SamplingParams, plus the seeded-Philox extension (north_star):
+ * key = (seed, utterance_id), counter = (frame, codebook 0..15). greedy != 0 -> argmax with
+ * lowest-index tie break (== reference `--top-k 1` barring exact ties). */
+typedef struct lqt_sampling {
+    float    temperature;
+    float    top_p;
+    int32_t  top_k;
+    int32_t  max_new_tokens;
+    uint32_t seed;
+    uint32_t utterance_id;
+    int32_t  greedy;
+} lqt_sampling;
+
+typedef struct lqt_info {
+    int32_t hidden, layers, heads, kv_heads, head_dim, vocab;      /* src/tts_onnx.h:31-35 */
+    int32_t cp_vocab, cp_steps;                                    /* src/tts_onnx.h:36-37 */
+    int32_t samples_per_frame, sample_rate;                        /* 1920, 24000 (tts_onnx.h:69) */
+    int32_t has_speaker_encoder;                                   /* tts_onnx.h:161 */
+    int32_t max_pos, num_sms;
+} lqt_info;
+
+typedef struct lqt_stats {
+    uint64_t kernel_launches;     /* kernels of this library launched since create/reset */
+    uint64_t graph_launches;
+    float    last_generate_ms;    /* CUDA-event time of the last device frame loop */
+    float    last_vocoder_ms;     /* CUDA-event time of the last vocoder pass */
+    float    last_prefill_ms;
+    int32_t  last_frames;
+} lqt_stats;
+
+/* src/tts_onnx.cpp:84-130 (TTSEngine ctor) + :134-232 (load_model): loads the 7 required graph
+ * files (+ optional speaker_encoder) from model_dir. On failure returns non-zero, *out = NULL and
+ * lqt_create_error() describes why (the reference sets error_msg_ and leaves ready_ = false). */
+int lqt_create(const char* model_dir, int device_id, lqt_engine** out);
+const char* lqt_create_error(void);
+void lqt_destroy(lqt_engine* h);
+const char* lqt_last_error(lqt_engine* h);
+int lqt_get_info(lqt_engine* h, lqt_info* out);
+int lqt_get_stats(lqt_engine* h, lqt_stats* out);
+int lqt_reset_stats(lqt_engine* h);
+
+/* ---- per-graph entry points: one per Ort::Session (parity-test surface) ---------------------- */
+
+/* text_project.onnx  src/tts_onnx.cpp:545-559: input_ids i64 [1,S] -> embeds f32 [1,S,H] */
+int lqt_text_project(lqt_engine* h, const int64_t* ids, int32_t S, float* out);
+/* codec_embed.onnx  :561-590: input_ids i64 [1,N] -> embeds f32 [1,N,H] */
+int lqt_codec_embed(lqt_engine* h, const int64_t* ids, int32_t N, float* out);
+/* code_predictor_embed.onnx  :592-613: (input_ids [1,1], generation_step [1]) -> embeds [1,1,H] */
+int lqt_code_predictor_embed(lqt_engine* h, int64_t id, int64_t generation_step, float* out);
+/* talker_prefill.onnx  :615-665: inputs_embeds [1,P,H] (attention_mask is all ones, :791) ->
+ * logits of the LAST position [V] (the only row the host reads, :797-798), last_hidden [H].
+ * present_key/value stay on the device in the paged bf16 KV cache of `slot` (reset first). */
+int lqt_talker_prefill(lqt_engine* h, int32_t slot, const float* embeds, int32_t P,
+                       float* logits_last, float* last_hidden);
+/* talker_decode.onnx  :667-732: inputs_embeds [1,1,H] + past KV of `slot` -> logits [V],
+ * last_hidden [H]; KV of `slot` grows by one position. */
+int lqt_talker_decode(lqt_engine* h, int32_t slot, const float* embed,
+                      float* logits, float* last_hidden);
+int lqt_kv_reset(lqt_engine* h, int32_t slot);
+int lqt_kv_len(lqt_engine* h, int32_t slot);
+/* code_predictor.onnx  :734-757: inputs_embeds [1,L,H] (L = 2..16), generation_step [1] ->
+ * logits [cp_vocab] of head `generation_step` at the last position. */
+int lqt_code_predictor(lqt_engine* h, const float* embeds, int32_t L, int64_t generation_step,
+                       float* logits);
+/* tokenizer12hz_decode.onnx  :759-776: audio_codes i64 [1,T,16] -> audio_values f32, lengths[0].
+ * `audio` must hold T * samples_per_frame floats. */
+int lqt_vocoder_decode(lqt_engine* h, const int64_t* codes, int32_t T, float* audio,
+                       int64_t* length);
+/* speaker_encoder.onnx  :367-403: log-mel f32 [1,frames,128] -> embedding [H] */
+int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float* out);
+/* sample_token  :878-905 (+ special-token mask :803-807 when mask_codec_specials != 0) on the
+ * device sampler, Philox counter (frame, codebook). */
+int lqt_sample(lqt_engine* h, const float* logits, int32_t V, const lqt_sampling* sp,
+               uint32_t frame, uint32_t codebook, int32_t mask_codec_specials, int64_t* id);
+
+/* ---- fast path: the two nested loops on the device ------------------------------------------- */
+
+/* generate_codes + predict_subcodes  src/tts_onnx.cpp:782-872.
+ * prompt [P,H], trailing_text_hidden [trailing_len,H], tts_pad_embed [H] as built by
+ * build_prompt_embeddings (:442-539). codes_out [max_new_tokens,16] i64, *n_frames = frames
+ * produced (stops at CODEC_EOS). forced_codes (nullable, [n_forced,16]) = teacher forcing: the
+ * sampled tokens are replaced by these after sampling (parity triage); logits_trace (nullable,
+ * [max_new_tokens,16,trace_stride] f32, trace_stride >= vocab) receives every logits vector. */
+int lqt_generate(lqt_engine* h, int32_t slot, const float* prompt, int32_t P,
+                 const float* trailing, int32_t trailing_len, const float* tts_pad,
+                 const lqt_sampling* sp, const int64_t* forced_codes, int32_t n_forced,
+                 int64_t* codes_out, int32_t* n_frames, float* logits_trace, int32_t trace_stride);
+
+/* synthesize_tokens  src/tts_onnx.cpp:405-436 (speaker_embed != NULL: the clone variant
+ * :299-313): prompt assembly (:442-539) + generate + vocoder, everything on the device.
+ * lang_codec_id = language_to_codec_id(lang) (0 = Auto, tts_onnx.h:230-238).
+ * audio_out capacity in floats; *n_samples = samples written (0 = empty result, which the
+ * reference also returns when the first code is EOS, :418). codes_out nullable [max_new,16]. */
+int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids,
+                          int32_t lang_codec_id, const float* speaker_embed,
+                          const lqt_sampling* sp, float* audio_out, int64_t audio_capacity,
+                          int64_t* n_samples, int64_t* codes_out, int32_t* n_frames);
+
+/* build_prompt_embeddings  :442-539 on the device; outputs to host for parity tests.
+ * prompt_out [10,H] capacity, *P rows used; trailing_out [n_ids,H] capacity, *trailing_len. */
+int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids,
+                     int32_t lang_codec_id, const float* speaker_embed,
+                     float* prompt_out, int32_t* P, float* trailing_out, int32_t* trailing_len,
+                     float* tts_pad_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQT_B200_H */

@@ -1,0 +1,1189 @@
+// C-ABI implementation (include/lqt_b200.h): weight loading, device buffers, the captured frame
+// graph and the per-graph entry points that stand where the reference's Ort::Session::Run calls
+// were (src/tts_onnx.cpp:545-776), plus the device frame loop (:782-872).
+#include "../../include/lqt_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "lqw_loader.h"
+#include "sampler.cuh"
+#include "vocoder.cuh"
+
+using namespace lqt;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+// reference constants (src/tts_onnx.h:39-62)
+constexpr long long TTS_BOS = 151672, TTS_EOS = 151673, TTS_PAD = 151671;
+constexpr int CODEC_BOS = 2149, CODEC_EOS = 2150, CODEC_PAD = 2148;
+constexpr int CODEC_THINK = 2154, CODEC_NOTHINK = 2155, CODEC_THINK_BOS = 2156, CODEC_THINK_EOS = 2157;
+constexpr int KV_PAGE_SHIFT = 6;                 // talker KV pages of 64 positions
+constexpr int KV_PAGE = 1 << KV_PAGE_SHIFT;
+constexpr int ATT_NSPLIT = 16;
+constexpr int CP_PAGE_SHIFT = 5;                 // predictor: one fp32 page of 32 positions
+constexpr int N_CODEBOOKS = 16;
+
+std::string g_create_error;
+
+struct LayerW {
+    const float *ln1 = nullptr, *ln2 = nullptr, *qnorm = nullptr, *knorm = nullptr, *ls1 = nullptr, *ls2 = nullptr;
+    const bf16 *wqkv = nullptr, *wo = nullptr, *wgate = nullptr, *wup = nullptr, *wdown = nullptr;
+};
+
+struct Spec {
+    int hidden, layers, heads, kv_heads, head_dim, inter, vocab, max_pos;
+    int cp_hidden, cp_layers, cp_heads, cp_kv_heads, cp_inter, cp_vocab, cp_steps, cp_max_pos;
+    int text_vocab, text_dim;
+    int voc_codebook_size, voc_codebook_dim, voc_rvq_out, voc_hidden, voc_layers, voc_heads, voc_head_dim,
+        voc_inter, voc_window, voc_max_pos, voc_decoder_dim;
+    std::vector<int> voc_up_ratios, voc_up_rates;
+    int spk_mels, spk_channels, spk_layers;
+    float rms_eps, voc_rms_eps;
+    int samples_per_frame;
+};
+
+struct VocBlockW {
+    const float *snake_a, *snake_b, *tconv_b;
+    const bf16* tconv_w;
+    struct Res { const float *s1a, *s1b, *c1b, *s2a, *s2b, *c2b; const bf16 *c1w, *c2w; } res[3];
+    int cin, cout, stride;
+};
+struct VocUpW {
+    const bf16 *tconv_w, *pw1_w, *pw2_w;
+    const float *tconv_b, *dw_w, *dw_b, *ln_w, *ln_b, *pw1_b, *pw2_b, *gamma;
+    int factor;
+};
+
+}  // namespace
+
+struct lqt_engine {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    Spec sp{};
+    LqwFile f_text, f_codec, f_cpe, f_talker, f_cp, f_voc, f_spk;
+    bool has_spk = false;
+    std::string err;
+    lqt_stats stats{};
+
+    // talker / predictor weights
+    std::vector<LayerW> tl, cl;
+    const float *t_norm = nullptr, *t_cos = nullptr, *t_sin = nullptr;
+    const bf16* t_head = nullptr;
+    const float *c_norm = nullptr, *c_cos = nullptr, *c_sin = nullptr, *c_inproj_b = nullptr;
+    const bf16 *c_heads = nullptr, *c_inproj_w = nullptr;
+    const bf16 *text_embed = nullptr, *fc1w = nullptr, *fc2w = nullptr, *codec_embed = nullptr, *cp_embed = nullptr;
+    const float *fc1b = nullptr, *fc2b = nullptr;
+    // vocoder weights
+    std::vector<LayerW> vl;
+    const float *v_norm = nullptr, *v_cos = nullptr, *v_sin = nullptr;
+    const bf16 *rvq_sem_cb = nullptr, *rvq_aco_cb = nullptr, *rvq_sem_proj = nullptr, *rvq_aco_proj = nullptr;
+    const bf16 *pre_conv_w = nullptr, *dec_in_w = nullptr;
+    const float *pre_conv_b = nullptr, *dec_in_b = nullptr, *out_sa = nullptr, *out_sb = nullptr, *out_w = nullptr, *out_b = nullptr;
+    std::vector<VocUpW> vup;
+    std::vector<VocBlockW> vblk;
+
+    // decode buffers
+    float *x = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr, *last_hidden = nullptr;
+    float *cx = nullptr, *cxin = nullptr, *cqkv = nullptr, *cattn = nullptr, *cact = nullptr, *clogits = nullptr;
+    float *cp_in = nullptr, *next_in = nullptr;
+    float *partial = nullptr, *cpartial = nullptr;
+    int *counters = nullptr, *ccounters = nullptr;
+    bf16* kv_pool = nullptr;
+    float* cp_kv = nullptr;
+    int *page_tables = nullptr, *cp_page_table = nullptr, *cp_pos_consts = nullptr;
+    int n_slots = 2, max_pages = 0;
+    std::vector<int> slot_len;
+    GenState* st = nullptr;
+    GenState* st_host = nullptr;              // pinned
+    SamplingDev* sampling_dev = nullptr;
+    long long *codes_dev = nullptr, *forced_dev = nullptr;
+    float *trailing_dev = nullptr, *tts_pad_dev = nullptr, *prompt_dev = nullptr;
+    float* trace_dev = nullptr; int trace_stride = 0;
+    int max_frames_cap = 0;
+    int* token_dev = nullptr;
+    // prompt building scratch
+    long long* ids_dev = nullptr; float *tp_emb = nullptr, *tp_h = nullptr, *tp_out = nullptr; int tp_cap = 0;
+    float* spk_dev = nullptr;
+    // frame graphs keyed by slot*2 + trace
+    std::map<int, cudaGraphExec_t> graphs;
+    int kernels_per_frame = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // vocoder workspace
+    std::map<std::string, std::pair<float*, size_t>> ws;
+    long long* voc_codes_dev = nullptr; size_t voc_codes_cap = 0;
+    float* audio_dev = nullptr; size_t audio_cap = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+const T* need(lqt_engine* h, const LqwFile& f, const std::string& name, bool& ok) {
+    const DevTensor* t = f.find(name);
+    if (!t) { h->err = "missing tensor " + name; ok = false; return nullptr; }
+    return reinterpret_cast<const T*>(t->ptr);
+}
+
+bool load_layers(lqt_engine* h, const LqwFile& f, const std::string& pre, int n, bool qk_norm, bool ls,
+                 std::vector<LayerW>& out) {
+    bool ok = true;
+    out.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const std::string p = pre + "l" + std::to_string(i) + ".";
+        LayerW& L = out[i];
+        L.ln1 = need<float>(h, f, p + "ln1", ok);   L.ln2 = need<float>(h, f, p + "ln2", ok);
+        L.wqkv = need<bf16>(h, f, p + "wqkv", ok);  L.wo = need<bf16>(h, f, p + "wo", ok);
+        L.wgate = need<bf16>(h, f, p + "wgate", ok); L.wup = need<bf16>(h, f, p + "wup", ok);
+        L.wdown = need<bf16>(h, f, p + "wdown", ok);
+        if (qk_norm) { L.qnorm = need<float>(h, f, p + "qnorm", ok); L.knorm = need<float>(h, f, p + "knorm", ok); }
+        if (ls) { L.ls1 = need<float>(h, f, p + "ls1", ok); L.ls2 = need<float>(h, f, p + "ls2", ok); }
+    }
+    return ok;
+}
+
+template <typename T>
+int dalloc(lqt_engine* h, T** p, size_t n) {
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    CK(cudaMemset(*p, 0, n * sizeof(T)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+void launch_gemv(lqt_engine* h, GemvParams p, bool glu) {
+    const int opi = glu ? 2 : 4;
+    const int warps = (p.N + opi - 1) / opi;
+    int ctas = (warps + GEMV_WARPS - 1) / GEMV_WARPS;
+    ctas = std::max(1, std::min(ctas, h->num_sms * 4));
+    const int kpad = (p.K + 255) & ~255;
+    const int MT = p.M <= 1 ? 1 : (p.M == 2 ? 2 : 4);
+    dim3 grid(ctas, (p.M + MT - 1) / MT);
+    const size_t smem = (size_t)MT * kpad * sizeof(float);
+#define LQT_GEMV_LAUNCH(MTV, GLUV) gemv_kernel<MTV, GLUV><<<grid, GEMV_THREADS, smem, h->stream>>>(p)
+    if (glu) {
+        if (MT == 1) LQT_GEMV_LAUNCH(1, true); else if (MT == 2) LQT_GEMV_LAUNCH(2, true); else LQT_GEMV_LAUNCH(4, true);
+    } else {
+        if (MT == 1) LQT_GEMV_LAUNCH(1, false); else if (MT == 2) LQT_GEMV_LAUNCH(2, false); else LQT_GEMV_LAUNCH(4, false);
+    }
+#undef LQT_GEMV_LAUNCH
+    h->stats.kernel_launches++;
+}
+
+GemvParams gemv_params(const bf16* W, int N, int K, const float* x, float* y, int M = 1) {
+    GemvParams p{};
+    p.W = W; p.N = N; p.K = K; p.x = x; p.y = y; p.M = M;
+    p.x_stride = K; p.y_stride = N; p.res_stride = N;
+    return p;
+}
+
+struct XfmrCtx {               // one decoder stack (talker or predictor) in decode mode
+    const std::vector<LayerW>* layers;
+    int H, heads, kv_heads, inter;
+    float eps;
+    const float *cos, *sin;
+    float *x, *qkv, *attn, *act, *partial;
+    int* counters;
+    void* kv_pool; const int* page_table; int page_shift; long long page_stride; bool kv_bf16;
+    int nsplit;
+    const int* done;
+};
+
+// one token through all layers: x_in [H] -> ctx.x [H] (residual stream). pos_ptr = device position.
+void run_stack(lqt_engine* h, const XfmrCtx& c, const float* x_in, const int* pos_ptr) {
+    const int D = ATT_D, qd = c.heads * D, kvd = c.kv_heads * D;
+    const int PS = 1 << c.page_shift;
+    const int nl = (int)c.layers->size();
+    for (int l = 0; l < nl; ++l) {
+        const LayerW& L = (*c.layers)[l];
+        const float* xin = (l == 0) ? x_in : c.x;
+        {   // RMSNorm + QKV
+            GemvParams p = gemv_params(L.wqkv, qd + 2 * kvd, c.H, xin, c.qkv);
+            p.norm_w = L.ln1; p.eps = c.eps; p.done = c.done;
+            launch_gemv(h, p, false);
+        }
+        {   // q/k norm + RoPE + KV append + attention
+            AttnParams a{};
+            a.qkv = c.qkv; a.qnorm = L.qnorm; a.knorm = L.knorm; a.rope_cos = c.cos; a.rope_sin = c.sin;
+            a.pos_ptr = pos_ptr; a.kv_pool = c.kv_pool; a.page_table = c.page_table;
+            a.partial = c.partial; a.counters = c.counters; a.out = c.attn; a.done = c.done;
+            a.page_stride = c.page_stride;
+            a.layer_off = (long long)l * 2 * c.kv_heads * PS * D;
+            a.page_shift = c.page_shift; a.n_kv = c.kv_heads; a.eps = c.eps;
+            a.scale = 1.0f / sqrtf((float)D);
+            dim3 grid(c.kv_heads, c.nsplit);
+            const int max_pages = c.kv_bf16 ? h->max_pages : 1;
+            const size_t smem = (size_t)2 * ((max_pages + c.nsplit - 1) / c.nsplit) * PS * sizeof(float);
+            if (c.kv_bf16) attn_decode_kernel<bf16, 2><<<grid, ATT_THREADS, smem, h->stream>>>(a);
+            else           attn_decode_kernel<float, 2><<<grid, ATT_THREADS, smem, h->stream>>>(a);
+            h->stats.kernel_launches++;
+        }
+        {   // O projection + residual
+            GemvParams p = gemv_params(L.wo, c.H, qd, c.attn, c.x);
+            p.residual = xin; p.scale = L.ls1; p.done = c.done;
+            launch_gemv(h, p, false);
+        }
+        {   // RMSNorm + SwiGLU
+            GemvParams p = gemv_params(L.wgate, c.inter, c.H, c.x, c.act);
+            p.W2 = L.wup; p.norm_w = L.ln2; p.eps = c.eps; p.done = c.done;
+            launch_gemv(h, p, true);
+        }
+        {   // down projection + residual
+            GemvParams p = gemv_params(L.wdown, c.H, c.inter, c.act, c.x);
+            p.residual = c.x; p.scale = L.ls2; p.done = c.done;
+            launch_gemv(h, p, false);
+        }
+    }
+}
+
+XfmrCtx talker_ctx(lqt_engine* h, int slot, const int* done) {
+    XfmrCtx c{};
+    c.layers = &h->tl; c.H = h->sp.hidden; c.heads = h->sp.heads; c.kv_heads = h->sp.kv_heads; c.inter = h->sp.inter;
+    c.eps = h->sp.rms_eps; c.cos = h->t_cos; c.sin = h->t_sin;
+    c.x = h->x; c.qkv = h->qkv; c.attn = h->attn; c.act = h->act; c.partial = h->partial; c.counters = h->counters;
+    c.kv_pool = h->kv_pool; c.page_table = h->page_tables + (size_t)slot * h->max_pages;
+    c.page_shift = KV_PAGE_SHIFT;
+    c.page_stride = (long long)h->sp.layers * 2 * h->sp.kv_heads * KV_PAGE * ATT_D;
+    c.kv_bf16 = true; c.nsplit = ATT_NSPLIT; c.done = done;
+    return c;
+}
+
+XfmrCtx cp_ctx(lqt_engine* h, const int* done) {
+    XfmrCtx c{};
+    c.layers = &h->cl; c.H = h->sp.cp_hidden; c.heads = h->sp.cp_heads; c.kv_heads = h->sp.cp_kv_heads; c.inter = h->sp.cp_inter;
+    c.eps = h->sp.rms_eps; c.cos = h->c_cos; c.sin = h->c_sin;
+    c.x = h->cx; c.qkv = h->cqkv; c.attn = h->cattn; c.act = h->cact; c.partial = h->cpartial; c.counters = h->ccounters;
+    c.kv_pool = h->cp_kv; c.page_table = h->cp_page_table; c.page_shift = CP_PAGE_SHIFT;
+    c.page_stride = (long long)h->sp.cp_layers * 2 * h->sp.cp_kv_heads * (1 << CP_PAGE_SHIFT) * ATT_D;
+    c.kv_bf16 = false; c.nsplit = 1; c.done = done;
+    return c;
+}
+
+// talker token: x_in -> (optionally) logits + last_hidden
+void run_talker_token(lqt_engine* h, int slot, const float* x_in, bool with_head, const int* done) {
+    XfmrCtx c = talker_ctx(h, slot, done);
+    run_stack(h, c, x_in, &h->st->pos);
+    if (with_head) {
+        GemvParams p = gemv_params(h->t_head, h->sp.vocab, h->sp.hidden, h->x, h->logits);
+        p.norm_w = h->t_norm; p.eps = h->sp.rms_eps; p.xnorm_out = h->last_hidden; p.done = done;
+        launch_gemv(h, p, false);
+    }
+}
+
+// predictor token at position s (0..16). x_row is talker-width [hidden]; head_idx >= 0 -> logits.
+void run_cp_token(lqt_engine* h, const float* x_row, int s, int head_idx, const int* done) {
+    XfmrCtx c = cp_ctx(h, done);
+    const float* xin = x_row;
+    if (h->c_inproj_w) {          // 1.7B: talker width -> predictor width
+        GemvParams p = gemv_params(h->c_inproj_w, h->sp.cp_hidden, h->sp.hidden, x_row, h->cxin);
+        p.bias = h->c_inproj_b; p.done = done;
+        launch_gemv(h, p, false);
+        xin = h->cxin;
+    }
+    run_stack(h, c, xin, h->cp_pos_consts + s);
+    if (head_idx >= 0) {
+        GemvParams p = gemv_params(h->c_heads + (size_t)head_idx * h->sp.cp_vocab * h->sp.cp_hidden,
+                                   h->sp.cp_vocab, h->sp.cp_hidden, h->cx, h->clogits);
+        p.norm_w = h->c_norm; p.eps = h->sp.rms_eps; p.done = done;
+        launch_gemv(h, p, false);
+    }
+}
+
+__global__ void advance_kernel(GenState* st) {
+    if (st->done) return;
+    st->pos += 1;
+}
+
+void launch_sample(lqt_engine* h, SampleParams sp) {
+    const size_t smem = (size_t)sp.V * 20;
+    sample_kernel<<<1, SMP_THREADS, smem, h->stream>>>(sp);
+    h->stats.kernel_launches++;
+}
+
+SampleParams frame_sample_params(lqt_engine* h, int codebook, bool trace) {
+    SampleParams s{};
+    s.sp = h->sampling_dev; s.codebook = codebook; s.st = h->st; s.token_out = nullptr;
+    s.H = h->sp.hidden; s.cp_in = h->cp_in; s.next_in = h->next_in;
+    s.trailing = h->trailing_dev; s.tts_pad = h->tts_pad_dev; s.codes_out = h->codes_dev;
+    s.forced = h->forced_dev; s.eos_id = CODEC_EOS; s.n_codebooks = N_CODEBOOKS;
+    if (trace) { s.trace = h->trace_dev; s.trace_stride = h->trace_stride; }
+    if (codebook == 0) {
+        s.logits = h->logits; s.V = h->sp.vocab;
+        s.mask_lo = 2048; s.mask_hi = h->sp.vocab; s.mask_keep = CODEC_EOS;      // src/tts_onnx.cpp:803-807
+        s.embed_table = h->codec_embed;
+    } else {
+        s.logits = h->clogits; s.V = h->sp.cp_vocab;
+        s.embed_table = h->cp_embed + (size_t)(codebook - 1) * h->sp.cp_vocab * h->sp.hidden;
+    }
+    return s;
+}
+
+// one frame of loops A+B (src/tts_onnx.cpp:801-846): sample code0 -> 15 sub-codes -> talker step
+void enqueue_frame(lqt_engine* h, int slot, bool trace) {
+    const int* done = &h->st->done;
+    launch_sample(h, frame_sample_params(h, 0, trace));
+    run_cp_token(h, h->last_hidden, 0, -1, done);                 // row 0 = talker last_hidden (:859)
+    for (int s = 1; s <= h->sp.cp_steps; ++s) {
+        run_cp_token(h, h->cp_in, s, s - 1, done);                // row s = embedding of the previous code
+        launch_sample(h, frame_sample_params(h, s, trace));
+    }
+    run_talker_token(h, slot, h->next_in, true, done);            // run_decode (:845)
+    advance_kernel<<<1, 1, 0, h->stream>>>(h->st);
+    h->stats.kernel_launches++;
+}
+
+int get_frame_graph(lqt_engine* h, int slot, bool trace, cudaGraphExec_t* out) {
+    const int key = slot * 2 + (trace ? 1 : 0);
+    auto it = h->graphs.find(key);
+    if (it != h->graphs.end()) { *out = it->second; return 0; }
+    cudaGraph_t g;
+    const uint64_t before = h->stats.kernel_launches;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_frame(h, slot, trace);
+    CK(cudaStreamEndCapture(h->stream, &g));
+    h->kernels_per_frame = (int)(h->stats.kernel_launches - before);
+    h->stats.kernel_launches = before;                 // capture does not execute
+    cudaGraphExec_t ge;
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    h->graphs[key] = ge;
+    *out = ge;
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// part 2: embeddings, prompt assembly, vocoder pipeline, generation loop, C-ABI
+// ================================================================================================
+namespace {
+
+__global__ void gather_rows_kernel(const bf16* __restrict__ table, const long long* __restrict__ ids,
+                                   int width, float* __restrict__ out) {
+    const long long id = ids[blockIdx.x];
+    const bf16* row = table + (size_t)id * width;
+    for (int i = threadIdx.x; i < width; i += blockDim.x)
+        out[(size_t)blockIdx.x * width + i] = __bfloat162float(row[i]);
+}
+
+// out[r][:] = tp[desc[r].x] (if >=0) + codec_embed[desc[r].y] (if >=0) + spk (if desc[r].z)
+__global__ void assemble_rows_kernel(const int* __restrict__ desc, const float* __restrict__ tp,
+                                     const bf16* __restrict__ codec, const float* __restrict__ spk,
+                                     int H, float* __restrict__ out) {
+    const int r = blockIdx.x;
+    const int ti = desc[r * 3], ci = desc[r * 3 + 1], sf = desc[r * 3 + 2];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        float v = 0.f;
+        if (ti >= 0) v = tp[(size_t)ti * H + i];
+        if (ci >= 0) v = v + __bfloat162float(codec[(size_t)ci * H + i]);
+        if (sf) v = v + spk[i];
+        out[(size_t)r * H + i] = v;
+    }
+}
+
+float* wsbuf(lqt_engine* h, const std::string& name, size_t n) {
+    auto& e = h->ws[name];
+    if (e.second < n) {
+        if (e.first) cudaFree(e.first);
+        e.first = nullptr; e.second = 0;
+        if (cudaMalloc((void**)&e.first, n * sizeof(float)) != cudaSuccess) { h->err = "workspace cudaMalloc failed: " + name; return nullptr; }
+        e.second = n;
+    }
+    return e.first;
+}
+
+void launch_conv_gemm(lqt_engine* h, ConvGemmParams p) {
+    if (p.bias_mod <= 0) p.bias_mod = p.N;
+    if (p.dil <= 0) p.dil = 1;
+    if (p.taps <= 0) p.taps = 1;
+    dim3 grid((p.L + CG_BM - 1) / CG_BM, (p.N + CG_BN - 1) / CG_BN);
+    conv_gemm_kernel<<<grid, CG_THREADS, 0, h->stream>>>(p);
+    h->stats.kernel_launches++;
+}
+
+ConvGemmParams cg(const float* x, int L, int Cin, const bf16* W, int N, float* y) {
+    ConvGemmParams p{};
+    p.x = x; p.L = L; p.Cin = Cin; p.W = W; p.N = N; p.y = y; p.taps = 1; p.dil = 1; p.bias_mod = N;
+    return p;
+}
+
+void launch_snake(lqt_engine* h, const float* x, float* y, long long n, int C, const float* a, const float* b) {
+    const long long n4 = n / 4;
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16);
+    snake_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(x, y, n4, C, a, b);
+    h->stats.kernel_launches++;
+}
+
+// text_project.onnx on the device: ids_dev [S] -> tp_out [S][H]
+int run_text_project(lqt_engine* h, const long long* ids_dev, int S, float* out) {
+    const int Dt = h->sp.text_dim, H = h->sp.hidden;
+    float* emb = wsbuf(h, "tp_emb", (size_t)S * Dt);
+    float* hid = wsbuf(h, "tp_hid", (size_t)S * Dt);
+    if (!emb || !hid) return 1;
+    gather_rows_kernel<<<S, 256, 0, h->stream>>>(h->text_embed, ids_dev, Dt, emb);
+    h->stats.kernel_launches++;
+    GemvParams p1 = gemv_params(h->fc1w, Dt, Dt, emb, hid, S);
+    p1.bias = h->fc1b; p1.act = 1;
+    launch_gemv(h, p1, false);
+    GemvParams p2 = gemv_params(h->fc2w, H, Dt, hid, out, S);
+    p2.bias = h->fc2b;
+    launch_gemv(h, p2, false);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// build_prompt_embeddings (src/tts_onnx.cpp:442-539) -> h->prompt_dev [P][H], h->trailing_dev, h->tts_pad_dev
+int build_prompt_device(lqt_engine* h, const int64_t* ids, int n, int lang_id, const float* spk_host,
+                        int* P_out, int* trailing_len_out) {
+    if (n < 5) { h->err = "token_ids must hold at least 5 ids (role x3, >=1 text, 2 trailer)"; return 1; }
+    const int H = h->sp.hidden;
+    const int n_text_rest = std::max(0, n - 6);              // ids[4 .. n-3]
+    if (n_text_rest + 1 > h->sp.max_pos) { h->err = "text too long"; return 1; }
+    std::vector<long long> all = {TTS_BOS, TTS_EOS, TTS_PAD, ids[0], ids[1], ids[2], ids[3]};
+    for (int i = 4; i < n - 2; ++i) all.push_back(ids[i]);
+    for (long long v : all)
+        if (v < 0 || v >= h->sp.text_vocab) { h->err = "text token id out of range"; return 1; }
+    const int S = (int)all.size();
+    long long* ids_dev = (long long*)wsbuf(h, "tp_ids", (size_t)S * 2);
+    float* tp = wsbuf(h, "tp_out", (size_t)S * H);
+    if (!ids_dev || !tp) return 1;
+    CK(cudaMemcpyAsync(ids_dev, all.data(), S * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (run_text_project(h, ids_dev, S, tp)) return 1;
+    if (spk_host) CK(cudaMemcpyAsync(h->spk_dev, spk_host, H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+
+    std::vector<int> prefill;                                                   // :466-476
+    if (lang_id == 0) prefill = {CODEC_NOTHINK, CODEC_THINK_BOS, CODEC_THINK_EOS};
+    else prefill = {CODEC_THINK, CODEC_THINK_BOS, lang_id, CODEC_THINK_EOS};
+    prefill.push_back(CODEC_PAD); prefill.push_back(CODEC_BOS);
+    std::vector<std::pair<int, int>> cod;                                       // (codec id, is_speaker)
+    for (size_t i = 0; i + 1 < prefill.size(); ++i) cod.push_back({prefill[i], 0});
+    if (spk_host) cod.push_back({-1, 1});                                       // :481-490
+    cod.push_back({prefill.back(), 0});
+    const int pad_count = (int)prefill.size() - 2 + (spk_host ? 1 : 0);         // :497-498
+    std::vector<int> desc;
+    auto row = [&](int tpi, int ci, int sf) { desc.push_back(tpi); desc.push_back(ci); desc.push_back(sf); };
+    row(3, -1, 0); row(4, -1, 0); row(5, -1, 0);                                // role (:493-494)
+    for (int i = 0; i < pad_count; ++i) row(2, cod[i].first, cod[i].second);    // tts_pad + codec (:499-512)
+    row(0, cod[pad_count].first, cod[pad_count].second);                        // tts_bos + codec/speaker
+    row(6, cod[pad_count + 1].first, cod[pad_count + 1].second);                // first text + codec_bos (:515-520)
+    const int P = (int)desc.size() / 3;
+    for (int i = 0; i < n_text_rest; ++i) row(7 + i, -1, 0);                    // trailing (:530-534)
+    row(1, -1, 0);                                                              // tts_eos (:535)
+    const int TL = n_text_rest + 1;
+    row(2, -1, 0);                                                              // tts_pad_embed_ (:463)
+    const int rows = (int)desc.size() / 3;
+    int* desc_dev = (int*)wsbuf(h, "tp_desc", desc.size());
+    float* asm_out = wsbuf(h, "tp_asm", (size_t)rows * H);
+    if (!desc_dev || !asm_out) return 1;
+    CK(cudaMemcpyAsync(desc_dev, desc.data(), desc.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    assemble_rows_kernel<<<rows, 256, 0, h->stream>>>(desc_dev, tp, h->codec_embed, h->spk_dev, H, asm_out);
+    h->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(h->prompt_dev, asm_out, (size_t)P * H * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->trailing_dev, asm_out + (size_t)P * H, (size_t)TL * H * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tts_pad_dev, asm_out + (size_t)(P + TL) * H, (size_t)H * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));      // desc/all vectors go out of scope
+    *P_out = P; *trailing_len_out = TL;
+    return 0;
+}
+
+// tokenizer12hz_decode (src/tts_onnx.cpp:759-776) on device codes [T][16] -> audio_dev [T*spf]
+int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio) {
+    const Spec& s = h->sp;
+    const int Dc = s.voc_codebook_dim, R = s.voc_rvq_out, Cv = s.voc_hidden, I = s.voc_inter;
+    const int vqd = s.voc_heads * s.voc_head_dim;
+    if (T > s.voc_max_pos) { h->err = "vocoder: too many frames"; return 1; }
+    // largest activation (elements) over all stages
+    size_t maxel = (size_t)T * std::max(std::max(3 * vqd, I), std::max(Cv, R));
+    {
+        size_t L = T;
+        for (int f : s.voc_up_ratios) { L *= f; maxel = std::max(maxel, L * (size_t)(4 * Cv)); }
+        maxel = std::max(maxel, L * (size_t)s.voc_decoder_dim);
+        int c = s.voc_decoder_dim;
+        for (int r : s.voc_up_rates) { L *= r; c /= 2; maxel = std::max(maxel, L * (size_t)c); }
+    }
+    float* b0 = wsbuf(h, "v0", maxel); float* b1 = wsbuf(h, "v1", maxel);
+    float* b2 = wsbuf(h, "v2", maxel); float* b3 = wsbuf(h, "v3", maxel);
+    if (!b0 || !b1 || !b2 || !b3) return 1;
+
+    // RVQ gather-sum + 1x1 output projections
+    float *sem = b1, *aco = b2;
+    rvq_gather_kernel<<<T, 256, 0, h->stream>>>(codes_dev, T, N_CODEBOOKS, h->rvq_sem_cb, h->rvq_aco_cb,
+                                                s.voc_codebook_size, Dc, sem, aco);
+    h->stats.kernel_launches++;
+    launch_conv_gemm(h, cg(sem, T, Dc, h->rvq_sem_proj, R, b0));
+    { ConvGemmParams p = cg(aco, T, Dc, h->rvq_aco_proj, R, b0); p.residual = b0; launch_conv_gemm(h, p); }
+    // pre_conv k3
+    float* xa = b3;
+    { ConvGemmParams p = cg(b0, T, R, h->pre_conv_w, Cv, xa); p.taps = 3; p.bias = h->pre_conv_b; launch_conv_gemm(h, p); }
+    // pre-transformer (sliding-window attention, LayerScale)
+    for (int l = 0; l < s.voc_layers; ++l) {
+        const LayerW& L = h->vl[l];
+        rmsnorm_rows_kernel<<<(T + 7) / 8, 256, 0, h->stream>>>(xa, b0, T, Cv, L.ln1, s.voc_rms_eps);
+        h->stats.kernel_launches++;
+        launch_conv_gemm(h, cg(b0, T, Cv, L.wqkv, 3 * vqd, b1));
+        WinAttnParams w{};
+        w.qkv = b1; w.out = b2; w.rope_cos = h->v_cos; w.rope_sin = h->v_sin; w.T = T; w.n_heads = s.voc_heads;
+        w.window = s.voc_window; w.scale = 1.0f / sqrtf((float)s.voc_head_dim);
+        window_attn_kernel<<<(int)(((long long)T * s.voc_heads + 7) / 8), 256, 0, h->stream>>>(w);
+        h->stats.kernel_launches++;
+        { ConvGemmParams p = cg(b2, T, vqd, L.wo, Cv, xa); p.scale = L.ls1; p.residual = xa; launch_conv_gemm(h, p); }
+        rmsnorm_rows_kernel<<<(T + 7) / 8, 256, 0, h->stream>>>(xa, b0, T, Cv, L.ln2, s.voc_rms_eps);
+        h->stats.kernel_launches++;
+        launch_conv_gemm(h, cg(b0, T, Cv, L.wgate, I, b1));
+        launch_conv_gemm(h, cg(b0, T, Cv, L.wup, I, b2));
+        silu_mul_kernel<<<std::min((int)(((size_t)T * I + 255) / 256), h->num_sms * 16), 256, 0, h->stream>>>(b1, b2, b1, (long long)T * I);
+        h->stats.kernel_launches++;
+        { ConvGemmParams p = cg(b1, T, I, L.wdown, Cv, xa); p.scale = L.ls2; p.residual = xa; launch_conv_gemm(h, p); }
+    }
+    rmsnorm_rows_kernel<<<(T + 7) / 8, 256, 0, h->stream>>>(xa, b0, T, Cv, h->v_norm, s.voc_rms_eps);
+    h->stats.kernel_launches++;
+    // upsample stages: transposed conv (kernel = stride) + ConvNeXt
+    float* cur = b0; float* o1 = b1; float* o2 = b2; float* o3 = b3;
+    int L = T;
+    for (size_t u = 0; u < h->vup.size(); ++u) {
+        const VocUpW& U = h->vup[u];
+        { ConvGemmParams p = cg(cur, L, Cv, U.tconv_w, U.factor * Cv, o1); p.bias = U.tconv_b; p.bias_mod = Cv; launch_conv_gemm(h, p); }
+        L *= U.factor;
+        dwconv_ln_kernel<<<L, 256, Cv * sizeof(float), h->stream>>>(o1, o2, L, Cv, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f);
+        h->stats.kernel_launches++;
+        { ConvGemmParams p = cg(o2, L, Cv, U.pw1_w, 4 * Cv, o3); p.bias = U.pw1_b; p.act = 3; launch_conv_gemm(h, p); }
+        { ConvGemmParams p = cg(o3, L, 4 * Cv, U.pw2_w, Cv, cur); p.bias = U.pw2_b; p.scale = U.gamma; p.residual = o1; launch_conv_gemm(h, p); }
+    }
+    // decoder
+    { ConvGemmParams p = cg(cur, L, Cv, h->dec_in_w, s.voc_decoder_dim, o1); p.taps = 7; p.bias = h->dec_in_b; launch_conv_gemm(h, p); }
+    float* t = o1;                       // running activation
+    float* fa = cur; float* fb = o2;                      // free buffers (o3 unused from here)
+    for (size_t b = 0; b < h->vblk.size(); ++b) {
+        const VocBlockW& B = h->vblk[b];
+        launch_snake(h, t, fa, (long long)L * B.cin, B.cin, B.snake_a, B.snake_b);
+        { ConvGemmParams p = cg(fa, L, B.cin, B.tconv_w, B.stride * B.cout, fb); p.taps = 2; p.tap_rev = 1; p.bias = B.tconv_b; p.bias_mod = B.cout; launch_conv_gemm(h, p); }
+        L *= B.stride;
+        std::swap(t, fb);                // t = tconv output; fb = old t (free)
+        const int dil[3] = {1, 3, 9};
+        for (int r = 0; r < 3; ++r) {
+            const auto& Rr = B.res[r];
+            launch_snake(h, t, fa, (long long)L * B.cout, B.cout, Rr.s1a, Rr.s1b);
+            { ConvGemmParams p = cg(fa, L, B.cout, Rr.c1w, B.cout, fb); p.taps = 7; p.dil = dil[r]; p.bias = Rr.c1b; launch_conv_gemm(h, p); }
+            launch_snake(h, fb, fa, (long long)L * B.cout, B.cout, Rr.s2a, Rr.s2b);
+            { ConvGemmParams p = cg(fa, L, B.cout, Rr.c2w, B.cout, t); p.bias = Rr.c2b; p.residual = t; launch_conv_gemm(h, p); }
+        }
+    }
+    const int Cl = h->vblk.empty() ? s.voc_decoder_dim : h->vblk.back().cout;
+    launch_snake(h, t, fa, (long long)L * Cl, Cl, h->out_sa, h->out_sb);
+    conv_out_kernel<<<(L + 7) / 8, 256, 0, h->stream>>>(fa, audio, L, Cl, h->out_w, h->out_b);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ensure_audio(lqt_engine* h, int T) {
+    const size_t need_codes = (size_t)T * N_CODEBOOKS, need_audio = (size_t)T * h->sp.samples_per_frame;
+    if (h->voc_codes_cap < need_codes) {
+        if (h->voc_codes_dev) cudaFree(h->voc_codes_dev);
+        CK(cudaMalloc((void**)&h->voc_codes_dev, need_codes * sizeof(long long)));
+        h->voc_codes_cap = need_codes;
+    }
+    if (h->audio_cap < need_audio) {
+        if (h->audio_dev) cudaFree(h->audio_dev);
+        CK(cudaMalloc((void**)&h->audio_dev, need_audio * sizeof(float)));
+        h->audio_cap = need_audio;
+    }
+    return 0;
+}
+
+int upload_sampling(lqt_engine* h, const lqt_sampling* sp) {
+    SamplingDev d{sp->temperature, sp->top_p, sp->top_k, sp->greedy, sp->seed, sp->utterance_id};
+    CK(cudaMemcpyAsync(h->sampling_dev, &d, sizeof(d), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// loops A+B on the device. prompt_dev / trailing_dev / tts_pad_dev / forced_dev already filled.
+int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sampling* sp, int n_forced,
+                  bool trace, int* n_frames_out) {
+    if (slot < 0 || slot >= h->n_slots) { h->err = "bad slot"; return 1; }
+    if (P < 1 || sp->max_new_tokens < 0 || sp->max_new_tokens > h->max_frames_cap ||
+        P + sp->max_new_tokens > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
+    cudaGraphExec_t graph;
+    if (get_frame_graph(h, slot, trace, &graph)) return 1;
+    if (upload_sampling(h, sp)) return 1;
+    GenState g{};
+    g.pos = 0; g.frame = 0; g.done = 0; g.n_frames = 0; g.trailing_len = trailing_len;
+    g.max_frames = sp->max_new_tokens; g.cp_pos = 0; g.n_forced = n_forced;
+    *h->st_host = g;
+    CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    // prefill (src/tts_onnx.cpp:794): P decode-shaped steps, head only on the last row
+    const int H = h->sp.hidden;
+    for (int i = 0; i < P; ++i) {
+        run_talker_token(h, slot, h->prompt_dev + (size_t)i * H, i == P - 1, nullptr);
+        advance_kernel<<<1, 1, 0, h->stream>>>(h->st);
+        h->stats.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    cudaEvent_t evg0, evg1, evpoll;
+    CK(cudaEventCreate(&evg0)); CK(cudaEventCreate(&evg1)); CK(cudaEventCreateWithFlags(&evpoll, cudaEventDisableTiming));
+    CK(cudaEventRecord(evg0, h->stream));
+    bool poll_pending = false;
+    int launched = 0;
+    for (int f = 0; f < sp->max_new_tokens; ++f) {
+        CK(cudaGraphLaunch(graph, h->stream));
+        h->stats.graph_launches++;
+        h->stats.kernel_launches += h->kernels_per_frame;
+        ++launched;
+        if ((f & 7) == 7) {
+            if (poll_pending && cudaEventQuery(evpoll) == cudaSuccess) {
+                poll_pending = false;
+                if (h->st_host->done) break;
+            }
+            if (!poll_pending) {
+                CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaEventRecord(evpoll, h->stream));
+                poll_pending = true;
+            }
+        }
+    }
+    CK(cudaEventRecord(evg1, h->stream));
+    CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    cudaEventElapsedTime(&h->stats.last_prefill_ms, h->ev0, h->ev1);
+    cudaEventElapsedTime(&h->stats.last_generate_ms, evg0, evg1);
+    cudaEventDestroy(evg0); cudaEventDestroy(evg1); cudaEventDestroy(evpoll);
+    h->slot_len[slot] = h->st_host->pos;
+    *n_frames_out = h->st_host->n_frames;
+    h->stats.last_frames = h->st_host->n_frames;
+    return 0;
+}
+
+int ensure_trace(lqt_engine* h, int frames, int stride) {
+    const size_t need_n = (size_t)std::max(frames, 1) * N_CODEBOOKS * stride;
+    auto& e = h->ws["trace"];
+    if (e.second < need_n || h->trace_stride != stride || h->trace_dev != e.first) {
+        for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+            if (it->first & 1) { cudaGraphExecDestroy(it->second); it = h->graphs.erase(it); } else ++it;
+        }
+        float* p = wsbuf(h, "trace", need_n);
+        if (!p) return 1;
+        h->trace_dev = p; h->trace_stride = stride;
+    }
+    CK(cudaMemsetAsync(h->trace_dev, 0, need_n * sizeof(float), h->stream));
+    return 0;
+}
+
+bool load_vocoder_weights(lqt_engine* h) {
+    bool ok = true;
+    const LqwFile& f = h->f_voc;
+    const Spec& s = h->sp;
+    h->rvq_sem_cb = need<bf16>(h, f, "rvq.sem.codebook", ok);  h->rvq_sem_proj = need<bf16>(h, f, "rvq.sem.out_proj", ok);
+    h->rvq_aco_cb = need<bf16>(h, f, "rvq.aco.codebook", ok);  h->rvq_aco_proj = need<bf16>(h, f, "rvq.aco.out_proj", ok);
+    h->pre_conv_w = need<bf16>(h, f, "pre_conv.weight", ok);   h->pre_conv_b = need<float>(h, f, "pre_conv.bias", ok);
+    ok = load_layers(h, f, "pt.", s.voc_layers, false, true, h->vl) && ok;
+    h->v_norm = need<float>(h, f, "pt.norm", ok);
+    h->v_cos = need<float>(h, f, "pt.rope_cos", ok); h->v_sin = need<float>(h, f, "pt.rope_sin", ok);
+    for (size_t u = 0; u < s.voc_up_ratios.size(); ++u) {
+        const std::string p = "up" + std::to_string(u) + ".";
+        VocUpW U{};
+        U.factor = s.voc_up_ratios[u];
+        U.tconv_w = need<bf16>(h, f, p + "tconv.weight", ok); U.tconv_b = need<float>(h, f, p + "tconv.bias", ok);
+        U.dw_w = need<float>(h, f, p + "dw.weight", ok); U.dw_b = need<float>(h, f, p + "dw.bias", ok);
+        U.ln_w = need<float>(h, f, p + "ln.weight", ok); U.ln_b = need<float>(h, f, p + "ln.bias", ok);
+        U.pw1_w = need<bf16>(h, f, p + "pw1.weight", ok); U.pw1_b = need<float>(h, f, p + "pw1.bias", ok);
+        U.pw2_w = need<bf16>(h, f, p + "pw2.weight", ok); U.pw2_b = need<float>(h, f, p + "pw2.bias", ok);
+        U.gamma = need<float>(h, f, p + "gamma", ok);
+        h->vup.push_back(U);
+    }
+    h->dec_in_w = need<bf16>(h, f, "dec.conv_in.weight", ok); h->dec_in_b = need<float>(h, f, "dec.conv_in.bias", ok);
+    int cin = s.voc_decoder_dim;
+    for (size_t b = 0; b < s.voc_up_rates.size(); ++b) {
+        const std::string p = "dec.b" + std::to_string(b) + ".";
+        VocBlockW B{};
+        B.cin = cin; B.cout = cin / 2; B.stride = s.voc_up_rates[b];
+        B.snake_a = need<float>(h, f, p + "snake.alpha", ok); B.snake_b = need<float>(h, f, p + "snake.beta", ok);
+        B.tconv_w = need<bf16>(h, f, p + "tconv.weight", ok); B.tconv_b = need<float>(h, f, p + "tconv.bias", ok);
+        for (int r = 0; r < 3; ++r) {
+            const std::string q = p + "r" + std::to_string(r) + ".";
+            auto& R = B.res[r];
+            R.s1a = need<float>(h, f, q + "snake1.alpha", ok); R.s1b = need<float>(h, f, q + "snake1.beta", ok);
+            R.c1w = need<bf16>(h, f, q + "conv1.weight", ok);  R.c1b = need<float>(h, f, q + "conv1.bias", ok);
+            R.s2a = need<float>(h, f, q + "snake2.alpha", ok); R.s2b = need<float>(h, f, q + "snake2.beta", ok);
+            R.c2w = need<bf16>(h, f, q + "conv2.weight", ok);  R.c2b = need<float>(h, f, q + "conv2.bias", ok);
+        }
+        h->vblk.push_back(B);
+        cin /= 2;
+    }
+    h->out_sa = need<float>(h, f, "dec.snake_out.alpha", ok); h->out_sb = need<float>(h, f, "dec.snake_out.beta", ok);
+    h->out_w = need<float>(h, f, "dec.conv_out.weight", ok);  h->out_b = need<float>(h, f, "dec.conv_out.bias", ok);
+    return ok;
+}
+
+// opt in to large dynamic shared memory once, outside any stream capture
+int prime_kernel_attributes(lqt_engine* h) {
+    const int big = 160 * 1024;
+    CK(cudaFuncSetAttribute(gemv_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(gemv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(gemv_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(gemv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(gemv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(gemv_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    return 0;
+}
+
+int init_engine(lqt_engine* h, const std::string& dir) {
+    if (prime_kernel_attributes(h)) return 1;
+    struct { const char* name; LqwFile* f; bool required; } files[] = {
+        {"text_project", &h->f_text, true}, {"codec_embed", &h->f_codec, true},
+        {"code_predictor_embed", &h->f_cpe, true}, {"talker_prefill", &h->f_talker, true},
+        {"code_predictor", &h->f_cp, true}, {"tokenizer12hz_decode", &h->f_voc, true},
+        {"speaker_encoder", &h->f_spk, false}};
+    // talker_decode.lqw must exist too (7-file layout, src/tts_onnx.cpp:91-104) but shares talker_prefill's tensors
+    {
+        FILE* t = std::fopen((dir + "/talker_decode.lqw").c_str(), "rb");
+        if (!t) { h->err = "Failed to load required model files: talker_decode.lqw missing"; return 1; }
+        std::fclose(t);
+    }
+    for (auto& e : files) {
+        const std::string path = dir + "/" + e.name + ".lqw";
+        FILE* t = std::fopen(path.c_str(), "rb");
+        if (!t) {
+            if (e.required) { h->err = std::string("Failed to load required model files: ") + e.name + ".lqw missing"; return 1; }
+            continue;
+        }
+        std::fclose(t);
+        const std::string er = load_lqw(path, *e.f);
+        if (!er.empty()) { h->err = er; return 1; }
+        if (e.f == &h->f_spk) h->has_spk = true;
+    }
+    const LqwFile& m = h->f_talker;
+    Spec& s = h->sp;
+    s.hidden = m.meta_int("hidden", 1024); s.layers = m.meta_int("layers", 28); s.heads = m.meta_int("heads", 16);
+    s.kv_heads = m.meta_int("kv_heads", 8); s.head_dim = m.meta_int("head_dim", 128); s.inter = m.meta_int("inter", 3072);
+    s.vocab = m.meta_int("vocab", 3072); s.max_pos = m.meta_int("max_pos", 2304);
+    s.cp_hidden = m.meta_int("cp_hidden", 1024); s.cp_layers = m.meta_int("cp_layers", 5); s.cp_heads = m.meta_int("cp_heads", 16);
+    s.cp_kv_heads = m.meta_int("cp_kv_heads", 8); s.cp_inter = m.meta_int("cp_inter", 3072); s.cp_vocab = m.meta_int("cp_vocab", 2048);
+    s.cp_steps = m.meta_int("cp_steps", 15); s.cp_max_pos = m.meta_int("cp_max_pos", 32);
+    s.text_vocab = m.meta_int("text_vocab", 151936); s.text_dim = m.meta_int("text_dim", 2048);
+    s.voc_codebook_size = m.meta_int("voc_codebook_size", 2048); s.voc_codebook_dim = m.meta_int("voc_codebook_dim", 256);
+    s.voc_rvq_out = m.meta_int("voc_rvq_out", 512); s.voc_hidden = m.meta_int("voc_hidden", 1024);
+    s.voc_layers = m.meta_int("voc_layers", 8); s.voc_heads = m.meta_int("voc_heads", 16); s.voc_head_dim = m.meta_int("voc_head_dim", 64);
+    s.voc_inter = m.meta_int("voc_inter", 3072); s.voc_window = m.meta_int("voc_window", 72); s.voc_max_pos = m.meta_int("voc_max_pos", 2304);
+    s.voc_decoder_dim = m.meta_int("voc_decoder_dim", 1536);
+    s.voc_up_ratios = m.meta_ints("voc_upsampling_ratios"); s.voc_up_rates = m.meta_ints("voc_upsample_rates");
+    s.spk_mels = m.meta_int("spk_mels", 128); s.spk_channels = m.meta_int("spk_channels", 512); s.spk_layers = m.meta_int("spk_layers", 3);
+    s.rms_eps = (float)m.meta_f("rms_eps", 1e-6); s.voc_rms_eps = (float)m.meta_f("voc_rms_eps", 1e-5);
+    s.samples_per_frame = 1;
+    for (int v : s.voc_up_ratios) s.samples_per_frame *= v;
+    for (int v : s.voc_up_rates) s.samples_per_frame *= v;
+    if (s.head_dim != ATT_D || s.voc_head_dim != 64) { h->err = "unsupported head_dim"; return 1; }
+    if (s.heads != 2 * s.kv_heads || s.cp_heads != 2 * s.cp_kv_heads) { h->err = "unsupported GQA ratio (need 2)"; return 1; }
+    if (s.cp_steps != N_CODEBOOKS - 1 || s.cp_steps + 2 > (1 << CP_PAGE_SHIFT)) { h->err = "unsupported cp_steps"; return 1; }
+    if (s.vocab > SMP_MAXV || s.cp_vocab > SMP_MAXV) { h->err = "vocab too large for the sampler"; return 1; }
+    if ((s.hidden % 8) || (s.inter % 8) || (s.text_dim % 8)) { h->err = "dims must be multiples of 8"; return 1; }
+
+    bool ok = true;
+    h->text_embed = need<bf16>(h, h->f_text, "embed", ok);
+    h->fc1w = need<bf16>(h, h->f_text, "fc1.weight", ok); h->fc1b = need<float>(h, h->f_text, "fc1.bias", ok);
+    h->fc2w = need<bf16>(h, h->f_text, "fc2.weight", ok); h->fc2b = need<float>(h, h->f_text, "fc2.bias", ok);
+    h->codec_embed = need<bf16>(h, h->f_codec, "embed", ok);
+    h->cp_embed = need<bf16>(h, h->f_cpe, "embed", ok);
+    ok = load_layers(h, h->f_talker, "", s.layers, true, false, h->tl) && ok;
+    h->t_norm = need<float>(h, h->f_talker, "norm", ok); h->t_head = need<bf16>(h, h->f_talker, "head", ok);
+    h->t_cos = need<float>(h, h->f_talker, "rope_cos", ok); h->t_sin = need<float>(h, h->f_talker, "rope_sin", ok);
+    ok = load_layers(h, h->f_cp, "", s.cp_layers, true, false, h->cl) && ok;
+    h->c_norm = need<float>(h, h->f_cp, "norm", ok); h->c_heads = need<bf16>(h, h->f_cp, "heads", ok);
+    h->c_cos = need<float>(h, h->f_cp, "rope_cos", ok); h->c_sin = need<float>(h, h->f_cp, "rope_sin", ok);
+    if (s.hidden != s.cp_hidden) {
+        h->c_inproj_w = need<bf16>(h, h->f_cp, "in_proj.weight", ok); h->c_inproj_b = need<float>(h, h->f_cp, "in_proj.bias", ok);
+    }
+    ok = load_vocoder_weights(h) && ok;
+    if (!ok) return 1;
+
+    const int H = s.hidden, Hc = s.cp_hidden, D = ATT_D;
+    if (dalloc(h, &h->x, H) || dalloc(h, &h->qkv, (s.heads + 2 * s.kv_heads) * D) || dalloc(h, &h->attn, s.heads * D) ||
+        dalloc(h, &h->act, s.inter) || dalloc(h, &h->logits, s.vocab) || dalloc(h, &h->last_hidden, H) ||
+        dalloc(h, &h->cx, Hc) || dalloc(h, &h->cxin, Hc) || dalloc(h, &h->cqkv, (s.cp_heads + 2 * s.cp_kv_heads) * D) ||
+        dalloc(h, &h->cattn, s.cp_heads * D) || dalloc(h, &h->cact, s.cp_inter) || dalloc(h, &h->clogits, s.cp_vocab) ||
+        dalloc(h, &h->cp_in, H) || dalloc(h, &h->next_in, H) || dalloc(h, &h->spk_dev, H) ||
+        dalloc(h, &h->partial, (size_t)s.kv_heads * ATT_NSPLIT * 2 * ATT_PSTRIDE) ||
+        dalloc(h, &h->cpartial, (size_t)s.cp_kv_heads * 2 * ATT_PSTRIDE) ||
+        dalloc(h, &h->counters, s.kv_heads) || dalloc(h, &h->ccounters, s.cp_kv_heads))
+        return 1;
+    const char* env_slots = std::getenv("LQT_SLOTS");
+    h->n_slots = env_slots ? std::max(1, std::atoi(env_slots)) : 2;
+    h->max_pages = (s.max_pos + KV_PAGE - 1) / KV_PAGE;
+    const size_t page_elems = (size_t)s.layers * 2 * s.kv_heads * KV_PAGE * D;
+    if (dalloc(h, &h->kv_pool, page_elems * h->max_pages * h->n_slots)) return 1;
+    if (dalloc(h, &h->cp_kv, (size_t)s.cp_layers * 2 * s.cp_kv_heads * (1 << CP_PAGE_SHIFT) * D)) return 1;
+    {
+        std::vector<int> pt((size_t)h->n_slots * h->max_pages);
+        for (size_t i = 0; i < pt.size(); ++i) pt[i] = (int)i;           // slot s owns pages [s*max_pages, ...)
+        if (dalloc(h, &h->page_tables, pt.size())) return 1;
+        CK(cudaMemcpy(h->page_tables, pt.data(), pt.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (dalloc(h, &h->cp_page_table, 1)) return 1;
+        std::vector<int> pc(32);
+        for (int i = 0; i < 32; ++i) pc[i] = i;
+        if (dalloc(h, &h->cp_pos_consts, 32)) return 1;
+        CK(cudaMemcpy(h->cp_pos_consts, pc.data(), 32 * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    h->slot_len.assign(h->n_slots, 0);
+    h->max_frames_cap = 4096;
+    if (dalloc(h, &h->st, 1) || dalloc(h, &h->sampling_dev, 1) || dalloc(h, &h->token_dev, 1) ||
+        dalloc(h, &h->codes_dev, (size_t)h->max_frames_cap * N_CODEBOOKS) ||
+        dalloc(h, &h->forced_dev, (size_t)h->max_frames_cap * N_CODEBOOKS) ||
+        dalloc(h, &h->trailing_dev, (size_t)s.max_pos * H) || dalloc(h, &h->tts_pad_dev, H) ||
+        dalloc(h, &h->prompt_dev, (size_t)16 * H))
+        return 1;
+    CK(cudaMallocHost((void**)&h->st_host, sizeof(GenState)));
+    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+const char* lqt_create_error(void) { return g_create_error.c_str(); }
+
+int lqt_create(const char* model_dir, int device_id, lqt_engine** out) {
+    if (out) *out = nullptr;
+    if (!model_dir || !out) { g_create_error = "null argument"; return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device (this library has no CPU fallback)";
+        return 1;
+    }
+    if (device_id < 0 || device_id >= ndev) { g_create_error = "bad device id"; return 1; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device_id);
+    if (prop.major < 10) { g_create_error = "device is not sm_100 (Blackwell) class"; return 1; }
+    if (cudaSetDevice(device_id) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return 1; }
+    lqt_engine* h = new lqt_engine();
+    h->device = device_id;
+    h->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaStreamCreate failed"; delete h; return 1;
+    }
+    if (init_engine(h, model_dir)) {
+        g_create_error = h->err.empty() ? "engine initialisation failed" : h->err;
+        lqt_destroy(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+void lqt_destroy(lqt_engine* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+    for (auto& w : h->ws) if (w.second.first) cudaFree(w.second.first);
+    void* bufs[] = {h->x, h->qkv, h->attn, h->act, h->logits, h->last_hidden, h->cx, h->cxin, h->cqkv, h->cattn, h->cact,
+                    h->clogits, h->cp_in, h->next_in, h->partial, h->cpartial, h->counters, h->ccounters, h->kv_pool,
+                    h->cp_kv, h->page_tables, h->cp_page_table, h->cp_pos_consts, h->st, h->sampling_dev, h->codes_dev,
+                    h->forced_dev, h->trailing_dev, h->tts_pad_dev, h->prompt_dev, h->token_dev, h->spk_dev,
+                    h->voc_codes_dev, h->audio_dev};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (h->st_host) cudaFreeHost(h->st_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    h->f_text.release(); h->f_codec.release(); h->f_cpe.release(); h->f_talker.release();
+    h->f_cp.release(); h->f_voc.release(); h->f_spk.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* lqt_last_error(lqt_engine* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lqt_get_info(lqt_engine* h, lqt_info* o) {
+    if (!h || !o) return 1;
+    const Spec& s = h->sp;
+    o->hidden = s.hidden; o->layers = s.layers; o->heads = s.heads; o->kv_heads = s.kv_heads; o->head_dim = s.head_dim;
+    o->vocab = s.vocab; o->cp_vocab = s.cp_vocab; o->cp_steps = s.cp_steps; o->samples_per_frame = s.samples_per_frame;
+    o->sample_rate = 24000; o->has_speaker_encoder = h->has_spk ? 1 : 0; o->max_pos = s.max_pos; o->num_sms = h->num_sms;
+    return 0;
+}
+
+int lqt_get_stats(lqt_engine* h, lqt_stats* o) { if (!h || !o) return 1; *o = h->stats; return 0; }
+int lqt_reset_stats(lqt_engine* h) { if (!h) return 1; h->stats = lqt_stats{}; return 0; }
+
+int lqt_text_project(lqt_engine* h, const int64_t* ids, int32_t S, float* out) {
+    if (!h || !ids || !out || S <= 0) return 1;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < S; ++i)
+        if (ids[i] < 0 || ids[i] >= h->sp.text_vocab) { h->err = "text token id out of range"; return 1; }
+    long long* d = (long long*)wsbuf(h, "tp_ids", (size_t)S * 2);
+    float* o = wsbuf(h, "tp_out", (size_t)S * h->sp.hidden);
+    if (!d || !o) return 1;
+    CK(cudaMemcpyAsync(d, ids, S * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (run_text_project(h, d, S, o)) return 1;
+    CK(cudaMemcpyAsync(out, o, (size_t)S * h->sp.hidden * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int gather_api(lqt_engine* h, const bf16* table, int rows, const int64_t* ids, int N, float* out) {
+    cudaSetDevice(h->device);
+    for (int i = 0; i < N; ++i)
+        if (ids[i] < 0 || ids[i] >= rows) { h->err = "embedding id out of range"; return 1; }
+    const int H = h->sp.hidden;
+    long long* d = (long long*)wsbuf(h, "tp_ids", (size_t)N * 2);
+    float* o = wsbuf(h, "tp_out", (size_t)N * H);
+    if (!d || !o) return 1;
+    CK(cudaMemcpyAsync(d, ids, N * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    gather_rows_kernel<<<N, 256, 0, h->stream>>>(table, d, H, o);
+    h->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(out, o, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lqt_codec_embed(lqt_engine* h, const int64_t* ids, int32_t N, float* out) {
+    if (!h || !ids || !out || N <= 0) return 1;
+    return gather_api(h, h->codec_embed, h->sp.vocab, ids, N, out);
+}
+
+int lqt_code_predictor_embed(lqt_engine* h, int64_t id, int64_t step, float* out) {
+    if (!h || !out) return 1;
+    if (step < 0 || step >= h->sp.cp_steps) { h->err = "generation_step out of range"; return 1; }
+    return gather_api(h, h->cp_embed + (size_t)step * h->sp.cp_vocab * h->sp.hidden, h->sp.cp_vocab, &id, 1, out);
+}
+
+int lqt_kv_reset(lqt_engine* h, int32_t slot) {
+    if (!h || slot < 0 || slot >= h->n_slots) return 1;
+    h->slot_len[slot] = 0;
+    return 0;
+}
+int lqt_kv_len(lqt_engine* h, int32_t slot) {
+    if (!h || slot < 0 || slot >= h->n_slots) return -1;
+    return h->slot_len[slot];
+}
+
+int lqt_talker_prefill(lqt_engine* h, int32_t slot, const float* embeds, int32_t P, float* logits_last, float* last_hidden) {
+    if (!h || !embeds || P <= 0 || slot < 0 || slot >= h->n_slots) return 1;
+    cudaSetDevice(h->device);
+    const int H = h->sp.hidden;
+    if (P > h->sp.max_pos) { h->err = "prefill longer than max_pos"; return 1; }
+    float* e = wsbuf(h, "prefill_in", (size_t)P * H);
+    if (!e) return 1;
+    CK(cudaMemcpyAsync(e, embeds, (size_t)P * H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    GenState g{}; *h->st_host = g;
+    CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < P; ++i) {
+        run_talker_token(h, slot, e + (size_t)i * H, i == P - 1, nullptr);
+        advance_kernel<<<1, 1, 0, h->stream>>>(h->st);
+        h->stats.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    if (logits_last) CK(cudaMemcpyAsync(logits_last, h->logits, h->sp.vocab * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (last_hidden) CK(cudaMemcpyAsync(last_hidden, h->last_hidden, H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->slot_len[slot] = P;
+    return 0;
+}
+
+int lqt_talker_decode(lqt_engine* h, int32_t slot, const float* embed, float* logits, float* last_hidden) {
+    if (!h || !embed || slot < 0 || slot >= h->n_slots) return 1;
+    cudaSetDevice(h->device);
+    const int H = h->sp.hidden;
+    if (h->slot_len[slot] >= h->sp.max_pos) { h->err = "KV cache full"; return 1; }
+    GenState g{}; g.pos = h->slot_len[slot]; *h->st_host = g;
+    CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->next_in, embed, H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    run_talker_token(h, slot, h->next_in, true, nullptr);
+    CK(cudaGetLastError());
+    if (logits) CK(cudaMemcpyAsync(logits, h->logits, h->sp.vocab * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (last_hidden) CK(cudaMemcpyAsync(last_hidden, h->last_hidden, H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->slot_len[slot] += 1;
+    return 0;
+}
+
+int lqt_code_predictor(lqt_engine* h, const float* embeds, int32_t L, int64_t step, float* logits) {
+    if (!h || !embeds || !logits) return 1;
+    cudaSetDevice(h->device);
+    if (L < 1 || L > h->sp.cp_steps + 2 || step < 0 || step >= h->sp.cp_steps) { h->err = "code_predictor: bad L or generation_step"; return 1; }
+    const int H = h->sp.hidden;
+    float* e = wsbuf(h, "cp_rows", (size_t)L * H);
+    if (!e) return 1;
+    CK(cudaMemcpyAsync(e, embeds, (size_t)L * H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < L; ++i) run_cp_token(h, e + (size_t)i * H, i, i == L - 1 ? (int)step : -1, nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(logits, h->clogits, h->sp.cp_vocab * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lqt_vocoder_decode(lqt_engine* h, const int64_t* codes, int32_t T, float* audio, int64_t* length) {
+    if (!h || !codes || !audio || T <= 0) return 1;
+    cudaSetDevice(h->device);
+    for (long long i = 0; i < (long long)T * N_CODEBOOKS; ++i)
+        if (codes[i] < 0 || codes[i] >= h->sp.voc_codebook_size) { h->err = "audio code out of range"; return 1; }
+    if (ensure_audio(h, T)) return 1;
+    CK(cudaMemcpyAsync(h->voc_codes_dev, codes, (size_t)T * N_CODEBOOKS * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (run_vocoder(h, h->voc_codes_dev, T, h->audio_dev)) return 1;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    const size_t n = (size_t)T * h->sp.samples_per_frame;
+    CK(cudaMemcpyAsync(audio, h->audio_dev, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->stats.last_vocoder_ms, h->ev0, h->ev1);
+    if (length) *length = (int64_t)n;
+    return 0;
+}
+
+int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float* out) {
+    if (!h || !mel_t || !out || frames <= 0) return 1;
+    if (!h->has_spk) { h->err = "speaker encoder not available"; return 1; }
+    cudaSetDevice(h->device);
+    const Spec& s = h->sp;
+    const int Cs = s.spk_channels, M = s.spk_mels;
+    bool ok = true;
+    const LqwFile& f = h->f_spk;
+    float* in = wsbuf(h, "spk_in", (size_t)frames * M);
+    float* a = wsbuf(h, "spk_a", (size_t)frames * Cs);
+    float* b = wsbuf(h, "spk_b", (size_t)frames * Cs);
+    float* pool = wsbuf(h, "spk_pool", (size_t)2 * Cs);
+    float* o = wsbuf(h, "spk_out", s.hidden);
+    if (!in || !a || !b || !pool || !o) return 1;
+    CK(cudaMemcpyAsync(in, mel_t, (size_t)frames * M * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const long long n = (long long)frames * Cs;
+    const int eb = (int)std::min<long long>((n + 255) / 256, 4096);
+    { ConvGemmParams p = cg(in, frames, M, need<bf16>(h, f, "in_conv.weight", ok), Cs, b); p.taps = 5; p.shift = 2; p.bias = need<float>(h, f, "in_conv.bias", ok);
+      if (!ok) return 1; launch_conv_gemm(h, p); }
+    relu_add_kernel<<<eb, 256, 0, h->stream>>>(b, nullptr, a, n); h->stats.kernel_launches++;
+    for (int i = 0; i < s.spk_layers; ++i) {
+        const std::string q = "l" + std::to_string(i) + ".conv.";
+        ConvGemmParams p = cg(a, frames, Cs, need<bf16>(h, f, q + "weight", ok), Cs, b); p.taps = 3; p.shift = 1; p.bias = need<float>(h, f, q + "bias", ok);
+        if (!ok) return 1;
+        launch_conv_gemm(h, p);
+        relu_add_kernel<<<eb, 256, 0, h->stream>>>(b, a, a, n); h->stats.kernel_launches++;
+    }
+    stat_pool_kernel<<<(Cs + 127) / 128, 128, 0, h->stream>>>(a, frames, Cs, pool); h->stats.kernel_launches++;
+    GemvParams g = gemv_params(need<bf16>(h, f, "fc.weight", ok), s.hidden, 2 * Cs, pool, o);
+    g.bias = need<float>(h, f, "fc.bias", ok);
+    if (!ok) return 1;
+    launch_gemv(h, g, false);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, o, s.hidden * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lqt_sample(lqt_engine* h, const float* logits, int32_t V, const lqt_sampling* sp, uint32_t frame, uint32_t codebook,
+               int32_t mask_codec_specials, int64_t* id) {
+    if (!h || !logits || !sp || !id || V <= 0 || V > SMP_MAXV) return 1;
+    cudaSetDevice(h->device);
+    float* d = wsbuf(h, "sample_logits", V);
+    if (!d) return 1;
+    CK(cudaMemcpyAsync(d, logits, V * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (upload_sampling(h, sp)) return 1;
+    SampleParams s{};
+    s.logits = d; s.V = V; s.sp = h->sampling_dev; s.frame_imm = frame; s.codebook = (int)codebook; s.token_out = h->token_dev;
+    s.n_codebooks = N_CODEBOOKS; s.eos_id = CODEC_EOS;
+    if (mask_codec_specials) { s.mask_lo = 2048; s.mask_hi = V; s.mask_keep = CODEC_EOS; }
+    launch_sample(h, s);
+    CK(cudaGetLastError());
+    int tok = 0;
+    CK(cudaMemcpyAsync(&tok, h->token_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *id = tok;
+    return 0;
+}
+
+int lqt_generate(lqt_engine* h, int32_t slot, const float* prompt, int32_t P, const float* trailing, int32_t trailing_len,
+                 const float* tts_pad, const lqt_sampling* sp, const int64_t* forced_codes, int32_t n_forced,
+                 int64_t* codes_out, int32_t* n_frames, float* logits_trace, int32_t trace_stride) {
+    if (!h || !prompt || !tts_pad || !sp || !codes_out || !n_frames) return 1;
+    cudaSetDevice(h->device);
+    const int H = h->sp.hidden;
+    if (P < 1 || P > 16) { h->err = "P must be in [1,16]"; return 1; }
+    if (trailing_len < 0 || trailing_len > h->sp.max_pos) { h->err = "bad trailing_len"; return 1; }
+    if (n_forced < 0 || n_forced > h->max_frames_cap) { h->err = "bad n_forced"; return 1; }
+    const bool trace = logits_trace != nullptr;
+    if (trace) {
+        if (trace_stride < std::max(h->sp.vocab, h->sp.cp_vocab)) { h->err = "trace_stride too small"; return 1; }
+        if (ensure_trace(h, sp->max_new_tokens, trace_stride)) return 1;
+    }
+    CK(cudaMemcpyAsync(h->prompt_dev, prompt, (size_t)P * H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (trailing_len > 0) CK(cudaMemcpyAsync(h->trailing_dev, trailing, (size_t)trailing_len * H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tts_pad_dev, tts_pad, H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (n_forced > 0) CK(cudaMemcpyAsync(h->forced_dev, forced_codes, (size_t)n_forced * N_CODEBOOKS * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    int nf = 0;
+    if (generate_core(h, slot, P, trailing_len, sp, n_forced, trace, &nf)) return 1;
+    if (nf > 0) CK(cudaMemcpyAsync(codes_out, h->codes_dev, (size_t)nf * N_CODEBOOKS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    if (trace && sp->max_new_tokens > 0)
+        CK(cudaMemcpyAsync(logits_trace, h->trace_dev, (size_t)sp->max_new_tokens * N_CODEBOOKS * trace_stride * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *n_frames = nf;
+    return 0;
+}
+
+int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
+                     float* prompt_out, int32_t* P, float* trailing_out, int32_t* trailing_len, float* tts_pad_out) {
+    if (!h || !token_ids || !P || !trailing_len) return 1;
+    cudaSetDevice(h->device);
+    int p = 0, tl = 0;
+    if (build_prompt_device(h, token_ids, n_ids, lang_codec_id, speaker_embed, &p, &tl)) return 1;
+    const int H = h->sp.hidden;
+    if (prompt_out) CK(cudaMemcpyAsync(prompt_out, h->prompt_dev, (size_t)p * H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (trailing_out) CK(cudaMemcpyAsync(trailing_out, h->trailing_dev, (size_t)tl * H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (tts_pad_out) CK(cudaMemcpyAsync(tts_pad_out, h->tts_pad_dev, H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *P = p; *trailing_len = tl;
+    return 0;
+}
+
+int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
+                          const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
+                          int64_t* codes_out, int32_t* n_frames) {
+    if (!h || !token_ids || !sp || !n_samples) return 1;
+    cudaSetDevice(h->device);
+    *n_samples = 0;
+    if (n_frames) *n_frames = 0;
+    int P = 0, TL = 0;
+    if (build_prompt_device(h, token_ids, n_ids, lang_codec_id, speaker_embed, &P, &TL)) return 1;
+    int nf = 0;
+    if (generate_core(h, 0, P, TL, sp, 0, false, &nf)) return 1;
+    if (n_frames) *n_frames = nf;
+    if (nf == 0) return 0;                                   // empty result, like src/tts_onnx.cpp:418
+    if (codes_out) CK(cudaMemcpyAsync(codes_out, h->codes_dev, (size_t)nf * N_CODEBOOKS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    const int64_t n = (int64_t)nf * h->sp.samples_per_frame;
+    if (!audio_out || audio_capacity < n) { h->err = "audio_out too small"; return 1; }
+    if (ensure_audio(h, nf)) return 1;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (run_vocoder(h, h->codes_dev, nf, h->audio_dev)) return 1;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaMemcpyAsync(audio_out, h->audio_dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->stats.last_vocoder_ms, h->ev0, h->ev1);
+    *n_samples = n;
+    return 0;
+}
+
+}  // extern "C"

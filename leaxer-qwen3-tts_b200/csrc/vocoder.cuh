@@ -1,0 +1,273 @@
+// tokenizer12hz_decode (src/tts_onnx.cpp:759-776) building blocks, channels-last activations.
+//   conv_gemm_kernel : implicit GEMM  y[L][N] = epi( A[L][taps*Cin] . W[N][taps*Cin]^T )
+//                      covers Linear, causal dilated conv (A row p = taps shifted input rows),
+//                      and transposed conv k=2s/stride s as s phase-GEMMs (N = s*Cout, A row =
+//                      [x[p], x[p-1]]), output [L][s*Cout] == channels-last [L*s][Cout].
+//   plus the memory-bound pieces: RVQ gather-sum, SnakeBeta, RMSNorm rows, depthwise conv +
+//   LayerNorm, SiLU*mul, final conv + clamp.
+// v1: fp32 CUDA-core tiles with bf16 weights (exact activations -> parity with the fp32 oracle).
+#pragma once
+#include "common.cuh"
+
+namespace lqt {
+
+struct ConvGemmParams {
+    const float* x;              // [L][Cin]
+    const __nv_bfloat16* W;      // [N][taps*Cin]
+    const float* bias;           // nullable, index n % bias_mod
+    const float* scale;          // nullable, index n % bias_mod (LayerScale / ConvNeXt gamma)
+    const float* residual;       // nullable [L][N]
+    float* y;                    // [L][N]
+    int L, Cin, N, taps, dil;
+    int tap_rev;                 // 0: tap j reads x[p-(taps-1-j)*dil] (causal conv); 1: x[p-j*dil] (tconv)
+    int shift;                   // added to the source position (0 = causal; (taps/2)*dil = 'same' padding)
+    int bias_mod;
+    int act;                     // 0 none, 1 SiLU, 3 GELU(erf)
+};
+
+constexpr int CG_BM = 64, CG_BN = 64, CG_BK = 16, CG_THREADS = 256;
+
+__global__ void __launch_bounds__(CG_THREADS)
+conv_gemm_kernel(const ConvGemmParams p) {
+    __shared__ float As[CG_BK][CG_BM + 4];
+    __shared__ float Bs[CG_BK][CG_BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * CG_BM, n0 = blockIdx.y * CG_BN;
+    const int K = p.taps * p.Cin;
+    const bool fast = (p.Cin % 16) == 0;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;
+    const int b_n = tid >> 1, b_kq = (tid & 1) * 8;
+
+    float a_reg[4];
+    float b_reg[8];
+
+    auto load_slab = [&](int k0) {
+        // ---- A: 64 rows x 16 k ---------------------------------------------------------------
+        const int pidx = m0 + a_row;
+        if (fast) {
+            const int k = k0 + a_kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pidx < p.L && k < K) {
+                const int tap = k / p.Cin, c = k - tap * p.Cin;
+                const int src = pidx + p.shift - (p.tap_rev ? tap : (p.taps - 1 - tap)) * p.dil;
+                if (src >= 0 && src < p.L) v = *reinterpret_cast<const float4*>(p.x + (size_t)src * p.Cin + c);
+            }
+            a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k0 + a_kq + e;
+                float v = 0.f;
+                if (pidx < p.L && k < K) {
+                    const int tap = k / p.Cin, c = k - tap * p.Cin;
+                    const int src = pidx + p.shift - (p.tap_rev ? tap : (p.taps - 1 - tap)) * p.dil;
+                    if (src >= 0 && src < p.L) v = p.x[(size_t)src * p.Cin + c];
+                }
+                a_reg[e] = v;
+            }
+        }
+        // ---- B: 64 n x 16 k (threads 0..127) ----------------------------------------------------
+        if (tid < 128) {
+            const int n = n0 + b_n, k = k0 + b_kq;
+            if (fast) {
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (n < p.N && k < K) w = *reinterpret_cast<const uint4*>(p.W + (size_t)n * K + k);
+                b_reg[0] = bf16lo(w.x); b_reg[1] = bf16hi(w.x); b_reg[2] = bf16lo(w.y); b_reg[3] = bf16hi(w.y);
+                b_reg[4] = bf16lo(w.z); b_reg[5] = bf16hi(w.z); b_reg[6] = bf16lo(w.w); b_reg[7] = bf16hi(w.w);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    b_reg[e] = (n < p.N && k + e < K) ? __bfloat162float(p.W[(size_t)n * K + k + e]) : 0.f;
+            }
+        }
+    };
+    auto store_slab = [&]() {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) As[a_kq + e][a_row] = a_reg[e];
+        if (tid < 128) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) Bs[b_kq + e][b_n] = b_reg[e];
+        }
+    };
+
+    load_slab(0);
+    for (int k0 = 0; k0 < K; k0 += CG_BK) {
+        store_slab();
+        __syncthreads();
+        if (k0 + CG_BK < K) load_slab(k0 + CG_BK);
+#pragma unroll
+        for (int kk = 0; kk < CG_BK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= p.L) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.N) continue;
+            float v = acc[i][j];
+            const int bn = n % p.bias_mod;
+            if (p.bias) v += p.bias[bn];
+            if (p.act == 1) v = silu_f(v);
+            else if (p.act == 3) v = gelu_erf_f(v);
+            if (p.scale) v *= p.scale[bn];
+            if (p.residual) v += p.residual[(size_t)m * p.N + n];
+            p.y[(size_t)m * p.N + n] = v;
+        }
+    }
+}
+
+// ---- RVQ dequantisation: gather-SUM per group (codebook order), output [T][Dc] each -------------
+__global__ void rvq_gather_kernel(const long long* __restrict__ codes, int T, int n_q,
+                                  const __nv_bfloat16* __restrict__ cb_sem,   // [1][size][Dc]
+                                  const __nv_bfloat16* __restrict__ cb_aco,   // [n_q-1][size][Dc]
+                                  int cb_size, int Dc, float* sem, float* aco) {
+    const int t = blockIdx.x;
+    if (t >= T) return;
+    for (int d = threadIdx.x; d < Dc; d += blockDim.x) {
+        const long long c0 = codes[(size_t)t * n_q];
+        sem[(size_t)t * Dc + d] = __bfloat162float(cb_sem[(size_t)c0 * Dc + d]);
+        float a = 0.f;
+        for (int j = 1; j < n_q; ++j) {
+            const long long c = codes[(size_t)t * n_q + j];
+            a += __bfloat162float(cb_aco[((size_t)(j - 1) * cb_size + c) * Dc + d]);
+        }
+        aco[(size_t)t * Dc + d] = a;
+    }
+}
+
+// ---- SnakeBeta: y = x + 1/(exp(beta)+1e-9) * sin(x*exp(alpha))^2, per channel --------------------
+__global__ void snake_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, int C,
+                             const float* __restrict__ alpha, const float* __restrict__ beta) {
+    // n4 = number of float4 groups; C % 4 == 0
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 4) % C);
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float4 al = *reinterpret_cast<const float4*>(alpha + c);
+        const float4 be = *reinterpret_cast<const float4*>(beta + c);
+        float s;
+        s = sinf(v.x * expf(al.x)); v.x = v.x + (1.0f / (expf(be.x) + 1e-9f)) * (s * s);
+        s = sinf(v.y * expf(al.y)); v.y = v.y + (1.0f / (expf(be.y) + 1e-9f)) * (s * s);
+        s = sinf(v.z * expf(al.z)); v.z = v.z + (1.0f / (expf(be.z) + 1e-9f)) * (s * s);
+        s = sinf(v.w * expf(al.w)); v.w = v.w + (1.0f / (expf(be.w) + 1e-9f)) * (s * s);
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
+// ---- RMSNorm over rows [L][C]; one warp per row ---------------------------------------------------
+__global__ void rmsnorm_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C,
+                                    const float* __restrict__ w, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= L) return;
+    const float* xr = x + (size_t)row * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) ss += xr[c] * xr[c];
+    ss = warp_sum(ss);
+    const float r = 1.0f / sqrtf(ss / (float)C + eps);
+    for (int c = lane; c < C; c += 32) y[(size_t)row * C + c] = (xr[c] * r) * w[c];
+}
+
+__global__ void silu_mul_kernel(const float* g, const float* u, float* y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = silu_f(g[i]) * u[i];
+}
+
+// ---- ConvNeXt front: depthwise causal conv k7 (+bias) then LayerNorm over channels ----------------
+// one CTA per position; dynamic smem = C floats
+__global__ void dwconv_ln_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C,
+                                 const float* __restrict__ dw_w /*[7][C]*/, const float* __restrict__ dw_b,
+                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps) {
+    extern __shared__ float hbuf[];
+    __shared__ float red[32];
+    __shared__ float stat;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float s = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) {
+        float a = dw_b[c];
+#pragma unroll
+        for (int tap = 0; tap < 7; ++tap) {
+            const int src = p - (6 - tap);
+            if (src >= 0) a = fmaf(dw_w[tap * C + c], x[(size_t)src * C + c], a);
+        }
+        hbuf[c] = a;
+        s += a;
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < nw; ++w) t += red[w]; stat = t / (float)C; }
+    __syncthreads();
+    const float mean = stat;
+    float v = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) { const float d = hbuf[c] - mean; v += d * d; }
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < nw; ++w) t += red[w]; stat = 1.0f / sqrtf(t / (float)C + eps); }
+    __syncthreads();
+    const float rstd = stat;
+    for (int c = tid; c < C; c += blockDim.x)
+        y[(size_t)p * C + c] = (hbuf[c] - mean) * rstd * ln_w[c] + ln_b[c];
+}
+
+// ---- final causal conv k7 C->1 (+bias) + clamp[-1,1]; input already SnakeBeta-activated ----------
+// one warp per output sample
+__global__ void conv_out_kernel(const float* __restrict__ x, float* __restrict__ y, long long L, int C,
+                                const float* __restrict__ w /*[7][C]*/, const float* __restrict__ b) {
+    const long long pos = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pos >= L) return;
+    float a = 0.f;
+    for (int tap = 0; tap < 7; ++tap) {
+        const long long src = pos - (6 - tap);
+        if (src < 0) continue;
+        for (int c = lane; c < C; c += 32) a = fmaf(w[tap * C + c], x[(size_t)src * C + c], a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) y[pos] = fminf(1.0f, fmaxf(-1.0f, a + b[0]));
+}
+
+// ---- speaker encoder helpers ------------------------------------------------------------------------
+// mean / std pooling over frames: x [F][C] -> out [2C] (mean | sqrt(var + 1e-5))
+__global__ void stat_pool_kernel(const float* __restrict__ x, int F, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int f = 0; f < F; ++f) s += x[(size_t)f * C + c];
+    const float mean = s / (float)F;
+    float v = 0.f;
+    for (int f = 0; f < F; ++f) { const float d = x[(size_t)f * C + c] - mean; v += d * d; }
+    out[c] = mean;
+    out[C + c] = sqrtf(v / (float)F + 1e-5f);
+}
+
+__global__ void relu_add_kernel(const float* h, const float* res, float* y, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = (res ? res[i] : 0.f) + fmaxf(h[i], 0.f);
+}
+
+}  // namespace lqt

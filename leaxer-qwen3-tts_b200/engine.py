@@ -1,0 +1,251 @@
+"""ctypes binding over the C-ABI (include/lqt_b200.h). This is the call surface tests and bench.py
+use; it mirrors leaxer_qwen::TTSEngine's private run_* graph runners and public synthesize_tokens
+(/root/reference/src/tts_onnx.h:118-226). No CPU fallback: a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblqt_b200.so")
+
+LANG_CODEC_ID = {"auto": 0, "en": 2050, "zh": 2051, "ja": 2052, "ko": 2053}   # tts_onnx.h:230-238
+
+# every symbol include/lqt_b200.h declares
+SYMBOLS = [
+    "lqt_create", "lqt_create_error", "lqt_destroy", "lqt_last_error", "lqt_get_info", "lqt_get_stats",
+    "lqt_reset_stats", "lqt_text_project", "lqt_codec_embed", "lqt_code_predictor_embed",
+    "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
+    "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
+    "lqt_build_prompt",
+]
+
+
+class Sampling(C.Structure):
+    _fields_ = [("temperature", C.c_float), ("top_p", C.c_float), ("top_k", C.c_int32),
+                ("max_new_tokens", C.c_int32), ("seed", C.c_uint32), ("utterance_id", C.c_uint32),
+                ("greedy", C.c_int32)]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "hidden", "layers", "heads", "kv_heads", "head_dim", "vocab", "cp_vocab", "cp_steps",
+        "samples_per_frame", "sample_rate", "has_speaker_encoder", "max_pos", "num_sms")]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64),
+                ("last_generate_ms", C.c_float), ("last_vocoder_ms", C.c_float),
+                ("last_prefill_ms", C.c_float), ("last_frames", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads liblqt_b200.so and checks that it exports every declared symbol. Raises if not."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                           f"g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f"liblqt_b200.so lacks symbols: {missing}")
+    lib.lqt_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lqt_create_error.restype = C.c_char_p
+    lib.lqt_destroy.argtypes = [C.c_void_p]
+    lib.lqt_destroy.restype = None
+    lib.lqt_last_error.argtypes = [C.c_void_p]
+    lib.lqt_last_error.restype = C.c_char_p
+    lib.lqt_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    lib.lqt_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.lqt_reset_stats.argtypes = [C.c_void_p]
+    P, I32, I64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.lqt_text_project.argtypes = [P, P, I32, P]
+    lib.lqt_codec_embed.argtypes = [P, P, I32, P]
+    lib.lqt_code_predictor_embed.argtypes = [P, I64, I64, P]
+    lib.lqt_talker_prefill.argtypes = [P, I32, P, I32, P, P]
+    lib.lqt_talker_decode.argtypes = [P, I32, P, P, P]
+    lib.lqt_kv_reset.argtypes = [P, I32]
+    lib.lqt_kv_len.argtypes = [P, I32]
+    lib.lqt_code_predictor.argtypes = [P, P, I32, I64, P]
+    lib.lqt_vocoder_decode.argtypes = [P, P, I32, P, C.POINTER(I64)]
+    lib.lqt_speaker_encoder.argtypes = [P, P, I32, P]
+    lib.lqt_sample.argtypes = [P, P, I32, C.POINTER(Sampling), C.c_uint32, C.c_uint32, I32, C.POINTER(I64)]
+    lib.lqt_generate.argtypes = [P, I32, P, I32, P, I32, P, C.POINTER(Sampling), P, I32, P,
+                                 C.POINTER(I32), P, I32]
+    lib.lqt_synthesize_tokens.argtypes = [P, P, I32, I32, P, C.POINTER(Sampling), P, I64,
+                                          C.POINTER(I64), P, C.POINTER(I32)]
+    lib.lqt_build_prompt.argtypes = [P, P, I32, I32, P, P, C.POINTER(I32), P, C.POINTER(I32), P]
+    _lib = lib
+    return lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine = one GPU = one host thread at a time (same contract as the reference)."""
+
+    def __init__(self, model_dir: str, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.lqt_create(model_dir.encode(), device, C.byref(h))
+        if rc != 0 or not h:
+            raise EngineError(self.lib.lqt_create_error().decode())
+        self.h = h
+        self.info = Info()
+        self.lib.lqt_get_info(self.h, C.byref(self.info))
+        self.H = self.info.hidden
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lqt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.lqt_last_error(self.h).decode())
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self.lib.lqt_get_stats(self.h, C.byref(s))
+        return s
+
+    def reset_stats(self):
+        self.lib.lqt_reset_stats(self.h)
+
+    @staticmethod
+    def sampling(temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=2048, seed=0,
+                 utterance_id=0, greedy=False) -> Sampling:
+        return Sampling(temperature, top_p, top_k, max_new_tokens, seed, utterance_id, 1 if greedy else 0)
+
+    # ---- per-graph runners (tts_onnx.h:196-212) ------------------------------------------------
+    def text_project(self, ids):
+        ids = _i64(ids)
+        out = np.empty((len(ids), self.H), np.float32)
+        self._ck(self.lib.lqt_text_project(self.h, _ptr(ids), len(ids), _ptr(out)))
+        return out
+
+    def codec_embed(self, ids):
+        ids = _i64(ids)
+        out = np.empty((len(ids), self.H), np.float32)
+        self._ck(self.lib.lqt_codec_embed(self.h, _ptr(ids), len(ids), _ptr(out)))
+        return out
+
+    def code_predictor_embed(self, token: int, step: int):
+        out = np.empty(self.H, np.float32)
+        self._ck(self.lib.lqt_code_predictor_embed(self.h, int(token), int(step), _ptr(out)))
+        return out
+
+    def talker_prefill(self, embeds, slot: int = 0):
+        e = _f32(embeds).reshape(-1, self.H)
+        logits = np.empty(self.info.vocab, np.float32)
+        hid = np.empty(self.H, np.float32)
+        self._ck(self.lib.lqt_talker_prefill(self.h, slot, _ptr(e), e.shape[0], _ptr(logits), _ptr(hid)))
+        return logits, hid
+
+    def talker_decode(self, embed, slot: int = 0):
+        e = _f32(embed).reshape(self.H)
+        logits = np.empty(self.info.vocab, np.float32)
+        hid = np.empty(self.H, np.float32)
+        self._ck(self.lib.lqt_talker_decode(self.h, slot, _ptr(e), _ptr(logits), _ptr(hid)))
+        return logits, hid
+
+    def kv_reset(self, slot: int = 0):
+        self._ck(self.lib.lqt_kv_reset(self.h, slot))
+
+    def kv_len(self, slot: int = 0) -> int:
+        return self.lib.lqt_kv_len(self.h, slot)
+
+    def code_predictor(self, embeds, step: int):
+        e = _f32(embeds).reshape(-1, self.H)
+        logits = np.empty(self.info.cp_vocab, np.float32)
+        self._ck(self.lib.lqt_code_predictor(self.h, _ptr(e), e.shape[0], int(step), _ptr(logits)))
+        return logits
+
+    def vocoder_decode(self, codes):
+        c = _i64(codes).reshape(-1, 16)
+        audio = np.empty(c.shape[0] * self.info.samples_per_frame, np.float32)
+        n = C.c_int64(0)
+        self._ck(self.lib.lqt_vocoder_decode(self.h, _ptr(c), c.shape[0], _ptr(audio), C.byref(n)))
+        return audio[: n.value]
+
+    def speaker_encoder(self, mel_t):
+        m = _f32(mel_t).reshape(-1, 128)
+        out = np.empty(self.H, np.float32)
+        self._ck(self.lib.lqt_speaker_encoder(self.h, _ptr(m), m.shape[0], _ptr(out)))
+        return out
+
+    def sample(self, logits, sp: Sampling, frame: int, codebook: int, mask_codec_specials=False) -> int:
+        lg = _f32(logits)
+        out = C.c_int64(0)
+        self._ck(self.lib.lqt_sample(self.h, _ptr(lg), lg.shape[0], C.byref(sp), frame, codebook,
+                                     1 if mask_codec_specials else 0, C.byref(out)))
+        return out.value
+
+    # ---- fast path ---------------------------------------------------------------------------------
+    def generate(self, prompt, trailing, tts_pad, sp: Sampling, slot: int = 0, forced_codes=None,
+                 trace: bool = False):
+        pr = _f32(prompt).reshape(-1, self.H)
+        tr = _f32(trailing).reshape(-1, self.H)
+        pad = _f32(tts_pad).reshape(self.H)
+        codes = np.zeros((max(sp.max_new_tokens, 1), 16), np.int64)
+        n = C.c_int32(0)
+        fc = _i64(forced_codes).reshape(-1, 16) if forced_codes is not None else None
+        stride = max(self.info.vocab, self.info.cp_vocab)
+        tb = np.zeros((max(sp.max_new_tokens, 1), 16, stride), np.float32) if trace else None
+        self._ck(self.lib.lqt_generate(self.h, slot, _ptr(pr), pr.shape[0], _ptr(tr), tr.shape[0], _ptr(pad),
+                                       C.byref(sp), _ptr(fc), 0 if fc is None else fc.shape[0],
+                                       _ptr(codes), C.byref(n), _ptr(tb), stride))
+        return (codes[: n.value].copy(), tb) if trace else codes[: n.value].copy()
+
+    def build_prompt(self, token_ids, lang: str = "auto", speaker_embed=None):
+        ids = _i64(token_ids)
+        prompt = np.empty((16, self.H), np.float32)
+        trailing = np.empty((max(len(ids), 1), self.H), np.float32)
+        pad = np.empty(self.H, np.float32)
+        P, TL = C.c_int32(0), C.c_int32(0)
+        spk = _f32(speaker_embed) if speaker_embed is not None else None
+        self._ck(self.lib.lqt_build_prompt(self.h, _ptr(ids), len(ids), LANG_CODEC_ID[lang], _ptr(spk),
+                                           _ptr(prompt), C.byref(P), _ptr(trailing), C.byref(TL), _ptr(pad)))
+        return prompt[: P.value].copy(), trailing[: TL.value].copy(), pad
+
+    def synthesize_tokens(self, token_ids, lang: str = "auto", temperature=0.8, top_k=50, top_p=0.95,
+                          max_new_tokens=2048, seed=0, utterance_id=0, greedy=False, speaker_embed=None):
+        """src/tts_onnx.cpp:405-436 -> (audio f32 [n], codes i64 [T,16])"""
+        ids = _i64(token_ids)
+        sp = self.sampling(temperature, top_k, top_p, max_new_tokens, seed, utterance_id, greedy)
+        cap = max(max_new_tokens, 1) * self.info.samples_per_frame
+        audio = np.empty(cap, np.float32)
+        codes = np.zeros((max(max_new_tokens, 1), 16), np.int64)
+        ns, nf = C.c_int64(0), C.c_int32(0)
+        spk = _f32(speaker_embed) if speaker_embed is not None else None
+        self._ck(self.lib.lqt_synthesize_tokens(self.h, _ptr(ids), len(ids), LANG_CODEC_ID[lang], _ptr(spk),
+                                                C.byref(sp), _ptr(audio), cap, C.byref(ns), _ptr(codes),
+                                                C.byref(nf)))
+        return audio[: ns.value].copy(), codes[: nf.value].copy()
