@@ -50,10 +50,20 @@ typedef struct lqt_stats {
     int32_t  last_frames;
 } lqt_stats;
 
+/* Engine options (lqt_create_ex). kv_dtype: LQT_KV_BF16 = paged bf16 talker KV cache (default,
+ * north_star); LQT_KV_F32 = "parity mode": fp32 pages, no rounding point in the talker, for
+ * free-running token-exact comparison against the fp32 oracle over long utterances. */
+enum { LQT_KV_BF16 = 0, LQT_KV_F32 = 1 };
+typedef struct lqt_options {
+    int32_t kv_dtype;
+    int32_t n_slots;      /* KV slots (utterances resident at once); 0 = default (2) */
+} lqt_options;
+
 /* src/tts_onnx.cpp:84-130 (TTSEngine ctor) + :134-232 (load_model): loads the 7 required graph
  * files (+ optional speaker_encoder) from model_dir. On failure returns non-zero, *out = NULL and
  * lqt_create_error() describes why (the reference sets error_msg_ and leaves ready_ = false). */
 int lqt_create(const char* model_dir, int device_id, lqt_engine** out);
+int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, lqt_engine** out);
 const char* lqt_create_error(void);
 void lqt_destroy(lqt_engine* h);
 const char* lqt_last_error(lqt_engine* h);

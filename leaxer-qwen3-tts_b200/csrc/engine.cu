@@ -100,7 +100,8 @@ struct lqt_engine {
     float *cp_in = nullptr, *next_in = nullptr;
     float *partial = nullptr, *cpartial = nullptr;
     int *counters = nullptr, *ccounters = nullptr;
-    bf16* kv_pool = nullptr;
+    void* kv_pool = nullptr;                  // bf16 (default) or fp32 pages
+    bool kv_f32 = false;
     float* cp_kv = nullptr;
     int *page_tables = nullptr, *cp_page_table = nullptr, *cp_pos_consts = nullptr;
     int n_slots = 2, max_pages = 0;
@@ -204,7 +205,7 @@ struct XfmrCtx {               // one decoder stack (talker or predictor) in dec
     const float *cos, *sin;
     float *x, *qkv, *attn, *act, *partial;
     int* counters;
-    void* kv_pool; const int* page_table; int page_shift; long long page_stride; bool kv_bf16;
+    void* kv_pool; const int* page_table; int page_shift; long long page_stride; bool kv_bf16; bool paged;
     int nsplit;
     const int* done;
 };
@@ -232,7 +233,7 @@ void run_stack(lqt_engine* h, const XfmrCtx& c, const float* x_in, const int* po
             a.page_shift = c.page_shift; a.n_kv = c.kv_heads; a.eps = c.eps;
             a.scale = 1.0f / sqrtf((float)D);
             dim3 grid(c.kv_heads, c.nsplit);
-            const int max_pages = c.kv_bf16 ? h->max_pages : 1;
+            const int max_pages = c.paged ? h->max_pages : 1;
             const size_t smem = (size_t)2 * ((max_pages + c.nsplit - 1) / c.nsplit) * PS * sizeof(float);
             if (c.kv_bf16) attn_decode_kernel<bf16, 2><<<grid, ATT_THREADS, smem, h->stream>>>(a);
             else           attn_decode_kernel<float, 2><<<grid, ATT_THREADS, smem, h->stream>>>(a);
@@ -264,7 +265,7 @@ XfmrCtx talker_ctx(lqt_engine* h, int slot, const int* done) {
     c.kv_pool = h->kv_pool; c.page_table = h->page_tables + (size_t)slot * h->max_pages;
     c.page_shift = KV_PAGE_SHIFT;
     c.page_stride = (long long)h->sp.layers * 2 * h->sp.kv_heads * KV_PAGE * ATT_D;
-    c.kv_bf16 = true; c.nsplit = ATT_NSPLIT; c.done = done;
+    c.kv_bf16 = !h->kv_f32; c.paged = true; c.nsplit = ATT_NSPLIT; c.done = done;
     return c;
 }
 
@@ -275,7 +276,7 @@ XfmrCtx cp_ctx(lqt_engine* h, const int* done) {
     c.x = h->cx; c.qkv = h->cqkv; c.attn = h->cattn; c.act = h->cact; c.partial = h->cpartial; c.counters = h->ccounters;
     c.kv_pool = h->cp_kv; c.page_table = h->cp_page_table; c.page_shift = CP_PAGE_SHIFT;
     c.page_stride = (long long)h->sp.cp_layers * 2 * h->sp.cp_kv_heads * (1 << CP_PAGE_SHIFT) * ATT_D;
-    c.kv_bf16 = false; c.nsplit = 1; c.done = done;
+    c.kv_bf16 = false; c.paged = false; c.nsplit = 1; c.done = done;
     return c;
 }
 
@@ -830,11 +831,13 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         dalloc(h, &h->cpartial, (size_t)s.cp_kv_heads * 2 * ATT_PSTRIDE) ||
         dalloc(h, &h->counters, s.kv_heads) || dalloc(h, &h->ccounters, s.cp_kv_heads))
         return 1;
-    const char* env_slots = std::getenv("LQT_SLOTS");
-    h->n_slots = env_slots ? std::max(1, std::atoi(env_slots)) : 2;
     h->max_pages = (s.max_pos + KV_PAGE - 1) / KV_PAGE;
     const size_t page_elems = (size_t)s.layers * 2 * s.kv_heads * KV_PAGE * D;
-    if (dalloc(h, &h->kv_pool, page_elems * h->max_pages * h->n_slots)) return 1;
+    {
+        const size_t bytes = page_elems * h->max_pages * h->n_slots * (h->kv_f32 ? sizeof(float) : sizeof(bf16));
+        CK(cudaMalloc(&h->kv_pool, bytes));
+        CK(cudaMemset(h->kv_pool, 0, bytes));
+    }
     if (dalloc(h, &h->cp_kv, (size_t)s.cp_layers * 2 * s.cp_kv_heads * (1 << CP_PAGE_SHIFT) * D)) return 1;
     {
         std::vector<int> pt((size_t)h->n_slots * h->max_pages);
@@ -870,6 +873,10 @@ extern "C" {
 const char* lqt_create_error(void) { return g_create_error.c_str(); }
 
 int lqt_create(const char* model_dir, int device_id, lqt_engine** out) {
+    return lqt_create_ex(model_dir, device_id, nullptr, out);
+}
+
+int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, lqt_engine** out) {
     if (out) *out = nullptr;
     if (!model_dir || !out) { g_create_error = "null argument"; return 1; }
     int ndev = 0;
@@ -885,6 +892,12 @@ int lqt_create(const char* model_dir, int device_id, lqt_engine** out) {
     lqt_engine* h = new lqt_engine();
     h->device = device_id;
     h->num_sms = prop.multiProcessorCount;
+    h->n_slots = 2;
+    if (opt) {
+        if (opt->kv_dtype != LQT_KV_BF16 && opt->kv_dtype != LQT_KV_F32) { g_create_error = "bad kv_dtype"; delete h; return 1; }
+        h->kv_f32 = opt->kv_dtype == LQT_KV_F32;
+        if (opt->n_slots > 0) h->n_slots = opt->n_slots;
+    }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaStreamCreate failed"; delete h; return 1;
     }

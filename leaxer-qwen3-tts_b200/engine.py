@@ -15,7 +15,7 @@ LANG_CODEC_ID = {"auto": 0, "en": 2050, "zh": 2051, "ja": 2052, "ko": 2053}   # 
 
 # every symbol include/lqt_b200.h declares
 SYMBOLS = [
-    "lqt_create", "lqt_create_error", "lqt_destroy", "lqt_last_error", "lqt_get_info", "lqt_get_stats",
+    "lqt_create", "lqt_create_ex", "lqt_create_error", "lqt_destroy", "lqt_last_error", "lqt_get_info", "lqt_get_stats",
     "lqt_reset_stats", "lqt_text_project", "lqt_codec_embed", "lqt_code_predictor_embed",
     "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
@@ -27,6 +27,10 @@ class Sampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("top_p", C.c_float), ("top_k", C.c_int32),
                 ("max_new_tokens", C.c_int32), ("seed", C.c_uint32), ("utterance_id", C.c_uint32),
                 ("greedy", C.c_int32)]
+
+
+class Options(C.Structure):
+    _fields_ = [("kv_dtype", C.c_int32), ("n_slots", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -57,6 +61,7 @@ def load_library():
     if missing:
         raise RuntimeError(f"liblqt_b200.so lacks symbols: {missing}")
     lib.lqt_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lqt_create_ex.argtypes = [C.c_char_p, C.c_int, C.POINTER(Options), C.POINTER(C.c_void_p)]
     lib.lqt_create_error.restype = C.c_char_p
     lib.lqt_destroy.argtypes = [C.c_void_p]
     lib.lqt_destroy.restype = None
@@ -105,10 +110,11 @@ class EngineError(RuntimeError):
 class Engine:
     """One engine = one GPU = one host thread at a time (same contract as the reference)."""
 
-    def __init__(self, model_dir: str, device: int = 0):
+    def __init__(self, model_dir: str, device: int = 0, kv_dtype: str = "bf16", n_slots: int = 0):
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.lqt_create(model_dir.encode(), device, C.byref(h))
+        opt = Options({"bf16": 0, "f32": 1}[kv_dtype], n_slots)
+        rc = self.lib.lqt_create_ex(model_dir.encode(), device, C.byref(opt), C.byref(h))
         if rc != 0 or not h:
             raise EngineError(self.lib.lqt_create_error().decode())
         self.h = h

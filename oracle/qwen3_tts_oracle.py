@@ -194,8 +194,9 @@ def rope_apply(x, cos, sin):
 
 
 class OracleModel:
-    def __init__(self, model_dir: str):
+    def __init__(self, model_dir: str, kv_bf16: bool = True):
         self.model_dir = model_dir
+        self.kv_bf16 = kv_bf16          # talker KV rounding point (False mirrors LQT_KV_F32 parity mode)
         self.spec, graphs = ms.load_model_dir(model_dir)
         missing = [g for g in ms.GRAPH_FILES if g not in graphs]
         if missing:
@@ -267,7 +268,7 @@ class OracleModel:
         for i in range(sp.layers):
             x, kv["k"][i], kv["v"][i] = self._layer(
                 g, f"l{i}", x, pos0, kv["k"][i], kv["v"][i], sp.rms_eps, sp.heads, sp.kv_heads,
-                sp.head_dim, g["rope_cos"], g["rope_sin"], kv_bf16=True)
+                sp.head_dim, g["rope_cos"], g["rope_sin"], kv_bf16=self.kv_bf16)
         kv["len"] = pos0 + x.shape[0]
         hid = rmsnorm(x, g["norm"], sp.rms_eps)
         return hid @ g["head"].T, hid

@@ -49,12 +49,25 @@ def full_oracle(full_dir, oracle_mod):
     return oracle_mod.OracleModel(full_dir)
 
 
-def _engine(model_dir):
+@pytest.fixture(scope="session")
+def full_f32_oracle(full_dir, oracle_mod):
+    """oracle without the bf16 KV rounding point (mirrors LQT_KV_F32 parity mode)"""
+    return oracle_mod.OracleModel(full_dir, kv_bf16=False)
+
+
+def _engine(model_dir, **kw):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     from leaxer_qwen3_tts_b200 import engine
-    return engine.Engine(model_dir, device=0)
+    return engine.Engine(model_dir, device=0, **kw)
+
+
+@pytest.fixture(scope="session")
+def full_f32_engine(full_dir):
+    e = _engine(full_dir, kv_dtype="f32")
+    yield e
+    e.close()
 
 
 @pytest.fixture(scope="session")

@@ -38,6 +38,15 @@ def pair(request, which):
     return request.getfixturevalue(f"{which}_engine"), request.getfixturevalue(f"{which}_oracle")
 
 
+def tight(which):
+    """Engineering bound. The default engine rounds talker K/V to bf16 when they enter the paged
+    cache (north_star); a value that lands within fp32 summation noise of a bf16 rounding boundary
+    can round the other way than in the oracle, which on the full-size model moves logits by up to
+    ~1e-2 (still inside the north_star 2e-2). The fp32-KV parity mode ("full_f32") has no such
+    rounding point and must meet the tight bound."""
+    return LOGIT_TOL if which == "full" else LOGIT_TOL_TIGHT
+
+
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("which", ["tiny", "full"])
 def test_embeddings(request, which):
@@ -53,7 +62,7 @@ def test_embeddings(request, which):
         assert np.array_equal(eng.code_predictor_embed(tok, step), m.code_predictor_embed(tok, step).numpy())
 
 
-@pytest.mark.parametrize("which", ["tiny", "full"])
+@pytest.mark.parametrize("which", ["tiny", "full", "full_f32"])
 def test_talker_prefill_and_decode(request, which):
     eng, m = pair(request, which)
     H = m.spec.hidden
@@ -64,14 +73,14 @@ def test_talker_prefill_and_decode(request, which):
     logits, hid = eng.talker_prefill(x, slot=0)
     assert eng.kv_len(0) == P
     e1, e2 = maxabs(logits, ref_logits[-1].numpy()), maxabs(hid, ref_hid.numpy())
-    assert e1 < LOGIT_TOL and e1 < LOGIT_TOL_TIGHT, e1
-    assert e2 < LOGIT_TOL_TIGHT, e2
+    assert e1 < LOGIT_TOL and e1 < tight(which), e1
+    assert e2 < tight(which), e2
     for step in range(4):
         e = rnd((H,), 10 + step, 4.0)
         rl, rh = m.talker_decode(torch.from_numpy(e), kv)
         lg, hd = eng.talker_decode(e, slot=0)
         e1, e2 = maxabs(lg, rl.numpy()), maxabs(hd, rh.numpy())
-        assert e1 < LOGIT_TOL_TIGHT and e2 < LOGIT_TOL_TIGHT, (step, e1, e2)
+        assert e1 < tight(which) and e2 < tight(which), (step, e1, e2)
         assert int(np.argmax(lg)) == int(np.argmax(rl.numpy()))
     assert eng.kv_len(0) == P + 4
 
@@ -194,7 +203,7 @@ def _run_generate(eng, m, orc, ids, lang, sp_o, sp_e, trace=True):
     return ref_codes, tr, got
 
 
-@pytest.mark.parametrize("which,frames", [("tiny", 12), ("full", 6)])
+@pytest.mark.parametrize("which,frames", [("tiny", 12), ("full", 6), ("full_f32", 6)])
 def test_generate_greedy_token_exact(request, which, frames):
     eng, m = pair(request, which)
     orc = request.getfixturevalue("oracle_mod")
@@ -207,9 +216,9 @@ def test_generate_greedy_token_exact(request, which, frames):
     for f in range(frames):
         ref0 = tr["talker_logits"][f]
         fin = np.isfinite(ref0)
-        assert maxabs(tb[f, 0, :V][fin], ref0[fin]) < LOGIT_TOL_TIGHT
+        assert maxabs(tb[f, 0, :V][fin], ref0[fin]) < tight(which)
         assert np.all(np.isneginf(tb[f, 0, :V][~fin]))
-        assert maxabs(tb[f, 1:, :Vs], tr["cp_logits"][f]) < LOGIT_TOL_TIGHT
+        assert maxabs(tb[f, 1:, :Vs], tr["cp_logits"][f]) < tight(which)
 
 
 @pytest.mark.parametrize("which,frames", [("tiny", 12), ("full", 5)])
