@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Qwen3-TTS hot path.
+
+Metric (BASELINE.json): real-time factor = audio seconds / wall seconds, plus p50 first-audio
+latency. A "step" is one pass of the hot path over one batch of synthetic input: at N GPUs every
+rank synthesises `--utterances` C2-shaped utterances (BASELINE.json configs[1]: 0.6B-Base, batch 1,
+30 s = 375 frames, English, temp 0.8 / top-k 50 / top-p 0.95, seeded Philox) through
+lqt_synthesize_tokens (prompt assembly -> prefill -> frame loop A+B -> vocoder, all on the device).
+Request-level data parallelism, no collective on the data path => "scaling": "weak".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+value  : audio-s / s with inputs resident on the device (CUDA-event time measured by the library on
+         its own stream, prompt build -> last vocoder kernel), max over ranks.
+e2e    : the same through the C-ABI with HOST buffers: token ids in, PCM + codes out (pinned),
+         wall clock between barrier+synchronize pairs, max over ranks.
+roofline: the frame loop (weight-streaming GEMV kernels) against the measured HBM peak:
+         algorithmic bytes per frame x frames / CUDA-event time of the frame loop.
+cpu_baseline / --impl reference: the CPU oracle executing the REFERENCE's schedule (48 graph calls
+         per frame, cache-less code predictor, whole-KV copy per step: src/tts_onnx.cpp:782-872) on
+         the box's host cores -- the stand-in for the ORT CPU path, which cannot be built here
+         (no onnxruntime, no .onnx graphs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+load_package()
+from leaxer_qwen3_tts_b200 import modelspec as ms  # noqa: E402
+
+METRIC = "real-time factor (audio s / wall s)"
+UNIT = "audio-s/s"
+FRAME_S = 0.08                      # 1920 samples @ 24 kHz per frame (src/tts_onnx.h:69)
+WORKLOAD = ("0.6B-Base batch-1 decode, 30 s English prompt (375 frames, 90 synthetic text ids), "
+            "temp 0.8 / top-k 50 / top-p 0.95, Philox seed 1234 [BASELINE.json configs[1]]")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def frame_bytes(spec: ms.ModelSpec, mean_kv_pos: float) -> dict:
+    """Algorithmic bytes one frame must move at batch 1 (bf16 weights, no cross-pass reuse):
+    talker step (all layers + final norm + codec head) + KV read + 15 predictor passes
+    (5 layers + one head each; 16 token passes through the body incl. the extra row of pass 0 is
+    still one weight read per pass in the minimum-traffic schedule: pass 0 reads the body once for
+    its 2 rows). SURVEY.md §8d."""
+    def layer(H, qd, kvd, I):
+        return H * (qd + 2 * kvd) + qd * H + 3 * H * I
+    talker = spec.layers * layer(spec.hidden, spec.q_dim, spec.kv_dim, spec.inter) + spec.vocab * spec.hidden
+    cp_body = spec.cp_layers * layer(spec.cp_hidden, spec.cp_q_dim, spec.cp_kv_dim, spec.cp_inter)
+    cp_head = spec.cp_vocab * spec.cp_hidden
+    kv = spec.layers * 2 * spec.kv_dim * 2 * mean_kv_pos
+    return {"talker": 2 * talker, "predictor": spec.cp_steps * 2 * (cp_body + cp_head), "kv": kv,
+            "total": 2 * talker + spec.cp_steps * 2 * (cp_body + cp_head) + kv}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev: int):
+        self.dev, self.proc, self.lines = dev, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU stand-in for the reference's ORT CPU path (oracle, reference schedule)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(mdir: str, token_ids, frames: int, threads: int, seed: int = 1234, warm: bool = True):
+    """-> (audio seconds, wall seconds) of one bounded sample: prompt + `frames` frames + vocoder."""
+    import torch
+    from oracle import qwen3_tts_oracle as orc
+    torch.set_num_threads(threads)
+    m = cpu_reference_run._model if getattr(cpu_reference_run, "_mdir", None) == mdir else None
+    if m is None:
+        m = orc.OracleModel(mdir)
+        cpu_reference_run._model, cpu_reference_run._mdir = m, mdir
+        if warm:                      # materialise the fp32 weight views outside the timed region
+            p = orc.SamplingParams(max_new_tokens=1, seed=seed)
+            orc.synthesize_tokens(m, token_ids, "en", p, schedule="reference")
+    p = orc.SamplingParams(temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=frames, seed=seed)
+    t0 = time.perf_counter()
+    audio, codes = orc.synthesize_tokens(m, token_ids, "en", p, schedule="reference")
+    dt = time.perf_counter() - t0
+    return codes.shape[0] * FRAME_S, dt
+
+
+def run_reference_arm(a, mdir, token_ids):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # size the per-step sample so that (steps + warmup) steps end within ~3 minutes
+    t0 = time.perf_counter()
+    cpu_reference_run(mdir, token_ids, 1, cores)
+    _, t1f = cpu_reference_run(mdir, token_ids, 2, cores)
+    per_frame = max(t1f / 2.0, 1e-3)
+    budget = 150.0 / max(a.steps + a.warmup, 1)
+    frames = int(max(1, min(a.frames, budget / per_frame)))
+    log(f"[reference] oracle load+warm {time.perf_counter() - t0:.1f}s, ~{per_frame * 1e3:.0f} ms/frame "
+        f"-> {frames} frames per step")
+    for _ in range(a.warmup):
+        cpu_reference_run(mdir, token_ids, frames, cores)
+    audio_s = wall = 0.0
+    for _ in range(a.steps):
+        s, dt = cpu_reference_run(mdir, token_ids, frames, cores)
+        audio_s += s; wall += dt
+    v = audio_s / wall
+    sample = (f"first {frames} frames of the C2 utterance per step (prompt assembly + prefill + frames + "
+              f"vocoder), reference schedule (48 graph calls/frame), torch CPU fp32, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": wall / a.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": frames, "parallelism": "cpu host cores, rank 0 only"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "ONNX Runtime and the .onnx graphs are not available offline; this is the CPU oracle "
+                    "(oracle/qwen3_tts_oracle.py) running the reference's schedule"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=375, help="max_new_tokens per utterance (375 = 30 s)")
+    ap.add_argument("--utterances", type=int, default=1, help="utterances per GPU per step (sequential)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spec", default="0.6b", choices=["0.6b", "1.7b", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=12, help="frames in the cpu_baseline sample")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "b200":
+        log("[bench] note: timing rules ask for >= 3 warm-up steps")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = {"0.6b": ms.spec_0p6b, "1.7b": ms.spec_1p7b, "tiny": ms.spec_tiny}[a.spec](0)
+    mdir = ms.default_model_dir(spec)
+    from leaxer_qwen3_tts_b200.engine import wrap_text_ids
+    token_ids = wrap_text_ids(ms.synthetic_text_ids(90, 1234))
+
+    if a.impl == "reference":
+        if rank == 0:
+            ms.generate_model_dir(mdir, spec)
+        return run_reference_arm(a, mdir, token_ids)
+
+    import torch
+    if not torch.cuda.is_available():
+        log("bench.py: no CUDA device; the product path has no CPU fallback")
+        return 2
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # weights: rank 0 of the node writes the seeded random-init model dir, the others wait
+    if local == 0:
+        t0 = time.time()
+        ms.generate_model_dir(mdir, spec)
+        log(f"[bench] model dir {mdir} ready ({time.time() - t0:.1f}s)")
+    if dist:
+        dist.barrier()
+
+    from leaxer_qwen3_tts_b200 import engine
+    eng = engine.Engine(mdir, device=local)
+    spf = eng.info.samples_per_frame
+    audio_pin = torch.empty(a.frames * spf, dtype=torch.float32).pin_memory().numpy()
+    codes_pin = torch.empty(a.frames * 16, dtype=torch.int64).pin_memory().numpy()
+    ids_np = np.asarray(token_ids, np.int64)
+
+    def one_step(step_idx):
+        dev_ms = gen_ms = voc_ms = 0.0
+        nfr = 0
+        for u in range(a.utterances):
+            utt = (rank * a.utterances + u) * 1000003 + step_idx          # distinct Philox key per utterance
+            audio, codes = eng.synthesize_tokens(ids_np, "en", 0.8, 50, 0.95, a.frames, 1234, utt,
+                                                 audio_out=audio_pin, codes_out=codes_pin)
+            st = eng.stats()
+            dev_ms += st.last_total_ms; gen_ms += st.last_generate_ms; voc_ms += st.last_vocoder_ms
+            nfr += codes.shape[0]
+            assert audio.shape[0] == codes.shape[0] * spf
+        return dev_ms, gen_ms, voc_ms, nfr
+
+    def fence():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        one_step(-1 - i)
+    eng.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    fence()
+    t0 = time.perf_counter()
+    dev_ms = gen_ms = voc_ms = 0.0
+    frames = 0
+    for i in range(a.steps):
+        d, g, v, n = one_step(i)
+        dev_ms += d; gen_ms += g; voc_ms += v; frames += n
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    fence()
+    clocks = sampler.stop() if rank == 0 else None
+    st = eng.stats()
+
+    vals = torch.tensor([wall, dev_ms, gen_ms, voc_ms], dtype=torch.float64, device=f"cuda:{local}")
+    tot = torch.tensor([float(frames), float(st.kernel_launches)], dtype=torch.float64, device=f"cuda:{local}")
+    if dist:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    wall_max, dev_ms_max, gen_ms_max, voc_ms_max = [float(x) for x in vals.tolist()]
+    frames_all, launches_all = [float(x) for x in tot.tolist()]
+    audio_s = frames_all * FRAME_S
+    value = audio_s / (dev_ms_max * 1e-3)
+    e2e = audio_s / wall_max
+
+    if rank != 0:
+        eng.close()
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    # roofline of the frame loop (rank 0's own loop; ranks are identical replicas)
+    hbm_peak, peak_src = peaks()
+    P = 9
+    fb = frame_bytes(spec, mean_kv_pos=P + (a.frames - 1) / 2.0)
+    frames_r0 = frames if frames else 1
+    gen_s = gen_ms * 1e-3
+    achieved = fb["total"] * frames_r0 / gen_s / 1e9 if gen_s > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None,
+                "kernel": "frame loop (weight-streaming GEMV + attention + sampler), per frame",
+                "algorithmic_bytes_per_frame": fb, "us_per_frame": gen_s / frames_r0 * 1e6,
+                "peak_source": peak_src}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        t0 = time.time()
+        s, dt = cpu_reference_run(mdir, token_ids, a.cpu_frames, cores)
+        cpu = {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {a.cpu_frames} frames of the same C2 utterance (prompt + prefill + frames + vocoder), "
+                         f"reference schedule, torch CPU fp32, {cores} threads, {dt:.1f}s of CPU work"}
+        log(f"[bench] cpu_baseline took {time.time() - t0:.1f}s incl. oracle load")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD if a.frames == 375 and a.spec == "0.6b" else f"{a.spec} {a.frames} frames (non-headline)",
+                   "spec": spec.name, "frames": a.frames, "utterances_per_gpu_per_step": a.utterances,
+                   "parallelism": f"dp{world} (request-level, no collective)",
+                   "l2": "inputs larger than L2: 1.05 GB of weights streamed per frame vs 126 MB L2",
+                   "kv_cache": "paged bf16"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes * a.utterances),
+                "d2h_bytes_per_step": int((a.frames * spf * 4 + a.frames * 16 * 8) * a.utterances),
+                "ms_per_step": wall_max / a.steps * 1e3},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "first_audio_ms_p50": wall_max / a.steps / a.utterances * 1e3,
+        "first_audio_note": "no chunked vocoding yet: first audio = full utterance latency (as in the reference)",
+        "breakdown_ms_per_step": {"frame_loop": gen_ms_max / a.steps, "vocoder": voc_ms_max / a.steps,
+                                  "device_total": dev_ms_max / a.steps, "host_wall": wall_max / a.steps * 1e3},
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

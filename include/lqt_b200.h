@@ -48,6 +48,7 @@ typedef struct lqt_stats {
     float    last_vocoder_ms;     /* CUDA-event time of the last vocoder pass */
     float    last_prefill_ms;
     int32_t  last_frames;
+    float    last_total_ms;       /* lqt_synthesize_tokens: CUDA-event time prompt build -> last vocoder kernel */
 } lqt_stats;
 
 /* Engine options (lqt_create_ex). kv_dtype: LQT_KV_BF16 = paged bf16 talker KV cache (default,

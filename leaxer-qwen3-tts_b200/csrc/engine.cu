@@ -120,7 +120,7 @@ struct lqt_engine {
     // frame graphs keyed by slot*2 + trace
     std::map<int, cudaGraphExec_t> graphs;
     int kernels_per_frame = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr;
     // vocoder workspace
     std::map<std::string, std::pair<float*, size_t>> ws;
     long long* voc_codes_dev = nullptr; size_t voc_codes_cap = 0;
@@ -859,7 +859,7 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         dalloc(h, &h->prompt_dev, (size_t)16 * H))
         return 1;
     CK(cudaMallocHost((void**)&h->st_host, sizeof(GenState)));
-    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev_t0));
     return 0;
 }
 
@@ -925,6 +925,7 @@ void lqt_destroy(lqt_engine* h) {
     if (h->st_host) cudaFreeHost(h->st_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     h->f_text.release(); h->f_codec.release(); h->f_cpe.release(); h->f_talker.release();
     h->f_cp.release(); h->f_voc.release(); h->f_spk.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1180,10 +1181,12 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     *n_samples = 0;
     if (n_frames) *n_frames = 0;
     int P = 0, TL = 0;
+    CK(cudaEventRecord(h->ev_t0, h->stream));
     if (build_prompt_device(h, token_ids, n_ids, lang_codec_id, speaker_embed, &P, &TL)) return 1;
     int nf = 0;
     if (generate_core(h, 0, P, TL, sp, 0, false, &nf)) return 1;
     if (n_frames) *n_frames = nf;
+    h->stats.last_total_ms = 0.f;
     if (nf == 0) return 0;                                   // empty result, like src/tts_onnx.cpp:418
     if (codes_out) CK(cudaMemcpyAsync(codes_out, h->codes_dev, (size_t)nf * N_CODEBOOKS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     const int64_t n = (int64_t)nf * h->sp.samples_per_frame;
@@ -1195,6 +1198,7 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     CK(cudaMemcpyAsync(audio_out, h->audio_dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->stats.last_vocoder_ms, h->ev0, h->ev1);
+    cudaEventElapsedTime(&h->stats.last_total_ms, h->ev_t0, h->ev1);
     *n_samples = n;
     return 0;
 }

@@ -42,7 +42,8 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64),
                 ("last_generate_ms", C.c_float), ("last_vocoder_ms", C.c_float),
-                ("last_prefill_ms", C.c_float), ("last_frames", C.c_int32)]
+                ("last_prefill_ms", C.c_float), ("last_frames", C.c_int32),
+                ("last_total_ms", C.c_float)]
 
 
 _lib = None
@@ -101,6 +102,15 @@ def _i64(a):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# src/tts_onnx.h:39-47 special text-token ids
+IM_START, IM_END, ASSISTANT, TTS_BOS, TTS_EOS, TTS_PAD = 151644, 151645, 77091, 151672, 151673, 151671
+
+
+def wrap_text_ids(text_ids):
+    """TTSEngine::synthesize id wrapping, src/tts_onnx.cpp:243-259."""
+    return [IM_START, ASSISTANT, TTS_BOS] + [int(t) for t in text_ids] + [TTS_EOS, IM_END]
 
 
 class EngineError(RuntimeError):
@@ -242,16 +252,28 @@ class Engine:
         return prompt[: P.value].copy(), trailing[: TL.value].copy(), pad
 
     def synthesize_tokens(self, token_ids, lang: str = "auto", temperature=0.8, top_k=50, top_p=0.95,
-                          max_new_tokens=2048, seed=0, utterance_id=0, greedy=False, speaker_embed=None):
-        """src/tts_onnx.cpp:405-436 -> (audio f32 [n], codes i64 [T,16])"""
+                          max_new_tokens=2048, seed=0, utterance_id=0, greedy=False, speaker_embed=None,
+                          audio_out=None, codes_out=None):
+        """src/tts_onnx.cpp:405-436 -> (audio f32 [n], codes i64 [T,16]).
+        audio_out / codes_out: optional caller-owned (e.g. pinned) host buffers; views are returned."""
         ids = _i64(token_ids)
         sp = self.sampling(temperature, top_k, top_p, max_new_tokens, seed, utterance_id, greedy)
         cap = max(max_new_tokens, 1) * self.info.samples_per_frame
-        audio = np.empty(cap, np.float32)
-        codes = np.zeros((max(max_new_tokens, 1), 16), np.int64)
+        if audio_out is not None:
+            assert audio_out.dtype == np.float32 and audio_out.size >= cap and audio_out.flags.c_contiguous
+            audio = audio_out.reshape(-1)
+        else:
+            audio = np.empty(cap, np.float32)
+        if codes_out is not None:
+            assert codes_out.dtype == np.int64 and codes_out.size >= max(max_new_tokens, 1) * 16
+            codes = codes_out.reshape(-1)[: max(max_new_tokens, 1) * 16].reshape(-1, 16)
+        else:
+            codes = np.zeros((max(max_new_tokens, 1), 16), np.int64)
         ns, nf = C.c_int64(0), C.c_int32(0)
         spk = _f32(speaker_embed) if speaker_embed is not None else None
         self._ck(self.lib.lqt_synthesize_tokens(self.h, _ptr(ids), len(ids), LANG_CODEC_ID[lang], _ptr(spk),
                                                 C.byref(sp), _ptr(audio), cap, C.byref(ns), _ptr(codes),
                                                 C.byref(nf)))
+        if audio_out is not None or codes_out is not None:
+            return audio[: ns.value], codes[: nf.value]
         return audio[: ns.value].copy(), codes[: nf.value].copy()

@@ -502,6 +502,13 @@ def load_model_dir(model_dir: str):
     return spec, graphs
 
 
+def synthetic_text_ids(n_text: int, seed: int = 1234):
+    """Synthetic prompt ids uniform in [0,151643); hash-based, machine independent.
+    Same stream as oracle.synthetic_text_ids (tests assert equality)."""
+    u = uniform_pm1(seed, "synthetic_text_ids", n_text)
+    return [int(x) for x in ((u.astype(np.float64) + 1.0) * 0.5 * 151643).astype(np.int64)]
+
+
 def default_model_dir(spec: ModelSpec) -> str:
     root = os.environ.get("LQT_MODEL_CACHE", "/tmp/lqt_models")
     return os.path.join(root, f"{spec.name}-seed{spec.seed}", "onnx_kv")

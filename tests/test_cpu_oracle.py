@@ -1,0 +1,295 @@
+"""CPU suite (`-m "not gpu"`): the oracle against its pins (known-answer vectors, committed golden
+fixtures), the model-spec / weight-file host logic, and the C-ABI library surface (loads, exports
+every symbol include/lqt_b200.h declares, fails loudly without a GPU). No GPU compute here."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+from leaxer_qwen3_tts_b200 import modelspec as ms
+
+
+# ---------------------------------------------------------------------------------------------
+# Philox4x32-10: Random123 known-answer vectors (kat_vectors of the Random123 distribution)
+# ---------------------------------------------------------------------------------------------
+PHILOX_KAT = [
+    ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+    ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+    ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+     (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+]
+
+
+def test_philox_known_answers(oracle_mod):
+    for ctr, key, want in PHILOX_KAT:
+        assert oracle_mod.philox4x32_10(ctr, key) == want
+    u = oracle_mod.philox_uniform(1234, 0, 0, 0)
+    assert 0.0 <= float(u) < 1.0 and u.dtype == np.float32
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler semantics (src/tts_onnx.cpp:878-950)
+# ---------------------------------------------------------------------------------------------
+def _ref_filtered(logits, t, k, p):
+    """independent float64-free restatement with python lists (small V), mirrors the C++ order"""
+    x = [np.float32(v) for v in logits]
+    if t > 0 and np.float32(t) != np.float32(1):
+        x = [np.float32(v / np.float32(t)) for v in x]
+    V = len(x)
+    if 0 < k < V:
+        thr = sorted(x, reverse=True)[k - 1]
+        x = [v if not (v < thr) else np.float32(-np.inf) for v in x]
+    m = max(x)
+    e = [np.float32(np.exp(np.float64(v - m))) if v != -np.inf else np.float32(0) for v in x]
+    s = np.float32(0)
+    for v in e:
+        s = np.float32(s + v)
+    pr = [np.float32(v / s) for v in e]
+    if p < 1.0:
+        order = sorted(range(V), key=lambda i: (-pr[i], i))
+        c, cut = np.float32(0), V
+        for n, i in enumerate(order):
+            c = np.float32(c + pr[i])
+            if c > np.float32(p):
+                cut = n + 1
+                break
+        for i in order[cut:]:
+            pr[i] = np.float32(0)
+        s2 = np.float32(0)
+        for v in pr:
+            s2 = np.float32(s2 + v)
+        if s2 > 0:
+            pr = [np.float32(v / s2) for v in pr]
+    return np.asarray(pr, np.float32)
+
+
+def test_sampler_filters_match_reference_order_of_operations(oracle_mod):
+    g = np.random.default_rng(0)
+    for t, k, p in [(0.8, 50, 0.95), (1.0, 5, 0.5), (0.0, 3, 0.9), (1.3, 0, 1.0), (0.7, 1, 0.95), (0.9, 400, 0.3)]:
+        for rep in range(3):
+            lg = (g.standard_normal(257) * 3).astype(np.float32)
+            if rep == 1:
+                lg = np.round(lg)                      # ties at the top-k threshold
+            sp = oracle_mod.SamplingParams(temperature=t, top_k=k, top_p=p)
+            got = oracle_mod.sampler_filtered_probs(lg, sp)
+            want = _ref_filtered(lg, t, k, p)
+            assert np.array_equal(got, want), (t, k, p, rep)
+            if k == 1:
+                assert got[np.argmax(lg)] == 1.0       # reference "greedy" == --top-k 1
+    # top-k keeps every value tied at the threshold (strict < at :924)
+    lg = np.array([1, 3, 3, 3, 0, -1], np.float32)
+    pr = oracle_mod.sampler_filtered_probs(lg, oracle_mod.SamplingParams(temperature=1.0, top_k=2, top_p=1.0))
+    assert np.count_nonzero(pr) == 3
+    # top-p: first index whose running sum EXCEEDS p is the last kept (:941-944)
+    lg = np.log(np.array([0.5, 0.3, 0.2], np.float32))
+    pr = oracle_mod.sampler_filtered_probs(lg, oracle_mod.SamplingParams(temperature=1.0, top_k=0, top_p=0.6))
+    assert np.count_nonzero(pr) == 2
+
+
+def test_sampler_golden_vectors(oracle_mod):
+    g = np.load(os.path.join(GOLDEN, "tiny_vectors.npz"))
+    lg = g["sampler_logits"]
+    toks = [oracle_mod.sample_token(lg[i], oracle_mod.SamplingParams(seed=1234, utterance_id=i), i, i)
+            for i in range(lg.shape[0])]
+    assert toks == g["sampler_tokens"].tolist()
+    assert oracle_mod.sample_token(lg[0], oracle_mod.SamplingParams(greedy=True), 0, 0) == int(np.argmax(lg[0]))
+
+
+# ---------------------------------------------------------------------------------------------
+# model spec / weight files
+# ---------------------------------------------------------------------------------------------
+def test_bf16_rounding_matches_torch():
+    x = (np.random.default_rng(1).standard_normal(100000) * 3).astype(np.float32)
+    x[:4] = [1.00390625, 1.01171875, -1.00390625, 0.0]                # exact ties -> even
+    got = ms.bf16_bits_to_f32(ms.f32_to_bf16_bits(x))
+    want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(got, want)
+
+
+def test_generator_is_deterministic_and_chunk_invariant():
+    a = ms.uniform_pm1(0, "g/t", 1000)
+    b = np.concatenate([ms.uniform_pm1(0, "g/t", 400), ms.uniform_pm1(0, "g/t", 600, 400)])
+    assert np.array_equal(a, b)
+    assert np.all(np.abs(a) < 1.0) and abs(float(a.mean())) < 0.1
+    assert not np.array_equal(a, ms.uniform_pm1(1, "g/t", 1000))
+    assert not np.array_equal(a, ms.uniform_pm1(0, "g/u", 1000))
+
+
+def test_lqw_roundtrip(tmp_path):
+    t = [("a.w", ms.DT_BF16, ms.f32_to_bf16_bits(np.arange(12, dtype=np.float32).reshape(3, 4))),
+         ("b", ms.DT_F32, np.linspace(0, 1, 7, dtype=np.float32))]
+    p = str(tmp_path / "x.lqw")
+    ms.write_lqw(p, t, {"hidden": 4, "rms_eps": 1e-6, "graph": "x"})
+    meta, tensors = ms.read_lqw(p)
+    assert meta["hidden"] == "4" and meta["graph"] == "x"
+    assert np.array_equal(np.asarray(tensors["a.w"]), t[0][2]) and tensors["a.w"].shape == (3, 4)
+    assert np.array_equal(np.asarray(tensors["b"]), t[1][2])
+    assert os.path.getsize(p) % 256 == 0
+
+
+def test_model_dir_layout_and_sizes(tiny_dir):
+    """seven graph files named after the reference's .onnx files (src/tts_onnx.cpp:91-97)"""
+    for g in ms.GRAPH_FILES:
+        assert os.path.exists(os.path.join(tiny_dir, g + ".lqw")), g
+    spec, graphs = ms.load_model_dir(tiny_dir)
+    assert spec.name == "qwen3-tts-tiny" and spec.samples_per_frame == 1920
+    assert graphs["talker_decode"] is graphs["talker_prefill"]
+    assert np.all(np.asarray(graphs["talker_prefill"]["head"])[2150] == 0)          # EOS row
+    full = ms.spec_0p6b()
+    defs = ms.graph_tensor_defs(full)
+    talker = sum(int(np.prod(t.shape)) for t in defs["talker_prefill"] if t.dtype == ms.DT_BF16)
+    assert talker == 443_547_648 + 0 or talker == 28 * 15_728_640 + 3072 * 1024   # SURVEY §8 derived sizes (weights only)
+    body = sum(int(np.prod(t.shape)) for t in defs["code_predictor"] if t.dtype == ms.DT_BF16 and t.name != "heads")
+    assert body == 5 * 15_728_640
+    assert ms.spec_1p7b().hidden == 2048 and any(t.name == "in_proj.weight" for t in ms.graph_tensor_defs(ms.spec_1p7b())["code_predictor"])
+
+
+def test_synthetic_ids_shared_between_product_and_oracle(oracle_mod):
+    from leaxer_qwen3_tts_b200 import engine
+    assert ms.synthetic_text_ids(90, 1234) == oracle_mod.synthetic_text_ids(90, 1234)
+    assert engine.wrap_text_ids([5, 6]) == oracle_mod.wrap_text_ids([5, 6]) == [151644, 77091, 151672, 5, 6, 151673, 151645]
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle vs committed golden fixtures
+# ---------------------------------------------------------------------------------------------
+def test_oracle_tiny_vocoder_golden(tiny_oracle):
+    g = np.load(os.path.join(GOLDEN, "tiny_vectors.npz"))
+    audio, n = tiny_oracle.vocoder(g["codes"])
+    assert n == g["codes"].shape[0] * 1920
+    assert np.allclose(audio.numpy(), g["audio"], atol=1e-5)
+    # causality: a prefix of the codes gives a prefix of the audio (what chunked decode relies on)
+    half, _ = tiny_oracle.vocoder(g["codes"][:3])
+    assert np.allclose(half.numpy(), g["audio"][: 3 * 1920], atol=1e-5)
+
+
+def test_oracle_prompt_layouts(tiny_oracle, oracle_mod):
+    """P = 8 / 9 / 10 and the row contents"""
+    m, o = tiny_oracle, oracle_mod
+    ids = o.wrap_text_ids([11, 12, 13])
+    H = m.spec.hidden
+    tp = lambda i: m.text_project([i])[0]
+    ce = lambda i: m.codec_embed([i])[0]
+    for lang, spk, P in [("auto", None, 8), ("en", None, 9), ("auto", np.ones(H, np.float32), 9), ("ko", np.ones(H, np.float32), 10)]:
+        st = o.UtteranceState(kv=m.new_kv())
+        pr = o.build_prompt_embeddings(m, ids, lang, st, spk)
+        assert pr.shape == (P, H)
+        assert torch.allclose(pr[0], tp(o.IM_START), atol=1e-5) and torch.allclose(pr[2], tp(o.TTS_BOS), atol=1e-5)
+        assert torch.allclose(pr[-1], tp(11) + ce(o.CODEC_BOS), atol=1e-5)
+        first_codec = o.CODEC_NOTHINK if lang == "auto" else o.CODEC_THINK
+        assert torch.allclose(pr[3], tp(o.TTS_PAD) + ce(first_codec), atol=1e-5)
+        if spk is not None:
+            assert torch.allclose(pr[-2], tp(o.TTS_BOS) + torch.ones(H), atol=1e-5)
+        else:
+            assert torch.allclose(pr[-2], tp(o.TTS_BOS) + ce(o.CODEC_PAD), atol=1e-5)
+        assert st.trailing_len == 3                                  # 2 remaining text tokens + tts_eos
+        assert torch.allclose(st.trailing_text_hidden[-1], tp(o.TTS_EOS), atol=1e-5)
+        if lang != "auto":
+            assert torch.allclose(pr[5], tp(o.TTS_PAD) + ce(o.LANG_IDS[lang]), atol=1e-5)
+
+
+def test_oracle_reference_schedule_equals_cached_schedule(tiny_oracle, oracle_mod):
+    """the reference re-runs the predictor on the growing sequence (no KV cache, :862-869); the
+    KV-cached form the engine uses is arithmetically the same graph"""
+    o = oracle_mod
+    ids = o.wrap_text_ids([100, 200, 300, 400])
+    p = o.SamplingParams(max_new_tokens=4, seed=3)
+    _, c_ref = o.synthesize_tokens(tiny_oracle, ids, "zh", p, schedule="reference", run_vocoder=False)
+    n_ref = tiny_oracle.graph_calls
+    _, c_cached = o.synthesize_tokens(tiny_oracle, ids, "zh", p, schedule="cached", run_vocoder=False)
+    assert np.array_equal(c_ref, c_cached) and c_ref.shape == (4, 16)
+    assert c_ref[:, 0].max() < 2048 or 2150 in c_ref[:, 0]
+    assert n_ref > 0
+
+
+def test_oracle_eos_semantics(tiny_oracle, oracle_mod):
+    o, m = oracle_mod, tiny_oracle
+    ids = o.wrap_text_ids([5, 6, 7])
+    forced = np.random.default_rng(0).integers(0, 2048, size=(5, 16))
+    forced[2, 0] = o.CODEC_EOS
+    _, codes = o.synthesize_tokens(m, ids, "auto", o.SamplingParams(max_new_tokens=5, greedy=True),
+                                   forced_codes=forced, run_vocoder=False)
+    assert codes.shape == (2, 16)
+    forced[0, 0] = o.CODEC_EOS
+    audio, codes = o.synthesize_tokens(m, ids, "auto", o.SamplingParams(max_new_tokens=5, greedy=True), forced_codes=forced)
+    assert codes.shape == (0, 16) and audio.shape == (0,)           # :418 empty result
+
+
+@pytest.mark.timeout(600)
+def test_oracle_full_c1_golden_prefix(full_oracle, oracle_mod):
+    """BASELINE.json configs[0] ('Hello world' en greedy) on the full 0.6B random-init model: the
+    oracle reproduces the committed fixture (first frames; the whole 25-frame run is what
+    tests/golden/make_golden.py executes)."""
+    o = oracle_mod
+    g = np.load(os.path.join(GOLDEN, "c1_hello_world_en_greedy.npz"))
+    tr = {}
+    _, codes = o.synthesize_tokens(full_oracle, g["token_ids"].tolist(), "en",
+                                   o.SamplingParams(max_new_tokens=3, greedy=True), trace=tr, run_vocoder=False)
+    assert np.array_equal(codes, g["codes"][:3])
+    assert np.allclose(tr["prompt"], g["prompt"], atol=1e-5)
+    assert np.allclose(tr["talker_logits"][0][:2048], g["talker_logits_f0"][:2048], atol=2e-4)
+    assert np.allclose(tr["cp_logits"][0], g["cp_logits_f0"], atol=2e-4)
+    g2 = np.load(os.path.join(GOLDEN, "c2_short_seeded.npz"))
+    sp = o.SamplingParams(temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=2, seed=1234, utterance_id=0)
+    _, codes2 = o.synthesize_tokens(full_oracle, g2["token_ids"].tolist(), "en", sp, run_vocoder=False)
+    assert np.array_equal(codes2, g2["codes"][:2])
+
+
+# ---------------------------------------------------------------------------------------------
+# C-ABI surface
+# ---------------------------------------------------------------------------------------------
+def _header_symbols():
+    out = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in os.listdir(inc):
+        if fn.endswith(".h"):
+            src = open(os.path.join(inc, fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            out |= set(re.findall(r"\b(lqt_[a-z0-9_]+)\s*\(", src))
+    return out
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import ctypes
+    from leaxer_qwen3_tts_b200 import engine
+    lib = engine.load_library()                    # raises if the .so is missing
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"liblqt_b200.so does not export {s}"
+    assert set(engine.SYMBOLS) == syms, syms ^ set(engine.SYMBOLS)
+    assert isinstance(lib, ctypes.CDLL)
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    from leaxer_qwen3_tts_b200 import engine
+    assert C.sizeof(engine.Sampling) == 28 and C.sizeof(engine.Info) == 13 * 4 and C.sizeof(engine.Options) == 8
+    assert C.sizeof(engine.Stats) == 8 + 8 + 4 * 3 + 4 + 4 + 4   # incl. tail padding to 8
+
+
+def test_product_path_fails_loudly_without_gpu(tiny_dir):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from leaxer_qwen3_tts_b200 import engine
+    with pytest.raises(engine.EngineError) as ei:
+        engine.Engine(tiny_dir, device=0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_code_never_imports_the_oracle():
+    """the product path may not import, include, link or dlopen anything under oracle/"""
+    pkg = os.path.join(ROOT, "leaxer-qwen3-tts_b200")
+    bad = re.compile(r"^\s*(from\s+oracle|import\s+oracle|from\s+\S*qwen3_tts_oracle|import\s+\S*qwen3_tts_oracle)"
+                     r"|#\s*include\s*[<\"][^>\"]*oracle|dlopen\([^)]*oracle|CDLL\([^)]*oracle|-l\S*oracle", re.M)
+    n = 0
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or fn == "Makefile":
+                src = open(os.path.join(dp, fn), errors="ignore").read()
+                assert not bad.search(src), fn
+                n += 1
+    assert n >= 8
