@@ -197,7 +197,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spec", default="0.6b", choices=["0.6b", "1.7b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=12, help="frames in the cpu_baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=150, help="frames in the cpu_baseline sample (~10-30 s of CPU work)")
+    ap.add_argument("--frame-impl", default="persistent", choices=["persistent", "graph"],
+                    help="persistent = one cooperative kernel per utterance (default); graph = round-1 v1 schedule (A/B only)")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")
@@ -233,7 +235,7 @@ def main():
         dist.barrier()
 
     from leaxer_qwen3_tts_b200 import engine
-    eng = engine.Engine(mdir, device=local)
+    eng = engine.Engine(mdir, device=local, frame_impl=a.frame_impl)
     spf = eng.info.samples_per_frame
     audio_pin = torch.empty(a.frames * spf, dtype=torch.float32).pin_memory().numpy()
     codes_pin = torch.empty(a.frames * 16, dtype=torch.int64).pin_memory().numpy()
@@ -325,7 +327,7 @@ def main():
                    "spec": spec.name, "frames": a.frames, "utterances_per_gpu_per_step": a.utterances,
                    "parallelism": f"dp{world} (request-level, no collective)",
                    "l2": "inputs larger than L2: 1.05 GB of weights streamed per frame vs 126 MB L2",
-                   "kv_cache": "paged bf16"},
+                   "kv_cache": "paged bf16", "frame_impl": a.frame_impl},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes * a.utterances),
                 "d2h_bytes_per_step": int((a.frames * spf * 4 + a.frames * 16 * 8) * a.utterances),
                 "ms_per_step": wall_max / a.steps * 1e3},

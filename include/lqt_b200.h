@@ -55,9 +55,14 @@ typedef struct lqt_stats {
  * north_star); LQT_KV_F32 = "parity mode": fp32 pages, no rounding point in the talker, for
  * free-running token-exact comparison against the fp32 oracle over long utterances. */
 enum { LQT_KV_BF16 = 0, LQT_KV_F32 = 1 };
+/* frame_impl: LQT_FRAME_PERSISTENT (default) = loops A+B run inside one persistent cooperative kernel
+ * whose producer warp streams the weights with TMA bulk copies; LQT_FRAME_GRAPH = the round-1 v1
+ * schedule (a CUDA graph of ~577 per-op kernels per frame), kept only for A/B measurements. */
+enum { LQT_FRAME_PERSISTENT = 0, LQT_FRAME_GRAPH = 1 };
 typedef struct lqt_options {
     int32_t kv_dtype;
     int32_t n_slots;      /* KV slots (utterances resident at once); 0 = default (2) */
+    int32_t frame_impl;
 } lqt_options;
 
 /* src/tts_onnx.cpp:84-130 (TTSEngine ctor) + :134-232 (load_model): loads the 7 required graph
@@ -135,6 +140,12 @@ int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids,
                      int32_t lang_codec_id, const float* speaker_embed,
                      float* prompt_out, int32_t* P, float* trailing_out, int32_t* trailing_len,
                      float* tts_pad_out);
+
+/* Profiling aid (no reference counterpart): phase timeline of one CTA of the persistent frame kernel.
+ * enable_entries > 0: arm recording of CTA `cta` for the following launches (buffer of that many
+ * entries, overwritten by every launch); enable_entries == 0: copy the last launch's entries to
+ * `out` (each = SM clock << 8 | tag, see csrc/frame_kernel.cuh) and return their count. */
+int lqt_debug_timeline(lqt_engine* h, int32_t enable_entries, int32_t cta, uint64_t* out, int32_t out_cap);
 
 #ifdef __cplusplus
 }

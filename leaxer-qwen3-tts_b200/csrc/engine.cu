@@ -14,6 +14,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "frame_kernel.cuh"
 #include "gemv.cuh"
 #include "lqw_loader.h"
 #include "sampler.cuh"
@@ -121,6 +122,17 @@ struct lqt_engine {
     std::map<int, cudaGraphExec_t> graphs;
     int kernels_per_frame = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr;
+    // persistent frame kernel (frame_kernel.cuh)
+    int frame_impl = 0;                       // 0 = persistent kernel, 1 = v1 graph of kernels
+    std::vector<void*> fk_allocs;             // regrouped weights, layer tables, activation buffers
+    FkStack fk_talker{}, fk_cp{};
+    std::vector<FkLayer> fk_tl, fk_cl;
+    float *fk_pa = nullptr, *fk_cxin = nullptr;
+    unsigned* fk_ctrl = nullptr;
+    unsigned* fk_ctrl_host = nullptr;         // pinned
+    unsigned long long* fk_dbg = nullptr; int fk_dbg_cap = 0, fk_dbg_cta = 0;
+    FkSmemOffsets fk_so{};
+    size_t fk_smem = 0;
     // vocoder workspace
     std::map<std::string, std::pair<float*, size_t>> ws;
     long long* voc_codes_dev = nullptr; size_t voc_codes_cap = 0;
@@ -619,20 +631,14 @@ int upload_sampling(lqt_engine* h, const lqt_sampling* sp) {
     return 0;
 }
 
-// loops A+B on the device. prompt_dev / trailing_dev / tts_pad_dev / forced_dev already filled.
-int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sampling* sp, int n_forced,
-                  bool trace, int* n_frames_out) {
-    if (slot < 0 || slot >= h->n_slots) { h->err = "bad slot"; return 1; }
-    if (P < 1 || sp->max_new_tokens < 0 || sp->max_new_tokens > h->max_frames_cap ||
-        P + sp->max_new_tokens > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
+int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int frame_end, bool trace);
+int fk_check_abort(lqt_engine* h);
+
+// v1 frame loop (kept for A/B measurements): prefill as P decode-shaped steps + one CUDA graph of
+// per-op kernels per frame. GenState already uploaded.
+int generate_core_graph(lqt_engine* h, int slot, int P, const lqt_sampling* sp, bool trace) {
     cudaGraphExec_t graph;
     if (get_frame_graph(h, slot, trace, &graph)) return 1;
-    if (upload_sampling(h, sp)) return 1;
-    GenState g{};
-    g.pos = 0; g.frame = 0; g.done = 0; g.n_frames = 0; g.trailing_len = trailing_len;
-    g.max_frames = sp->max_new_tokens; g.cp_pos = 0; g.n_forced = n_forced;
-    *h->st_host = g;
-    CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     // prefill (src/tts_onnx.cpp:794): P decode-shaped steps, head only on the last row
     const int H = h->sp.hidden;
@@ -672,6 +678,35 @@ int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sa
     cudaEventElapsedTime(&h->stats.last_prefill_ms, h->ev0, h->ev1);
     cudaEventElapsedTime(&h->stats.last_generate_ms, evg0, evg1);
     cudaEventDestroy(evg0); cudaEventDestroy(evg1); cudaEventDestroy(evpoll);
+    return 0;
+}
+
+// loops A+B on the device. prompt_dev / trailing_dev / tts_pad_dev / forced_dev already filled.
+int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sampling* sp, int n_forced,
+                  bool trace, int* n_frames_out) {
+    if (slot < 0 || slot >= h->n_slots) { h->err = "bad slot"; return 1; }
+    if (P < 1 || sp->max_new_tokens < 0 || sp->max_new_tokens > h->max_frames_cap ||
+        P + sp->max_new_tokens > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
+    if (upload_sampling(h, sp)) return 1;
+    GenState g{};
+    g.pos = 0; g.frame = 0; g.done = 0; g.n_frames = 0; g.trailing_len = trailing_len;
+    g.max_frames = sp->max_new_tokens; g.cp_pos = 0; g.n_forced = n_forced;
+    *h->st_host = g;
+    CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
+    if (h->frame_impl == 0) {
+        // persistent frame kernel: prefill + all frames in one cooperative launch (frame_kernel.cuh)
+        CK(cudaEventRecord(h->ev0, h->stream));
+        if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        if (fk_check_abort(h)) return 1;
+        cudaEventElapsedTime(&h->stats.last_generate_ms, h->ev0, h->ev1);
+        h->stats.last_prefill_ms = 0.f;             // included in last_generate_ms
+    } else {
+        if (generate_core_graph(h, slot, P, sp, trace)) return 1;
+    }
     h->slot_len[slot] = h->st_host->pos;
     *n_frames_out = h->st_host->n_frames;
     h->stats.last_frames = h->st_host->n_frames;
@@ -737,6 +772,133 @@ bool load_vocoder_weights(lqt_engine* h) {
     h->out_sa = need<float>(h, f, "dec.snake_out.alpha", ok); h->out_sb = need<float>(h, f, "dec.snake_out.beta", ok);
     h->out_w = need<float>(h, f, "dec.conv_out.weight", ok);  h->out_b = need<float>(h, f, "dec.conv_out.bias", ok);
     return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent frame kernel: one-time weight regrouping, tables, launch
+// ------------------------------------------------------------------------------------------------
+// Wo [H][n_kv*gK] -> [n_kv][H][gK]  (each CTA's O-projection slice becomes one contiguous block)
+__global__ void regroup_wo_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int H, int n_kv, int gK) {
+    const long long n = (long long)H * n_kv * gK;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % gK); const long long r = i / gK; const int row = (int)(r % H); const int g = (int)(r / H);
+        dst[i] = src[(size_t)row * (n_kv * gK) + (size_t)g * gK + c];
+    }
+}
+// gate [I][H], up [I][H] -> [2I][H] with gate row n at 2n and up row n at 2n+1
+__global__ void interleave_gu_kernel(const bf16* __restrict__ g, const bf16* __restrict__ u, bf16* __restrict__ dst, int I, int H) {
+    const long long n = (long long)2 * I * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % H); const long long r = i / H;
+        const bf16* src = (r & 1) ? u : g;
+        dst[i] = src[(size_t)(r >> 1) * H + c];
+    }
+}
+
+template <typename T>
+int fk_alloc(lqt_engine* h, T** p, size_t n) {
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    CK(cudaMemset(*p, 0, n * sizeof(T)));
+    h->fk_allocs.push_back((void*)*p);
+    return 0;
+}
+
+int fk_build_stack(lqt_engine* h, const std::vector<LayerW>& layers, int H, int heads, int kv_heads, int inter,
+                   const float* cosr, const float* sinr, const float* final_norm, FkStack* out, std::vector<FkLayer>* tab_out) {
+    const int gK = (heads / kv_heads) * ATT_D, qkv_dim = (heads + 2 * kv_heads) * ATT_D;
+    std::vector<FkLayer> tab(layers.size());
+    for (size_t l = 0; l < layers.size(); ++l) {
+        bf16 *wo_g = nullptr, *wgu = nullptr;
+        if (fk_alloc(h, &wo_g, (size_t)H * kv_heads * gK) || fk_alloc(h, &wgu, (size_t)2 * inter * H)) return 1;
+        regroup_wo_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(layers[l].wo, wo_g, H, kv_heads, gK);
+        interleave_gu_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(layers[l].wgate, layers[l].wup, wgu, inter, H);
+        tab[l] = FkLayer{layers[l].wqkv, wo_g, wgu, layers[l].wdown, layers[l].ln1, layers[l].ln2, layers[l].qnorm, layers[l].knorm};
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    *tab_out = tab;
+    FkStack S{};
+    S.n_layers = (int)layers.size(); S.H = H; S.heads = heads; S.kv_heads = kv_heads; S.inter = inter;
+    S.cos = cosr; S.sin = sinr; S.final_norm = final_norm;
+    if (fk_alloc(h, &S.x, (size_t)2 * H) || fk_alloc(h, &S.xmid, (size_t)2 * H) || fk_alloc(h, &S.qkv, (size_t)2 * qkv_dim) ||
+        fk_alloc(h, &S.po, (size_t)2 * kv_heads * H) || fk_alloc(h, &S.act, (size_t)2 * inter))
+        return 1;
+    *out = S;
+    return 0;
+}
+
+int fk_init(lqt_engine* h) {
+    const Spec& s = h->sp;
+    auto chk = [&](int K, int RG, const char* what) -> bool {
+        if (K % 256 != 0 || (size_t)RG * K * 2 > (size_t)FK_STAGE_BYTES) {
+            h->err = std::string("frame kernel: unsupported dimension for ") + what; return false;
+        }
+        return true;
+    };
+    if (!chk(s.hidden, 2, "hidden") || !chk(s.inter, 1, "inter") || !chk(s.cp_hidden, 2, "cp_hidden") || !chk(s.cp_inter, 1, "cp_inter"))
+        return 1;
+    if (s.kv_heads > FK_NGRP_MAX || s.cp_kv_heads > FK_NGRP_MAX || s.kv_heads != s.cp_kv_heads) { h->err = "frame kernel: kv head count"; return 1; }
+    if (s.cp_steps + 2 > FK_CP_POS) { h->err = "frame kernel: cp_steps"; return 1; }
+    if (h->num_sms < s.kv_heads) { h->err = "frame kernel: too few SMs"; return 1; }
+    if (s.layers > FK_MAX_TLAYERS || s.cp_layers > FK_MAX_CLAYERS) { h->err = "frame kernel: too many layers"; return 1; }
+    if (fk_build_stack(h, h->tl, s.hidden, s.heads, s.kv_heads, s.inter, h->t_cos, h->t_sin, h->t_norm, &h->fk_talker, &h->fk_tl)) return 1;
+    if (fk_build_stack(h, h->cl, s.cp_hidden, s.cp_heads, s.cp_kv_heads, s.cp_inter, h->c_cos, h->c_sin, h->c_norm, &h->fk_cp, &h->fk_cl)) return 1;
+    if (fk_alloc(h, &h->fk_pa, (size_t)s.kv_heads * FK_NS_MAX * 2 * ATT_PSTRIDE) || fk_alloc(h, &h->fk_cxin, (size_t)2 * s.cp_hidden) ||
+        fk_alloc(h, &h->fk_ctrl, 2))
+        return 1;
+    CK(cudaMallocHost((void**)&h->fk_ctrl_host, 2 * sizeof(unsigned)));
+    const int maxV = std::max(s.vocab, s.cp_vocab);
+    auto pad = [](int k) { return (k + 255) & ~255; };
+    int xs_floats = std::max(pad(std::max(s.hidden, s.inter)), 2 * pad(std::max(std::max(s.cp_hidden, s.cp_inter), 256)));
+    xs_floats = std::max(xs_floats, 2 * pad(s.hidden));
+    const FkSmemLayout L = fk_smem_layout(maxV, xs_floats, s.hidden);
+    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.xs_bytes = (unsigned)(((size_t)xs_floats * 4 + 127) & ~(size_t)127);
+    h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
+    h->fk_smem = L.total;
+    CK(cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
+    int coop = 0, nb = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frame_kernel, FK_THREADS, h->fk_smem));
+    if (!coop || nb < 1) { h->err = "frame kernel: cooperative launch with one CTA per SM is not possible on this device"; return 1; }
+    return 0;
+}
+
+// one cooperative launch. mode 0: prefill (if st->pos == 0) + frames < frame_end ; mode 1: one talker token from next_in
+int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int frame_end, bool trace) {
+    const Spec& s = h->sp;
+    FkParams p{};
+    p.talker = h->fk_talker; p.cp = h->fk_cp;
+    for (size_t l = 0; l < h->fk_tl.size(); ++l) p.t_layers[l] = h->fk_tl[l];
+    for (size_t l = 0; l < h->fk_cl.size(); ++l) p.c_layers[l] = h->fk_cl[l];
+    p.t_head = h->t_head; p.vocab = s.vocab;
+    p.c_heads = h->c_heads; p.cp_vocab = s.cp_vocab; p.cp_steps = s.cp_steps;
+    p.c_inproj_w = h->c_inproj_w; p.c_inproj_b = h->c_inproj_b; p.cxin = h->fk_cxin;
+    p.eps = s.rms_eps;
+    p.kv_pool = h->kv_pool; p.page_table = h->page_tables + (size_t)slot * h->max_pages; p.page_shift = KV_PAGE_SHIFT;
+    p.page_stride = (long long)s.layers * 2 * s.kv_heads * KV_PAGE * ATT_D; p.kv_f32 = h->kv_f32 ? 1 : 0;
+    p.pa = h->fk_pa; p.cp_kv = h->cp_kv;
+    p.logits = h->logits; p.clogits = h->clogits; p.last_hidden = h->last_hidden;
+    p.cp_in = h->cp_in; p.next_in = h->next_in;
+    p.codec_embed = h->codec_embed; p.cp_embed = h->cp_embed;
+    p.prompt = prompt; p.P = P;
+    p.trailing = h->trailing_dev; p.tts_pad = h->tts_pad_dev;
+    p.st = h->st; p.sp = h->sampling_dev;
+    p.codes_out = h->codes_dev; p.forced = h->forced_dev;
+    p.trace = trace ? h->trace_dev : nullptr; p.trace_stride = h->trace_stride;
+    p.ctrl = h->fk_ctrl; p.frame_end = frame_end; p.mode = mode;
+    p.dbg = h->fk_dbg; p.dbg_cap = h->fk_dbg_cap; p.dbg_cta = h->fk_dbg_cta;
+    CK(cudaMemsetAsync(h->fk_ctrl, 0, 2 * sizeof(unsigned), h->stream));
+    FkSmemOffsets so = h->fk_so;
+    void* args[] = {(void*)&p, (void*)&so};
+    CK(cudaLaunchCooperativeKernel((const void*)frame_kernel, dim3(h->num_sms), dim3(FK_THREADS), args, h->fk_smem, h->stream));
+    h->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(h->fk_ctrl_host, h->fk_ctrl, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+int fk_check_abort(lqt_engine* h) {       // after a stream synchronize
+    if (h->fk_ctrl_host[1] != 0) { h->err = "frame kernel aborted: a device-side wait timed out"; return 1; }
+    return 0;
 }
 
 // opt in to large dynamic shared memory once, outside any stream capture
@@ -826,7 +988,7 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         dalloc(h, &h->act, s.inter) || dalloc(h, &h->logits, s.vocab) || dalloc(h, &h->last_hidden, H) ||
         dalloc(h, &h->cx, Hc) || dalloc(h, &h->cxin, Hc) || dalloc(h, &h->cqkv, (s.cp_heads + 2 * s.cp_kv_heads) * D) ||
         dalloc(h, &h->cattn, s.cp_heads * D) || dalloc(h, &h->cact, s.cp_inter) || dalloc(h, &h->clogits, s.cp_vocab) ||
-        dalloc(h, &h->cp_in, H) || dalloc(h, &h->next_in, H) || dalloc(h, &h->spk_dev, H) ||
+        dalloc(h, &h->cp_in, (size_t)2 * H) || dalloc(h, &h->next_in, H) || dalloc(h, &h->spk_dev, H) ||
         dalloc(h, &h->partial, (size_t)s.kv_heads * ATT_NSPLIT * 2 * ATT_PSTRIDE) ||
         dalloc(h, &h->cpartial, (size_t)s.cp_kv_heads * 2 * ATT_PSTRIDE) ||
         dalloc(h, &h->counters, s.kv_heads) || dalloc(h, &h->ccounters, s.cp_kv_heads))
@@ -860,6 +1022,7 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         return 1;
     CK(cudaMallocHost((void**)&h->st_host, sizeof(GenState)));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev_t0));
+    if (h->frame_impl == 0 && fk_init(h)) return 1;
     return 0;
 }
 
@@ -897,6 +1060,8 @@ int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, 
         if (opt->kv_dtype != LQT_KV_BF16 && opt->kv_dtype != LQT_KV_F32) { g_create_error = "bad kv_dtype"; delete h; return 1; }
         h->kv_f32 = opt->kv_dtype == LQT_KV_F32;
         if (opt->n_slots > 0) h->n_slots = opt->n_slots;
+        if (opt->frame_impl != LQT_FRAME_PERSISTENT && opt->frame_impl != LQT_FRAME_GRAPH) { g_create_error = "bad frame_impl"; delete h; return 1; }
+        h->frame_impl = opt->frame_impl;
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaStreamCreate failed"; delete h; return 1;
@@ -922,6 +1087,8 @@ void lqt_destroy(lqt_engine* h) {
                     h->forced_dev, h->trailing_dev, h->tts_pad_dev, h->prompt_dev, h->token_dev, h->spk_dev,
                     h->voc_codes_dev, h->audio_dev};
     for (void* b : bufs) if (b) cudaFree(b);
+    for (void* b : h->fk_allocs) if (b) cudaFree(b);
+    if (h->fk_ctrl_host) cudaFreeHost(h->fk_ctrl_host);
     if (h->st_host) cudaFreeHost(h->st_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1008,15 +1175,20 @@ int lqt_talker_prefill(lqt_engine* h, int32_t slot, const float* embeds, int32_t
     CK(cudaMemcpyAsync(e, embeds, (size_t)P * H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     GenState g{}; *h->st_host = g;
     CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
-    for (int i = 0; i < P; ++i) {
-        run_talker_token(h, slot, e + (size_t)i * H, i == P - 1, nullptr);
-        advance_kernel<<<1, 1, 0, h->stream>>>(h->st);
-        h->stats.kernel_launches++;
+    if (h->frame_impl == 0) {
+        if (fk_launch(h, slot, 0, e, P, 0, false)) return 1;        // prefill only (frame_end = 0)
+    } else {
+        for (int i = 0; i < P; ++i) {
+            run_talker_token(h, slot, e + (size_t)i * H, i == P - 1, nullptr);
+            advance_kernel<<<1, 1, 0, h->stream>>>(h->st);
+            h->stats.kernel_launches++;
+        }
     }
     CK(cudaGetLastError());
     if (logits_last) CK(cudaMemcpyAsync(logits_last, h->logits, h->sp.vocab * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (last_hidden) CK(cudaMemcpyAsync(last_hidden, h->last_hidden, H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->frame_impl == 0 && fk_check_abort(h)) return 1;
     h->slot_len[slot] = P;
     return 0;
 }
@@ -1029,11 +1201,13 @@ int lqt_talker_decode(lqt_engine* h, int32_t slot, const float* embed, float* lo
     GenState g{}; g.pos = h->slot_len[slot]; *h->st_host = g;
     CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->next_in, embed, H * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    run_talker_token(h, slot, h->next_in, true, nullptr);
+    if (h->frame_impl == 0) { if (fk_launch(h, slot, 1, nullptr, 0, 0, false)) return 1; }
+    else run_talker_token(h, slot, h->next_in, true, nullptr);
     CK(cudaGetLastError());
     if (logits) CK(cudaMemcpyAsync(logits, h->logits, h->sp.vocab * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (last_hidden) CK(cudaMemcpyAsync(last_hidden, h->last_hidden, H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->frame_impl == 0 && fk_check_abort(h)) return 1;
     h->slot_len[slot] += 1;
     return 0;
 }
@@ -1156,6 +1330,29 @@ int lqt_generate(lqt_engine* h, int32_t slot, const float* prompt, int32_t P, co
     CK(cudaStreamSynchronize(h->stream));
     *n_frames = nf;
     return 0;
+}
+
+int lqt_debug_timeline(lqt_engine* h, int32_t enable_entries, int32_t cta, uint64_t* out, int32_t out_cap) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    if (enable_entries > 0) {                      // arm: the next frame-kernel launches record CTA `cta`
+        if (h->fk_dbg_cap < enable_entries + 1) {
+            unsigned long long* d = nullptr;
+            if (cudaMalloc((void**)&d, (size_t)(enable_entries + 1) * 8) != cudaSuccess) { h->err = "timeline cudaMalloc failed"; return -1; }
+            h->fk_allocs.push_back(d);
+            h->fk_dbg = d; h->fk_dbg_cap = enable_entries + 1;
+        }
+        cudaMemsetAsync(h->fk_dbg, 0, (size_t)h->fk_dbg_cap * 8, h->stream);
+        h->fk_dbg_cta = cta;
+        return 0;
+    }
+    if (!h->fk_dbg || !out) return 0;
+    unsigned long long n = 0;
+    cudaMemcpyAsync(&n, h->fk_dbg, 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    const int m = (int)std::min<unsigned long long>(n, (unsigned long long)std::max(out_cap, 0));
+    if (m > 0) cudaMemcpy(out, h->fk_dbg + 1, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    return m;
 }
 
 int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,

@@ -31,6 +31,7 @@ constexpr int FK_THREADS = FK_CTHREADS + 32;      // + one producer warp
 constexpr int FK_STAGE_BYTES = 16 * 1024;
 constexpr int FK_STAGES = 9;                      // 144 KB weight ring per SM
 constexpr int FK_NS_MAX = 24;                     // max CTAs per kv group (attention splits)
+constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_MAXV = 4096;
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
 constexpr unsigned long long FK_SPIN_LIMIT = 6000000000ull;   // ~3 s of SM clocks: abort, never hang
@@ -43,8 +44,9 @@ struct FkLayer {
     const float *ln1, *ln2, *qnorm, *knorm;
 };
 
+constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
+
 struct FkStack {
-    const FkLayer* layers;
     int n_layers, H, heads, kv_heads, inter;
     const float *cos, *sin, *final_norm;
     float *x, *xmid, *qkv, *po, *act;     // [2][H] [2][H] [2][qkv_dim] [2][n_kv][H] [2][inter]
@@ -52,6 +54,8 @@ struct FkStack {
 
 struct FkParams {
     FkStack talker, cp;
+    FkLayer t_layers[FK_MAX_TLAYERS];     // in the kernel-parameter constant bank: no load latency
+    FkLayer c_layers[FK_MAX_CLAYERS];
     const bf16_t* t_head; int vocab;
     const bf16_t* c_heads; int cp_vocab, cp_steps;
     const bf16_t* c_inproj_w; const float* c_inproj_b; float* cxin;     // 1.7B: talker width -> predictor width
@@ -69,6 +73,8 @@ struct FkParams {
     unsigned* ctrl;            // [0] grid-barrier counter, [1] abort flag (both zero at launch)
     int frame_end;             // run frames while frame < frame_end (<= max_frames)
     int mode;                  // 0 = prefill (if pos == 0) + frames; 1 = one talker token from next_in (head on), no frames
+    unsigned long long* dbg;   // nullable: phase timeline of CTA dbg_cta, entries (clock64 << 8 | tag), [0] = count
+    int dbg_cap, dbg_cta;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -99,6 +105,12 @@ LQT_DEVINL void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+LQT_DEVINL unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+LQT_DEVINL void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 LQT_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -149,7 +161,19 @@ struct FkCtx {
     unsigned gen;             // grid-barrier generation (arrivals so far)
     unsigned stage_ctr;       // ring stages consumed so far
     bool aborted;
+    unsigned long long* dbg; int dbg_n, dbg_cap, dbg_tag;   // dbg_tag = (stack << 9) | (kind << 4) of the current phase
 };
+
+// timeline entries: (SM clock << 16) | (stack << 9) | (phase kind << 4) | point. Points:
+//  0 phase begin   1 descriptor ready (before the grid wait)   2 grid wait done   3 attention / rows staged
+//  4 RMSNorm done  5 first weight stage landed (inside the GEMV)   6 this warp's GEMV rows done
+//  7 all warps done (CTA barrier inside the arrive)   8 release-add issued
+enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_SAMPLE = 7, FKT_INPROJ = 8, FKT_GLUE = 9 };
+LQT_DEVINL void fk_mark(FkCtx& c, int point) {
+    if (c.dbg && c.tid == 0 && c.dbg_n < c.dbg_cap)
+        c.dbg[c.dbg_n++] = ((unsigned long long)clock64() << 16) | (unsigned)(c.dbg_tag | point);
+}
+LQT_DEVINL void fk_phase(FkCtx& c, int stack, int kind) { c.dbg_tag = (stack << 9) | (kind << 4); }
 
 // ------------------------------------------------------------------------------------------------
 // weight slices: which rows of a matrix this CTA owns (identical arithmetic in producer and consumers)
@@ -159,14 +183,14 @@ struct FkSlice { int row0, nrows; };
 // N rows in groups of RG consecutive rows, dealt contiguously over all CTAs
 LQT_DEVINL FkSlice flat_slice(int N, int RG, int cta, int ncta) {
     const int ng = N / RG;
-    const int g0 = (int)(((long long)cta * ng) / ncta), g1 = (int)(((long long)(cta + 1) * ng) / ncta);
+    const int g0 = (int)(((unsigned)cta * (unsigned)ng) / (unsigned)ncta), g1 = (int)(((unsigned)(cta + 1) * (unsigned)ng) / (unsigned)ncta);
     return FkSlice{g0 * RG, (g1 - g0) * RG};
 }
 // kv-group decomposition: CTA c serves group c % n_kv as member c / n_kv of ns_g members
 LQT_DEVINL int grp_members(int g, int n_kv, int ncta) { return (ncta - g + n_kv - 1) / n_kv; }
 LQT_DEVINL FkSlice group_slice(int Nout, int cta, int ncta, int n_kv) {
     const int g = cta % n_kv, s = cta / n_kv, ns = grp_members(g, n_kv, ncta);
-    const int r0 = (int)(((long long)s * Nout) / ns), r1 = (int)(((long long)(s + 1) * Nout) / ns);
+    const int r0 = (int)(((unsigned)s * (unsigned)Nout) / (unsigned)ns), r1 = (int)(((unsigned)(s + 1) * (unsigned)Nout) / (unsigned)ns);
     return FkSlice{r0, r1 - r0};
 }
 LQT_DEVINL int rows_per_stage(int K, int RG) {
@@ -178,49 +202,24 @@ LQT_DEVINL int rows_per_stage(int K, int RG) {
 // ------------------------------------------------------------------------------------------------
 // producer: stream this CTA's slices in program order
 // ------------------------------------------------------------------------------------------------
-struct FkProducer {
-    FkShared* sh; unsigned char* ring;
-    unsigned issued;
-    bool stopped;
+// flat schedule of one token pass: [in_proj] + n_layers x (A qkv, B attention, C o-proj, D gate/up, E down) + [head]
+struct FkOp { int kind, layer; };
+LQT_DEVINL int pass_ops(int n_layers, bool inproj, bool head) { return (inproj ? 1 : 0) + n_layers * 5 + (head ? 1 : 0); }
+LQT_DEVINL FkOp pass_op(int it, int n_layers, bool inproj) {
+    const int n_pre = inproj ? 1 : 0;
+    if (it < n_pre) return FkOp{8 /*FKT_INPROJ*/, 0};
+    const int r = it - n_pre;
+    if (r < n_layers * 5) return FkOp{1 + r % 5, r / 5};
+    return FkOp{6 /*FKT_HEAD*/, 0};
+}
 
-    LQT_DEVINL void push(const bf16_t* W, int row0, int nrows, int K, int RG) {
-        if (stopped || nrows <= 0) return;
-        const int rps = rows_per_stage(K, RG);
-        const char* src = reinterpret_cast<const char*>(W + (size_t)row0 * K);
-        for (int r = 0; r < nrows; r += rps) {
-            const int n = min(rps, nrows - r);
-            const unsigned slot = issued % FK_STAGES, par = ((issued / FK_STAGES) & 1u) ^ 1u;
-            unsigned long long t0 = 0;
-            while (!mbar_try_wait(&sh->empty[slot], par)) {
-                if (sh->stop) { stopped = true; return; }
-                if (t0 == 0) t0 = clock64();
-                else if (clock64() - t0 > FK_SPIN_LIMIT) { stopped = true; return; }
-            }
-            const uint32_t bytes = (uint32_t)n * K * 2;
-            mbar_expect_tx(&sh->full[slot], bytes);
-            bulk_g2s(ring + (size_t)slot * FK_STAGE_BYTES, src + (size_t)r * K * 2, bytes, &sh->full[slot]);
-            ++issued;
-        }
-    }
-};
-
-LQT_DEVINL void produce_token(FkProducer& pr, const FkParams& p, bool is_cp, const bf16_t* head_w, int head_n,
-                              int cta, int ncta) {
-    const FkStack& S = is_cp ? p.cp : p.talker;
-    const int H = S.H, qd = S.heads * ATT_D, kvd = S.kv_heads * ATT_D, rep = S.heads / S.kv_heads;
-    if (is_cp && p.c_inproj_w) {
-        const FkSlice s = flat_slice(H, 1, cta, ncta);
-        pr.push(p.c_inproj_w, s.row0, s.nrows, p.talker.H, 1);
-    }
-    for (int l = 0; l < S.n_layers; ++l) {
-        const FkLayer L = S.layers[l];
-        { const FkSlice s = flat_slice(qd + 2 * kvd, 1, cta, ncta); pr.push(L.wqkv, s.row0, s.nrows, H, 1); }
-        { const FkSlice s = group_slice(H, cta, ncta, S.kv_heads);
-          pr.push(L.wo_g + (size_t)(cta % S.kv_heads) * H * (rep * ATT_D), s.row0, s.nrows, rep * ATT_D, 1); }
-        { const FkSlice s = flat_slice(2 * S.inter, 2, cta, ncta); pr.push(L.wgu, s.row0, s.nrows, H, 2); }
-        { const FkSlice s = flat_slice(H, 1, cta, ncta); pr.push(L.wdown, s.row0, s.nrows, S.inter, 1); }
-    }
-    if (head_w) { const FkSlice s = flat_slice(head_n, 1, cta, ncta); pr.push(head_w, s.row0, s.nrows, H, 1); }
+// which pass comes q-th in this launch (identical in producer and consumers as long as no EOS)
+struct FkPassId { bool is_cp; int cb; bool head; };    // cb: predictor pass index (0..cp_steps-1)
+LQT_DEVINL FkPassId launch_pass(long long q, int mode, int n_prefill, int cp_steps) {
+    if (mode == 1) return FkPassId{false, 0, true};
+    if (q < n_prefill) return FkPassId{false, 0, q == n_prefill - 1};
+    const int r = (int)((q - n_prefill) % (cp_steps + 1));
+    return (r < cp_steps) ? FkPassId{true, r, true} : FkPassId{false, 0, true};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,21 +227,24 @@ LQT_DEVINL void produce_token(FkProducer& pr, const FkParams& p, bool is_cp, con
 // ------------------------------------------------------------------------------------------------
 LQT_DEVINL void gbar_arrive(FkCtx& c) {
     csync();                                   // this CTA's global writes are ordered before the release
+    fk_mark(c, 7);
     ++c.gen;
     if (c.tid == 0) red_release_add(&c.p->ctrl[0], 1u);
+    fk_mark(c, 8);
 }
 LQT_DEVINL void gbar_wait(FkCtx& c) {
     if (c.tid == 0) {
         const unsigned target = c.gen * (unsigned)c.ncta;
         unsigned long long t0 = 0;
         int it = 0;
-        while (ld_acquire_u32(&c.p->ctrl[0]) < target) {
+        while (ld_relaxed_u32(&c.p->ctrl[0]) < target) {
             if ((++it & 255) == 0) {
-                if (ld_acquire_u32(&c.p->ctrl[1]) != 0) { c.sh->aborted = 1; break; }
+                if (ld_relaxed_u32(&c.p->ctrl[1]) != 0) { c.sh->aborted = 1; break; }
                 if (t0 == 0) t0 = clock64();
                 else if (clock64() - t0 > FK_SPIN_LIMIT) { atomicExch(&c.p->ctrl[1], 1u); c.sh->aborted = 1; break; }
             }
         }
+        fence_acq_rel_gpu();
     }
     csync();
     if (c.sh->aborted) c.aborted = true;
@@ -361,6 +363,7 @@ LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
     for (int st = 0; st < nst; ++st) {
         const unsigned ast = c.stage_ctr + st;
         wait_full(c, ast);
+        if (st == 0) fk_mark(c, 5);
         const unsigned char* base = c.ring + (size_t)(ast % FK_STAGES) * FK_STAGE_BYTES;
         const int rs = min(rps, nrows - st * rps);          // rows in this stage
         for (int g = c.warp; g * RG < rs; g += FK_CWARPS) {
@@ -372,13 +375,17 @@ LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
 #pragma unroll
             for (int r = 0; r < RG; ++r) {
                 const unsigned char* rowp = base + (size_t)(g * RG + r) * (K * 2) + c.lane * 16;
-                uint4 w[KC];
+                constexpr int JB = KC < 4 ? KC : 4;          // weight loads in flight per lane
 #pragma unroll
-                for (int j = 0; j < KC; ++j) w[j] = lds128(rowp + j * 512);
+                for (int j0 = 0; j0 < KC; j0 += JB) {
+                    uint4 w[JB];
 #pragma unroll
-                for (int j = 0; j < KC; ++j)
+                    for (int j = 0; j < JB; ++j) w[j] = lds128(rowp + (j0 + j) * 512);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) acc[r][m] = dot8(w[j], xa[m][j], xb[m][j], acc[r][m]);
+                    for (int j = 0; j < JB; ++j)
+#pragma unroll
+                        for (int m = 0; m < M; ++m) acc[r][m] = dot8(w[j], xa[m][j0 + j], xb[m][j0 + j], acc[r][m]);
+                }
             }
 #pragma unroll
             for (int r = 0; r < RG; ++r)
@@ -442,28 +449,45 @@ LQT_DEVINL void gemv_smem(FkCtx& c, int K, int M, int row0, int nrows, const FkE
     c.stage_ctr += nst;
 }
 
-template <int RG>
-LQT_DEVINL void gemv_phase(FkCtx& c, int K, int M, int row0, int nrows, const FkEpi& e) {
+LQT_DEVINL void gemv_phase(FkCtx& c, int K, int M, int RG, int row0, int nrows, const FkEpi& e) {
     if (nrows <= 0) return;
     const int KC = K >> 8;
+    if (RG == 2) {                      // SwiGLU pairs: K = hidden
+        if (M == 1) {
+            switch (KC) {
+                case 1: gemv_reg<1, 1, 2>(c, row0, nrows, e); return;
+                case 4: gemv_reg<4, 1, 2>(c, row0, nrows, e); return;
+                case 8: gemv_reg<8, 1, 2>(c, row0, nrows, e); return;
+                default: break;
+            }
+        } else {
+            switch (KC) {
+                case 1: gemv_reg<1, 2, 2>(c, row0, nrows, e); return;
+                case 4: gemv_reg<4, 2, 2>(c, row0, nrows, e); return;
+                default: break;
+            }
+        }
+        gemv_smem<2>(c, K, M, row0, nrows, e);
+        return;
+    }
     if (M == 1) {
         switch (KC) {
-            case 1:  gemv_reg<1, 1, RG>(c, row0, nrows, e); return;
-            case 2:  gemv_reg<2, 1, RG>(c, row0, nrows, e); return;
-            case 4:  gemv_reg<4, 1, RG>(c, row0, nrows, e); return;
-            case 8:  gemv_reg<8, 1, RG>(c, row0, nrows, e); return;
-            case 12: gemv_reg<12, 1, RG>(c, row0, nrows, e); return;
+            case 1:  gemv_reg<1, 1, 1>(c, row0, nrows, e); return;
+            case 2:  gemv_reg<2, 1, 1>(c, row0, nrows, e); return;
+            case 4:  gemv_reg<4, 1, 1>(c, row0, nrows, e); return;
+            case 8:  gemv_reg<8, 1, 1>(c, row0, nrows, e); return;
+            case 12: gemv_reg<12, 1, 1>(c, row0, nrows, e); return;
             default: break;
         }
     } else {
         switch (KC) {
-            case 1: gemv_reg<1, 2, RG>(c, row0, nrows, e); return;
-            case 2: gemv_reg<2, 2, RG>(c, row0, nrows, e); return;
-            case 4: gemv_reg<4, 2, RG>(c, row0, nrows, e); return;
+            case 1: gemv_reg<1, 2, 1>(c, row0, nrows, e); return;
+            case 2: gemv_reg<2, 2, 1>(c, row0, nrows, e); return;
+            case 4: gemv_reg<4, 2, 1>(c, row0, nrows, e); return;
             default: break;
         }
     }
-    gemv_smem<RG>(c, K, M, row0, nrows, e);
+    gemv_smem<1>(c, K, M, row0, nrows, e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,10 +516,10 @@ template <typename KVT>
 LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t) {
     const FkParams& p = *c.p;
     const FkStack& S = p.talker;
-    const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv, ns = grp_members(g, n_kv, c.ncta);
+    const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
     const int n_pos = t + 1, chunk = (n_pos + ns - 1) / ns;
     const int j0 = s * chunk, j1 = min(n_pos, j0 + chunk);
-    if (j0 >= j1) return;                                      // idle split (short contexts)
+    if (s >= ns || j0 >= j1) return;                           // idle split (short contexts / spare CTAs)
     const int PS = 1 << p.page_shift;
     const int q_dim = S.heads * ATT_D, kv_dim = n_kv * ATT_D;
     const float* cosr = S.cos + (size_t)t * (ATT_D / 2);
@@ -591,7 +615,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
 // talker: combine the splits of group g -> xs[0][0..rep*128)  (input of the grouped O-projection)
 LQT_DEVINL void talker_attn_combine(FkCtx& c, int t) {
     const FkParams& p = *c.p;
-    const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = grp_members(g, n_kv, c.ncta);
+    const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
     const int n_pos = t + 1, chunk = (n_pos + ns - 1) / ns, active = (n_pos + chunk - 1) / chunk;
     const int r = c.tid >> 7, d = c.tid & 127;
     float Mx = -INFINITY;
@@ -681,87 +705,102 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// one token (M rows) through a stack.  x0: layer-0 input rows in global memory [M][x0_stride]
-// (also the layer-0 residual); x0_in_smem: the rows are already staged in xs (sampler glue).
+// one token pass (M rows) through a stack, as ONE loop over the flat op schedule so that every helper
+// is instantiated exactly once (the context stays in registers; no local memory on the hot path).
+// x0: layer-0 input rows in global memory [M][x0_stride] (also the layer-0 residual);
+// x0_in_smem: the rows are already staged in xs (sampler glue).
 // ------------------------------------------------------------------------------------------------
-LQT_DEVINL void consume_token(FkCtx& c, bool is_cp, int M, int pos0, const float* x0, int x0_stride, bool x0_in_smem,
-                              const bf16_t* head_w, int head_n, float* head_out, float* hidden_out) {
-    const FkParams& p = *c.p;
+struct FkPass {
+    bool is_cp; int M, pos0;
+    const float* x0; int x0_stride; bool x0_in_smem;
+    const bf16_t* head_w; int head_n; float* head_out; float* hidden_out;
+};
+
+LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
+    const bool is_cp = ps.is_cp;
     const FkStack& S = is_cp ? p.cp : p.talker;
+    const int tk = is_cp ? 1 : 0, M = ps.M;
     const int H = S.H, qd = S.heads * ATT_D, kvd = S.kv_heads * ATT_D, qkv_dim = qd + 2 * kvd;
     const int rep = S.heads / S.kv_heads, gK = rep * ATT_D, n_kv = S.kv_heads;
-    const float* lin = x0; int lin_stride = x0_stride;        // layer input rows (global)
-    bool in_smem = x0_in_smem;
-    if (is_cp && p.c_inproj_w) {                              // 1.7B: rows are talker-width; project to cp width
-        if (!in_smem) { stage_rows(c, x0, x0_stride, M, p.talker.H, nullptr, 0, nullptr); }
-        const FkSlice s = flat_slice(H, 1, c.cta, c.ncta);
-        const FkEpi e{EPI_STORE, p.cxin, H, p.c_inproj_b, 0, nullptr, 0};
-        gemv_phase<1>(c, p.talker.H, M, s.row0, s.nrows, e);
-        gbar_arrive(c);
-        lin = p.cxin; lin_stride = H; in_smem = false;
-        gbar_wait(c); if (c.aborted) return;
-    }
-    for (int l = 0; l < S.n_layers; ++l) {
-        const FkLayer L = S.layers[l];
-        // ---- A: RMSNorm + QKV ---------------------------------------------------------------------
-        if (!(l == 0 && in_smem)) {
-            if (l > 0) { gbar_wait(c); if (c.aborted) return; }
-            stage_rows(c, lin, lin_stride, M, H, nullptr, 0, nullptr);
+    const bool inproj = is_cp && p.c_inproj_w != nullptr;
+    const int total = pass_ops(S.n_layers, inproj, ps.head_w != nullptr);
+    const float* lin = ps.x0; int lin_stride = ps.x0_stride;   // layer input rows (global)
+    bool in_smem = ps.x0_in_smem;
+    for (int it = 0; it < total && !c.aborted; ++it) {
+        const FkOp op = pass_op(it, S.n_layers, inproj);
+        const int kind = op.kind, l = op.layer;
+        if (kind == FKT_B && is_cp) continue;                 // the predictor's attention lives inside phase C
+        fk_phase(c, tk, kind);
+        fk_mark(c, 0);
+        const FkLayer& L = is_cp ? p.c_layers[l] : p.t_layers[l];
+        // ---- what this phase stages and multiplies ---------------------------------------------
+        const float* src = nullptr; int sstride = 0, sK = 0, sM = M, npart = 0;
+        const float* part = nullptr; float* scopy = nullptr; bool do_stage = false;
+        const float* nw = nullptr; float* ncopy = nullptr;
+        int gK_ = 0, gM = M, rg = 1; FkSlice sl{0, 0};
+        FkEpi e{EPI_STORE, nullptr, 0, nullptr, 0, nullptr, 0};
+        bool need_wait = true;
+        switch (kind) {
+            case FKT_INPROJ:
+                need_wait = false;
+                do_stage = !in_smem; src = lin; sstride = lin_stride; sK = p.talker.H;
+                gK_ = p.talker.H; sl = flat_slice(H, 1, c.cta, c.ncta);
+                e = FkEpi{EPI_STORE, p.cxin, H, p.c_inproj_b, 0, nullptr, 0};
+                break;
+            case FKT_A:
+                need_wait = !(l == 0 && !inproj);
+                do_stage = !(l == 0 && in_smem); src = lin; sstride = lin_stride; sK = H;
+                nw = L.ln1;
+                gK_ = H; sl = flat_slice(qkv_dim, 1, c.cta, c.ncta);
+                e = FkEpi{EPI_STORE, S.qkv, qkv_dim, nullptr, 0, nullptr, 0};
+                break;
+            case FKT_B:
+                break;
+            case FKT_C:
+                gK_ = gK; sl = group_slice(H, c.cta, c.ncta, n_kv);
+                e = FkEpi{EPI_STORE, S.po + (size_t)(c.cta % n_kv) * H, n_kv * H, nullptr, 0, nullptr, 0};
+                break;
+            case FKT_D:
+                do_stage = true; src = lin; sstride = lin_stride; sK = H; part = S.po; npart = n_kv; scopy = S.xmid;
+                nw = L.ln2;
+                gK_ = H; rg = 2; sl = flat_slice(2 * S.inter, 2, c.cta, c.ncta);
+                e = FkEpi{EPI_GLU, S.act, S.inter, nullptr, 0, nullptr, 0};
+                break;
+            case FKT_E:
+                do_stage = true; src = S.act; sstride = S.inter; sK = S.inter;
+                gK_ = S.inter; sl = flat_slice(H, 1, c.cta, c.ncta);
+                e = FkEpi{EPI_RESID, S.x, H, nullptr, 0, S.xmid, H};
+                break;
+            default:   // FKT_HEAD: final norm of the LAST row + head
+                do_stage = true; src = S.x + (size_t)(M - 1) * H; sstride = H; sK = H; sM = 1;
+                nw = S.final_norm; ncopy = ps.hidden_out;
+                gK_ = H; gM = 1; sl = flat_slice(ps.head_n, 1, c.cta, c.ncta);
+                e = FkEpi{EPI_STORE, ps.head_out, ps.head_n, nullptr, 0, nullptr, 0};
+                break;
         }
-        norm_rows(c, L.ln1, M, H, p.eps, nullptr);
-        {
-            const FkSlice s = flat_slice(qkv_dim, 1, c.cta, c.ncta);
-            const FkEpi e{EPI_STORE, S.qkv, qkv_dim, nullptr, 0, nullptr, 0};
-            gemv_phase<1>(c, H, M, s.row0, s.nrows, e);
-        }
-        gbar_arrive(c);
-        // ---- B/C: attention + O-projection by kv group -> partial outputs po[m][g][:] -------------
-        gbar_wait(c); if (c.aborted) return;
-        if (is_cp) {
-            cp_attn_local(c, L, l, M, pos0);
-        } else {
-            if (p.kv_f32) talker_attn_partial<float>(c, L, l, pos0);
-            else          talker_attn_partial<bf16_t>(c, L, l, pos0);
+        fk_mark(c, 1);
+        if (need_wait) { gbar_wait(c); if (c.aborted) break; }
+        fk_mark(c, 2);
+        if (kind == FKT_B) {
+            if (p.kv_f32) talker_attn_partial<float>(c, L, l, ps.pos0);
+            else          talker_attn_partial<bf16_t>(c, L, l, ps.pos0);
+            fk_mark(c, 3);
             gbar_arrive(c);
-            gbar_wait(c); if (c.aborted) return;
-            talker_attn_combine(c, pos0);
+            continue;
         }
-        {
-            const int g = c.cta % n_kv;
-            const FkSlice s = group_slice(H, c.cta, c.ncta, n_kv);
-            const FkEpi e{EPI_STORE, S.po + (size_t)g * H, n_kv * H, nullptr, 0, nullptr, 0};
-            gemv_phase<1>(c, gK, M, s.row0, s.nrows, e);
+        if (kind == FKT_C) {
+            if (is_cp) cp_attn_local(c, L, l, M, ps.pos0);
+            else       talker_attn_combine(c, ps.pos0);
         }
+        if (do_stage) stage_rows(c, src, sstride, sM, sK, part, npart, scopy);
+        fk_mark(c, 3);
+        if (nw) norm_rows(c, nw, sM, sK, p.eps, ncopy);
+        fk_mark(c, 4);
+        gemv_phase(c, gK_, gM, rg, sl.row0, sl.nrows, e);
+        fk_mark(c, 6);
         gbar_arrive(c);
-        // ---- D: residual + RMSNorm + SwiGLU -------------------------------------------------------
-        gbar_wait(c); if (c.aborted) return;
-        stage_rows(c, lin, lin_stride, M, H, S.po, n_kv, S.xmid);
-        norm_rows(c, L.ln2, M, H, p.eps, nullptr);
-        {
-            const FkSlice s = flat_slice(2 * S.inter, 2, c.cta, c.ncta);
-            const FkEpi e{EPI_GLU, S.act, S.inter, nullptr, 0, nullptr, 0};
-            gemv_phase<2>(c, H, M, s.row0, s.nrows, e);
-        }
-        gbar_arrive(c);
-        // ---- E: down projection + residual -> x ----------------------------------------------------
-        gbar_wait(c); if (c.aborted) return;
-        stage_rows(c, S.act, S.inter, M, S.inter, nullptr, 0, nullptr);
-        {
-            const FkSlice s = flat_slice(H, 1, c.cta, c.ncta);
-            const FkEpi e{EPI_RESID, S.x, H, nullptr, 0, S.xmid, H};
-            gemv_phase<1>(c, S.inter, M, s.row0, s.nrows, e);
-        }
-        gbar_arrive(c);
-        lin = S.x; lin_stride = H; in_smem = false;
-    }
-    if (head_w) {       // final norm of the LAST row + head
-        gbar_wait(c); if (c.aborted) return;
-        stage_rows(c, S.x + (size_t)(M - 1) * H, H, 1, H, nullptr, 0, nullptr);
-        norm_rows(c, S.final_norm, 1, H, p.eps, hidden_out);
-        const FkSlice s = flat_slice(head_n, 1, c.cta, c.ncta);
-        const FkEpi e{EPI_STORE, head_out, head_n, nullptr, 0, nullptr, 0};
-        gemv_phase<1>(c, H, 1, s.row0, s.nrows, e);
-        gbar_arrive(c);
+        if (kind == FKT_E) { lin = S.x; lin_stride = H; in_smem = false; }
+        if (kind == FKT_INPROJ) { lin = p.cxin; lin_stride = H; in_smem = false; }
     }
 }
 
@@ -938,7 +977,7 @@ inline FkSmemLayout fk_smem_layout(int maxV, int max_xs_floats, int H) {
 struct FkSmemOffsets { unsigned scratch, xs_bytes, nxt, shared; int maxV; };
 
 __global__ void __launch_bounds__(FK_THREADS, 1)
-frame_kernel(const FkParams p, const FkSmemOffsets so) {
+frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     extern __shared__ __align__(1024) unsigned char fk_smem[];
     FkShared* sh = reinterpret_cast<FkShared*>(fk_smem + so.shared);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -956,18 +995,56 @@ frame_kernel(const FkParams p, const FkSmemOffsets so) {
 
     if (warp == FK_CWARPS) {
         // ============================ producer warp ============================================
+        // Walks the same flat schedule as the consumers, one stage at a time, as far ahead as the
+        // ring allows. All state in registers of one lane.
         if (lane == 0) {
-            FkProducer pr{sh, fk_smem, 0u, false};
-            if (p.mode == 1) {
-                produce_token(pr, p, false, p.t_head, p.vocab, cta, ncta);
-            } else {
-                for (int i = 0; i < n_prefill && !pr.stopped; ++i)
-                    produce_token(pr, p, false, (i == n_prefill - 1) ? p.t_head : nullptr, p.vocab, cta, ncta);
-                if (!st0.done) {
-                    for (int f = st0.frame; f < frame_end && !pr.stopped; ++f) {
-                        for (int j = 0; j < p.cp_steps && !pr.stopped; ++j)
-                            produce_token(pr, p, true, p.c_heads + (size_t)j * p.cp_vocab * p.cp.H, p.cp_vocab, cta, ncta);
-                        produce_token(pr, p, false, p.t_head, p.vocab, cta, ncta);
+            long long n_pass;
+            if (p.mode == 1) n_pass = 1;
+            else {
+                const int nf = (!st0.done && frame_end > st0.frame) ? (frame_end - st0.frame) : 0;
+                n_pass = (long long)n_prefill + (long long)nf * (p.cp_steps + 1);
+            }
+            unsigned issued = 0;
+            bool stopped = false;
+            for (long long q = 0; q < n_pass && !stopped; ++q) {
+                const FkPassId id = launch_pass(q, p.mode, n_prefill, p.cp_steps);
+                const FkStack& S = id.is_cp ? p.cp : p.talker;
+                const int H = S.H, qd = S.heads * ATT_D, kvd = S.kv_heads * ATT_D, rep = S.heads / S.kv_heads;
+                const bool inproj = id.is_cp && p.c_inproj_w != nullptr;
+                const int total = pass_ops(S.n_layers, inproj, id.head);
+                for (int it = 0; it < total && !stopped; ++it) {
+                    const FkOp op = pass_op(it, S.n_layers, inproj);
+                    if (op.kind == FKT_B) continue;
+                    const FkLayer& L = id.is_cp ? p.c_layers[op.layer] : p.t_layers[op.layer];
+                    const bf16_t* W; int K, RG = 1; FkSlice sl;
+                    switch (op.kind) {
+                        case FKT_INPROJ: W = p.c_inproj_w; K = p.talker.H; sl = flat_slice(H, 1, cta, ncta); break;
+                        case FKT_A: W = L.wqkv; K = H; sl = flat_slice(qd + 2 * kvd, 1, cta, ncta); break;
+                        case FKT_C: W = L.wo_g + (size_t)(cta % S.kv_heads) * H * (rep * ATT_D); K = rep * ATT_D;
+                                    sl = group_slice(H, cta, ncta, S.kv_heads); break;
+                        case FKT_D: W = L.wgu; K = H; RG = 2; sl = flat_slice(2 * S.inter, 2, cta, ncta); break;
+                        case FKT_E: W = L.wdown; K = S.inter; sl = flat_slice(H, 1, cta, ncta); break;
+                        default:
+                            if (id.is_cp) { W = p.c_heads + (size_t)id.cb * p.cp_vocab * H; sl = flat_slice(p.cp_vocab, 1, cta, ncta); }
+                            else          { W = p.t_head; sl = flat_slice(p.vocab, 1, cta, ncta); }
+                            K = H; break;
+                    }
+                    const int rps = rows_per_stage(K, RG);
+                    const char* srcb = reinterpret_cast<const char*>(W + (size_t)sl.row0 * K);
+                    for (int r = 0; r < sl.nrows && !stopped; r += rps) {
+                        const int n = min(rps, sl.nrows - r);
+                        const unsigned slot = issued % FK_STAGES, par = ((issued / FK_STAGES) & 1u) ^ 1u;
+                        unsigned long long t0 = 0;
+                        while (!mbar_try_wait(&sh->empty[slot], par)) {
+                            if (sh->stop) { stopped = true; break; }
+                            if (t0 == 0) t0 = clock64();
+                            else if (clock64() - t0 > FK_SPIN_LIMIT) { stopped = true; break; }
+                        }
+                        if (stopped) break;
+                        const uint32_t bytes = (uint32_t)n * K * 2;
+                        mbar_expect_tx(&sh->full[slot], bytes);
+                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)r * K * 2, bytes, &sh->full[slot]);
+                        ++issued;
                     }
                 }
             }
@@ -975,7 +1052,7 @@ frame_kernel(const FkParams p, const FkSmemOffsets so) {
             unsigned long long t0 = clock64();
             while (!sh->stop) { if (clock64() - t0 > 4 * FK_SPIN_LIMIT) break; __nanosleep(200); }
             __threadfence_block();
-            for (unsigned stg = (unsigned)sh->consumed; stg < pr.issued; ++stg) {
+            for (unsigned stg = (unsigned)sh->consumed; stg < issued; ++stg) {
                 const unsigned slot = stg % FK_STAGES, par = (stg / FK_STAGES) & 1u;
                 unsigned long long t1 = clock64();
                 while (!mbar_try_wait(&sh->full[slot], par)) { if (clock64() - t1 > FK_SPIN_LIMIT) break; }
@@ -992,110 +1069,103 @@ frame_kernel(const FkParams p, const FkSmemOffsets so) {
     c.nxt = reinterpret_cast<float*>(fk_smem + so.nxt);
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
     c.gen = 0; c.stage_ctr = 0; c.aborted = false;
+    c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
     FkSampScratch ss;
     ss.x = reinterpret_cast<float*>(fk_smem + so.scratch);
     ss.pr = ss.x + so.maxV; ss.spr = ss.pr + so.maxV;
     ss.idx = reinterpret_cast<unsigned short*>(ss.spr + so.maxV); ss.rank = ss.idx + so.maxV;
 
     const int H = p.talker.H;
+    const int Kpad4 = ((H + 255) & ~255) >> 2;
+    float4* xs4 = reinterpret_cast<float4*>(c.xs);
     int pos = st0.pos, frame = st0.frame, done = st0.done, n_frames = st0.n_frames;
+    const SamplingDev sp = *p.sp;
+    int prefill_i = 0;
+    int cb = 0;                      // next codebook to draw in the current frame (0 = talker code)
+    bool mode1_done = false;
 
-    if (p.mode == 1) {
-        consume_token(c, false, 1, pos, p.next_in, H, false, p.t_head, p.vocab, p.logits, p.last_hidden);
-        pos += 1;
-    } else {
-        // ---- prefill (src/tts_onnx.cpp:794): P talker tokens, head on the last ------------------
-        for (int i = 0; i < n_prefill && !c.aborted; ++i) {
-            if (i > 0) { gbar_wait(c); if (c.aborted) break; }
-            const bool last = (i == n_prefill - 1);
-            consume_token(c, false, 1, pos, p.prompt + (size_t)i * H, H, false, last ? p.t_head : nullptr, p.vocab,
-                          p.logits, p.last_hidden);
-            pos += 1;
-        }
-        // ---- frames (:801-846) -------------------------------------------------------------------
-        const SamplingDev sp = *p.sp;
-        while (!done && frame < frame_end && !c.aborted) {
-            // code0 from the talker logits (:803-812)
+    // One loop, one pass per iteration: [draw + glue ->] token pass. (src/tts_onnx.cpp:794, 801-846)
+    while (!c.aborted) {
+        FkPass ps;
+        if (p.mode == 1) {
+            if (mode1_done) break;
+            ps = FkPass{false, 1, pos, p.next_in, H, false, p.t_head, p.vocab, p.logits, p.last_hidden};
+        } else if (prefill_i < n_prefill) {
+            const bool last = (prefill_i == n_prefill - 1);
+            ps = FkPass{false, 1, pos, p.prompt + (size_t)prefill_i * H, H, false, last ? p.t_head : nullptr, p.vocab,
+                        p.logits, p.last_hidden};
+        } else {
+            if (done || frame >= frame_end) break;
+            // ---- draw codebook cb of this frame (:803-812 for cb 0, :863-864 otherwise) -----------------
+            const int tk = cb ? 1 : 0;
+            fk_phase(c, tk, FKT_SAMPLE);
+            fk_mark(c, 1);
             gbar_wait(c); if (c.aborted) break;
-            float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + 0) * p.trace_stride : nullptr;
-            int tok = fk_sample(c, ss, p.logits, p.vocab, 2048, p.vocab, 2150, sp, (uint32_t)frame, 0, tr);
-            if (p.forced && frame < st0.n_forced) tok = (int)p.forced[(size_t)frame * 16];
-            if (tok == 2150) { done = 1; break; }                                   // CODEC_EOS
-            if (cta == 0 && tid == 0) p.codes_out[(size_t)frame * 16] = tok;
-            // predictor rows: [last_hidden, codec_embed(code0)] (:854-860); next talker input starts (:824)
-            {
-                const int Kpad4 = ((H + 255) & ~255) >> 2;
-                float4* xs4 = reinterpret_cast<float4*>(c.xs);
-                const bf16_t* row = p.codec_embed + (size_t)tok * H;
-                for (int k4 = tid; k4 < Kpad4; k4 += FK_CTHREADS) {
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                    if (k4 < (H >> 2)) {
-                        a = __ldcg(reinterpret_cast<const float4*>(p.last_hidden) + k4);
-                        const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + k4);
-                        b = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
-                        reinterpret_cast<float4*>(c.nxt)[k4] = b;
-                        if (cta == 0) {
-                            reinterpret_cast<float4*>(p.cp_in)[k4] = a;
-                            reinterpret_cast<float4*>(p.cp_in + H)[k4] = b;
-                        }
-                    }
-                    xs4[xs_perm4(k4)] = a;
-                    xs4[Kpad4 + xs_perm4(k4)] = b;
-                }
-                csync();
-            }
-            for (int j = 0; j < p.cp_steps && !c.aborted; ++j) {
-                const int M = (j == 0) ? 2 : 1, p0 = (j == 0) ? 0 : j + 1;
-                consume_token(c, true, M, p0, p.cp_in, H, true, p.c_heads + (size_t)j * p.cp_vocab * p.cp.H, p.cp_vocab,
-                              p.clogits, nullptr);
-                if (c.aborted) break;
-                gbar_wait(c); if (c.aborted) break;
-                float* tr2 = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + j + 1) * p.trace_stride : nullptr;
-                int t2 = fk_sample(c, ss, p.clogits, p.cp_vocab, 0, 0, -1, sp, (uint32_t)frame, j + 1, tr2);
-                if (p.forced && frame < st0.n_forced) t2 = (int)p.forced[(size_t)frame * 16 + j + 1];
-                if (cta == 0 && tid == 0) p.codes_out[(size_t)frame * 16 + j + 1] = t2;
-                // embedding of the sub-code (:867-868) and the running 16-way sum (:825-830)
-                const bool last_cb = (j == p.cp_steps - 1);
-                const bool use_tr = frame < st0.trailing_len;
-                const bf16_t* row = p.cp_embed + ((size_t)j * p.cp_vocab + t2) * H;
-                const int Kpad4 = ((H + 255) & ~255) >> 2;
-                float4* xs4 = reinterpret_cast<float4*>(c.xs);
-                for (int k4 = tid; k4 < Kpad4; k4 += FK_CTHREADS) {
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f), acc = e;
-                    if (k4 < (H >> 2)) {
-                        const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + k4);
-                        e = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
-                        acc = reinterpret_cast<float4*>(c.nxt)[k4];
+            fk_mark(c, 2);
+            float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + cb) * p.trace_stride : nullptr;
+            int tok = (cb == 0) ? fk_sample(c, ss, p.logits, p.vocab, 2048, p.vocab, 2150, sp, (uint32_t)frame, 0, tr)
+                                : fk_sample(c, ss, p.clogits, p.cp_vocab, 0, 0, -1, sp, (uint32_t)frame, cb, tr);
+            if (p.forced && frame < st0.n_forced) tok = (int)p.forced[(size_t)frame * 16 + cb];
+            fk_mark(c, 3);
+            if (cb == 0 && tok == 2150) { done = 1; break; }                        // CODEC_EOS (:812)
+            if (cta == 0 && tid == 0) p.codes_out[(size_t)frame * 16 + cb] = tok;   // :818-821
+            // ---- glue: embedding of the drawn code, running 16-way sum, next input rows ------------------
+            const bool last_cb = (cb == p.cp_steps);
+            const bool use_tr = frame < st0.trailing_len;
+            const bf16_t* row = (cb == 0) ? p.codec_embed + (size_t)tok * H
+                                          : p.cp_embed + ((size_t)(cb - 1) * p.cp_vocab + tok) * H;
+            for (int k4 = tid; k4 < Kpad4; k4 += FK_CTHREADS) {
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f), acc = e, lh = e;
+                if (k4 < (H >> 2)) {
+                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + k4);
+                    e = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
+                    if (cb == 0) {
+                        acc = e;                                                    // :824
+                        lh = __ldcg(reinterpret_cast<const float4*>(p.last_hidden) + k4);   // :859
+                    } else {
+                        acc = reinterpret_cast<float4*>(c.nxt)[k4];                 // :825-830
                         acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
-                        if (last_cb) {                                              // :833-842
-                            const float4 tt = use_tr ? __ldg(reinterpret_cast<const float4*>(p.trailing + (size_t)frame * H) + k4)
-                                                     : __ldg(reinterpret_cast<const float4*>(p.tts_pad) + k4);
-                            acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
-                        }
-                        reinterpret_cast<float4*>(c.nxt)[k4] = acc;
-                        if (cta == 0) {
-                            if (last_cb) reinterpret_cast<float4*>(p.next_in)[k4] = acc;
-                            else reinterpret_cast<float4*>(p.cp_in)[k4] = e;
-                        }
                     }
-                    xs4[xs_perm4(k4)] = last_cb ? acc : e;
+                    if (last_cb) {                                                  // :833-842
+                        const float4 tt = use_tr ? __ldg(reinterpret_cast<const float4*>(p.trailing + (size_t)frame * H) + k4)
+                                                 : __ldg(reinterpret_cast<const float4*>(p.tts_pad) + k4);
+                        acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
+                    }
+                    reinterpret_cast<float4*>(c.nxt)[k4] = acc;
+                    if (cta == 0) {                                                 // layer-0 residual of the next pass
+                        if (last_cb) reinterpret_cast<float4*>(p.next_in)[k4] = acc;
+                        else if (cb == 0) { reinterpret_cast<float4*>(p.cp_in)[k4] = lh; reinterpret_cast<float4*>(p.cp_in + H)[k4] = e; }
+                        else reinterpret_cast<float4*>(p.cp_in)[k4] = e;
+                    }
                 }
-                csync();
+                if (cb == 0) { xs4[xs_perm4(k4)] = lh; xs4[Kpad4 + xs_perm4(k4)] = e; }
+                else xs4[xs_perm4(k4)] = last_cb ? acc : e;
             }
-            if (c.aborted) break;
-            n_frames = frame + 1;
-            // talker step on the summed embedding (:845)
-            consume_token(c, false, 1, pos, p.next_in, H, true, p.t_head, p.vocab, p.logits, p.last_hidden);
-            pos += 1; frame += 1;
+            csync();
+            fk_mark(c, 4);
+            if (last_cb) {
+                n_frames = frame + 1;
+                ps = FkPass{false, 1, pos, p.next_in, H, true, p.t_head, p.vocab, p.logits, p.last_hidden};   // :845
+            } else {
+                ps = FkPass{true, cb == 0 ? 2 : 1, cb == 0 ? 0 : cb + 1, p.cp_in, H, true,
+                            p.c_heads + (size_t)cb * p.cp_vocab * p.cp.H, p.cp_vocab, p.clogits, nullptr};
+            }
         }
-        if (!done && frame >= st0.max_frames) done = 1;
+        consume_token(c, p, ps);
+        if (c.aborted) break;
+        if (p.mode == 1) { pos += 1; mode1_done = true; }
+        else if (prefill_i < n_prefill) { pos += 1; ++prefill_i; }
+        else if (cb == p.cp_steps) { pos += 1; frame += 1; cb = 0; }
+        else ++cb;
     }
+    if (p.mode == 0 && !done && frame >= st0.max_frames) done = 1;
     // ---- exit: publish state, stop the producer -----------------------------------------------------
     csync();
     if (tid == 0) {
         if (cta == 0) {
             p.st->pos = pos; p.st->frame = frame; p.st->done = done; p.st->n_frames = n_frames;
         }
+        if (c.dbg) c.dbg[-1] = (unsigned long long)c.dbg_n;
         sh->consumed = (int)c.stage_ctr;
         __threadfence_block();
         sh->stop = 1;

@@ -19,7 +19,7 @@ SYMBOLS = [
     "lqt_reset_stats", "lqt_text_project", "lqt_codec_embed", "lqt_code_predictor_embed",
     "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
-    "lqt_build_prompt",
+    "lqt_build_prompt", "lqt_debug_timeline",
 ]
 
 
@@ -30,7 +30,7 @@ class Sampling(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("kv_dtype", C.c_int32), ("n_slots", C.c_int32)]
+    _fields_ = [("kv_dtype", C.c_int32), ("n_slots", C.c_int32), ("frame_impl", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -88,6 +88,7 @@ def load_library():
     lib.lqt_synthesize_tokens.argtypes = [P, P, I32, I32, P, C.POINTER(Sampling), P, I64,
                                           C.POINTER(I64), P, C.POINTER(I32)]
     lib.lqt_build_prompt.argtypes = [P, P, I32, I32, P, P, C.POINTER(I32), P, C.POINTER(I32), P]
+    lib.lqt_debug_timeline.argtypes = [P, I32, I32, P, I32]
     _lib = lib
     return lib
 
@@ -120,10 +121,11 @@ class EngineError(RuntimeError):
 class Engine:
     """One engine = one GPU = one host thread at a time (same contract as the reference)."""
 
-    def __init__(self, model_dir: str, device: int = 0, kv_dtype: str = "bf16", n_slots: int = 0):
+    def __init__(self, model_dir: str, device: int = 0, kv_dtype: str = "bf16", n_slots: int = 0,
+                 frame_impl: str = "persistent"):
         self.lib = load_library()
         h = C.c_void_p()
-        opt = Options({"bf16": 0, "f32": 1}[kv_dtype], n_slots)
+        opt = Options({"bf16": 0, "f32": 1}[kv_dtype], n_slots, {"persistent": 0, "graph": 1}[frame_impl])
         rc = self.lib.lqt_create_ex(model_dir.encode(), device, C.byref(opt), C.byref(h))
         if rc != 0 or not h:
             raise EngineError(self.lib.lqt_create_error().decode())
@@ -239,6 +241,18 @@ class Engine:
                                        C.byref(sp), _ptr(fc), 0 if fc is None else fc.shape[0],
                                        _ptr(codes), C.byref(n), _ptr(tb), stride))
         return (codes[: n.value].copy(), tb) if trace else codes[: n.value].copy()
+
+    def timeline_arm(self, entries: int = 200000, cta: int = 0):
+        if self.lib.lqt_debug_timeline(self.h, entries, cta, None, 0) != 0:
+            raise EngineError(self.lib.lqt_last_error(self.h).decode())
+        self._tl_cap = entries
+
+    def timeline_read(self):
+        """-> (clock uint64 [n], tag int [n]) of the last frame-kernel launch"""
+        out = np.zeros(self._tl_cap, np.uint64)
+        n = self.lib.lqt_debug_timeline(self.h, 0, 0, _ptr(out), self._tl_cap)
+        out = out[: max(n, 0)]
+        return (out >> np.uint64(16)), (out & np.uint64(0xFFFF)).astype(np.int64)
 
     def build_prompt(self, token_ids, lang: str = "auto", speaker_embed=None):
         ids = _i64(token_ids)
