@@ -127,7 +127,8 @@ struct lqt_engine {
     std::vector<void*> fk_allocs;             // regrouped weights, layer tables, activation buffers
     FkStack fk_talker{}, fk_cp{};
     std::vector<FkLayer> fk_tl, fk_cl;
-    float *fk_pa = nullptr, *fk_cxin = nullptr;
+    uint2* fk_arena = nullptr; size_t fk_arena_words = 0;     // all LL exchange buffers (zeroed at every launch)
+    uint2 *fk_pa = nullptr, *fk_cxin = nullptr, *fk_logits_ll = nullptr, *fk_clogits_ll = nullptr;
     unsigned* fk_ctrl = nullptr;
     unsigned* fk_ctrl_host = nullptr;         // pinned
     unsigned long long* fk_dbg = nullptr; int fk_dbg_cap = 0, fk_dbg_cta = 0;
@@ -820,9 +821,7 @@ int fk_build_stack(lqt_engine* h, const std::vector<LayerW>& layers, int H, int 
     FkStack S{};
     S.n_layers = (int)layers.size(); S.H = H; S.heads = heads; S.kv_heads = kv_heads; S.inter = inter;
     S.cos = cosr; S.sin = sinr; S.final_norm = final_norm;
-    if (fk_alloc(h, &S.x, (size_t)2 * H) || fk_alloc(h, &S.xmid, (size_t)2 * H) || fk_alloc(h, &S.qkv, (size_t)2 * qkv_dim) ||
-        fk_alloc(h, &S.po, (size_t)2 * kv_heads * H) || fk_alloc(h, &S.act, (size_t)2 * inter))
-        return 1;
+    (void)qkv_dim;
     *out = S;
     return 0;
 }
@@ -843,17 +842,35 @@ int fk_init(lqt_engine* h) {
     if (s.layers > FK_MAX_TLAYERS || s.cp_layers > FK_MAX_CLAYERS) { h->err = "frame kernel: too many layers"; return 1; }
     if (fk_build_stack(h, h->tl, s.hidden, s.heads, s.kv_heads, s.inter, h->t_cos, h->t_sin, h->t_norm, &h->fk_talker, &h->fk_tl)) return 1;
     if (fk_build_stack(h, h->cl, s.cp_hidden, s.cp_heads, s.cp_kv_heads, s.cp_inter, h->c_cos, h->c_sin, h->c_norm, &h->fk_cp, &h->fk_cl)) return 1;
-    if (fk_alloc(h, &h->fk_pa, (size_t)s.kv_heads * FK_NS_MAX * 2 * ATT_PSTRIDE) || fk_alloc(h, &h->fk_cxin, (size_t)2 * s.cp_hidden) ||
-        fk_alloc(h, &h->fk_ctrl, 2))
-        return 1;
+    {   // one arena for every LL exchange buffer
+        auto al = [](size_t n) { return (n + 31) & ~(size_t)31; };
+        const size_t qkv_t = (size_t)(s.heads + 2 * s.kv_heads) * ATT_D, qkv_c = (size_t)(s.cp_heads + 2 * s.cp_kv_heads) * ATT_D;
+        size_t off = 0;
+        auto take = [&](size_t n) { const size_t o = off; off += al(n); return o; };
+        const size_t o_tx = take(2 * (size_t)s.hidden), o_tq = take(2 * qkv_t), o_tp = take(2 * (size_t)s.kv_heads * s.hidden), o_ta = take(2 * (size_t)s.inter);
+        const size_t o_cx = take(2 * (size_t)s.cp_hidden), o_cq = take(2 * qkv_c), o_cp = take(2 * (size_t)s.cp_kv_heads * s.cp_hidden), o_ca = take(2 * (size_t)s.cp_inter);
+        const size_t o_pa = take((size_t)s.kv_heads * FK_NS_MAX * 2 * ATT_PSTRIDE), o_ci = take(2 * (size_t)s.cp_hidden);
+        const size_t o_lg = take((size_t)s.vocab), o_cl = take((size_t)s.cp_vocab);
+        if (fk_alloc(h, &h->fk_arena, off)) return 1;
+        h->fk_arena_words = off;
+        uint2* a = h->fk_arena;
+        h->fk_talker.x = a + o_tx; h->fk_talker.qkv = a + o_tq; h->fk_talker.po = a + o_tp; h->fk_talker.act = a + o_ta;
+        h->fk_cp.x = a + o_cx; h->fk_cp.qkv = a + o_cq; h->fk_cp.po = a + o_cp; h->fk_cp.act = a + o_ca;
+        h->fk_pa = a + o_pa; h->fk_cxin = a + o_ci; h->fk_logits_ll = a + o_lg; h->fk_clogits_ll = a + o_cl;
+    }
+    if (fk_alloc(h, &h->fk_ctrl, 2)) return 1;
     CK(cudaMallocHost((void**)&h->fk_ctrl_host, 2 * sizeof(unsigned)));
     const int maxV = std::max(s.vocab, s.cp_vocab);
     auto pad = [](int k) { return (k + 255) & ~255; };
     int xs_floats = std::max(pad(std::max(s.hidden, s.inter)), 2 * pad(std::max(std::max(s.cp_hidden, s.cp_inter), 256)));
     xs_floats = std::max(xs_floats, 2 * pad(s.hidden));
-    const FkSmemLayout L = fk_smem_layout(maxV, xs_floats, s.hidden);
-    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.xs_bytes = (unsigned)(((size_t)xs_floats * 4 + 127) & ~(size_t)127);
-    h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
+    if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV & 3)) { h->err = "frame kernel: hidden > 2048 or vocab % 4 != 0"; return 1; }
+    const int res0_floats = std::max(s.hidden, 2 * s.hidden * (s.hidden == s.cp_hidden ? 1 : 1));
+    const FkSmemLayout L = fk_smem_layout(maxV, xs_floats, s.hidden, 2 * s.hidden);
+    (void)res0_floats;
+    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.xs_bytes = (unsigned)L.xs_bytes;
+    h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.res0 = (unsigned)L.res0; h->fk_so.lh = (unsigned)L.lh;
+    h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
     h->fk_smem = L.total;
     CK(cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
     int coop = 0, nb = 0;
@@ -877,8 +894,9 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.kv_pool = h->kv_pool; p.page_table = h->page_tables + (size_t)slot * h->max_pages; p.page_shift = KV_PAGE_SHIFT;
     p.page_stride = (long long)s.layers * 2 * s.kv_heads * KV_PAGE * ATT_D; p.kv_f32 = h->kv_f32 ? 1 : 0;
     p.pa = h->fk_pa; p.cp_kv = h->cp_kv;
+    p.logits_ll = h->fk_logits_ll; p.clogits_ll = h->fk_clogits_ll;
     p.logits = h->logits; p.clogits = h->clogits; p.last_hidden = h->last_hidden;
-    p.cp_in = h->cp_in; p.next_in = h->next_in;
+    p.next_in = h->next_in;
     p.codec_embed = h->codec_embed; p.cp_embed = h->cp_embed;
     p.prompt = prompt; p.P = P;
     p.trailing = h->trailing_dev; p.tts_pad = h->tts_pad_dev;
@@ -888,6 +906,7 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.ctrl = h->fk_ctrl; p.frame_end = frame_end; p.mode = mode;
     p.dbg = h->fk_dbg; p.dbg_cap = h->fk_dbg_cap; p.dbg_cta = h->fk_dbg_cta;
     CK(cudaMemsetAsync(h->fk_ctrl, 0, 2 * sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->fk_arena, 0, h->fk_arena_words * sizeof(uint2), h->stream));   // sequence numbers restart at 1
     FkSmemOffsets so = h->fk_so;
     void* args[] = {(void*)&p, (void*)&so};
     CK(cudaLaunchCooperativeKernel((const void*)frame_kernel, dim3(h->num_sms), dim3(FK_THREADS), args, h->fk_smem, h->stream));

@@ -2,20 +2,26 @@
 // cooperative launch per utterance (or per chunk of frames).
 //
 // Why one kernel: a frame is 31 dependent network passes (1 talker step + 15 predictor passes, each
-// followed by a draw) = ~460 dependent matrix-vector phases of a few microseconds each. As separate
-// launches the HBM pipe drains at every kernel boundary. Here every SM keeps one CTA resident:
-//   * warp 8 (producer) walks the static weight schedule of the whole frame and streams this CTA's
+// followed by a draw) = ~460 dependent matrix-vector phases of ~1 us each. As separate launches the
+// HBM pipe drains at every kernel boundary (round-1 v1: 577 launches, 4.2 ms per frame).
+// Here every SM keeps one CTA resident:
+//   * warp 8 (producer) walks the static weight schedule of the whole launch and streams this CTA's
 //     slice of every matrix into a shared-memory ring with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx), running AHEAD of the math across phase boundaries, so
-//     HBM stays busy while the consumers sit in a grid barrier;
+//     (cp.async.bulk + mbarrier complete_tx), running AHEAD of the math across phase boundaries;
 //   * warps 0-7 (consumers) run the phases: assemble the input vector (RMSNorm / attention / partial
-//     sums), dot it with the rows in the ring (x in registers, weights read once from smem), write
-//     their few outputs, and meet the other CTAs at a release/acquire grid barrier;
+//     sums), dot it with the rows in the ring (x in registers, weights read once from smem) and
+//     publish their few outputs;
+//   * there is NO grid barrier. Activations travel between CTAs as 8-byte (value, sequence) pairs
+//     written with one store each ("LL" exchange, as in NCCL's low-latency protocol): a reader polls
+//     the data itself until every word carries the sequence number of the phase that produces it.
+//     One L2 write + one L2 read per hop instead of fence + atomic + poll + fence.
+//     Every CTA executes the same numbered phases, so the expected number is always "previous phase";
+//     a CTA can run at most one phase ahead of the slowest one, which makes one buffer per phase
+//     kind race-free;
 //   * the sampler and the embedding glue (src/tts_onnx.cpp:803-842, 854-868, 878-950) run redundantly
-//     in every CTA, so a draw costs no extra barrier and no broadcast.
+//     in every CTA, so a draw costs no broadcast.
 // Phases per layer: QKV | [talker: split-KV attention] | O-projection by kv-group (the code predictor
 // computes its <=17-position attention inside this phase) | gate/up (SwiGLU) | down.
-// All cross-CTA activations are read with ld.global.cg (L2), never through L1.
 #pragma once
 #include "attention.cuh"
 #include "common.cuh"
@@ -30,10 +36,11 @@ constexpr int FK_CTHREADS = FK_CWARPS * 32;       // consumer threads
 constexpr int FK_THREADS = FK_CTHREADS + 32;      // + one producer warp
 constexpr int FK_STAGE_BYTES = 16 * 1024;
 constexpr int FK_STAGES = 9;                      // 144 KB weight ring per SM
-constexpr int FK_NS_MAX = 24;                     // max CTAs per kv group (attention splits)
+constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_MAXV = 4096;
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
+constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
 constexpr unsigned long long FK_SPIN_LIMIT = 6000000000ull;   // ~3 s of SM clocks: abort, never hang
 
 struct FkLayer {
@@ -44,12 +51,10 @@ struct FkLayer {
     const float *ln1, *ln2, *qnorm, *knorm;
 };
 
-constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
-
 struct FkStack {
     int n_layers, H, heads, kv_heads, inter;
     const float *cos, *sin, *final_norm;
-    float *x, *xmid, *qkv, *po, *act;     // [2][H] [2][H] [2][qkv_dim] [2][n_kv][H] [2][inter]
+    uint2 *x, *qkv, *po, *act;            // LL buffers: [2][H] [2][qkv_dim] [2][n_kv][H] [2][inter]
 };
 
 struct FkParams {
@@ -58,22 +63,22 @@ struct FkParams {
     FkLayer c_layers[FK_MAX_CLAYERS];
     const bf16_t* t_head; int vocab;
     const bf16_t* c_heads; int cp_vocab, cp_steps;
-    const bf16_t* c_inproj_w; const float* c_inproj_b; float* cxin;     // 1.7B: talker width -> predictor width
+    const bf16_t* c_inproj_w; const float* c_inproj_b; uint2* cxin;     // 1.7B: talker width -> predictor width (LL [2][Hc])
     float eps;
     void* kv_pool; const int* page_table; int page_shift; long long page_stride; int kv_f32;
-    float* pa;                 // talker attention partials [n_kv][FK_NS_MAX][2][ATT_PSTRIDE]
+    uint2* pa;                 // talker attention partials, LL [n_kv][FK_NS_MAX][2][ATT_PSTRIDE]
     float* cp_kv;              // [layer][k|v][n_kv][FK_CP_POS][128] fp32
-    float *logits, *clogits, *last_hidden;
-    float *cp_in, *next_in;    // layer-0 inputs of the predictor pass [2][H] / talker step [H] (written by CTA 0)
+    uint2 *logits_ll, *clogits_ll;
+    float *logits, *clogits, *last_hidden, *next_in;   // plain copies: API outputs, resume across launches, mode-1 input
     const bf16_t *codec_embed, *cp_embed;
     const float* prompt; int P;           // prefill rows (run when st->pos == 0)
     const float *trailing, *tts_pad;
     GenState* st; const SamplingDev* sp;
     long long* codes_out; const long long* forced; float* trace; int trace_stride;
-    unsigned* ctrl;            // [0] grid-barrier counter, [1] abort flag (both zero at launch)
+    unsigned* ctrl;            // [1] abort flag (zero at launch)
     int frame_end;             // run frames while frame < frame_end (<= max_frames)
     int mode;                  // 0 = prefill (if pos == 0) + frames; 1 = one talker token from next_in (head on), no frames
-    unsigned long long* dbg;   // nullable: phase timeline of CTA dbg_cta, entries (clock64 << 8 | tag), [0] = count
+    unsigned long long* dbg;   // nullable: phase timeline of CTA dbg_cta, [0] = count
     int dbg_cap, dbg_cta;
 };
 
@@ -105,43 +110,44 @@ LQT_DEVINL void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-LQT_DEVINL unsigned ld_relaxed_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-LQT_DEVINL void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-LQT_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-LQT_DEVINL void red_release_add(unsigned* p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 LQT_DEVINL void csync() { asm volatile("bar.sync 1, %0;" ::"n"(FK_CTHREADS) : "memory"); }
 LQT_DEVINL uint4 lds128(const void* p) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
     return r;
 }
+// LL exchange: 8-byte (value, sequence) words. volatile accesses always go to L2 (the coherence point).
+LQT_DEVINL void st_ll(uint2* p, float v, unsigned seq) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+}
+LQT_DEVINL uint4 ld_ll2(const uint2* p) {          // two consecutive words (16-byte aligned)
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+LQT_DEVINL uint2 ld_ll1(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------
+struct FkDesc { int row0, nrows, K, RG; };     // this CTA's weight slice of one phase kind
 struct FkShared {
     uint64_t full[FK_STAGES];
     uint64_t empty[FK_STAGES];
     volatile int stop;            // consumers -> producer: stop issuing
     volatile int consumed;        // stages consumed when stop was raised
-    int aborted;
+    volatile int aborted;
     int hist[256];
     int wtot[FK_CWARPS];
     float redf[FK_CWARPS][2];
     int redi[FK_CWARPS];
     uint32_t sel_prefix; int sel_k;
     int tok; float fsum;
-    float rstd[2];
+    FkDesc desc[2][10];           // [stack][phase kind]
 };
 
 // x vectors live in smem as float4, permuted inside every 256-float chunk so that a lane's two
@@ -156,19 +162,20 @@ struct FkCtx {
     float* xs;                // x staging: [M][Kpad] (permuted)        | aliases the sampler scratch
     float* att;               // attention scratch                        |
     float* nxt;               // running next talker input [H]
+    float* res0;              // layer-0 input rows of the current pass [M][H0] (also its residual)
+    float* lh;                // talker last_hidden [H] (code-predictor row 0, src/tts_onnx.cpp:859)
     int tid, lane, warp;
     int cta, ncta;
-    unsigned gen;             // grid-barrier generation (arrivals so far)
+    unsigned seq;             // number of the current phase (1, 2, ...): tag of everything it publishes
     unsigned stage_ctr;       // ring stages consumed so far
     bool aborted;
     unsigned long long* dbg; int dbg_n, dbg_cap, dbg_tag;   // dbg_tag = (stack << 9) | (kind << 4) of the current phase
 };
 
 // timeline entries: (SM clock << 16) | (stack << 9) | (phase kind << 4) | point. Points:
-//  0 phase begin   1 descriptor ready (before the grid wait)   2 grid wait done   3 attention / rows staged
-//  4 RMSNorm done  5 first weight stage landed (inside the GEMV)   6 this warp's GEMV rows done
-//  7 all warps done (CTA barrier inside the arrive)   8 release-add issued
-enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_SAMPLE = 7, FKT_INPROJ = 8, FKT_GLUE = 9 };
+//  0 phase begin   3 inputs complete (polling, attention, RMSNorm done; before the GEMV)
+//  4 glue done (sampler phases)   5 first weight stage landed (inside the GEMV)   6 this warp's GEMV rows done
+enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_SAMPLE = 7, FKT_INPROJ = 8 };
 LQT_DEVINL void fk_mark(FkCtx& c, int point) {
     if (c.dbg && c.tid == 0 && c.dbg_n < c.dbg_cap)
         c.dbg[c.dbg_n++] = ((unsigned long long)clock64() << 16) | (unsigned)(c.dbg_tag | point);
@@ -198,21 +205,32 @@ LQT_DEVINL int rows_per_stage(int K, int RG) {
     r = (r / RG) * RG;
     return r < RG ? RG : r;       // host guarantees RG * K * 2 <= FK_STAGE_BYTES
 }
+LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, int ncta) {
+    const FkStack& S = is_cp ? p.cp : p.talker;
+    const int H = S.H, qkv_dim = (S.heads + 2 * S.kv_heads) * ATT_D, gK = (S.heads / S.kv_heads) * ATT_D;
+    FkSlice s{0, 0}; int K = 256, RG = 1;
+    switch (kind) {
+        case FKT_INPROJ: s = flat_slice(H, 1, cta, ncta); K = p.talker.H; break;
+        case FKT_A: s = flat_slice(qkv_dim, 1, cta, ncta); K = H; break;
+        case FKT_C: s = group_slice(H, cta, ncta, S.kv_heads); K = gK; break;
+        case FKT_D: s = flat_slice(2 * S.inter, 2, cta, ncta); K = H; RG = 2; break;
+        case FKT_E: s = flat_slice(H, 1, cta, ncta); K = S.inter; break;
+        case FKT_HEAD: s = flat_slice(is_cp ? p.cp_vocab : p.vocab, 1, cta, ncta); K = H; break;
+        default: break;
+    }
+    return FkDesc{s.row0, s.nrows, K, RG};
+}
 
-// ------------------------------------------------------------------------------------------------
-// producer: stream this CTA's slices in program order
-// ------------------------------------------------------------------------------------------------
 // flat schedule of one token pass: [in_proj] + n_layers x (A qkv, B attention, C o-proj, D gate/up, E down) + [head]
 struct FkOp { int kind, layer; };
 LQT_DEVINL int pass_ops(int n_layers, bool inproj, bool head) { return (inproj ? 1 : 0) + n_layers * 5 + (head ? 1 : 0); }
 LQT_DEVINL FkOp pass_op(int it, int n_layers, bool inproj) {
     const int n_pre = inproj ? 1 : 0;
-    if (it < n_pre) return FkOp{8 /*FKT_INPROJ*/, 0};
+    if (it < n_pre) return FkOp{FKT_INPROJ, 0};
     const int r = it - n_pre;
     if (r < n_layers * 5) return FkOp{1 + r % 5, r / 5};
-    return FkOp{6 /*FKT_HEAD*/, 0};
+    return FkOp{FKT_HEAD, 0};
 }
-
 // which pass comes q-th in this launch (identical in producer and consumers as long as no EOS)
 struct FkPassId { bool is_cp; int cb; bool head; };    // cb: predictor pass index (0..cp_steps-1)
 LQT_DEVINL FkPassId launch_pass(long long q, int mode, int n_prefill, int cp_steps) {
@@ -223,116 +241,162 @@ LQT_DEVINL FkPassId launch_pass(long long q, int mode, int n_prefill, int cp_ste
 }
 
 // ------------------------------------------------------------------------------------------------
-// grid barrier (all CTAs co-resident: cooperative launch)
+// LL polling
 // ------------------------------------------------------------------------------------------------
-LQT_DEVINL void gbar_arrive(FkCtx& c) {
-    csync();                                   // this CTA's global writes are ordered before the release
-    fk_mark(c, 7);
-    ++c.gen;
-    if (c.tid == 0) red_release_add(&c.p->ctrl[0], 1u);
-    fk_mark(c, 8);
+LQT_DEVINL bool ll_giveup(FkCtx& c, int& spins, unsigned long long& t0) {
+    if ((++spins & 1023) != 0) return false;
+    if (c.sh->aborted || *reinterpret_cast<volatile unsigned*>(&c.p->ctrl[1]) != 0) { c.sh->aborted = 1; return true; }
+    if (t0 == 0) { t0 = clock64(); return false; }
+    if (clock64() - t0 > FK_SPIN_LIMIT) { atomicExch(&c.p->ctrl[1], 1u); c.sh->aborted = 1; return true; }
+    return false;
 }
-LQT_DEVINL void gbar_wait(FkCtx& c) {
-    if (c.tid == 0) {
-        const unsigned target = c.gen * (unsigned)c.ncta;
-        unsigned long long t0 = 0;
-        int it = 0;
-        while (ld_relaxed_u32(&c.p->ctrl[0]) < target) {
-            if ((++it & 255) == 0) {
-                if (ld_relaxed_u32(&c.p->ctrl[1]) != 0) { c.sh->aborted = 1; break; }
-                if (t0 == 0) t0 = clock64();
-                else if (clock64() - t0 > FK_SPIN_LIMIT) { atomicExch(&c.p->ctrl[1], 1u); c.sh->aborted = 1; break; }
-            }
-        }
-        fence_acq_rel_gpu();
+// four consecutive words (32-byte aligned group), all tagged `seq`
+LQT_DEVINL float4 ll_poll4(FkCtx& c, const uint2* p, unsigned seq) {
+    uint4 a = ld_ll2(p), b = ld_ll2(p + 2);
+    int spins = 0; unsigned long long t0 = 0;
+    while (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
+        if (ll_giveup(c, spins, t0)) break;
+        a = ld_ll2(p); b = ld_ll2(p + 2);
     }
-    csync();
-    if (c.sh->aborted) c.aborted = true;
+    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
+LQT_DEVINL float ll_poll1(FkCtx& c, const uint2* p, unsigned seq) {
+    uint2 a = ld_ll1(p);
+    int spins = 0; unsigned long long t0 = 0;
+    while (a.y != seq) {
+        if (ll_giveup(c, spins, t0)) break;
+        a = ld_ll1(p);
+    }
+    return __uint_as_float(a.x);
+}
+// values already verified by this CTA in an earlier phase
+LQT_DEVINL float4 ll_val4(const uint2* p) {
+    const uint4 a = ld_ll2(p), b = ld_ll2(p + 2);
+    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+LQT_DEVINL float ll_val1(const uint2* p) { return __uint_as_float(ld_ll1(p).x); }
 
 // ------------------------------------------------------------------------------------------------
-// input staging
+// input staging: rows -> xs (permuted float4), optional partial sums, optional RMSNorm (fused:
+// values stay in registers until rstd is known, so xs is written exactly once)
 // ------------------------------------------------------------------------------------------------
-// xs[m][:] = src[m*stride + :] (+ sum of n_part partial vectors at part[(m*n_part + g)*K + :])
-LQT_DEVINL void stage_rows(FkCtx& c, const float* src, int stride, int M, int K, const float* part, int n_part,
-                           float* copy_out /* nullable: CTA 0 writes the assembled rows [M][K] */) {
-    const int K4 = K >> 2, Kpad4 = ((K + 255) & ~255) >> 2;
-    float4* xs4 = reinterpret_cast<float4*>(c.xs);
-    for (int m = 0; m < M; ++m) {
-        for (int k4 = c.tid; k4 < Kpad4; k4 += FK_CTHREADS) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k4 < K4) {
-                v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)m * stride) + k4);
-                for (int g = 0; g < n_part; ++g) {
-                    const float4 a = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)m * n_part + g) * K) + k4);
-                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                }
-                if (copy_out && c.cta == 0) reinterpret_cast<float4*>(copy_out + (size_t)m * K)[k4] = v;
-            }
-            xs4[m * Kpad4 + xs_perm4(k4)] = v;
-        }
-    }
-    csync();
-}
-
-// in-place RMSNorm of the staged rows: xs = (xs * rstd) * w ; optional copy of the result (CTA 0)
-LQT_DEVINL void norm_rows(FkCtx& c, const float* w, int M, int K, float eps, float* copy_out) {
-    const int K4 = K >> 2, Kpad4 = ((K + 255) & ~255) >> 2;
-    float4* xs4 = reinterpret_cast<float4*>(c.xs);
-    float ss[2] = {0.f, 0.f};
-    for (int k4 = c.tid; k4 < K4; k4 += FK_CTHREADS) {
-        const int d = xs_perm4(k4);
-        for (int m = 0; m < M; ++m) {
-            const float4 v = xs4[m * Kpad4 + d];
-            ss[m] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
-    }
-    for (int m = 0; m < M; ++m) {
-        const float s = warp_sum(ss[m]);
-        if (c.lane == 0) c.sh->redf[c.warp][m] = s;
-    }
-    csync();
-    if (c.tid < M) {
-        float s = 0.f;
-        for (int w2 = 0; w2 < FK_CWARPS; ++w2) s += c.sh->redf[w2][c.tid];
-        c.sh->rstd[c.tid] = 1.0f / sqrtf(s / (float)K + eps);
-    }
-    csync();
-    for (int k4 = c.tid; k4 < K4; k4 += FK_CTHREADS) {
-        const int d = xs_perm4(k4);
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + k4);
-        for (int m = 0; m < M; ++m) {
-            float4 v = xs4[m * Kpad4 + d];
-            const float r = c.sh->rstd[m];
-            v.x = (v.x * r) * wv.x; v.y = (v.y * r) * wv.y; v.z = (v.z * r) * wv.z; v.w = (v.w * r) * wv.w;
-            xs4[m * Kpad4 + d] = v;
-            if (copy_out && c.cta == 0) reinterpret_cast<float4*>(copy_out + (size_t)m * K)[k4] = v;
-        }
-    }
-    csync();
-}
-
-// ------------------------------------------------------------------------------------------------
-// GEMV over this CTA's slice, weights from the ring
-// ------------------------------------------------------------------------------------------------
-enum { EPI_STORE = 0, EPI_GLU = 1, EPI_RESID = 2 };
-struct FkEpi {
-    int kind;
-    float* out; int out_stride;          // out[m*out_stride + n]   (GLU: n/2)
-    const float* bias; int act;          // STORE only
-    const float* resid; int resid_stride;
+struct FkStage {
+    const uint2* ll;        // polled source rows [M][ll_stride] (nullptr: rows come from `sm`)
+    int ll_stride;
+    bool verified;          // source words were already verified by this CTA (no polling)
+    const float* sm;        // smem source rows [M][sm_stride] (plain layout)
+    int sm_stride;
+    const uint2* part;      // nullable: n_part polled partial vectors per row at part[(m*n_part + g)*K + k]
+    int n_part;
+    const float* nw;        // nullable RMSNorm weight [K]
+    float* copy_sm;         // nullable: normalised row 0 also to smem plain [K] (last_hidden)
+    float* copy_gl;         // nullable: and to global [K] by CTA 0
 };
 
-LQT_DEVINL void epi_store(const FkEpi& e, int m, int n, float v, float v2) {
-    if (e.kind == EPI_GLU) {
-        e.out[(size_t)m * e.out_stride + (n >> 1)] = silu_f(v) * v2;
-    } else if (e.kind == EPI_RESID) {
-        e.out[(size_t)m * e.out_stride + n] = __ldcg(e.resid + (size_t)m * e.resid_stride + n) + v;
-    } else {
-        if (e.bias) v += __ldg(e.bias + n);
-        if (e.act == 1) v = silu_f(v);
-        e.out[(size_t)m * e.out_stride + n] = v;
+LQT_DEVINL void stage_rows(FkCtx& c, const FkStage& s, int M, int K, unsigned want, float eps) {
+    const int K4 = K >> 2, Kpad4 = ((K + 255) & ~255) >> 2;
+    float4* xs4 = reinterpret_cast<float4*>(c.xs);
+    if (!s.nw) {
+        for (int m = 0; m < M; ++m) {
+            for (int k4 = c.tid; k4 < Kpad4; k4 += FK_CTHREADS) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k4 < K4) {
+                    if (s.ll) v = s.verified ? ll_val4(s.ll + (size_t)m * s.ll_stride + k4 * 4)
+                                             : ll_poll4(c, s.ll + (size_t)m * s.ll_stride + k4 * 4, want);
+                    else v = reinterpret_cast<const float4*>(s.sm + (size_t)m * s.sm_stride)[k4];
+                }
+                xs4[m * Kpad4 + xs_perm4(k4)] = v;
+            }
+        }
+        csync();
+        return;
     }
+    // norm path: K = hidden <= 2048 -> at most 2 float4 per thread per row
+    float4 v[2][2];
+    float4 wv[2];
+    float ss[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int k4 = c.tid + i * FK_CTHREADS;
+        wv[i] = (k4 < K4) ? __ldg(reinterpret_cast<const float4*>(s.nw) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int k4 = c.tid + i * FK_CTHREADS;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && k4 < K4) {
+                if (s.ll) a = s.verified ? ll_val4(s.ll + (size_t)m * s.ll_stride + k4 * 4)
+                                         : ll_poll4(c, s.ll + (size_t)m * s.ll_stride + k4 * 4, want);
+                else a = reinterpret_cast<const float4*>(s.sm + (size_t)m * s.sm_stride)[k4];
+                if (s.part) {
+#pragma unroll 8
+                    for (int g = 0; g < s.n_part; ++g) {
+                        const float4 b = ll_poll4(c, s.part + ((size_t)m * s.n_part + g) * K + k4 * 4, want);
+                        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                    }
+                }
+                ss[m] += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            }
+            v[m][i] = a;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const float t = warp_sum(ss[m]);
+        if (c.lane == 0) c.sh->redf[c.warp][m] = t;
+    }
+    csync();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (m < M) {
+            float t = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < FK_CWARPS; ++w2) t += c.sh->redf[w2][m];
+            const float r = 1.0f / sqrtf(t / (float)K + eps);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int k4 = c.tid + i * FK_CTHREADS;
+                if (k4 < Kpad4) {
+                    float4 a = v[m][i];
+                    a.x = (a.x * r) * wv[i].x; a.y = (a.y * r) * wv[i].y; a.z = (a.z * r) * wv[i].z; a.w = (a.w * r) * wv[i].w;
+                    xs4[m * Kpad4 + xs_perm4(k4)] = a;
+                    if (m == 0 && k4 < K4) {
+                        if (s.copy_sm) reinterpret_cast<float4*>(s.copy_sm)[k4] = a;
+                        if (s.copy_gl && c.cta == 0) reinterpret_cast<float4*>(s.copy_gl)[k4] = a;
+                    }
+                }
+            }
+        }
+    }
+    csync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMV over this CTA's slice, weights from the ring, outputs published as LL words
+// ------------------------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_GLU = 1, EPI_RESID = 2, EPI_LOGITS = 3 };
+struct FkEpi {
+    int kind;
+    uint2* out; int out_stride;          // out[m*out_stride + n]   (GLU: n/2)
+    const float* bias;                   // STORE only, nullable
+    float* plain;                        // LOGITS: second, plain copy [n]
+    // RESID: out = (x_in[n] + sum_g po[g][n]) + v, recomputed exactly as phase D staged it
+    const float* res_sm; int res_sm_stride;     // layer-0 residual rows in smem, or
+    const uint2* res_ll; int res_ll_stride;     // verified LL rows
+    const uint2* po; int n_part, H;
+};
+
+LQT_DEVINL float epi_resid(const FkEpi& e, int m, int n) {
+    float r = e.res_sm ? e.res_sm[(size_t)m * e.res_sm_stride + n] : ll_val1(e.res_ll + (size_t)m * e.res_ll_stride + n);
+    float pv[FK_NGRP_MAX];
+#pragma unroll
+    for (int g = 0; g < FK_NGRP_MAX; ++g)
+        pv[g] = (g < e.n_part) ? ll_val1(e.po + ((size_t)m * e.n_part + g) * e.H + n) : 0.f;
+#pragma unroll
+    for (int g = 0; g < FK_NGRP_MAX; ++g) if (g < e.n_part) r += pv[g];
+    return r;
 }
 
 LQT_DEVINL void wait_full(FkCtx& c, unsigned st) {
@@ -344,8 +408,18 @@ LQT_DEVINL void wait_full(FkCtx& c, unsigned st) {
     }
 }
 
-// x in registers: KC chunks of 256 elements, M rows. RG rows per group (GLU: gate, up).
-template <int KC, int M, int RG>
+// two interleaved accumulator chains per dot product
+LQT_DEVINL void dot8x2(const uint4& w, const float4& a, const float4& b, float& acc0, float& acc1) {
+    acc0 = fmaf(bf16lo(w.x), a.x, acc0); acc1 = fmaf(bf16hi(w.x), a.y, acc1);
+    acc0 = fmaf(bf16lo(w.y), a.z, acc0); acc1 = fmaf(bf16hi(w.y), a.w, acc1);
+    acc0 = fmaf(bf16lo(w.z), b.x, acc0); acc1 = fmaf(bf16hi(w.z), b.y, acc1);
+    acc0 = fmaf(bf16lo(w.w), b.z, acc0); acc1 = fmaf(bf16hi(w.w), b.w, acc1);
+}
+
+// x in registers (KC chunks of 256 elements, M rows). A stage's rows are dealt to warps in batches of
+// RB rows (RB % RG == 0) that one warp processes together (independent accumulator chains, batched
+// shuffles); batches of consecutive stages go to different warps so several stages are in work at once.
+template <int KC, int M, int RG, int RB>
 LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
     constexpr int K = KC * 256;
     const int Kpad4 = K >> 2;
@@ -360,45 +434,68 @@ LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
         }
     const int rps = rows_per_stage(K, RG);
     const int nst = (nrows + rps - 1) / rps;
+    const int nbs = (rps + RB - 1) / RB;                     // batches per (full) stage
     for (int st = 0; st < nst; ++st) {
         const unsigned ast = c.stage_ctr + st;
         wait_full(c, ast);
         if (st == 0) fk_mark(c, 5);
         const unsigned char* base = c.ring + (size_t)(ast % FK_STAGES) * FK_STAGE_BYTES;
         const int rs = min(rps, nrows - st * rps);          // rows in this stage
-        for (int g = c.warp; g * RG < rs; g += FK_CWARPS) {
-            float acc[RG][M];
-#pragma unroll
-            for (int r = 0; r < RG; ++r)
-#pragma unroll
-                for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
-#pragma unroll
-            for (int r = 0; r < RG; ++r) {
-                const unsigned char* rowp = base + (size_t)(g * RG + r) * (K * 2) + c.lane * 16;
-                constexpr int JB = KC < 4 ? KC : 4;          // weight loads in flight per lane
-#pragma unroll
-                for (int j0 = 0; j0 < KC; j0 += JB) {
-                    uint4 w[JB];
-#pragma unroll
-                    for (int j = 0; j < JB; ++j) w[j] = lds128(rowp + (j0 + j) * 512);
-#pragma unroll
-                    for (int j = 0; j < JB; ++j)
-#pragma unroll
-                        for (int m = 0; m < M; ++m) acc[r][m] = dot8(w[j], xa[m][j0 + j], xb[m][j0 + j], acc[r][m]);
-                }
+        for (int b = (c.warp + FK_CWARPS - ((st * nbs) & (FK_CWARPS - 1))) & (FK_CWARPS - 1); b * RB < rs; b += FK_CWARPS) {
+            const int rb0 = b * RB;                          // first row of the batch inside the stage
+            // residual values for the outputs this lane will publish (latency hidden behind the dots)
+            float resid = 0.f;
+            if (e.kind == EPI_RESID && c.lane < RB * M) {
+                const int r = c.lane / M, m = c.lane - r * M;
+                if (rb0 + r < rs) resid = epi_resid(e, m, row0 + st * rps + rb0 + r);
             }
+            float acc[RB][M][2];
 #pragma unroll
-            for (int r = 0; r < RG; ++r)
+            for (int r = 0; r < RB; ++r)
 #pragma unroll
-                for (int m = 0; m < M; ++m) acc[r][m] = warp_sum(acc[r][m]);
-            if (c.lane == 0) {
-                const int n = row0 + st * rps + g * RG;
+                for (int m = 0; m < M; ++m) { acc[r][m][0] = 0.f; acc[r][m][1] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < KC; ++j) {
+                uint4 w[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+                    w[r] = (rb0 + r < rs) ? lds128(base + (size_t)(rb0 + r) * (K * 2) + c.lane * 16 + j * 512)
+                                          : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+#pragma unroll
+                    for (int m = 0; m < M; ++m) dot8x2(w[r], xa[m][j], xb[m][j], acc[r][m][0], acc[r][m][1]);
+            }
+            float tot[RB][M];
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int m = 0; m < M; ++m) tot[r][m] = acc[r][m][0] + acc[r][m][1];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+#pragma unroll
+                    for (int m = 0; m < M; ++m) tot[r][m] += __shfl_xor_sync(0xffffffffu, tot[r][m], o);
+            // lane (g*RG*M + m) publishes output group g of the batch (RESID has RG == 1: lane r*M + m, as above)
+#pragma unroll
+            for (int g = 0; g < RB / RG; ++g)
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    if (RG == 2) epi_store(e, m, n, acc[0][m], acc[RG - 1][m]);
-                    else epi_store(e, m, n, acc[0][m], 0.f);
+                    if (c.lane == g * RG * M + m && rb0 + g * RG < rs) {
+                        const int n = row0 + st * rps + rb0 + g * RG;
+                        float v = tot[g * RG][m];
+                        if (RG == 2) {
+                            st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(v) * tot[g * RG + RG - 1][m], c.seq);
+                        } else if (e.kind == EPI_RESID) {
+                            st_ll(e.out + (size_t)m * e.out_stride + n, resid + v, c.seq);
+                        } else {
+                            if (e.bias) v += __ldg(e.bias + n);
+                            st_ll(e.out + (size_t)m * e.out_stride + n, v, c.seq);
+                            if (e.kind == EPI_LOGITS) e.plain[n] = v;
+                        }
+                    }
                 }
-            }
         }
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.sh->empty[ast % FK_STAGES]);
@@ -406,7 +503,7 @@ LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
     c.stage_ctr += nst;
 }
 
-// generic fallback: x read from smem inside the loop (any K % 256 == 0, M <= 2)
+// generic fallback: x read from smem inside the loop (any K % 256 == 0, M <= 2), one row group per warp turn
 template <int RG>
 LQT_DEVINL void gemv_smem(FkCtx& c, int K, int M, int row0, int nrows, const FkEpi& e) {
     const int KC = K >> 8, Kpad4 = K >> 2;
@@ -416,9 +513,13 @@ LQT_DEVINL void gemv_smem(FkCtx& c, int K, int M, int row0, int nrows, const FkE
     for (int st = 0; st < nst; ++st) {
         const unsigned ast = c.stage_ctr + st;
         wait_full(c, ast);
+        if (st == 0) fk_mark(c, 5);
         const unsigned char* base = c.ring + (size_t)(ast % FK_STAGES) * FK_STAGE_BYTES;
         const int rs = min(rps, nrows - st * rps);
-        for (int g = c.warp; g * RG < rs; g += FK_CWARPS) {
+        for (int g = (c.warp + FK_CWARPS - (st & (FK_CWARPS - 1))) & (FK_CWARPS - 1); g * RG < rs; g += FK_CWARPS) {
+            const int n = row0 + st * rps + g * RG;
+            float resid = 0.f;
+            if (e.kind == EPI_RESID && c.lane < M) resid = epi_resid(e, c.lane, n);
             float acc[RG][2];
 #pragma unroll
             for (int r = 0; r < RG; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
@@ -434,12 +535,20 @@ LQT_DEVINL void gemv_smem(FkCtx& c, int K, int M, int row0, int nrows, const FkE
                 }
             }
 #pragma unroll
-            for (int r = 0; r < RG; ++r) { acc[r][0] = warp_sum(acc[r][0]); if (M > 1) acc[r][1] = warp_sum(acc[r][1]); }
-            if (c.lane == 0) {
-                const int n = row0 + st * rps + g * RG;
-                for (int m = 0; m < M; ++m) {
-                    if (RG == 2) epi_store(e, m, n, acc[0][m], acc[RG - 1][m]);
-                    else epi_store(e, m, n, acc[0][m], 0.f);
+            for (int r = 0; r < RG; ++r) { acc[r][0] = warp_sum(acc[r][0]); acc[r][1] = warp_sum(acc[r][1]); }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (c.lane == m && m < M) {
+                    float v = acc[0][m];
+                    if (RG == 2) {
+                        st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(v) * acc[RG - 1][m], c.seq);
+                    } else if (e.kind == EPI_RESID) {
+                        st_ll(e.out + (size_t)m * e.out_stride + n, resid + v, c.seq);
+                    } else {
+                        if (e.bias) v += __ldg(e.bias + n);
+                        st_ll(e.out + (size_t)m * e.out_stride + n, v, c.seq);
+                        if (e.kind == EPI_LOGITS) e.plain[n] = v;
+                    }
                 }
             }
         }
@@ -455,15 +564,15 @@ LQT_DEVINL void gemv_phase(FkCtx& c, int K, int M, int RG, int row0, int nrows, 
     if (RG == 2) {                      // SwiGLU pairs: K = hidden
         if (M == 1) {
             switch (KC) {
-                case 1: gemv_reg<1, 1, 2>(c, row0, nrows, e); return;
-                case 4: gemv_reg<4, 1, 2>(c, row0, nrows, e); return;
-                case 8: gemv_reg<8, 1, 2>(c, row0, nrows, e); return;
+                case 1: gemv_reg<1, 1, 2, 4>(c, row0, nrows, e); return;
+                case 4: gemv_reg<4, 1, 2, 4>(c, row0, nrows, e); return;
+                case 8: gemv_reg<8, 1, 2, 2>(c, row0, nrows, e); return;
                 default: break;
             }
         } else {
             switch (KC) {
-                case 1: gemv_reg<1, 2, 2>(c, row0, nrows, e); return;
-                case 4: gemv_reg<4, 2, 2>(c, row0, nrows, e); return;
+                case 1: gemv_reg<1, 2, 2, 4>(c, row0, nrows, e); return;
+                case 4: gemv_reg<4, 2, 2, 2>(c, row0, nrows, e); return;
                 default: break;
             }
         }
@@ -472,18 +581,18 @@ LQT_DEVINL void gemv_phase(FkCtx& c, int K, int M, int RG, int row0, int nrows, 
     }
     if (M == 1) {
         switch (KC) {
-            case 1:  gemv_reg<1, 1, 1>(c, row0, nrows, e); return;
-            case 2:  gemv_reg<2, 1, 1>(c, row0, nrows, e); return;
-            case 4:  gemv_reg<4, 1, 1>(c, row0, nrows, e); return;
-            case 8:  gemv_reg<8, 1, 1>(c, row0, nrows, e); return;
-            case 12: gemv_reg<12, 1, 1>(c, row0, nrows, e); return;
+            case 1:  gemv_reg<1, 1, 1, 4>(c, row0, nrows, e); return;
+            case 2:  gemv_reg<2, 1, 1, 4>(c, row0, nrows, e); return;
+            case 4:  gemv_reg<4, 1, 1, 4>(c, row0, nrows, e); return;
+            case 8:  gemv_reg<8, 1, 1, 2>(c, row0, nrows, e); return;
+            case 12: gemv_reg<12, 1, 1, 2>(c, row0, nrows, e); return;
             default: break;
         }
     } else {
         switch (KC) {
-            case 1: gemv_reg<1, 2, 1>(c, row0, nrows, e); return;
-            case 2: gemv_reg<2, 2, 1>(c, row0, nrows, e); return;
-            case 4: gemv_reg<4, 2, 1>(c, row0, nrows, e); return;
+            case 1: gemv_reg<1, 2, 1, 4>(c, row0, nrows, e); return;
+            case 2: gemv_reg<2, 2, 1, 4>(c, row0, nrows, e); return;
+            case 4: gemv_reg<4, 2, 1, 2>(c, row0, nrows, e); return;
             default: break;
         }
     }
@@ -511,9 +620,9 @@ template <> LQT_DEVINL float4 kv_load4_cg<bf16_t>(const bf16_t* p) {
 }
 template <> LQT_DEVINL float4 kv_load4_cg<float>(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// talker: split-KV partial attention of kv group g over this CTA's chunk of positions
+// talker: split-KV partial attention of kv group g over this CTA's chunk of positions -> pa (LL)
 template <typename KVT>
-LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t) {
+LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.talker;
     const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
@@ -532,24 +641,25 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     float* vn = c.att + FA_VN;
     const bool owns_new = (j1 == n_pos);
     if (c.warp < 2) {
-        float4 v = __ldcg(reinterpret_cast<const float4*>(S.qkv + (size_t)(g * 2 + c.warp) * ATT_D) + c.lane);
+        float4 v = ll_poll4(c, S.qkv + (size_t)(g * 2 + c.warp) * ATT_D + c.lane * 4, want);
         v = head_norm_rope(v, L.qnorm, p.eps, cosr, sinr, c.lane);
         reinterpret_cast<float4*>(q_s + c.warp * ATT_D)[c.lane] = v;
     } else if (owns_new && c.warp < 4) {
         const long long base = (long long)p.page_table[t >> p.page_shift] * p.page_stride + layer_off + head_off +
                                (long long)(t & (PS - 1)) * ATT_D;
         if (c.warp == 2) {
-            float4 v = __ldcg(reinterpret_cast<const float4*>(S.qkv + q_dim + (size_t)g * ATT_D) + c.lane);
+            float4 v = ll_poll4(c, S.qkv + q_dim + (size_t)g * ATT_D + c.lane * 4, want);
             v = head_norm_rope(v, L.knorm, p.eps, cosr, sinr, c.lane);
             KvIO<KVT>::store4(pool + base + c.lane * 4, v);
             v.x = KvIO<KVT>::round(v.x); v.y = KvIO<KVT>::round(v.y); v.z = KvIO<KVT>::round(v.z); v.w = KvIO<KVT>::round(v.w);
             reinterpret_cast<float4*>(kn)[c.lane] = v;
         } else {
-            float4 v = __ldcg(reinterpret_cast<const float4*>(S.qkv + q_dim + kv_dim + (size_t)g * ATT_D) + c.lane);
+            float4 v = ll_poll4(c, S.qkv + q_dim + kv_dim + (size_t)g * ATT_D + c.lane * 4, want);
             KvIO<KVT>::store4(pool + base + v_off + c.lane * 4, v);
             v.x = KvIO<KVT>::round(v.x); v.y = KvIO<KVT>::round(v.y); v.z = KvIO<KVT>::round(v.z); v.w = KvIO<KVT>::round(v.w);
             reinterpret_cast<float4*>(vn)[c.lane] = v;
         }
+        __threadfence();        // the cache line must be visible before any later word of this CTA says "done"
     }
     csync();
     const float4 q0 = reinterpret_cast<const float4*>(q_s)[c.lane];
@@ -598,42 +708,63 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     {
         const int r = c.tid >> 7, d = c.tid & 127;              // 256 threads = 2 heads x 128 dims
         float Mx = -INFINITY;
+#pragma unroll
         for (int w2 = 0; w2 < FK_CWARPS; ++w2) Mx = fmaxf(Mx, wm[w2 * 2 + r]);
         float num = 0.f, den = 0.f;
+#pragma unroll
         for (int w2 = 0; w2 < FK_CWARPS; ++w2) {
             const float mw = wm[w2 * 2 + r];
             const float f = (mw == -INFINITY) ? 0.f : expf(mw - Mx);
             num = fmaf(f, wo[(w2 * 2 + r) * ATT_D + d], num);
             den = fmaf(f, wl[w2 * 2 + r], den);
         }
-        float* part = p.pa + ((size_t)(g * FK_NS_MAX + s) * 2 + r) * ATT_PSTRIDE;
-        part[d] = num;
-        if (d == 0) { part[ATT_D] = Mx; part[ATT_D + 1] = den; }
+        uint2* part = p.pa + ((size_t)(g * FK_NS_MAX + s) * 2 + r) * ATT_PSTRIDE;
+        st_ll(part + d, num, c.seq);
+        if (d == 0) { st_ll(part + ATT_D, Mx, c.seq); st_ll(part + ATT_D + 1, den, c.seq); }
     }
+    csync();                     // scratch is reused by the next phase
 }
 
 // talker: combine the splits of group g -> xs[0][0..rep*128)  (input of the grouped O-projection)
-LQT_DEVINL void talker_attn_combine(FkCtx& c, int t) {
+LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
     const FkParams& p = *c.p;
     const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
     const int n_pos = t + 1, chunk = (n_pos + ns - 1) / ns, active = (n_pos + chunk - 1) / chunk;
     const int r = c.tid >> 7, d = c.tid & 127;
-    float Mx = -INFINITY;
-    for (int s = 0; s < active; ++s)
-        Mx = fmaxf(Mx, __ldcg(p.pa + ((size_t)(g * FK_NS_MAX + s) * 2 + r) * ATT_PSTRIDE + ATT_D));
-    float num = 0.f, den = 0.f;
-    for (int s = 0; s < active; ++s) {
-        const float* ps = p.pa + ((size_t)(g * FK_NS_MAX + s) * 2 + r) * ATT_PSTRIDE;
-        const float f = expf(__ldcg(ps + ATT_D) - Mx);
-        num = fmaf(f, __ldcg(ps + d), num);
-        den = fmaf(f, __ldcg(ps + ATT_D + 1), den);
+    float Mx = -INFINITY, num = 0.f, den = 0.f;
+    for (int s0 = 0; s0 < active; s0 += 4) {
+        float ms[4], ls[4], os[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ms[u] = -INFINITY; ls[u] = 0.f; os[u] = 0.f;
+            if (s0 + u < active) {
+                const uint2* ps = p.pa + ((size_t)(g * FK_NS_MAX + s0 + u) * 2 + r) * ATT_PSTRIDE;
+                const uint4 ml = ld_ll2(ps + ATT_D);
+                const uint2 ov = ld_ll1(ps + d);
+                if (ml.y == want && ml.w == want && ov.y == want) {
+                    ms[u] = __uint_as_float(ml.x); ls[u] = __uint_as_float(ml.z); os[u] = __uint_as_float(ov.x);
+                } else {
+                    ms[u] = ll_poll1(c, ps + ATT_D, want); ls[u] = ll_poll1(c, ps + ATT_D + 1, want); os[u] = ll_poll1(c, ps + d, want);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (s0 + u < active) {
+                const float Mn = fmaxf(Mx, ms[u]);
+                const float f0 = expf(Mx - Mn), f1 = expf(ms[u] - Mn);
+                num = num * f0 + f1 * os[u];
+                den = den * f0 + f1 * ls[u];
+                Mx = Mn;
+            }
+        }
     }
     c.xs[xs_idx(c.tid)] = num / den;
     csync();
 }
 
 // code predictor: full attention of kv group g for the M new positions p0.., result -> xs[m][0..256)
-LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int p0) {
+LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int p0, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.cp;
     const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv;
@@ -641,41 +772,67 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
     float* q_s = c.att + FA_Q; float* kn = c.att + FA_KN; float* vn = c.att + FA_VN; float* sc = c.att + FA_SC;
     float* kc = p.cp_kv + ((size_t)(layer * 2 + 0) * n_kv + g) * FK_CP_POS * ATT_D;
     float* vc = p.cp_kv + ((size_t)(layer * 2 + 1) * n_kv + g) * FK_CP_POS * ATT_D;
+    // prefetch the cached V column of this thread and the cached K rows of this warp (positions < p0)
+    // while q/k/v of the new rows are polled
+    const int r_t = c.tid >> 7, d_t = c.tid & 127;
+    float vcol[FK_CP_POS / 2];
+#pragma unroll
+    for (int j = 0; j < FK_CP_POS / 2; ++j) vcol[j] = (j < p0) ? __ldcg(vc + (size_t)j * ATT_D + d_t) : 0.f;
+    float4 kpre[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = c.warp + u * FK_CWARPS;
+        kpre[u] = (j < p0) ? __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // warps 0..2M-1: q heads ; 2M..3M-1: k ; 3M..4M-1: v
     for (int job = c.warp; job < 4 * M; job += FK_CWARPS) {
         if (job < 2 * M) {
             const int m = job >> 1, r = job & 1, pos = p0 + m;
-            float4 v = __ldcg(reinterpret_cast<const float4*>(S.qkv + (size_t)m * qkv_dim + (size_t)(g * 2 + r) * ATT_D) + c.lane);
+            float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + (size_t)(g * 2 + r) * ATT_D + c.lane * 4, want);
             v = head_norm_rope(v, L.qnorm, p.eps, S.cos + (size_t)pos * (ATT_D / 2), S.sin + (size_t)pos * (ATT_D / 2), c.lane);
             reinterpret_cast<float4*>(q_s + (m * 2 + r) * ATT_D)[c.lane] = v;
         } else if (job < 3 * M) {
             const int m = job - 2 * M, pos = p0 + m;
-            float4 v = __ldcg(reinterpret_cast<const float4*>(S.qkv + (size_t)m * qkv_dim + q_dim + (size_t)g * ATT_D) + c.lane);
+            float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + q_dim + (size_t)g * ATT_D + c.lane * 4, want);
             v = head_norm_rope(v, L.knorm, p.eps, S.cos + (size_t)pos * (ATT_D / 2), S.sin + (size_t)pos * (ATT_D / 2), c.lane);
             reinterpret_cast<float4*>(kn + m * ATT_D)[c.lane] = v;
-            if (s == 0) reinterpret_cast<float4*>(kc + (size_t)pos * ATT_D)[c.lane] = v;
+            if (s == 0) { reinterpret_cast<float4*>(kc + (size_t)pos * ATT_D)[c.lane] = v; __threadfence(); }
         } else {
             const int m = job - 3 * M, pos = p0 + m;
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(S.qkv + (size_t)m * qkv_dim + q_dim + kv_dim + (size_t)g * ATT_D) + c.lane);
+            const float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + q_dim + kv_dim + (size_t)g * ATT_D + c.lane * 4, want);
             reinterpret_cast<float4*>(vn + m * ATT_D)[c.lane] = v;
-            if (s == 0) reinterpret_cast<float4*>(vc + (size_t)pos * ATT_D)[c.lane] = v;
+            if (s == 0) { reinterpret_cast<float4*>(vc + (size_t)pos * ATT_D)[c.lane] = v; __threadfence(); }
         }
     }
     csync();
     const float scale = 1.0f / sqrtf((float)ATT_D);
-    // scores: combos (m, j) -> both heads
+    // scores: key j against both heads of every row m that may see it (warp handles j = warp, warp + 8, warp + 16)
     const int n_last = p0 + M;                       // positions visible to the last row
-    for (int cb = c.warp; cb < M * n_last; cb += FK_CWARPS) {
-        const int m = cb / n_last, j = cb - m * n_last;
-        if (j > p0 + m) continue;                    // causal
-        const float4 k4 = (j < p0) ? __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + c.lane)
-                                   : reinterpret_cast<const float4*>(kn + (j - p0) * ATT_D)[c.lane];
-        const float4 qa = reinterpret_cast<const float4*>(q_s + (m * 2 + 0) * ATT_D)[c.lane];
-        const float4 qb = reinterpret_cast<const float4*>(q_s + (m * 2 + 1) * ATT_D)[c.lane];
-        float d0 = k4.x * qa.x + k4.y * qa.y + k4.z * qa.z + k4.w * qa.w;
-        float d1 = k4.x * qb.x + k4.y * qb.y + k4.z * qb.z + k4.w * qb.w;
-        d0 = warp_sum(d0) * scale; d1 = warp_sum(d1) * scale;
-        if (c.lane == 0) { sc[(m * 2 + 0) * FK_CP_POS + j] = d0; sc[(m * 2 + 1) * FK_CP_POS + j] = d1; }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int j = c.warp + u * FK_CWARPS;
+        if (j < n_last) {
+            float4 k4;
+            if (j >= p0) k4 = reinterpret_cast<const float4*>(kn + (j - p0) * ATT_D)[c.lane];
+            else if (u < 2) k4 = kpre[u < 2 ? u : 0];
+            else k4 = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + c.lane);
+            float d[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {            // i = m*2 + r
+                const float4 q = reinterpret_cast<const float4*>(q_s + i * ATT_D)[c.lane];
+                d[i] = k4.x * q.x + k4.y * q.y + k4.z * q.z + k4.w * q.w;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
+            if (c.lane < 2 * M) {
+                const int m = c.lane >> 1;
+                float v = d[0];
+                if (c.lane == 1) v = d[1]; else if (c.lane == 2) v = d[2]; else if (c.lane == 3) v = d[3];
+                if (j <= p0 + m) sc[c.lane * FK_CP_POS + j] = v * scale;
+            }
+        }
     }
     csync();
     if (c.warp < 2 * M) {                            // softmax of row (m, r) over j <= p0 + m
@@ -688,18 +845,14 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
         if (c.lane < np) row[c.lane] = e / sum;
     }
     csync();
-    {
-        const int r = c.tid >> 7, d = c.tid & 127;
-        for (int m = 0; m < M; ++m) {
-            const int np = p0 + m + 1;
-            const float* row = sc + (m * 2 + r) * FK_CP_POS;
-            float o = 0.f;
-            for (int j = 0; j < np; ++j) {
-                const float vv = (j < p0) ? __ldcg(vc + (size_t)j * ATT_D + d) : vn[(j - p0) * ATT_D + d];
-                o = fmaf(row[j], vv, o);
-            }
-            c.xs[m * 256 + xs_idx(c.tid)] = o;       // K = 256 -> Kpad = 256
-        }
+    for (int m = 0; m < M; ++m) {
+        const int np = p0 + m + 1;
+        const float* row = sc + (m * 2 + r_t) * FK_CP_POS;
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < FK_CP_POS / 2; ++j) if (j < p0) o = fmaf(row[j], vcol[j], o);
+        for (int j = p0; j < np; ++j) o = fmaf(row[j], vn[(j - p0) * ATT_D + d_t], o);
+        c.xs[m * 256 + xs_idx(c.tid)] = o;           // K = 256 -> Kpad = 256
     }
     csync();
 }
@@ -707,13 +860,11 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
 // ------------------------------------------------------------------------------------------------
 // one token pass (M rows) through a stack, as ONE loop over the flat op schedule so that every helper
 // is instantiated exactly once (the context stays in registers; no local memory on the hot path).
-// x0: layer-0 input rows in global memory [M][x0_stride] (also the layer-0 residual);
-// x0_in_smem: the rows are already staged in xs (sampler glue).
+// The layer-0 input rows are in c.res0 (smem, plain layout, stride = talker hidden).
 // ------------------------------------------------------------------------------------------------
 struct FkPass {
     bool is_cp; int M, pos0;
-    const float* x0; int x0_stride; bool x0_in_smem;
-    const bf16_t* head_w; int head_n; float* head_out; float* hidden_out;
+    const bf16_t* head_w; int head_n;
 };
 
 LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
@@ -721,86 +872,79 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
     const FkStack& S = is_cp ? p.cp : p.talker;
     const int tk = is_cp ? 1 : 0, M = ps.M;
     const int H = S.H, qd = S.heads * ATT_D, kvd = S.kv_heads * ATT_D, qkv_dim = qd + 2 * kvd;
-    const int rep = S.heads / S.kv_heads, gK = rep * ATT_D, n_kv = S.kv_heads;
+    const int n_kv = S.kv_heads;
+    const int H0 = p.talker.H;                                   // width of the rows in res0
     const bool inproj = is_cp && p.c_inproj_w != nullptr;
     const int total = pass_ops(S.n_layers, inproj, ps.head_w != nullptr);
-    const float* lin = ps.x0; int lin_stride = ps.x0_stride;   // layer input rows (global)
-    bool in_smem = ps.x0_in_smem;
     for (int it = 0; it < total && !c.aborted; ++it) {
         const FkOp op = pass_op(it, S.n_layers, inproj);
         const int kind = op.kind, l = op.layer;
         if (kind == FKT_B && is_cp) continue;                 // the predictor's attention lives inside phase C
+        ++c.seq;
+        const unsigned want = c.seq - 1;
         fk_phase(c, tk, kind);
         fk_mark(c, 0);
         const FkLayer& L = is_cp ? p.c_layers[l] : p.t_layers[l];
-        // ---- what this phase stages and multiplies ---------------------------------------------
-        const float* src = nullptr; int sstride = 0, sK = 0, sM = M, npart = 0;
-        const float* part = nullptr; float* scopy = nullptr; bool do_stage = false;
-        const float* nw = nullptr; float* ncopy = nullptr;
-        int gK_ = 0, gM = M, rg = 1; FkSlice sl{0, 0};
-        FkEpi e{EPI_STORE, nullptr, 0, nullptr, 0, nullptr, 0};
-        bool need_wait = true;
-        switch (kind) {
-            case FKT_INPROJ:
-                need_wait = false;
-                do_stage = !in_smem; src = lin; sstride = lin_stride; sK = p.talker.H;
-                gK_ = p.talker.H; sl = flat_slice(H, 1, c.cta, c.ncta);
-                e = FkEpi{EPI_STORE, p.cxin, H, p.c_inproj_b, 0, nullptr, 0};
-                break;
-            case FKT_A:
-                need_wait = !(l == 0 && !inproj);
-                do_stage = !(l == 0 && in_smem); src = lin; sstride = lin_stride; sK = H;
-                nw = L.ln1;
-                gK_ = H; sl = flat_slice(qkv_dim, 1, c.cta, c.ncta);
-                e = FkEpi{EPI_STORE, S.qkv, qkv_dim, nullptr, 0, nullptr, 0};
-                break;
-            case FKT_B:
-                break;
-            case FKT_C:
-                gK_ = gK; sl = group_slice(H, c.cta, c.ncta, n_kv);
-                e = FkEpi{EPI_STORE, S.po + (size_t)(c.cta % n_kv) * H, n_kv * H, nullptr, 0, nullptr, 0};
-                break;
-            case FKT_D:
-                do_stage = true; src = lin; sstride = lin_stride; sK = H; part = S.po; npart = n_kv; scopy = S.xmid;
-                nw = L.ln2;
-                gK_ = H; rg = 2; sl = flat_slice(2 * S.inter, 2, c.cta, c.ncta);
-                e = FkEpi{EPI_GLU, S.act, S.inter, nullptr, 0, nullptr, 0};
-                break;
-            case FKT_E:
-                do_stage = true; src = S.act; sstride = S.inter; sK = S.inter;
-                gK_ = S.inter; sl = flat_slice(H, 1, c.cta, c.ncta);
-                e = FkEpi{EPI_RESID, S.x, H, nullptr, 0, S.xmid, H};
-                break;
-            default:   // FKT_HEAD: final norm of the LAST row + head
-                do_stage = true; src = S.x + (size_t)(M - 1) * H; sstride = H; sK = H; sM = 1;
-                nw = S.final_norm; ncopy = ps.hidden_out;
-                gK_ = H; gM = 1; sl = flat_slice(ps.head_n, 1, c.cta, c.ncta);
-                e = FkEpi{EPI_STORE, ps.head_out, ps.head_n, nullptr, 0, nullptr, 0};
-                break;
-        }
-        fk_mark(c, 1);
-        if (need_wait) { gbar_wait(c); if (c.aborted) break; }
-        fk_mark(c, 2);
+        const FkDesc d = c.sh->desc[tk][kind];
+        // the layer input rows: res0 (smem) for layer 0 without in_proj, else an LL buffer
+        const bool in_res0 = (l == 0 && !inproj);
+        const uint2* lin = (l == 0) ? p.cxin : S.x;           // (only read when !in_res0)
         if (kind == FKT_B) {
-            if (p.kv_f32) talker_attn_partial<float>(c, L, l, ps.pos0);
-            else          talker_attn_partial<bf16_t>(c, L, l, ps.pos0);
+            if (p.kv_f32) talker_attn_partial<float>(c, L, l, ps.pos0, want);
+            else          talker_attn_partial<bf16_t>(c, L, l, ps.pos0, want);
             fk_mark(c, 3);
-            gbar_arrive(c);
+            if (c.sh->aborted) { c.aborted = true; break; }
             continue;
         }
-        if (kind == FKT_C) {
-            if (is_cp) cp_attn_local(c, L, l, M, ps.pos0);
-            else       talker_attn_combine(c, ps.pos0);
+        FkStage sg{nullptr, 0, false, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr};
+        FkEpi e{EPI_STORE, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0};
+        int sM = M, gM = M;
+        bool do_stage = true;
+        switch (kind) {
+            case FKT_INPROJ:
+                sg.sm = c.res0; sg.sm_stride = H0;
+                e.out = p.cxin; e.out_stride = H; e.bias = p.c_inproj_b;
+                break;
+            case FKT_A:
+                if (in_res0) { sg.sm = c.res0; sg.sm_stride = H0; }
+                else { sg.ll = lin; sg.ll_stride = H; }
+                sg.nw = L.ln1;
+                e.out = S.qkv; e.out_stride = qkv_dim;
+                break;
+            case FKT_C:
+                do_stage = false;
+                e.out = S.po + (size_t)(c.cta % n_kv) * H; e.out_stride = n_kv * H;
+                break;
+            case FKT_D:
+                if (in_res0) { sg.sm = c.res0; sg.sm_stride = H0; }
+                else { sg.ll = lin; sg.ll_stride = H; sg.verified = true; }
+                sg.part = S.po; sg.n_part = n_kv; sg.nw = L.ln2;
+                e.kind = EPI_GLU; e.out = S.act; e.out_stride = S.inter;
+                break;
+            case FKT_E:
+                sg.ll = S.act; sg.ll_stride = S.inter;
+                e.kind = EPI_RESID; e.out = S.x; e.out_stride = H;
+                if (in_res0) { e.res_sm = c.res0; e.res_sm_stride = H0; }
+                else { e.res_ll = lin; e.res_ll_stride = H; }
+                e.po = S.po; e.n_part = n_kv; e.H = H;
+                break;
+            default:   // FKT_HEAD: final norm of the LAST row + head
+                sg.ll = S.x + (size_t)(M - 1) * H; sg.ll_stride = H; sM = 1; gM = 1;
+                sg.nw = S.final_norm;
+                if (!is_cp) { sg.copy_sm = c.lh; sg.copy_gl = p.last_hidden; }
+                e.kind = EPI_LOGITS; e.out = is_cp ? p.clogits_ll : p.logits_ll; e.out_stride = 0;
+                e.plain = is_cp ? p.clogits : p.logits;
+                break;
         }
-        if (do_stage) stage_rows(c, src, sstride, sM, sK, part, npart, scopy);
+        if (kind == FKT_C) {
+            if (is_cp) cp_attn_local(c, L, l, M, ps.pos0, want);
+            else       talker_attn_combine(c, ps.pos0, want);
+        }
+        if (do_stage) stage_rows(c, sg, sM, d.K, want, p.eps);
         fk_mark(c, 3);
-        if (nw) norm_rows(c, nw, sM, sK, p.eps, ncopy);
-        fk_mark(c, 4);
-        gemv_phase(c, gK_, gM, rg, sl.row0, sl.nrows, e);
+        if (c.sh->aborted) { c.aborted = true; break; }
+        gemv_phase(c, d.K, gM, d.RG, d.row0, d.nrows, e);
         fk_mark(c, 6);
-        gbar_arrive(c);
-        if (kind == FKT_E) { lin = S.x; lin_stride = H; in_smem = false; }
-        if (kind == FKT_INPROJ) { lin = p.cxin; lin_stride = H; in_smem = false; }
     }
 }
 
@@ -824,23 +968,29 @@ LQT_DEVINL int block_excl_scan(FkCtx& c, int v, int* total) {          // 256-th
     return base + inc - v;
 }
 
-LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const float* logits, int V, int mask_lo, int mask_hi,
-                         int mask_keep, const SamplingDev& sp, uint32_t frame, int codebook, float* trace_row) {
+// logits: LL words tagged `want` (ll != nullptr) or a plain array (first draw after a resume)
+LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, const float* plain, unsigned want, int V,
+                         int mask_lo, int mask_hi, int mask_keep, const SamplingDev& sp, uint32_t frame, int codebook,
+                         float* trace_row) {
     FkShared* sh = c.sh;
     const bool temper = !sp.greedy && sp.temperature > 0.0f && sp.temperature != 1.0f;
-    for (int i = c.tid; i < V; i += FK_CTHREADS) {
-        float v = __ldcg(logits + i);
-        if (i >= mask_lo && i < mask_hi && i != mask_keep) v = -INFINITY;
-        if (trace_row) trace_row[i] = v;
-        if (temper) v = v / sp.temperature;
-        s.x[i] = v;
-    }
-    csync();
-    // block max + argmax (lowest index on ties)
+    // thread owns the contiguous range [i0, i1) (V % 4 == 0, ranges are multiples of 4)
+    const int per = (((V + FK_CTHREADS - 1) / FK_CTHREADS) + 3) & ~3;
+    const int i0 = min(V, c.tid * per), i1 = min(V, i0 + per);
     float bv = -INFINITY; int bi = 0x7fffffff;
-    for (int i = c.tid; i < V; i += FK_CTHREADS) {
-        const float v = s.x[i];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    for (int i = i0; i < i1; i += 4) {
+        const float4 q = ll ? ll_poll4(c, ll + i, want) : *reinterpret_cast<const float4*>(plain + i);
+        const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v = vv[u];
+            const int ii = i + u;
+            if (ii >= mask_lo && ii < mask_hi && ii != mask_keep) v = -INFINITY;
+            if (trace_row) trace_row[ii] = v;
+            if (temper) v = v / sp.temperature;
+            s.x[ii] = v;
+            if (v > bv) { bv = v; bi = ii; }                   // ascending ii: first maximum wins
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -857,10 +1007,10 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const float* logits, 
             if (sh->redf[w2][0] > v || (sh->redf[w2][0] == v && sh->redi[w2] < i)) { v = sh->redf[w2][0]; i = sh->redi[w2]; }
         bv = v; bi = (i == 0x7fffffff) ? 0 : i;
     }
-    if (sp.greedy) return bi;
+    if (sp.greedy) { csync(); return bi; }
     const float mx = bv;
 
-    // top-k threshold: 4 x 8-bit radix select of the k-th largest key
+    // top-k threshold: 4 x 8-bit radix select of the k-th largest key (warp-aggregated histogram)
     float thr = -INFINITY;
     if (sp.top_k > 0 && sp.top_k < V) {
         if (c.tid == 0) { sh->sel_prefix = 0u; sh->sel_k = sp.top_k; }
@@ -870,9 +1020,13 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const float* logits, 
             const uint32_t prefix = sh->sel_prefix;
             const int kk = sh->sel_k;
             const uint32_t himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-            for (int i = c.tid; i < V; i += FK_CTHREADS) {
-                const uint32_t key = float_key(s.x[i]);
-                if ((key & himask) == prefix) atomicAdd(&sh->hist[(key >> shift) & 255], 1);
+            for (int i = i0; i < i0 + per; ++i) {               // uniform trip count: __match_any needs the full warp
+                const bool in = i < i1;
+                const uint32_t key = in ? float_key(s.x[i]) : 0u;
+                const bool hit = in && ((key & himask) == prefix);
+                const int bin = hit ? (int)((key >> shift) & 255) : (256 + c.lane);   // misses never match each other
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (hit && (__ffs(peers) - 1) == c.lane) atomicAdd(&sh->hist[bin], __popc(peers));
             }
             csync();
             // suffix sums S(b) = sum_{b' >= b} hist[b']; pick b with S(b) >= kk > S(b+1)
@@ -888,8 +1042,6 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const float* logits, 
         thr = __uint_as_float((kkey & 0x80000000u) ? (kkey & 0x7fffffffu) : ~kkey);
     }
     // compaction in index order (thread owns a contiguous range)
-    const int per = (V + FK_CTHREADS - 1) / FK_CTHREADS;
-    const int i0 = c.tid * per, i1 = min(V, i0 + per);
     int cnt = 0;
     for (int i = i0; i < i1; ++i) { const float v = s.x[i]; cnt += (!(v < thr) && v != -INFINITY) ? 1 : 0; }
     int n_surv;
@@ -952,44 +1104,49 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const float* logits, 
         sh->tok = last;
     }
     csync();
-    return sh->tok;
+    const int tok = sh->tok;
+    csync();                     // everyone has read tok/scratch before the glue overwrites anything
+    return tok;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-struct FkSmemLayout { size_t ring, scratch, nxt, shared, total; };
-inline FkSmemLayout fk_smem_layout(int maxV, int max_xs_floats, int H) {
+struct FkSmemLayout { size_t scratch, xs_bytes, nxt, res0, lh, shared, total; };
+inline FkSmemLayout fk_smem_layout(int maxV, int max_xs_floats, int H, int res0_floats) {
     FkSmemLayout L{};
     auto up = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    L.ring = 0;
     size_t off = (size_t)FK_STAGES * FK_STAGE_BYTES;
     L.scratch = off;
+    L.xs_bytes = up((size_t)max_xs_floats * 4);
     const size_t samp = (size_t)maxV * (4 + 4 + 4 + 2 + 2);
-    const size_t xsatt = up((size_t)max_xs_floats * 4) + (size_t)FA_FLOATS * 4;
+    const size_t xsatt = L.xs_bytes + (size_t)FA_FLOATS * 4;
     off += up(samp > xsatt ? samp : xsatt);
     L.nxt = off; off += up((size_t)H * 4);
+    L.res0 = off; off += up((size_t)res0_floats * 4);
+    L.lh = off; off += up((size_t)H * 4);
     L.shared = off; off += up(sizeof(FkShared));
     L.total = off;
     return L;
 }
 
-struct FkSmemOffsets { unsigned scratch, xs_bytes, nxt, shared; int maxV; };
+struct FkSmemOffsets { unsigned scratch, xs_bytes, nxt, res0, lh, shared; int maxV; };
 
 __global__ void __launch_bounds__(FK_THREADS, 1)
 frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     extern __shared__ __align__(1024) unsigned char fk_smem[];
     FkShared* sh = reinterpret_cast<FkShared*>(fk_smem + so.shared);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
         for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }
         sh->stop = 0; sh->consumed = 0; sh->aborted = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
     __syncthreads();
 
     const GenState st0 = *p.st;                    // written by the host before launch
-    const int cta = blockIdx.x, ncta = gridDim.x;
     const int n_prefill = (p.mode == 0 && st0.pos == 0) ? p.P : 0;
     const int frame_end = min(p.frame_end, st0.max_frames);
 
@@ -1009,30 +1166,28 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             for (long long q = 0; q < n_pass && !stopped; ++q) {
                 const FkPassId id = launch_pass(q, p.mode, n_prefill, p.cp_steps);
                 const FkStack& S = id.is_cp ? p.cp : p.talker;
-                const int H = S.H, qd = S.heads * ATT_D, kvd = S.kv_heads * ATT_D, rep = S.heads / S.kv_heads;
+                const int H = S.H, rep = S.heads / S.kv_heads;
                 const bool inproj = id.is_cp && p.c_inproj_w != nullptr;
                 const int total = pass_ops(S.n_layers, inproj, id.head);
                 for (int it = 0; it < total && !stopped; ++it) {
                     const FkOp op = pass_op(it, S.n_layers, inproj);
                     if (op.kind == FKT_B) continue;
                     const FkLayer& L = id.is_cp ? p.c_layers[op.layer] : p.t_layers[op.layer];
-                    const bf16_t* W; int K, RG = 1; FkSlice sl;
+                    const FkDesc d = sh->desc[id.is_cp ? 1 : 0][op.kind];
+                    const bf16_t* W;
                     switch (op.kind) {
-                        case FKT_INPROJ: W = p.c_inproj_w; K = p.talker.H; sl = flat_slice(H, 1, cta, ncta); break;
-                        case FKT_A: W = L.wqkv; K = H; sl = flat_slice(qd + 2 * kvd, 1, cta, ncta); break;
-                        case FKT_C: W = L.wo_g + (size_t)(cta % S.kv_heads) * H * (rep * ATT_D); K = rep * ATT_D;
-                                    sl = group_slice(H, cta, ncta, S.kv_heads); break;
-                        case FKT_D: W = L.wgu; K = H; RG = 2; sl = flat_slice(2 * S.inter, 2, cta, ncta); break;
-                        case FKT_E: W = L.wdown; K = S.inter; sl = flat_slice(H, 1, cta, ncta); break;
-                        default:
-                            if (id.is_cp) { W = p.c_heads + (size_t)id.cb * p.cp_vocab * H; sl = flat_slice(p.cp_vocab, 1, cta, ncta); }
-                            else          { W = p.t_head; sl = flat_slice(p.vocab, 1, cta, ncta); }
-                            K = H; break;
+                        case FKT_INPROJ: W = p.c_inproj_w; break;
+                        case FKT_A: W = L.wqkv; break;
+                        case FKT_C: W = L.wo_g + (size_t)(cta % S.kv_heads) * H * (rep * ATT_D); break;
+                        case FKT_D: W = L.wgu; break;
+                        case FKT_E: W = L.wdown; break;
+                        default: W = id.is_cp ? p.c_heads + (size_t)id.cb * p.cp_vocab * H : p.t_head; break;
                     }
-                    const int rps = rows_per_stage(K, RG);
-                    const char* srcb = reinterpret_cast<const char*>(W + (size_t)sl.row0 * K);
-                    for (int r = 0; r < sl.nrows && !stopped; r += rps) {
-                        const int n = min(rps, sl.nrows - r);
+                    const int K = d.K;
+                    const int rps = rows_per_stage(K, d.RG);
+                    const char* srcb = reinterpret_cast<const char*>(W + (size_t)d.row0 * K);
+                    for (int r = 0; r < d.nrows && !stopped; r += rps) {
+                        const int n = min(rps, d.nrows - r);
                         const unsigned slot = issued % FK_STAGES, par = ((issued / FK_STAGES) & 1u) ^ 1u;
                         unsigned long long t0 = 0;
                         while (!mbar_try_wait(&sh->empty[slot], par)) {
@@ -1067,88 +1222,91 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     c.xs = reinterpret_cast<float*>(fk_smem + so.scratch);
     c.att = reinterpret_cast<float*>(fk_smem + so.scratch + so.xs_bytes);
     c.nxt = reinterpret_cast<float*>(fk_smem + so.nxt);
+    c.res0 = reinterpret_cast<float*>(fk_smem + so.res0);
+    c.lh = reinterpret_cast<float*>(fk_smem + so.lh);
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
-    c.gen = 0; c.stage_ctr = 0; c.aborted = false;
+    c.seq = 0; c.stage_ctr = 0; c.aborted = false;
     c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
     FkSampScratch ss;
     ss.x = reinterpret_cast<float*>(fk_smem + so.scratch);
     ss.pr = ss.x + so.maxV; ss.spr = ss.pr + so.maxV;
     ss.idx = reinterpret_cast<unsigned short*>(ss.spr + so.maxV); ss.rank = ss.idx + so.maxV;
 
-    const int H = p.talker.H;
-    const int Kpad4 = ((H + 255) & ~255) >> 2;
-    float4* xs4 = reinterpret_cast<float4*>(c.xs);
+    const int H = p.talker.H, H4 = H >> 2;
     int pos = st0.pos, frame = st0.frame, done = st0.done, n_frames = st0.n_frames;
     const SamplingDev sp = *p.sp;
     int prefill_i = 0;
     int cb = 0;                      // next codebook to draw in the current frame (0 = talker code)
     bool mode1_done = false;
+    bool resumed = (p.mode == 0 && n_prefill == 0);   // first draw reads the plain logits / last_hidden of the previous launch
+    if (resumed) {
+        for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)
+            reinterpret_cast<float4*>(c.lh)[k4] = __ldcg(reinterpret_cast<const float4*>(p.last_hidden) + k4);
+        csync();
+    }
 
     // One loop, one pass per iteration: [draw + glue ->] token pass. (src/tts_onnx.cpp:794, 801-846)
     while (!c.aborted) {
         FkPass ps;
-        if (p.mode == 1) {
-            if (mode1_done) break;
-            ps = FkPass{false, 1, pos, p.next_in, H, false, p.t_head, p.vocab, p.logits, p.last_hidden};
-        } else if (prefill_i < n_prefill) {
-            const bool last = (prefill_i == n_prefill - 1);
-            ps = FkPass{false, 1, pos, p.prompt + (size_t)prefill_i * H, H, false, last ? p.t_head : nullptr, p.vocab,
-                        p.logits, p.last_hidden};
+        if (p.mode == 1 || prefill_i < n_prefill) {
+            if (p.mode == 1 && mode1_done) break;
+            const float* src = (p.mode == 1) ? p.next_in : p.prompt + (size_t)prefill_i * H;
+            for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)
+                reinterpret_cast<float4*>(c.res0)[k4] = __ldcg(reinterpret_cast<const float4*>(src) + k4);
+            csync();
+            const bool head = (p.mode == 1) || (prefill_i == n_prefill - 1);
+            ps = FkPass{false, 1, pos, head ? p.t_head : nullptr, p.vocab};
         } else {
             if (done || frame >= frame_end) break;
             // ---- draw codebook cb of this frame (:803-812 for cb 0, :863-864 otherwise) -----------------
             const int tk = cb ? 1 : 0;
             fk_phase(c, tk, FKT_SAMPLE);
-            fk_mark(c, 1);
-            gbar_wait(c); if (c.aborted) break;
-            fk_mark(c, 2);
+            fk_mark(c, 0);
             float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + cb) * p.trace_stride : nullptr;
-            int tok = (cb == 0) ? fk_sample(c, ss, p.logits, p.vocab, 2048, p.vocab, 2150, sp, (uint32_t)frame, 0, tr)
-                                : fk_sample(c, ss, p.clogits, p.cp_vocab, 0, 0, -1, sp, (uint32_t)frame, cb, tr);
+            int tok;
+            if (cb == 0) tok = fk_sample(c, ss, resumed ? nullptr : p.logits_ll, p.logits, c.seq, p.vocab, 2048, p.vocab, 2150,
+                                         sp, (uint32_t)frame, 0, tr);
+            else         tok = fk_sample(c, ss, p.clogits_ll, nullptr, c.seq, p.cp_vocab, 0, 0, -1, sp, (uint32_t)frame, cb, tr);
+            resumed = false;
+            if (c.sh->aborted) { c.aborted = true; break; }
             if (p.forced && frame < st0.n_forced) tok = (int)p.forced[(size_t)frame * 16 + cb];
             fk_mark(c, 3);
             if (cb == 0 && tok == 2150) { done = 1; break; }                        // CODEC_EOS (:812)
             if (cta == 0 && tid == 0) p.codes_out[(size_t)frame * 16 + cb] = tok;   // :818-821
-            // ---- glue: embedding of the drawn code, running 16-way sum, next input rows ------------------
+            // ---- glue: embedding of the drawn code, running 16-way sum, next input rows (in res0) --------
             const bool last_cb = (cb == p.cp_steps);
             const bool use_tr = frame < st0.trailing_len;
             const bf16_t* row = (cb == 0) ? p.codec_embed + (size_t)tok * H
                                           : p.cp_embed + ((size_t)(cb - 1) * p.cp_vocab + tok) * H;
-            for (int k4 = tid; k4 < Kpad4; k4 += FK_CTHREADS) {
-                float4 e = make_float4(0.f, 0.f, 0.f, 0.f), acc = e, lh = e;
-                if (k4 < (H >> 2)) {
-                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + k4);
-                    e = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
-                    if (cb == 0) {
-                        acc = e;                                                    // :824
-                        lh = __ldcg(reinterpret_cast<const float4*>(p.last_hidden) + k4);   // :859
-                    } else {
-                        acc = reinterpret_cast<float4*>(c.nxt)[k4];                 // :825-830
-                        acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
-                    }
-                    if (last_cb) {                                                  // :833-842
-                        const float4 tt = use_tr ? __ldg(reinterpret_cast<const float4*>(p.trailing + (size_t)frame * H) + k4)
-                                                 : __ldg(reinterpret_cast<const float4*>(p.tts_pad) + k4);
-                        acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
-                    }
-                    reinterpret_cast<float4*>(c.nxt)[k4] = acc;
-                    if (cta == 0) {                                                 // layer-0 residual of the next pass
-                        if (last_cb) reinterpret_cast<float4*>(p.next_in)[k4] = acc;
-                        else if (cb == 0) { reinterpret_cast<float4*>(p.cp_in)[k4] = lh; reinterpret_cast<float4*>(p.cp_in + H)[k4] = e; }
-                        else reinterpret_cast<float4*>(p.cp_in)[k4] = e;
-                    }
+            for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + k4);
+                const float4 e = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
+                float4 acc = e;                                                 // :824
+                if (cb != 0) {                                                  // :825-830
+                    acc = reinterpret_cast<float4*>(c.nxt)[k4];
+                    acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
                 }
-                if (cb == 0) { xs4[xs_perm4(k4)] = lh; xs4[Kpad4 + xs_perm4(k4)] = e; }
-                else xs4[xs_perm4(k4)] = last_cb ? acc : e;
+                if (last_cb) {                                                  // :833-842
+                    const float4 tt = use_tr ? __ldg(reinterpret_cast<const float4*>(p.trailing + (size_t)frame * H) + k4)
+                                             : __ldg(reinterpret_cast<const float4*>(p.tts_pad) + k4);
+                    acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
+                }
+                reinterpret_cast<float4*>(c.nxt)[k4] = acc;
+                if (cb == 0) {                                                  // rows [last_hidden, codec_embed(code0)] (:854-860)
+                    reinterpret_cast<float4*>(c.res0)[k4] = reinterpret_cast<const float4*>(c.lh)[k4];
+                    reinterpret_cast<float4*>(c.res0 + H)[k4] = e;
+                } else {
+                    reinterpret_cast<float4*>(c.res0)[k4] = last_cb ? acc : e;  // :867-868 / :845
+                }
+                if (last_cb && cta == 0) reinterpret_cast<float4*>(p.next_in)[k4] = acc;
             }
             csync();
             fk_mark(c, 4);
             if (last_cb) {
                 n_frames = frame + 1;
-                ps = FkPass{false, 1, pos, p.next_in, H, true, p.t_head, p.vocab, p.logits, p.last_hidden};   // :845
+                ps = FkPass{false, 1, pos, p.t_head, p.vocab};                  // :845
             } else {
-                ps = FkPass{true, cb == 0 ? 2 : 1, cb == 0 ? 0 : cb + 1, p.cp_in, H, true,
-                            p.c_heads + (size_t)cb * p.cp_vocab * p.cp.H, p.cp_vocab, p.clogits, nullptr};
+                ps = FkPass{true, cb == 0 ? 2 : 1, cb == 0 ? 0 : cb + 1, p.c_heads + (size_t)cb * p.cp_vocab * p.cp.H, p.cp_vocab};
             }
         }
         consume_token(c, p, ps);
