@@ -241,32 +241,67 @@ LQT_DEVINL FkPassId launch_pass(long long q, int mode, int n_prefill, int cp_ste
 }
 
 // ------------------------------------------------------------------------------------------------
-// LL polling
+// LL polling. The retry paths are cold and kept out of line (instruction-cache footprint of the layer
+// loop matters); they take plain scalars so that the context struct can stay in registers.
 // ------------------------------------------------------------------------------------------------
-LQT_DEVINL bool ll_giveup(FkCtx& c, int& spins, unsigned long long& t0) {
-    if ((++spins & 1023) != 0) return false;
-    if (c.sh->aborted || *reinterpret_cast<volatile unsigned*>(&c.p->ctrl[1]) != 0) { c.sh->aborted = 1; return true; }
-    if (t0 == 0) { t0 = clock64(); return false; }
-    if (clock64() - t0 > FK_SPIN_LIMIT) { atomicExch(&c.p->ctrl[1], 1u); c.sh->aborted = 1; return true; }
+__device__ __noinline__ bool ll_giveup_slow(volatile int* aborted, unsigned* ctrl, unsigned long long* t0) {
+    if (*aborted || *reinterpret_cast<volatile unsigned*>(&ctrl[1]) != 0) { *aborted = 1; return true; }
+    if (*t0 == 0) { *t0 = clock64(); return false; }
+    if (clock64() - *t0 > FK_SPIN_LIMIT) { atomicExch(&ctrl[1], 1u); *aborted = 1; return true; }
     return false;
+}
+struct FkLL4 { uint4 a, b; };
+__device__ __noinline__ FkLL4 ll_poll4_slow(const uint2* p, unsigned seq, volatile int* aborted, unsigned* ctrl) {
+    FkLL4 r;
+    int spins = 0; unsigned long long t0 = 0;
+    do {
+        if ((++spins & 255) == 0 && ll_giveup_slow(aborted, ctrl, &t0)) { r.a = ld_ll2(p); r.b = ld_ll2(p + 2); break; }
+        __nanosleep(100);
+        r.a = ld_ll2(p); r.b = ld_ll2(p + 2);
+    } while (r.a.y != seq || r.a.w != seq || r.b.y != seq || r.b.w != seq);
+    return r;
+}
+__device__ __noinline__ uint2 ll_poll1_slow(const uint2* p, unsigned seq, volatile int* aborted, unsigned* ctrl, unsigned sleep_ns) {
+    uint2 a;
+    int spins = 0; unsigned long long t0 = 0;
+    do {
+        if ((++spins & 255) == 0 && ll_giveup_slow(aborted, ctrl, &t0)) { a = ld_ll1(p); break; }
+        __nanosleep(sleep_ns);
+        a = ld_ll1(p);
+    } while (a.y != seq);
+    return a;
+}
+__device__ __noinline__ bool wait_full_slow(uint64_t* bar, unsigned par, unsigned* ctrl) {
+    unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, par)) {
+        if (clock64() - t0 > FK_SPIN_LIMIT) { atomicExch(&ctrl[1], 1u); return false; }
+    }
+    return true;
+}
+
+// Readiness probe before a CTA-wide read: warp 0 polls 32 words spread over the region (one per lane,
+// with back-off) and everybody else waits at the CTA barrier, so that a not-yet-complete vector costs
+// 32 L2 requests per CTA and round instead of one per thread (148 CTAs polling the same lines would
+// otherwise starve the very stores they wait for).
+LQT_DEVINL void ll_probe(FkCtx& c, const uint2* base, int nwords, unsigned seq) {
+    if (c.warp == 0) {
+        const uint2* p = base + (((c.lane + 1) * nwords) >> 5) - 1;
+        if (ld_ll1(p).y != seq) ll_poll1_slow(p, seq, &c.sh->aborted, c.p->ctrl, 40);
+    }
+    csync();
 }
 // four consecutive words (32-byte aligned group), all tagged `seq`
 LQT_DEVINL float4 ll_poll4(FkCtx& c, const uint2* p, unsigned seq) {
     uint4 a = ld_ll2(p), b = ld_ll2(p + 2);
-    int spins = 0; unsigned long long t0 = 0;
-    while (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
-        if (ll_giveup(c, spins, t0)) break;
-        a = ld_ll2(p); b = ld_ll2(p + 2);
+    if (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
+        const FkLL4 r = ll_poll4_slow(p, seq, &c.sh->aborted, c.p->ctrl);
+        a = r.a; b = r.b;
     }
     return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 LQT_DEVINL float ll_poll1(FkCtx& c, const uint2* p, unsigned seq) {
     uint2 a = ld_ll1(p);
-    int spins = 0; unsigned long long t0 = 0;
-    while (a.y != seq) {
-        if (ll_giveup(c, spins, t0)) break;
-        a = ld_ll1(p);
-    }
+    if (a.y != seq) a = ll_poll1_slow(p, seq, &c.sh->aborted, c.p->ctrl, 100);
     return __uint_as_float(a.x);
 }
 // values already verified by this CTA in an earlier phase
@@ -293,81 +328,83 @@ struct FkStage {
     float* copy_gl;         // nullable: and to global [K] by CTA 0
 };
 
+LQT_DEVINL float4 stage_fetch(FkCtx& c, const FkStage& s, int m, int k4, int K, unsigned want) {
+    float4 a;
+    if (s.ll) a = s.verified ? ll_val4(s.ll + (size_t)m * s.ll_stride + k4 * 4)
+                             : ll_poll4(c, s.ll + (size_t)m * s.ll_stride + k4 * 4, want);
+    else a = reinterpret_cast<const float4*>(s.sm + (size_t)m * s.sm_stride)[k4];
+    if (s.part) {
+        // all partial vectors in flight at once, validated afterwards (stragglers: slow path)
+        uint4 q[FK_NGRP_MAX][2];
+#pragma unroll
+        for (int g = 0; g < FK_NGRP_MAX; ++g) {
+            if (g < s.n_part) {
+                const uint2* pp = s.part + ((size_t)m * s.n_part + g) * K + k4 * 4;
+                q[g][0] = ld_ll2(pp); q[g][1] = ld_ll2(pp + 2);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < FK_NGRP_MAX; ++g) {
+            if (g < s.n_part) {
+                float4 b;
+                if (q[g][0].y == want && q[g][0].w == want && q[g][1].y == want && q[g][1].w == want)
+                    b = make_float4(__uint_as_float(q[g][0].x), __uint_as_float(q[g][0].z), __uint_as_float(q[g][1].x), __uint_as_float(q[g][1].z));
+                else
+                    b = ll_poll4(c, s.part + ((size_t)m * s.n_part + g) * K + k4 * 4, want);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+        }
+    }
+    return a;
+}
+
 LQT_DEVINL void stage_rows(FkCtx& c, const FkStage& s, int M, int K, unsigned want, float eps) {
     const int K4 = K >> 2, Kpad4 = ((K + 255) & ~255) >> 2;
     float4* xs4 = reinterpret_cast<float4*>(c.xs);
-    if (!s.nw) {
-        for (int m = 0; m < M; ++m) {
-            for (int k4 = c.tid; k4 < Kpad4; k4 += FK_CTHREADS) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k4 < K4) {
-                    if (s.ll) v = s.verified ? ll_val4(s.ll + (size_t)m * s.ll_stride + k4 * 4)
-                                             : ll_poll4(c, s.ll + (size_t)m * s.ll_stride + k4 * 4, want);
-                    else v = reinterpret_cast<const float4*>(s.sm + (size_t)m * s.sm_stride)[k4];
-                }
-                xs4[m * Kpad4 + xs_perm4(k4)] = v;
-            }
-        }
-        csync();
-        return;
-    }
-    // norm path: K = hidden <= 2048 -> at most 2 float4 per thread per row
-    float4 v[2][2];
-    float4 wv[2];
-    float ss[2] = {0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int k4 = c.tid + i * FK_CTHREADS;
-        wv[i] = (k4 < K4) ? __ldg(reinterpret_cast<const float4*>(s.nw) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int k4 = c.tid + i * FK_CTHREADS;
+    if (s.part) ll_probe(c, s.part, M * s.n_part * K, want);
+    else if (s.ll && !s.verified) ll_probe(c, s.ll, (M - 1) * s.ll_stride + K, want);
+    const bool norm = s.nw != nullptr;         // norm path: K = hidden <= 2048 -> at most 2 float4 per thread per row,
+    float4 v00, v01, v10, v11;                 // kept in registers until rstd is known (xs is written once)
+    v00 = v01 = v10 = v11 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+#pragma unroll 1
+        for (int k4 = c.tid, i = 0; k4 < Kpad4; k4 += FK_CTHREADS, ++i) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < M && k4 < K4) {
-                if (s.ll) a = s.verified ? ll_val4(s.ll + (size_t)m * s.ll_stride + k4 * 4)
-                                         : ll_poll4(c, s.ll + (size_t)m * s.ll_stride + k4 * 4, want);
-                else a = reinterpret_cast<const float4*>(s.sm + (size_t)m * s.sm_stride)[k4];
-                if (s.part) {
-#pragma unroll 8
-                    for (int g = 0; g < s.n_part; ++g) {
-                        const float4 b = ll_poll4(c, s.part + ((size_t)m * s.n_part + g) * K + k4 * 4, want);
-                        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                    }
-                }
-                ss[m] += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            if (k4 < K4) a = stage_fetch(c, s, m, k4, K, want);
+            if (norm) {
+                const float q = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+                if (m == 0) { ss0 += q; if (i == 0) v00 = a; else v01 = a; }
+                else        { ss1 += q; if (i == 0) v10 = a; else v11 = a; }
+            } else {
+                xs4[m * Kpad4 + xs_perm4(k4)] = a;
             }
-            v[m][i] = a;
         }
     }
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        const float t = warp_sum(ss[m]);
-        if (c.lane == 0) c.sh->redf[c.warp][m] = t;
-    }
+    if (!norm) { csync(); return; }
+    ss0 = warp_sum(ss0); ss1 = warp_sum(ss1);
+    if (c.lane == 0) { c.sh->redf[c.warp][0] = ss0; c.sh->redf[c.warp][1] = ss1; }
     csync();
+    float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        if (m < M) {
-            float t = 0.f;
-#pragma unroll
-            for (int w2 = 0; w2 < FK_CWARPS; ++w2) t += c.sh->redf[w2][m];
-            const float r = 1.0f / sqrtf(t / (float)K + eps);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int k4 = c.tid + i * FK_CTHREADS;
-                if (k4 < Kpad4) {
-                    float4 a = v[m][i];
-                    a.x = (a.x * r) * wv[i].x; a.y = (a.y * r) * wv[i].y; a.z = (a.z * r) * wv[i].z; a.w = (a.w * r) * wv[i].w;
-                    xs4[m * Kpad4 + xs_perm4(k4)] = a;
-                    if (m == 0 && k4 < K4) {
-                        if (s.copy_sm) reinterpret_cast<float4*>(s.copy_sm)[k4] = a;
-                        if (s.copy_gl && c.cta == 0) reinterpret_cast<float4*>(s.copy_gl)[k4] = a;
-                    }
+    for (int w2 = 0; w2 < FK_CWARPS; ++w2) { t0 += c.sh->redf[w2][0]; t1 += c.sh->redf[w2][1]; }
+    const float r0 = 1.0f / sqrtf(t0 / (float)K + eps), r1 = 1.0f / sqrtf(t1 / (float)K + eps);
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+#pragma unroll 1
+        for (int k4 = c.tid, i = 0; k4 < Kpad4; k4 += FK_CTHREADS, ++i) {
+            float4 a = (m == 0) ? (i == 0 ? v00 : v01) : (i == 0 ? v10 : v11);
+            const float r = (m == 0) ? r0 : r1;
+            if (k4 < K4) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(s.nw) + k4);
+                a.x = (a.x * r) * w.x; a.y = (a.y * r) * w.y; a.z = (a.z * r) * w.z; a.w = (a.w * r) * w.w;
+                if (m == 0) {
+                    if (s.copy_sm) reinterpret_cast<float4*>(s.copy_sm)[k4] = a;
+                    if (s.copy_gl && c.cta == 0) reinterpret_cast<float4*>(s.copy_gl)[k4] = a;
                 }
             }
+            xs4[m * Kpad4 + xs_perm4(k4)] = a;
         }
     }
     csync();
@@ -401,10 +438,8 @@ LQT_DEVINL float epi_resid(const FkEpi& e, int m, int n) {
 
 LQT_DEVINL void wait_full(FkCtx& c, unsigned st) {
     const unsigned slot = st % FK_STAGES, par = (st / FK_STAGES) & 1u;
-    unsigned long long t0 = 0;
-    while (!mbar_try_wait(&c.sh->full[slot], par)) {
-        if (t0 == 0) t0 = clock64();
-        else if (clock64() - t0 > FK_SPIN_LIMIT) { c.aborted = true; atomicExch(&c.p->ctrl[1], 1u); break; }
+    if (!mbar_try_wait(&c.sh->full[slot], par)) {
+        if (!wait_full_slow(&c.sh->full[slot], par, c.p->ctrl)) c.aborted = true;
     }
 }
 
@@ -416,12 +451,16 @@ LQT_DEVINL void dot8x2(const uint4& w, const float4& a, const float4& b, float& 
     acc0 = fmaf(bf16lo(w.w), b.z, acc0); acc1 = fmaf(bf16hi(w.w), b.w, acc1);
 }
 
-// x in registers (KC chunks of 256 elements, M rows). A stage's rows are dealt to warps in batches of
-// RB rows (RB % RG == 0) that one warp processes together (independent accumulator chains, batched
-// shuffles); batches of consecutive stages go to different warps so several stages are in work at once.
-template <int KC, int M, int RG, int RB>
-LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
-    constexpr int K = KC * 256;
+// ONE compact routine for every matrix (instruction-cache footprint matters: the whole layer loop has
+// to stay resident). K is processed in segments of KC*256 elements whose x values sit in registers;
+// a stage's rows are dealt to warps in batches of 4 rows that one warp processes together (independent
+// accumulator chains, batched shuffles); batches of consecutive stages go to different warps so that
+// several stages are in work at once. RG (1, or 2 = SwiGLU gate/up pairs) only affects the epilogue.
+constexpr int FK_RB = 4;
+template <int KC, int M>
+LQT_DEVINL void gemv_seg(FkCtx& c, int K, int RG, int row0, int nrows, const FkEpi& e) {
+    constexpr int KS = KC * 256;                             // segment length
+    const int nseg = K / KS;
     const int Kpad4 = K >> 2;
     const float4* xs4 = reinterpret_cast<const float4*>(c.xs);
     float4 xa[M][KC], xb[M][KC];
@@ -434,117 +473,80 @@ LQT_DEVINL void gemv_reg(FkCtx& c, int row0, int nrows, const FkEpi& e) {
         }
     const int rps = rows_per_stage(K, RG);
     const int nst = (nrows + rps - 1) / rps;
-    const int nbs = (rps + RB - 1) / RB;                     // batches per (full) stage
+    const int nbs = (rps + FK_RB - 1) / FK_RB;               // batches per (full) stage
+#pragma unroll 1
     for (int st = 0; st < nst; ++st) {
         const unsigned ast = c.stage_ctr + st;
         wait_full(c, ast);
         if (st == 0) fk_mark(c, 5);
         const unsigned char* base = c.ring + (size_t)(ast % FK_STAGES) * FK_STAGE_BYTES;
         const int rs = min(rps, nrows - st * rps);          // rows in this stage
-        for (int b = (c.warp + FK_CWARPS - ((st * nbs) & (FK_CWARPS - 1))) & (FK_CWARPS - 1); b * RB < rs; b += FK_CWARPS) {
-            const int rb0 = b * RB;                          // first row of the batch inside the stage
+#pragma unroll 1
+        for (int b = (c.warp + FK_CWARPS - ((st * nbs) & (FK_CWARPS - 1))) & (FK_CWARPS - 1); b * FK_RB < rs; b += FK_CWARPS) {
+            const int rb0 = b * FK_RB;                       // first row of the batch inside the stage
             // residual values for the outputs this lane will publish (latency hidden behind the dots)
             float resid = 0.f;
-            if (e.kind == EPI_RESID && c.lane < RB * M) {
+            if (e.kind == EPI_RESID && c.lane < FK_RB * M) {
                 const int r = c.lane / M, m = c.lane - r * M;
                 if (rb0 + r < rs) resid = epi_resid(e, m, row0 + st * rps + rb0 + r);
             }
-            float acc[RB][M][2];
+            float acc[FK_RB][M][2];
 #pragma unroll
-            for (int r = 0; r < RB; ++r)
+            for (int r = 0; r < FK_RB; ++r)
 #pragma unroll
                 for (int m = 0; m < M; ++m) { acc[r][m][0] = 0.f; acc[r][m][1] = 0.f; }
+#pragma unroll 1
+            for (int sg = 0; sg < nseg; ++sg) {
+                if (nseg > 1) {                              // x registers of this segment
 #pragma unroll
-            for (int j = 0; j < KC; ++j) {
-                uint4 w[RB];
+                    for (int m = 0; m < M; ++m)
 #pragma unroll
-                for (int r = 0; r < RB; ++r)
-                    w[r] = (rb0 + r < rs) ? lds128(base + (size_t)(rb0 + r) * (K * 2) + c.lane * 16 + j * 512)
-                                          : make_uint4(0u, 0u, 0u, 0u);
+                        for (int j = 0; j < KC; ++j) {
+                            xa[m][j] = xs4[m * Kpad4 + sg * (KC * 64) + j * 64 + c.lane];
+                            xb[m][j] = xs4[m * Kpad4 + sg * (KC * 64) + j * 64 + 32 + c.lane];
+                        }
+                }
+                const unsigned char* sbase = base + (size_t)rb0 * ((size_t)K * 2) + (size_t)sg * (KS * 2) + c.lane * 16;
 #pragma unroll
-                for (int r = 0; r < RB; ++r)
+                for (int j = 0; j < KC; ++j) {
+                    uint4 w[FK_RB];
 #pragma unroll
-                    for (int m = 0; m < M; ++m) dot8x2(w[r], xa[m][j], xb[m][j], acc[r][m][0], acc[r][m][1]);
+                    for (int r = 0; r < FK_RB; ++r)
+                        w[r] = (rb0 + r < rs) ? lds128(sbase + (size_t)r * ((size_t)K * 2) + j * 512) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int r = 0; r < FK_RB; ++r)
+#pragma unroll
+                        for (int m = 0; m < M; ++m) dot8x2(w[r], xa[m][j], xb[m][j], acc[r][m][0], acc[r][m][1]);
+                }
             }
-            float tot[RB][M];
+            float tot[FK_RB][M];
 #pragma unroll
-            for (int r = 0; r < RB; ++r)
+            for (int r = 0; r < FK_RB; ++r)
 #pragma unroll
                 for (int m = 0; m < M; ++m) tot[r][m] = acc[r][m][0] + acc[r][m][1];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int r = 0; r < RB; ++r)
+                for (int r = 0; r < FK_RB; ++r)
 #pragma unroll
                     for (int m = 0; m < M; ++m) tot[r][m] += __shfl_xor_sync(0xffffffffu, tot[r][m], o);
-            // lane (g*RG*M + m) publishes output group g of the batch (RESID has RG == 1: lane r*M + m, as above)
+            // lane (r*M + m) publishes row r of the batch (SwiGLU: the lane of the gate row publishes the pair)
+            float mine = 0.f, partner = 0.f;
 #pragma unroll
-            for (int g = 0; g < RB / RG; ++g)
+            for (int r = 0; r < FK_RB; ++r)
 #pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    if (c.lane == g * RG * M + m && rb0 + g * RG < rs) {
-                        const int n = row0 + st * rps + rb0 + g * RG;
-                        float v = tot[g * RG][m];
-                        if (RG == 2) {
-                            st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(v) * tot[g * RG + RG - 1][m], c.seq);
-                        } else if (e.kind == EPI_RESID) {
-                            st_ll(e.out + (size_t)m * e.out_stride + n, resid + v, c.seq);
-                        } else {
-                            if (e.bias) v += __ldg(e.bias + n);
-                            st_ll(e.out + (size_t)m * e.out_stride + n, v, c.seq);
-                            if (e.kind == EPI_LOGITS) e.plain[n] = v;
-                        }
-                    }
-                }
-        }
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.sh->empty[ast % FK_STAGES]);
-    }
-    c.stage_ctr += nst;
-}
-
-// generic fallback: x read from smem inside the loop (any K % 256 == 0, M <= 2), one row group per warp turn
-template <int RG>
-LQT_DEVINL void gemv_smem(FkCtx& c, int K, int M, int row0, int nrows, const FkEpi& e) {
-    const int KC = K >> 8, Kpad4 = K >> 2;
-    const float4* xs4 = reinterpret_cast<const float4*>(c.xs);
-    const int rps = rows_per_stage(K, RG);
-    const int nst = (nrows + rps - 1) / rps;
-    for (int st = 0; st < nst; ++st) {
-        const unsigned ast = c.stage_ctr + st;
-        wait_full(c, ast);
-        if (st == 0) fk_mark(c, 5);
-        const unsigned char* base = c.ring + (size_t)(ast % FK_STAGES) * FK_STAGE_BYTES;
-        const int rs = min(rps, nrows - st * rps);
-        for (int g = (c.warp + FK_CWARPS - (st & (FK_CWARPS - 1))) & (FK_CWARPS - 1); g * RG < rs; g += FK_CWARPS) {
-            const int n = row0 + st * rps + g * RG;
-            float resid = 0.f;
-            if (e.kind == EPI_RESID && c.lane < M) resid = epi_resid(e, c.lane, n);
-            float acc[RG][2];
-#pragma unroll
-            for (int r = 0; r < RG; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
-            for (int j = 0; j < KC; ++j) {
-                const float4 a0 = xs4[j * 64 + c.lane], b0 = xs4[j * 64 + 32 + c.lane];
-                float4 a1 = a0, b1 = b0;
-                if (M > 1) { a1 = xs4[Kpad4 + j * 64 + c.lane]; b1 = xs4[Kpad4 + j * 64 + 32 + c.lane]; }
-#pragma unroll
-                for (int r = 0; r < RG; ++r) {
-                    const uint4 w = lds128(base + (size_t)(g * RG + r) * ((size_t)K * 2) + c.lane * 16 + j * 512);
-                    acc[r][0] = dot8(w, a0, b0, acc[r][0]);
-                    if (M > 1) acc[r][1] = dot8(w, a1, b1, acc[r][1]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < RG; ++r) { acc[r][0] = warp_sum(acc[r][0]); acc[r][1] = warp_sum(acc[r][1]); }
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                if (c.lane == m && m < M) {
-                    float v = acc[0][m];
+                for (int m = 0; m < M; ++m)
+                    if (c.lane == r * M + m) { mine = tot[r][m]; partner = tot[(r + 1) & (FK_RB - 1)][m]; }
+            if (c.lane < FK_RB * M) {
+                const int r = c.lane / M, m = c.lane - r * M;
+                const int n = row0 + st * rps + rb0 + r;
+                if (rb0 + r < rs) {
                     if (RG == 2) {
-                        st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(v) * acc[RG - 1][m], c.seq);
+                        if ((r & 1) == 0) st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(mine) * partner, c.seq);
                     } else if (e.kind == EPI_RESID) {
-                        st_ll(e.out + (size_t)m * e.out_stride + n, resid + v, c.seq);
+                        st_ll(e.out + (size_t)m * e.out_stride + n, resid + mine, c.seq);
                     } else {
+                        float v = mine;
                         if (e.bias) v += __ldg(e.bias + n);
                         st_ll(e.out + (size_t)m * e.out_stride + n, v, c.seq);
                         if (e.kind == EPI_LOGITS) e.plain[n] = v;
@@ -560,43 +562,13 @@ LQT_DEVINL void gemv_smem(FkCtx& c, int K, int M, int row0, int nrows, const FkE
 
 LQT_DEVINL void gemv_phase(FkCtx& c, int K, int M, int RG, int row0, int nrows, const FkEpi& e) {
     if (nrows <= 0) return;
-    const int KC = K >> 8;
-    if (RG == 2) {                      // SwiGLU pairs: K = hidden
-        if (M == 1) {
-            switch (KC) {
-                case 1: gemv_reg<1, 1, 2, 4>(c, row0, nrows, e); return;
-                case 4: gemv_reg<4, 1, 2, 4>(c, row0, nrows, e); return;
-                case 8: gemv_reg<8, 1, 2, 2>(c, row0, nrows, e); return;
-                default: break;
-            }
-        } else {
-            switch (KC) {
-                case 1: gemv_reg<1, 2, 2, 4>(c, row0, nrows, e); return;
-                case 4: gemv_reg<4, 2, 2, 2>(c, row0, nrows, e); return;
-                default: break;
-            }
-        }
-        gemv_smem<2>(c, K, M, row0, nrows, e);
-        return;
-    }
-    if (M == 1) {
-        switch (KC) {
-            case 1:  gemv_reg<1, 1, 1, 4>(c, row0, nrows, e); return;
-            case 2:  gemv_reg<2, 1, 1, 4>(c, row0, nrows, e); return;
-            case 4:  gemv_reg<4, 1, 1, 4>(c, row0, nrows, e); return;
-            case 8:  gemv_reg<8, 1, 1, 2>(c, row0, nrows, e); return;
-            case 12: gemv_reg<12, 1, 1, 2>(c, row0, nrows, e); return;
-            default: break;
-        }
+    if ((K & 1023) == 0) {
+        if (M == 1) gemv_seg<4, 1>(c, K, RG, row0, nrows, e); else gemv_seg<4, 2>(c, K, RG, row0, nrows, e);
+    } else if ((K & 511) == 0) {
+        if (M == 1) gemv_seg<2, 1>(c, K, RG, row0, nrows, e); else gemv_seg<2, 2>(c, K, RG, row0, nrows, e);
     } else {
-        switch (KC) {
-            case 1: gemv_reg<1, 2, 1, 4>(c, row0, nrows, e); return;
-            case 2: gemv_reg<2, 2, 1, 4>(c, row0, nrows, e); return;
-            case 4: gemv_reg<4, 2, 1, 2>(c, row0, nrows, e); return;
-            default: break;
-        }
+        if (M == 1) gemv_seg<1, 1>(c, K, RG, row0, nrows, e); else gemv_seg<1, 2>(c, K, RG, row0, nrows, e);
     }
-    gemv_smem<1>(c, K, M, row0, nrows, e);
 }
 
 // ------------------------------------------------------------------------------------------------
