@@ -127,6 +127,7 @@ struct lqt_engine {
     std::vector<void*> fk_allocs;             // regrouped weights, layer tables, activation buffers
     FkStack fk_talker{}, fk_cp{};
     std::vector<FkLayer> fk_tl, fk_cl;
+    const bf16 *fk_t_head = nullptr, *fk_c_heads = nullptr, *fk_c_inproj = nullptr; long long fk_c_head_stride = 0;
     uint2* fk_arena = nullptr; size_t fk_arena_words = 0;     // all LL exchange buffers (zeroed at every launch)
     uint2 *fk_pa = nullptr, *fk_cxin = nullptr, *fk_logits_ll = nullptr, *fk_clogits_ll = nullptr;
     unsigned* fk_ctrl = nullptr;
@@ -778,21 +779,32 @@ bool load_vocoder_weights(lqt_engine* h) {
 // ------------------------------------------------------------------------------------------------
 // persistent frame kernel: one-time weight regrouping, tables, launch
 // ------------------------------------------------------------------------------------------------
-// Wo [H][n_kv*gK] -> [n_kv][H][gK]  (each CTA's O-projection slice becomes one contiguous block)
-__global__ void regroup_wo_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int H, int n_kv, int gK) {
-    const long long n = (long long)H * n_kv * gK;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % gK); const long long r = i / gK; const int row = (int)(r % H); const int g = (int)(r / H);
-        dst[i] = src[(size_t)row * (n_kv * gK) + (size_t)g * gK + c];
-    }
-}
-// gate [I][H], up [I][H] -> [2I][H] with gate row n at 2n and up row n at 2n+1
-__global__ void interleave_gu_kernel(const bf16* __restrict__ g, const bf16* __restrict__ u, bf16* __restrict__ dst, int I, int H) {
-    const long long n = (long long)2 * I * H;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % H); const long long r = i / H;
-        const bf16* src = (r & 1) ? u : g;
-        dst[i] = src[(size_t)(r >> 1) * H + c];
+// Per-CTA weight images in canonical K-major SWIZZLE_128B tile layout (see frame_kernel.cuh FkLayer).
+struct ImgJob {
+    const bf16* src0; const bf16* src1;   // mode 1: gate / up
+    bf16* dst;
+    int N, K, RG, mode;                   // mode 0 flat rows, 1 gate/up interleave, 2 O-projection sliced by kv group
+    int src_stride, n_kv, rmax8;
+};
+__global__ void fk_build_image_kernel(const ImgJob j) {
+    const int c = blockIdx.x, ncta = gridDim.x;
+    const FkSlice sl = (j.mode == 2) ? group_slice(j.N, c, ncta, j.n_kv) : flat_slice(j.N, j.RG, c, ncta);
+    const int r8 = (sl.nrows + 7) & ~7, ntile = j.K >> 6;
+    const long long nchunk = (long long)ntile * r8 * 8;
+    bf16* dst = j.dst + (size_t)c * j.rmax8 * j.K;
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < nchunk; i += (long long)gridDim.y * blockDim.x) {
+        const int tile = (int)(i / (r8 * 8)), rem = (int)(i % (r8 * 8)), r = rem >> 3, pc = rem & 7;
+        const int k0 = tile * 64 + ((pc ^ (r & 7)) << 3);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < sl.nrows) {
+            const int n = sl.row0 + r;
+            const bf16* src;
+            if (j.mode == 1) src = ((n & 1) ? j.src1 : j.src0) + (size_t)(n >> 1) * j.src_stride + k0;
+            else if (j.mode == 2) src = j.src0 + (size_t)n * j.src_stride + (size_t)(c % j.n_kv) * j.K + k0;
+            else src = j.src0 + (size_t)n * j.src_stride + k0;
+            v = *reinterpret_cast<const uint4*>(src);
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)tile * r8 * 64 + (size_t)r * 64 + pc * 8) = v;
     }
 }
 
@@ -804,16 +816,39 @@ int fk_alloc(lqt_engine* h, T** p, size_t n) {
     return 0;
 }
 
+int fk_rmax8(int N, int RG, int mode, int n_kv, int ncta) {       // must match make_desc() in frame_kernel.cuh
+    int rmax;
+    if (mode == 2) { const int ns = ncta / n_kv; rmax = (N + ns - 1) / ns; }
+    else rmax = ((N / RG + ncta - 1) / ncta) * RG;
+    return (rmax + 7) & ~7;
+}
+
+// builds one image; returns its device pointer (nullptr on failure)
+bf16* fk_image(lqt_engine* h, const bf16* src0, const bf16* src1, int N, int K, int RG, int mode, int src_stride, int n_kv,
+               size_t* elems_out = nullptr) {
+    ImgJob j{};
+    j.src0 = src0; j.src1 = src1; j.N = N; j.K = K; j.RG = RG; j.mode = mode; j.src_stride = src_stride; j.n_kv = n_kv;
+    j.rmax8 = fk_rmax8(N, RG, mode, n_kv, h->num_sms);
+    const size_t elems = (size_t)h->num_sms * j.rmax8 * K;
+    bf16* dst = nullptr;
+    if (fk_alloc(h, &dst, elems)) return nullptr;
+    j.dst = dst;
+    fk_build_image_kernel<<<dim3(h->num_sms, 4), 256, 0, h->stream>>>(j);
+    if (elems_out) *elems_out = elems;
+    return dst;
+}
+
 int fk_build_stack(lqt_engine* h, const std::vector<LayerW>& layers, int H, int heads, int kv_heads, int inter,
                    const float* cosr, const float* sinr, const float* final_norm, FkStack* out, std::vector<FkLayer>* tab_out) {
     const int gK = (heads / kv_heads) * ATT_D, qkv_dim = (heads + 2 * kv_heads) * ATT_D;
     std::vector<FkLayer> tab(layers.size());
     for (size_t l = 0; l < layers.size(); ++l) {
-        bf16 *wo_g = nullptr, *wgu = nullptr;
-        if (fk_alloc(h, &wo_g, (size_t)H * kv_heads * gK) || fk_alloc(h, &wgu, (size_t)2 * inter * H)) return 1;
-        regroup_wo_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(layers[l].wo, wo_g, H, kv_heads, gK);
-        interleave_gu_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(layers[l].wgate, layers[l].wup, wgu, inter, H);
-        tab[l] = FkLayer{layers[l].wqkv, wo_g, wgu, layers[l].wdown, layers[l].ln1, layers[l].ln2, layers[l].qnorm, layers[l].knorm};
+        const bf16* wqkv = fk_image(h, layers[l].wqkv, nullptr, qkv_dim, H, 1, 0, H, kv_heads);
+        const bf16* wo = fk_image(h, layers[l].wo, nullptr, H, gK, 1, 2, kv_heads * gK, kv_heads);
+        const bf16* wgu = fk_image(h, layers[l].wgate, layers[l].wup, 2 * inter, H, 2, 1, H, kv_heads);
+        const bf16* wdown = fk_image(h, layers[l].wdown, nullptr, H, inter, 1, 0, inter, kv_heads);
+        if (!wqkv || !wo || !wgu || !wdown) return 1;
+        tab[l] = FkLayer{wqkv, wo, wgu, wdown, layers[l].ln1, layers[l].ln2, layers[l].qnorm, layers[l].knorm};
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -821,27 +856,53 @@ int fk_build_stack(lqt_engine* h, const std::vector<LayerW>& layers, int H, int 
     FkStack S{};
     S.n_layers = (int)layers.size(); S.H = H; S.heads = heads; S.kv_heads = kv_heads; S.inter = inter;
     S.cos = cosr; S.sin = sinr; S.final_norm = final_norm;
-    (void)qkv_dim;
     *out = S;
     return 0;
 }
 
 int fk_init(lqt_engine* h) {
     const Spec& s = h->sp;
-    auto chk = [&](int K, int RG, const char* what) -> bool {
-        if (K % 256 != 0 || (size_t)RG * K * 2 > (size_t)FK_STAGE_BYTES) {
-            h->err = std::string("frame kernel: unsupported dimension for ") + what; return false;
-        }
+    const int maxK = std::max(std::max(s.hidden, s.inter), std::max(s.cp_hidden, s.cp_inter));
+    auto chk = [&](int K, const char* what) -> bool {
+        if (K % 256 != 0 || K > 3072) { h->err = std::string("frame kernel: unsupported dimension for ") + what; return false; }
         return true;
     };
-    if (!chk(s.hidden, 2, "hidden") || !chk(s.inter, 1, "inter") || !chk(s.cp_hidden, 2, "cp_hidden") || !chk(s.cp_inter, 1, "cp_inter"))
+    if (!chk(s.hidden, "hidden") || !chk(s.inter, "inter") || !chk(s.cp_hidden, "cp_hidden") || !chk(s.cp_inter, "cp_inter"))
         return 1;
+    {   // every CTA slice must fit two 64-row MMA blocks and one ring stage per tile
+        const int nc = h->num_sms;
+        const int worst = std::max(std::max(fk_rmax8(2 * s.inter, 2, 1, s.kv_heads, nc), fk_rmax8((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc)),
+                                   std::max(fk_rmax8(s.hidden, 1, 2, s.kv_heads, nc), fk_rmax8(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc)));
+        const int worst_c = std::max(fk_rmax8(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax8((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
+        if (std::max(worst, worst_c) > 128) { h->err = "frame kernel: too many rows per SM"; return 1; }
+    }
     if (s.kv_heads > FK_NGRP_MAX || s.cp_kv_heads > FK_NGRP_MAX || s.kv_heads != s.cp_kv_heads) { h->err = "frame kernel: kv head count"; return 1; }
     if (s.cp_steps + 2 > FK_CP_POS) { h->err = "frame kernel: cp_steps"; return 1; }
     if (h->num_sms < s.kv_heads) { h->err = "frame kernel: too few SMs"; return 1; }
     if (s.layers > FK_MAX_TLAYERS || s.cp_layers > FK_MAX_CLAYERS) { h->err = "frame kernel: too many layers"; return 1; }
     if (fk_build_stack(h, h->tl, s.hidden, s.heads, s.kv_heads, s.inter, h->t_cos, h->t_sin, h->t_norm, &h->fk_talker, &h->fk_tl)) return 1;
     if (fk_build_stack(h, h->cl, s.cp_hidden, s.cp_heads, s.cp_kv_heads, s.cp_inter, h->c_cos, h->c_sin, h->c_norm, &h->fk_cp, &h->fk_cl)) return 1;
+    {   // head / in_proj images
+        h->fk_t_head = fk_image(h, h->t_head, nullptr, s.vocab, s.hidden, 1, 0, s.hidden, s.kv_heads);
+        if (!h->fk_t_head) return 1;
+        const int r8 = fk_rmax8(s.cp_vocab, 1, 0, s.cp_kv_heads, h->num_sms);
+        h->fk_c_head_stride = (long long)h->num_sms * r8 * s.cp_hidden;
+        bf16* all = nullptr;
+        if (fk_alloc(h, &all, (size_t)h->fk_c_head_stride * s.cp_steps)) return 1;
+        for (int j = 0; j < s.cp_steps; ++j) {
+            ImgJob job{};
+            job.src0 = h->c_heads + (size_t)j * s.cp_vocab * s.cp_hidden; job.N = s.cp_vocab; job.K = s.cp_hidden; job.RG = 1; job.mode = 0;
+            job.src_stride = s.cp_hidden; job.n_kv = s.cp_kv_heads; job.rmax8 = r8; job.dst = all + (size_t)j * h->fk_c_head_stride;
+            fk_build_image_kernel<<<dim3(h->num_sms, 4), 256, 0, h->stream>>>(job);
+        }
+        h->fk_c_heads = all;
+        if (h->c_inproj_w) {
+            h->fk_c_inproj = fk_image(h, h->c_inproj_w, nullptr, s.cp_hidden, s.hidden, 1, 0, s.hidden, s.cp_kv_heads);
+            if (!h->fk_c_inproj) return 1;
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
+    }
     {   // one arena for every LL exchange buffer
         auto al = [](size_t n) { return (n + 31) & ~(size_t)31; };
         const size_t qkv_t = (size_t)(s.heads + 2 * s.kv_heads) * ATT_D, qkv_c = (size_t)(s.cp_heads + 2 * s.cp_kv_heads) * ATT_D;
@@ -861,14 +922,9 @@ int fk_init(lqt_engine* h) {
     if (fk_alloc(h, &h->fk_ctrl, 2)) return 1;
     CK(cudaMallocHost((void**)&h->fk_ctrl_host, 2 * sizeof(unsigned)));
     const int maxV = std::max(s.vocab, s.cp_vocab);
-    auto pad = [](int k) { return (k + 255) & ~255; };
-    int xs_floats = std::max(pad(std::max(s.hidden, s.inter)), 2 * pad(std::max(std::max(s.cp_hidden, s.cp_inter), 256)));
-    xs_floats = std::max(xs_floats, 2 * pad(s.hidden));
     if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV & 3)) { h->err = "frame kernel: hidden > 2048 or vocab % 4 != 0"; return 1; }
-    const int res0_floats = std::max(s.hidden, 2 * s.hidden * (s.hidden == s.cp_hidden ? 1 : 1));
-    const FkSmemLayout L = fk_smem_layout(maxV, xs_floats, s.hidden, 2 * s.hidden);
-    (void)res0_floats;
-    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.xs_bytes = (unsigned)L.xs_bytes;
+    const FkSmemLayout L = fk_smem_layout(maxV, maxK, s.hidden, 2 * s.hidden);
+    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.att = (unsigned)L.att;
     h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.res0 = (unsigned)L.res0; h->fk_so.lh = (unsigned)L.lh;
     h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
     h->fk_smem = L.total;
@@ -887,9 +943,9 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.talker = h->fk_talker; p.cp = h->fk_cp;
     for (size_t l = 0; l < h->fk_tl.size(); ++l) p.t_layers[l] = h->fk_tl[l];
     for (size_t l = 0; l < h->fk_cl.size(); ++l) p.c_layers[l] = h->fk_cl[l];
-    p.t_head = h->t_head; p.vocab = s.vocab;
-    p.c_heads = h->c_heads; p.cp_vocab = s.cp_vocab; p.cp_steps = s.cp_steps;
-    p.c_inproj_w = h->c_inproj_w; p.c_inproj_b = h->c_inproj_b; p.cxin = h->fk_cxin;
+    p.t_head = h->fk_t_head; p.vocab = s.vocab;
+    p.c_heads = h->fk_c_heads; p.cp_vocab = s.cp_vocab; p.cp_steps = s.cp_steps; p.c_head_stride = h->fk_c_head_stride;
+    p.c_inproj_w = h->fk_c_inproj; p.c_inproj_b = h->c_inproj_b; p.cxin = h->fk_cxin;
     p.eps = s.rms_eps;
     p.kv_pool = h->kv_pool; p.page_table = h->page_tables + (size_t)slot * h->max_pages; p.page_shift = KV_PAGE_SHIFT;
     p.page_stride = (long long)s.layers * 2 * s.kv_heads * KV_PAGE * ATT_D; p.kv_f32 = h->kv_f32 ? 1 : 0;

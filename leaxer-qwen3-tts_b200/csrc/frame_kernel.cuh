@@ -9,8 +9,14 @@
 //     slice of every matrix into a shared-memory ring with 1-D TMA bulk copies
 //     (cp.async.bulk + mbarrier complete_tx), running AHEAD of the math across phase boundaries;
 //   * warps 0-7 (consumers) run the phases: assemble the input vector (RMSNorm / attention / partial
-//     sums), dot it with the rows in the ring (x in registers, weights read once from smem) and
-//     publish their few outputs;
+//     sums) and publish the outputs. The matrix-vector product itself runs on the 5th-gen tensor
+//     cores: the weights are stored in HBM per CTA as ready-made K-major SWIZZLE_128B tiles, so the
+//     bulk copies land operand A in canonical UMMA layout; the activation vector is split exactly
+//     into three bf16 terms (x = hi + mid + lo, 24 mantissa bits) that form operand B (N = 8
+//     columns); ONE thread issues K/16 tcgen05.mma (M=64, N=8, fp32 accumulate in TMEM) per phase,
+//     tcgen05.commit frees the ring slots, and 64-128 threads read their row back with tcgen05.ld and
+//     publish it in parallel. (The fp32 FMA version of this loop was issue/latency bound: 2-4 us
+//     per phase with 8 warps.);
 //   * there is NO grid barrier. Activations travel between CTAs as 8-byte (value, sequence) pairs
 //     written with one store each ("LL" exchange, as in NCCL's low-latency protocol): a reader polls
 //     the data itself until every word carries the sequence number of the phase that produces it.
@@ -35,7 +41,7 @@ constexpr int FK_CWARPS = 8;
 constexpr int FK_CTHREADS = FK_CWARPS * 32;       // consumer threads
 constexpr int FK_THREADS = FK_CTHREADS + 32;      // + one producer warp
 constexpr int FK_STAGE_BYTES = 16 * 1024;
-constexpr int FK_STAGES = 9;                      // 144 KB weight ring per SM
+constexpr int FK_STAGES = 8;                      // 128 KB weight ring per SM
 constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_MAXV = 4096;
@@ -43,11 +49,15 @@ constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity 
 constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
 constexpr unsigned long long FK_SPIN_LIMIT = 6000000000ull;   // ~3 s of SM clocks: abort, never hang
 
+// Weight "images": for every matrix and every CTA c, the rows this CTA owns (padded to a multiple of 8
+// with zero rows) as K/64 tiles of [R8 rows][128 bytes], each tile in the canonical K-major
+// SWIZZLE_128B layout (16-byte chunk index XOR (row & 7)); CTA c's image starts at c * rmax8 * K
+// elements. Built once at engine init (fk_build_image_kernel) from the .lqw tensors.
 struct FkLayer {
-    const bf16_t* wqkv;     // [q_dim + 2 kv_dim][H]
-    const bf16_t* wo_g;     // [n_kv][H][rep*128]   (O-projection regrouped by kv group)
-    const bf16_t* wgu;      // [2*inter][H]         (gate row n, up row n interleaved)
-    const bf16_t* wdown;    // [H][inter]
+    const bf16_t* wqkv;     // image of [q_dim + 2 kv_dim][H]
+    const bf16_t* wo_g;     // image of the O-projection sliced by kv group (K = rep*128)
+    const bf16_t* wgu;      // image of gate/up interleaved (row 2n = gate n, 2n+1 = up n)
+    const bf16_t* wdown;    // image of [H][inter]
     const float *ln1, *ln2, *qnorm, *knorm;
 };
 
@@ -61,8 +71,8 @@ struct FkParams {
     FkStack talker, cp;
     FkLayer t_layers[FK_MAX_TLAYERS];     // in the kernel-parameter constant bank: no load latency
     FkLayer c_layers[FK_MAX_CLAYERS];
-    const bf16_t* t_head; int vocab;
-    const bf16_t* c_heads; int cp_vocab, cp_steps;
+    const bf16_t* t_head; int vocab;          // images
+    const bf16_t* c_heads; int cp_vocab, cp_steps; long long c_head_stride;   // image elements per predictor head
     const bf16_t* c_inproj_w; const float* c_inproj_b; uint2* cxin;     // 1.7B: talker width -> predictor width (LL [2][Hc])
     float eps;
     void* kv_pool; const int* page_table; int page_shift; long long page_stride; int kv_f32;
@@ -116,6 +126,34 @@ LQT_DEVINL uint4 lds128(const void* p) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
     return r;
 }
+// ---- tcgen05 / TMEM ----
+LQT_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+LQT_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+LQT_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100): start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 |
+// version 1 <<46 | layout SWIZZLE_128B (2) << 61   (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
+LQT_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, N = 8, M = 64 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t FK_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 17) | (4u << 24);
+LQT_DEVINL void umma_bf16_m64n8k16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(FK_IDESC), "r"(accumulate) : "memory");
+}
+LQT_DEVINL void umma_commit(uint64_t* bar) {      // arrives on the mbarrier when all prior tcgen05.mma of this thread are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+LQT_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {     // this thread's TMEM lane, 16 consecutive columns
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // LL exchange: 8-byte (value, sequence) words. volatile accesses always go to L2 (the coherence point).
 LQT_DEVINL void st_ll(uint2* p, float v, unsigned seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
@@ -134,7 +172,13 @@ LQT_DEVINL uint2 ld_ll1(const uint2* p) {
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------
-struct FkDesc { int row0, nrows, K, RG; };     // this CTA's weight slice of one phase kind
+struct FkDesc {                 // this CTA's weight slice of one phase kind
+    int row0, nrows, K, RG;
+    int r8;                     // rows padded to a multiple of 8 (tile = r8 rows x 128 bytes)
+    int tps;                    // tiles (64-element K chunks) per ring stage
+    unsigned img_off;           // element offset of this CTA's image inside the matrix image
+    int pad_;
+};
 struct FkShared {
     uint64_t full[FK_STAGES];
     uint64_t empty[FK_STAGES];
@@ -147,20 +191,52 @@ struct FkShared {
     int redi[FK_CWARPS];
     uint32_t sel_prefix; int sel_k;
     int tok; float fsum;
+    uint64_t mma_done;            // tcgen05.commit of the last MMA of a phase arrives here
+    uint32_t tmem_base;           // written by tcgen05.alloc
     FkDesc desc[2][10];           // [stack][phase kind]
 };
 
-// x vectors live in smem as float4, permuted inside every 256-float chunk so that a lane's two
-// float4 reads (elements lane*8 .. lane*8+7 of the chunk) are bank-conflict free.
-LQT_DEVINL int xs_perm4(int k4) { return (k4 & ~63) + ((k4 & 1) << 5) + ((k4 & 63) >> 1); }
-LQT_DEVINL int xs_idx(int k) { return xs_perm4(k >> 2) * 4 + (k & 3); }
+// Operand B of the tensor-core GEMV. Row n = 3*m + j of the 8-row tile holds term j (hi, mid, lo) of
+// activation row m; element k lives in tile k/64 at byte n*128 + (((k%64)/8) ^ n)*16 + (k%8)*2.
+LQT_DEVINL void bf16_split3(float x, unsigned short& h, unsigned short& m, unsigned short& l) {
+    const __nv_bfloat16 bh = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(bh);
+    const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(bm);
+    const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
+    h = __bfloat16_as_ushort(bh); m = __bfloat16_as_ushort(bm); l = __bfloat16_as_ushort(bl);
+}
+LQT_DEVINL void xb_store4(unsigned char* bt, int m, int k4, const float4& v) {     // elements 4*k4 .. 4*k4+3 of row m
+    const int k = k4 << 2, tile = k >> 6, c16 = (k & 63) >> 3, e0 = k & 7;
+    unsigned short h[4], md[4], l[4];
+    bf16_split3(v.x, h[0], md[0], l[0]); bf16_split3(v.y, h[1], md[1], l[1]);
+    bf16_split3(v.z, h[2], md[2], l[2]); bf16_split3(v.w, h[3], md[3], l[3]);
+    unsigned char* base = bt + (size_t)tile * 1024 + e0 * 2;
+    const int n0 = 3 * m;
+    *reinterpret_cast<uint2*>(base + (n0 + 0) * 128 + ((c16 ^ (n0 + 0)) << 4)) =
+        make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(base + (n0 + 1) * 128 + ((c16 ^ (n0 + 1)) << 4)) =
+        make_uint2((uint32_t)md[0] | ((uint32_t)md[1] << 16), (uint32_t)md[2] | ((uint32_t)md[3] << 16));
+    *reinterpret_cast<uint2*>(base + (n0 + 2) * 128 + ((c16 ^ (n0 + 2)) << 4)) =
+        make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+LQT_DEVINL void xb_store1(unsigned char* bt, int m, int k, float v) {
+    const int tile = k >> 6, c16 = (k & 63) >> 3, e = k & 7;
+    unsigned short h, md, l;
+    bf16_split3(v, h, md, l);
+    unsigned char* base = bt + (size_t)tile * 1024 + e * 2;
+    const int n0 = 3 * m;
+    *reinterpret_cast<unsigned short*>(base + (n0 + 0) * 128 + ((c16 ^ (n0 + 0)) << 4)) = h;
+    *reinterpret_cast<unsigned short*>(base + (n0 + 1) * 128 + ((c16 ^ (n0 + 1)) << 4)) = md;
+    *reinterpret_cast<unsigned short*>(base + (n0 + 2) * 128 + ((c16 ^ (n0 + 2)) << 4)) = l;
+}
 
 struct FkCtx {
     const FkParams* p;
     FkShared* sh;
     unsigned char* ring;      // FK_STAGES * FK_STAGE_BYTES
-    float* xs;                // x staging: [M][Kpad] (permuted)        | aliases the sampler scratch
-    float* att;               // attention scratch                        |
+    unsigned char* bt;        // operand B: x as bf16 (hi, mid, lo) per row, K-major SWIZZLE_128B, K/64 tiles of 8 x 128 B | aliases the sampler scratch
+    float* att;               // attention scratch
     float* nxt;               // running next talker input [H]
     float* res0;              // layer-0 input rows of the current pass [M][H0] (also its residual)
     float* lh;                // talker last_hidden [H] (code-predictor row 0, src/tts_onnx.cpp:859)
@@ -168,6 +244,8 @@ struct FkCtx {
     int cta, ncta;
     unsigned seq;             // number of the current phase (1, 2, ...): tag of everything it publishes
     unsigned stage_ctr;       // ring stages consumed so far
+    unsigned mma_phase;       // parity of the next wait on sh->mma_done
+    uint32_t tmem;            // TMEM base address (lane 0, column 0) of the 32 allocated columns
     bool aborted;
     unsigned long long* dbg; int dbg_n, dbg_cap, dbg_tag;   // dbg_tag = (stack << 9) | (kind << 4) of the current phase
 };
@@ -200,25 +278,28 @@ LQT_DEVINL FkSlice group_slice(int Nout, int cta, int ncta, int n_kv) {
     const int r0 = (int)(((unsigned)s * (unsigned)Nout) / (unsigned)ns), r1 = (int)(((unsigned)(s + 1) * (unsigned)Nout) / (unsigned)ns);
     return FkSlice{r0, r1 - r0};
 }
-LQT_DEVINL int rows_per_stage(int K, int RG) {
-    int r = FK_STAGE_BYTES / (K * 2);
-    r = (r / RG) * RG;
-    return r < RG ? RG : r;       // host guarantees RG * K * 2 <= FK_STAGE_BYTES
-}
 LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, int ncta) {
     const FkStack& S = is_cp ? p.cp : p.talker;
     const int H = S.H, qkv_dim = (S.heads + 2 * S.kv_heads) * ATT_D, gK = (S.heads / S.kv_heads) * ATT_D;
-    FkSlice s{0, 0}; int K = 256, RG = 1;
+    FkSlice s{0, 0}; int K = 256, RG = 1, rmax = 0;
+    auto flat_max = [&](int N, int rg) { return ((N / rg + ncta - 1) / ncta) * rg; };
     switch (kind) {
-        case FKT_INPROJ: s = flat_slice(H, 1, cta, ncta); K = p.talker.H; break;
-        case FKT_A: s = flat_slice(qkv_dim, 1, cta, ncta); K = H; break;
-        case FKT_C: s = group_slice(H, cta, ncta, S.kv_heads); K = gK; break;
-        case FKT_D: s = flat_slice(2 * S.inter, 2, cta, ncta); K = H; RG = 2; break;
-        case FKT_E: s = flat_slice(H, 1, cta, ncta); K = S.inter; break;
-        case FKT_HEAD: s = flat_slice(is_cp ? p.cp_vocab : p.vocab, 1, cta, ncta); K = H; break;
+        case FKT_INPROJ: s = flat_slice(H, 1, cta, ncta); K = p.talker.H; rmax = flat_max(H, 1); break;
+        case FKT_A: s = flat_slice(qkv_dim, 1, cta, ncta); K = H; rmax = flat_max(qkv_dim, 1); break;
+        case FKT_C: s = group_slice(H, cta, ncta, S.kv_heads); K = gK; rmax = (H + ncta / S.kv_heads - 1) / (ncta / S.kv_heads); break;
+        case FKT_D: s = flat_slice(2 * S.inter, 2, cta, ncta); K = H; RG = 2; rmax = flat_max(2 * S.inter, 2); break;
+        case FKT_E: s = flat_slice(H, 1, cta, ncta); K = S.inter; rmax = flat_max(H, 1); break;
+        case FKT_HEAD: { const int V = is_cp ? p.cp_vocab : p.vocab; s = flat_slice(V, 1, cta, ncta); K = H; rmax = flat_max(V, 1); break; }
         default: break;
     }
-    return FkDesc{s.row0, s.nrows, K, RG};
+    FkDesc d;
+    d.row0 = s.row0; d.nrows = s.nrows; d.K = K; d.RG = RG;
+    d.r8 = (s.nrows + 7) & ~7;
+    const int tile_bytes = d.r8 * 128;
+    d.tps = tile_bytes > 0 ? max(1, FK_STAGE_BYTES / tile_bytes) : 1;
+    d.img_off = (unsigned)cta * (unsigned)((rmax + 7) & ~7) * (unsigned)K;
+    d.pad_ = 0;
+    return d;
 }
 
 // flat schedule of one token pass: [in_proj] + n_layers x (A qkv, B attention, C o-proj, D gate/up, E down) + [head]
@@ -359,54 +440,52 @@ LQT_DEVINL float4 stage_fetch(FkCtx& c, const FkStage& s, int m, int k4, int K, 
 }
 
 LQT_DEVINL void stage_rows(FkCtx& c, const FkStage& s, int M, int K, unsigned want, float eps) {
-    const int K4 = K >> 2, Kpad4 = ((K + 255) & ~255) >> 2;
-    float4* xs4 = reinterpret_cast<float4*>(c.xs);
+    const int K4 = K >> 2;
     if (s.part) ll_probe(c, s.part, M * s.n_part * K, want);
     else if (s.ll && !s.verified) ll_probe(c, s.ll, (M - 1) * s.ll_stride + K, want);
     const bool norm = s.nw != nullptr;         // norm path: K = hidden <= 2048 -> at most 2 float4 per thread per row,
-    float4 v00, v01, v10, v11;                 // kept in registers until rstd is known (xs is written once)
+    float4 v00, v01, v10, v11;                 // kept in registers until rstd is known (operand B is written once)
     v00 = v01 = v10 = v11 = make_float4(0.f, 0.f, 0.f, 0.f);
     float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
     for (int m = 0; m < M; ++m) {
 #pragma unroll 1
-        for (int k4 = c.tid, i = 0; k4 < Kpad4; k4 += FK_CTHREADS, ++i) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k4 < K4) a = stage_fetch(c, s, m, k4, K, want);
+        for (int k4 = c.tid, i = 0; k4 < K4; k4 += FK_CTHREADS, ++i) {
+            const float4 a = stage_fetch(c, s, m, k4, K, want);
             if (norm) {
                 const float q = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
                 if (m == 0) { ss0 += q; if (i == 0) v00 = a; else v01 = a; }
                 else        { ss1 += q; if (i == 0) v10 = a; else v11 = a; }
             } else {
-                xs4[m * Kpad4 + xs_perm4(k4)] = a;
+                xb_store4(c.bt, m, k4, a);
             }
         }
     }
-    if (!norm) { csync(); return; }
-    ss0 = warp_sum(ss0); ss1 = warp_sum(ss1);
-    if (c.lane == 0) { c.sh->redf[c.warp][0] = ss0; c.sh->redf[c.warp][1] = ss1; }
-    csync();
-    float t0 = 0.f, t1 = 0.f;
+    if (norm) {
+        ss0 = warp_sum(ss0); ss1 = warp_sum(ss1);
+        if (c.lane == 0) { c.sh->redf[c.warp][0] = ss0; c.sh->redf[c.warp][1] = ss1; }
+        csync();
+        float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-    for (int w2 = 0; w2 < FK_CWARPS; ++w2) { t0 += c.sh->redf[w2][0]; t1 += c.sh->redf[w2][1]; }
-    const float r0 = 1.0f / sqrtf(t0 / (float)K + eps), r1 = 1.0f / sqrtf(t1 / (float)K + eps);
+        for (int w2 = 0; w2 < FK_CWARPS; ++w2) { t0 += c.sh->redf[w2][0]; t1 += c.sh->redf[w2][1]; }
+        const float r0 = 1.0f / sqrtf(t0 / (float)K + eps), r1 = 1.0f / sqrtf(t1 / (float)K + eps);
 #pragma unroll 1
-    for (int m = 0; m < M; ++m) {
+        for (int m = 0; m < M; ++m) {
 #pragma unroll 1
-        for (int k4 = c.tid, i = 0; k4 < Kpad4; k4 += FK_CTHREADS, ++i) {
-            float4 a = (m == 0) ? (i == 0 ? v00 : v01) : (i == 0 ? v10 : v11);
-            const float r = (m == 0) ? r0 : r1;
-            if (k4 < K4) {
+            for (int k4 = c.tid, i = 0; k4 < K4; k4 += FK_CTHREADS, ++i) {
+                float4 a = (m == 0) ? (i == 0 ? v00 : v01) : (i == 0 ? v10 : v11);
+                const float r = (m == 0) ? r0 : r1;
                 const float4 w = __ldg(reinterpret_cast<const float4*>(s.nw) + k4);
                 a.x = (a.x * r) * w.x; a.y = (a.y * r) * w.y; a.z = (a.z * r) * w.z; a.w = (a.w * r) * w.w;
                 if (m == 0) {
                     if (s.copy_sm) reinterpret_cast<float4*>(s.copy_sm)[k4] = a;
                     if (s.copy_gl && c.cta == 0) reinterpret_cast<float4*>(s.copy_gl)[k4] = a;
                 }
+                xb_store4(c.bt, m, k4, a);
             }
-            xs4[m * Kpad4 + xs_perm4(k4)] = a;
         }
     }
+    fence_proxy_async_smem();                  // operand B was written through the generic proxy; the MMA reads it through the async proxy
     csync();
 }
 
@@ -443,110 +522,97 @@ LQT_DEVINL void wait_full(FkCtx& c, unsigned st) {
     }
 }
 
-// two interleaved accumulator chains per dot product
-LQT_DEVINL void dot8x2(const uint4& w, const float4& a, const float4& b, float& acc0, float& acc1) {
-    acc0 = fmaf(bf16lo(w.x), a.x, acc0); acc1 = fmaf(bf16hi(w.x), a.y, acc1);
-    acc0 = fmaf(bf16lo(w.y), a.z, acc0); acc1 = fmaf(bf16hi(w.y), a.w, acc1);
-    acc0 = fmaf(bf16lo(w.z), b.x, acc0); acc1 = fmaf(bf16hi(w.z), b.y, acc1);
-    acc0 = fmaf(bf16lo(w.w), b.z, acc0); acc1 = fmaf(bf16hi(w.w), b.w, acc1);
-}
-
-// ONE compact routine for every matrix (instruction-cache footprint matters: the whole layer loop has
-// to stay resident). K is processed in segments of KC*256 elements whose x values sit in registers;
-// a stage's rows are dealt to warps in batches of 4 rows that one warp processes together (independent
-// accumulator chains, batched shuffles); batches of consecutive stages go to different warps so that
-// several stages are in work at once. RG (1, or 2 = SwiGLU gate/up pairs) only affects the epilogue.
-constexpr int FK_RB = 4;
-template <int KC, int M>
-LQT_DEVINL void gemv_seg(FkCtx& c, int K, int RG, int row0, int nrows, const FkEpi& e) {
-    constexpr int KS = KC * 256;                             // segment length
-    const int nseg = K / KS;
-    const int Kpad4 = K >> 2;
-    const float4* xs4 = reinterpret_cast<const float4*>(c.xs);
-    float4 xa[M][KC], xb[M][KC];
+// Tensor-core GEMV of one phase. Operand A = this CTA's weight tiles as they land in the ring
+// (K/64 tiles of r8 x 128 B, SWIZZLE_128B), operand B = c.bt, D = TMEM columns 0-7 (rows 0-63) and
+// 8-15 (rows 64-127): row r of a 64-row block sits in TMEM lane (r % 16) + 32 * (r / 16).
+// One thread issues everything; tcgen05.commit releases each ring stage and finally signals mma_done.
+// Then thread (warp q < 4, lane l < 16) owns rows 16q + l and 64 + 16q + l and publishes them.
+LQT_DEVINL void gemv_tc(FkCtx& c, const FkDesc& d, int M, const FkEpi& e) {
+    const int ntile = d.K >> 6;
+    const int nst = d.nrows > 0 ? (ntile + d.tps - 1) / d.tps : 0;
+    const bool two = d.r8 > 64;
+    if (nst > 0 && c.tid == 4 * 32) {                       // the MMA issuer: lane 0 of warp 4
+        tc_fence_after();
+        const uint32_t bt_addr = smem_u32(c.bt);
+        const uint32_t tile_bytes = (uint32_t)d.r8 * 128u;
+        int tile = 0;
+#pragma unroll 1
+        for (int st = 0; st < nst; ++st) {
+            const unsigned ast = c.stage_ctr + st, slot = ast % FK_STAGES;
+            wait_full(c, ast);
+            tc_fence_after();
+            const uint32_t a_stage = smem_u32(c.ring + (size_t)slot * FK_STAGE_BYTES);
+            const int nt = min(d.tps, ntile - tile);
+#pragma unroll 1
+            for (int t = 0; t < nt; ++t, ++tile) {
+                const uint32_t a_tile = a_stage + (uint32_t)t * tile_bytes;
+                const uint32_t b_tile = bt_addr + (uint32_t)tile * 1024u;
 #pragma unroll
-    for (int m = 0; m < M; ++m)
-#pragma unroll
-        for (int j = 0; j < KC; ++j) {
-            xa[m][j] = xs4[m * Kpad4 + j * 64 + c.lane];
-            xb[m][j] = xs4[m * Kpad4 + j * 64 + 32 + c.lane];
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t acc = (tile | ks) ? 1u : 0u;
+                    const uint64_t bd = umma_desc_sw128(b_tile + ks * 32);
+                    umma_bf16_m64n8k16(c.tmem, umma_desc_sw128(a_tile + ks * 32), bd, acc);
+                    if (two) umma_bf16_m64n8k16(c.tmem + 8, umma_desc_sw128(a_tile + 8192 + ks * 32), bd, acc);
+                }
+            }
+            umma_commit(&c.sh->empty[slot]);                // ring slot reusable once these MMAs have read it
         }
-    const int rps = rows_per_stage(K, RG);
-    const int nst = (nrows + rps - 1) / rps;
-    const int nbs = (rps + FK_RB - 1) / FK_RB;               // batches per (full) stage
-#pragma unroll 1
-    for (int st = 0; st < nst; ++st) {
-        const unsigned ast = c.stage_ctr + st;
-        wait_full(c, ast);
-        if (st == 0) fk_mark(c, 5);
-        const unsigned char* base = c.ring + (size_t)(ast % FK_STAGES) * FK_STAGE_BYTES;
-        const int rs = min(rps, nrows - st * rps);          // rows in this stage
-#pragma unroll 1
-        for (int b = (c.warp + FK_CWARPS - ((st * nbs) & (FK_CWARPS - 1))) & (FK_CWARPS - 1); b * FK_RB < rs; b += FK_CWARPS) {
-            const int rb0 = b * FK_RB;                       // first row of the batch inside the stage
-            // residual values for the outputs this lane will publish (latency hidden behind the dots)
-            float resid = 0.f;
-            if (e.kind == EPI_RESID && c.lane < FK_RB * M) {
-                const int r = c.lane / M, m = c.lane - r * M;
-                if (rb0 + r < rs) resid = epi_resid(e, m, row0 + st * rps + rb0 + r);
+        umma_commit(&c.sh->mma_done);
+    }
+    c.stage_ctr += nst;
+    if (nst == 0) return;
+    // ---- epilogue ------------------------------------------------------------------------------
+    const bool epi_thread = c.warp < 4;
+    const int rA = 16 * c.warp + c.lane, rB = 64 + rA;       // rows of this thread (lanes < 16 only)
+    const bool vA = epi_thread && c.lane < 16 && rA < d.nrows, vB = epi_thread && c.lane < 16 && two && rB < d.nrows;
+    float resA[2] = {0.f, 0.f}, resB[2] = {0.f, 0.f};
+    if (e.kind == EPI_RESID) {                               // overlaps the MMAs
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (m < M) {
+                if (vA) resA[m] = epi_resid(e, m, d.row0 + rA);
+                if (vB) resB[m] = epi_resid(e, m, d.row0 + rB);
             }
-            float acc[FK_RB][M][2];
+        }
+    }
+    {   // everybody waits: operand B and the TMEM accumulators are reused by the next phase
+        if (!mbar_try_wait(&c.sh->mma_done, c.mma_phase)) {
+            if (!wait_full_slow(&c.sh->mma_done, c.mma_phase, c.p->ctrl)) c.aborted = true;
+        }
+        c.mma_phase ^= 1u;
+    }
+    tc_fence_after();
+    if (epi_thread) {
+        uint32_t r[16];
+        tmem_ld16(c.tmem + ((uint32_t)(32 * c.warp) << 16), r);
+        tc_fence_before();
+        float yA[2], yB[2];
 #pragma unroll
-            for (int r = 0; r < FK_RB; ++r)
+        for (int m = 0; m < 2; ++m) {
+            yA[m] = (__uint_as_float(r[3 * m]) + __uint_as_float(r[3 * m + 1])) + __uint_as_float(r[3 * m + 2]);
+            yB[m] = (__uint_as_float(r[8 + 3 * m]) + __uint_as_float(r[8 + 3 * m + 1])) + __uint_as_float(r[8 + 3 * m + 2]);
+        }
+        // SwiGLU: the gate row (even) needs the up row (odd) of the next lane
+        float uA[2], uB[2];
 #pragma unroll
-                for (int m = 0; m < M; ++m) { acc[r][m][0] = 0.f; acc[r][m][1] = 0.f; }
-#pragma unroll 1
-            for (int sg = 0; sg < nseg; ++sg) {
-                if (nseg > 1) {                              // x registers of this segment
+        for (int m = 0; m < 2; ++m) {
+            uA[m] = __shfl_down_sync(0xffffffffu, yA[m], 1);
+            uB[m] = __shfl_down_sync(0xffffffffu, yB[m], 1);
+        }
 #pragma unroll
-                    for (int m = 0; m < M; ++m)
+        for (int m = 0; m < 2; ++m) {
+            if (m < M) {
 #pragma unroll
-                        for (int j = 0; j < KC; ++j) {
-                            xa[m][j] = xs4[m * Kpad4 + sg * (KC * 64) + j * 64 + c.lane];
-                            xb[m][j] = xs4[m * Kpad4 + sg * (KC * 64) + j * 64 + 32 + c.lane];
-                        }
-                }
-                const unsigned char* sbase = base + (size_t)rb0 * ((size_t)K * 2) + (size_t)sg * (KS * 2) + c.lane * 16;
-#pragma unroll
-                for (int j = 0; j < KC; ++j) {
-                    uint4 w[FK_RB];
-#pragma unroll
-                    for (int r = 0; r < FK_RB; ++r)
-                        w[r] = (rb0 + r < rs) ? lds128(sbase + (size_t)r * ((size_t)K * 2) + j * 512) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                    for (int r = 0; r < FK_RB; ++r)
-#pragma unroll
-                        for (int m = 0; m < M; ++m) dot8x2(w[r], xa[m][j], xb[m][j], acc[r][m][0], acc[r][m][1]);
-                }
-            }
-            float tot[FK_RB][M];
-#pragma unroll
-            for (int r = 0; r < FK_RB; ++r)
-#pragma unroll
-                for (int m = 0; m < M; ++m) tot[r][m] = acc[r][m][0] + acc[r][m][1];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int r = 0; r < FK_RB; ++r)
-#pragma unroll
-                    for (int m = 0; m < M; ++m) tot[r][m] += __shfl_xor_sync(0xffffffffu, tot[r][m], o);
-            // lane (r*M + m) publishes row r of the batch (SwiGLU: the lane of the gate row publishes the pair)
-            float mine = 0.f, partner = 0.f;
-#pragma unroll
-            for (int r = 0; r < FK_RB; ++r)
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-                    if (c.lane == r * M + m) { mine = tot[r][m]; partner = tot[(r + 1) & (FK_RB - 1)][m]; }
-            if (c.lane < FK_RB * M) {
-                const int r = c.lane / M, m = c.lane - r * M;
-                const int n = row0 + st * rps + rb0 + r;
-                if (rb0 + r < rs) {
-                    if (RG == 2) {
-                        if ((r & 1) == 0) st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(mine) * partner, c.seq);
+                for (int blk = 0; blk < 2; ++blk) {
+                    const bool valid = blk ? vB : vA;
+                    if (!valid) continue;
+                    const int n = d.row0 + (blk ? rB : rA);
+                    float v = blk ? yB[m] : yA[m];
+                    if (d.RG == 2) {
+                        if ((n & 1) == 0) st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(v) * (blk ? uB[m] : uA[m]), c.seq);
                     } else if (e.kind == EPI_RESID) {
-                        st_ll(e.out + (size_t)m * e.out_stride + n, resid + mine, c.seq);
+                        st_ll(e.out + (size_t)m * e.out_stride + n, (blk ? resB[m] : resA[m]) + v, c.seq);
                     } else {
-                        float v = mine;
                         if (e.bias) v += __ldg(e.bias + n);
                         st_ll(e.out + (size_t)m * e.out_stride + n, v, c.seq);
                         if (e.kind == EPI_LOGITS) e.plain[n] = v;
@@ -554,20 +620,6 @@ LQT_DEVINL void gemv_seg(FkCtx& c, int K, int RG, int row0, int nrows, const FkE
                 }
             }
         }
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.sh->empty[ast % FK_STAGES]);
-    }
-    c.stage_ctr += nst;
-}
-
-LQT_DEVINL void gemv_phase(FkCtx& c, int K, int M, int RG, int row0, int nrows, const FkEpi& e) {
-    if (nrows <= 0) return;
-    if ((K & 1023) == 0) {
-        if (M == 1) gemv_seg<4, 1>(c, K, RG, row0, nrows, e); else gemv_seg<4, 2>(c, K, RG, row0, nrows, e);
-    } else if ((K & 511) == 0) {
-        if (M == 1) gemv_seg<2, 1>(c, K, RG, row0, nrows, e); else gemv_seg<2, 2>(c, K, RG, row0, nrows, e);
-    } else {
-        if (M == 1) gemv_seg<1, 1>(c, K, RG, row0, nrows, e); else gemv_seg<1, 2>(c, K, RG, row0, nrows, e);
     }
 }
 
@@ -731,7 +783,8 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
             }
         }
     }
-    c.xs[xs_idx(c.tid)] = num / den;
+    xb_store1(c.bt, 0, c.tid, num / den);
+    fence_proxy_async_smem();
     csync();
 }
 
@@ -824,8 +877,9 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
 #pragma unroll
         for (int j = 0; j < FK_CP_POS / 2; ++j) if (j < p0) o = fmaf(row[j], vcol[j], o);
         for (int j = p0; j < np; ++j) o = fmaf(row[j], vn[(j - p0) * ATT_D + d_t], o);
-        c.xs[m * 256 + xs_idx(c.tid)] = o;           // K = 256 -> Kpad = 256
+        xb_store1(c.bt, m, c.tid, o);
     }
+    fence_proxy_async_smem();
     csync();
 }
 
@@ -915,8 +969,9 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         if (do_stage) stage_rows(c, sg, sM, d.K, want, p.eps);
         fk_mark(c, 3);
         if (c.sh->aborted) { c.aborted = true; break; }
-        gemv_phase(c, d.K, gM, d.RG, d.row0, d.nrows, e);
+        gemv_tc(c, d, gM, e);
         fk_mark(c, 6);
+        if (c.aborted) break;
     }
 }
 
@@ -1084,16 +1139,15 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-struct FkSmemLayout { size_t scratch, xs_bytes, nxt, res0, lh, shared, total; };
-inline FkSmemLayout fk_smem_layout(int maxV, int max_xs_floats, int H, int res0_floats) {
+struct FkSmemLayout { size_t scratch, att, nxt, res0, lh, shared, total; };
+inline FkSmemLayout fk_smem_layout(int maxV, int maxK, int H, int res0_floats) {
     FkSmemLayout L{};
-    auto up = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
     size_t off = (size_t)FK_STAGES * FK_STAGE_BYTES;
-    L.scratch = off;
-    L.xs_bytes = up((size_t)max_xs_floats * 4);
-    const size_t samp = (size_t)maxV * (4 + 4 + 4 + 2 + 2);
-    const size_t xsatt = L.xs_bytes + (size_t)FA_FLOATS * 4;
-    off += up(samp > xsatt ? samp : xsatt);
+    L.scratch = off;                                           // operand B (maxK * 16 bytes) | sampler scratch
+    const size_t samp = (size_t)maxV * (4 + 4 + 4 + 2 + 2), bt = (size_t)maxK * 16;
+    off += up(samp > bt ? samp : bt);
+    L.att = off; off += up((size_t)FA_FLOATS * 4);
     L.nxt = off; off += up((size_t)H * 4);
     L.res0 = off; off += up((size_t)res0_floats * 4);
     L.lh = off; off += up((size_t)H * 4);
@@ -1102,7 +1156,7 @@ inline FkSmemLayout fk_smem_layout(int maxV, int max_xs_floats, int H, int res0_
     return L;
 }
 
-struct FkSmemOffsets { unsigned scratch, xs_bytes, nxt, res0, lh, shared; int maxV; };
+struct FkSmemOffsets { unsigned scratch, att, nxt, res0, lh, shared; int maxV; };
 
 __global__ void __launch_bounds__(FK_THREADS, 1)
 frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
@@ -1111,12 +1165,19 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
-        for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }
+        for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], 1); }
+        mbar_init(&sh->mma_done, 1);
         sh->stop = 0; sh->consumed = 0; sh->aborted = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
+    if (warp == 0) {                               // 32 TMEM columns: accumulators of the tensor-core GEMV
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&sh->tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
 
     const GenState st0 = *p.st;                    // written by the host before launch
     const int n_prefill = (p.mode == 0 && st0.pos == 0) ? p.P : 0;
@@ -1138,7 +1199,6 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             for (long long q = 0; q < n_pass && !stopped; ++q) {
                 const FkPassId id = launch_pass(q, p.mode, n_prefill, p.cp_steps);
                 const FkStack& S = id.is_cp ? p.cp : p.talker;
-                const int H = S.H, rep = S.heads / S.kv_heads;
                 const bool inproj = id.is_cp && p.c_inproj_w != nullptr;
                 const int total = pass_ops(S.n_layers, inproj, id.head);
                 for (int it = 0; it < total && !stopped; ++it) {
@@ -1150,16 +1210,17 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                     switch (op.kind) {
                         case FKT_INPROJ: W = p.c_inproj_w; break;
                         case FKT_A: W = L.wqkv; break;
-                        case FKT_C: W = L.wo_g + (size_t)(cta % S.kv_heads) * H * (rep * ATT_D); break;
+                        case FKT_C: W = L.wo_g; break;
                         case FKT_D: W = L.wgu; break;
                         case FKT_E: W = L.wdown; break;
-                        default: W = id.is_cp ? p.c_heads + (size_t)id.cb * p.cp_vocab * H : p.t_head; break;
+                        default: W = id.is_cp ? p.c_heads + (size_t)id.cb * p.c_head_stride : p.t_head; break;
                     }
-                    const int K = d.K;
-                    const int rps = rows_per_stage(K, d.RG);
-                    const char* srcb = reinterpret_cast<const char*>(W + (size_t)d.row0 * K);
-                    for (int r = 0; r < d.nrows && !stopped; r += rps) {
-                        const int n = min(rps, d.nrows - r);
+                    if (d.nrows <= 0) continue;
+                    const int ntile = d.K >> 6;
+                    const uint32_t tile_bytes = (uint32_t)d.r8 * 128u;
+                    const char* srcb = reinterpret_cast<const char*>(W + d.img_off);
+                    for (int t0i = 0; t0i < ntile && !stopped; t0i += d.tps) {
+                        const int nt = min(d.tps, ntile - t0i);
                         const unsigned slot = issued % FK_STAGES, par = ((issued / FK_STAGES) & 1u) ^ 1u;
                         unsigned long long t0 = 0;
                         while (!mbar_try_wait(&sh->empty[slot], par)) {
@@ -1168,9 +1229,9 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                             else if (clock64() - t0 > FK_SPIN_LIMIT) { stopped = true; break; }
                         }
                         if (stopped) break;
-                        const uint32_t bytes = (uint32_t)n * K * 2;
+                        const uint32_t bytes = (uint32_t)nt * tile_bytes;
                         mbar_expect_tx(&sh->full[slot], bytes);
-                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)r * K * 2, bytes, &sh->full[slot]);
+                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)t0i * tile_bytes, bytes, &sh->full[slot]);
                         ++issued;
                     }
                 }
@@ -1191,13 +1252,13 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     // ================================ consumer warps ===============================================
     FkCtx c;
     c.p = &p; c.sh = sh; c.ring = fk_smem;
-    c.xs = reinterpret_cast<float*>(fk_smem + so.scratch);
-    c.att = reinterpret_cast<float*>(fk_smem + so.scratch + so.xs_bytes);
+    c.bt = fk_smem + so.scratch;
+    c.att = reinterpret_cast<float*>(fk_smem + so.att);
     c.nxt = reinterpret_cast<float*>(fk_smem + so.nxt);
     c.res0 = reinterpret_cast<float*>(fk_smem + so.res0);
     c.lh = reinterpret_cast<float*>(fk_smem + so.lh);
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
-    c.seq = 0; c.stage_ctr = 0; c.aborted = false;
+    c.seq = 0; c.stage_ctr = 0; c.aborted = false; c.mma_phase = 0; c.tmem = sh->tmem_base;
     c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
     FkSampScratch ss;
     ss.x = reinterpret_cast<float*>(fk_smem + so.scratch);
@@ -1289,8 +1350,13 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
         else ++cb;
     }
     if (p.mode == 0 && !done && frame >= st0.max_frames) done = 1;
-    // ---- exit: publish state, stop the producer -----------------------------------------------------
+    // ---- exit: publish state, stop the producer, release TMEM -----------------------------------------
+    tc_fence_before();
     csync();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(c.tmem) : "memory");
+    }
     if (tid == 0) {
         if (cta == 0) {
             p.st->pos = pos; p.st->frame = frame; p.st->done = done; p.st->n_frames = n_frames;
