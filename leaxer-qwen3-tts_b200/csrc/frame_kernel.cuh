@@ -46,6 +46,8 @@ constexpr int FK_NS_MAX = 24;                     // max attention splits per kv
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_MAXV = 4096;
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
+constexpr int FK_NACC = 8;                        // TMEM accumulator sets (16 columns each), one per issuing warp
+constexpr int FK_TMEM_COLS = FK_NACC * 16;        // 256
 constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
 constexpr unsigned long long FK_SPIN_LIMIT = 6000000000ull;   // ~3 s of SM clocks: abort, never hang
 
@@ -143,6 +145,11 @@ LQT_DEVINL void umma_bf16_m64n8k16(uint32_t d_tmem, uint64_t adesc, uint64_t bde
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(FK_IDESC), "r"(accumulate) : "memory");
+}
+LQT_DEVINL bool elect_one() {                     // one lane of a converged warp (warp-uniform control flow around it)
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 LQT_DEVINL void umma_commit(uint64_t* bar) {      // arrives on the mbarrier when all prior tcgen05.mma of this thread are done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -251,8 +258,8 @@ struct FkCtx {
 };
 
 // timeline entries: (SM clock << 16) | (stack << 9) | (phase kind << 4) | point. Points:
-//  0 phase begin   3 inputs complete (polling, attention, RMSNorm done; before the GEMV)
-//  4 glue done (sampler phases)   5 first weight stage landed (inside the GEMV)   6 this warp's GEMV rows done
+//  0 phase begin   1 input probe passed   2 inputs fetched   3 inputs complete (polling, attention, RMSNorm done; before the GEMV)
+//  4 glue done (sampler phases)   5 all MMAs of the phase done   7 accumulators read back   6 outputs published
 enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_SAMPLE = 7, FKT_INPROJ = 8 };
 LQT_DEVINL void fk_mark(FkCtx& c, int point) {
     if (c.dbg && c.tid == 0 && c.dbg_n < c.dbg_cap)
@@ -443,6 +450,7 @@ LQT_DEVINL void stage_rows(FkCtx& c, const FkStage& s, int M, int K, unsigned wa
     const int K4 = K >> 2;
     if (s.part) ll_probe(c, s.part, M * s.n_part * K, want);
     else if (s.ll && !s.verified) ll_probe(c, s.ll, (M - 1) * s.ll_stride + K, want);
+    fk_mark(c, 1);
     const bool norm = s.nw != nullptr;         // norm path: K = hidden <= 2048 -> at most 2 float4 per thread per row,
     float4 v00, v01, v10, v11;                 // kept in registers until rstd is known (operand B is written once)
     v00 = v01 = v10 = v11 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -461,6 +469,7 @@ LQT_DEVINL void stage_rows(FkCtx& c, const FkStage& s, int M, int K, unsigned wa
             }
         }
     }
+    fk_mark(c, 2);
     if (norm) {
         ss0 = warp_sum(ss0); ss1 = warp_sum(ss1);
         if (c.lane == 0) { c.sh->redf[c.warp][0] = ss0; c.sh->redf[c.warp][1] = ss1; }
@@ -531,33 +540,42 @@ LQT_DEVINL void gemv_tc(FkCtx& c, const FkDesc& d, int M, const FkEpi& e) {
     const int ntile = d.K >> 6;
     const int nst = d.nrows > 0 ? (ntile + d.tps - 1) / d.tps : 0;
     const bool two = d.r8 > 64;
-    if (nst > 0 && c.tid == 4 * 32) {                       // the MMA issuer: lane 0 of warp 4
+    if (nst > 0) {
+        // All eight consumer warps issue: warp w takes K-step (w & 3) of the tiles with parity (w >> 2). A
+        // tcgen05.mma costs its issuing warp ~140 cycles (measured), whatever surrounds it, while MMAs of
+        // different warps overlap, so the issue is spread as wide as possible. Control flow is warp-uniform,
+        // one elected lane issues. Accumulator set = warp (its own TMEM columns): 8 independent chains.
         tc_fence_after();
-        const uint32_t bt_addr = smem_u32(c.bt);
-        const uint32_t tile_bytes = (uint32_t)d.r8 * 128u;
+        const int ks = c.warp & 3, par = c.warp >> 2;
+        const uint32_t tile16 = ((uint32_t)d.r8 * 128u) >> 4;                 // tile size in 16-byte units
+        const uint32_t dcol = c.tmem + (uint32_t)c.warp * 16u;
+        const uint64_t bd0 = umma_desc_sw128(smem_u32(c.bt) + ks * 32);
+        uint32_t acc = 0u;                                                     // first MMA of this warp overwrites
         int tile = 0;
 #pragma unroll 1
         for (int st = 0; st < nst; ++st) {
             const unsigned ast = c.stage_ctr + st, slot = ast % FK_STAGES;
             wait_full(c, ast);
             tc_fence_after();
-            const uint32_t a_stage = smem_u32(c.ring + (size_t)slot * FK_STAGE_BYTES);
+            const uint64_t ad0 = umma_desc_sw128(smem_u32(c.ring + (size_t)slot * FK_STAGE_BYTES) + ks * 32);
             const int nt = min(d.tps, ntile - tile);
 #pragma unroll 1
-            for (int t = 0; t < nt; ++t, ++tile) {
-                const uint32_t a_tile = a_stage + (uint32_t)t * tile_bytes;
-                const uint32_t b_tile = bt_addr + (uint32_t)tile * 1024u;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t acc = (tile | ks) ? 1u : 0u;
-                    const uint64_t bd = umma_desc_sw128(b_tile + ks * 32);
-                    umma_bf16_m64n8k16(c.tmem, umma_desc_sw128(a_tile + ks * 32), bd, acc);
-                    if (two) umma_bf16_m64n8k16(c.tmem + 8, umma_desc_sw128(a_tile + 8192 + ks * 32), bd, acc);
+            for (int t = 0; t < nt; ++t) {
+                if (((tile + t) & 1) == par) {
+                    const uint64_t ad = ad0 + (uint64_t)((uint32_t)t * tile16), bd = bd0 + (uint64_t)((uint32_t)(tile + t) * 64u);
+                    if (elect_one()) {
+                        umma_bf16_m64n8k16(dcol, ad, bd, acc);
+                        if (two) umma_bf16_m64n8k16(dcol + 8, ad + 512, bd, acc);   // rows 64..127: + 8192 B
+                    }
+                    acc = 1u;
                 }
             }
-            umma_commit(&c.sh->empty[slot]);                // ring slot reusable once these MMAs have read it
+            tile += nt;
+            if (elect_one()) umma_commit(&c.sh->empty[slot]);   // ring slot reusable once these MMAs have read it
+            __syncwarp();
         }
-        umma_commit(&c.sh->mma_done);
+        if (elect_one()) umma_commit(&c.sh->mma_done);
+        __syncwarp();
     }
     c.stage_ctr += nst;
     if (nst == 0) return;
@@ -582,16 +600,34 @@ LQT_DEVINL void gemv_tc(FkCtx& c, const FkDesc& d, int M, const FkEpi& e) {
         c.mma_phase ^= 1u;
     }
     tc_fence_after();
+    fk_mark(c, 5);
     if (epi_thread) {
-        uint32_t r[16];
-        tmem_ld16(c.tmem + ((uint32_t)(32 * c.warp) << 16), r);
-        tc_fence_before();
-        float yA[2], yB[2];
+        const int nset = (ntile >= 2) ? FK_NACC : 4;          // warps with tile parity 1 issue nothing when there is one tile
+        float yA[2] = {0.f, 0.f}, yB[2] = {0.f, 0.f};
+#pragma unroll 1
+        for (int s0 = 0; s0 < nset; s0 += 2) {
+            uint32_t r0[16], r1[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]),
+                           "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+                         : "r"(c.tmem + ((uint32_t)(32 * c.warp) << 16) + (uint32_t)s0 * 16u) : "memory");
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]),
+                           "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                         : "r"(c.tmem + ((uint32_t)(32 * c.warp) << 16) + (uint32_t)(s0 + 1) * 16u) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            yA[m] = (__uint_as_float(r[3 * m]) + __uint_as_float(r[3 * m + 1])) + __uint_as_float(r[3 * m + 2]);
-            yB[m] = (__uint_as_float(r[8 + 3 * m]) + __uint_as_float(r[8 + 3 * m + 1])) + __uint_as_float(r[8 + 3 * m + 2]);
+            for (int m = 0; m < 2; ++m) {
+                yA[m] += (__uint_as_float(r0[3 * m]) + __uint_as_float(r0[3 * m + 1])) + __uint_as_float(r0[3 * m + 2]);
+                yB[m] += (__uint_as_float(r0[8 + 3 * m]) + __uint_as_float(r0[8 + 3 * m + 1])) + __uint_as_float(r0[8 + 3 * m + 2]);
+                if (s0 + 1 < nset) {
+                    yA[m] += (__uint_as_float(r1[3 * m]) + __uint_as_float(r1[3 * m + 1])) + __uint_as_float(r1[3 * m + 2]);
+                    yB[m] += (__uint_as_float(r1[8 + 3 * m]) + __uint_as_float(r1[8 + 3 * m + 1])) + __uint_as_float(r1[8 + 3 * m + 2]);
+                }
+            }
         }
+        tc_fence_before();
+        fk_mark(c, 7);
         // SwiGLU: the gate row (even) needs the up row (odd) of the next lane
         float uA[2], uB[2];
 #pragma unroll
@@ -1165,14 +1201,14 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
-        for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], 1); }
-        mbar_init(&sh->mma_done, 1);
+        for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }   // every consumer warp issues MMAs and commits
+        mbar_init(&sh->mma_done, FK_CWARPS);
         sh->stop = 0; sh->consumed = 0; sh->aborted = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
-    if (warp == 0) {                               // 32 TMEM columns: accumulators of the tensor-core GEMV
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&sh->tmem_base)) : "memory");
+    if (warp == 0) {                               // TMEM: FK_NACC accumulator sets of the tensor-core GEMV
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "n"(FK_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -1355,7 +1391,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     csync();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(c.tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(FK_TMEM_COLS) : "memory");
     }
     if (tid == 0) {
         if (cta == 0) {
