@@ -551,24 +551,25 @@ LQT_DEVINL void gemv_tc(FkCtx& c, const FkDesc& d, int M, const FkEpi& e) {
         const uint32_t dcol = c.tmem + (uint32_t)c.warp * 16u;
         const uint64_t bd0 = umma_desc_sw128(smem_u32(c.bt) + ks * 32);
         uint32_t acc = 0u;                                                     // first MMA of this warp overwrites
-        int tile = 0;
+        int tile = 0;                                                          // first tile of the current stage
+        const uint64_t astep = (uint64_t)(2u * tile16);
 #pragma unroll 1
         for (int st = 0; st < nst; ++st) {
             const unsigned ast = c.stage_ctr + st, slot = ast % FK_STAGES;
             wait_full(c, ast);
             tc_fence_after();
-            const uint64_t ad0 = umma_desc_sw128(smem_u32(c.ring + (size_t)slot * FK_STAGE_BYTES) + ks * 32);
             const int nt = min(d.tps, ntile - tile);
+            const int t0 = ((tile & 1) == par) ? 0 : 1;                         // this warp's first tile inside the stage
+            uint64_t ad = umma_desc_sw128(smem_u32(c.ring + (size_t)slot * FK_STAGE_BYTES) + ks * 32) + (uint64_t)((uint32_t)t0 * tile16);
+            uint64_t bd = bd0 + (uint64_t)((uint32_t)(tile + t0) * 64u);
 #pragma unroll 1
-            for (int t = 0; t < nt; ++t) {
-                if (((tile + t) & 1) == par) {
-                    const uint64_t ad = ad0 + (uint64_t)((uint32_t)t * tile16), bd = bd0 + (uint64_t)((uint32_t)(tile + t) * 64u);
-                    if (elect_one()) {
-                        umma_bf16_m64n8k16(dcol, ad, bd, acc);
-                        if (two) umma_bf16_m64n8k16(dcol + 8, ad + 512, bd, acc);   // rows 64..127: + 8192 B
-                    }
-                    acc = 1u;
+            for (int t = t0; t < nt; t += 2) {
+                if (elect_one()) {
+                    umma_bf16_m64n8k16(dcol, ad, bd, acc);
+                    if (two) umma_bf16_m64n8k16(dcol + 8, ad + 512, bd, acc);   // rows 64..127: + 8192 B
                 }
+                acc = 1u;
+                ad += astep; bd += 128;
             }
             tile += nt;
             if (elect_one()) umma_commit(&c.sh->empty[slot]);   // ring slot reusable once these MMAs have read it
