@@ -134,6 +134,7 @@ struct lqt_engine {
     unsigned* fk_ctrl_host = nullptr;         // pinned
     unsigned long long* fk_dbg = nullptr; int fk_dbg_cap = 0, fk_dbg_cta = 0;
     FkSmemOffsets fk_so{};
+    bool fk_wide = false;
     size_t fk_smem = 0;
     // vocoder workspace
     std::map<std::string, std::pair<float*, size_t>> ws;
@@ -779,32 +780,27 @@ bool load_vocoder_weights(lqt_engine* h) {
 // ------------------------------------------------------------------------------------------------
 // persistent frame kernel: one-time weight regrouping, tables, launch
 // ------------------------------------------------------------------------------------------------
-// Per-CTA weight images in canonical K-major SWIZZLE_128B tile layout (see frame_kernel.cuh FkLayer).
+// Per-CTA weight images: CTA c's rows of the matrix, row-major [rmax][K] bf16 (see frame_kernel.cuh FkLayer).
 struct ImgJob {
     const bf16* src0; const bf16* src1;   // mode 1: gate / up
     bf16* dst;
     int N, K, RG, mode;                   // mode 0 flat rows, 1 gate/up interleave, 2 O-projection sliced by kv group
-    int src_stride, n_kv, rmax8;
+    int src_stride, n_kv, rmax;
 };
 __global__ void fk_build_image_kernel(const ImgJob j) {
     const int c = blockIdx.x, ncta = gridDim.x;
     const FkSlice sl = (j.mode == 2) ? group_slice(j.N, c, ncta, j.n_kv) : flat_slice(j.N, j.RG, c, ncta);
-    const int r8 = (sl.nrows + 7) & ~7, ntile = j.K >> 6;
-    const long long nchunk = (long long)ntile * r8 * 8;
-    bf16* dst = j.dst + (size_t)c * j.rmax8 * j.K;
+    const int kc = j.K >> 3;                                        // 16-byte chunks per row
+    const long long nchunk = (long long)sl.nrows * kc;
+    bf16* dst = j.dst + (size_t)c * j.rmax * j.K;
     for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < nchunk; i += (long long)gridDim.y * blockDim.x) {
-        const int tile = (int)(i / (r8 * 8)), rem = (int)(i % (r8 * 8)), r = rem >> 3, pc = rem & 7;
-        const int k0 = tile * 64 + ((pc ^ (r & 7)) << 3);
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < sl.nrows) {
-            const int n = sl.row0 + r;
-            const bf16* src;
-            if (j.mode == 1) src = ((n & 1) ? j.src1 : j.src0) + (size_t)(n >> 1) * j.src_stride + k0;
-            else if (j.mode == 2) src = j.src0 + (size_t)n * j.src_stride + (size_t)(c % j.n_kv) * j.K + k0;
-            else src = j.src0 + (size_t)n * j.src_stride + k0;
-            v = *reinterpret_cast<const uint4*>(src);
-        }
-        *reinterpret_cast<uint4*>(dst + (size_t)tile * r8 * 64 + (size_t)r * 64 + pc * 8) = v;
+        const int r = (int)(i / kc), k0 = (int)(i % kc) << 3;
+        const int n = sl.row0 + r;
+        const bf16* src;
+        if (j.mode == 1) src = ((n & 1) ? j.src1 : j.src0) + (size_t)(n >> 1) * j.src_stride + k0;
+        else if (j.mode == 2) src = j.src0 + (size_t)n * j.src_stride + (size_t)(c % j.n_kv) * j.K + k0;
+        else src = j.src0 + (size_t)n * j.src_stride + k0;
+        *reinterpret_cast<uint4*>(dst + (size_t)r * j.K + k0) = *reinterpret_cast<const uint4*>(src);
     }
 }
 
@@ -816,11 +812,9 @@ int fk_alloc(lqt_engine* h, T** p, size_t n) {
     return 0;
 }
 
-int fk_rmax8(int N, int RG, int mode, int n_kv, int ncta) {       // must match make_desc() in frame_kernel.cuh
-    int rmax;
-    if (mode == 2) { const int ns = ncta / n_kv; rmax = (N + ns - 1) / ns; }
-    else rmax = ((N / RG + ncta - 1) / ncta) * RG;
-    return (rmax + 7) & ~7;
+int fk_rmax(int N, int RG, int mode, int n_kv, int ncta) {        // must match make_desc() in frame_kernel.cuh
+    if (mode == 2) { const int ns = ncta / n_kv; return (N + ns - 1) / ns; }
+    return ((N / RG + ncta - 1) / ncta) * RG;
 }
 
 // builds one image; returns its device pointer (nullptr on failure)
@@ -828,8 +822,8 @@ bf16* fk_image(lqt_engine* h, const bf16* src0, const bf16* src1, int N, int K, 
                size_t* elems_out = nullptr) {
     ImgJob j{};
     j.src0 = src0; j.src1 = src1; j.N = N; j.K = K; j.RG = RG; j.mode = mode; j.src_stride = src_stride; j.n_kv = n_kv;
-    j.rmax8 = fk_rmax8(N, RG, mode, n_kv, h->num_sms);
-    const size_t elems = (size_t)h->num_sms * j.rmax8 * K;
+    j.rmax = fk_rmax(N, RG, mode, n_kv, h->num_sms);
+    const size_t elems = (size_t)h->num_sms * j.rmax * K + 64;
     bf16* dst = nullptr;
     if (fk_alloc(h, &dst, elems)) return nullptr;
     j.dst = dst;
@@ -864,17 +858,22 @@ int fk_init(lqt_engine* h) {
     const Spec& s = h->sp;
     const int maxK = std::max(std::max(s.hidden, s.inter), std::max(s.cp_hidden, s.cp_inter));
     auto chk = [&](int K, const char* what) -> bool {
-        if (K % 256 != 0 || K > 3072) { h->err = std::string("frame kernel: unsupported dimension for ") + what; return false; }
+        if (K % 8 != 0 || K > 6144) { h->err = std::string("frame kernel: unsupported dimension for ") + what; return false; }
         return true;
     };
     if (!chk(s.hidden, "hidden") || !chk(s.inter, "inter") || !chk(s.cp_hidden, "cp_hidden") || !chk(s.cp_inter, "cp_inter"))
         return 1;
-    {   // every CTA slice must fit two 64-row MMA blocks and one ring stage per tile
+    h->fk_wide = maxK > 3072;                       // frame_kernel<6, 5> instead of <3, 8>
+    {   // row counts per CTA: warp partials [FK_RED_STRIDE] (two rows at once: 48 each), x1own
         const int nc = h->num_sms;
-        const int worst = std::max(std::max(fk_rmax8(2 * s.inter, 2, 1, s.kv_heads, nc), fk_rmax8((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc)),
-                                   std::max(fk_rmax8(s.hidden, 1, 2, s.kv_heads, nc), fk_rmax8(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc)));
-        const int worst_c = std::max(fk_rmax8(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax8((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
-        if (std::max(worst, worst_c) > 128) { h->err = "frame kernel: too many rows per SM"; return 1; }
+        const int worst = std::max(std::max(fk_rmax(2 * s.inter, 2, 1, s.kv_heads, nc), fk_rmax((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc)),
+                                   fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc));
+        const int worst_c = std::max(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
+        if (worst > FK_RED_STRIDE || worst_c > FK_RED_STRIDE) { h->err = "frame kernel: too many rows per SM"; return 1; }
+        if (std::max(fk_rmax(s.hidden, 1, 0, s.kv_heads, nc), fk_rmax(s.cp_hidden, 1, 0, s.cp_kv_heads, nc)) > FK_X1OWN) { h->err = "frame kernel: too many down-projection rows per SM"; return 1; }
+        if ((s.heads / s.kv_heads) * ATT_D > FK_XS_STRIDE || (s.cp_heads / s.cp_kv_heads) * ATT_D > FK_XS_STRIDE || s.heads != 2 * s.kv_heads || s.cp_heads != 2 * s.cp_kv_heads) {
+            h->err = "frame kernel: needs 2 query heads per kv head"; return 1;
+        }
     }
     if (s.kv_heads > FK_NGRP_MAX || s.cp_kv_heads > FK_NGRP_MAX || s.kv_heads != s.cp_kv_heads) { h->err = "frame kernel: kv head count"; return 1; }
     if (s.cp_steps + 2 > FK_CP_POS) { h->err = "frame kernel: cp_steps"; return 1; }
@@ -885,14 +884,14 @@ int fk_init(lqt_engine* h) {
     {   // head / in_proj images
         h->fk_t_head = fk_image(h, h->t_head, nullptr, s.vocab, s.hidden, 1, 0, s.hidden, s.kv_heads);
         if (!h->fk_t_head) return 1;
-        const int r8 = fk_rmax8(s.cp_vocab, 1, 0, s.cp_kv_heads, h->num_sms);
+        const int r8 = fk_rmax(s.cp_vocab, 1, 0, s.cp_kv_heads, h->num_sms);
         h->fk_c_head_stride = (long long)h->num_sms * r8 * s.cp_hidden;
         bf16* all = nullptr;
-        if (fk_alloc(h, &all, (size_t)h->fk_c_head_stride * s.cp_steps)) return 1;
+        if (fk_alloc(h, &all, (size_t)h->fk_c_head_stride * s.cp_steps + 64)) return 1;
         for (int j = 0; j < s.cp_steps; ++j) {
             ImgJob job{};
             job.src0 = h->c_heads + (size_t)j * s.cp_vocab * s.cp_hidden; job.N = s.cp_vocab; job.K = s.cp_hidden; job.RG = 1; job.mode = 0;
-            job.src_stride = s.cp_hidden; job.n_kv = s.cp_kv_heads; job.rmax8 = r8; job.dst = all + (size_t)j * h->fk_c_head_stride;
+            job.src_stride = s.cp_hidden; job.n_kv = s.cp_kv_heads; job.rmax = r8; job.dst = all + (size_t)j * h->fk_c_head_stride;
             fk_build_image_kernel<<<dim3(h->num_sms, 4), 256, 0, h->stream>>>(job);
         }
         h->fk_c_heads = all;
@@ -919,19 +918,21 @@ int fk_init(lqt_engine* h) {
         h->fk_cp.x = a + o_cx; h->fk_cp.qkv = a + o_cq; h->fk_cp.po = a + o_cp; h->fk_cp.act = a + o_ca;
         h->fk_pa = a + o_pa; h->fk_cxin = a + o_ci; h->fk_logits_ll = a + o_lg; h->fk_clogits_ll = a + o_cl;
     }
-    if (fk_alloc(h, &h->fk_ctrl, 2)) return 1;
+    if (fk_alloc(h, &h->fk_ctrl, 64)) return 1;      // [1] abort flag, [32] grid arrival counter (own cache line)
     CK(cudaMallocHost((void**)&h->fk_ctrl_host, 2 * sizeof(unsigned)));
     const int maxV = std::max(s.vocab, s.cp_vocab);
     if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV & 3)) { h->err = "frame kernel: hidden > 2048 or vocab % 4 != 0"; return 1; }
-    const FkSmemLayout L = fk_smem_layout(maxV, maxK, s.hidden, 2 * s.hidden);
-    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.att = (unsigned)L.att;
+    const FkSmemLayout L = fk_smem_layout(h->fk_wide ? 5 : 6, maxV, s.hidden, s.hidden);
+    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.att = (unsigned)L.att; h->fk_so.xs = (unsigned)L.xs; h->fk_so.red = (unsigned)L.red;
     h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.res0 = (unsigned)L.res0; h->fk_so.lh = (unsigned)L.lh;
     h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
     h->fk_smem = L.total;
-    CK(cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
+    const void* fn = h->fk_wide ? (const void*)frame_kernel<6, 5> : (const void*)frame_kernel<3, 6>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
     int coop = 0, nb = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frame_kernel, FK_THREADS, h->fk_smem));
+    if (h->fk_wide) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frame_kernel<6, 5>, FK_THREADS, h->fk_smem)); }
+    else            { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frame_kernel<3, 6>, FK_THREADS, h->fk_smem)); }
     if (!coop || nb < 1) { h->err = "frame kernel: cooperative launch with one CTA per SM is not possible on this device"; return 1; }
     return 0;
 }
@@ -961,11 +962,11 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.trace = trace ? h->trace_dev : nullptr; p.trace_stride = h->trace_stride;
     p.ctrl = h->fk_ctrl; p.frame_end = frame_end; p.mode = mode;
     p.dbg = h->fk_dbg; p.dbg_cap = h->fk_dbg_cap; p.dbg_cta = h->fk_dbg_cta;
-    CK(cudaMemsetAsync(h->fk_ctrl, 0, 2 * sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->fk_ctrl, 0, 64 * sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->fk_arena, 0, h->fk_arena_words * sizeof(uint2), h->stream));   // sequence numbers restart at 1
     FkSmemOffsets so = h->fk_so;
     void* args[] = {(void*)&p, (void*)&so};
-    CK(cudaLaunchCooperativeKernel((const void*)frame_kernel, dim3(h->num_sms), dim3(FK_THREADS), args, h->fk_smem, h->stream));
+    CK(cudaLaunchCooperativeKernel(h->fk_wide ? (const void*)frame_kernel<6, 5> : (const void*)frame_kernel<3, 6>, dim3(h->num_sms), dim3(FK_THREADS), args, h->fk_smem, h->stream));
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(h->fk_ctrl_host, h->fk_ctrl, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     return 0;

@@ -6,17 +6,20 @@
 // HBM pipe drains at every kernel boundary (round-1 v1: 577 launches, 4.2 ms per frame).
 // Here every SM keeps one CTA resident:
 //   * warp 8 (producer) walks the static weight schedule of the whole launch and streams this CTA's
-//     slice of every matrix into a shared-memory ring with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx), running AHEAD of the math across phase boundaries;
-//   * warps 0-7 (consumers) run the phases: assemble the input vector (RMSNorm / attention / partial
-//     sums) and publish the outputs. The matrix-vector product itself runs on the 5th-gen tensor
-//     cores: the weights are stored in HBM per CTA as ready-made K-major SWIZZLE_128B tiles, so the
-//     bulk copies land operand A in canonical UMMA layout; the activation vector is split exactly
-//     into three bf16 terms (x = hi + mid + lo, 24 mantissa bits) that form operand B (N = 8
-//     columns); ONE thread issues K/16 tcgen05.mma (M=64, N=8, fp32 accumulate in TMEM) per phase,
-//     tcgen05.commit frees the ring slots, and 64-128 threads read their row back with tcgen05.ld and
-//     publish it in parallel. (The fp32 FMA version of this loop was issue/latency bound: 2-4 us
-//     per phase with 8 warps.);
+//     rows of every matrix into a shared-memory ring with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), running AHEAD of the math across phase boundaries.
+//     The weights are regrouped once at load time into per-CTA row-major images, so one stage of the
+//     ring = a few complete rows = one contiguous copy;
+//   * warps 0-7 (consumers) run the phases. A matrix-vector product is K-split over the 256 threads:
+//     thread t owns columns 4t..4t+3 of every 1024-column chunk, so its slice of the input vector lives
+//     in REGISTERS (polled straight from L2, no shared-memory staging, no barrier), the weights are read
+//     with conflict-free 8-byte shared loads, eight rows are reduced at a time with a transposing
+//     butterfly (9 shuffles for 8 rows) and the eight warp partials meet in shared memory: ONE CTA
+//     barrier per phase. RMSNorm is folded: the product runs on x*w_norm while the sum of squares
+//     travels with the partials, and 1/rms is applied in the epilogue (exact up to rounding order).
+//     (Round-1 v10 ran this on tcgen05 with M64N8K16 MMAs: K/16 dependent MMAs of ~46 cycles per phase
+//     plus bf16x3 operand staging made a phase 8-10 us; the FMA form is bounded by the shared-memory
+//     read of the weights, ~0.25 us per phase.);
 //   * there is NO grid barrier. Activations travel between CTAs as 8-byte (value, sequence) pairs
 //     written with one store each ("LL" exchange, as in NCCL's low-latency protocol): a reader polls
 //     the data itself until every word carries the sequence number of the phase that produces it.
@@ -40,20 +43,18 @@ typedef __nv_bfloat16 bf16_t;
 constexpr int FK_CWARPS = 8;
 constexpr int FK_CTHREADS = FK_CWARPS * 32;       // consumer threads
 constexpr int FK_THREADS = FK_CTHREADS + 32;      // + one producer warp
-constexpr int FK_STAGE_BYTES = 16 * 1024;
-constexpr int FK_STAGES = 8;                      // 128 KB weight ring per SM
+constexpr int FK_STAGE_BYTES = 24 * 1024;         // 8 rows of K=1024 (16 KB used), 4 rows of K=3072, 48 rows of K=256
 constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
-constexpr int FK_MAXV = 4096;
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
-constexpr int FK_NACC = 8;                        // TMEM accumulator sets (16 columns each), one per issuing warp
-constexpr int FK_TMEM_COLS = FK_NACC * 16;        // 256
+constexpr int FK_RED_STRIDE = 96;                 // warp-partial row sums: [warp][FK_RED_STRIDE]; M = 2 -> second row at +48
+constexpr int FK_X1OWN = 16;                      // max rows of the down projection per CTA
+constexpr int FK_XS_STRIDE = 512;                 // attention output rows (input of the grouped O-projection)
 constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
 constexpr unsigned long long FK_SPIN_LIMIT = 6000000000ull;   // ~3 s of SM clocks: abort, never hang
 
-// Weight "images": for every matrix and every CTA c, the rows this CTA owns (padded to a multiple of 8
-// with zero rows) as K/64 tiles of [R8 rows][128 bytes], each tile in the canonical K-major
-// SWIZZLE_128B layout (16-byte chunk index XOR (row & 7)); CTA c's image starts at c * rmax8 * K
+// Weight "images": for every matrix and every CTA c, the rows this CTA owns, row-major [rmax][K] bf16
+// (rmax = the largest row count of any CTA, unused rows zero); CTA c's image starts at c * rmax * K
 // elements. Built once at engine init (fk_build_image_kernel) from the .lqw tensors.
 struct FkLayer {
     const bf16_t* wqkv;     // image of [q_dim + 2 kv_dim][H]
@@ -87,7 +88,7 @@ struct FkParams {
     const float *trailing, *tts_pad;
     GenState* st; const SamplingDev* sp;
     long long* codes_out; const long long* forced; float* trace; int trace_stride;
-    unsigned* ctrl;            // [1] abort flag (zero at launch)
+    unsigned* ctrl;            // [1] abort flag, [32] grid arrival counter (all zero at launch)
     int frame_end;             // run frames while frame < frame_end (<= max_frames)
     int mode;                  // 0 = prefill (if pos == 0) + frames; 1 = one talker token from next_in (head on), no frames
     unsigned long long* dbg;   // nullable: phase timeline of CTA dbg_cta, [0] = count
@@ -123,43 +124,15 @@ LQT_DEVINL void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 LQT_DEVINL void csync() { asm volatile("bar.sync 1, %0;" ::"n"(FK_CTHREADS) : "memory"); }
+LQT_DEVINL uint2 lds64(const void* p) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem_u32(p)));
+    return r;
+}
 LQT_DEVINL uint4 lds128(const void* p) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
     return r;
-}
-// ---- tcgen05 / TMEM ----
-LQT_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-LQT_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-LQT_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100): start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 |
-// version 1 <<46 | layout SWIZZLE_128B (2) << 61   (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
-LQT_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D fp32, A/B bf16, both K-major, N = 8, M = 64 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t FK_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 17) | (4u << 24);
-LQT_DEVINL void umma_bf16_m64n8k16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(FK_IDESC), "r"(accumulate) : "memory");
-}
-LQT_DEVINL bool elect_one() {                     // one lane of a converged warp (warp-uniform control flow around it)
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-LQT_DEVINL void umma_commit(uint64_t* bar) {      // arrives on the mbarrier when all prior tcgen05.mma of this thread are done
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-LQT_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {     // this thread's TMEM lane, 16 consecutive columns
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 // LL exchange: 8-byte (value, sequence) words. volatile accesses always go to L2 (the coherence point).
 LQT_DEVINL void st_ll(uint2* p, float v, unsigned seq) {
@@ -181,14 +154,13 @@ LQT_DEVINL uint2 ld_ll1(const uint2* p) {
 // ------------------------------------------------------------------------------------------------
 struct FkDesc {                 // this CTA's weight slice of one phase kind
     int row0, nrows, K, RG;
-    int r8;                     // rows padded to a multiple of 8 (tile = r8 rows x 128 bytes)
-    int tps;                    // tiles (64-element K chunks) per ring stage
+    int rps;                    // rows per ring stage
     unsigned img_off;           // element offset of this CTA's image inside the matrix image
-    int pad_;
+    int pad0_, pad1_;
 };
 struct FkShared {
-    uint64_t full[FK_STAGES];
-    uint64_t empty[FK_STAGES];
+    uint64_t full[16];
+    uint64_t empty[16];
     volatile int stop;            // consumers -> producer: stop issuing
     volatile int consumed;        // stages consumed when stop was raised
     volatile int aborted;
@@ -198,52 +170,18 @@ struct FkShared {
     int redi[FK_CWARPS];
     uint32_t sel_prefix; int sel_k;
     int tok; float fsum;
-    uint64_t mma_done;            // tcgen05.commit of the last MMA of a phase arrives here
-    uint32_t tmem_base;           // written by tcgen05.alloc
+    float ssred[2][FK_CWARPS];        // [phase parity][warp]: partial sums of squares (RMSNorm)
+    float x1own[FK_X1OWN];         // post-attention residual stream at the rows of this CTA's down-projection slice
     FkDesc desc[2][10];           // [stack][phase kind]
 };
-
-// Operand B of the tensor-core GEMV. Row n = 3*m + j of the 8-row tile holds term j (hi, mid, lo) of
-// activation row m; element k lives in tile k/64 at byte n*128 + (((k%64)/8) ^ n)*16 + (k%8)*2.
-LQT_DEVINL void bf16_split3(float x, unsigned short& h, unsigned short& m, unsigned short& l) {
-    const __nv_bfloat16 bh = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(bh);
-    const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(bm);
-    const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
-    h = __bfloat16_as_ushort(bh); m = __bfloat16_as_ushort(bm); l = __bfloat16_as_ushort(bl);
-}
-LQT_DEVINL void xb_store4(unsigned char* bt, int m, int k4, const float4& v) {     // elements 4*k4 .. 4*k4+3 of row m
-    const int k = k4 << 2, tile = k >> 6, c16 = (k & 63) >> 3, e0 = k & 7;
-    unsigned short h[4], md[4], l[4];
-    bf16_split3(v.x, h[0], md[0], l[0]); bf16_split3(v.y, h[1], md[1], l[1]);
-    bf16_split3(v.z, h[2], md[2], l[2]); bf16_split3(v.w, h[3], md[3], l[3]);
-    unsigned char* base = bt + (size_t)tile * 1024 + e0 * 2;
-    const int n0 = 3 * m;
-    *reinterpret_cast<uint2*>(base + (n0 + 0) * 128 + ((c16 ^ (n0 + 0)) << 4)) =
-        make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-    *reinterpret_cast<uint2*>(base + (n0 + 1) * 128 + ((c16 ^ (n0 + 1)) << 4)) =
-        make_uint2((uint32_t)md[0] | ((uint32_t)md[1] << 16), (uint32_t)md[2] | ((uint32_t)md[3] << 16));
-    *reinterpret_cast<uint2*>(base + (n0 + 2) * 128 + ((c16 ^ (n0 + 2)) << 4)) =
-        make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
-}
-LQT_DEVINL void xb_store1(unsigned char* bt, int m, int k, float v) {
-    const int tile = k >> 6, c16 = (k & 63) >> 3, e = k & 7;
-    unsigned short h, md, l;
-    bf16_split3(v, h, md, l);
-    unsigned char* base = bt + (size_t)tile * 1024 + e * 2;
-    const int n0 = 3 * m;
-    *reinterpret_cast<unsigned short*>(base + (n0 + 0) * 128 + ((c16 ^ (n0 + 0)) << 4)) = h;
-    *reinterpret_cast<unsigned short*>(base + (n0 + 1) * 128 + ((c16 ^ (n0 + 1)) << 4)) = md;
-    *reinterpret_cast<unsigned short*>(base + (n0 + 2) * 128 + ((c16 ^ (n0 + 2)) << 4)) = l;
-}
 
 struct FkCtx {
     const FkParams* p;
     FkShared* sh;
-    unsigned char* ring;      // FK_STAGES * FK_STAGE_BYTES
-    unsigned char* bt;        // operand B: x as bf16 (hi, mid, lo) per row, K-major SWIZZLE_128B, K/64 tiles of 8 x 128 B | aliases the sampler scratch
+    unsigned char* ring;      // nstages * FK_STAGE_BYTES
     float* att;               // attention scratch
+    float* xs;                // attention output rows [2][FK_XS_STRIDE] (input of the grouped O-projection)
+    float* red;               // [2 parity][FK_CWARPS][FK_RED_STRIDE] warp-partial row sums
     float* nxt;               // running next talker input [H]
     float* res0;              // layer-0 input rows of the current pass [M][H0] (also its residual)
     float* lh;                // talker last_hidden [H] (code-predictor row 0, src/tts_onnx.cpp:859)
@@ -251,15 +189,13 @@ struct FkCtx {
     int cta, ncta;
     unsigned seq;             // number of the current phase (1, 2, ...): tag of everything it publishes
     unsigned stage_ctr;       // ring stages consumed so far
-    unsigned mma_phase;       // parity of the next wait on sh->mma_done
-    uint32_t tmem;            // TMEM base address (lane 0, column 0) of the 32 allocated columns
     bool aborted;
     unsigned long long* dbg; int dbg_n, dbg_cap, dbg_tag;   // dbg_tag = (stack << 9) | (kind << 4) of the current phase
 };
 
 // timeline entries: (SM clock << 16) | (stack << 9) | (phase kind << 4) | point. Points:
-//  0 phase begin   1 input probe passed   2 inputs fetched   3 inputs complete (polling, attention, RMSNorm done; before the GEMV)
-//  4 glue done (sampler phases)   5 all MMAs of the phase done   7 accumulators read back   6 outputs published
+//  0 phase begin   2 inputs in registers (polling done)   3 inputs complete (attention / staging done; before the GEMV)
+//  4 glue done (sampler phases)   5 weights consumed (all FMAs done)   6 outputs published
 enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_SAMPLE = 7, FKT_INPROJ = 8 };
 LQT_DEVINL void fk_mark(FkCtx& c, int point) {
     if (c.dbg && c.tid == 0 && c.dbg_n < c.dbg_cap)
@@ -301,11 +237,10 @@ LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, in
     }
     FkDesc d;
     d.row0 = s.row0; d.nrows = s.nrows; d.K = K; d.RG = RG;
-    d.r8 = (s.nrows + 7) & ~7;
-    const int tile_bytes = d.r8 * 128;
-    d.tps = tile_bytes > 0 ? max(1, FK_STAGE_BYTES / tile_bytes) : 1;
-    d.img_off = (unsigned)cta * (unsigned)((rmax + 7) & ~7) * (unsigned)K;
-    d.pad_ = 0;
+    d.rps = max(1, FK_STAGE_BYTES / (K * 2));
+    if (kind != FKT_C) { const int grp = (K <= 1024) ? 8 : 4; if (d.rps > grp) d.rps -= d.rps % grp; }
+    d.img_off = (unsigned)cta * (unsigned)rmax * (unsigned)K;
+    d.pad0_ = 0; d.pad1_ = 0;
     return d;
 }
 
@@ -324,8 +259,10 @@ struct FkPassId { bool is_cp; int cb; bool head; };    // cb: predictor pass ind
 LQT_DEVINL FkPassId launch_pass(long long q, int mode, int n_prefill, int cp_steps) {
     if (mode == 1) return FkPassId{false, 0, true};
     if (q < n_prefill) return FkPassId{false, 0, q == n_prefill - 1};
-    const int r = (int)((q - n_prefill) % (cp_steps + 1));
-    return (r < cp_steps) ? FkPassId{true, r, true} : FkPassId{false, 0, true};
+    // per frame: predictor row 0 (talker last_hidden, no head), predictor passes 0..cp_steps-1 (head = pass), talker step
+    const int r = (int)((q - n_prefill) % (cp_steps + 2));
+    if (r == 0) return FkPassId{true, 0, false};
+    return (r <= cp_steps) ? FkPassId{true, r - 1, true} : FkPassId{false, 0, true};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,7 +281,7 @@ __device__ __noinline__ FkLL4 ll_poll4_slow(const uint2* p, unsigned seq, volati
     int spins = 0; unsigned long long t0 = 0;
     do {
         if ((++spins & 255) == 0 && ll_giveup_slow(aborted, ctrl, &t0)) { r.a = ld_ll2(p); r.b = ld_ll2(p + 2); break; }
-        __nanosleep(100);
+        __nanosleep(40);
         r.a = ld_ll2(p); r.b = ld_ll2(p + 2);
     } while (r.a.y != seq || r.a.w != seq || r.b.y != seq || r.b.w != seq);
     return r;
@@ -367,297 +304,244 @@ __device__ __noinline__ bool wait_full_slow(uint64_t* bar, unsigned par, unsigne
     return true;
 }
 
-// Readiness probe before a CTA-wide read: warp 0 polls 32 words spread over the region (one per lane,
-// with back-off) and everybody else waits at the CTA barrier, so that a not-yet-complete vector costs
-// 32 L2 requests per CTA and round instead of one per thread (148 CTAs polling the same lines would
-// otherwise starve the very stores they wait for).
-LQT_DEVINL void ll_probe(FkCtx& c, const uint2* base, int nwords, unsigned seq) {
-    if (c.warp == 0) {
-        const uint2* p = base + (((c.lane + 1) * nwords) >> 5) - 1;
-        if (ld_ll1(p).y != seq) ll_poll1_slow(p, seq, &c.sh->aborted, c.p->ctrl, 40);
+// four consecutive words (32-byte aligned group), all tagged `seq`
+struct FkRaw4 { uint4 a, b; };
+LQT_DEVINL FkRaw4 ll_issue4(const uint2* p) { FkRaw4 r; r.a = ld_ll2(p); r.b = ld_ll2(p + 2); return r; }
+LQT_DEVINL float4 ll_finish4(FkCtx& c, FkRaw4 r, const uint2* p, unsigned seq) {
+    if (r.a.y != seq || r.a.w != seq || r.b.y != seq || r.b.w != seq) {
+        const FkLL4 q = ll_poll4_slow(p, seq, &c.sh->aborted, c.p->ctrl);
+        r.a = q.a; r.b = q.b;
+    }
+    return make_float4(__uint_as_float(r.a.x), __uint_as_float(r.a.z), __uint_as_float(r.b.x), __uint_as_float(r.b.z));
+}
+LQT_DEVINL float4 ll_poll4(FkCtx& c, const uint2* p, unsigned seq) { return ll_finish4(c, ll_issue4(p), p, seq); }
+
+// ------------------------------------------------------------------------------------------------
+// Phase hand-over. Polling the data words themselves from 38k threads swamps the L2 slices that hold them
+// (and delays the very stores being waited for), so the "when" travels separately: after a CTA has ISSUED
+// the stores of phase n, one lane adds 1 to a grid counter (no fence: the stores may still be in flight);
+// the next phase starts when one lane per CTA sees ncta * n, then every thread reads its inputs once and
+// validates the (value, sequence) words -- a word whose store has not landed yet is simply re-read.
+// ------------------------------------------------------------------------------------------------
+LQT_DEVINL void grid_arrive(FkCtx& c) {          // one lane, after the CTA's stores of this phase were issued
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(c.p->ctrl + 32) : "memory");
+}
+__device__ __noinline__ void grid_wait_slow(const unsigned* ctr, unsigned target, volatile int* aborted, unsigned* ctrl) {
+    int spins = 0; unsigned long long t0 = 0;
+    unsigned v;
+    do {
+        if ((++spins & 1023) == 0 && ll_giveup_slow(aborted, ctrl, &t0)) break;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0);
+}
+// all consumer threads; returns when every CTA has issued the outputs of phase `n`
+LQT_DEVINL void grid_wait(FkCtx& c, unsigned n) {
+    if (c.tid == 0 && n != 0) {
+        const unsigned target = n * (unsigned)c.ncta;
+        unsigned v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
+        if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &c.sh->aborted, c.p->ctrl);
     }
     csync();
-}
-// four consecutive words (32-byte aligned group), all tagged `seq`
-LQT_DEVINL float4 ll_poll4(FkCtx& c, const uint2* p, unsigned seq) {
-    uint4 a = ld_ll2(p), b = ld_ll2(p + 2);
-    if (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
-        const FkLL4 r = ll_poll4_slow(p, seq, &c.sh->aborted, c.p->ctrl);
-        a = r.a; b = r.b;
-    }
-    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
 }
 LQT_DEVINL float ll_poll1(FkCtx& c, const uint2* p, unsigned seq) {
     uint2 a = ld_ll1(p);
     if (a.y != seq) a = ll_poll1_slow(p, seq, &c.sh->aborted, c.p->ctrl, 100);
     return __uint_as_float(a.x);
 }
-// values already verified by this CTA in an earlier phase
-LQT_DEVINL float4 ll_val4(const uint2* p) {
-    const uint4 a = ld_ll2(p), b = ld_ll2(p + 2);
-    return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
-}
-LQT_DEVINL float ll_val1(const uint2* p) { return __uint_as_float(ld_ll1(p).x); }
 
 // ------------------------------------------------------------------------------------------------
-// input staging: rows -> xs (permuted float4), optional partial sums, optional RMSNorm (fused:
-// values stay in registers until rstd is known, so xs is written exactly once)
+// K-split matrix-vector product over this CTA's rows, weights from the ring
 // ------------------------------------------------------------------------------------------------
-struct FkStage {
-    const uint2* ll;        // polled source rows [M][ll_stride] (nullptr: rows come from `sm`)
-    int ll_stride;
-    bool verified;          // source words were already verified by this CTA (no polling)
-    const float* sm;        // smem source rows [M][sm_stride] (plain layout)
-    int sm_stride;
-    const uint2* part;      // nullable: n_part polled partial vectors per row at part[(m*n_part + g)*K + k]
-    int n_part;
-    const float* nw;        // nullable RMSNorm weight [K]
-    float* copy_sm;         // nullable: normalised row 0 also to smem plain [K] (last_hidden)
-    float* copy_gl;         // nullable: and to global [K] by CTA 0
-};
-
-LQT_DEVINL float4 stage_fetch(FkCtx& c, const FkStage& s, int m, int k4, int K, unsigned want) {
-    float4 a;
-    if (s.ll) a = s.verified ? ll_val4(s.ll + (size_t)m * s.ll_stride + k4 * 4)
-                             : ll_poll4(c, s.ll + (size_t)m * s.ll_stride + k4 * 4, want);
-    else a = reinterpret_cast<const float4*>(s.sm + (size_t)m * s.sm_stride)[k4];
-    if (s.part) {
-        // all partial vectors in flight at once, validated afterwards (stragglers: slow path)
-        uint4 q[FK_NGRP_MAX][2];
-#pragma unroll
-        for (int g = 0; g < FK_NGRP_MAX; ++g) {
-            if (g < s.n_part) {
-                const uint2* pp = s.part + ((size_t)m * s.n_part + g) * K + k4 * 4;
-                q[g][0] = ld_ll2(pp); q[g][1] = ld_ll2(pp + 2);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < FK_NGRP_MAX; ++g) {
-            if (g < s.n_part) {
-                float4 b;
-                if (q[g][0].y == want && q[g][0].w == want && q[g][1].y == want && q[g][1].w == want)
-                    b = make_float4(__uint_as_float(q[g][0].x), __uint_as_float(q[g][0].z), __uint_as_float(q[g][1].x), __uint_as_float(q[g][1].z));
-                else
-                    b = ll_poll4(c, s.part + ((size_t)m * s.n_part + g) * K + k4 * 4, want);
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-        }
-    }
-    return a;
-}
-
-LQT_DEVINL void stage_rows(FkCtx& c, const FkStage& s, int M, int K, unsigned want, float eps) {
-    const int K4 = K >> 2;
-    if (s.part) ll_probe(c, s.part, M * s.n_part * K, want);
-    else if (s.ll && !s.verified) ll_probe(c, s.ll, (M - 1) * s.ll_stride + K, want);
-    fk_mark(c, 1);
-    const bool norm = s.nw != nullptr;         // norm path: K = hidden <= 2048 -> at most 2 float4 per thread per row,
-    float4 v00, v01, v10, v11;                 // kept in registers until rstd is known (operand B is written once)
-    v00 = v01 = v10 = v11 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ss0 = 0.f, ss1 = 0.f;
-#pragma unroll 1
-    for (int m = 0; m < M; ++m) {
-#pragma unroll 1
-        for (int k4 = c.tid, i = 0; k4 < K4; k4 += FK_CTHREADS, ++i) {
-            const float4 a = stage_fetch(c, s, m, k4, K, want);
-            if (norm) {
-                const float q = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-                if (m == 0) { ss0 += q; if (i == 0) v00 = a; else v01 = a; }
-                else        { ss1 += q; if (i == 0) v10 = a; else v11 = a; }
-            } else {
-                xb_store4(c.bt, m, k4, a);
-            }
-        }
-    }
-    fk_mark(c, 2);
-    if (norm) {
-        ss0 = warp_sum(ss0); ss1 = warp_sum(ss1);
-        if (c.lane == 0) { c.sh->redf[c.warp][0] = ss0; c.sh->redf[c.warp][1] = ss1; }
-        csync();
-        float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-        for (int w2 = 0; w2 < FK_CWARPS; ++w2) { t0 += c.sh->redf[w2][0]; t1 += c.sh->redf[w2][1]; }
-        const float r0 = 1.0f / sqrtf(t0 / (float)K + eps), r1 = 1.0f / sqrtf(t1 / (float)K + eps);
-#pragma unroll 1
-        for (int m = 0; m < M; ++m) {
-#pragma unroll 1
-            for (int k4 = c.tid, i = 0; k4 < K4; k4 += FK_CTHREADS, ++i) {
-                float4 a = (m == 0) ? (i == 0 ? v00 : v01) : (i == 0 ? v10 : v11);
-                const float r = (m == 0) ? r0 : r1;
-                const float4 w = __ldg(reinterpret_cast<const float4*>(s.nw) + k4);
-                a.x = (a.x * r) * w.x; a.y = (a.y * r) * w.y; a.z = (a.z * r) * w.z; a.w = (a.w * r) * w.w;
-                if (m == 0) {
-                    if (s.copy_sm) reinterpret_cast<float4*>(s.copy_sm)[k4] = a;
-                    if (s.copy_gl && c.cta == 0) reinterpret_cast<float4*>(s.copy_gl)[k4] = a;
-                }
-                xb_store4(c.bt, m, k4, a);
-            }
-        }
-    }
-    fence_proxy_async_smem();                  // operand B was written through the generic proxy; the MMA reads it through the async proxy
-    csync();
-}
-
-// ------------------------------------------------------------------------------------------------
-// GEMV over this CTA's slice, weights from the ring, outputs published as LL words
-// ------------------------------------------------------------------------------------------------
-enum { EPI_STORE = 0, EPI_GLU = 1, EPI_RESID = 2, EPI_LOGITS = 3 };
-struct FkEpi {
-    int kind;
-    uint2* out; int out_stride;          // out[m*out_stride + n]   (GLU: n/2)
-    const float* bias;                   // STORE only, nullable
-    float* plain;                        // LOGITS: second, plain copy [n]
-    // RESID: out = (x_in[n] + sum_g po[g][n]) + v, recomputed exactly as phase D staged it
-    const float* res_sm; int res_sm_stride;     // layer-0 residual rows in smem, or
-    const uint2* res_ll; int res_ll_stride;     // verified LL rows
-    const uint2* po; int n_part, H;
-};
-
-LQT_DEVINL float epi_resid(const FkEpi& e, int m, int n) {
-    float r = e.res_sm ? e.res_sm[(size_t)m * e.res_sm_stride + n] : ll_val1(e.res_ll + (size_t)m * e.res_ll_stride + n);
-    float pv[FK_NGRP_MAX];
-#pragma unroll
-    for (int g = 0; g < FK_NGRP_MAX; ++g)
-        pv[g] = (g < e.n_part) ? ll_val1(e.po + ((size_t)m * e.n_part + g) * e.H + n) : 0.f;
-#pragma unroll
-    for (int g = 0; g < FK_NGRP_MAX; ++g) if (g < e.n_part) r += pv[g];
-    return r;
-}
-
-LQT_DEVINL void wait_full(FkCtx& c, unsigned st) {
-    const unsigned slot = st % FK_STAGES, par = (st / FK_STAGES) & 1u;
+LQT_DEVINL void wait_full(FkCtx& c, unsigned st, int nstages) {
+    const unsigned slot = st % (unsigned)nstages, par = (st / (unsigned)nstages) & 1u;
     if (!mbar_try_wait(&c.sh->full[slot], par)) {
         if (!wait_full_slow(&c.sh->full[slot], par, c.p->ctrl)) c.aborted = true;
     }
 }
 
-// Tensor-core GEMV of one phase. Operand A = this CTA's weight tiles as they land in the ring
-// (K/64 tiles of r8 x 128 B, SWIZZLE_128B), operand B = c.bt, D = TMEM columns 0-7 (rows 0-63) and
-// 8-15 (rows 64-127): row r of a 64-row block sits in TMEM lane (r % 16) + 32 * (r / 16).
-// One thread issues everything; tcgen05.commit releases each ring stage and finally signals mma_done.
-// Then thread (warp q < 4, lane l < 16) owns rows 16q + l and 64 + 16q + l and publishes them.
-LQT_DEVINL void gemv_tc(FkCtx& c, const FkDesc& d, int M, const FkEpi& e) {
-    const int ntile = d.K >> 6;
-    const int nst = d.nrows > 0 ? (ntile + d.tps - 1) / d.tps : 0;
-    const bool two = d.r8 > 64;
-    if (nst > 0) {
-        // All eight consumer warps issue: warp w takes K-step (w & 3) of the tiles with parity (w >> 2). A
-        // tcgen05.mma costs its issuing warp ~140 cycles (measured), whatever surrounds it, while MMAs of
-        // different warps overlap, so the issue is spread as wide as possible. Control flow is warp-uniform,
-        // one elected lane issues. Accumulator set = warp (its own TMEM columns): 8 independent chains.
-        tc_fence_after();
-        const int ks = c.warp & 3, par = c.warp >> 2;
-        const uint32_t tile16 = ((uint32_t)d.r8 * 128u) >> 4;                 // tile size in 16-byte units
-        const uint32_t dcol = c.tmem + (uint32_t)c.warp * 16u;
-        const uint64_t bd0 = umma_desc_sw128(smem_u32(c.bt) + ks * 32);
-        uint32_t acc = 0u;                                                     // first MMA of this warp overwrites
-        int tile = 0;                                                          // first tile of the current stage
-        const uint64_t astep = (uint64_t)(2u * tile16);
-#pragma unroll 1
-        for (int st = 0; st < nst; ++st) {
-            const unsigned ast = c.stage_ctr + st, slot = ast % FK_STAGES;
-            wait_full(c, ast);
-            tc_fence_after();
-            const int nt = min(d.tps, ntile - tile);
-            const int t0 = ((tile & 1) == par) ? 0 : 1;                         // this warp's first tile inside the stage
-            uint64_t ad = umma_desc_sw128(smem_u32(c.ring + (size_t)slot * FK_STAGE_BYTES) + ks * 32) + (uint64_t)((uint32_t)t0 * tile16);
-            uint64_t bd = bd0 + (uint64_t)((uint32_t)(tile + t0) * 64u);
-#pragma unroll 1
-            for (int t = t0; t < nt; t += 2) {
-                if (elect_one()) {
-                    umma_bf16_m64n8k16(dcol, ad, bd, acc);
-                    if (two) umma_bf16_m64n8k16(dcol + 8, ad + 512, bd, acc);   // rows 64..127: + 8192 B
-                }
-                acc = 1u;
-                ad += astep; bd += 128;
-            }
-            tile += nt;
-            if (elect_one()) umma_commit(&c.sh->empty[slot]);   // ring slot reusable once these MMAs have read it
-            __syncwarp();
+// sums of 8 values over the 32 lanes with a transposing butterfly: on return every lane holds the
+// full-warp sum of a[lane >> 2] (9 shuffles instead of 40)
+LQT_DEVINL float reduce8(const float (&a)[8], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    float q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? a[i] : a[i + 4], keep = b4 ? a[i + 4] : a[i];
+        q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float d[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? q[i] : q[i + 2], keep = b3 ? q[i + 2] : q[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = b2 ? d[0] : d[1], keep = b2 ? d[1] : d[0];
+    float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
+}
+
+// sums of 4 values over the 32 lanes: on return every lane holds the full-warp sum of a[lane >> 3] (6 shuffles)
+LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    float d[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b4 ? a[i] : a[i + 2], keep = b4 ? a[i + 2] : a[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const float send = b3 ? d[0] : d[1], keep = b3 ? d[1] : d[0];
+    float s = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
+}
+
+// One group of NR rows x NJ 1024-column chunks, branch-free: all weight loads are issued before the FMAs.
+// Rows beyond nr re-read the last row (discarded), chunks a thread does not own read offset 0 with x = 0.
+template <int KJ, int NJ, int NR>
+LQT_DEVINL void ks_group(const unsigned char* sb, int rowbytes, int nr, const int (&coff)[KJ], const float (&xr)[KJ][4],
+                         float* red, int lane) {
+    uint2 w[NR][NJ];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const unsigned char* rb = sb + min(r, nr - 1) * rowbytes;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) w[r][j] = lds64(rb + coff[j]);
+    }
+    float a[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        a[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            a[r] = fmaf(bf16lo(w[r][j].x), xr[j][0], a[r]); a[r] = fmaf(bf16hi(w[r][j].x), xr[j][1], a[r]);
+            a[r] = fmaf(bf16lo(w[r][j].y), xr[j][2], a[r]); a[r] = fmaf(bf16hi(w[r][j].y), xr[j][3], a[r]);
         }
-        if (elect_one()) umma_commit(&c.sh->mma_done);
+    }
+    constexpr int SH = (NR == 8) ? 2 : 3;                       // log2(lanes per row) after the butterfly
+    const int rl = lane >> SH;
+    float s;
+    if (NR == 8) s = reduce8(reinterpret_cast<const float(&)[8]>(a), lane);
+    else         s = reduce4(reinterpret_cast<const float(&)[4]>(a), lane);
+    if ((lane & ((1 << SH) - 1)) == 0 && rl < nr) red[rl] = s;
+}
+
+// xr[j][i] = input element j*1024 + 4*tid + i (zero beyond K). Leaves the eight warp partials of every row in
+// c.red (parity of c.seq); the caller synchronises and runs the epilogue.
+template <int KJ, int NST>
+LQT_DEVINL void gemv_ks(FkCtx& c, const FkDesc& d, const float (&xr)[KJ][4]) {
+    float* red = c.red + (c.seq & 1u) * (FK_CWARPS * FK_RED_STRIDE) + c.warp * FK_RED_STRIDE;
+    const int rowbytes = d.K * 2, tid4 = c.tid * 4;
+    const int kj = (d.K + 1023) >> 10;
+    int coff[KJ];
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) coff[j] = (j * 1024 + tid4 < d.K) ? j * 2048 + c.tid * 8 : 0;
+    const int nst = (d.nrows + d.rps - 1) / d.rps;
+    int row = 0;
+#pragma unroll 1
+    for (int st = 0; st < nst; ++st) {
+        const unsigned ast = c.stage_ctr + st, slot = ast % (unsigned)NST;
+        wait_full(c, ast, NST);
+        const int nrs = min(d.rps, d.nrows - row);
+        const unsigned char* sb = c.ring + (size_t)slot * FK_STAGE_BYTES;
+        if (kj == 1) {
+#pragma unroll 1
+            for (int r0 = 0; r0 < nrs; r0 += 8) ks_group<KJ, 1, 8>(sb + (size_t)r0 * rowbytes, rowbytes, nrs - r0, coff, xr, red + row + r0, c.lane);
+        } else if (kj <= 3 || KJ <= 3) {
+#pragma unroll 1
+            for (int r0 = 0; r0 < nrs; r0 += 4) ks_group<KJ, 3, 4>(sb + (size_t)r0 * rowbytes, rowbytes, nrs - r0, coff, xr, red + row + r0, c.lane);
+        } else {
+#pragma unroll 1
+            for (int r0 = 0; r0 < nrs; r0 += 4) ks_group<KJ, KJ, 4>(sb + (size_t)r0 * rowbytes, rowbytes, nrs - r0, coff, xr, red + row + r0, c.lane);
+        }
         __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.sh->empty[slot]);       // this warp is done with the stage
+        row += nrs;
     }
     c.stage_ctr += nst;
-    if (nst == 0) return;
-    // ---- epilogue ------------------------------------------------------------------------------
-    const bool epi_thread = c.warp < 4;
-    const int rA = 16 * c.warp + c.lane, rB = 64 + rA;       // rows of this thread (lanes < 16 only)
-    const bool vA = epi_thread && c.lane < 16 && rA < d.nrows, vB = epi_thread && c.lane < 16 && two && rB < d.nrows;
-    float resA[2] = {0.f, 0.f}, resB[2] = {0.f, 0.f};
-    if (e.kind == EPI_RESID) {                               // overlaps the MMAs
+}
+
+// Row-per-warp product for the grouped O-projection (K = rep*128 <= 512, input row in c.xs): warp w owns
+// rows w, w + 8, ... of every stage; results are published straight from the reduction (no CTA barrier).
+template <int NST, int NC>
+LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, uint2* out) {
+    const int K = d.K, rowbytes = K * 2;
+    float x0[NC][8];
+    int coff[NC];
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            if (m < M) {
-                if (vA) resA[m] = epi_resid(e, m, d.row0 + rA);
-                if (vB) resB[m] = epi_resid(e, m, d.row0 + rB);
-            }
-        }
+    for (int cc = 0; cc < NC; ++cc) {
+        const int k = cc * 256 + c.lane * 8;
+        const bool act = k < K;
+        coff[cc] = act ? k * 2 : 0;
+        float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+        if (act) { u0 = *reinterpret_cast<const float4*>(c.xs + k); u1 = *reinterpret_cast<const float4*>(c.xs + k + 4); }
+        x0[cc][0] = u0.x; x0[cc][1] = u0.y; x0[cc][2] = u0.z; x0[cc][3] = u0.w; x0[cc][4] = u1.x; x0[cc][5] = u1.y; x0[cc][6] = u1.z; x0[cc][7] = u1.w;
     }
-    {   // everybody waits: operand B and the TMEM accumulators are reused by the next phase
-        if (!mbar_try_wait(&c.sh->mma_done, c.mma_phase)) {
-            if (!wait_full_slow(&c.sh->mma_done, c.mma_phase, c.p->ctrl)) c.aborted = true;
-        }
-        c.mma_phase ^= 1u;
-    }
-    tc_fence_after();
-    fk_mark(c, 5);
-    if (epi_thread) {
-        const int nset = (ntile >= 2) ? FK_NACC : 4;          // warps with tile parity 1 issue nothing when there is one tile
-        float yA[2] = {0.f, 0.f}, yB[2] = {0.f, 0.f};
+    const int nst = (d.nrows + d.rps - 1) / d.rps;
+    int row = 0;
 #pragma unroll 1
-        for (int s0 = 0; s0 < nset; s0 += 2) {
-            uint32_t r0[16], r1[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]),
-                           "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
-                         : "r"(c.tmem + ((uint32_t)(32 * c.warp) << 16) + (uint32_t)s0 * 16u) : "memory");
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]),
-                           "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
-                         : "r"(c.tmem + ((uint32_t)(32 * c.warp) << 16) + (uint32_t)(s0 + 1) * 16u) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int st = 0; st < nst; ++st) {
+        const unsigned ast = c.stage_ctr + st, slot = ast % (unsigned)NST;
+        wait_full(c, ast, NST);
+        const int nrs = min(d.rps, d.nrows - row);
+        const unsigned char* sb = c.ring + (size_t)slot * FK_STAGE_BYTES;
+#pragma unroll 1
+        for (int r0 = 0; r0 < nrs; r0 += 64) {
+            uint4 w[8][NC];
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                yA[m] += (__uint_as_float(r0[3 * m]) + __uint_as_float(r0[3 * m + 1])) + __uint_as_float(r0[3 * m + 2]);
-                yB[m] += (__uint_as_float(r0[8 + 3 * m]) + __uint_as_float(r0[8 + 3 * m + 1])) + __uint_as_float(r0[8 + 3 * m + 2]);
-                if (s0 + 1 < nset) {
-                    yA[m] += (__uint_as_float(r1[3 * m]) + __uint_as_float(r1[3 * m + 1])) + __uint_as_float(r1[3 * m + 2]);
-                    yB[m] += (__uint_as_float(r1[8 + 3 * m]) + __uint_as_float(r1[8 + 3 * m + 1])) + __uint_as_float(r1[8 + 3 * m + 2]);
+            for (int i = 0; i < 8; ++i) {
+                const unsigned char* rb = sb + min(r0 + c.warp + 8 * i, nrs - 1) * rowbytes;
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) w[i][cc] = lds128(rb + coff[cc]);
+            }
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) {
+                    a[i] = fmaf(bf16lo(w[i][cc].x), x0[cc][0], a[i]); a[i] = fmaf(bf16hi(w[i][cc].x), x0[cc][1], a[i]);
+                    a[i] = fmaf(bf16lo(w[i][cc].y), x0[cc][2], a[i]); a[i] = fmaf(bf16hi(w[i][cc].y), x0[cc][3], a[i]);
+                    a[i] = fmaf(bf16lo(w[i][cc].z), x0[cc][4], a[i]); a[i] = fmaf(bf16hi(w[i][cc].z), x0[cc][5], a[i]);
+                    a[i] = fmaf(bf16lo(w[i][cc].w), x0[cc][6], a[i]); a[i] = fmaf(bf16hi(w[i][cc].w), x0[cc][7], a[i]);
                 }
             }
+            const float s = reduce8(a, c.lane);
+            const int r = r0 + c.warp + 8 * (c.lane >> 2);
+            if ((c.lane & 3) == 0 && r < nrs) st_ll(out + d.row0 + row + r, s, c.seq);
         }
-        tc_fence_before();
-        fk_mark(c, 7);
-        // SwiGLU: the gate row (even) needs the up row (odd) of the next lane
-        float uA[2], uB[2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            uA[m] = __shfl_down_sync(0xffffffffu, yA[m], 1);
-            uB[m] = __shfl_down_sync(0xffffffffu, yB[m], 1);
-        }
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            if (m < M) {
-#pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    const bool valid = blk ? vB : vA;
-                    if (!valid) continue;
-                    const int n = d.row0 + (blk ? rB : rA);
-                    float v = blk ? yB[m] : yA[m];
-                    if (d.RG == 2) {
-                        if ((n & 1) == 0) st_ll(e.out + (size_t)m * e.out_stride + (n >> 1), silu_f(v) * (blk ? uB[m] : uA[m]), c.seq);
-                    } else if (e.kind == EPI_RESID) {
-                        st_ll(e.out + (size_t)m * e.out_stride + n, (blk ? resB[m] : resA[m]) + v, c.seq);
-                    } else {
-                        if (e.bias) v += __ldg(e.bias + n);
-                        st_ll(e.out + (size_t)m * e.out_stride + n, v, c.seq);
-                        if (e.kind == EPI_LOGITS) e.plain[n] = v;
-                    }
-                }
-            }
-        }
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.sh->empty[slot]);
+        row += nrs;
     }
+    c.stage_ctr += nst;
+}
+template <int NST>
+LQT_DEVINL void gemv_rw(FkCtx& c, const FkDesc& d, uint2* out) {
+    if (d.K <= 256) gemv_rw_n<NST, 1>(c, d, out); else gemv_rw_n<NST, 2>(c, d, out);
+}
+
+LQT_DEVINL float red_total(const float* red, int idx) {        // fixed order: bit-reproducible
+    float s = red[idx];
+#pragma unroll
+    for (int w = 1; w < FK_CWARPS; ++w) s += red[w * FK_RED_STRIDE + idx];
+    return s;
+}
+LQT_DEVINL float ss_rstd(FkCtx& c, int K, float eps) {
+    const float* q = &c.sh->ssred[c.seq & 1u][0];
+    float t = q[0];
+#pragma unroll
+    for (int w = 1; w < FK_CWARPS; ++w) t += q[w];
+    return 1.0f / sqrtf(t / (float)K + eps);
+}
+// this thread's partial sum of squares -> shared (parity of c.seq); read after the phase's CTA barrier
+LQT_DEVINL void ss_publish(FkCtx& c, float ss) {
+    ss = warp_sum(ss);
+    if (c.lane == 0) c.sh->ssred[c.seq & 1u][c.warp] = ss;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -786,7 +670,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     csync();                     // scratch is reused by the next phase
 }
 
-// talker: combine the splits of group g -> xs[0][0..rep*128)  (input of the grouped O-projection)
+// talker: combine the splits of group g -> c.xs[0][0..rep*128)  (input of the grouped O-projection)
 LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
     const FkParams& p = *c.p;
     const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
@@ -820,12 +704,11 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
             }
         }
     }
-    xb_store1(c.bt, 0, c.tid, num / den);
-    fence_proxy_async_smem();
+    c.xs[c.tid] = num / den;
     csync();
 }
 
-// code predictor: full attention of kv group g for the M new positions p0.., result -> xs[m][0..256)
+// code predictor: full attention of kv group g for the M new positions p0.., result -> c.xs[m][0..256)
 LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int p0, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.cp;
@@ -914,31 +797,68 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
 #pragma unroll
         for (int j = 0; j < FK_CP_POS / 2; ++j) if (j < p0) o = fmaf(row[j], vcol[j], o);
         for (int j = p0; j < np; ++j) o = fmaf(row[j], vn[(j - p0) * ATT_D + d_t], o);
-        xb_store1(c.bt, m, c.tid, o);
+        c.xs[m * FK_XS_STRIDE + c.tid] = o;
     }
-    fence_proxy_async_smem();
     csync();
 }
-
 // ------------------------------------------------------------------------------------------------
-// one token pass (M rows) through a stack, as ONE loop over the flat op schedule so that every helper
-// is instantiated exactly once (the context stays in registers; no local memory on the hot path).
-// The layer-0 input rows are in c.res0 (smem, plain layout, stride = talker hidden).
+// one token pass (one row) through a stack, as ONE loop over the flat op schedule so that every helper
+// is instantiated exactly once. The layer-0 input row is in c.res0 (smem, plain layout). The residual
+// stream of the current layer stays in registers (xin) from phase A to D.
 // ------------------------------------------------------------------------------------------------
-struct FkPass {
-    bool is_cp; int M, pos0;
-    const bf16_t* head_w; int head_n;
-};
+struct FkPass { bool is_cp; int pos0; bool head; };
 
+LQT_DEVINL void f4_to(float (&d)[4], const float4& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+
+// this thread's columns (4*tid.. of every 1024-chunk, J chunks) of an LL vector of K words tagged `want`
+template <int J>
+LQT_DEVINL void ll_row(FkCtx& c, const uint2* src, int K, unsigned want, float (&out)[J][4]) {
+    const int tid4 = c.tid * 4;
+    FkRaw4 raw[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { const int k = j * 1024 + tid4; raw[j] = ll_issue4(src + (k < K ? k : 0)); }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = j * 1024 + tid4;
+        const float4 v = ll_finish4(c, raw[j], src + (k < K ? k : 0), want);
+        if (k < K) f4_to(out[j], v);
+        else { out[j][0] = 0.f; out[j][1] = 0.f; out[j][2] = 0.f; out[j][3] = 0.f; }
+    }
+}
+// x += sum over the kv groups of the O-projection partials, in group order
+template <int J>
+LQT_DEVINL void ll_add_partials(FkCtx& c, const uint2* po, int n_kv, int H, unsigned want, float (&x)[J][4]) {
+    const int tid4 = c.tid * 4;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int k = j * 1024 + tid4;
+        const bool act = k < H;
+        FkRaw4 raw[FK_NGRP_MAX];
+#pragma unroll
+        for (int g = 0; g < FK_NGRP_MAX; ++g) raw[g] = ll_issue4(po + (size_t)(g < n_kv ? g : 0) * H + (act ? k : 0));
+#pragma unroll
+        for (int g = 0; g < FK_NGRP_MAX; ++g) {
+            const float4 b = ll_finish4(c, raw[g], po + (size_t)(g < n_kv ? g : 0) * H + (act ? k : 0), want);
+            if (g < n_kv && act) { x[j][0] += b.x; x[j][1] += b.y; x[j][2] += b.z; x[j][3] += b.w; }
+        }
+    }
+}
+
+template <int KJ, int NST>
 LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
+    constexpr int HJ = (KJ > 3) ? 2 : 1;                         // 1024-column chunks of the hidden size
     const bool is_cp = ps.is_cp;
     const FkStack& S = is_cp ? p.cp : p.talker;
-    const int tk = is_cp ? 1 : 0, M = ps.M;
-    const int H = S.H, qd = S.heads * ATT_D, kvd = S.kv_heads * ATT_D, qkv_dim = qd + 2 * kvd;
-    const int n_kv = S.kv_heads;
-    const int H0 = p.talker.H;                                   // width of the rows in res0
+    const int tk = is_cp ? 1 : 0;
+    const int H = S.H, n_kv = S.kv_heads;
+    const int H0 = p.talker.H;                                   // width of the row in res0
     const bool inproj = is_cp && p.c_inproj_w != nullptr;
-    const int total = pass_ops(S.n_layers, inproj, ps.head_w != nullptr);
+    const int total = pass_ops(S.n_layers, inproj, ps.head);
+    const int tid4 = c.tid * 4;
+    float xin[HJ][4];                                            // layer input (residual stream), this thread's columns
+#pragma unroll
+    for (int j = 0; j < HJ; ++j) { xin[j][0] = 0.f; xin[j][1] = 0.f; xin[j][2] = 0.f; xin[j][3] = 0.f; }
+
     for (int it = 0; it < total && !c.aborted; ++it) {
         const FkOp op = pass_op(it, S.n_layers, inproj);
         const int kind = op.kind, l = op.layer;
@@ -947,66 +867,134 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         const unsigned want = c.seq - 1;
         fk_phase(c, tk, kind);
         fk_mark(c, 0);
+        grid_wait(c, want);
+        fk_mark(c, 1);
         const FkLayer& L = is_cp ? p.c_layers[l] : p.t_layers[l];
         const FkDesc d = c.sh->desc[tk][kind];
-        // the layer input rows: res0 (smem) for layer 0 without in_proj, else an LL buffer
+        // the layer input row: res0 (smem) for layer 0 without in_proj, else an LL buffer
         const bool in_res0 = (l == 0 && !inproj);
         const uint2* lin = (l == 0) ? p.cxin : S.x;           // (only read when !in_res0)
         if (kind == FKT_B) {
             if (p.kv_f32) talker_attn_partial<float>(c, L, l, ps.pos0, want);
             else          talker_attn_partial<bf16_t>(c, L, l, ps.pos0, want);
+            csync();
+            if (c.tid == 0) grid_arrive(c);
             fk_mark(c, 3);
             if (c.sh->aborted) { c.aborted = true; break; }
             continue;
         }
-        FkStage sg{nullptr, 0, false, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr};
-        FkEpi e{EPI_STORE, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, 0};
-        int sM = M, gM = M;
-        bool do_stage = true;
-        switch (kind) {
-            case FKT_INPROJ:
-                sg.sm = c.res0; sg.sm_stride = H0;
-                e.out = p.cxin; e.out_stride = H; e.bias = p.c_inproj_b;
-                break;
-            case FKT_A:
-                if (in_res0) { sg.sm = c.res0; sg.sm_stride = H0; }
-                else { sg.ll = lin; sg.ll_stride = H; }
-                sg.nw = L.ln1;
-                e.out = S.qkv; e.out_stride = qkv_dim;
-                break;
-            case FKT_C:
-                do_stage = false;
-                e.out = S.po + (size_t)(c.cta % n_kv) * H; e.out_stride = n_kv * H;
-                break;
-            case FKT_D:
-                if (in_res0) { sg.sm = c.res0; sg.sm_stride = H0; }
-                else { sg.ll = lin; sg.ll_stride = H; sg.verified = true; }
-                sg.part = S.po; sg.n_part = n_kv; sg.nw = L.ln2;
-                e.kind = EPI_GLU; e.out = S.act; e.out_stride = S.inter;
-                break;
-            case FKT_E:
-                sg.ll = S.act; sg.ll_stride = S.inter;
-                e.kind = EPI_RESID; e.out = S.x; e.out_stride = H;
-                if (in_res0) { e.res_sm = c.res0; e.res_sm_stride = H0; }
-                else { e.res_ll = lin; e.res_ll_stride = H; }
-                e.po = S.po; e.n_part = n_kv; e.H = H;
-                break;
-            default:   // FKT_HEAD: final norm of the LAST row + head
-                sg.ll = S.x + (size_t)(M - 1) * H; sg.ll_stride = H; sM = 1; gM = 1;
-                sg.nw = S.final_norm;
-                if (!is_cp) { sg.copy_sm = c.lh; sg.copy_gl = p.last_hidden; }
-                e.kind = EPI_LOGITS; e.out = is_cp ? p.clogits_ll : p.logits_ll; e.out_stride = 0;
-                e.plain = is_cp ? p.clogits : p.logits;
-                break;
-        }
         if (kind == FKT_C) {
-            if (is_cp) cp_attn_local(c, L, l, M, ps.pos0, want);
+            if (is_cp) cp_attn_local(c, L, l, 1, ps.pos0, want);
             else       talker_attn_combine(c, ps.pos0, want);
+            fk_mark(c, 3);
+            if (c.sh->aborted) { c.aborted = true; break; }
+            gemv_rw<NST>(c, d, S.po + (size_t)(c.cta % n_kv) * H);
+            csync();
+            if (c.tid == 0) grid_arrive(c);
+            fk_mark(c, 6);
+            if (c.aborted) break;
+            continue;
         }
-        if (do_stage) stage_rows(c, sg, sM, d.K, want, p.eps);
+        // ---- K-split phases: inputs -> registers ------------------------------------------------------
+        float xr[KJ][4];
+#pragma unroll
+        for (int j = 0; j < KJ; ++j) { xr[j][0] = 0.f; xr[j][1] = 0.f; xr[j][2] = 0.f; xr[j][3] = 0.f; }
+        const float* nw = nullptr;
+        switch (kind) {
+            case FKT_INPROJ: {
+#pragma unroll
+                for (int j = 0; j < KJ; ++j)
+                    if (j * 1024 + tid4 < H0) f4_to(xr[j], *reinterpret_cast<const float4*>(c.res0 + j * 1024 + tid4));
+                break;
+            }
+            case FKT_A: {
+                if (in_res0) {
+#pragma unroll
+                    for (int j = 0; j < HJ; ++j)
+                        if (j * 1024 + tid4 < H) f4_to(xin[j], *reinterpret_cast<const float4*>(c.res0 + j * 1024 + tid4));
+                } else {
+                    ll_row<HJ>(c, lin, H, want, xin);
+                }
+                nw = L.ln1;
+                break;
+            }
+            case FKT_D: {
+                ll_add_partials<HJ>(c, S.po, n_kv, H, want, xin);
+                const FkDesc& de = c.sh->desc[tk][FKT_E];
+#pragma unroll
+                for (int j = 0; j < HJ; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {                          // residual for this CTA's down-projection rows
+                        const unsigned rel = (unsigned)(j * 1024 + tid4 + i - de.row0);
+                        if (rel < (unsigned)de.nrows) c.sh->x1own[rel] = xin[j][i];
+                    }
+                nw = L.ln2;
+                break;
+            }
+            case FKT_E: ll_row<KJ>(c, S.act, d.K, want, xr); break;
+            default:   // FKT_HEAD: final norm + head
+                ll_row<HJ>(c, S.x, H, want, xin);
+                nw = S.final_norm;
+                break;
+        }
+        fk_mark(c, 2);
+        if (nw) {                                              // RMSNorm, folded: product on x*w, 1/rms in the epilogue
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) {
+                if (j * 1024 + tid4 < H) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(nw + j * 1024 + tid4));
+                    ss = fmaf(xin[j][0], xin[j][0], ss); ss = fmaf(xin[j][1], xin[j][1], ss);
+                    ss = fmaf(xin[j][2], xin[j][2], ss); ss = fmaf(xin[j][3], xin[j][3], ss);
+                    xr[j][0] = xin[j][0] * w.x; xr[j][1] = xin[j][1] * w.y; xr[j][2] = xin[j][2] * w.z; xr[j][3] = xin[j][3] * w.w;
+                }
+            }
+            ss_publish(c, ss);
+        }
         fk_mark(c, 3);
         if (c.sh->aborted) { c.aborted = true; break; }
-        gemv_tc(c, d, gM, e);
+        gemv_ks<KJ, NST>(c, d, xr);
+        fk_mark(c, 5);
+        csync();
+        // ---- epilogue: warp partials -> outputs (warp 0 publishes everything, then signals the grid) ----------
+        {
+            const float* red = c.red + (c.seq & 1u) * (FK_CWARPS * FK_RED_STRIDE);
+            const float rs = nw ? ss_rstd(c, H, p.eps) : 1.f;
+            if (c.warp == 0) {
+                if (kind == FKT_D) {
+                    const int nq = d.nrows >> 1;
+                    for (int q = c.lane; q < nq; q += 32) {
+                        const float g = red_total(red, 2 * q) * rs, u = red_total(red, 2 * q + 1) * rs;
+                        st_ll(S.act + (d.row0 >> 1) + q, silu_f(g) * u, c.seq);
+                    }
+                } else {
+                    for (int r = c.lane; r < d.nrows; r += 32) {
+                        const int n = d.row0 + r;
+                        const float v = red_total(red, r) * rs;
+                        if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
+                        else if (kind == FKT_E) st_ll(S.x + n, c.sh->x1own[r] + v, c.seq);
+                        else if (kind == FKT_INPROJ) st_ll(p.cxin + n, v + __ldg(p.c_inproj_b + n), c.seq);
+                        else {
+                            st_ll((is_cp ? p.clogits_ll : p.logits_ll) + n, v, c.seq);
+                            (is_cp ? p.clogits : p.logits)[n] = v;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (c.lane == 0) grid_arrive(c);
+            }
+            if (kind == FKT_HEAD && !is_cp) {                  // talker last_hidden = final-norm of the row (:859)
+#pragma unroll
+                for (int j = 0; j < HJ; ++j) {
+                    if (j * 1024 + tid4 < H) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(nw + j * 1024 + tid4));
+                        const float4 o = make_float4((xin[j][0] * rs) * w.x, (xin[j][1] * rs) * w.y, (xin[j][2] * rs) * w.z, (xin[j][3] * rs) * w.w);
+                        *reinterpret_cast<float4*>(c.lh + j * 1024 + tid4) = o;
+                        if (c.cta == 0) *reinterpret_cast<float4*>(p.last_hidden + j * 1024 + tid4) = o;
+                    }
+                }
+            }
+        }
         fk_mark(c, 6);
         if (c.aborted) break;
     }
@@ -1176,15 +1164,17 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-struct FkSmemLayout { size_t scratch, att, nxt, res0, lh, shared, total; };
-inline FkSmemLayout fk_smem_layout(int maxV, int maxK, int H, int res0_floats) {
+struct FkSmemLayout { size_t scratch, att, xs, red, nxt, res0, lh, shared, total; };
+inline FkSmemLayout fk_smem_layout(int nstages, int maxV, int H, int res0_floats) {
     FkSmemLayout L{};
     auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
-    size_t off = (size_t)FK_STAGES * FK_STAGE_BYTES;
-    L.scratch = off;                                           // operand B (maxK * 16 bytes) | sampler scratch
-    const size_t samp = (size_t)maxV * (4 + 4 + 4 + 2 + 2), bt = (size_t)maxK * 16;
-    off += up(samp > bt ? samp : bt);
-    L.att = off; off += up((size_t)FA_FLOATS * 4);
+    size_t off = (size_t)nstages * FK_STAGE_BYTES;
+    L.scratch = off;                                           // sampler scratch | attention scratch + attention output rows
+    const size_t samp = (size_t)maxV * (4 + 4 + 4 + 2 + 2);
+    const size_t attb = up((size_t)FA_FLOATS * 4), xsb = (size_t)2 * FK_XS_STRIDE * 4;
+    L.att = off; L.xs = off + attb;
+    off += up(samp > attb + xsb ? samp : attb + xsb);
+    L.red = off; off += up((size_t)2 * FK_CWARPS * FK_RED_STRIDE * 4);
     L.nxt = off; off += up((size_t)H * 4);
     L.res0 = off; off += up((size_t)res0_floats * 4);
     L.lh = off; off += up((size_t)H * 4);
@@ -1193,8 +1183,10 @@ inline FkSmemLayout fk_smem_layout(int maxV, int maxK, int H, int res0_floats) {
     return L;
 }
 
-struct FkSmemOffsets { unsigned scratch, att, nxt, res0, lh, shared; int maxV; };
+struct FkSmemOffsets { unsigned scratch, att, xs, red, nxt, res0, lh, shared; int maxV; };
 
+// KJ = 1024-column chunks of the widest matrix (3: inter <= 3072, 6: <= 6144); NST = ring stages
+template <int KJ, int NST>
 __global__ void __launch_bounds__(FK_THREADS, 1)
 frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     extern __shared__ __align__(1024) unsigned char fk_smem[];
@@ -1202,19 +1194,12 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
-        for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }   // every consumer warp issues MMAs and commits
-        mbar_init(&sh->mma_done, FK_CWARPS);
+        for (int i = 0; i < NST; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }   // every consumer warp releases a stage
         sh->stop = 0; sh->consumed = 0; sh->aborted = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
-    if (warp == 0) {                               // TMEM: FK_NACC accumulator sets of the tensor-core GEMV
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "n"(FK_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
 
     const GenState st0 = *p.st;                    // written by the host before launch
     const int n_prefill = (p.mode == 0 && st0.pos == 0) ? p.P : 0;
@@ -1229,7 +1214,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             if (p.mode == 1) n_pass = 1;
             else {
                 const int nf = (!st0.done && frame_end > st0.frame) ? (frame_end - st0.frame) : 0;
-                n_pass = (long long)n_prefill + (long long)nf * (p.cp_steps + 1);
+                n_pass = (long long)n_prefill + (long long)nf * (p.cp_steps + 2);
             }
             unsigned issued = 0;
             bool stopped = false;
@@ -1253,12 +1238,11 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                         default: W = id.is_cp ? p.c_heads + (size_t)id.cb * p.c_head_stride : p.t_head; break;
                     }
                     if (d.nrows <= 0) continue;
-                    const int ntile = d.K >> 6;
-                    const uint32_t tile_bytes = (uint32_t)d.r8 * 128u;
+                    const uint32_t row_bytes = (uint32_t)d.K * 2u;
                     const char* srcb = reinterpret_cast<const char*>(W + d.img_off);
-                    for (int t0i = 0; t0i < ntile && !stopped; t0i += d.tps) {
-                        const int nt = min(d.tps, ntile - t0i);
-                        const unsigned slot = issued % FK_STAGES, par = ((issued / FK_STAGES) & 1u) ^ 1u;
+                    for (int r0 = 0; r0 < d.nrows && !stopped; r0 += d.rps) {
+                        const int nr = min(d.rps, d.nrows - r0);
+                        const unsigned slot = issued % (unsigned)NST, par = ((issued / (unsigned)NST) & 1u) ^ 1u;
                         unsigned long long t0 = 0;
                         while (!mbar_try_wait(&sh->empty[slot], par)) {
                             if (sh->stop) { stopped = true; break; }
@@ -1266,9 +1250,9 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                             else if (clock64() - t0 > FK_SPIN_LIMIT) { stopped = true; break; }
                         }
                         if (stopped) break;
-                        const uint32_t bytes = (uint32_t)nt * tile_bytes;
+                        const uint32_t bytes = (uint32_t)nr * row_bytes;
                         mbar_expect_tx(&sh->full[slot], bytes);
-                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)t0i * tile_bytes, bytes, &sh->full[slot]);
+                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)r0 * row_bytes, bytes, &sh->full[slot]);
                         ++issued;
                     }
                 }
@@ -1278,7 +1262,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             while (!sh->stop) { if (clock64() - t0 > 4 * FK_SPIN_LIMIT) break; __nanosleep(200); }
             __threadfence_block();
             for (unsigned stg = (unsigned)sh->consumed; stg < issued; ++stg) {
-                const unsigned slot = stg % FK_STAGES, par = (stg / FK_STAGES) & 1u;
+                const unsigned slot = stg % (unsigned)NST, par = (stg / (unsigned)NST) & 1u;
                 unsigned long long t1 = clock64();
                 while (!mbar_try_wait(&sh->full[slot], par)) { if (clock64() - t1 > FK_SPIN_LIMIT) break; }
             }
@@ -1289,13 +1273,14 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     // ================================ consumer warps ===============================================
     FkCtx c;
     c.p = &p; c.sh = sh; c.ring = fk_smem;
-    c.bt = fk_smem + so.scratch;
     c.att = reinterpret_cast<float*>(fk_smem + so.att);
+    c.xs = reinterpret_cast<float*>(fk_smem + so.xs);
+    c.red = reinterpret_cast<float*>(fk_smem + so.red);
     c.nxt = reinterpret_cast<float*>(fk_smem + so.nxt);
     c.res0 = reinterpret_cast<float*>(fk_smem + so.res0);
     c.lh = reinterpret_cast<float*>(fk_smem + so.lh);
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
-    c.seq = 0; c.stage_ctr = 0; c.aborted = false; c.mma_phase = 0; c.tmem = sh->tmem_base;
+    c.seq = 0; c.stage_ctr = 0; c.aborted = false;
     c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
     FkSampScratch ss;
     ss.x = reinterpret_cast<float*>(fk_smem + so.scratch);
@@ -1308,6 +1293,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     int prefill_i = 0;
     int cb = 0;                      // next codebook to draw in the current frame (0 = talker code)
     bool mode1_done = false;
+    bool row1_next = false;          // the next iteration runs predictor position 1 (no draw in between)
     bool resumed = (p.mode == 0 && n_prefill == 0);   // first draw reads the plain logits / last_hidden of the previous launch
     if (resumed) {
         for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)
@@ -1325,13 +1311,21 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                 reinterpret_cast<float4*>(c.res0)[k4] = __ldcg(reinterpret_cast<const float4*>(src) + k4);
             csync();
             const bool head = (p.mode == 1) || (prefill_i == n_prefill - 1);
-            ps = FkPass{false, 1, pos, head ? p.t_head : nullptr, p.vocab};
+            ps = FkPass{false, pos, head};
+        } else if (row1_next) {
+            for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)                      // predictor position 1: codec_embed(code0) (= the running sum so far)
+                reinterpret_cast<float4*>(c.res0)[k4] = reinterpret_cast<const float4*>(c.nxt)[k4];
+            csync();
+            ps = FkPass{true, 1, true};
+            row1_next = false;
         } else {
             if (done || frame >= frame_end) break;
             // ---- draw codebook cb of this frame (:803-812 for cb 0, :863-864 otherwise) -----------------
             const int tk = cb ? 1 : 0;
             fk_phase(c, tk, FKT_SAMPLE);
             fk_mark(c, 0);
+            grid_wait(c, resumed ? 0u : c.seq);                 // the logits of the head phase have been issued everywhere
+            fk_mark(c, 1);
             float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + cb) * p.trace_stride : nullptr;
             int tok;
             if (cb == 0) tok = fk_sample(c, ss, resumed ? nullptr : p.logits_ll, p.logits, c.seq, p.vocab, 2048, p.vocab, 2150,
@@ -1362,9 +1356,8 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                     acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
                 }
                 reinterpret_cast<float4*>(c.nxt)[k4] = acc;
-                if (cb == 0) {                                                  // rows [last_hidden, codec_embed(code0)] (:854-860)
+                if (cb == 0) {                                                  // rows [last_hidden, codec_embed(code0)] (:854-860): two single-row passes
                     reinterpret_cast<float4*>(c.res0)[k4] = reinterpret_cast<const float4*>(c.lh)[k4];
-                    reinterpret_cast<float4*>(c.res0 + H)[k4] = e;
                 } else {
                     reinterpret_cast<float4*>(c.res0)[k4] = last_cb ? acc : e;  // :867-868 / :845
                 }
@@ -1374,26 +1367,23 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             fk_mark(c, 4);
             if (last_cb) {
                 n_frames = frame + 1;
-                ps = FkPass{false, 1, pos, p.t_head, p.vocab};                  // :845
+                ps = FkPass{false, pos, true};                                  // :845
             } else {
-                ps = FkPass{true, cb == 0 ? 2 : 1, cb == 0 ? 0 : cb + 1, p.c_heads + (size_t)cb * p.cp_vocab * p.cp.H, p.cp_vocab};
+                if (cb == 0) { ps = FkPass{true, 0, false}; row1_next = true; }  // predictor position 0: talker last_hidden, no head
+                else ps = FkPass{true, cb + 1, true};
             }
         }
-        consume_token(c, p, ps);
+        consume_token<KJ, NST>(c, p, ps);
         if (c.aborted) break;
         if (p.mode == 1) { pos += 1; mode1_done = true; }
         else if (prefill_i < n_prefill) { pos += 1; ++prefill_i; }
+        else if (row1_next) { }                                                 // position 0 done, position 1 follows without a draw
         else if (cb == p.cp_steps) { pos += 1; frame += 1; cb = 0; }
         else ++cb;
     }
     if (p.mode == 0 && !done && frame >= st0.max_frames) done = 1;
-    // ---- exit: publish state, stop the producer, release TMEM -----------------------------------------
-    tc_fence_before();
+    // ---- exit: publish state, stop the producer -------------------------------------------------------
     csync();
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(FK_TMEM_COLS) : "memory");
-    }
     if (tid == 0) {
         if (cta == 0) {
             p.st->pos = pos; p.st->frame = frame; p.st->done = done; p.st->n_frames = n_frames;

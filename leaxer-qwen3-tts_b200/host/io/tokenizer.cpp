@@ -1,0 +1,266 @@
+// Re-implementation of the reference tokenizer's behaviour (src/io/tokenizer.cpp), written from its
+// behavioural description and checked against the compiled reference on
+// random inputs (tests/test_host_io.py). Differences in construction, not in results:
+//   * the pre-tokeniser is a hand-written scanner equivalent to the reference's ECMAScript pattern
+//     ('s|'t|'re|'ve|'m|'ll|'d| ?[A-Za-z]+|[0-9]+| ?[^\s\w]+|\s+) instead of a std::regex compiled
+//     on every call;
+//   * the byte -> symbol table is built once; merge ranks live in one string-keyed hash map.
+// Quirks that are part of the behaviour and therefore kept: bytes 161-172 / 174-255 map to
+// themselves as single raw bytes (not to UTF-8 code points), so non-ASCII text falls back to raw
+// byte ids; characters matched by no alternative (e.g. '_') are dropped; the "#version" header line
+// of merges.txt is stored as a rank-0 pair.
+#include "tokenizer.h"
+
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+
+namespace leaxer_qwen {
+namespace io {
+namespace {
+
+struct Symbols {                          // GPT-2 byte encoder with the reference's raw-byte quirk
+    std::string of[256];
+    Symbols() {
+        int shifted = 0;
+        for (int b = 0; b < 256; ++b) {
+            const bool direct = (b >= 33 && b <= 126) || (b >= 161 && b <= 172) || (b >= 174 && b <= 255);
+            if (direct) {
+                of[b] = std::string(1, static_cast<char>(b));
+            } else {
+                const int cp = 0x100 + shifted++;           // U+0100 + number of non-direct bytes below b
+                of[b].push_back(static_cast<char>(0xC0 | (cp >> 6)));
+                of[b].push_back(static_cast<char>(0x80 | (cp & 0x3F)));
+            }
+        }
+    }
+};
+const Symbols& symbols() { static const Symbols s; return s; }
+
+inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+inline bool is_alpha(unsigned char c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); }
+inline bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
+inline bool is_word(unsigned char c) { return is_alpha(c) || is_digit(c) || c == '_'; }
+inline bool is_other(unsigned char c) { return !is_space(c) && !is_word(c); }     // [^\s\w]
+
+// length of the match of the reference pattern starting exactly at s[i], 0 if none
+size_t match_at(const std::string& s, size_t i) {
+    const size_t n = s.size();
+    const unsigned char c = static_cast<unsigned char>(s[i]);
+    if (c == '\'' && i + 1 < n) {                                    // contractions, in pattern order
+        const char a = s[i + 1];
+        const char b = (i + 2 < n) ? s[i + 2] : '\0';
+        if (a == 's' || a == 't') return 2;
+        if (a == 'r' && b == 'e') return 3;
+        if (a == 'v' && b == 'e') return 3;
+        if (a == 'm') return 2;
+        if (a == 'l' && b == 'l') return 3;
+        if (a == 'd') return 2;
+    }
+    {   // " ?[A-Za-z]+"
+        size_t j = i + ((c == ' ') ? 1 : 0);
+        size_t k = j;
+        while (k < n && is_alpha(static_cast<unsigned char>(s[k]))) ++k;
+        if (k > j) return k - i;
+    }
+    if (is_digit(c)) {                                               // "[0-9]+"
+        size_t k = i;
+        while (k < n && is_digit(static_cast<unsigned char>(s[k]))) ++k;
+        return k - i;
+    }
+    {   // " ?[^\s\w]+"   (a leading ' ' that is not followed by such a character backtracks to no space:
+        //                then s[i] == ' ' itself is \s and the alternative fails)
+        size_t j = i + ((c == ' ') ? 1 : 0);
+        size_t k = j;
+        while (k < n && is_other(static_cast<unsigned char>(s[k]))) ++k;
+        if (k > j) return k - i;
+    }
+    if (is_space(c)) {                                               // "\s+"
+        size_t k = i;
+        while (k < n && is_space(static_cast<unsigned char>(s[k]))) ++k;
+        return k - i;
+    }
+    return 0;
+}
+
+class Bpe {
+public:
+    bool read_vocab(const std::string& path);
+    bool read_merges(const std::string& path);
+    bool vocab_ok() const { return vocab_ok_; }
+    bool merges_ok() const { return merges_ok_; }
+    std::vector<int32_t> encode(const std::string& text) const;
+    std::string text_of(int32_t id) const { auto it = by_id_.find(id); return it == by_id_.end() ? std::string() : it->second; }
+    int32_t id_of(const std::string& tok) const { auto it = by_text_.find(tok); return it == by_text_.end() ? -1 : it->second; }
+
+private:
+    static std::string pair_key(const std::string& a, const std::string& b) {
+        std::string k = std::to_string(a.size());
+        k.push_back(':'); k += a; k += b;
+        return k;
+    }
+    void merge_chunk(const std::string& chunk, std::vector<std::string>& out) const;
+
+    bool vocab_ok_ = false, merges_ok_ = false;
+    std::unordered_map<std::string, int32_t> by_text_;
+    std::unordered_map<int32_t, std::string> by_id_;
+    std::unordered_map<std::string, int> rank_;
+    size_t n_merges_ = 0;
+};
+
+int hex_value(char c) {
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+    return -1;
+}
+
+bool Bpe::read_vocab(const std::string& path) {
+    by_text_.clear(); by_id_.clear();
+    vocab_ok_ = false;
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) { std::fprintf(stderr, "Failed to open vocab file: %s\n", path.c_str()); return false; }
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    if (sz <= 0 || sz > 100L * 1024 * 1024) { std::fprintf(stderr, "Invalid file size: %ld\n", sz); std::fclose(f); return false; }
+    std::string buf(static_cast<size_t>(sz), '\0');
+    const size_t got = std::fread(&buf[0], 1, buf.size(), f);
+    std::fclose(f);
+    if (got != buf.size()) { std::fprintf(stderr, "Failed to read file\n"); return false; }
+
+    const size_t n = buf.size();
+    size_t p = 0;
+    auto skip_ws = [&]() { while (p < n && std::isspace(static_cast<unsigned char>(buf[p]))) ++p; };
+    skip_ws();
+    if (p >= n || buf[p] != '{') { std::fprintf(stderr, "Expected '{' at start of JSON\n"); return false; }
+    ++p;
+    int count = 0;
+    for (;;) {
+        skip_ws();
+        if (p >= n || buf[p] == '}') break;
+        if (buf[p] == ',') { ++p; continue; }
+        if (buf[p] != '"') { std::fprintf(stderr, "Expected '\"' at position %zu\n", p); return false; }
+        ++p;
+        std::string key;
+        while (p < n && buf[p] != '"') {
+            char ch = buf[p];
+            if (ch != '\\') { key.push_back(ch); ++p; continue; }
+            if (++p >= n) { std::fprintf(stderr, "Unexpected end of file in escape sequence\n"); return false; }
+            ch = buf[p];
+            if (ch == 'n') key.push_back('\n');
+            else if (ch == 't') key.push_back('\t');
+            else if (ch == 'r') key.push_back('\r');
+            else if (ch == 'u') {
+                if (p + 4 >= n) { std::fprintf(stderr, "Invalid unicode escape\n"); return false; }
+                int cp = 0;
+                for (int i = 1; i <= 4; ++i) {
+                    const int d = hex_value(buf[p + i]);
+                    if (d < 0) { std::fprintf(stderr, "Invalid hex digit in unicode escape\n"); return false; }
+                    cp = cp * 16 + d;
+                }
+                if (cp < 0x80) key.push_back(static_cast<char>(cp));
+                else if (cp < 0x800) { key.push_back(static_cast<char>(0xC0 | (cp >> 6))); key.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
+                else { key.push_back(static_cast<char>(0xE0 | (cp >> 12))); key.push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F)));
+                       key.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }          // BMP only, surrogates not joined
+                p += 4;
+            } else key.push_back(ch);                                                    // '\\', '"' and anything else: literal
+            ++p;
+        }
+        if (p >= n) { std::fprintf(stderr, "Unexpected end of file in token string\n"); return false; }
+        ++p;
+        skip_ws();
+        if (p >= n || buf[p] != ':') { std::fprintf(stderr, "Expected ':' after token\n"); return false; }
+        ++p;
+        skip_ws();
+        if (p >= n || !std::isdigit(static_cast<unsigned char>(buf[p]))) { std::fprintf(stderr, "Expected digit for token ID\n"); return false; }
+        int32_t id = 0;
+        while (p < n && std::isdigit(static_cast<unsigned char>(buf[p]))) { id = id * 10 + (buf[p] - '0'); ++p; }
+        by_text_[key] = id;
+        by_id_[id] = key;
+        if (++count % 10000 == 0) std::fprintf(stderr, "Loaded %d tokens...\n", count);
+    }
+    std::fprintf(stderr, "Successfully loaded %d tokens\n", count);
+    if (by_text_.empty()) return false;
+    vocab_ok_ = true;
+    return true;
+}
+
+bool Bpe::read_merges(const std::string& path) {
+    rank_.clear(); n_merges_ = 0;
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) { std::fprintf(stderr, "Failed to open merges file: %s\n", path.c_str()); return false; }
+    char line[1024];
+    int rank = 0;
+    while (std::fgets(line, sizeof(line), f)) {
+        size_t len = std::strlen(line);
+        while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r')) line[--len] = '\0';
+        if (len == 0) continue;
+        char* sp = std::strchr(line, ' ');
+        if (!sp) { std::fprintf(stderr, "Invalid merge line (no space): %s\n", line); continue; }
+        *sp = '\0';
+        rank_[pair_key(line, sp + 1)] = rank;          // a repeated pair keeps its LAST rank
+        ++rank;
+        if (++n_merges_ % 10000 == 0) std::fprintf(stderr, "Loaded %zu merge rules...\n", n_merges_);
+    }
+    std::fclose(f);
+    std::fprintf(stderr, "Successfully loaded %zu merge rules\n", n_merges_);
+    merges_ok_ = true;                                  // set even when the file was empty, like the reference
+    return n_merges_ > 0;
+}
+
+void Bpe::merge_chunk(const std::string& chunk, std::vector<std::string>& out) const {
+    out.clear();
+    for (unsigned char c : chunk) out.push_back(symbols().of[c]);
+    while (out.size() > 1) {
+        int best = INT_MAX;
+        size_t at = 0;
+        for (size_t i = 0; i + 1 < out.size(); ++i) {
+            auto it = rank_.find(pair_key(out[i], out[i + 1]));
+            if (it != rank_.end() && it->second < best) { best = it->second; at = i; }    // leftmost on equal rank
+        }
+        if (best == INT_MAX) break;
+        out[at] += out[at + 1];
+        out.erase(out.begin() + static_cast<long>(at) + 1);
+    }
+}
+
+std::vector<int32_t> Bpe::encode(const std::string& text) const {
+    std::vector<int32_t> ids;
+    if (text.empty()) return ids;
+    if (!vocab_ok_) {                                   // no vocab: raw byte values
+        for (unsigned char c : text) ids.push_back(c);
+        return ids;
+    }
+    std::vector<std::string> parts;
+    size_t i = 0;
+    while (i < text.size()) {
+        const size_t m = match_at(text, i);
+        if (m == 0) { ++i; continue; }                  // matched by no alternative: dropped
+        const std::string chunk = text.substr(i, m);
+        i += m;
+        if (merges_ok_) merge_chunk(chunk, parts);
+        else { parts.clear(); for (char c : chunk) parts.push_back(std::string(1, c)); }
+        for (const std::string& tok : parts) {
+            auto it = by_text_.find(tok);
+            if (it != by_text_.end()) ids.push_back(it->second);
+            else for (unsigned char c : tok) ids.push_back(c);     // unknown symbol: its byte values
+        }
+    }
+    return ids;
+}
+
+Bpe& instance() { static Bpe t; return t; }
+
+}  // namespace
+
+bool load_vocab(const std::string& vocab_path) { return instance().read_vocab(vocab_path); }
+bool load_merges(const std::string& merges_path) { return instance().read_merges(merges_path); }
+bool is_tokenizer_ready() { return instance().vocab_ok() && instance().merges_ok(); }
+std::vector<int32_t> tokenize(const std::string& text) { return instance().encode(text); }
+std::string token_to_string(int32_t id) { return instance().text_of(id); }
+int32_t string_to_token(const std::string& token) { return instance().id_of(token); }
+
+} // namespace io
+} // namespace leaxer_qwen
