@@ -147,6 +147,9 @@ int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids,
  * `out` (each = SM clock << 8 | tag, see csrc/frame_kernel.cuh) and return their count. */
 int lqt_debug_timeline(lqt_engine* h, int32_t enable_entries, int32_t cta, uint64_t* out, int32_t out_cap);
 
+/* Profiling/debug aid: values of one activation exchange buffer of the persistent frame kernel after the last launch. */
+int lqt_debug_exchange(lqt_engine* h, int32_t which, float* out, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

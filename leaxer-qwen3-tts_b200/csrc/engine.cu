@@ -135,6 +135,8 @@ struct lqt_engine {
     unsigned long long* fk_dbg = nullptr; int fk_dbg_cap = 0, fk_dbg_cta = 0;
     FkSmemOffsets fk_so{};
     bool fk_wide = false;
+    int fk_ncta = 0;                          // CTAs of the frame kernel = 8 x co-resident clusters
+    bool fk_coop = true;
     size_t fk_smem = 0;
     // vocoder workspace
     std::map<std::string, std::pair<float*, size_t>> ws;
@@ -822,12 +824,12 @@ bf16* fk_image(lqt_engine* h, const bf16* src0, const bf16* src1, int N, int K, 
                size_t* elems_out = nullptr) {
     ImgJob j{};
     j.src0 = src0; j.src1 = src1; j.N = N; j.K = K; j.RG = RG; j.mode = mode; j.src_stride = src_stride; j.n_kv = n_kv;
-    j.rmax = fk_rmax(N, RG, mode, n_kv, h->num_sms);
-    const size_t elems = (size_t)h->num_sms * j.rmax * K + 64;
+    j.rmax = fk_rmax(N, RG, mode, n_kv, h->fk_ncta);
+    const size_t elems = (size_t)h->fk_ncta * j.rmax * K + 64;
     bf16* dst = nullptr;
     if (fk_alloc(h, &dst, elems)) return nullptr;
     j.dst = dst;
-    fk_build_image_kernel<<<dim3(h->num_sms, 4), 256, 0, h->stream>>>(j);
+    fk_build_image_kernel<<<dim3(h->fk_ncta, 4), 256, 0, h->stream>>>(j);
     if (elems_out) *elems_out = elems;
     return dst;
 }
@@ -863,36 +865,63 @@ int fk_init(lqt_engine* h) {
     };
     if (!chk(s.hidden, "hidden") || !chk(s.inter, "inter") || !chk(s.cp_hidden, "cp_hidden") || !chk(s.cp_inter, "cp_inter"))
         return 1;
-    h->fk_wide = maxK > 3072;                       // frame_kernel<6, 5> instead of <3, 8>
+    h->fk_wide = maxK > 3072;                       // frame_kernel<6, 3> instead of <3, 8>
+    const int maxV = std::max(s.vocab, s.cp_vocab);
+    if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV % 16) || maxV > FK_LAND_WORDS || (s.hidden % 16) || (s.cp_hidden % 16) || (s.inter % 16) || (s.cp_inter % 16)) {
+        h->err = "frame kernel: hidden > 2048, vocab > 3072 or a dimension that is not a multiple of 16"; return 1;
+    }
+    {   // shared-memory carve-up and the number of co-resident clusters (the grid)
+        const FkSmemLayout L = fk_smem_layout(h->fk_wide ? 3 : 4, maxV, s.hidden, maxK);
+        h->fk_so.land = (unsigned)L.land; h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.att = (unsigned)L.att; h->fk_so.xs = (unsigned)L.xs;
+        h->fk_so.red = (unsigned)L.red; h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.res0 = (unsigned)L.res0; h->fk_so.lh = (unsigned)L.lh;
+        h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
+        h->fk_smem = L.total;
+        const void* fn = h->fk_wide ? (const void*)frame_kernel<6, 3> : (const void*)frame_kernel<3, 4>;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(FK_CLUSTER * 64); cfg.blockDim = dim3(FK_THREADS); cfg.dynamicSmemBytes = h->fk_smem; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = FK_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        CK(cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg));
+        if (ncl < 1) { h->err = "frame kernel: no cluster of 8 CTAs fits on this device"; return 1; }
+        h->fk_ncta = FK_CLUSTER * ncl;
+        if (const char* e = getenv("LQT_FK_CLUSTERS")) { const int v = atoi(e); if (v >= 1 && v <= ncl) h->fk_ncta = FK_CLUSTER * v; }
+        if (getenv("LQT_DEBUG")) fprintf(stderr, "[lqt] frame kernel: %d clusters of %d CTAs co-resident, using %d CTAs, %zu B shared memory\n", ncl, FK_CLUSTER, h->fk_ncta, h->fk_smem);
+    }
     {   // row counts per CTA: warp partials [FK_RED_STRIDE] (two rows at once: 48 each), x1own
-        const int nc = h->num_sms;
+        const int nc = h->fk_ncta;
         const int worst = std::max(std::max(fk_rmax(2 * s.inter, 2, 1, s.kv_heads, nc), fk_rmax((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc)),
                                    fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc));
         const int worst_c = std::max(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
-        if (worst > FK_RED_STRIDE || worst_c > FK_RED_STRIDE) { h->err = "frame kernel: too many rows per SM"; return 1; }
+        if (worst > 64 || worst_c > 64) { h->err = "frame kernel: too many rows per SM"; return 1; }
         if (std::max(fk_rmax(s.hidden, 1, 0, s.kv_heads, nc), fk_rmax(s.cp_hidden, 1, 0, s.cp_kv_heads, nc)) > FK_X1OWN) { h->err = "frame kernel: too many down-projection rows per SM"; return 1; }
+        if (FK_CLUSTER % s.kv_heads || FK_CLUSTER % s.cp_kv_heads) { h->err = "frame kernel: kv heads must divide the cluster size (8)"; return 1; }
+        const int rpp_t = (fk_rmax(s.hidden, 1, 2, s.kv_heads, nc) + s.kv_heads - 1) / s.kv_heads, rpp_c = (fk_rmax(s.cp_hidden, 1, 2, s.cp_kv_heads, nc) + s.cp_kv_heads - 1) / s.cp_kv_heads;
+        if (std::max(rpp_t, rpp_c) > FK_RPP_MAX) { h->err = "frame kernel: too many O-projection rows per SM"; return 1; }
         if ((s.heads / s.kv_heads) * ATT_D > FK_XS_STRIDE || (s.cp_heads / s.cp_kv_heads) * ATT_D > FK_XS_STRIDE || s.heads != 2 * s.kv_heads || s.cp_heads != 2 * s.cp_kv_heads) {
             h->err = "frame kernel: needs 2 query heads per kv head"; return 1;
         }
     }
     if (s.kv_heads > FK_NGRP_MAX || s.cp_kv_heads > FK_NGRP_MAX || s.kv_heads != s.cp_kv_heads) { h->err = "frame kernel: kv head count"; return 1; }
     if (s.cp_steps + 2 > FK_CP_POS) { h->err = "frame kernel: cp_steps"; return 1; }
-    if (h->num_sms < s.kv_heads) { h->err = "frame kernel: too few SMs"; return 1; }
+    if (h->fk_ncta < s.kv_heads) { h->err = "frame kernel: too few SMs"; return 1; }
     if (s.layers > FK_MAX_TLAYERS || s.cp_layers > FK_MAX_CLAYERS) { h->err = "frame kernel: too many layers"; return 1; }
     if (fk_build_stack(h, h->tl, s.hidden, s.heads, s.kv_heads, s.inter, h->t_cos, h->t_sin, h->t_norm, &h->fk_talker, &h->fk_tl)) return 1;
     if (fk_build_stack(h, h->cl, s.cp_hidden, s.cp_heads, s.cp_kv_heads, s.cp_inter, h->c_cos, h->c_sin, h->c_norm, &h->fk_cp, &h->fk_cl)) return 1;
     {   // head / in_proj images
         h->fk_t_head = fk_image(h, h->t_head, nullptr, s.vocab, s.hidden, 1, 0, s.hidden, s.kv_heads);
         if (!h->fk_t_head) return 1;
-        const int r8 = fk_rmax(s.cp_vocab, 1, 0, s.cp_kv_heads, h->num_sms);
-        h->fk_c_head_stride = (long long)h->num_sms * r8 * s.cp_hidden;
+        const int r8 = fk_rmax(s.cp_vocab, 1, 0, s.cp_kv_heads, h->fk_ncta);
+        h->fk_c_head_stride = (long long)h->fk_ncta * r8 * s.cp_hidden;
         bf16* all = nullptr;
         if (fk_alloc(h, &all, (size_t)h->fk_c_head_stride * s.cp_steps + 64)) return 1;
         for (int j = 0; j < s.cp_steps; ++j) {
             ImgJob job{};
             job.src0 = h->c_heads + (size_t)j * s.cp_vocab * s.cp_hidden; job.N = s.cp_vocab; job.K = s.cp_hidden; job.RG = 1; job.mode = 0;
             job.src_stride = s.cp_hidden; job.n_kv = s.cp_kv_heads; job.rmax = r8; job.dst = all + (size_t)j * h->fk_c_head_stride;
-            fk_build_image_kernel<<<dim3(h->num_sms, 4), 256, 0, h->stream>>>(job);
+            fk_build_image_kernel<<<dim3(h->fk_ncta, 4), 256, 0, h->stream>>>(job);
         }
         h->fk_c_heads = all;
         if (h->c_inproj_w) {
@@ -909,31 +938,17 @@ int fk_init(lqt_engine* h) {
         auto take = [&](size_t n) { const size_t o = off; off += al(n); return o; };
         const size_t o_tx = take(2 * (size_t)s.hidden), o_tq = take(2 * qkv_t), o_tp = take(2 * (size_t)s.kv_heads * s.hidden), o_ta = take(2 * (size_t)s.inter);
         const size_t o_cx = take(2 * (size_t)s.cp_hidden), o_cq = take(2 * qkv_c), o_cp = take(2 * (size_t)s.cp_kv_heads * s.cp_hidden), o_ca = take(2 * (size_t)s.cp_inter);
-        const size_t o_pa = take((size_t)s.kv_heads * FK_NS_MAX * 2 * ATT_PSTRIDE), o_ci = take(2 * (size_t)s.cp_hidden);
+        const size_t o_pa = take((size_t)8 * FK_NS_MAX * 2 * ATT_PSTRIDE + 8 * 4096), o_ci = take(2 * (size_t)s.cp_hidden);
         const size_t o_lg = take((size_t)s.vocab), o_cl = take((size_t)s.cp_vocab);
         if (fk_alloc(h, &h->fk_arena, off)) return 1;
         h->fk_arena_words = off;
         uint2* a = h->fk_arena;
-        h->fk_talker.x = a + o_tx; h->fk_talker.qkv = a + o_tq; h->fk_talker.po = a + o_tp; h->fk_talker.act = a + o_ta;
-        h->fk_cp.x = a + o_cx; h->fk_cp.qkv = a + o_cq; h->fk_cp.po = a + o_cp; h->fk_cp.act = a + o_ca;
+        h->fk_talker.x = a + o_tx; h->fk_talker.qkv = a + o_tq; h->fk_talker.x1 = a + o_tp; h->fk_talker.act = a + o_ta;
+        h->fk_cp.x = a + o_cx; h->fk_cp.qkv = a + o_cq; h->fk_cp.x1 = a + o_cp; h->fk_cp.act = a + o_ca;
         h->fk_pa = a + o_pa; h->fk_cxin = a + o_ci; h->fk_logits_ll = a + o_lg; h->fk_clogits_ll = a + o_cl;
     }
     if (fk_alloc(h, &h->fk_ctrl, 64)) return 1;      // [1] abort flag, [32] grid arrival counter (own cache line)
     CK(cudaMallocHost((void**)&h->fk_ctrl_host, 2 * sizeof(unsigned)));
-    const int maxV = std::max(s.vocab, s.cp_vocab);
-    if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV & 3)) { h->err = "frame kernel: hidden > 2048 or vocab % 4 != 0"; return 1; }
-    const FkSmemLayout L = fk_smem_layout(h->fk_wide ? 5 : 6, maxV, s.hidden, s.hidden);
-    h->fk_so.scratch = (unsigned)L.scratch; h->fk_so.att = (unsigned)L.att; h->fk_so.xs = (unsigned)L.xs; h->fk_so.red = (unsigned)L.red;
-    h->fk_so.nxt = (unsigned)L.nxt; h->fk_so.res0 = (unsigned)L.res0; h->fk_so.lh = (unsigned)L.lh;
-    h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
-    h->fk_smem = L.total;
-    const void* fn = h->fk_wide ? (const void*)frame_kernel<6, 5> : (const void*)frame_kernel<3, 6>;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
-    int coop = 0, nb = 0;
-    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-    if (h->fk_wide) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frame_kernel<6, 5>, FK_THREADS, h->fk_smem)); }
-    else            { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, frame_kernel<3, 6>, FK_THREADS, h->fk_smem)); }
-    if (!coop || nb < 1) { h->err = "frame kernel: cooperative launch with one CTA per SM is not possible on this device"; return 1; }
     return 0;
 }
 
@@ -966,7 +981,22 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     CK(cudaMemsetAsync(h->fk_arena, 0, h->fk_arena_words * sizeof(uint2), h->stream));   // sequence numbers restart at 1
     FkSmemOffsets so = h->fk_so;
     void* args[] = {(void*)&p, (void*)&so};
-    CK(cudaLaunchCooperativeKernel(h->fk_wide ? (const void*)frame_kernel<6, 5> : (const void*)frame_kernel<3, 6>, dim3(h->num_sms), dim3(FK_THREADS), args, h->fk_smem, h->stream));
+    {
+        const void* fn = h->fk_wide ? (const void*)frame_kernel<6, 3> : (const void*)frame_kernel<3, 4>;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(h->fk_ncta); cfg.blockDim = dim3(FK_THREADS); cfg.dynamicSmemBytes = h->fk_smem; cfg.stream = h->stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = FK_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = h->fk_coop ? 2 : 1;
+        cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+        if (e != cudaSuccess && h->fk_coop) {          // cluster + cooperative rejected: all CTAs are co-resident anyway (grid = occupancy)
+            (void)cudaGetLastError();
+            h->fk_coop = false; cfg.numAttrs = 1;
+            e = cudaLaunchKernelExC(&cfg, fn, args);
+        }
+        CK(e);
+    }
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(h->fk_ctrl_host, h->fk_ctrl, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     return 0;
@@ -1429,6 +1459,20 @@ int lqt_debug_timeline(lqt_engine* h, int32_t enable_entries, int32_t cta, uint6
     const int m = (int)std::min<unsigned long long>(n, (unsigned long long)std::max(out_cap, 0));
     if (m > 0) cudaMemcpy(out, h->fk_dbg + 1, (size_t)m * 8, cudaMemcpyDeviceToHost);
     return m;
+}
+
+// Debug aid (no reference counterpart): values of one exchange buffer of the persistent frame kernel as left by the
+// last launch. which: 0 talker x, 1 talker qkv, 2 talker x1, 3 talker act, 4..7 the same for the code predictor.
+int lqt_debug_exchange(lqt_engine* h, int32_t which, float* out, int32_t n) {
+    if (!h || !out || n <= 0 || h->frame_impl != 0) return 1;
+    cudaSetDevice(h->device);
+    const FkStack& S = (which & 4) ? h->fk_cp : h->fk_talker;
+    const uint2* src = (which & 3) == 0 ? S.x : (which & 3) == 1 ? S.qkv : (which & 3) == 2 ? S.x1 : S.act;
+    std::vector<uint2> tmp((size_t)n);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(tmp.data(), src, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) { float f; memcpy(&f, &tmp[i].x, 4); out[i] = f; }
+    return 0;
 }
 
 int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,

@@ -42,13 +42,16 @@ typedef __nv_bfloat16 bf16_t;
 
 constexpr int FK_CWARPS = 8;
 constexpr int FK_CTHREADS = FK_CWARPS * 32;       // consumer threads
-constexpr int FK_THREADS = FK_CTHREADS + 32;      // + one producer warp
-constexpr int FK_STAGE_BYTES = 24 * 1024;         // 8 rows of K=1024 (16 KB used), 4 rows of K=3072, 48 rows of K=256
+constexpr int FK_THREADS = FK_CTHREADS + 128;     // + one producer warpgroup (one lane works; a whole warpgroup so that setmaxnreg can hand its registers over)
+constexpr int FK_STAGE_BYTES = 32 * 1024;         // 16 rows of K=1024, 5 rows of K=3072, 64 rows of K=256
+constexpr int FK_CLUSTER = 8;                     // CTAs per thread-block cluster (multicast + DSMEM domain)
+constexpr int FK_LAND_WORDS = 3072;               // landing buffer of a multicast vector fetch (LL words), two of them
+constexpr int FK_X1OWN = 16;                      // max rows of the down projection per CTA
+constexpr int FK_RPP_MAX = 16;                    // O-projection rows reduced per CTA (DSMEM)
 constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
 constexpr int FK_RED_STRIDE = 96;                 // warp-partial row sums: [warp][FK_RED_STRIDE]; M = 2 -> second row at +48
-constexpr int FK_X1OWN = 16;                      // max rows of the down projection per CTA
 constexpr int FK_XS_STRIDE = 512;                 // attention output rows (input of the grouped O-projection)
 constexpr int FK_MAX_TLAYERS = 32, FK_MAX_CLAYERS = 8;
 constexpr unsigned long long FK_SPIN_LIMIT = 6000000000ull;   // ~3 s of SM clocks: abort, never hang
@@ -67,7 +70,7 @@ struct FkLayer {
 struct FkStack {
     int n_layers, H, heads, kv_heads, inter;
     const float *cos, *sin, *final_norm;
-    uint2 *x, *qkv, *po, *act;            // LL buffers: [2][H] [2][qkv_dim] [2][n_kv][H] [2][inter]
+    uint2 *x, *qkv, *x1, *act;            // LL buffers: layer output [H], projections [qkv_dim], post-attention stream [H], SwiGLU [inter]
 };
 
 struct FkParams {
@@ -123,17 +126,33 @@ LQT_DEVINL void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-LQT_DEVINL void csync() { asm volatile("bar.sync 1, %0;" ::"n"(FK_CTHREADS) : "memory"); }
-LQT_DEVINL uint2 lds64(const void* p) {
+// 1-D TMA bulk copy global -> the same shared offset of every CTA in `mask` of this cluster; each destination's
+// mbarrier (same offset) receives complete_tx for the bytes written to it
+LQT_DEVINL void bulk_g2s_mc(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+LQT_DEVINL uint32_t dsmem_addr(const void* local, unsigned cta_rank) {       // address of `local` in another CTA of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(cta_rank));
+    return r;
+}
+LQT_DEVINL void st_ll_dsmem(uint32_t addr, float v, unsigned seq) {
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+}
+LQT_DEVINL uint2 ld_ll_smem(const uint2* p) {
     uint2 r;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem_u32(p)));
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem_u32(p)) : "memory");
     return r;
 }
-LQT_DEVINL uint4 lds128(const void* p) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
-    return r;
+LQT_DEVINL void cluster_sync_all() {                // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+LQT_DEVINL void csync() { asm volatile("bar.sync 1, %0;" ::"n"(FK_CTHREADS) : "memory"); }
+// plain loads (not asm volatile) so that ptxas can batch them ahead of the FMAs; visibility of the TMA
+// writes is ordered by the mbarrier wait (asm volatile with a memory clobber) that precedes them
+LQT_DEVINL uint2 lds64(const void* p) { return *reinterpret_cast<const uint2*>(p); }
+LQT_DEVINL uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 // LL exchange: 8-byte (value, sequence) words. volatile accesses always go to L2 (the coherence point).
 LQT_DEVINL void st_ll(uint2* p, float v, unsigned seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
@@ -171,7 +190,9 @@ struct FkShared {
     uint32_t sel_prefix; int sel_k;
     int tok; float fsum;
     float ssred[2][FK_CWARPS];        // [phase parity][warp]: partial sums of squares (RMSNorm)
-    float x1own[FK_X1OWN];         // post-attention residual stream at the rows of this CTA's down-projection slice
+    float x1own[FK_X1OWN];            // post-attention stream at the rows of this CTA's down-projection slice (its residual)
+    uint64_t land_bar[2];             // multicast landing buffers: complete_tx from all CTAs of the cluster
+    uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
     FkDesc desc[2][10];           // [stack][phase kind]
 };
 
@@ -181,7 +202,12 @@ struct FkCtx {
     unsigned char* ring;      // nstages * FK_STAGE_BYTES
     float* att;               // attention scratch
     float* xs;                // attention output rows [2][FK_XS_STRIDE] (input of the grouped O-projection)
-    float* red;               // [2 parity][FK_CWARPS][FK_RED_STRIDE] warp-partial row sums
+    float* xp;                // plain input vector of the current matrix-vector phase [maxK]
+    uint2* land;              // [2][FK_LAND_WORDS] multicast landing buffers
+    unsigned land_n;          // fetches so far (buffer = land_n & 1, barrier parity = (land_n >> 1) & 1)
+    const uint2* land_a;      // where this layer's input row landed (residual of the O-projection)
+    unsigned rank;            // CTA rank in the cluster
+    uint2* dbg_pg;            // FK_NO_DSMEM: partials through global memory
     float* nxt;               // running next talker input [H]
     float* res0;              // layer-0 input rows of the current pass [M][H0] (also its residual)
     float* lh;                // talker last_hidden [H] (code-predictor row 0, src/tts_onnx.cpp:859)
@@ -238,7 +264,6 @@ LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, in
     FkDesc d;
     d.row0 = s.row0; d.nrows = s.nrows; d.K = K; d.RG = RG;
     d.rps = max(1, FK_STAGE_BYTES / (K * 2));
-    if (kind != FKT_C) { const int grp = (K <= 1024) ? 8 : 4; if (d.rps > grp) d.rps -= d.rps % grp; }
     d.img_off = (unsigned)cta * (unsigned)rmax * (unsigned)K;
     d.pad0_ = 0; d.pad1_ = 0;
     return d;
@@ -383,92 +408,83 @@ LQT_DEVINL float reduce8(const float (&a)[8], int lane) {
     return s;
 }
 
-// sums of 4 values over the 32 lanes: on return every lane holds the full-warp sum of a[lane >> 3] (6 shuffles)
-LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
-    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
-    float d[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b4 ? a[i] : a[i + 2], keep = b4 ? a[i + 2] : a[i];
-        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    const float send = b3 ? d[0] : d[1], keep = b3 ? d[1] : d[0];
-    float s = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    return s;
-}
-
-// One group of NR rows x NJ 1024-column chunks, branch-free: all weight loads are issued before the FMAs.
-// Rows beyond nr re-read the last row (discarded), chunks a thread does not own read offset 0 with x = 0.
-template <int KJ, int NJ, int NR>
-LQT_DEVINL void ks_group(const unsigned char* sb, int rowbytes, int nr, const int (&coff)[KJ], const float (&xr)[KJ][4],
-                         float* red, int lane) {
-    uint2 w[NR][NJ];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const unsigned char* rb = sb + min(r, nr - 1) * rowbytes;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) w[r][j] = lds64(rb + coff[j]);
-    }
-    float a[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        a[r] = 0.f;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            a[r] = fmaf(bf16lo(w[r][j].x), xr[j][0], a[r]); a[r] = fmaf(bf16hi(w[r][j].x), xr[j][1], a[r]);
-            a[r] = fmaf(bf16lo(w[r][j].y), xr[j][2], a[r]); a[r] = fmaf(bf16hi(w[r][j].y), xr[j][3], a[r]);
-        }
-    }
-    constexpr int SH = (NR == 8) ? 2 : 3;                       // log2(lanes per row) after the butterfly
-    const int rl = lane >> SH;
-    float s;
-    if (NR == 8) s = reduce8(reinterpret_cast<const float(&)[8]>(a), lane);
-    else         s = reduce4(reinterpret_cast<const float(&)[4]>(a), lane);
-    if ((lane & ((1 << SH) - 1)) == 0 && rl < nr) red[rl] = s;
-}
-
-// xr[j][i] = input element j*1024 + 4*tid + i (zero beyond K). Leaves the eight warp partials of every row in
-// c.red (parity of c.seq); the caller synchronises and runs the epilogue.
-template <int KJ, int NST>
-LQT_DEVINL void gemv_ks(FkCtx& c, const FkDesc& d, const float (&xr)[KJ][4]) {
-    float* red = c.red + (c.seq & 1u) * (FK_CWARPS * FK_RED_STRIDE) + c.warp * FK_RED_STRIDE;
-    const int rowbytes = d.K * 2, tid4 = c.tid * 4;
-    const int kj = (d.K + 1023) >> 10;
-    int coff[KJ];
-#pragma unroll
-    for (int j = 0; j < KJ; ++j) coff[j] = (j * 1024 + tid4 < d.K) ? j * 2048 + c.tid * 8 : 0;
+// ------------------------------------------------------------------------------------------------
+// Row-per-warp matrix-vector product (all phases except the grouped O-projection, which has its own below).
+// Row group q (RG = 1 row, or RG = 2 for a gate/up pair) belongs to warp q % 8; the 32 lanes split K
+// (lane l owns columns 256*i + 8*l .. +7 of every 1024-column chunk: conflict-free 16-byte shared loads),
+// the input vector is read from its plain copy in shared memory (xp), and up to eight dot products per
+// warp are reduced with warp shuffles. On return lane s (< 8) holds the sum of slot s:
+// slot s = (q / 8) * RG + t  <->  row ((s / RG) * 8 + warp) * RG + t.
+// No cross-warp reduction, no CTA barrier: the epilogue runs on the lanes that hold the sums.
+// ------------------------------------------------------------------------------------------------
+template <int NST, int RG>
+LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
+    const int K = d.K, rowbytes = K * 2;
+    const int nch = (K + 1023) >> 10;
     const int nst = (d.nrows + d.rps - 1) / d.rps;
-    int row = 0;
-#pragma unroll 1
-    for (int st = 0; st < nst; ++st) {
-        const unsigned ast = c.stage_ctr + st, slot = ast % (unsigned)NST;
-        wait_full(c, ast, NST);
-        const int nrs = min(d.rps, d.nrows - row);
-        const unsigned char* sb = c.ring + (size_t)slot * FK_STAGE_BYTES;
-        if (kj == 1) {
-#pragma unroll 1
-            for (int r0 = 0; r0 < nrs; r0 += 8) ks_group<KJ, 1, 8>(sb + (size_t)r0 * rowbytes, rowbytes, nrs - r0, coff, xr, red + row + r0, c.lane);
-        } else if (kj <= 3 || KJ <= 3) {
-#pragma unroll 1
-            for (int r0 = 0; r0 < nrs; r0 += 4) ks_group<KJ, 3, 4>(sb + (size_t)r0 * rowbytes, rowbytes, nrs - r0, coff, xr, red + row + r0, c.lane);
-        } else {
-#pragma unroll 1
-            for (int r0 = 0; r0 < nrs; r0 += 4) ks_group<KJ, KJ, 4>(sb + (size_t)r0 * rowbytes, rowbytes, nrs - r0, coff, xr, red + row + r0, c.lane);
+    float xk[32];
+    auto load_chunk = [&](int ch) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = ch * 1024 + i * 256 + c.lane * 8;
+            float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+            if (k < K) { u0 = *reinterpret_cast<const float4*>(xp + k); u1 = *reinterpret_cast<const float4*>(xp + k + 4); }
+            xk[i * 8 + 0] = u0.x; xk[i * 8 + 1] = u0.y; xk[i * 8 + 2] = u0.z; xk[i * 8 + 3] = u0.w;
+            xk[i * 8 + 4] = u1.x; xk[i * 8 + 5] = u1.y; xk[i * 8 + 6] = u1.z; xk[i * 8 + 7] = u1.w;
         }
+    };
+    if (nch == 1) load_chunk(0);
+    float mine = 0.f;                             // lane s keeps the sum of slot s
+    int cur = 0;                                  // next ring stage of this phase this warp has not released yet
+    bool have = false;                            // full[cur] already observed
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) {
+        const int r = ((s / RG) * 8 + c.warp) * RG + (s % RG);
+        if (r >= d.nrows) break;                  // warp-uniform; rows grow with s
+        const int g = r / d.rps;
+        while (cur < g) {                         // stages that hold no (further) row of this warp
+            if (!have) wait_full(c, c.stage_ctr + cur, NST);
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&c.sh->empty[(c.stage_ctr + cur) % (unsigned)NST]);
+            ++cur; have = false;
+        }
+        if (!have) { wait_full(c, c.stage_ctr + cur, NST); have = true; }
+        const unsigned char* wr = c.ring + (size_t)((c.stage_ctr + g) % (unsigned)NST) * FK_STAGE_BYTES + (size_t)(r - g * d.rps) * rowbytes + c.lane * 16;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ++ch) {
+            if (nch > 1) load_chunk(ch);
+            uint4 w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = (ch * 1024 + i * 256 < K) ? lds128(wr + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
+            a0 = fmaf(bf16lo(w[0].x), xk[0], a0); a0 = fmaf(bf16hi(w[0].x), xk[1], a0); a0 = fmaf(bf16lo(w[0].y), xk[2], a0); a0 = fmaf(bf16hi(w[0].y), xk[3], a0);
+            a0 = fmaf(bf16lo(w[0].z), xk[4], a0); a0 = fmaf(bf16hi(w[0].z), xk[5], a0); a0 = fmaf(bf16lo(w[0].w), xk[6], a0); a0 = fmaf(bf16hi(w[0].w), xk[7], a0);
+            a1 = fmaf(bf16lo(w[1].x), xk[8], a1); a1 = fmaf(bf16hi(w[1].x), xk[9], a1); a1 = fmaf(bf16lo(w[1].y), xk[10], a1); a1 = fmaf(bf16hi(w[1].y), xk[11], a1);
+            a1 = fmaf(bf16lo(w[1].z), xk[12], a1); a1 = fmaf(bf16hi(w[1].z), xk[13], a1); a1 = fmaf(bf16lo(w[1].w), xk[14], a1); a1 = fmaf(bf16hi(w[1].w), xk[15], a1);
+            a2 = fmaf(bf16lo(w[2].x), xk[16], a2); a2 = fmaf(bf16hi(w[2].x), xk[17], a2); a2 = fmaf(bf16lo(w[2].y), xk[18], a2); a2 = fmaf(bf16hi(w[2].y), xk[19], a2);
+            a2 = fmaf(bf16lo(w[2].z), xk[20], a2); a2 = fmaf(bf16hi(w[2].z), xk[21], a2); a2 = fmaf(bf16lo(w[2].w), xk[22], a2); a2 = fmaf(bf16hi(w[2].w), xk[23], a2);
+            a3 = fmaf(bf16lo(w[3].x), xk[24], a3); a3 = fmaf(bf16hi(w[3].x), xk[25], a3); a3 = fmaf(bf16lo(w[3].y), xk[26], a3); a3 = fmaf(bf16hi(w[3].y), xk[27], a3);
+            a3 = fmaf(bf16lo(w[3].z), xk[28], a3); a3 = fmaf(bf16hi(w[3].z), xk[29], a3); a3 = fmaf(bf16lo(w[3].w), xk[30], a3); a3 = fmaf(bf16hi(w[3].w), xk[31], a3);
+        }
+        const float a = warp_sum((a0 + a1) + (a2 + a3));
+        if (c.lane == s) mine = a;
+    }
+    while (cur < nst) {
+        if (!have) wait_full(c, c.stage_ctr + cur, NST);
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.sh->empty[slot]);       // this warp is done with the stage
-        row += nrs;
+        if (c.lane == 0) mbar_arrive(&c.sh->empty[(c.stage_ctr + cur) % (unsigned)NST]);
+        ++cur; have = false;
     }
     c.stage_ctr += nst;
+    return mine;
 }
 
 // Row-per-warp product for the grouped O-projection (K = rep*128 <= 512, input row in c.xs): warp w owns
-// rows w, w + 8, ... of every stage; results are published straight from the reduction (no CTA barrier).
+// rows w, w + 8, ... of every stage. The n_kv CTAs that hold the partials of the same rows (one per kv group) sit
+// in the same cluster: partial (row r) goes straight from the reduction into the shared memory of partner
+// r / rpp as a (value, sequence) word (DSMEM store, no barrier); the partner sums them (reduce_partials).
 template <int NST, int NC>
-LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, uint2* out) {
+LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
     const int K = d.K, rowbytes = K * 2;
     float x0[NC][8];
     int coff[NC];
@@ -481,6 +497,7 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, uint2* out) {
         if (act) { u0 = *reinterpret_cast<const float4*>(c.xs + k); u1 = *reinterpret_cast<const float4*>(c.xs + k + 4); }
         x0[cc][0] = u0.x; x0[cc][1] = u0.y; x0[cc][2] = u0.z; x0[cc][3] = u0.w; x0[cc][4] = u1.x; x0[cc][5] = u1.y; x0[cc][6] = u1.z; x0[cc][7] = u1.w;
     }
+    const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
     const int nst = (d.nrows + d.rps - 1) / d.rps;
     int row = 0;
 #pragma unroll 1
@@ -512,7 +529,15 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, uint2* out) {
             }
             const float s = reduce8(a, c.lane);
             const int r = r0 + c.warp + 8 * (c.lane >> 2);
-            if ((c.lane & 3) == 0 && r < nrs) st_ll(out + d.row0 + row + r, s, c.seq);
+            if ((c.lane & 3) == 0 && r < nrs) {
+                const int rr = row + r, tg = rr / rpp;
+#ifdef FK_NO_DSMEM                                // bisecting aid: partials through global memory
+                st_ll(c.dbg_pg + (size_t)g * 4096 + d.row0 + rr, s, c.seq);
+                (void)tg; (void)base;
+#else
+                st_ll_dsmem(dsmem_addr(&c.sh->redc[g][rr - tg * rpp], base + (unsigned)tg), s, c.seq);
+#endif
+            }
         }
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.sh->empty[slot]);
@@ -521,16 +546,10 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, uint2* out) {
     c.stage_ctr += nst;
 }
 template <int NST>
-LQT_DEVINL void gemv_rw(FkCtx& c, const FkDesc& d, uint2* out) {
-    if (d.K <= 256) gemv_rw_n<NST, 1>(c, d, out); else gemv_rw_n<NST, 2>(c, d, out);
+LQT_DEVINL void gemv_rw(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
+    if (d.K <= 256) gemv_rw_n<NST, 1>(c, d, n_kv, rpp); else gemv_rw_n<NST, 2>(c, d, n_kv, rpp);
 }
 
-LQT_DEVINL float red_total(const float* red, int idx) {        // fixed order: bit-reproducible
-    float s = red[idx];
-#pragma unroll
-    for (int w = 1; w < FK_CWARPS; ++w) s += red[w * FK_RED_STRIDE + idx];
-    return s;
-}
 LQT_DEVINL float ss_rstd(FkCtx& c, int K, float eps) {
     const float* q = &c.sh->ssred[c.seq & 1u][0];
     float t = q[0];
@@ -810,38 +829,91 @@ struct FkPass { bool is_cp; int pos0; bool head; };
 
 LQT_DEVINL void f4_to(float (&d)[4], const float4& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
 
-// this thread's columns (4*tid.. of every 1024-chunk, J chunks) of an LL vector of K words tagged `want`
-template <int J>
-LQT_DEVINL void ll_row(FkCtx& c, const uint2* src, int K, unsigned want, float (&out)[J][4]) {
-    const int tid4 = c.tid * 4;
-    FkRaw4 raw[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) { const int k = j * 1024 + tid4; raw[j] = ll_issue4(src + (k < K ? k : 0)); }
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const int k = j * 1024 + tid4;
-        const float4 v = ll_finish4(c, raw[j], src + (k < K ? k : 0), want);
-        if (k < K) f4_to(out[j], v);
-        else { out[j][0] = 0.f; out[j][1] = 0.f; out[j][2] = 0.f; out[j][3] = 0.f; }
+// ------------------------------------------------------------------------------------------------
+// Multicast fetch of a broadcast vector. Every CTA needs every activation vector, and 148 SMs reading the
+// same freshly written lines is what saturates the L2 slices that hold them (tools/bench_exchange.cu:
+// ~2 TB/s aggregate, which also delays the weight stream). So the eight CTAs of a cluster share the
+// read: CTA r copies words [r*W/8, (r+1)*W/8) ONCE from L2 into the landing buffer of all eight
+// (cp.async.bulk .multicast::cluster), every landing barrier collects complete_tx from all eight copies.
+// Two landing buffers alternate; a buffer is rewritten two fetches later, i.e. behind at least one grid
+// hand-over that every reader of its previous content has already passed.
+// Readers validate the (value, sequence) words they use; a word whose store had not landed in L2 when the
+// copy read it is re-polled from global memory and patched in place.
+// ------------------------------------------------------------------------------------------------
+LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W) {
+    const unsigned b = c.land_n & 1u, par = (c.land_n >> 1) & 1u;
+    uint2* dst = c.land + b * FK_LAND_WORDS;
+    uint64_t* bar = &c.sh->land_bar[b];
+#ifdef FK_NO_MC                                   // bisecting aid: plain per-CTA copy instead of the multicast
+    for (int w = c.tid * 2; w < W; w += FK_CTHREADS * 2) *reinterpret_cast<uint4*>(dst + w) = ld_ll2(src + w);
+    csync();
+    ++c.land_n;
+    (void)par; (void)bar;
+    return dst;
+#endif
+    if (c.tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic writes to the buffer (patches, sampler scratch)
+        mbar_expect_tx(bar, (uint32_t)W * 8u);
+        const int share = W / FK_CLUSTER;                                // W % 16 == 0: 16-byte multiples
+        bulk_g2s_mc(dst + c.rank * share, src + c.rank * share, (uint32_t)share * 8u, bar, (uint16_t)((1u << FK_CLUSTER) - 1u));
     }
+    if (!mbar_try_wait(bar, par)) {
+        if (!wait_full_slow(bar, par, c.p->ctrl)) c.aborted = true;
+    }
+    ++c.land_n;
+    return dst;
 }
-// x += sum over the kv groups of the O-projection partials, in group order
+// this thread's columns (4*tid.. of every 1024-chunk, J chunks) of a landed LL vector of K words tagged `want`
 template <int J>
-LQT_DEVINL void ll_add_partials(FkCtx& c, const uint2* po, int n_kv, int H, unsigned want, float (&x)[J][4]) {
+LQT_DEVINL void land_row(FkCtx& c, uint2* land, const uint2* src, int K, unsigned want, float (&out)[J][4]) {
     const int tid4 = c.tid * 4;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int k = j * 1024 + tid4;
-        const bool act = k < H;
-        FkRaw4 raw[FK_NGRP_MAX];
-#pragma unroll
-        for (int g = 0; g < FK_NGRP_MAX; ++g) raw[g] = ll_issue4(po + (size_t)(g < n_kv ? g : 0) * H + (act ? k : 0));
-#pragma unroll
-        for (int g = 0; g < FK_NGRP_MAX; ++g) {
-            const float4 b = ll_finish4(c, raw[g], po + (size_t)(g < n_kv ? g : 0) * H + (act ? k : 0), want);
-            if (g < n_kv && act) { x[j][0] += b.x; x[j][1] += b.y; x[j][2] += b.z; x[j][3] += b.w; }
+        out[j][0] = 0.f; out[j][1] = 0.f; out[j][2] = 0.f; out[j][3] = 0.f;
+        if (k < K) {
+            uint4 a = *reinterpret_cast<const uint4*>(land + k), b = *reinterpret_cast<const uint4*>(land + k + 2);
+            if (a.y != want || a.w != want || b.y != want || b.w != want) {
+                const FkLL4 q = ll_poll4_slow(src + k, want, &c.sh->aborted, c.p->ctrl);
+                a = q.a; b = q.b;
+                *reinterpret_cast<uint4*>(land + k) = a; *reinterpret_cast<uint4*>(land + k + 2) = b;
+            }
+            out[j][0] = __uint_as_float(a.x); out[j][1] = __uint_as_float(a.z); out[j][2] = __uint_as_float(b.x); out[j][3] = __uint_as_float(b.z);
         }
     }
+}
+__device__ __noinline__ uint2 redc_poll_slow(const uint2* p, unsigned seq, volatile int* aborted, unsigned* ctrl) {
+    uint2 a;
+    int spins = 0; unsigned long long t0 = 0;
+    do {
+        if ((++spins & 1023) == 0 && ll_giveup_slow(aborted, ctrl, &t0)) { a = ld_ll_smem(p); break; }
+        a = ld_ll_smem(p);
+    } while (a.y != seq);
+    return a;
+}
+// warp 0: sum the O-projection partials that the partner CTAs pushed into c.sh->redc (+ residual) for the rows this CTA
+// reduces, publish the post-attention stream x1 (global LL), then signal the grid
+LQT_DEVINL void reduce_partials(FkCtx& c, const FkDesc& d, int n_kv, int rpp, const float* res_plain, const uint2* res_land, uint2* x1) {
+    if (c.warp != 0) return;
+    const int g = (int)(c.rank % (unsigned)n_kv);
+    const int r0 = g * rpp, nmine = max(0, min(d.nrows, r0 + rpp) - r0);
+    if (c.lane < nmine) {
+        const int row = d.row0 + r0 + c.lane;
+        float acc = res_plain ? res_plain[row] : __uint_as_float(res_land[row].x);
+#pragma unroll 1
+        for (int gg = 0; gg < n_kv; ++gg) {
+#ifdef FK_NO_DSMEM
+            acc += ll_poll1(c, c.dbg_pg + (size_t)gg * 4096 + row, c.seq);
+#else
+            uint2 v = ld_ll_smem(&c.sh->redc[gg][c.lane]);
+            if (v.y != c.seq) v = redc_poll_slow(&c.sh->redc[gg][c.lane], c.seq, &c.sh->aborted, c.p->ctrl);
+            acc += __uint_as_float(v.x);
+#endif
+        }
+        st_ll(x1 + row, acc, c.seq);
+    }
+    __syncwarp();
+    if (c.lane == 0) grid_arrive(c);
 }
 
 template <int KJ, int NST>
@@ -851,13 +923,9 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
     const FkStack& S = is_cp ? p.cp : p.talker;
     const int tk = is_cp ? 1 : 0;
     const int H = S.H, n_kv = S.kv_heads;
-    const int H0 = p.talker.H;                                   // width of the row in res0
     const bool inproj = is_cp && p.c_inproj_w != nullptr;
     const int total = pass_ops(S.n_layers, inproj, ps.head);
     const int tid4 = c.tid * 4;
-    float xin[HJ][4];                                            // layer input (residual stream), this thread's columns
-#pragma unroll
-    for (int j = 0; j < HJ; ++j) { xin[j][0] = 0.f; xin[j][1] = 0.f; xin[j][2] = 0.f; xin[j][3] = 0.f; }
 
     for (int it = 0; it < total && !c.aborted; ++it) {
         const FkOp op = pass_op(it, S.n_layers, inproj);
@@ -867,10 +935,15 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         const unsigned want = c.seq - 1;
         fk_phase(c, tk, kind);
         fk_mark(c, 0);
-        grid_wait(c, want);
-        fk_mark(c, 1);
         const FkLayer& L = is_cp ? p.c_layers[l] : p.t_layers[l];
         const FkDesc d = c.sh->desc[tk][kind];
+        // RMSNorm weight of this phase: fetched BEFORE the grid hand-over (independent of the activations)
+        const float* nw = (kind == FKT_A) ? L.ln1 : (kind == FKT_D) ? L.ln2 : (kind == FKT_HEAD) ? S.final_norm : nullptr;
+        float4 nwv[HJ];
+#pragma unroll
+        for (int j = 0; j < HJ; ++j)
+            nwv[j] = (nw && j * 1024 + tid4 < H) ? __ldg(reinterpret_cast<const float4*>(nw + j * 1024 + tid4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        grid_wait(c, want);
         // the layer input row: res0 (smem) for layer 0 without in_proj, else an LL buffer
         const bool in_res0 = (l == 0 && !inproj);
         const uint2* lin = (l == 0) ? p.cxin : S.x;           // (only read when !in_res0)
@@ -888,38 +961,36 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             else       talker_attn_combine(c, ps.pos0, want);
             fk_mark(c, 3);
             if (c.sh->aborted) { c.aborted = true; break; }
-            gemv_rw<NST>(c, d, S.po + (size_t)(c.cta % n_kv) * H);
-            csync();
-            if (c.tid == 0) grid_arrive(c);
+            const int rpp = (d.nrows + n_kv - 1) / n_kv;
+            gemv_rw<NST>(c, d, n_kv, rpp);
+            fk_mark(c, 5);
+            reduce_partials(c, d, n_kv, rpp, in_res0 ? c.res0 : nullptr, c.land_a, S.x1);
             fk_mark(c, 6);
-            if (c.aborted) break;
+            if (c.aborted || c.sh->aborted) { c.aborted = true; break; }
             continue;
         }
-        // ---- K-split phases: inputs -> registers ------------------------------------------------------
-        float xr[KJ][4];
+        // ---- K phases: stage the input vector as plain floats (x * w_norm for the normalised phases) ------------
+        float xin[HJ][4];                                      // the raw row (this thread's columns): sum of squares, last_hidden
 #pragma unroll
-        for (int j = 0; j < KJ; ++j) { xr[j][0] = 0.f; xr[j][1] = 0.f; xr[j][2] = 0.f; xr[j][3] = 0.f; }
-        const float* nw = nullptr;
+        for (int j = 0; j < HJ; ++j) { xin[j][0] = 0.f; xin[j][1] = 0.f; xin[j][2] = 0.f; xin[j][3] = 0.f; }
+        const float* xp = c.xp;
         switch (kind) {
-            case FKT_INPROJ: {
-#pragma unroll
-                for (int j = 0; j < KJ; ++j)
-                    if (j * 1024 + tid4 < H0) f4_to(xr[j], *reinterpret_cast<const float4*>(c.res0 + j * 1024 + tid4));
-                break;
-            }
+            case FKT_INPROJ: xp = c.res0; break;               // plain row in shared memory already, no norm
             case FKT_A: {
                 if (in_res0) {
 #pragma unroll
                     for (int j = 0; j < HJ; ++j)
                         if (j * 1024 + tid4 < H) f4_to(xin[j], *reinterpret_cast<const float4*>(c.res0 + j * 1024 + tid4));
                 } else {
-                    ll_row<HJ>(c, lin, H, want, xin);
+                    uint2* land = mc_fetch(c, lin, H);
+                    land_row<HJ>(c, land, lin, H, want, xin);
+                    c.land_a = land;
                 }
-                nw = L.ln1;
                 break;
             }
             case FKT_D: {
-                ll_add_partials<HJ>(c, S.po, n_kv, H, want, xin);
+                uint2* land = mc_fetch(c, S.x1, H);
+                land_row<HJ>(c, land, S.x1, H, want, xin);
                 const FkDesc& de = c.sh->desc[tk][FKT_E];
 #pragma unroll
                 for (int j = 0; j < HJ; ++j)
@@ -928,14 +999,26 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                         const unsigned rel = (unsigned)(j * 1024 + tid4 + i - de.row0);
                         if (rel < (unsigned)de.nrows) c.sh->x1own[rel] = xin[j][i];
                     }
-                nw = L.ln2;
                 break;
             }
-            case FKT_E: ll_row<KJ>(c, S.act, d.K, want, xr); break;
-            default:   // FKT_HEAD: final norm + head
-                ll_row<HJ>(c, S.x, H, want, xin);
-                nw = S.final_norm;
+            case FKT_E: {
+#pragma unroll 1
+                for (int w0 = 0; w0 < d.K; w0 += FK_LAND_WORDS) {          // wide models: two landing-buffer loads
+                    const int wn = min(FK_LAND_WORDS, d.K - w0);
+                    float t3[3][4];
+                    uint2* land = mc_fetch(c, S.act + w0, wn);
+                    land_row<3>(c, land, S.act + w0, wn, want, t3);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (j * 1024 + tid4 < wn) *reinterpret_cast<float4*>(c.xp + w0 + j * 1024 + tid4) = make_float4(t3[j][0], t3[j][1], t3[j][2], t3[j][3]);
+                }
                 break;
+            }
+            default: {  // FKT_HEAD: final norm + head
+                uint2* land = mc_fetch(c, S.x, H);
+                land_row<HJ>(c, land, S.x, H, want, xin);
+                break;
+            }
         }
         fk_mark(c, 2);
         if (nw) {                                              // RMSNorm, folded: product on x*w, 1/rms in the epilogue
@@ -943,57 +1026,55 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
 #pragma unroll
             for (int j = 0; j < HJ; ++j) {
                 if (j * 1024 + tid4 < H) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(nw + j * 1024 + tid4));
+                    const float4 w = nwv[j];
                     ss = fmaf(xin[j][0], xin[j][0], ss); ss = fmaf(xin[j][1], xin[j][1], ss);
                     ss = fmaf(xin[j][2], xin[j][2], ss); ss = fmaf(xin[j][3], xin[j][3], ss);
-                    xr[j][0] = xin[j][0] * w.x; xr[j][1] = xin[j][1] * w.y; xr[j][2] = xin[j][2] * w.z; xr[j][3] = xin[j][3] * w.w;
+                    *reinterpret_cast<float4*>(c.xp + j * 1024 + tid4) = make_float4(xin[j][0] * w.x, xin[j][1] * w.y, xin[j][2] * w.z, xin[j][3] * w.w);
                 }
             }
             ss_publish(c, ss);
         }
-        fk_mark(c, 3);
+        if (c.aborted || c.sh->aborted) { c.aborted = true; }
+        if (kind != FKT_INPROJ) csync();                       // the plain input vector (and the sum-of-squares partials) are complete
         if (c.sh->aborted) { c.aborted = true; break; }
-        gemv_ks<KJ, NST>(c, d, xr);
-        fk_mark(c, 5);
-        csync();
-        // ---- epilogue: warp partials -> outputs (warp 0 publishes everything, then signals the grid) ----------
+        // ---- product + epilogue on the lanes that hold the sums ----------------------------------------------
         {
-            const float* red = c.red + (c.seq & 1u) * (FK_CWARPS * FK_RED_STRIDE);
             const float rs = nw ? ss_rstd(c, H, p.eps) : 1.f;
-            if (c.warp == 0) {
-                if (kind == FKT_D) {
-                    const int nq = d.nrows >> 1;
-                    for (int q = c.lane; q < nq; q += 32) {
-                        const float g = red_total(red, 2 * q) * rs, u = red_total(red, 2 * q + 1) * rs;
-                        st_ll(S.act + (d.row0 >> 1) + q, silu_f(g) * u, c.seq);
-                    }
-                } else {
-                    for (int r = c.lane; r < d.nrows; r += 32) {
-                        const int n = d.row0 + r;
-                        const float v = red_total(red, r) * rs;
-                        if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
-                        else if (kind == FKT_E) st_ll(S.x + n, c.sh->x1own[r] + v, c.seq);
-                        else if (kind == FKT_INPROJ) st_ll(p.cxin + n, v + __ldg(p.c_inproj_b + n), c.seq);
-                        else {
-                            st_ll((is_cp ? p.clogits_ll : p.logits_ll) + n, v, c.seq);
-                            (is_cp ? p.clogits : p.logits)[n] = v;
-                        }
+            const int slot = c.lane;
+            const bool lead = c.lane < 8;
+            if (kind == FKT_D) {
+                const float v = gemv_rpw<NST, 2>(c, d, xp);
+                fk_mark(c, 5);
+                const float up = __shfl_down_sync(0xffffffffu, v, 1);          // slot s + 1 = the up row of the same pair
+                const int q = (slot >> 1) * 8 + c.warp;
+                if (lead && (slot & 1) == 0 && 2 * q < d.nrows) st_ll(S.act + (d.row0 >> 1) + q, silu_f(v * rs) * (up * rs), c.seq);
+            } else {
+                const float v = gemv_rpw<NST, 1>(c, d, xp) * rs;
+                fk_mark(c, 5);
+                const int r = slot * 8 + c.warp, n = d.row0 + r;
+                if (lead && r < d.nrows) {
+                    if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
+                    else if (kind == FKT_E) st_ll(S.x + n, c.sh->x1own[r] + v, c.seq);
+                    else if (kind == FKT_INPROJ) st_ll(p.cxin + n, v + __ldg(p.c_inproj_b + n), c.seq);
+                    else {
+                        st_ll((is_cp ? p.clogits_ll : p.logits_ll) + n, v, c.seq);
+                        (is_cp ? p.clogits : p.logits)[n] = v;
                     }
                 }
-                __syncwarp();
-                if (c.lane == 0) grid_arrive(c);
             }
             if (kind == FKT_HEAD && !is_cp) {                  // talker last_hidden = final-norm of the row (:859)
 #pragma unroll
                 for (int j = 0; j < HJ; ++j) {
                     if (j * 1024 + tid4 < H) {
-                        const float4 w = __ldg(reinterpret_cast<const float4*>(nw + j * 1024 + tid4));
+                        const float4 w = nwv[j];
                         const float4 o = make_float4((xin[j][0] * rs) * w.x, (xin[j][1] * rs) * w.y, (xin[j][2] * rs) * w.z, (xin[j][3] * rs) * w.w);
                         *reinterpret_cast<float4*>(c.lh + j * 1024 + tid4) = o;
                         if (c.cta == 0) *reinterpret_cast<float4*>(p.last_hidden + j * 1024 + tid4) = o;
                     }
                 }
             }
+            csync();                                           // every warp has issued its outputs (and finished reading xp)
+            if (c.tid == 0) grid_arrive(c);
         }
         fk_mark(c, 6);
         if (c.aborted) break;
@@ -1020,8 +1101,115 @@ LQT_DEVINL int block_excl_scan(FkCtx& c, int v, int* total) {          // 256-th
     return base + inc - v;
 }
 
-// logits: LL words tagged `want` (ll != nullptr) or a plain array (first draw after a resume)
-LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, const float* plain, unsigned want, int V,
+// Fast path of the draw for 0 < top_k <= 64 (same results as the general path below, bit for bit):
+// a 256-bin histogram of (max - x) * 16 locates the bin that holds the k-th largest value, the <= 64
+// candidates up to that bin are compacted in index order, and ONE warp finishes: exact top-k by rank
+// (ties survive, src/tts_onnx.cpp:917-927), softmax (:907-915), top-p (:929-950), renormalisation and the
+// categorical draw in index order (:893-905), all sums serial in the reference's order.
+// Returns -1 when the shape does not fit (flat logits): the caller falls back to the general path.
+LQT_DEVINL int fk_sample_fast(FkCtx& c, const FkSampScratch& s, int i0, int i1, float mx, const SamplingDev& sp,
+                              uint32_t frame, int codebook) {
+    FkShared* sh = c.sh;
+    const int k = sp.top_k;
+    sh->hist[c.tid] = 0;
+    csync();
+    for (int i = i0; i < i1; ++i) {
+        const float dlt = (mx - s.x[i]) * 16.0f;               // >= 0; +inf for masked entries
+        if (dlt < 255.0f) atomicAdd(&sh->hist[(int)dlt], 1);
+    }
+    csync();
+    if (c.warp == 0) {
+        int h[8], loc = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { h[q] = sh->hist[c.lane * 8 + q]; loc += h[q]; }
+        int inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (c.lane >= o) inc += t; }
+        int cum = inc - loc, myB = -1;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { cum += h[q]; if (myB < 0 && cum >= k) myB = c.lane * 8 + q; }
+        const unsigned bal = __ballot_sync(0xffffffffu, myB >= 0);
+        const int B = bal ? __shfl_sync(0xffffffffu, myB, __ffs(bal) - 1) : -1;
+        if (c.lane == 0) sh->sel_k = B;
+    }
+    csync();
+    const int B = sh->sel_k;
+    if (B < 0) { csync(); return -1; }
+    const float lim = (float)(B + 1);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += ((mx - s.x[i]) * 16.0f < lim) ? 1 : 0;
+    int n_c;
+    int wpos = block_excl_scan(c, cnt, &n_c);
+    if (n_c > 64) { csync(); return -1; }
+    for (int i = i0; i < i1; ++i) {
+        const float v = s.x[i];
+        if ((mx - v) * 16.0f < lim) { s.idx[wpos] = (unsigned short)i; s.pr[wpos] = v; ++wpos; }
+    }
+    csync();
+    if (c.warp == 0) {
+        const int e0 = c.lane, e1 = c.lane + 32;
+        const float x0 = (e0 < n_c) ? s.pr[e0] : -INFINITY, x1 = (e1 < n_c) ? s.pr[e1] : -INFINITY;
+        int gt0 = 0, gt1 = 0;
+        for (int j = 0; j < n_c; ++j) { const float xj = s.pr[j]; gt0 += (xj > x0) ? 1 : 0; gt1 += (xj > x1) ? 1 : 0; }
+        const bool sv0 = e0 < n_c && gt0 < k, sv1 = e1 < n_c && gt1 < k;      // x >= (k-th largest)  <=>  fewer than k values above it
+        const unsigned b0 = __ballot_sync(0xffffffffu, sv0), b1 = __ballot_sync(0xffffffffu, sv1);
+        const unsigned lt = (1u << c.lane) - 1u;
+        const int p0 = __popc(b0 & lt), p1 = __popc(b0) + __popc(b1 & lt), ns = __popc(b0) + __popc(b1);
+        if (sv0) { s.spr[p0] = (float)exp((double)(x0 - mx)); s.rank[p0] = s.idx[e0]; }
+        if (sv1) { s.spr[p1] = (float)exp((double)(x1 - mx)); s.rank[p1] = s.idx[e1]; }
+        __syncwarp();
+        float sum = 0.f;
+        for (int i = 0; i < ns; ++i) sum += s.spr[i];          // serial, index order (every lane redundantly)
+        const int q0 = c.lane, q1 = c.lane + 32;
+        float pr0 = (q0 < ns) ? s.spr[q0] / sum : 0.f, pr1 = (q1 < ns) ? s.spr[q1] / sum : 0.f;
+        __syncwarp();
+        if (q0 < ns) s.spr[q0] = pr0;
+        if (q1 < ns) s.spr[q1] = pr1;
+        __syncwarp();
+        if (sp.top_p < 1.0f) {
+            int r0 = 0, r1 = 0;
+            for (int j = 0; j < ns; ++j) {
+                const float pj = s.spr[j];
+                r0 += (pj > pr0 || (pj == pr0 && j < q0)) ? 1 : 0;
+                r1 += (pj > pr1 || (pj == pr1 && j < q1)) ? 1 : 0;
+            }
+            if (q0 < ns) s.pr[r0] = pr0;                       // probabilities in descending order (ties: index order)
+            if (q1 < ns) s.pr[r1] = pr1;
+            __syncwarp();
+            int cut = ns;
+            float cs = 0.f;
+            for (int r = 0; r < ns; ++r) { cs += s.pr[r]; if (cs > sp.top_p) { cut = r + 1; break; } }
+            if (r0 >= cut) pr0 = 0.f;
+            if (r1 >= cut) pr1 = 0.f;
+            if (q0 < ns) s.spr[q0] = pr0;
+            if (q1 < ns) s.spr[q1] = pr1;
+            __syncwarp();
+            float s2 = 0.f;
+            for (int i = 0; i < ns; ++i) { const float v = s.spr[i]; if (v > 0.f) s2 += v; }
+            if (s2 > 0.f) { pr0 = pr0 / s2; pr1 = pr1 / s2; }
+            __syncwarp();
+            if (q0 < ns) s.spr[q0] = pr0;
+            if (q1 < ns) s.spr[q1] = pr1;
+            __syncwarp();
+        }
+        uint32_t r4[4];
+        philox4x32_10(frame, (uint32_t)codebook, 0u, 0u, sp.seed, sp.utt, r4);
+        const float u = (float)(r4[0] >> 8) * 5.9604644775390625e-08f;
+        float cdf = 0.f; int last = (ns > 0) ? (int)s.rank[0] : 0;
+        for (int i = 0; i < ns; ++i) {
+            const float pi = s.spr[i];
+            if (pi > 0.f) { cdf += pi; last = (int)s.rank[i]; if (cdf > u) break; }
+        }
+        if (c.lane == 0) sh->tok = last;
+    }
+    csync();
+    const int tok = sh->tok;
+    csync();                     // everyone has read tok/scratch before the glue overwrites anything
+    return tok;
+}
+
+// logits: LL words tagged `want` (ll != nullptr; already multicast into `land`) or a plain array (first draw after a resume)
+LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, const uint2* land, const float* plain, unsigned want, int V,
                          int mask_lo, int mask_hi, int mask_keep, const SamplingDev& sp, uint32_t frame, int codebook,
                          float* trace_row) {
     FkShared* sh = c.sh;
@@ -1030,18 +1218,33 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
     const int per = (((V + FK_CTHREADS - 1) / FK_CTHREADS) + 3) & ~3;
     const int i0 = min(V, c.tid * per), i1 = min(V, i0 + per);
     float bv = -INFINITY; int bi = 0x7fffffff;
-    for (int i = i0; i < i1; i += 4) {
-        const float4 q = ll ? ll_poll4(c, ll + i, want) : *reinterpret_cast<const float4*>(plain + i);
-        const float vv[4] = {q.x, q.y, q.z, q.w};
+    constexpr int FK_SAMP_Q = 4;                               // float4 groups per thread (V <= 4096)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float v = vv[u];
-            const int ii = i + u;
-            if (ii >= mask_lo && ii < mask_hi && ii != mask_keep) v = -INFINITY;
-            if (trace_row) trace_row[ii] = v;
-            if (temper) v = v / sp.temperature;
-            s.x[ii] = v;
-            if (v > bv) { bv = v; bi = ii; }                   // ascending ii: first maximum wins
+    for (int u4 = 0; u4 < FK_SAMP_Q; ++u4) {
+        const int i = i0 + 4 * u4;
+        if (i < i1) {
+            float4 q;
+            if (ll) {                                          // landed (value, sequence) words, validated like every other input
+                uint4 a = *reinterpret_cast<const uint4*>(land + i), b = *reinterpret_cast<const uint4*>(land + i + 2);
+                if (a.y != want || a.w != want || b.y != want || b.w != want) {
+                    const FkLL4 r = ll_poll4_slow(ll + i, want, &c.sh->aborted, c.p->ctrl);
+                    a = r.a; b = r.b;
+                }
+                q = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+            } else {
+                q = *reinterpret_cast<const float4*>(plain + i);
+            }
+            const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float v = vv[u];
+                const int ii = i + u;
+                if (ii >= mask_lo && ii < mask_hi && ii != mask_keep) v = -INFINITY;
+                if (trace_row) trace_row[ii] = v;
+                if (temper) v = v / sp.temperature;
+                s.x[ii] = v;
+                if (v > bv) { bv = v; bi = ii; }                   // ascending ii: first maximum wins
+            }
         }
     }
 #pragma unroll
@@ -1061,6 +1264,10 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
     }
     if (sp.greedy) { csync(); return bi; }
     const float mx = bv;
+    if (sp.top_k > 0 && sp.top_k < V && sp.top_k <= 64) {      // common case: a handful of survivors, finished by one warp
+        const int t = fk_sample_fast(c, s, i0, i1, mx, sp, frame, codebook);
+        if (t >= 0) return t;
+    }
 
     // top-k threshold: 4 x 8-bit radix select of the k-th largest key (warp-aggregated histogram)
     float thr = -INFINITY;
@@ -1164,26 +1371,29 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-struct FkSmemLayout { size_t scratch, att, xs, red, nxt, res0, lh, shared, total; };
-inline FkSmemLayout fk_smem_layout(int nstages, int maxV, int H, int res0_floats) {
+struct FkSmemLayout { size_t land, scratch, att, xs, red, nxt, res0, lh, shared, total; };
+inline FkSmemLayout fk_smem_layout(int nstages, int maxV, int H, int maxK) {
     FkSmemLayout L{};
     auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
     size_t off = (size_t)nstages * FK_STAGE_BYTES;
-    L.scratch = off;                                           // sampler scratch | attention scratch + attention output rows
-    const size_t samp = (size_t)maxV * (4 + 4 + 4 + 2 + 2);
+    L.land = off; off += (size_t)2 * FK_LAND_WORDS * 8;        // multicast landing buffers | sampler arrays pr/spr/idx/rank (general path)
+    L.scratch = off;                                           // sampler logits x[V] | attention scratch + attention output row
     const size_t attb = up((size_t)FA_FLOATS * 4), xsb = (size_t)2 * FK_XS_STRIDE * 4;
     L.att = off; L.xs = off + attb;
-    off += up(samp > attb + xsb ? samp : attb + xsb);
-    L.red = off; off += up((size_t)2 * FK_CWARPS * FK_RED_STRIDE * 4);
+    size_t sc = attb + xsb;
+    if ((size_t)maxV * 4 > sc) sc = (size_t)maxV * 4;
+    if ((size_t)maxK * 4 > sc) sc = (size_t)maxK * 4;       // plain input vector of a matrix-vector phase
+    off += up(sc);
+    L.red = off;
     L.nxt = off; off += up((size_t)H * 4);
-    L.res0 = off; off += up((size_t)res0_floats * 4);
+    L.res0 = off; off += up((size_t)H * 4);
     L.lh = off; off += up((size_t)H * 4);
     L.shared = off; off += up(sizeof(FkShared));
     L.total = off;
     return L;
 }
 
-struct FkSmemOffsets { unsigned scratch, att, xs, red, nxt, res0, lh, shared; int maxV; };
+struct FkSmemOffsets { unsigned land, scratch, att, xs, red, nxt, res0, lh, shared; int maxV; };
 
 // KJ = 1024-column chunks of the widest matrix (3: inter <= 3072, 6: <= 6144); NST = ring stages
 template <int KJ, int NST>
@@ -1195,21 +1405,27 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }   // every consumer warp releases a stage
+        mbar_init(&sh->land_bar[0], 1); mbar_init(&sh->land_bar[1], 1);
         sh->stop = 0; sh->consumed = 0; sh->aborted = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
+    for (int i = tid; i < FK_NGRP_MAX * FK_RPP_MAX; i += FK_THREADS) (&sh->redc[0][0])[i] = make_uint2(0u, 0u);
     __syncthreads();
+    cluster_sync_all();                            // every landing barrier of the cluster is initialised before any multicast can arrive
 
     const GenState st0 = *p.st;                    // written by the host before launch
     const int n_prefill = (p.mode == 0 && st0.pos == 0) ? p.P : 0;
     const int frame_end = min(p.frame_end, st0.max_frames);
 
-    if (warp == FK_CWARPS) {
+    if (warp >= FK_CWARPS) {
+#ifndef FK_NO_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
         // ============================ producer warp ============================================
         // Walks the same flat schedule as the consumers, one stage at a time, as far ahead as the
         // ring allows. All state in registers of one lane.
-        if (lane == 0) {
+        if (warp == FK_CWARPS && lane == 0) {
             long long n_pass;
             if (p.mode == 1) n_pass = 1;
             else {
@@ -1267,24 +1483,34 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                 while (!mbar_try_wait(&sh->full[slot], par)) { if (clock64() - t1 > FK_SPIN_LIMIT) break; }
             }
         }
+        __syncwarp();
+        cluster_sync_all();                        // no CTA leaves while a partner may still write into its shared memory
         return;
     }
 
     // ================================ consumer warps ===============================================
+#ifndef FK_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+#endif
     FkCtx c;
     c.p = &p; c.sh = sh; c.ring = fk_smem;
     c.att = reinterpret_cast<float*>(fk_smem + so.att);
     c.xs = reinterpret_cast<float*>(fk_smem + so.xs);
-    c.red = reinterpret_cast<float*>(fk_smem + so.red);
+    c.xp = reinterpret_cast<float*>(fk_smem + so.scratch);
+    c.land = reinterpret_cast<uint2*>(fk_smem + so.land);
+    c.land_n = 0; c.land_a = c.land;
+    c.rank = (unsigned)cta % FK_CLUSTER;
+    c.dbg_pg = p.pa + 8 * FK_NS_MAX * 2 * ATT_PSTRIDE;
     c.nxt = reinterpret_cast<float*>(fk_smem + so.nxt);
     c.res0 = reinterpret_cast<float*>(fk_smem + so.res0);
     c.lh = reinterpret_cast<float*>(fk_smem + so.lh);
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
     c.seq = 0; c.stage_ctr = 0; c.aborted = false;
     c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
-    FkSampScratch ss;
+    FkSampScratch ss;                              // x: own scratch; the arrays of the general path reuse the landing buffers
     ss.x = reinterpret_cast<float*>(fk_smem + so.scratch);
-    ss.pr = ss.x + so.maxV; ss.spr = ss.pr + so.maxV;
+    ss.pr = reinterpret_cast<float*>(fk_smem + so.land);
+    ss.spr = ss.pr + so.maxV;
     ss.idx = reinterpret_cast<unsigned short*>(ss.spr + so.maxV); ss.rank = ss.idx + so.maxV;
 
     const int H = p.talker.H, H4 = H >> 2;
@@ -1327,10 +1553,12 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             grid_wait(c, resumed ? 0u : c.seq);                 // the logits of the head phase have been issued everywhere
             fk_mark(c, 1);
             float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + cb) * p.trace_stride : nullptr;
-            int tok;
-            if (cb == 0) tok = fk_sample(c, ss, resumed ? nullptr : p.logits_ll, p.logits, c.seq, p.vocab, 2048, p.vocab, 2150,
-                                         sp, (uint32_t)frame, 0, tr);
-            else         tok = fk_sample(c, ss, p.clogits_ll, nullptr, c.seq, p.cp_vocab, 0, 0, -1, sp, (uint32_t)frame, cb, tr);
+            const bool t0 = (cb == 0);                          // one call site: the sampler is instantiated once
+            const uint2* lg = t0 ? (resumed ? nullptr : p.logits_ll) : p.clogits_ll;
+            const int Vd = t0 ? p.vocab : p.cp_vocab;
+            const uint2* land = lg ? mc_fetch(c, lg, Vd) : nullptr;
+            int tok = fk_sample(c, ss, lg, land, t0 ? p.logits : nullptr, c.seq, Vd, t0 ? 2048 : 0, t0 ? p.vocab : 0, t0 ? 2150 : -1,
+                                sp, (uint32_t)frame, cb, tr);
             resumed = false;
             if (c.sh->aborted) { c.aborted = true; break; }
             if (p.forced && frame < st0.n_forced) tok = (int)p.forced[(size_t)frame * 16 + cb];
@@ -1393,6 +1621,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
         __threadfence_block();
         sh->stop = 1;
     }
+    cluster_sync_all();
 }
 
 }  // namespace lqt

@@ -19,7 +19,7 @@ SYMBOLS = [
     "lqt_reset_stats", "lqt_text_project", "lqt_codec_embed", "lqt_code_predictor_embed",
     "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
-    "lqt_build_prompt", "lqt_debug_timeline",
+    "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library():
                                           C.POINTER(I64), P, C.POINTER(I32)]
     lib.lqt_build_prompt.argtypes = [P, P, I32, I32, P, P, C.POINTER(I32), P, C.POINTER(I32), P]
     lib.lqt_debug_timeline.argtypes = [P, I32, I32, P, I32]
+    lib.lqt_debug_exchange.argtypes = [P, I32, P, I32]
     _lib = lib
     return lib
 
@@ -241,6 +242,12 @@ class Engine:
                                        C.byref(sp), _ptr(fc), 0 if fc is None else fc.shape[0],
                                        _ptr(codes), C.byref(n), _ptr(tb), stride))
         return (codes[: n.value].copy(), tb) if trace else codes[: n.value].copy()
+
+    def debug_exchange(self, which: int, n: int):
+        """values of one exchange buffer of the frame kernel after the last launch (0 x, 1 qkv, 2 x1, 3 act; +4 = code predictor)"""
+        out = np.empty(n, np.float32)
+        self._ck(self.lib.lqt_debug_exchange(self.h, which, _ptr(out), n))
+        return out
 
     def timeline_arm(self, entries: int = 200000, cta: int = 0):
         if self.lib.lqt_debug_timeline(self.h, entries, cta, None, 0) != 0:
