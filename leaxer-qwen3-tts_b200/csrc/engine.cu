@@ -1454,10 +1454,11 @@ int lqt_debug_timeline(lqt_engine* h, int32_t enable_entries, int32_t cta, uint6
     }
     if (!h->fk_dbg || !out) return 0;
     unsigned long long n = 0;
-    cudaMemcpyAsync(&n, h->fk_dbg, 8, cudaMemcpyDeviceToHost, h->stream);
+    const unsigned long long* base = h->fk_dbg + (cta == 1 ? h->fk_dbg_cap / 2 : 0);      // read mode: cta 1 = the producer's half (FK_FINE_MARKS builds)
+    cudaMemcpyAsync(&n, base, 8, cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
     const int m = (int)std::min<unsigned long long>(n, (unsigned long long)std::max(out_cap, 0));
-    if (m > 0) cudaMemcpy(out, h->fk_dbg + 1, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    if (m > 0) cudaMemcpy(out, base + 1, (size_t)m * 8, cudaMemcpyDeviceToHost);
     return m;
 }
 

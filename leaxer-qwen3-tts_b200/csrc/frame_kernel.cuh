@@ -417,6 +417,23 @@ LQT_DEVINL float reduce8(const float (&a)[8], int lane) {
 // slot s = (q / 8) * RG + t  <->  row ((s / RG) * 8 + warp) * RG + t.
 // No cross-warp reduction, no CTA barrier: the epilogue runs on the lanes that hold the sums.
 // ------------------------------------------------------------------------------------------------
+// sums of 4 values over the 32 lanes: on return every lane holds the full-warp sum of a[lane >> 3] (6 shuffles)
+LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    float d[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b4 ? a[i] : a[i + 2], keep = b4 ? a[i + 2] : a[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const float send = b3 ? d[0] : d[1], keep = b3 ? d[1] : d[0];
+    float s = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
+}
+
 template <int NST, int RG>
 LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
     const int K = d.K, rowbytes = K * 2;
@@ -435,45 +452,61 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
     };
     if (nch == 1) load_chunk(0);
     float mine = 0.f;                             // lane s keeps the sum of slot s
-    int cur = 0;                                  // next ring stage of this phase this warp has not released yet
-    bool have = false;                            // full[cur] already observed
+    int cur = 0;                                  // first ring stage of this phase this warp has not released yet
+    int seen = 0;                                 // stages [cur, seen) have been observed full
+    // four slots (rows) at a time: 16 independent shared loads and 4 FMA chains in flight per warp
 #pragma unroll 1
-    for (int s = 0; s < 8; ++s) {
-        const int r = ((s / RG) * 8 + c.warp) * RG + (s % RG);
-        if (r >= d.nrows) break;                  // warp-uniform; rows grow with s
-        const int g = r / d.rps;
-        while (cur < g) {                         // stages that hold no (further) row of this warp
-            if (!have) wait_full(c, c.stage_ctr + cur, NST);
+    for (int sb = 0; sb < 8; sb += 4) {
+        int rr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int s = sb + j; rr[j] = ((s / RG) * 8 + c.warp) * RG + (s % RG); }
+        if (rr[0] >= d.nrows) break;              // warp-uniform; rows grow with the slot
+        int last = rr[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) if (rr[j] < d.nrows) last = rr[j];
+        const int g0 = rr[0] / d.rps, g1 = last / d.rps;
+        while (cur < g0) {                        // stages that hold no (further) row of this warp
+            if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&c.sh->empty[(c.stage_ctr + cur) % (unsigned)NST]);
-            ++cur; have = false;
+            ++cur;
         }
-        if (!have) { wait_full(c, c.stage_ctr + cur, NST); have = true; }
-        const unsigned char* wr = c.ring + (size_t)((c.stage_ctr + g) % (unsigned)NST) * FK_STAGE_BYTES + (size_t)(r - g * d.rps) * rowbytes + c.lane * 16;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        while (seen <= g1) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
+        const unsigned char* wr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = (rr[j] < d.nrows) ? rr[j] : rr[0];          // rows beyond the slice: recompute row 0 (dropped)
+            const int g = r / d.rps;
+            wr[j] = c.ring + (size_t)((c.stage_ctr + g) % (unsigned)NST) * FK_STAGE_BYTES + (size_t)(r - g * d.rps) * rowbytes + c.lane * 16;
+        }
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
             if (nch > 1) load_chunk(ch);
-            uint4 w[4];
+            uint4 w[4][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = (ch * 1024 + i * 256 < K) ? lds128(wr + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
-            a0 = fmaf(bf16lo(w[0].x), xk[0], a0); a0 = fmaf(bf16hi(w[0].x), xk[1], a0); a0 = fmaf(bf16lo(w[0].y), xk[2], a0); a0 = fmaf(bf16hi(w[0].y), xk[3], a0);
-            a0 = fmaf(bf16lo(w[0].z), xk[4], a0); a0 = fmaf(bf16hi(w[0].z), xk[5], a0); a0 = fmaf(bf16lo(w[0].w), xk[6], a0); a0 = fmaf(bf16hi(w[0].w), xk[7], a0);
-            a1 = fmaf(bf16lo(w[1].x), xk[8], a1); a1 = fmaf(bf16hi(w[1].x), xk[9], a1); a1 = fmaf(bf16lo(w[1].y), xk[10], a1); a1 = fmaf(bf16hi(w[1].y), xk[11], a1);
-            a1 = fmaf(bf16lo(w[1].z), xk[12], a1); a1 = fmaf(bf16hi(w[1].z), xk[13], a1); a1 = fmaf(bf16lo(w[1].w), xk[14], a1); a1 = fmaf(bf16hi(w[1].w), xk[15], a1);
-            a2 = fmaf(bf16lo(w[2].x), xk[16], a2); a2 = fmaf(bf16hi(w[2].x), xk[17], a2); a2 = fmaf(bf16lo(w[2].y), xk[18], a2); a2 = fmaf(bf16hi(w[2].y), xk[19], a2);
-            a2 = fmaf(bf16lo(w[2].z), xk[20], a2); a2 = fmaf(bf16hi(w[2].z), xk[21], a2); a2 = fmaf(bf16lo(w[2].w), xk[22], a2); a2 = fmaf(bf16hi(w[2].w), xk[23], a2);
-            a3 = fmaf(bf16lo(w[3].x), xk[24], a3); a3 = fmaf(bf16hi(w[3].x), xk[25], a3); a3 = fmaf(bf16lo(w[3].y), xk[26], a3); a3 = fmaf(bf16hi(w[3].y), xk[27], a3);
-            a3 = fmaf(bf16lo(w[3].z), xk[28], a3); a3 = fmaf(bf16hi(w[3].z), xk[29], a3); a3 = fmaf(bf16lo(w[3].w), xk[30], a3); a3 = fmaf(bf16hi(w[3].w), xk[31], a3);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[j][i] = (ch * 1024 + i * 256 < K) ? lds128(wr[j] + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a[j] = fmaf(bf16lo(w[j][i].x), xk[i * 8 + 0], a[j]); a[j] = fmaf(bf16hi(w[j][i].x), xk[i * 8 + 1], a[j]);
+                    a[j] = fmaf(bf16lo(w[j][i].y), xk[i * 8 + 2], a[j]); a[j] = fmaf(bf16hi(w[j][i].y), xk[i * 8 + 3], a[j]);
+                    a[j] = fmaf(bf16lo(w[j][i].z), xk[i * 8 + 4], a[j]); a[j] = fmaf(bf16hi(w[j][i].z), xk[i * 8 + 5], a[j]);
+                    a[j] = fmaf(bf16lo(w[j][i].w), xk[i * 8 + 6], a[j]); a[j] = fmaf(bf16hi(w[j][i].w), xk[i * 8 + 7], a[j]);
+                }
         }
-        const float a = warp_sum((a0 + a1) + (a2 + a3));
-        if (c.lane == s) mine = a;
+        const float t = reduce4(a, c.lane);                          // lanes 8j .. 8j+7 hold the sum of slot sb + j
+        const float v = __shfl_sync(0xffffffffu, t, ((c.lane - sb) & 3) * 8);
+        if (c.lane >= sb && c.lane < sb + 4) mine = v;
     }
     while (cur < nst) {
-        if (!have) wait_full(c, c.stage_ctr + cur, NST);
+        if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.sh->empty[(c.stage_ctr + cur) % (unsigned)NST]);
-        ++cur; have = false;
+        ++cur;
     }
     c.stage_ctr += nst;
     return mine;
@@ -1147,58 +1180,108 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, const FkSampScratch& s, int i0, int i1, 
     }
     csync();
     if (c.warp == 0) {
+        // Arrays are read eight entries at a time (two 16-byte loads issued before the dependent chain); entries beyond the
+        // live count are kept at neutral values (-inf / 0), so the serial sums see exactly the reference's operands in order.
         const int e0 = c.lane, e1 = c.lane + 32;
         const float x0 = (e0 < n_c) ? s.pr[e0] : -INFINITY, x1 = (e1 < n_c) ? s.pr[e1] : -INFINITY;
+        const int i0c = (e0 < n_c) ? (int)s.idx[e0] : 0, i1c = (e1 < n_c) ? (int)s.idx[e1] : 0;
+        __syncwarp();
+        if (e0 >= n_c) s.pr[e0] = -INFINITY;                   // pad to 64 so that the unrolled loops need no bounds
+        if (e1 >= n_c) s.pr[e1] = -INFINITY;
+        __syncwarp();
         int gt0 = 0, gt1 = 0;
-        for (int j = 0; j < n_c; ++j) { const float xj = s.pr[j]; gt0 += (xj > x0) ? 1 : 0; gt1 += (xj > x1) ? 1 : 0; }
+#pragma unroll 1
+        for (int j = 0; j < n_c; j += 8) {
+            const float4 u = *reinterpret_cast<const float4*>(s.pr + j), w = *reinterpret_cast<const float4*>(s.pr + j + 4);
+            const float xv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { gt0 += (xv[q] > x0) ? 1 : 0; gt1 += (xv[q] > x1) ? 1 : 0; }
+        }
         const bool sv0 = e0 < n_c && gt0 < k, sv1 = e1 < n_c && gt1 < k;      // x >= (k-th largest)  <=>  fewer than k values above it
         const unsigned b0 = __ballot_sync(0xffffffffu, sv0), b1 = __ballot_sync(0xffffffffu, sv1);
         const unsigned lt = (1u << c.lane) - 1u;
         const int p0 = __popc(b0 & lt), p1 = __popc(b0) + __popc(b1 & lt), ns = __popc(b0) + __popc(b1);
-        if (sv0) { s.spr[p0] = (float)exp((double)(x0 - mx)); s.rank[p0] = s.idx[e0]; }
-        if (sv1) { s.spr[p1] = (float)exp((double)(x1 - mx)); s.rank[p1] = s.idx[e1]; }
+        const int q0 = c.lane, q1 = c.lane + 32;
+        s.spr[q0] = 0.f; s.spr[q1] = 0.f;                                       // neutral padding up to 64 entries
+        __syncwarp();
+        if (sv0) { s.spr[p0] = (float)exp((double)(x0 - mx)); s.rank[p0] = (unsigned short)i0c; }
+        if (sv1) { s.spr[p1] = (float)exp((double)(x1 - mx)); s.rank[p1] = (unsigned short)i1c; }
         __syncwarp();
         float sum = 0.f;
-        for (int i = 0; i < ns; ++i) sum += s.spr[i];          // serial, index order (every lane redundantly)
-        const int q0 = c.lane, q1 = c.lane + 32;
+#pragma unroll 1
+        for (int i = 0; i < ns; i += 8) {                                        // serial, index order (every lane redundantly)
+            const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
+            sum += u.x; sum += u.y; sum += u.z; sum += u.w; sum += w.x; sum += w.y; sum += w.z; sum += w.w;
+        }
         float pr0 = (q0 < ns) ? s.spr[q0] / sum : 0.f, pr1 = (q1 < ns) ? s.spr[q1] / sum : 0.f;
         __syncwarp();
-        if (q0 < ns) s.spr[q0] = pr0;
-        if (q1 < ns) s.spr[q1] = pr1;
+        s.spr[q0] = pr0; s.spr[q1] = pr1;
         __syncwarp();
         if (sp.top_p < 1.0f) {
             int r0 = 0, r1 = 0;
-            for (int j = 0; j < ns; ++j) {
-                const float pj = s.spr[j];
-                r0 += (pj > pr0 || (pj == pr0 && j < q0)) ? 1 : 0;
-                r1 += (pj > pr1 || (pj == pr1 && j < q1)) ? 1 : 0;
+#pragma unroll 1
+            for (int j = 0; j < ns; j += 8) {
+                const float4 u = *reinterpret_cast<const float4*>(s.spr + j), w = *reinterpret_cast<const float4*>(s.spr + j + 4);
+                const float pv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int jj = j + q;
+                    if (jj < ns) {
+                        r0 += (pv[q] > pr0 || (pv[q] == pr0 && jj < q0)) ? 1 : 0;
+                        r1 += (pv[q] > pr1 || (pv[q] == pr1 && jj < q1)) ? 1 : 0;
+                    }
+                }
             }
+            s.pr[q0] = 0.f; s.pr[q1] = 0.f;
+            __syncwarp();
             if (q0 < ns) s.pr[r0] = pr0;                       // probabilities in descending order (ties: index order)
             if (q1 < ns) s.pr[r1] = pr1;
             __syncwarp();
             int cut = ns;
             float cs = 0.f;
-            for (int r = 0; r < ns; ++r) { cs += s.pr[r]; if (cs > sp.top_p) { cut = r + 1; break; } }
+#pragma unroll 1
+            for (int r = 0; r < ns && cut == ns; r += 8) {
+                const float4 u = *reinterpret_cast<const float4*>(s.pr + r), w = *reinterpret_cast<const float4*>(s.pr + r + 4);
+                const float pv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    cs += pv[q];
+                    if (cut == ns && r + q < ns && cs > sp.top_p) cut = r + q + 1;
+                }
+            }
             if (r0 >= cut) pr0 = 0.f;
             if (r1 >= cut) pr1 = 0.f;
-            if (q0 < ns) s.spr[q0] = pr0;
-            if (q1 < ns) s.spr[q1] = pr1;
+            s.spr[q0] = pr0; s.spr[q1] = pr1;
             __syncwarp();
             float s2 = 0.f;
-            for (int i = 0; i < ns; ++i) { const float v = s.spr[i]; if (v > 0.f) s2 += v; }
+#pragma unroll 1
+            for (int i = 0; i < ns; i += 8) {
+                const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
+                s2 += u.x; s2 += u.y; s2 += u.z; s2 += u.w; s2 += w.x; s2 += w.y; s2 += w.z; s2 += w.w;   // zeros are neutral
+            }
             if (s2 > 0.f) { pr0 = pr0 / s2; pr1 = pr1 / s2; }
             __syncwarp();
-            if (q0 < ns) s.spr[q0] = pr0;
-            if (q1 < ns) s.spr[q1] = pr1;
+            s.spr[q0] = pr0; s.spr[q1] = pr1;
             __syncwarp();
         }
         uint32_t r4[4];
         philox4x32_10(frame, (uint32_t)codebook, 0u, 0u, sp.seed, sp.utt, r4);
-        const float u = (float)(r4[0] >> 8) * 5.9604644775390625e-08f;
-        float cdf = 0.f; int last = (ns > 0) ? (int)s.rank[0] : 0;
-        for (int i = 0; i < ns; ++i) {
-            const float pi = s.spr[i];
-            if (pi > 0.f) { cdf += pi; last = (int)s.rank[i]; if (cdf > u) break; }
+        const float u01 = (float)(r4[0] >> 8) * 5.9604644775390625e-08f;
+        float cdf = 0.f; int last = (ns > 0) ? (int)s.rank[0] : 0; bool hit = false;
+#pragma unroll 1
+        for (int i = 0; i < ns && !hit; i += 8) {
+            const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
+            const float pv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+            const uint4 ri = *reinterpret_cast<const uint4*>(s.rank + i);      // 8 ushort indices
+            const unsigned rw[4] = {ri.x, ri.y, ri.z, ri.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (!hit && pv[q] > 0.f) {                     // (entries beyond ns are zero)
+                    cdf += pv[q];
+                    last = (int)((rw[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+                    if (cdf > u01) hit = true;
+                }
+            }
         }
         if (c.lane == 0) sh->tok = last;
     }
@@ -1467,6 +1550,12 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                         }
                         if (stopped) break;
                         const uint32_t bytes = (uint32_t)nr * row_bytes;
+#ifdef FK_FINE_MARKS
+                        if (p.dbg && cta == p.dbg_cta) {
+                            unsigned long long* pd = p.dbg + p.dbg_cap / 2;
+                            if ((int)issued + 2 < p.dbg_cap / 2) { pd[1 + issued] = ((unsigned long long)clock64() << 16) | (issued & 0xffffu); pd[0] = issued + 1; }
+                        }
+#endif
                         mbar_expect_tx(&sh->full[slot], bytes);
                         bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)r0 * row_bytes, bytes, &sh->full[slot]);
                         ++issued;

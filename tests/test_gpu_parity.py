@@ -211,14 +211,29 @@ def test_generate_greedy_token_exact(request, which, frames):
     sp_o = orc.SamplingParams(max_new_tokens=frames, greedy=True)
     ref_codes, tr, (codes, tb) = _run_generate(eng, m, orc, ids, "en", sp_o, eng.sampling(max_new_tokens=frames, greedy=True))
     assert codes.shape == ref_codes.shape == (frames, 16)
-    assert np.array_equal(codes, ref_codes), np.argwhere(codes != ref_codes)[:4]
     V, Vs = m.spec.vocab, m.spec.cp_vocab
+    # Free-running greedy decoding is token-exact UNTIL the oracle itself is at a near-tie: a top-2 margin below the
+    # logit tolerance cannot be resolved by any implementation that sums in a different order ("exact-token
+    # parity is numerically fragile"). A flip is accepted only there, only towards the oracle's runner-up, and ends the comparison.
+    diff = np.argwhere(codes != ref_codes)
+    n_cmp = frames * 16 if len(diff) == 0 else int(diff[0][0]) * 16 + int(diff[0][1])
+    if len(diff):
+        f, j = int(diff[0][0]), int(diff[0][1])
+        r = np.asarray(tr["talker_logits"][f] if j == 0 else tr["cp_logits"][f][j - 1], dtype=np.float64)
+        order = np.argsort(-np.where(np.isfinite(r), r, -np.inf))
+        margin = r[order[0]] - r[order[1]]
+        assert margin < LOGIT_TOL_TIGHT, (f, j, margin, "token flip away from a near-tie")
+        assert int(codes[f, j]) == int(order[1]) and int(ref_codes[f, j]) == int(order[0]), (f, j, codes[f, j], order[:2])
+        assert n_cmp >= 16, "diverged inside the first frame"
     for f in range(frames):
-        ref0 = tr["talker_logits"][f]
-        fin = np.isfinite(ref0)
-        assert maxabs(tb[f, 0, :V][fin], ref0[fin]) < tight(which)
-        assert np.all(np.isneginf(tb[f, 0, :V][~fin]))
-        assert maxabs(tb[f, 1:, :Vs], tr["cp_logits"][f]) < tight(which)
+        for j in range(16):
+            if f * 16 + j > n_cmp:
+                break
+            ref = tr["talker_logits"][f] if j == 0 else tr["cp_logits"][f][j - 1]
+            got = tb[f, 0, :V] if j == 0 else tb[f, j, :Vs]
+            fin = np.isfinite(ref)
+            assert maxabs(got[fin], np.asarray(ref)[fin]) < tight(which), (f, j)
+            assert np.all(np.isneginf(got[~fin]))
 
 
 @pytest.mark.parametrize("which,frames", [("tiny", 12), ("full", 5)])
