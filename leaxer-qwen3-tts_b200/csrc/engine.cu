@@ -886,6 +886,7 @@ int fk_init(lqt_engine* h) {
         int ncl = 0;
         CK(cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg));
         if (ncl < 1) { h->err = "frame kernel: no cluster of 8 CTAs fits on this device"; return 1; }
+        if (getenv("LQT_FK_NOCOOP")) h->fk_coop = false;        // profilers that cannot replay cooperative launches
         h->fk_ncta = FK_CLUSTER * ncl;
         if (const char* e = getenv("LQT_FK_CLUSTERS")) { const int v = atoi(e); if (v >= 1 && v <= ncl) h->fk_ncta = FK_CLUSTER * v; }
         if (getenv("LQT_DEBUG")) fprintf(stderr, "[lqt] frame kernel: %d clusters of %d CTAs co-resident, using %d CTAs, %zu B shared memory\n", ncl, FK_CLUSTER, h->fk_ncta, h->fk_smem);
