@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE (oracle side): a tiny driver around the io/ API shared by the reference and this repo
+// (leaxer_qwen::io: MelExtractor, read_wav, resample, tokenizer). It is compiled twice:
+//   oracle/_ref/io_dump_ref  <- against the reference's own sources where they lie (/root/reference/src/io/*.cpp)
+//   host/build/io_dump       <- against this repo's re-implementation (leaxer-qwen3-tts_b200/host/io/*.cpp)
+// and tests/ compare the two byte streams (and the committed fixtures made from the reference build).
+// Output: raw little-endian values on stdout. Commands:
+//   mel N SEED            log-mel [128][frames] of N synthetic samples (24 kHz, n_fft 1024, hop 256: src/tts_onnx.cpp:347-354)
+//   wav PATH              int32 sample rate (or -1) followed by the decoded samples
+//   resample N SRC DST    resample(N synthetic samples)
+//   tok VOCAB MERGES TEXT int32 token ids ("-" for a missing file: tokenizer without vocab/merges)
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mel.h"
+#include "tokenizer.h"
+#include "wav_reader.h"
+
+using namespace leaxer_qwen::io;
+
+static std::vector<float> synth(int n, unsigned seed) {
+    std::vector<float> a(static_cast<size_t>(n));
+    uint32_t s = seed * 2654435761u + 12345u;
+    for (int i = 0; i < n; ++i) {
+        s = s * 1664525u + 1013904223u;
+        const float noise = (static_cast<float>(s >> 8) / 16777216.0f - 0.5f) * 0.1f;
+        const double t = static_cast<double>(i) / 24000.0;
+        a[static_cast<size_t>(i)] = static_cast<float>(0.4 * std::sin(2 * M_PI * 220.0 * t) + 0.25 * std::sin(2 * M_PI * 1330.0 * t) + 0.1 * std::sin(2 * M_PI * 5100.0 * t)) + noise;
+    }
+    return a;
+}
+static void put_f(const std::vector<float>& v) { if (!v.empty()) std::fwrite(v.data(), 4, v.size(), stdout); }
+static void put_i(int32_t v) { std::fwrite(&v, 4, 1, stdout); }
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    const std::string cmd = argv[1];
+    if (cmd == "mel" && argc >= 4) {
+        MelConfig mc;
+        mc.sample_rate = 24000; mc.n_fft = 1024; mc.hop_size = 256; mc.win_size = 1024; mc.num_mels = 128; mc.fmin = 0.0f; mc.fmax = 12000.0f;
+        MelExtractor mel(mc);
+        const std::vector<float> m = mel.extract(synth(std::atoi(argv[2]), static_cast<unsigned>(std::atoi(argv[3]))));
+        put_i(static_cast<int32_t>(mel.num_frames()));
+        put_f(m);
+        return 0;
+    }
+    if (cmd == "wav" && argc >= 3) {
+        int sr = -1;
+        const std::vector<float> a = read_wav(argv[2], sr);
+        put_i(sr);
+        put_f(a);
+        return 0;
+    }
+    if (cmd == "resample" && argc >= 5) {
+        put_f(resample(synth(std::atoi(argv[2]), 7u), std::atoi(argv[3]), std::atoi(argv[4])));
+        return 0;
+    }
+    if (cmd == "tok" && argc >= 5) {
+        if (std::strcmp(argv[2], "-") != 0) load_vocab(argv[2]);
+        if (std::strcmp(argv[3], "-") != 0) load_merges(argv[3]);
+        put_i(is_tokenizer_ready() ? 1 : 0);
+        for (int32_t t : tokenize(argv[4])) put_i(t);
+        return 0;
+    }
+    return 2;
+}

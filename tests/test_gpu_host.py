@@ -1,0 +1,75 @@
+"""The C++17 host (leaxer_qwen::TTSEngine + CLI, leaxer-qwen3-tts_b200/host/) end to end on the GPU: the WAV the
+CLI writes must equal what the ctypes binding produces for the same token ids / sampling parameters / Philox seed
+(both go through lqt_synthesize_tokens), and the clone path (--ref) must run through read_wav -> mel -> speaker encoder."""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import io_cases  # noqa: E402
+
+HOST = os.path.join(ROOT, "leaxer-qwen3-tts_b200", "host")
+pytestmark = pytest.mark.gpu
+
+
+def _read_pcm16(path):
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE" and raw[36:40] == b"data"
+    rate, = struct.unpack("<I", raw[24:28])
+    n, = struct.unpack("<I", raw[40:44])
+    return rate, np.frombuffer(raw[44:44 + n], "<i2")
+
+
+def _pcm16(audio):
+    return (np.clip(audio, -1.0, 1.0).astype(np.float32) * np.float32(32767.0)).astype(np.int16)     # truncation toward zero, src/main_onnx.cpp:40-50
+
+
+@pytest.fixture(scope="module")
+def host_env(tiny_dir):
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    tokdir = os.path.join(os.path.dirname(tiny_dir), "models", "Qwen3-TTS-12Hz-0.6B-Base")        # where the reference looks (src/tts_onnx.cpp:110-112)
+    vp, mp = io_cases.write_tokenizer_files(tokdir)
+    return {"cli": os.path.join(HOST, "leaxer-qwen-b200"), "dump": os.path.join(HOST, "build", "io_dump"), "vocab": vp, "merges": mp}
+
+
+def test_cli_matches_binding(tiny_engine, tiny_dir, host_env, tmp_path):
+    text = "hello world speech testing 123"
+    out = subprocess.run([host_env["dump"], "tok", host_env["vocab"], host_env["merges"], text], check=True, stdout=subprocess.PIPE).stdout
+    toks = np.frombuffer(out, "<i4")[1:].tolist()
+    from leaxer_qwen3_tts_b200.engine import wrap_text_ids
+    ids = wrap_text_ids(toks)
+    audio, codes = tiny_engine.synthesize_tokens(ids, "en", temperature=0.7, top_k=20, top_p=0.9, max_new_tokens=6, seed=4242, utterance_id=0)
+    wav = tmp_path / "sub" / "cli.wav"
+    r = subprocess.run([host_env["cli"], "-m", tiny_dir, "-p", text, "--lang", "en", "--temp", "0.7", "--top-k", "20", "--top-p", "0.9",
+                        "--max-tokens", "6", "--seed", "4242", "-o", str(wav), "--bogus-flag"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Synthesizing..." in r.stdout and "Generated 0.48 seconds of audio" in r.stdout and f"Saved to: {wav}" in r.stdout
+    rate, pcm = _read_pcm16(wav)
+    assert rate == 24000 and pcm.shape[0] == 6 * 1920
+    assert np.array_equal(pcm, _pcm16(audio))
+
+
+def test_cli_voice_clone(tiny_engine, tiny_dir, host_env, tmp_path):
+    """--ref: 3 s synthetic 24 kHz clip -> 278 mel frames -> speaker encoder -> one extra prompt row (src/tts_onnx.cpp:264-403)"""
+    t = np.arange(72000) / 24000.0
+    clip = 0.4 * np.sin(2 * np.pi * 220 * t) + 0.2 * np.sin(2 * np.pi * 1330 * t)
+    ref = tmp_path / "ref.wav"
+    io_cases._wav(str(ref), 1, 1, 24000, 16, (clip * 32767).astype("<i2").tobytes())
+    wav = tmp_path / "clone.wav"
+    r = subprocess.run([host_env["cli"], "-m", tiny_dir, "-p", "hello world", "--lang", "zh", "--ref", str(ref), "--max-tokens", "4",
+                        "--seed", "7", "-o", str(wav)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"Reference: {ref}" in r.stdout
+    rate, pcm = _read_pcm16(wav)
+    assert rate == 24000 and pcm.shape[0] == 4 * 1920 and np.abs(pcm).max() > 0
+    # same result through the binding with the speaker embedding computed from the same mel (python mirror of the front end is
+    # the io_dump 'mel' path; here we only require determinism of the CLI: a second run is bit-identical)
+    wav2 = tmp_path / "clone2.wav"
+    r2 = subprocess.run([host_env["cli"], "-m", tiny_dir, "-p", "hello world", "--lang", "zh", "--ref", str(ref), "--max-tokens", "4",
+                         "--seed", "7", "-o", str(wav2)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r2.returncode == 0 and np.array_equal(_read_pcm16(wav2)[1], pcm)
