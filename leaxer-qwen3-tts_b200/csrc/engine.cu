@@ -1129,7 +1129,13 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         return 1;
     CK(cudaMallocHost((void**)&h->st_host, sizeof(GenState)));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev_t0));
-    if (h->frame_impl == 0 && fk_init(h)) return 1;
+    if (h->frame_impl == 0 && fk_init(h)) {
+        // shapes the persistent kernel does not cover yet (e.g. the 1.7B talker: > 64 rows per CTA): run loops A+B as the
+        // CUDA graph of per-op sm_100a kernels instead (still device-only; there is no CPU path)
+        fprintf(stderr, "[lqt] persistent frame kernel unavailable (%s): using the graph-of-kernels frame loop\n", h->err.c_str());
+        h->err.clear();
+        h->frame_impl = 1;
+    }
     return 0;
 }
 
