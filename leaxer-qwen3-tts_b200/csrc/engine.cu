@@ -949,7 +949,7 @@ int fk_init(lqt_engine* h) {
         h->fk_pa = a + o_pa; h->fk_cxin = a + o_ci; h->fk_logits_ll = a + o_lg; h->fk_clogits_ll = a + o_cl;
     }
     if (fk_alloc(h, &h->fk_ctrl, 64)) return 1;      // [1] abort flag, [32] grid arrival counter (own cache line)
-    CK(cudaMallocHost((void**)&h->fk_ctrl_host, 2 * sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&h->fk_ctrl_host, 64 * sizeof(unsigned)));
     return 0;
 }
 
@@ -999,11 +999,12 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
         CK(e);
     }
     h->stats.kernel_launches++;
-    CK(cudaMemcpyAsync(h->fk_ctrl_host, h->fk_ctrl, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->fk_ctrl_host, h->fk_ctrl, 64 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
 
 int fk_check_abort(lqt_engine* h) {       // after a stream synchronize
+    if (getenv("LQT_DEBUG") && h->fk_ctrl_host[41]) fprintf(stderr, "[lqt] frame kernel: %u multicast fetches (all CTAs), %u stale 4-word groups re-polled\n", h->fk_ctrl_host[41], h->fk_ctrl_host[40]);
     if (h->fk_ctrl_host[1] != 0) { h->err = "frame kernel aborted: a device-side wait timed out"; return 1; }
     return 0;
 }

@@ -39,7 +39,7 @@ def main():
     clk, tag = eng.timeline_read()
     print(f"entries {len(clk)}  total {(int(clk[-1]) - int(clk[0])) / a.mhz / 1e3:.2f} ms for prefill + {a.frames} frames "
           f"(generate_ms {eng.stats().last_generate_ms:.2f})")
-    POINTS = {0: "begin", 1: "grid go", 2: "fetched", 3: "inputs staged", 4: "glue", 5: "fma done", 6: "published", 8: "stage landed", 9: "stage done"}
+    POINTS = {0: "begin", 1: "grid go", 2: "fetched", 3: "inputs staged", 4: "glue", 5: "fma done", 6: "published", 8: "after csync", 9: "x loaded", 10: "batch done", 11: "stages released"}
     seg = collections.defaultdict(list)
     for i in range(1, len(clk)):
         st, kind, pt = (tag[i] >> 9) & 1, (tag[i] >> 4) & 31, tag[i] & 15
