@@ -897,6 +897,13 @@ int fk_init(lqt_engine* h) {
                                    fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc));
         const int worst_c = std::max(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
         if (worst > 64 || worst_c > 64) { h->err = "frame kernel: too many rows per SM"; return 1; }
+        {   // gemv_rpw locates a row's ring stage with three compares: at most four stages per slice
+            auto nst_of = [&](int rows, int K) { const int rps = std::max(1, FK_STAGE_BYTES / (K * 2)); return (rows + rps - 1) / rps; };
+            const int a = nst_of(fk_rmax((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc), s.hidden), dd = nst_of(fk_rmax(2 * s.inter, 2, 1, s.kv_heads, nc), s.hidden);
+            const int ee = nst_of(fk_rmax(s.hidden, 1, 0, s.kv_heads, nc), s.inter), hh = nst_of(fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc), s.hidden);
+            const int ce = nst_of(fk_rmax(s.cp_hidden, 1, 0, s.cp_kv_heads, nc), s.cp_inter), cd = nst_of(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), s.cp_hidden);
+            if (std::max(std::max(std::max(a, dd), std::max(ee, hh)), std::max(ce, cd)) > 4) { h->err = "frame kernel: more than four ring stages per slice"; return 1; }
+        }
         if (std::max(fk_rmax(s.hidden, 1, 0, s.kv_heads, nc), fk_rmax(s.cp_hidden, 1, 0, s.cp_kv_heads, nc)) > FK_X1OWN) { h->err = "frame kernel: too many down-projection rows per SM"; return 1; }
         if (FK_CLUSTER % s.kv_heads || FK_CLUSTER % s.cp_kv_heads) { h->err = "frame kernel: kv heads must divide the cluster size (8)"; return 1; }
         const int rpp_t = (fk_rmax(s.hidden, 1, 2, s.kv_heads, nc) + s.kv_heads - 1) / s.kv_heads, rpp_c = (fk_rmax(s.cp_hidden, 1, 2, s.cp_kv_heads, nc) + s.cp_kv_heads - 1) / s.cp_kv_heads;

@@ -153,6 +153,13 @@ LQT_DEVINL void csync() { asm volatile("bar.sync 1, %0;" ::"n"(FK_CTHREADS) : "m
 // writes is ordered by the mbarrier wait (asm volatile with a memory clobber) that precedes them
 LQT_DEVINL uint2 lds64(const void* p) { return *reinterpret_cast<const uint2*>(p); }
 LQT_DEVINL uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+// shared-space load by 32-bit shared address: the generic->shared conversion (an S2R SR_CgaCtaId under clusters) is done once
+// by the caller instead of once per access. volatile: must stay behind the mbarrier wait that made the data visible.
+LQT_DEVINL uint4 lds128_s(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
 // LL exchange: 8-byte (value, sequence) words. volatile accesses always go to L2 (the coherence point).
 LQT_DEVINL void st_ll(uint2* p, float v, unsigned seq) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
@@ -408,6 +415,26 @@ LQT_DEVINL float reduce8(const float (&a)[8], int lane) {
     return s;
 }
 
+// Blackwell packed fp32 FMA (FFMA2): two independent fp32 FMAs per instruction on 64-bit register pairs. A u32 holding two
+// bf16 weights unpacks into the pair (w << 16, w & 0xffff0000) = (element 0, element 1); the accumulator pair holds the
+// partial sums of the even and of the odd columns.
+LQT_DEVINL unsigned long long pack2(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+LQT_DEVINL unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+LQT_DEVINL unsigned long long bf16x2_to_f32x2(uint32_t u) { return pack2(u << 16, u & 0xffff0000u); }
+LQT_DEVINL float sum2(unsigned long long v) {
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return __uint_as_float(lo) + __uint_as_float(hi);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row-per-warp matrix-vector product (all phases except the grouped O-projection, which has its own below).
 // Row group q (RG = 1 row, or RG = 2 for a gate/up pair) belongs to warp q % 8; the 32 lanes split K
@@ -434,20 +461,25 @@ LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
     return s;
 }
 
+// ring stage of row r of a slice with rps rows per stage, for slices of at most four stages (checked by the host):
+// three compares instead of an integer division (~150 cycles, and several per batch)
+LQT_DEVINL int stage_of(int r, int rps) { return (r >= rps ? 1 : 0) + (r >= 2 * rps ? 1 : 0) + (r >= 3 * rps ? 1 : 0); }
+
 template <int NST, int RG>
 LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
     const int K = d.K, rowbytes = K * 2;
     const int nch = (K + 1023) >> 10;
-    const int nst = (d.nrows + d.rps - 1) / d.rps;
-    float xk[32];
+    const int nst = stage_of(d.nrows - 1, d.rps) + 1;
+    const uint32_t ring_s = smem_u32(c.ring), xp_s = smem_u32(xp);      // shared-space addresses, converted once
+    unsigned long long xk[16];                    // this lane's 32 input values of the current 1024-column chunk, as f32x2 pairs
     auto load_chunk = [&](int ch) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int k = ch * 1024 + i * 256 + c.lane * 8;
-            float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
-            if (k < K) { u0 = *reinterpret_cast<const float4*>(xp + k); u1 = *reinterpret_cast<const float4*>(xp + k + 4); }
-            xk[i * 8 + 0] = u0.x; xk[i * 8 + 1] = u0.y; xk[i * 8 + 2] = u0.z; xk[i * 8 + 3] = u0.w;
-            xk[i * 8 + 4] = u1.x; xk[i * 8 + 5] = u1.y; xk[i * 8 + 6] = u1.z; xk[i * 8 + 7] = u1.w;
+            uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
+            if (k < K) { u0 = lds128_s(xp_s + k * 4); u1 = lds128_s(xp_s + k * 4 + 16); }
+            xk[i * 4 + 0] = pack2(u0.x, u0.y); xk[i * 4 + 1] = pack2(u0.z, u0.w);
+            xk[i * 4 + 2] = pack2(u1.x, u1.y); xk[i * 4 + 3] = pack2(u1.z, u1.w);
         }
     };
     if (nch == 1) load_chunk(0);
@@ -464,7 +496,7 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
         int last = rr[0];
 #pragma unroll
         for (int j = 1; j < 4; ++j) if (rr[j] < d.nrows) last = rr[j];
-        const int g0 = rr[0] / d.rps, g1 = last / d.rps;
+        const int g0 = stage_of(rr[0], d.rps), g1 = stage_of(last, d.rps);
         while (cur < g0) {                        // stages that hold no (further) row of this warp
             if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
             __syncwarp();
@@ -472,14 +504,14 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
             ++cur;
         }
         while (seen <= g1) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
-        const unsigned char* wr[4];
+        uint32_t wr[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = (rr[j] < d.nrows) ? rr[j] : rr[0];          // rows beyond the slice: recompute row 0 (dropped)
-            const int g = r / d.rps;
-            wr[j] = c.ring + (size_t)((c.stage_ctr + g) % (unsigned)NST) * FK_STAGE_BYTES + (size_t)(r - g * d.rps) * rowbytes + c.lane * 16;
+            const int g = stage_of(r, d.rps);
+            wr[j] = ring_s + ((c.stage_ctr + g) % (unsigned)NST) * FK_STAGE_BYTES + (unsigned)(r - g * d.rps) * (unsigned)rowbytes + c.lane * 16;
         }
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned long long a2[4] = {0ull, 0ull, 0ull, 0ull};         // (even-column sum, odd-column sum) per row
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
             if (nch > 1) load_chunk(ch);
@@ -487,17 +519,22 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w[j][i] = (ch * 1024 + i * 256 < K) ? lds128(wr[j] + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < 4; ++i) w[j][i] = (ch * 1024 + i * 256 < K) ? lds128_s(wr[j] + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
+            // the four rows' chains are interleaved instruction by instruction (row index innermost): consecutive FMAs are
+            // independent, so the 4-cycle FMA latency is covered by the other three rows
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    a[j] = fmaf(bf16lo(w[j][i].x), xk[i * 8 + 0], a[j]); a[j] = fmaf(bf16hi(w[j][i].x), xk[i * 8 + 1], a[j]);
-                    a[j] = fmaf(bf16lo(w[j][i].y), xk[i * 8 + 2], a[j]); a[j] = fmaf(bf16hi(w[j][i].y), xk[i * 8 + 3], a[j]);
-                    a[j] = fmaf(bf16lo(w[j][i].z), xk[i * 8 + 4], a[j]); a[j] = fmaf(bf16hi(w[j][i].z), xk[i * 8 + 5], a[j]);
-                    a[j] = fmaf(bf16lo(w[j][i].w), xk[i * 8 + 6], a[j]); a[j] = fmaf(bf16hi(w[j][i].w), xk[i * 8 + 7], a[j]);
-                }
+                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].x), xk[i * 4 + 0], a2[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].y), xk[i * 4 + 1], a2[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].z), xk[i * 4 + 2], a2[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].w), xk[i * 4 + 3], a2[j]);
+            }
         }
+        const float a[4] = {sum2(a2[0]), sum2(a2[1]), sum2(a2[2]), sum2(a2[3])};
         const float t = reduce4(a, c.lane);                          // lanes 8j .. 8j+7 hold the sum of slot sb + j
         const float v = __shfl_sync(0xffffffffu, t, ((c.lane - sb) & 3) * 8);
         if (c.lane >= sb && c.lane < sb + 4) mine = v;
@@ -538,15 +575,15 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
         const unsigned ast = c.stage_ctr + st, slot = ast % (unsigned)NST;
         wait_full(c, ast, NST);
         const int nrs = min(d.rps, d.nrows - row);
-        const unsigned char* sb = c.ring + (size_t)slot * FK_STAGE_BYTES;
+        const uint32_t sb = smem_u32(c.ring) + slot * FK_STAGE_BYTES;
 #pragma unroll 1
         for (int r0 = 0; r0 < nrs; r0 += 64) {
             uint4 w[8][NC];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const unsigned char* rb = sb + min(r0 + c.warp + 8 * i, nrs - 1) * rowbytes;
+                const uint32_t rb = sb + (unsigned)(min(r0 + c.warp + 8 * i, nrs - 1) * rowbytes);
 #pragma unroll
-                for (int cc = 0; cc < NC; ++cc) w[i][cc] = lds128(rb + coff[cc]);
+                for (int cc = 0; cc < NC; ++cc) w[i][cc] = lds128_s(rb + coff[cc]);
             }
             float a[8];
 #pragma unroll
