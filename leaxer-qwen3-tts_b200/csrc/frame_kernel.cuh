@@ -1581,6 +1581,10 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                         const unsigned slot = issued % (unsigned)NST, par = ((issued / (unsigned)NST) & 1u) ^ 1u;
                         unsigned long long t0 = 0;
                         while (!mbar_try_wait(&sh->empty[slot], par)) {
+                            // The ring is full: the producer is ~10 us ahead of the consumers (profiles/r1_v19_ring_latency.txt), so it
+                            // sleeps between polls instead of spinning -- it shares its scheduler with consumer warps 0 and 4, and
+                            // warp 0 (grid hand-over, reductions, sampler tail) is the critical path of every phase.
+                            __nanosleep(400);
                             if (sh->stop) { stopped = true; break; }
                             if (t0 == 0) t0 = clock64();
                             else if (clock64() - t0 > FK_SPIN_LIMIT) { stopped = true; break; }
