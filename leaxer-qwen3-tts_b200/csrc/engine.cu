@@ -987,8 +987,8 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.dbg = h->fk_dbg; p.dbg_cap = h->fk_dbg_cap; p.dbg_cta = h->fk_dbg_cta;
     CK(cudaMemsetAsync(h->fk_ctrl, 0, 64 * sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->fk_arena, 0, h->fk_arena_words * sizeof(uint2), h->stream));   // sequence numbers restart at 1
-    FkSmemOffsets so = h->fk_so;
-    void* args[] = {(void*)&p, (void*)&so};
+    p.so = h->fk_so;
+    void* args[] = {(void*)&p};
     {
         const void* fn = h->fk_wide ? (const void*)frame_kernel<6, 3> : (const void*)frame_kernel<3, 4>;
         cudaLaunchConfig_t cfg{};

@@ -40,6 +40,8 @@ namespace lqt {
 
 typedef __nv_bfloat16 bf16_t;
 
+extern __shared__ __align__(1024) unsigned char fk_smem[];     // the frame kernel's dynamic shared memory
+
 constexpr int FK_CWARPS = 8;
 constexpr int FK_CTHREADS = FK_CWARPS * 32;       // consumer threads
 constexpr int FK_THREADS = FK_CTHREADS + 128;     // + one producer warpgroup (one lane works; a whole warpgroup so that setmaxnreg can hand its registers over)
@@ -73,7 +75,12 @@ struct FkStack {
     uint2 *x, *qkv, *x1, *act;            // LL buffers: layer output [H], projections [qkv_dim], post-attention stream [H], SwiGLU [inter]
 };
 
+struct FkSmemOffsets { unsigned land, scratch, att, xs, red, nxt, res0, lh, shared; int maxV; };
+
 struct FkParams {
+    FkSmemOffsets so;          // carve-up of the dynamic shared memory (constant bank): shared-memory addresses are derived from the fk_smem
+                               // symbol where they are used, so they are shared-space accesses (no generic->shared conversion, which under
+                               // clusters costs an S2R SR_CgaCtaId per access) and occupy no registers
     FkStack talker, cp;
     FkLayer t_layers[FK_MAX_TLAYERS];     // in the kernel-parameter constant bank: no load latency
     FkLayer c_layers[FK_MAX_CLAYERS];
@@ -205,19 +212,9 @@ struct FkShared {
 
 struct FkCtx {
     const FkParams* p;
-    FkShared* sh;
-    unsigned char* ring;      // nstages * FK_STAGE_BYTES
-    float* att;               // attention scratch
-    float* xs;                // attention output rows [2][FK_XS_STRIDE] (input of the grouped O-projection)
-    float* xp;                // plain input vector of the current matrix-vector phase [maxK]
-    uint2* land;              // [2][FK_LAND_WORDS] multicast landing buffers
     unsigned land_n;          // fetches so far (buffer = land_n & 1, barrier parity = (land_n >> 1) & 1)
-    const uint2* land_a;      // where this layer's input row landed (residual of the O-projection)
+    unsigned land_a;          // landing buffer (0/1) that holds this layer's input row (residual of the O-projection)
     unsigned rank;            // CTA rank in the cluster
-    uint2* dbg_pg;            // FK_NO_DSMEM: partials through global memory
-    float* nxt;               // running next talker input [H]
-    float* res0;              // layer-0 input rows of the current pass [M][H0] (also its residual)
-    float* lh;                // talker last_hidden [H] (code-predictor row 0, src/tts_onnx.cpp:859)
     int tid, lane, warp;
     int cta, ncta;
     unsigned seq;             // number of the current phase (1, 2, ...): tag of everything it publishes
@@ -225,6 +222,17 @@ struct FkCtx {
     bool aborted;
     unsigned long long* dbg; int dbg_n, dbg_cap, dbg_tag;   // dbg_tag = (stack << 9) | (kind << 4) of the current phase
 };
+
+// shared-memory regions, derived from the carve-up in the constant bank (see fk_smem_layout)
+#define FK_SH(c)   (reinterpret_cast<FkShared*>(fk_smem + (c).p->so.shared))
+#define FK_RING(c) (fk_smem)
+#define FK_ATT(c)  (reinterpret_cast<float*>(fk_smem + (c).p->so.att))
+#define FK_XS(c)   (reinterpret_cast<float*>(fk_smem + (c).p->so.xs))
+#define FK_XP(c)   (reinterpret_cast<float*>(fk_smem + (c).p->so.scratch))
+#define FK_LAND(c) (reinterpret_cast<uint2*>(fk_smem + (c).p->so.land))
+#define FK_NXT(c)  (reinterpret_cast<float*>(fk_smem + (c).p->so.nxt))
+#define FK_RES0(c) (reinterpret_cast<float*>(fk_smem + (c).p->so.res0))
+#define FK_LH(c)   (reinterpret_cast<float*>(fk_smem + (c).p->so.lh))
 
 // timeline entries: (SM clock << 16) | (stack << 9) | (phase kind << 4) | point. Points:
 //  0 phase begin   2 inputs in registers (polling done)   3 inputs complete (attention / staging done; before the GEMV)
@@ -341,7 +349,7 @@ struct FkRaw4 { uint4 a, b; };
 LQT_DEVINL FkRaw4 ll_issue4(const uint2* p) { FkRaw4 r; r.a = ld_ll2(p); r.b = ld_ll2(p + 2); return r; }
 LQT_DEVINL float4 ll_finish4(FkCtx& c, FkRaw4 r, const uint2* p, unsigned seq) {
     if (r.a.y != seq || r.a.w != seq || r.b.y != seq || r.b.w != seq) {
-        const FkLL4 q = ll_poll4_slow(p, seq, &c.sh->aborted, c.p->ctrl);
+        const FkLL4 q = ll_poll4_slow(p, seq, &FK_SH(c)->aborted, c.p->ctrl);
         r.a = q.a; r.b = q.b;
     }
     return make_float4(__uint_as_float(r.a.x), __uint_as_float(r.a.z), __uint_as_float(r.b.x), __uint_as_float(r.b.z));
@@ -372,13 +380,13 @@ LQT_DEVINL void grid_wait(FkCtx& c, unsigned n) {
         const unsigned target = n * (unsigned)c.ncta;
         unsigned v;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
-        if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &c.sh->aborted, c.p->ctrl);
+        if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &FK_SH(c)->aborted, c.p->ctrl);
     }
     csync();
 }
 LQT_DEVINL float ll_poll1(FkCtx& c, const uint2* p, unsigned seq) {
     uint2 a = ld_ll1(p);
-    if (a.y != seq) a = ll_poll1_slow(p, seq, &c.sh->aborted, c.p->ctrl, 100);
+    if (a.y != seq) a = ll_poll1_slow(p, seq, &FK_SH(c)->aborted, c.p->ctrl, 100);
     return __uint_as_float(a.x);
 }
 
@@ -387,8 +395,8 @@ LQT_DEVINL float ll_poll1(FkCtx& c, const uint2* p, unsigned seq) {
 // ------------------------------------------------------------------------------------------------
 LQT_DEVINL void wait_full(FkCtx& c, unsigned st, int nstages) {
     const unsigned slot = st % (unsigned)nstages, par = (st / (unsigned)nstages) & 1u;
-    if (!mbar_try_wait(&c.sh->full[slot], par)) {
-        if (!wait_full_slow(&c.sh->full[slot], par, c.p->ctrl)) c.aborted = true;
+    if (!mbar_try_wait(&FK_SH(c)->full[slot], par)) {
+        if (!wait_full_slow(&FK_SH(c)->full[slot], par, c.p->ctrl)) c.aborted = true;
     }
 }
 
@@ -470,7 +478,7 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
     const int K = d.K, rowbytes = K * 2;
     const int nch = (K + 1023) >> 10;
     const int nst = stage_of(d.nrows - 1, d.rps) + 1;
-    const uint32_t ring_s = smem_u32(c.ring), xp_s = smem_u32(xp);      // shared-space addresses, converted once
+    const uint32_t ring_s = smem_u32(FK_RING(c)), xp_s = smem_u32(xp);      // shared-space addresses, converted once
     unsigned long long xk[16];                    // this lane's 32 input values of the current 1024-column chunk, as f32x2 pairs
     auto load_chunk = [&](int ch) {
 #pragma unroll
@@ -500,7 +508,7 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
         while (cur < g0) {                        // stages that hold no (further) row of this warp
             if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
             __syncwarp();
-            if (c.lane == 0) mbar_arrive(&c.sh->empty[(c.stage_ctr + cur) % (unsigned)NST]);
+            if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + cur) % (unsigned)NST]);
             ++cur;
         }
         while (seen <= g1) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
@@ -542,14 +550,14 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
     while (cur < nst) {
         if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.sh->empty[(c.stage_ctr + cur) % (unsigned)NST]);
+        if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + cur) % (unsigned)NST]);
         ++cur;
     }
     c.stage_ctr += nst;
     return mine;
 }
 
-// Row-per-warp product for the grouped O-projection (K = rep*128 <= 512, input row in c.xs): warp w owns
+// Row-per-warp product for the grouped O-projection (K = rep*128 <= 512, input row in FK_XS(c)): warp w owns
 // rows w, w + 8, ... of every stage. The n_kv CTAs that hold the partials of the same rows (one per kv group) sit
 // in the same cluster: partial (row r) goes straight from the reduction into the shared memory of partner
 // r / rpp as a (value, sequence) word (DSMEM store, no barrier); the partner sums them (reduce_partials).
@@ -564,7 +572,7 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
         const bool act = k < K;
         coff[cc] = act ? k * 2 : 0;
         float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
-        if (act) { u0 = *reinterpret_cast<const float4*>(c.xs + k); u1 = *reinterpret_cast<const float4*>(c.xs + k + 4); }
+        if (act) { u0 = *reinterpret_cast<const float4*>(FK_XS(c) + k); u1 = *reinterpret_cast<const float4*>(FK_XS(c) + k + 4); }
         x0[cc][0] = u0.x; x0[cc][1] = u0.y; x0[cc][2] = u0.z; x0[cc][3] = u0.w; x0[cc][4] = u1.x; x0[cc][5] = u1.y; x0[cc][6] = u1.z; x0[cc][7] = u1.w;
     }
     const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
@@ -575,7 +583,7 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
         const unsigned ast = c.stage_ctr + st, slot = ast % (unsigned)NST;
         wait_full(c, ast, NST);
         const int nrs = min(d.rps, d.nrows - row);
-        const uint32_t sb = smem_u32(c.ring) + slot * FK_STAGE_BYTES;
+        const uint32_t sb = smem_u32(FK_RING(c)) + slot * FK_STAGE_BYTES;
 #pragma unroll 1
         for (int r0 = 0; r0 < nrs; r0 += 64) {
             uint4 w[8][NC];
@@ -602,15 +610,15 @@ LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
             if ((c.lane & 3) == 0 && r < nrs) {
                 const int rr = row + r, tg = rr / rpp;
 #ifdef FK_NO_DSMEM                                // bisecting aid: partials through global memory
-                st_ll(c.dbg_pg + (size_t)g * 4096 + d.row0 + rr, s, c.seq);
+                st_ll((c.p->pa + 8 * FK_NS_MAX * 2 * ATT_PSTRIDE) + (size_t)g * 4096 + d.row0 + rr, s, c.seq);
                 (void)tg; (void)base;
 #else
-                st_ll_dsmem(dsmem_addr(&c.sh->redc[g][rr - tg * rpp], base + (unsigned)tg), s, c.seq);
+                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][rr - tg * rpp], base + (unsigned)tg), s, c.seq);
 #endif
             }
         }
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.sh->empty[slot]);
+        if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[slot]);
         row += nrs;
     }
     c.stage_ctr += nst;
@@ -621,7 +629,7 @@ LQT_DEVINL void gemv_rw(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
 }
 
 LQT_DEVINL float ss_rstd(FkCtx& c, int K, float eps) {
-    const float* q = &c.sh->ssred[c.seq & 1u][0];
+    const float* q = &FK_SH(c)->ssred[c.seq & 1u][0];
     float t = q[0];
 #pragma unroll
     for (int w = 1; w < FK_CWARPS; ++w) t += q[w];
@@ -630,13 +638,13 @@ LQT_DEVINL float ss_rstd(FkCtx& c, int K, float eps) {
 // this thread's partial sum of squares -> shared (parity of c.seq); read after the phase's CTA barrier
 LQT_DEVINL void ss_publish(FkCtx& c, float ss) {
     ss = warp_sum(ss);
-    if (c.lane == 0) c.sh->ssred[c.seq & 1u][c.warp] = ss;
+    if (c.lane == 0) FK_SH(c)->ssred[c.seq & 1u][c.warp] = ss;
 }
 
 // ------------------------------------------------------------------------------------------------
 // attention pieces
 // ------------------------------------------------------------------------------------------------
-// attention scratch layout (floats) inside c.att
+// attention scratch layout (floats) inside FK_ATT(c)
 constexpr int FA_Q = 0;                              // q_s   [2 m][2 r][128]
 constexpr int FA_KN = FA_Q + 4 * ATT_D;              // knew  [2 m][128]
 constexpr int FA_VN = FA_KN + 2 * ATT_D;             // vnew  [2 m][128]
@@ -670,9 +678,9 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     KVT* pool = reinterpret_cast<KVT*>(p.kv_pool);
     const long long layer_off = (long long)layer * 2 * n_kv * PS * ATT_D;
     const long long head_off = (long long)g * PS * ATT_D, v_off = (long long)n_kv * PS * ATT_D;
-    float* q_s = c.att + FA_Q;
-    float* kn = c.att + FA_KN;
-    float* vn = c.att + FA_VN;
+    float* q_s = FK_ATT(c) + FA_Q;
+    float* kn = FK_ATT(c) + FA_KN;
+    float* vn = FK_ATT(c) + FA_VN;
     const bool owns_new = (j1 == n_pos);
     if (c.warp < 2) {
         float4 v = ll_poll4(c, S.qkv + (size_t)(g * 2 + c.warp) * ATT_D + c.lane * 4, want);
@@ -734,7 +742,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
             }
         }
     }
-    float* wm = c.att + FA_WM; float* wl = c.att + FA_WL; float* wo = c.att + FA_WO;
+    float* wm = FK_ATT(c) + FA_WM; float* wl = FK_ATT(c) + FA_WL; float* wo = FK_ATT(c) + FA_WO;
     reinterpret_cast<float4*>(wo + (c.warp * 2 + 0) * ATT_D)[c.lane] = a0;
     reinterpret_cast<float4*>(wo + (c.warp * 2 + 1) * ATT_D)[c.lane] = a1;
     if (c.lane == 0) { wm[c.warp * 2] = m0; wm[c.warp * 2 + 1] = m1; wl[c.warp * 2] = l0; wl[c.warp * 2 + 1] = l1; }
@@ -759,7 +767,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     csync();                     // scratch is reused by the next phase
 }
 
-// talker: combine the splits of group g -> c.xs[0][0..rep*128)  (input of the grouped O-projection)
+// talker: combine the splits of group g -> FK_XS(c)[0][0..rep*128)  (input of the grouped O-projection)
 LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
     const FkParams& p = *c.p;
     const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
@@ -793,17 +801,17 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
             }
         }
     }
-    c.xs[c.tid] = num / den;
+    FK_XS(c)[c.tid] = num / den;
     csync();
 }
 
-// code predictor: full attention of kv group g for the M new positions p0.., result -> c.xs[m][0..256)
+// code predictor: full attention of kv group g for the M new positions p0.., result -> FK_XS(c)[m][0..256)
 LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int p0, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.cp;
     const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv;
     const int q_dim = S.heads * ATT_D, kv_dim = n_kv * ATT_D, qkv_dim = q_dim + 2 * kv_dim;
-    float* q_s = c.att + FA_Q; float* kn = c.att + FA_KN; float* vn = c.att + FA_VN; float* sc = c.att + FA_SC;
+    float* q_s = FK_ATT(c) + FA_Q; float* kn = FK_ATT(c) + FA_KN; float* vn = FK_ATT(c) + FA_VN; float* sc = FK_ATT(c) + FA_SC;
     float* kc = p.cp_kv + ((size_t)(layer * 2 + 0) * n_kv + g) * FK_CP_POS * ATT_D;
     float* vc = p.cp_kv + ((size_t)(layer * 2 + 1) * n_kv + g) * FK_CP_POS * ATT_D;
     // prefetch the cached V column of this thread and the cached K rows of this warp (positions < p0)
@@ -886,13 +894,13 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
 #pragma unroll
         for (int j = 0; j < FK_CP_POS / 2; ++j) if (j < p0) o = fmaf(row[j], vcol[j], o);
         for (int j = p0; j < np; ++j) o = fmaf(row[j], vn[(j - p0) * ATT_D + d_t], o);
-        c.xs[m * FK_XS_STRIDE + c.tid] = o;
+        FK_XS(c)[m * FK_XS_STRIDE + c.tid] = o;
     }
     csync();
 }
 // ------------------------------------------------------------------------------------------------
 // one token pass (one row) through a stack, as ONE loop over the flat op schedule so that every helper
-// is instantiated exactly once. The layer-0 input row is in c.res0 (smem, plain layout). The residual
+// is instantiated exactly once. The layer-0 input row is in FK_RES0(c) (smem, plain layout). The residual
 // stream of the current layer stays in registers (xin) from phase A to D.
 // ------------------------------------------------------------------------------------------------
 struct FkPass { bool is_cp; int pos0; bool head; };
@@ -912,8 +920,8 @@ LQT_DEVINL void f4_to(float (&d)[4], const float4& v) { d[0] = v.x; d[1] = v.y; 
 // ------------------------------------------------------------------------------------------------
 LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W) {
     const unsigned b = c.land_n & 1u, par = (c.land_n >> 1) & 1u;
-    uint2* dst = c.land + b * FK_LAND_WORDS;
-    uint64_t* bar = &c.sh->land_bar[b];
+    uint2* dst = FK_LAND(c) + b * FK_LAND_WORDS;
+    uint64_t* bar = &FK_SH(c)->land_bar[b];
 #ifdef FK_NO_MC                                   // bisecting aid: plain per-CTA copy instead of the multicast
     for (int w = c.tid * 2; w < W; w += FK_CTHREADS * 2) *reinterpret_cast<uint4*>(dst + w) = ld_ll2(src + w);
     csync();
@@ -944,7 +952,7 @@ LQT_DEVINL void land_row(FkCtx& c, uint2* land, const uint2* src, int K, unsigne
         if (k < K) {
             uint4 a = *reinterpret_cast<const uint4*>(land + k), b = *reinterpret_cast<const uint4*>(land + k + 2);
             if (a.y != want || a.w != want || b.y != want || b.w != want) {
-                const FkLL4 q = ll_poll4_slow(src + k, want, &c.sh->aborted, c.p->ctrl);
+                const FkLL4 q = ll_poll4_slow(src + k, want, &FK_SH(c)->aborted, c.p->ctrl);
                 a = q.a; b = q.b;
                 *reinterpret_cast<uint4*>(land + k) = a; *reinterpret_cast<uint4*>(land + k + 2) = b;
             }
@@ -961,7 +969,7 @@ __device__ __noinline__ uint2 redc_poll_slow(const uint2* p, unsigned seq, volat
     } while (a.y != seq);
     return a;
 }
-// warp 0: sum the O-projection partials that the partner CTAs pushed into c.sh->redc (+ residual) for the rows this CTA
+// warp 0: sum the O-projection partials that the partner CTAs pushed into FK_SH(c)->redc (+ residual) for the rows this CTA
 // reduces, publish the post-attention stream x1 (global LL), then signal the grid
 LQT_DEVINL void reduce_partials(FkCtx& c, const FkDesc& d, int n_kv, int rpp, const float* res_plain, const uint2* res_land, uint2* x1) {
     if (c.warp != 0) return;
@@ -973,10 +981,10 @@ LQT_DEVINL void reduce_partials(FkCtx& c, const FkDesc& d, int n_kv, int rpp, co
 #pragma unroll 1
         for (int gg = 0; gg < n_kv; ++gg) {
 #ifdef FK_NO_DSMEM
-            acc += ll_poll1(c, c.dbg_pg + (size_t)gg * 4096 + row, c.seq);
+            acc += ll_poll1(c, (c.p->pa + 8 * FK_NS_MAX * 2 * ATT_PSTRIDE) + (size_t)gg * 4096 + row, c.seq);
 #else
-            uint2 v = ld_ll_smem(&c.sh->redc[gg][c.lane]);
-            if (v.y != c.seq) v = redc_poll_slow(&c.sh->redc[gg][c.lane], c.seq, &c.sh->aborted, c.p->ctrl);
+            uint2 v = ld_ll_smem(&FK_SH(c)->redc[gg][c.lane]);
+            if (v.y != c.seq) v = redc_poll_slow(&FK_SH(c)->redc[gg][c.lane], c.seq, &FK_SH(c)->aborted, c.p->ctrl);
             acc += __uint_as_float(v.x);
 #endif
         }
@@ -1006,7 +1014,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         fk_phase(c, tk, kind);
         fk_mark(c, 0);
         const FkLayer& L = is_cp ? p.c_layers[l] : p.t_layers[l];
-        const FkDesc d = c.sh->desc[tk][kind];
+        const FkDesc d = FK_SH(c)->desc[tk][kind];
         // RMSNorm weight of this phase: fetched BEFORE the grid hand-over (independent of the activations)
         const float* nw = (kind == FKT_A) ? L.ln1 : (kind == FKT_D) ? L.ln2 : (kind == FKT_HEAD) ? S.final_norm : nullptr;
         float4 nwv[HJ];
@@ -1023,51 +1031,51 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             csync();
             if (c.tid == 0) grid_arrive(c);
             fk_mark(c, 3);
-            if (c.sh->aborted) { c.aborted = true; break; }
+            if (FK_SH(c)->aborted) { c.aborted = true; break; }
             continue;
         }
         if (kind == FKT_C) {
             if (is_cp) cp_attn_local(c, L, l, 1, ps.pos0, want);
             else       talker_attn_combine(c, ps.pos0, want);
             fk_mark(c, 3);
-            if (c.sh->aborted) { c.aborted = true; break; }
+            if (FK_SH(c)->aborted) { c.aborted = true; break; }
             const int rpp = (d.nrows + n_kv - 1) / n_kv;
             gemv_rw<NST>(c, d, n_kv, rpp);
             fk_mark(c, 5);
-            reduce_partials(c, d, n_kv, rpp, in_res0 ? c.res0 : nullptr, c.land_a, S.x1);
+            reduce_partials(c, d, n_kv, rpp, in_res0 ? FK_RES0(c) : nullptr, FK_LAND(c) + c.land_a * FK_LAND_WORDS, S.x1);
             fk_mark(c, 6);
-            if (c.aborted || c.sh->aborted) { c.aborted = true; break; }
+            if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; break; }
             continue;
         }
         // ---- K phases: stage the input vector as plain floats (x * w_norm for the normalised phases) ------------
         float xin[HJ][4];                                      // the raw row (this thread's columns): sum of squares, last_hidden
 #pragma unroll
         for (int j = 0; j < HJ; ++j) { xin[j][0] = 0.f; xin[j][1] = 0.f; xin[j][2] = 0.f; xin[j][3] = 0.f; }
-        const float* xp = c.xp;
+        const float* xp = FK_XP(c);
         switch (kind) {
-            case FKT_INPROJ: xp = c.res0; break;               // plain row in shared memory already, no norm
+            case FKT_INPROJ: xp = FK_RES0(c); break;               // plain row in shared memory already, no norm
             case FKT_A: {
                 if (in_res0) {
 #pragma unroll
                     for (int j = 0; j < HJ; ++j)
-                        if (j * 1024 + tid4 < H) f4_to(xin[j], *reinterpret_cast<const float4*>(c.res0 + j * 1024 + tid4));
+                        if (j * 1024 + tid4 < H) f4_to(xin[j], *reinterpret_cast<const float4*>(FK_RES0(c) + j * 1024 + tid4));
                 } else {
                     uint2* land = mc_fetch(c, lin, H);
                     land_row<HJ>(c, land, lin, H, want, xin);
-                    c.land_a = land;
+                    c.land_a = (c.land_n - 1u) & 1u;
                 }
                 break;
             }
             case FKT_D: {
                 uint2* land = mc_fetch(c, S.x1, H);
                 land_row<HJ>(c, land, S.x1, H, want, xin);
-                const FkDesc& de = c.sh->desc[tk][FKT_E];
+                const FkDesc& de = FK_SH(c)->desc[tk][FKT_E];
 #pragma unroll
                 for (int j = 0; j < HJ; ++j)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {                          // residual for this CTA's down-projection rows
                         const unsigned rel = (unsigned)(j * 1024 + tid4 + i - de.row0);
-                        if (rel < (unsigned)de.nrows) c.sh->x1own[rel] = xin[j][i];
+                        if (rel < (unsigned)de.nrows) FK_SH(c)->x1own[rel] = xin[j][i];
                     }
                 break;
             }
@@ -1080,7 +1088,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     land_row<3>(c, land, S.act + w0, wn, want, t3);
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
-                        if (j * 1024 + tid4 < wn) *reinterpret_cast<float4*>(c.xp + w0 + j * 1024 + tid4) = make_float4(t3[j][0], t3[j][1], t3[j][2], t3[j][3]);
+                        if (j * 1024 + tid4 < wn) *reinterpret_cast<float4*>(FK_XP(c) + w0 + j * 1024 + tid4) = make_float4(t3[j][0], t3[j][1], t3[j][2], t3[j][3]);
                 }
                 break;
             }
@@ -1099,14 +1107,14 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     const float4 w = nwv[j];
                     ss = fmaf(xin[j][0], xin[j][0], ss); ss = fmaf(xin[j][1], xin[j][1], ss);
                     ss = fmaf(xin[j][2], xin[j][2], ss); ss = fmaf(xin[j][3], xin[j][3], ss);
-                    *reinterpret_cast<float4*>(c.xp + j * 1024 + tid4) = make_float4(xin[j][0] * w.x, xin[j][1] * w.y, xin[j][2] * w.z, xin[j][3] * w.w);
+                    *reinterpret_cast<float4*>(FK_XP(c) + j * 1024 + tid4) = make_float4(xin[j][0] * w.x, xin[j][1] * w.y, xin[j][2] * w.z, xin[j][3] * w.w);
                 }
             }
             ss_publish(c, ss);
         }
-        if (c.aborted || c.sh->aborted) { c.aborted = true; }
+        if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; }
         if (kind != FKT_INPROJ) csync();                       // the plain input vector (and the sum-of-squares partials) are complete
-        if (c.sh->aborted) { c.aborted = true; break; }
+        if (FK_SH(c)->aborted) { c.aborted = true; break; }
         // ---- product + epilogue on the lanes that hold the sums ----------------------------------------------
         {
             const float rs = nw ? ss_rstd(c, H, p.eps) : 1.f;
@@ -1124,7 +1132,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                 const int r = slot * 8 + c.warp, n = d.row0 + r;
                 if (lead && r < d.nrows) {
                     if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
-                    else if (kind == FKT_E) st_ll(S.x + n, c.sh->x1own[r] + v, c.seq);
+                    else if (kind == FKT_E) st_ll(S.x + n, FK_SH(c)->x1own[r] + v, c.seq);
                     else if (kind == FKT_INPROJ) st_ll(p.cxin + n, v + __ldg(p.c_inproj_b + n), c.seq);
                     else {
                         st_ll((is_cp ? p.clogits_ll : p.logits_ll) + n, v, c.seq);
@@ -1138,7 +1146,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     if (j * 1024 + tid4 < H) {
                         const float4 w = nwv[j];
                         const float4 o = make_float4((xin[j][0] * rs) * w.x, (xin[j][1] * rs) * w.y, (xin[j][2] * rs) * w.z, (xin[j][3] * rs) * w.w);
-                        *reinterpret_cast<float4*>(c.lh + j * 1024 + tid4) = o;
+                        *reinterpret_cast<float4*>(FK_LH(c) + j * 1024 + tid4) = o;
                         if (c.cta == 0) *reinterpret_cast<float4*>(p.last_hidden + j * 1024 + tid4) = o;
                     }
                 }
@@ -1156,17 +1164,28 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
 // executed redundantly by every CTA on the same logits
 // ------------------------------------------------------------------------------------------------
 struct FkSampScratch { float* x; float* pr; float* spr; unsigned short* idx; unsigned short* rank; };
+// x: own scratch; the arrays of the general path reuse the landing buffers. Built where it is used so that the pointers stay
+// shared-space addresses derived from the fk_smem symbol.
+LQT_DEVINL FkSampScratch fk_scratch(const FkCtx& c) {
+    FkSampScratch s;
+    const FkSmemOffsets& so = c.p->so;
+    s.x = reinterpret_cast<float*>(fk_smem + so.scratch);
+    s.pr = reinterpret_cast<float*>(fk_smem + so.land);
+    s.spr = s.pr + so.maxV;
+    s.idx = reinterpret_cast<unsigned short*>(s.spr + so.maxV); s.rank = s.idx + so.maxV;
+    return s;
+}
 
 LQT_DEVINL int block_excl_scan(FkCtx& c, int v, int* total) {          // 256-thread exclusive scan
     int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (c.lane >= o) inc += t; }
     csync();
-    if (c.lane == 31) c.sh->wtot[c.warp] = inc;
+    if (c.lane == 31) FK_SH(c)->wtot[c.warp] = inc;
     csync();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int w2 = 0; w2 < FK_CWARPS; ++w2) { const int t = c.sh->wtot[w2]; if (w2 < c.warp) base += t; tot += t; }
+    for (int w2 = 0; w2 < FK_CWARPS; ++w2) { const int t = FK_SH(c)->wtot[w2]; if (w2 < c.warp) base += t; tot += t; }
     *total = tot;
     return base + inc - v;
 }
@@ -1177,9 +1196,10 @@ LQT_DEVINL int block_excl_scan(FkCtx& c, int v, int* total) {          // 256-th
 // (ties survive, src/tts_onnx.cpp:917-927), softmax (:907-915), top-p (:929-950), renormalisation and the
 // categorical draw in index order (:893-905), all sums serial in the reference's order.
 // Returns -1 when the shape does not fit (flat logits): the caller falls back to the general path.
-LQT_DEVINL int fk_sample_fast(FkCtx& c, const FkSampScratch& s, int i0, int i1, float mx, const SamplingDev& sp,
+LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const SamplingDev& sp,
                               uint32_t frame, int codebook) {
-    FkShared* sh = c.sh;
+    FkShared* sh = FK_SH(c);
+    const FkSampScratch s = fk_scratch(c);
     const int k = sp.top_k;
     sh->hist[c.tid] = 0;
     csync();
@@ -1329,10 +1349,11 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, const FkSampScratch& s, int i0, int i1, 
 }
 
 // logits: LL words tagged `want` (ll != nullptr; already multicast into `land`) or a plain array (first draw after a resume)
-LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, const uint2* land, const float* plain, unsigned want, int V,
+LQT_DEVINL int fk_sample(FkCtx& c, const uint2* ll, const uint2* land, const float* plain, unsigned want, int V,
                          int mask_lo, int mask_hi, int mask_keep, const SamplingDev& sp, uint32_t frame, int codebook,
                          float* trace_row) {
-    FkShared* sh = c.sh;
+    FkShared* sh = FK_SH(c);
+    const FkSampScratch s = fk_scratch(c);
     const bool temper = !sp.greedy && sp.temperature > 0.0f && sp.temperature != 1.0f;
     // thread owns the contiguous range [i0, i1) (V % 4 == 0, ranges are multiples of 4)
     const int per = (((V + FK_CTHREADS - 1) / FK_CTHREADS) + 3) & ~3;
@@ -1347,7 +1368,7 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
             if (ll) {                                          // landed (value, sequence) words, validated like every other input
                 uint4 a = *reinterpret_cast<const uint4*>(land + i), b = *reinterpret_cast<const uint4*>(land + i + 2);
                 if (a.y != want || a.w != want || b.y != want || b.w != want) {
-                    const FkLL4 r = ll_poll4_slow(ll + i, want, &c.sh->aborted, c.p->ctrl);
+                    const FkLL4 r = ll_poll4_slow(ll + i, want, &FK_SH(c)->aborted, c.p->ctrl);
                     a = r.a; b = r.b;
                 }
                 q = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
@@ -1385,7 +1406,7 @@ LQT_DEVINL int fk_sample(FkCtx& c, const FkSampScratch& s, const uint2* ll, cons
     if (sp.greedy) { csync(); return bi; }
     const float mx = bv;
     if (sp.top_k > 0 && sp.top_k < V && sp.top_k <= 64) {      // common case: a handful of survivors, finished by one warp
-        const int t = fk_sample_fast(c, s, i0, i1, mx, sp, frame, codebook);
+        const int t = fk_sample_fast(c, i0, i1, mx, sp, frame, codebook);
         if (t >= 0) return t;
     }
 
@@ -1513,14 +1534,11 @@ inline FkSmemLayout fk_smem_layout(int nstages, int maxV, int H, int maxK) {
     return L;
 }
 
-struct FkSmemOffsets { unsigned land, scratch, att, xs, red, nxt, res0, lh, shared; int maxV; };
-
 // KJ = 1024-column chunks of the widest matrix (3: inter <= 3072, 6: <= 6144); NST = ring stages
 template <int KJ, int NST>
 __global__ void __launch_bounds__(FK_THREADS, 1)
-frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
-    extern __shared__ __align__(1024) unsigned char fk_smem[];
-    FkShared* sh = reinterpret_cast<FkShared*>(fk_smem + so.shared);
+frame_kernel(const __grid_constant__ FkParams p) {
+    FkShared* sh = reinterpret_cast<FkShared*>(fk_smem + p.so.shared);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
@@ -1623,26 +1641,12 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
 #endif
     FkCtx c;
-    c.p = &p; c.sh = sh; c.ring = fk_smem;
-    c.att = reinterpret_cast<float*>(fk_smem + so.att);
-    c.xs = reinterpret_cast<float*>(fk_smem + so.xs);
-    c.xp = reinterpret_cast<float*>(fk_smem + so.scratch);
-    c.land = reinterpret_cast<uint2*>(fk_smem + so.land);
-    c.land_n = 0; c.land_a = c.land;
+    c.p = &p;
+    c.land_n = 0; c.land_a = 0;
     c.rank = (unsigned)cta % FK_CLUSTER;
-    c.dbg_pg = p.pa + 8 * FK_NS_MAX * 2 * ATT_PSTRIDE;
-    c.nxt = reinterpret_cast<float*>(fk_smem + so.nxt);
-    c.res0 = reinterpret_cast<float*>(fk_smem + so.res0);
-    c.lh = reinterpret_cast<float*>(fk_smem + so.lh);
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
     c.seq = 0; c.stage_ctr = 0; c.aborted = false;
     c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
-    FkSampScratch ss;                              // x: own scratch; the arrays of the general path reuse the landing buffers
-    ss.x = reinterpret_cast<float*>(fk_smem + so.scratch);
-    ss.pr = reinterpret_cast<float*>(fk_smem + so.land);
-    ss.spr = ss.pr + so.maxV;
-    ss.idx = reinterpret_cast<unsigned short*>(ss.spr + so.maxV); ss.rank = ss.idx + so.maxV;
-
     const int H = p.talker.H, H4 = H >> 2;
     int pos = st0.pos, frame = st0.frame, done = st0.done, n_frames = st0.n_frames;
     const SamplingDev sp = *p.sp;
@@ -1653,7 +1657,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
     bool resumed = (p.mode == 0 && n_prefill == 0);   // first draw reads the plain logits / last_hidden of the previous launch
     if (resumed) {
         for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)
-            reinterpret_cast<float4*>(c.lh)[k4] = __ldcg(reinterpret_cast<const float4*>(p.last_hidden) + k4);
+            reinterpret_cast<float4*>(FK_LH(c))[k4] = __ldcg(reinterpret_cast<const float4*>(p.last_hidden) + k4);
         csync();
     }
 
@@ -1664,13 +1668,13 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             if (p.mode == 1 && mode1_done) break;
             const float* src = (p.mode == 1) ? p.next_in : p.prompt + (size_t)prefill_i * H;
             for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)
-                reinterpret_cast<float4*>(c.res0)[k4] = __ldcg(reinterpret_cast<const float4*>(src) + k4);
+                reinterpret_cast<float4*>(FK_RES0(c))[k4] = __ldcg(reinterpret_cast<const float4*>(src) + k4);
             csync();
             const bool head = (p.mode == 1) || (prefill_i == n_prefill - 1);
             ps = FkPass{false, pos, head};
         } else if (row1_next) {
             for (int k4 = tid; k4 < H4; k4 += FK_CTHREADS)                      // predictor position 1: codec_embed(code0) (= the running sum so far)
-                reinterpret_cast<float4*>(c.res0)[k4] = reinterpret_cast<const float4*>(c.nxt)[k4];
+                reinterpret_cast<float4*>(FK_RES0(c))[k4] = reinterpret_cast<const float4*>(FK_NXT(c))[k4];
             csync();
             ps = FkPass{true, 1, true};
             row1_next = false;
@@ -1687,10 +1691,10 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
             const uint2* lg = t0 ? (resumed ? nullptr : p.logits_ll) : p.clogits_ll;
             const int Vd = t0 ? p.vocab : p.cp_vocab;
             const uint2* land = lg ? mc_fetch(c, lg, Vd) : nullptr;
-            int tok = fk_sample(c, ss, lg, land, t0 ? p.logits : nullptr, c.seq, Vd, t0 ? 2048 : 0, t0 ? p.vocab : 0, t0 ? 2150 : -1,
+            int tok = fk_sample(c, lg, land, t0 ? p.logits : nullptr, c.seq, Vd, t0 ? 2048 : 0, t0 ? p.vocab : 0, t0 ? 2150 : -1,
                                 sp, (uint32_t)frame, cb, tr);
             resumed = false;
-            if (c.sh->aborted) { c.aborted = true; break; }
+            if (FK_SH(c)->aborted) { c.aborted = true; break; }
             if (p.forced && frame < st0.n_forced) tok = (int)p.forced[(size_t)frame * 16 + cb];
             fk_mark(c, 3);
             if (cb == 0 && tok == 2150) { done = 1; break; }                        // CODEC_EOS (:812)
@@ -1705,7 +1709,7 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                 const float4 e = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
                 float4 acc = e;                                                 // :824
                 if (cb != 0) {                                                  // :825-830
-                    acc = reinterpret_cast<float4*>(c.nxt)[k4];
+                    acc = reinterpret_cast<float4*>(FK_NXT(c))[k4];
                     acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
                 }
                 if (last_cb) {                                                  // :833-842
@@ -1713,11 +1717,11 @@ frame_kernel(const __grid_constant__ FkParams p, const FkSmemOffsets so) {
                                              : __ldg(reinterpret_cast<const float4*>(p.tts_pad) + k4);
                     acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
                 }
-                reinterpret_cast<float4*>(c.nxt)[k4] = acc;
+                reinterpret_cast<float4*>(FK_NXT(c))[k4] = acc;
                 if (cb == 0) {                                                  // rows [last_hidden, codec_embed(code0)] (:854-860): two single-row passes
-                    reinterpret_cast<float4*>(c.res0)[k4] = reinterpret_cast<const float4*>(c.lh)[k4];
+                    reinterpret_cast<float4*>(FK_RES0(c))[k4] = reinterpret_cast<const float4*>(FK_LH(c))[k4];
                 } else {
-                    reinterpret_cast<float4*>(c.res0)[k4] = last_cb ? acc : e;  // :867-868 / :845
+                    reinterpret_cast<float4*>(FK_RES0(c))[k4] = last_cb ? acc : e;  // :867-868 / :845
                 }
                 if (last_cb && cta == 0) reinterpret_cast<float4*>(p.next_in)[k4] = acc;
             }
