@@ -245,15 +245,17 @@ def main():
     def one_step(step_idx):
         dev_ms = gen_ms = voc_ms = 0.0
         nfr = 0
+        first = []
         for u in my_utts:                                                 # this rank's share (dispatch.assign: LPT, no collective)
             utt = dispatch.utterance_key(1234, u * 1000003 + step_idx)[1]   # Philox key from the GLOBAL utterance index: invariant to the GPU count
             audio, codes = eng.synthesize_tokens(ids_np, "en", 0.8, 50, 0.95, a.frames, 1234, utt,
                                                  audio_out=audio_pin, codes_out=codes_pin)
             st = eng.stats()
             dev_ms += st.last_total_ms; gen_ms += st.last_generate_ms; voc_ms += st.last_vocoder_ms
+            first.append(st.first_audio_ms)
             nfr += codes.shape[0]
             assert audio.shape[0] == codes.shape[0] * spf
-        return dev_ms, gen_ms, voc_ms, nfr
+        return dev_ms, gen_ms, voc_ms, nfr, first
 
     def fence():
         torch.cuda.synchronize()
@@ -271,9 +273,11 @@ def main():
     t0 = time.perf_counter()
     dev_ms = gen_ms = voc_ms = 0.0
     frames = 0
+    first_ms = []
     for i in range(a.steps):
-        d, g, v, n = one_step(i)
+        d, g, v, n, fa = one_step(i)
         dev_ms += d; gen_ms += g; voc_ms += v; frames += n
+        first_ms += fa
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     fence()
@@ -341,8 +345,10 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "first_audio_ms_p50": wall_max / a.steps / a.utterances * 1e3,
-        "first_audio_note": "no chunked vocoding yet: first audio = full utterance latency (as in the reference)",
+        "first_audio_ms_p50": statistics.median(first_ms) if first_ms else None,
+        "full_utterance_ms_p50": wall_max / a.steps / a.utterances * 1e3,
+        "first_audio_note": "rank 0, CUDA events: request start -> first 25 frames (2 s of PCM) vocoded on a second stream and copied into the "
+                            "caller's pinned buffer while the frame kernel generates the rest; the reference has no streaming (first audio = full utterance)",
         "breakdown_ms_per_step": {"frame_loop": gen_ms_max / a.steps, "vocoder": voc_ms_max / a.steps,
                                   "device_total": dev_ms_max / a.steps, "host_wall": wall_max / a.steps * 1e3},
     }

@@ -49,6 +49,8 @@ typedef struct lqt_stats {
     float    last_prefill_ms;
     int32_t  last_frames;
     float    last_total_ms;       /* lqt_synthesize_tokens: CUDA-event time prompt build -> last vocoder kernel */
+    float    first_audio_ms;      /* lqt_synthesize_tokens: CUDA-event time prompt build -> the first chunk of PCM (2 s) copied into
+                                     the caller's buffer (chunked vocoding on a second stream); = last_total_ms when chunking is off */
 } lqt_stats;
 
 /* Engine options (lqt_create_ex). kv_dtype: LQT_KV_BF16 = paged bf16 talker KV cache (default,

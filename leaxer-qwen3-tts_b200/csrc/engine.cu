@@ -122,6 +122,11 @@ struct lqt_engine {
     std::map<int, cudaGraphExec_t> graphs;
     int kernels_per_frame = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr;
+    // first-audio path: the first `first_chunk` frames are vocoded on a second stream while the frame kernel keeps generating
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_chunk = nullptr, ev_first = nullptr;
+    int first_chunk = 25;                     // frames (2 s of audio); 0 = off; $LQT_FIRST_CHUNK
+    float* chunk_audio_dev = nullptr; size_t chunk_audio_cap = 0;
     // persistent frame kernel (frame_kernel.cuh)
     int frame_impl = 0;                       // 0 = persistent kernel, 1 = v1 graph of kernels
     std::vector<void*> fk_allocs;             // regrouped weights, layer tables, activation buffers
@@ -688,7 +693,7 @@ int generate_core_graph(lqt_engine* h, int slot, int P, const lqt_sampling* sp, 
 
 // loops A+B on the device. prompt_dev / trailing_dev / tts_pad_dev / forced_dev already filled.
 int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sampling* sp, int n_forced,
-                  bool trace, int* n_frames_out) {
+                  bool trace, int* n_frames_out, int* chunk_out = nullptr, int (*chunk_hook)(lqt_engine*, int) = nullptr) {
     if (slot < 0 || slot >= h->n_slots) { h->err = "bad slot"; return 1; }
     if (P < 1 || sp->max_new_tokens < 0 || sp->max_new_tokens > h->max_frames_cap ||
         P + sp->max_new_tokens > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
@@ -699,9 +704,26 @@ int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sa
     *h->st_host = g;
     CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
     if (h->frame_impl == 0) {
-        // persistent frame kernel: prefill + all frames in one cooperative launch (frame_kernel.cuh)
+        // persistent frame kernel: prefill + all frames in one cluster launch (frame_kernel.cuh). With a first-audio request the
+        // launch is split: prefill + the first chunk of frames, then the rest (the kernel resumes from GenState and the plain
+        // logits/last_hidden copies), so that the chunk can be vocoded on a second stream while generation continues.
         CK(cudaEventRecord(h->ev0, h->stream));
-        if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;
+        const int chunk = (chunk_out && h->first_chunk > 0 && h->first_chunk < sp->max_new_tokens) ? h->first_chunk : 0;
+        if (chunk_out) *chunk_out = 0;
+        if (chunk) {
+            if (fk_launch(h, slot, 0, h->prompt_dev, P, chunk, trace)) return 1;
+            CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (fk_check_abort(h)) return 1;
+            if (!h->st_host->done && h->st_host->n_frames == chunk) {
+                CK(cudaEventRecord(h->ev_chunk, h->stream));
+                *chunk_out = chunk;
+                if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;   // resumes: pos != 0
+                if (chunk_hook && chunk_hook(h, chunk)) return 1;      // enqueues the chunk vocoder + copy on stream2 (after the launch above)
+            }
+        } else {
+            if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;
+        }
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1137,6 +1159,9 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         return 1;
     CK(cudaMallocHost((void**)&h->st_host, sizeof(GenState)));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev_t0));
+    CK(cudaEventCreate(&h->ev_chunk)); CK(cudaEventCreate(&h->ev_first));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    if (const char* e = getenv("LQT_FIRST_CHUNK")) h->first_chunk = std::max(0, atoi(e));
     if (h->frame_impl == 0 && fk_init(h)) {
         // shapes the persistent kernel does not cover yet (e.g. the 1.7B talker: > 64 rows per CTA): run loops A+B as the
         // CUDA graph of per-op sm_100a kernels instead (still device-only; there is no CPU path)
@@ -1214,6 +1239,10 @@ void lqt_destroy(lqt_engine* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
+    if (h->ev_first) cudaEventDestroy(h->ev_first);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
     h->f_text.release(); h->f_codec.release(); h->f_cpe.release(); h->f_talker.release();
     h->f_cp.release(); h->f_voc.release(); h->f_spk.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1506,6 +1535,29 @@ int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int
     return 0;
 }
 
+// First-audio path (the reference vocodes once at the end, src/tts_onnx.cpp:430): every vocoder op is causal
+// (causal convs, causal sliding-window attention, right-trimmed transposed convs), so decoding the first `chunk` frames alone
+// gives exactly the first chunk * 1920 samples of the full decode. Runs on stream2 while the frame kernel generates the rest.
+static float* g_chunk_audio_out = nullptr; static int64_t g_chunk_audio_cap = 0;
+static int first_chunk_hook(lqt_engine* h, int chunk) {
+    const size_t n = (size_t)chunk * h->sp.samples_per_frame;
+    if ((int64_t)n > g_chunk_audio_cap) return 0;
+    if (h->chunk_audio_cap < n) {
+        if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
+        CK(cudaMalloc((void**)&h->chunk_audio_dev, n * sizeof(float)));
+        h->chunk_audio_cap = n;
+    }
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_chunk, 0));
+    cudaStream_t main_stream = h->stream;
+    h->stream = h->stream2;                                   // the vocoder launches on h->stream
+    const int rc = run_vocoder(h, h->codes_dev, chunk, h->chunk_audio_dev);
+    h->stream = main_stream;
+    if (rc) return 1;
+    CK(cudaMemcpyAsync(g_chunk_audio_out, h->chunk_audio_dev, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
+    CK(cudaEventRecord(h->ev_first, h->stream2));             // first audio is in the caller's buffer
+    return 0;
+}
+
 int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
                           const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
                           int64_t* codes_out, int32_t* n_frames) {
@@ -1516,8 +1568,10 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     int P = 0, TL = 0;
     CK(cudaEventRecord(h->ev_t0, h->stream));
     if (build_prompt_device(h, token_ids, n_ids, lang_codec_id, speaker_embed, &P, &TL)) return 1;
-    int nf = 0;
-    if (generate_core(h, 0, P, TL, sp, 0, false, &nf)) return 1;
+    int nf = 0, chunk = 0;
+    h->stats.first_audio_ms = 0.f;
+    g_chunk_audio_out = audio_out; g_chunk_audio_cap = audio_capacity;
+    if (generate_core(h, 0, P, TL, sp, 0, false, &nf, audio_out ? &chunk : nullptr, first_chunk_hook)) return 1;
     if (n_frames) *n_frames = nf;
     h->stats.last_total_ms = 0.f;
     if (nf == 0) return 0;                                   // empty result, like src/tts_onnx.cpp:418
@@ -1525,6 +1579,7 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     const int64_t n = (int64_t)nf * h->sp.samples_per_frame;
     if (!audio_out || audio_capacity < n) { h->err = "audio_out too small"; return 1; }
     if (ensure_audio(h, nf)) return 1;
+    if (chunk) CK(cudaStreamWaitEvent(h->stream, h->ev_first, 0));      // the chunk pass shares the vocoder workspace
     CK(cudaEventRecord(h->ev0, h->stream));
     if (run_vocoder(h, h->codes_dev, nf, h->audio_dev)) return 1;
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -1532,6 +1587,8 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     CK(cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->stats.last_vocoder_ms, h->ev0, h->ev1);
     cudaEventElapsedTime(&h->stats.last_total_ms, h->ev_t0, h->ev1);
+    if (chunk) cudaEventElapsedTime(&h->stats.first_audio_ms, h->ev_t0, h->ev_first);
+    else h->stats.first_audio_ms = h->stats.last_total_ms;
     *n_samples = n;
     return 0;
 }

@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64),
                 ("last_generate_ms", C.c_float), ("last_vocoder_ms", C.c_float),
                 ("last_prefill_ms", C.c_float), ("last_frames", C.c_int32),
-                ("last_total_ms", C.c_float)]
+                ("last_total_ms", C.c_float), ("first_audio_ms", C.c_float)]
 
 
 _lib = None

@@ -321,3 +321,25 @@ def test_synthesize_tokens_matches_golden(request):
     # size-independent property: the vocoder is causal, so a prefix of the codes gives a prefix of the audio
     half = eng.vocoder_decode(g["codes"][:10])
     assert rel_l2(half, audio[: half.shape[0]]) < 1e-5
+
+
+def test_first_audio_chunk_is_exact_prefix(tiny_dir, monkeypatch):
+    """the first chunk (25 frames) is vocoded early on a second stream; every vocoder op is causal, so the result
+    must be bit-identical to a run without chunking, and the first-audio time must be shorter than the full latency."""
+    from leaxer_qwen3_tts_b200 import engine
+    ids = engine.wrap_text_ids([14990, 14615, 88225, 20339])
+    monkeypatch.setenv("LQT_FIRST_CHUNK", "0")
+    e0 = engine.Engine(tiny_dir, device=0)
+    a0, c0 = e0.synthesize_tokens(ids, "en", max_new_tokens=60, seed=5, utterance_id=1)
+    s0 = e0.stats()
+    assert abs(s0.first_audio_ms - s0.last_total_ms) < 1e-3
+    e0.close()
+    monkeypatch.setenv("LQT_FIRST_CHUNK", "25")
+    e1 = engine.Engine(tiny_dir, device=0)
+    a1, c1 = e1.synthesize_tokens(ids, "en", max_new_tokens=60, seed=5, utterance_id=1)
+    s1 = e1.stats()
+    assert np.array_equal(c0, c1) and np.array_equal(a0, a1)
+    assert 0 < s1.first_audio_ms < s1.last_total_ms
+    a2, c2 = e1.synthesize_tokens(ids, "en", max_new_tokens=20, seed=5, utterance_id=1)      # shorter than the chunk: no split
+    assert c2.shape[0] == 20 and np.array_equal(c2, c0[:20])
+    e1.close()
