@@ -133,6 +133,7 @@ struct lqt_engine {
     FkStack fk_talker{}, fk_cp{};
     std::vector<FkLayer> fk_tl, fk_cl;
     const bf16 *fk_t_head = nullptr, *fk_c_heads = nullptr, *fk_c_inproj = nullptr; long long fk_c_head_stride = 0;
+    float* fk_cp_kv = nullptr;                // per-CTA predictor KV copies of the frame kernel
     uint2* fk_arena = nullptr; size_t fk_arena_words = 0;     // all LL exchange buffers (zeroed at every launch)
     uint2 *fk_pa = nullptr, *fk_cxin = nullptr, *fk_logits_ll = nullptr, *fk_clogits_ll = nullptr;
     unsigned* fk_ctrl = nullptr;
@@ -977,6 +978,7 @@ int fk_init(lqt_engine* h) {
         h->fk_cp.x = a + o_cx; h->fk_cp.qkv = a + o_cq; h->fk_cp.x1 = a + o_cp; h->fk_cp.act = a + o_ca;
         h->fk_pa = a + o_pa; h->fk_cxin = a + o_ci; h->fk_logits_ll = a + o_lg; h->fk_clogits_ll = a + o_cl;
     }
+    if (fk_alloc(h, &h->fk_cp_kv, (size_t)h->fk_ncta * s.cp_layers * 2 * FK_CP_POS * ATT_D)) return 1;
     if (fk_alloc(h, &h->fk_ctrl, 64)) return 1;      // [1] abort flag, [32] grid arrival counter (own cache line)
     CK(cudaMallocHost((void**)&h->fk_ctrl_host, 64 * sizeof(unsigned)));
     return 0;
@@ -995,7 +997,7 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.eps = s.rms_eps;
     p.kv_pool = h->kv_pool; p.page_table = h->page_tables + (size_t)slot * h->max_pages; p.page_shift = KV_PAGE_SHIFT;
     p.page_stride = (long long)s.layers * 2 * s.kv_heads * KV_PAGE * ATT_D; p.kv_f32 = h->kv_f32 ? 1 : 0;
-    p.pa = h->fk_pa; p.cp_kv = h->cp_kv;
+    p.pa = h->fk_pa; p.cp_kv = h->fk_cp_kv;
     p.logits_ll = h->fk_logits_ll; p.clogits_ll = h->fk_clogits_ll;
     p.logits = h->logits; p.clogits = h->clogits; p.last_hidden = h->last_hidden;
     p.next_in = h->next_in;

@@ -90,7 +90,8 @@ struct FkParams {
     float eps;
     void* kv_pool; const int* page_table; int page_shift; long long page_stride; int kv_f32;
     uint2* pa;                 // talker attention partials, LL [n_kv][FK_NS_MAX][2][ATT_PSTRIDE]
-    float* cp_kv;              // [layer][k|v][n_kv][FK_CP_POS][128] fp32
+    float* cp_kv;              // PER-CTA copies [cta][layer][k|v][FK_CP_POS][128] fp32 of the predictor KV of the CTA's own kv group: every CTA
+                               // computes the new k/v row of its group anyway, so it keeps them itself -- no writer fence, no shared lines
     uint2 *logits_ll, *clogits_ll;
     float *logits, *clogits, *last_hidden, *next_in;   // plain copies: API outputs, resume across launches, mode-1 input
     const bf16_t *codec_embed, *cp_embed;
@@ -809,11 +810,11 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
 LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int p0, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.cp;
-    const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv;
+    const int n_kv = S.kv_heads, g = c.cta % n_kv;
     const int q_dim = S.heads * ATT_D, kv_dim = n_kv * ATT_D, qkv_dim = q_dim + 2 * kv_dim;
     float* q_s = FK_ATT(c) + FA_Q; float* kn = FK_ATT(c) + FA_KN; float* vn = FK_ATT(c) + FA_VN; float* sc = FK_ATT(c) + FA_SC;
-    float* kc = p.cp_kv + ((size_t)(layer * 2 + 0) * n_kv + g) * FK_CP_POS * ATT_D;
-    float* vc = p.cp_kv + ((size_t)(layer * 2 + 1) * n_kv + g) * FK_CP_POS * ATT_D;
+    float* kc = p.cp_kv + (((size_t)c.cta * S.n_layers + layer) * 2 + 0) * FK_CP_POS * ATT_D;     // this CTA's private copy
+    float* vc = p.cp_kv + (((size_t)c.cta * S.n_layers + layer) * 2 + 1) * FK_CP_POS * ATT_D;
     // prefetch the cached V column of this thread and the cached K rows of this warp (positions < p0)
     // while q/k/v of the new rows are polled
     const int r_t = c.tid >> 7, d_t = c.tid & 127;
@@ -838,12 +839,12 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
             float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + q_dim + (size_t)g * ATT_D + c.lane * 4, want);
             v = head_norm_rope(v, L.knorm, p.eps, S.cos + (size_t)pos * (ATT_D / 2), S.sin + (size_t)pos * (ATT_D / 2), c.lane);
             reinterpret_cast<float4*>(kn + m * ATT_D)[c.lane] = v;
-            if (s == 0) { reinterpret_cast<float4*>(kc + (size_t)pos * ATT_D)[c.lane] = v; __threadfence(); }
+            reinterpret_cast<float4*>(kc + (size_t)pos * ATT_D)[c.lane] = v;      // read back only by this CTA, after CTA barriers
         } else {
             const int m = job - 3 * M, pos = p0 + m;
             const float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + q_dim + kv_dim + (size_t)g * ATT_D + c.lane * 4, want);
             reinterpret_cast<float4*>(vn + m * ATT_D)[c.lane] = v;
-            if (s == 0) { reinterpret_cast<float4*>(vc + (size_t)pos * ATT_D)[c.lane] = v; __threadfence(); }
+            reinterpret_cast<float4*>(vc + (size_t)pos * ATT_D)[c.lane] = v;
         }
     }
     csync();
