@@ -474,8 +474,10 @@ LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
 // three compares instead of an integer division (~150 cycles, and several per batch)
 LQT_DEVINL int stage_of(int r, int rps) { return (r >= rps ? 1 : 0) + (r >= 2 * rps ? 1 : 0) + (r >= 3 * rps ? 1 : 0); }
 
-template <int NST, int RG>
-LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
+// RG (1 or 2 consecutive rows per slot pair) is a run-time argument: ONE copy of this routine serves every matrix-vector
+// phase, so its ~18 KB of code stay warm in the instruction cache across the phases of a layer.
+template <int NST>
+LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int RG) {
     const int K = d.K, rowbytes = K * 2;
     const int nch = (K + 1023) >> 10;
     const int nst = stage_of(d.nrows - 1, d.rps) + 1;
@@ -500,7 +502,7 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp) {
     for (int sb = 0; sb < 8; sb += 4) {
         int rr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int s = sb + j; rr[j] = ((s / RG) * 8 + c.warp) * RG + (s % RG); }
+        for (int j = 0; j < 4; ++j) { const int s = sb + j; rr[j] = (RG == 2) ? ((s >> 1) * 8 + c.warp) * 2 + (s & 1) : s * 8 + c.warp; }
         if (rr[0] >= d.nrows) break;              // warp-uniform; rows grow with the slot
         int last = rr[0];
 #pragma unroll
@@ -1121,15 +1123,15 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             const float rs = nw ? ss_rstd(c, H, p.eps) : 1.f;
             const int slot = c.lane;
             const bool lead = c.lane < 8;
+            const float vraw = gemv_rpw<NST>(c, d, xp, kind == FKT_D ? 2 : 1);      // the only call site
+            fk_mark(c, 5);
             if (kind == FKT_D) {
-                const float v = gemv_rpw<NST, 2>(c, d, xp);
-                fk_mark(c, 5);
+                const float v = vraw;
                 const float up = __shfl_down_sync(0xffffffffu, v, 1);          // slot s + 1 = the up row of the same pair
                 const int q = (slot >> 1) * 8 + c.warp;
                 if (lead && (slot & 1) == 0 && 2 * q < d.nrows) st_ll(S.act + (d.row0 >> 1) + q, silu_f(v * rs) * (up * rs), c.seq);
             } else {
-                const float v = gemv_rpw<NST, 1>(c, d, xp) * rs;
-                fk_mark(c, 5);
+                const float v = vraw * rs;
                 const int r = slot * 8 + c.warp, n = d.row0 + r;
                 if (lead && r < d.nrows) {
                     if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
@@ -1238,18 +1240,24 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
     }
     csync();
     if (c.warp == 0) {
-        // Arrays are read eight entries at a time (two 16-byte loads issued before the dependent chain); entries beyond the
-        // live count are kept at neutral values (-inf / 0), so the serial sums see exactly the reference's operands in order.
-        const int e0 = c.lane, e1 = c.lane + 32;
+        // One warp, lane l owns candidates l and l + 32 (candidates are in index order). Everything stays in candidate order:
+        // a candidate that drops out (below the k-th value, beyond the top-p cut) becomes an exact 0.0f, which is neutral in
+        // every serial sum, so the sums see the reference's operands in the reference's order without any compaction.
+        // Arrays are padded to 64 entries and read eight at a time (two 16-byte loads ahead of each dependent chain); no
+        // per-entry bounds checks anywhere. The lane index goes through an opaque asm: ptxas would otherwise re-read
+        // SR_TID.X (a long-latency S2R) in front of every comparison of this single-warp section.
+        int lane;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+        const int e0 = lane, e1 = lane + 32;
+        const int n8 = (n_c + 7) & ~7;
         const float x0 = (e0 < n_c) ? s.pr[e0] : -INFINITY, x1 = (e1 < n_c) ? s.pr[e1] : -INFINITY;
-        const int i0c = (e0 < n_c) ? (int)s.idx[e0] : 0, i1c = (e1 < n_c) ? (int)s.idx[e1] : 0;
         __syncwarp();
-        if (e0 >= n_c) s.pr[e0] = -INFINITY;                   // pad to 64 so that the unrolled loops need no bounds
+        if (e0 >= n_c) s.pr[e0] = -INFINITY;
         if (e1 >= n_c) s.pr[e1] = -INFINITY;
         __syncwarp();
         int gt0 = 0, gt1 = 0;
 #pragma unroll 1
-        for (int j = 0; j < n_c; j += 8) {
+        for (int j = 0; j < n8; j += 8) {
             const float4 u = *reinterpret_cast<const float4*>(s.pr + j), w = *reinterpret_cast<const float4*>(s.pr + j + 4);
             const float xv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -1257,43 +1265,36 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
         }
         const bool sv0 = e0 < n_c && gt0 < k, sv1 = e1 < n_c && gt1 < k;      // x >= (k-th largest)  <=>  fewer than k values above it
         const unsigned b0 = __ballot_sync(0xffffffffu, sv0), b1 = __ballot_sync(0xffffffffu, sv1);
-        const unsigned lt = (1u << c.lane) - 1u;
-        const int p0 = __popc(b0 & lt), p1 = __popc(b0) + __popc(b1 & lt), ns = __popc(b0) + __popc(b1);
-        const int q0 = c.lane, q1 = c.lane + 32;
-        s.spr[q0] = 0.f; s.spr[q1] = 0.f;                                       // neutral padding up to 64 entries
-        __syncwarp();
-        if (sv0) { s.spr[p0] = (float)exp((double)(x0 - mx)); s.rank[p0] = (unsigned short)i0c; }
-        if (sv1) { s.spr[p1] = (float)exp((double)(x1 - mx)); s.rank[p1] = (unsigned short)i1c; }
+        const int ns = __popc(b0) + __popc(b1);
+        float pr0 = sv0 ? (float)exp((double)(x0 - mx)) : 0.f, pr1 = sv1 ? (float)exp((double)(x1 - mx)) : 0.f;
+        s.spr[e0] = pr0; s.spr[e1] = pr1;
         __syncwarp();
         float sum = 0.f;
 #pragma unroll 1
-        for (int i = 0; i < ns; i += 8) {                                        // serial, index order (every lane redundantly)
+        for (int i = 0; i < n8; i += 8) {                                        // serial, index order (every lane redundantly)
             const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
             sum += u.x; sum += u.y; sum += u.z; sum += u.w; sum += w.x; sum += w.y; sum += w.z; sum += w.w;
         }
-        float pr0 = (q0 < ns) ? s.spr[q0] / sum : 0.f, pr1 = (q1 < ns) ? s.spr[q1] / sum : 0.f;
+        pr0 = pr0 / sum; pr1 = pr1 / sum;                                        // (dropped candidates stay 0)
         __syncwarp();
-        s.spr[q0] = pr0; s.spr[q1] = pr1;
+        s.spr[e0] = pr0; s.spr[e1] = pr1;
         __syncwarp();
         if (sp.top_p < 1.0f) {
-            int r0 = 0, r1 = 0;
+            int r0 = 0, r1 = 0;                                                  // position in descending order (ties: index order)
 #pragma unroll 1
-            for (int j = 0; j < ns; j += 8) {
+            for (int j = 0; j < n8; j += 8) {
                 const float4 u = *reinterpret_cast<const float4*>(s.spr + j), w = *reinterpret_cast<const float4*>(s.spr + j + 4);
                 const float pv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int jj = j + q;
-                    if (jj < ns) {
-                        r0 += (pv[q] > pr0 || (pv[q] == pr0 && jj < q0)) ? 1 : 0;
-                        r1 += (pv[q] > pr1 || (pv[q] == pr1 && jj < q1)) ? 1 : 0;
-                    }
+                    r0 += (pv[q] > pr0 || (pv[q] == pr0 && j + q < e0)) ? 1 : 0;
+                    r1 += (pv[q] > pr1 || (pv[q] == pr1 && j + q < e1)) ? 1 : 0;
                 }
             }
-            s.pr[q0] = 0.f; s.pr[q1] = 0.f;
+            s.pr[e0] = 0.f; s.pr[e1] = 0.f;
             __syncwarp();
-            if (q0 < ns) s.pr[r0] = pr0;                       // probabilities in descending order (ties: index order)
-            if (q1 < ns) s.pr[r1] = pr1;
+            if (sv0) s.pr[r0] = pr0;                                             // survivors only: their positions are 0..ns-1
+            if (sv1) s.pr[r1] = pr1;
             __syncwarp();
             int cut = ns;
             float cs = 0.f;
@@ -1303,45 +1304,46 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
                 const float pv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    cs += pv[q];
-                    if (cut == ns && r + q < ns && cs > sp.top_p) cut = r + q + 1;
+                    cs += pv[q];                                                 // (zeros beyond ns never move cs across the threshold)
+                    if (cut == ns && cs > sp.top_p) cut = min(ns, r + q + 1);
                 }
             }
             if (r0 >= cut) pr0 = 0.f;
             if (r1 >= cut) pr1 = 0.f;
-            s.spr[q0] = pr0; s.spr[q1] = pr1;
+            s.spr[e0] = pr0; s.spr[e1] = pr1;
             __syncwarp();
             float s2 = 0.f;
 #pragma unroll 1
-            for (int i = 0; i < ns; i += 8) {
+            for (int i = 0; i < n8; i += 8) {
                 const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
-                s2 += u.x; s2 += u.y; s2 += u.z; s2 += u.w; s2 += w.x; s2 += w.y; s2 += w.z; s2 += w.w;   // zeros are neutral
+                s2 += u.x; s2 += u.y; s2 += u.z; s2 += u.w; s2 += w.x; s2 += w.y; s2 += w.z; s2 += w.w;
             }
             if (s2 > 0.f) { pr0 = pr0 / s2; pr1 = pr1 / s2; }
             __syncwarp();
-            s.spr[q0] = pr0; s.spr[q1] = pr1;
+            s.spr[e0] = pr0; s.spr[e1] = pr1;
             __syncwarp();
         }
         uint32_t r4[4];
         philox4x32_10(frame, (uint32_t)codebook, 0u, 0u, sp.seed, sp.utt, r4);
         const float u01 = (float)(r4[0] >> 8) * 5.9604644775390625e-08f;
-        float cdf = 0.f; int last = (ns > 0) ? (int)s.rank[0] : 0; bool hit = false;
+        const int first = b0 ? (__ffs(b0) - 1) : (b1 ? 32 + __ffs(b1) - 1 : 0);
+        float cdf = 0.f; int last = (int)s.idx[first]; bool hit = false;
 #pragma unroll 1
-        for (int i = 0; i < ns && !hit; i += 8) {
+        for (int i = 0; i < n8 && !hit; i += 8) {
             const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
             const float pv[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
-            const uint4 ri = *reinterpret_cast<const uint4*>(s.rank + i);      // 8 ushort indices
+            const uint4 ri = *reinterpret_cast<const uint4*>(s.idx + i);       // 8 ushort token indices
             const unsigned rw[4] = {ri.x, ri.y, ri.z, ri.w};
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                if (!hit && pv[q] > 0.f) {                     // (entries beyond ns are zero)
+                if (!hit && pv[q] > 0.f) {
                     cdf += pv[q];
                     last = (int)((rw[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
                     if (cdf > u01) hit = true;
                 }
             }
         }
-        if (c.lane == 0) sh->tok = last;
+        if (lane == 0) sh->tok = last;
     }
     csync();
     const int tok = sh->tok;
@@ -1360,11 +1362,9 @@ LQT_DEVINL int fk_sample(FkCtx& c, const uint2* ll, const uint2* land, const flo
     const int per = (((V + FK_CTHREADS - 1) / FK_CTHREADS) + 3) & ~3;
     const int i0 = min(V, c.tid * per), i1 = min(V, i0 + per);
     float bv = -INFINITY; int bi = 0x7fffffff;
-    constexpr int FK_SAMP_Q = 4;                               // float4 groups per thread (V <= 4096)
-#pragma unroll
-    for (int u4 = 0; u4 < FK_SAMP_Q; ++u4) {
-        const int i = i0 + 4 * u4;
-        if (i < i1) {
+#pragma unroll 1
+    for (int i = i0; i < i1; i += 4) {                         // rolled: this code runs once per draw, cold in the instruction cache
+        {
             float4 q;
             if (ll) {                                          // landed (value, sequence) words, validated like every other input
                 uint4 a = *reinterpret_cast<const uint4*>(land + i), b = *reinterpret_cast<const uint4*>(land + i + 2);
