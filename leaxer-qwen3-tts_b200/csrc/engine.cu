@@ -936,7 +936,7 @@ int fk_init(lqt_engine* h) {
         }
     }
     if (s.kv_heads > FK_NGRP_MAX || s.cp_kv_heads > FK_NGRP_MAX || s.kv_heads != s.cp_kv_heads) { h->err = "frame kernel: kv head count"; return 1; }
-    if (s.cp_steps + 2 > FK_CP_POS) { h->err = "frame kernel: cp_steps"; return 1; }
+    if (s.cp_steps + 1 > FK_CP_POS / 2) { h->err = "frame kernel: cp_steps"; return 1; }   // predictor positions 0..cp_steps
     if (h->fk_ncta < s.kv_heads) { h->err = "frame kernel: too few SMs"; return 1; }
     if (s.layers > FK_MAX_TLAYERS || s.cp_layers > FK_MAX_CLAYERS) { h->err = "frame kernel: too many layers"; return 1; }
     if (fk_build_stack(h, h->tl, s.hidden, s.heads, s.kv_heads, s.inter, h->t_cos, h->t_sin, h->t_norm, &h->fk_talker, &h->fk_tl)) return 1;

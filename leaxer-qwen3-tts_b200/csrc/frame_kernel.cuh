@@ -808,17 +808,19 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
     csync();
 }
 
-// code predictor: full attention of kv group g for the M new positions p0.., result -> FK_XS(c)[m][0..256)
-LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int p0, unsigned want) {
+// code predictor: full attention of kv group g for the ONE new position p0 (< FK_CP_POS / 2), result -> FK_XS(c)[0..256).
+// Written for a small instruction footprint (it runs in every predictor layer): one polling / norm / rope path shared by
+// q, k and v, two-value butterfly reductions.
+LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.cp;
     const int n_kv = S.kv_heads, g = c.cta % n_kv;
-    const int q_dim = S.heads * ATT_D, kv_dim = n_kv * ATT_D, qkv_dim = q_dim + 2 * kv_dim;
+    const int q_dim = S.heads * ATT_D, kv_dim = n_kv * ATT_D;
     float* q_s = FK_ATT(c) + FA_Q; float* kn = FK_ATT(c) + FA_KN; float* vn = FK_ATT(c) + FA_VN; float* sc = FK_ATT(c) + FA_SC;
     float* kc = p.cp_kv + (((size_t)c.cta * S.n_layers + layer) * 2 + 0) * FK_CP_POS * ATT_D;     // this CTA's private copy
-    float* vc = p.cp_kv + (((size_t)c.cta * S.n_layers + layer) * 2 + 1) * FK_CP_POS * ATT_D;
+    float* vc = kc + (size_t)FK_CP_POS * ATT_D;
     // prefetch the cached V column of this thread and the cached K rows of this warp (positions < p0)
-    // while q/k/v of the new rows are polled
+    // while q/k/v of the new row are polled
     const int r_t = c.tid >> 7, d_t = c.tid & 127;
     float vcol[FK_CP_POS / 2];
 #pragma unroll
@@ -829,75 +831,56 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int M, int 
         const int j = c.warp + u * FK_CWARPS;
         kpre[u] = (j < p0) ? __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // warps 0..2M-1: q heads ; 2M..3M-1: k ; 3M..4M-1: v
-    for (int job = c.warp; job < 4 * M; job += FK_CWARPS) {
-        if (job < 2 * M) {
-            const int m = job >> 1, r = job & 1, pos = p0 + m;
-            float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + (size_t)(g * 2 + r) * ATT_D + c.lane * 4, want);
-            v = head_norm_rope(v, L.qnorm, p.eps, S.cos + (size_t)pos * (ATT_D / 2), S.sin + (size_t)pos * (ATT_D / 2), c.lane);
-            reinterpret_cast<float4*>(q_s + (m * 2 + r) * ATT_D)[c.lane] = v;
-        } else if (job < 3 * M) {
-            const int m = job - 2 * M, pos = p0 + m;
-            float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + q_dim + (size_t)g * ATT_D + c.lane * 4, want);
-            v = head_norm_rope(v, L.knorm, p.eps, S.cos + (size_t)pos * (ATT_D / 2), S.sin + (size_t)pos * (ATT_D / 2), c.lane);
-            reinterpret_cast<float4*>(kn + m * ATT_D)[c.lane] = v;
-            reinterpret_cast<float4*>(kc + (size_t)pos * ATT_D)[c.lane] = v;      // read back only by this CTA, after CTA barriers
-        } else {
-            const int m = job - 3 * M, pos = p0 + m;
-            const float4 v = ll_poll4(c, S.qkv + (size_t)m * qkv_dim + q_dim + kv_dim + (size_t)g * ATT_D + c.lane * 4, want);
-            reinterpret_cast<float4*>(vn + m * ATT_D)[c.lane] = v;
-            reinterpret_cast<float4*>(vc + (size_t)pos * ATT_D)[c.lane] = v;
-        }
+    if (c.warp < 4) {                                // warps 0, 1: the two q heads of the group; 2: k; 3: v
+        const int job = c.warp;
+        const int off = (job < 2) ? (g * 2 + job) * ATT_D : (job == 2 ? q_dim : q_dim + kv_dim) + g * ATT_D;
+        float4 v = ll_poll4(c, S.qkv + off + c.lane * 4, want);
+        if (job < 3) v = head_norm_rope(v, job == 2 ? L.knorm : L.qnorm, p.eps, S.cos + (size_t)p0 * (ATT_D / 2), S.sin + (size_t)p0 * (ATT_D / 2), c.lane);
+        float* dst = (job < 2) ? q_s + job * ATT_D : (job == 2 ? kn : vn);
+        reinterpret_cast<float4*>(dst)[c.lane] = v;
+        if (job >= 2) reinterpret_cast<float4*>((job == 2 ? kc : vc) + (size_t)p0 * ATT_D)[c.lane] = v;   // read back only by this CTA, after CTA barriers
     }
     csync();
     const float scale = 1.0f / sqrtf((float)ATT_D);
-    // scores: key j against both heads of every row m that may see it (warp handles j = warp, warp + 8, warp + 16)
-    const int n_last = p0 + M;                       // positions visible to the last row
+    // scores: key j against both heads (warp handles j = warp, warp + 8)
+    {
+        const float4 q0 = reinterpret_cast<const float4*>(q_s)[c.lane], q1 = reinterpret_cast<const float4*>(q_s + ATT_D)[c.lane];
+        const float4 knew = reinterpret_cast<const float4*>(kn)[c.lane];
+        const bool hi = (c.lane & 16) != 0;
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-        const int j = c.warp + u * FK_CWARPS;
-        if (j < n_last) {
-            float4 k4;
-            if (j >= p0) k4 = reinterpret_cast<const float4*>(kn + (j - p0) * ATT_D)[c.lane];
-            else if (u < 2) k4 = kpre[u < 2 ? u : 0];
-            else k4 = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + c.lane);
-            float d[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {            // i = m*2 + r
-                const float4 q = reinterpret_cast<const float4*>(q_s + i * ATT_D)[c.lane];
-                d[i] = k4.x * q.x + k4.y * q.y + k4.z * q.z + k4.w * q.w;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
-            if (c.lane < 2 * M) {
-                const int m = c.lane >> 1;
-                float v = d[0];
-                if (c.lane == 1) v = d[1]; else if (c.lane == 2) v = d[2]; else if (c.lane == 3) v = d[3];
-                if (j <= p0 + m) sc[c.lane * FK_CP_POS + j] = v * scale;
+        for (int u = 0; u < 2; ++u) {
+            const int j = c.warp + u * FK_CWARPS;
+            if (j <= p0) {
+                const float4 k4 = (j == p0) ? knew : kpre[u];
+                const float d0 = k4.x * q0.x + k4.y * q0.y + k4.z * q0.z + k4.w * q0.w;
+                const float d1 = k4.x * q1.x + k4.y * q1.y + k4.z * q1.z + k4.w * q1.w;
+                // both sums with five shuffles: the halves of the warp swap one value each, then reduce within the half
+                float t = (hi ? d1 : d0) + __shfl_xor_sync(0xffffffffu, hi ? d0 : d1, 16);
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                if ((c.lane & 15) == 0) sc[(c.lane >> 4) * FK_CP_POS + j] = t * scale;
             }
         }
     }
     csync();
-    if (c.warp < 2 * M) {                            // softmax of row (m, r) over j <= p0 + m
-        const int m = c.warp >> 1, np = p0 + m + 1;
+    if (c.warp < 2) {                                // softmax of head `warp` over j <= p0
         float* row = sc + c.warp * FK_CP_POS;
-        const float v = (c.lane < np) ? row[c.lane] : -INFINITY;
+        const float v = (c.lane <= p0) ? row[c.lane] : -INFINITY;
         const float mx = warp_max(v);
-        const float e = (c.lane < np) ? expf(v - mx) : 0.f;
+        const float e = (c.lane <= p0) ? expf(v - mx) : 0.f;
         const float sum = warp_sum(e);
-        if (c.lane < np) row[c.lane] = e / sum;
+        if (c.lane <= p0) row[c.lane] = e / sum;
     }
     csync();
-    for (int m = 0; m < M; ++m) {
-        const int np = p0 + m + 1;
-        const float* row = sc + (m * 2 + r_t) * FK_CP_POS;
+    {
+        const float* row = sc + r_t * FK_CP_POS;
         float o = 0.f;
 #pragma unroll
         for (int j = 0; j < FK_CP_POS / 2; ++j) if (j < p0) o = fmaf(row[j], vcol[j], o);
-        for (int j = p0; j < np; ++j) o = fmaf(row[j], vn[(j - p0) * ATT_D + d_t], o);
-        FK_XS(c)[m * FK_XS_STRIDE + c.tid] = o;
+        o = fmaf(row[p0], vn[d_t], o);
+        FK_XS(c)[c.tid] = o;
     }
     csync();
 }
@@ -1038,7 +1021,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             continue;
         }
         if (kind == FKT_C) {
-            if (is_cp) cp_attn_local(c, L, l, 1, ps.pos0, want);
+            if (is_cp) cp_attn_local(c, L, l, ps.pos0, want);
             else       talker_attn_combine(c, ps.pos0, want);
             fk_mark(c, 3);
             if (FK_SH(c)->aborted) { c.aborted = true; break; }
