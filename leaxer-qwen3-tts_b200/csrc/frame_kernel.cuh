@@ -205,6 +205,7 @@ struct FkShared {
     uint32_t sel_prefix; int sel_k;
     int tok; float fsum;
     float ssred[2][FK_CWARPS];        // [phase parity][warp]: partial sums of squares (RMSNorm)
+    alignas(16) float part[FK_CWARPS][8][32];   // matrix-vector per-lane partial sums [warp][slot][lane]
     float x1own[FK_X1OWN];            // post-attention stream at the rows of this CTA's down-projection slice (its residual)
     uint64_t land_bar[2];             // multicast landing buffers: complete_tx from all CTAs of the cluster
     uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
@@ -474,14 +475,21 @@ LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
 // three compares instead of an integer division (~150 cycles, and several per batch)
 LQT_DEVINL int stage_of(int r, int rps) { return (r >= rps ? 1 : 0) + (r >= 2 * rps ? 1 : 0) + (r >= 3 * rps ? 1 : 0); }
 
-// RG (1 or 2 consecutive rows per slot pair) is a run-time argument: ONE copy of this routine serves every matrix-vector
-// phase, so its ~18 KB of code stay warm in the instruction cache across the phases of a layer.
+// Matrix-vector product of this CTA's weight slice (rows in the ring, row-major bf16) with the plain fp32 vector xp.
+// Slot s of warp w is row s * 8 + w (RG == 1) or row ((s >> 1) * 8 + w) * 2 + (s & 1) (RG == 2: gate/up pairs); a warp owns at
+// most eight slots. The lanes split K (16-byte shared loads, conflict-free), TWO rows at a time with two accumulator pairs
+// each: four independent FFMA2 chains, eight loads in flight, and at most one padding row per warp (the kernel is bound by
+// instruction issue on its 8 consumer warps, so rows are not padded to a wider batch). Per-lane partial sums go to shared
+// memory; one pass at the end reduces all slots of the warp (lane 4s + q sums a quarter of slot s, two shuffles finish).
+// On return lane s (< 8) holds the sum of slot s. RG is a run-time argument: ONE copy of this routine serves every
+// matrix-vector phase, so its code stays warm in the instruction cache across the phases of a layer.
 template <int NST>
 LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int RG) {
     const int K = d.K, rowbytes = K * 2;
     const int nch = (K + 1023) >> 10;
     const int nst = stage_of(d.nrows - 1, d.rps) + 1;
     const uint32_t ring_s = smem_u32(FK_RING(c)), xp_s = smem_u32(xp);      // shared-space addresses, converted once
+    float* part = &FK_SH(c)->part[c.warp][0][0];
     unsigned long long xk[16];                    // this lane's 32 input values of the current 1024-column chunk, as f32x2 pairs
     auto load_chunk = [&](int ch) {
 #pragma unroll
@@ -494,20 +502,15 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int 
         }
     };
     if (nch == 1) load_chunk(0);
-    float mine = 0.f;                             // lane s keeps the sum of slot s
     int cur = 0;                                  // first ring stage of this phase this warp has not released yet
     int seen = 0;                                 // stages [cur, seen) have been observed full
-    // four slots (rows) at a time: 16 independent shared loads and 4 FMA chains in flight per warp
 #pragma unroll 1
-    for (int sb = 0; sb < 8; sb += 4) {
-        int rr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const int s = sb + j; rr[j] = (RG == 2) ? ((s >> 1) * 8 + c.warp) * 2 + (s & 1) : s * 8 + c.warp; }
-        if (rr[0] >= d.nrows) break;              // warp-uniform; rows grow with the slot
-        int last = rr[0];
-#pragma unroll
-        for (int j = 1; j < 4; ++j) if (rr[j] < d.nrows) last = rr[j];
-        const int g0 = stage_of(rr[0], d.rps), g1 = stage_of(last, d.rps);
+    for (int sb = 0; sb < 8; sb += 2) {
+        const int ra = (RG == 2) ? ((sb >> 1) * 8 + c.warp) * 2 : sb * 8 + c.warp;
+        if (ra >= d.nrows) break;                 // warp-uniform; rows grow with the slot
+        int rb = (RG == 2) ? ra + 1 : ra + 8;
+        if (rb >= d.nrows) rb = ra;               // padding row: recomputes row a, result never read
+        const int g0 = stage_of(ra, d.rps), g1 = stage_of(rb, d.rps);
         while (cur < g0) {                        // stages that hold no (further) row of this warp
             if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
             __syncwarp();
@@ -515,40 +518,35 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int 
             ++cur;
         }
         while (seen <= g1) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
-        uint32_t wr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = (rr[j] < d.nrows) ? rr[j] : rr[0];          // rows beyond the slice: recompute row 0 (dropped)
-            const int g = stage_of(r, d.rps);
-            wr[j] = ring_s + ((c.stage_ctr + g) % (unsigned)NST) * FK_STAGE_BYTES + (unsigned)(r - g * d.rps) * (unsigned)rowbytes + c.lane * 16;
-        }
-        unsigned long long a2[4] = {0ull, 0ull, 0ull, 0ull};         // (even-column sum, odd-column sum) per row
+        const uint32_t wa = ring_s + ((c.stage_ctr + g0) % (unsigned)NST) * FK_STAGE_BYTES + (unsigned)(ra - g0 * d.rps) * (unsigned)rowbytes + c.lane * 16;
+        const uint32_t wb = ring_s + ((c.stage_ctr + g1) % (unsigned)NST) * FK_STAGE_BYTES + (unsigned)(rb - g1 * d.rps) * (unsigned)rowbytes + c.lane * 16;
+        unsigned long long a2[2][2] = {{0ull, 0ull}, {0ull, 0ull}};      // [row][accumulator]: (even-column sum, odd-column sum)
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
             if (nch > 1) load_chunk(ch);
-            uint4 w[4][4];
+            uint4 w[2][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) w[j][i] = (ch * 1024 + i * 256 < K) ? lds128_s(wr[j] + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
-            // the four rows' chains are interleaved instruction by instruction (row index innermost): consecutive FMAs are
-            // independent, so the 4-cycle FMA latency is covered by the other three rows
+            for (int i = 0; i < 4; ++i) {
+                const bool in = ch * 1024 + i * 256 < K;
+                w[0][i] = in ? lds128_s(wa + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
+                w[1][i] = in ? lds128_s(wb + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].x), xk[i * 4 + 0], a2[j]);
+                for (int j = 0; j < 2; ++j) {
+                    a2[j][0] = ffma2(bf16x2_to_f32x2(w[j][i].x), xk[i * 4 + 0], a2[j][0]);
+                    a2[j][1] = ffma2(bf16x2_to_f32x2(w[j][i].y), xk[i * 4 + 1], a2[j][1]);
+                }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].y), xk[i * 4 + 1], a2[j]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].z), xk[i * 4 + 2], a2[j]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) a2[j] = ffma2(bf16x2_to_f32x2(w[j][i].w), xk[i * 4 + 3], a2[j]);
+                for (int j = 0; j < 2; ++j) {
+                    a2[j][0] = ffma2(bf16x2_to_f32x2(w[j][i].z), xk[i * 4 + 2], a2[j][0]);
+                    a2[j][1] = ffma2(bf16x2_to_f32x2(w[j][i].w), xk[i * 4 + 3], a2[j][1]);
+                }
             }
         }
-        const float a[4] = {sum2(a2[0]), sum2(a2[1]), sum2(a2[2]), sum2(a2[3])};
-        const float t = reduce4(a, c.lane);                          // lanes 8j .. 8j+7 hold the sum of slot sb + j
-        const float v = __shfl_sync(0xffffffffu, t, ((c.lane - sb) & 3) * 8);
-        if (c.lane >= sb && c.lane < sb + 4) mine = v;
+        part[sb * 32 + c.lane] = sum2(a2[0][0]) + sum2(a2[0][1]);
+        part[(sb + 1) * 32 + c.lane] = sum2(a2[1][0]) + sum2(a2[1][1]);
     }
     while (cur < nst) {
         if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
@@ -557,6 +555,14 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int 
         ++cur;
     }
     c.stage_ctr += nst;
+    __syncwarp();
+    // lane 4s + q: a quarter of slot s (slots this warp did not compute hold stale values; their lanes are never read)
+    const float4 u = *reinterpret_cast<const float4*>(part + c.lane * 8), v = *reinterpret_cast<const float4*>(part + c.lane * 8 + 4);
+    float t = ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    const float mine = __shfl_sync(0xffffffffu, t, (c.lane & 7) * 4);
+    __syncwarp();                                 // everyone has read the partials before the next call overwrites them
     return mine;
 }
 
