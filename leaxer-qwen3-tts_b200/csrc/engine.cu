@@ -805,27 +805,52 @@ bool load_vocoder_weights(lqt_engine* h) {
 // ------------------------------------------------------------------------------------------------
 // persistent frame kernel: one-time weight regrouping, tables, launch
 // ------------------------------------------------------------------------------------------------
-// Per-CTA weight images: CTA c's rows of the matrix, row-major [rmax][K] bf16 (see frame_kernel.cuh FkLayer).
+// Per-CTA weight images (see frame_kernel.cuh): CTA c's rows of the matrix.
+//  mode 2 (O-projection, sliced by kv group): row-major [rows][K] bf16.
+//  mode 0 (flat rows) / 1 (gate/up interleaved rows): mma.m16n8k16 A-fragment order (gemv_mma): rows in tiles of 8, two tiles
+//  per 16-row operand; for tile pair p and 16-column block kt the 32 lanes' fragments are contiguous, [p][kt][lane][a0 a1 a2 a3]
+//  (a0/a2: row g of the first tile, columns 2tg.. and 8 + 2tg..; a1/a3: row g of the second tile); an odd last tile stores
+//  [kt][lane][a0 a2]. No padding: image bytes = rows * K * 2.
 struct ImgJob {
     const bf16* src0; const bf16* src1;   // mode 1: gate / up
     bf16* dst;
-    int N, K, RG, mode;                   // mode 0 flat rows, 1 gate/up interleave, 2 O-projection sliced by kv group
+    int N, K, RG, mode;
     int src_stride, n_kv, rmax;
 };
 __global__ void fk_build_image_kernel(const ImgJob j) {
     const int c = blockIdx.x, ncta = gridDim.x;
-    const FkSlice sl = (j.mode == 2) ? group_slice(j.N, c, ncta, j.n_kv) : flat_slice(j.N, j.RG, c, ncta);
-    const int kc = j.K >> 3;                                        // 16-byte chunks per row
-    const long long nchunk = (long long)sl.nrows * kc;
     bf16* dst = j.dst + (size_t)c * j.rmax * j.K;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < nchunk; i += (long long)gridDim.y * blockDim.x) {
-        const int r = (int)(i / kc), k0 = (int)(i % kc) << 3;
-        const int n = sl.row0 + r;
-        const bf16* src;
-        if (j.mode == 1) src = ((n & 1) ? j.src1 : j.src0) + (size_t)(n >> 1) * j.src_stride + k0;
-        else if (j.mode == 2) src = j.src0 + (size_t)n * j.src_stride + (size_t)(c % j.n_kv) * j.K + k0;
-        else src = j.src0 + (size_t)n * j.src_stride + k0;
-        *reinterpret_cast<uint4*>(dst + (size_t)r * j.K + k0) = *reinterpret_cast<const uint4*>(src);
+    if (j.mode == 2) {
+        const FkSlice sl = group_slice(j.N, c, ncta, j.n_kv);
+        const int kc = j.K >> 3;                                    // 16-byte chunks per row
+        const long long nchunk = (long long)sl.nrows * kc;
+        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < nchunk; i += (long long)gridDim.y * blockDim.x) {
+            const int r = (int)(i / kc), k0 = (int)(i % kc) << 3;
+            const bf16* src = j.src0 + (size_t)(sl.row0 + r) * j.src_stride + (size_t)(c % j.n_kv) * j.K + k0;
+            *reinterpret_cast<uint4*>(dst + (size_t)r * j.K + k0) = *reinterpret_cast<const uint4*>(src);
+        }
+        return;
+    }
+    const FkSlice sl = flat_slice(j.N, FK_TILE_ROWS, c, ncta);
+    const int nkt = j.K >> 4, nt = sl.nrows >> 3, npair = nt >> 1;
+    const long long nword = (long long)sl.nrows * j.K / 2;          // 32-bit words (bf16 pairs)
+    const long long pair_words = (long long)npair * nkt * 128;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < nword; i += (long long)gridDim.y * blockDim.x) {
+        int row, col;
+        if (i < pair_words) {
+            const int p = (int)(i / (nkt * 128)), rem = (int)(i % (nkt * 128));
+            const int kt = rem >> 7, w = rem & 127, lane = w >> 2, reg = w & 3, g = lane >> 2, tg = lane & 3;
+            row = (2 * p + (reg & 1)) * 8 + g; col = 16 * kt + 2 * tg + (reg >> 1) * 8;
+        } else {
+            const int rem = (int)(i - pair_words);
+            const int kt = rem >> 6, w = rem & 63, lane = w >> 1, reg = w & 1, g = lane >> 2, tg = lane & 3;
+            row = (nt - 1) * 8 + g; col = 16 * kt + 2 * tg + reg * 8;
+        }
+        const int n = sl.row0 + row;
+        const bf16* src = (j.mode == 1) ? ((n & 1) ? j.src1 : j.src0) + (size_t)(n >> 1) * j.src_stride + col
+                                        : j.src0 + (size_t)n * j.src_stride + col;
+        dw[i] = *reinterpret_cast<const uint32_t*>(src);
     }
 }
 
@@ -839,7 +864,8 @@ int fk_alloc(lqt_engine* h, T** p, size_t n) {
 
 int fk_rmax(int N, int RG, int mode, int n_kv, int ncta) {        // must match make_desc() in frame_kernel.cuh
     if (mode == 2) { const int ns = ncta / n_kv; return (N + ns - 1) / ns; }
-    return ((N / RG + ncta - 1) / ncta) * RG;
+    (void)RG;
+    return ((N / FK_TILE_ROWS + ncta - 1) / ncta) * FK_TILE_ROWS;           // rows are dealt in tiles of 8
 }
 
 // builds one image; returns its device pointer (nullptr on failure)
@@ -883,14 +909,15 @@ int fk_init(lqt_engine* h) {
     const Spec& s = h->sp;
     const int maxK = std::max(std::max(s.hidden, s.inter), std::max(s.cp_hidden, s.cp_inter));
     auto chk = [&](int K, const char* what) -> bool {
-        if (K % 8 != 0 || K > 6144) { h->err = std::string("frame kernel: unsupported dimension for ") + what; return false; }
+        if (K % 256 != 0 || K > 6144) {                 // gemv_mma: 16-column blocks, an even number per warp
+            h->err = std::string("frame kernel: unsupported dimension for ") + what; return false; }
         return true;
     };
     if (!chk(s.hidden, "hidden") || !chk(s.inter, "inter") || !chk(s.cp_hidden, "cp_hidden") || !chk(s.cp_inter, "cp_inter"))
         return 1;
     h->fk_wide = maxK > 3072;                       // frame_kernel<6, 3> instead of <3, 8>
     const int maxV = std::max(s.vocab, s.cp_vocab);
-    if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV % 16) || maxV > FK_LAND_WORDS || (s.hidden % 16) || (s.cp_hidden % 16) || (s.inter % 16) || (s.cp_inter % 16)) {
+    if (s.hidden > 2048 || s.cp_hidden > 2048 || (maxV % 16) || (s.vocab % 16) || (s.cp_vocab % 16) || maxV > FK_LAND_WORDS || (s.hidden % 16) || (s.cp_hidden % 16) || (s.inter % 16) || (s.cp_inter % 16)) {
         h->err = "frame kernel: hidden > 2048, vocab > 3072 or a dimension that is not a multiple of 16"; return 1;
     }
     {   // shared-memory carve-up and the number of co-resident clusters (the grid)
@@ -920,12 +947,13 @@ int fk_init(lqt_engine* h) {
                                    fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc));
         const int worst_c = std::max(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
         if (worst > 64 || worst_c > 64) { h->err = "frame kernel: too many rows per SM"; return 1; }
-        {   // gemv_rpw locates a row's ring stage with three compares: at most four stages per slice
-            auto nst_of = [&](int rows, int K) { const int rps = std::max(1, FK_STAGE_BYTES / (K * 2)); return (rows + rps - 1) / rps; };
+        {   // a slice must fit the ring: at most NST stages in flight per phase
+            auto nst_of = [&](int rows, int K) { return (int)(((size_t)rows * K * 2 + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES); };
             const int a = nst_of(fk_rmax((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc), s.hidden), dd = nst_of(fk_rmax(2 * s.inter, 2, 1, s.kv_heads, nc), s.hidden);
             const int ee = nst_of(fk_rmax(s.hidden, 1, 0, s.kv_heads, nc), s.inter), hh = nst_of(fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc), s.hidden);
             const int ce = nst_of(fk_rmax(s.cp_hidden, 1, 0, s.cp_kv_heads, nc), s.cp_inter), cd = nst_of(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), s.cp_hidden);
-            if (std::max(std::max(std::max(a, dd), std::max(ee, hh)), std::max(ce, cd)) > 4) { h->err = "frame kernel: more than four ring stages per slice"; return 1; }
+            const int ca = nst_of(fk_rmax((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc), s.cp_hidden);
+            if (std::max(std::max(std::max(a, dd), std::max(ee, hh)), std::max(std::max(ce, cd), ca)) > (h->fk_wide ? 3 : 4)) { h->err = "frame kernel: a weight slice exceeds the ring"; return 1; }
         }
         if (std::max(fk_rmax(s.hidden, 1, 0, s.kv_heads, nc), fk_rmax(s.cp_hidden, 1, 0, s.cp_kv_heads, nc)) > FK_X1OWN) { h->err = "frame kernel: too many down-projection rows per SM"; return 1; }
         if (FK_CLUSTER % s.kv_heads || FK_CLUSTER % s.cp_kv_heads) { h->err = "frame kernel: kv heads must divide the cluster size (8)"; return 1; }
@@ -989,6 +1017,7 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     const Spec& s = h->sp;
     FkParams p{};
     p.talker = h->fk_talker; p.cp = h->fk_cp;
+    { static const int sl = getenv("LQT_FK_SLEEP") ? atoi(getenv("LQT_FK_SLEEP")) : 400; p.producer_sleep_ns = (unsigned)(sl < 0 ? 0 : sl); }
     for (size_t l = 0; l < h->fk_tl.size(); ++l) p.t_layers[l] = h->fk_tl[l];
     for (size_t l = 0; l < h->fk_cl.size(); ++l) p.c_layers[l] = h->fk_cl[l];
     p.t_head = h->fk_t_head; p.vocab = s.vocab;

@@ -52,6 +52,7 @@ constexpr int FK_X1OWN = 16;                      // max rows of the down projec
 constexpr int FK_RPP_MAX = 16;                    // O-projection rows reduced per CTA (DSMEM)
 constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
+constexpr int FK_TILE_ROWS = 8;                   // rows per weight tile of the tensor-core matrix-vector phases
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
 constexpr int FK_RED_STRIDE = 96;                 // warp-partial row sums: [warp][FK_RED_STRIDE]; M = 2 -> second row at +48
 constexpr int FK_XS_STRIDE = 512;                 // attention output rows (input of the grouped O-projection)
@@ -101,6 +102,7 @@ struct FkParams {
     long long* codes_out; const long long* forced; float* trace; int trace_stride;
     unsigned* ctrl;            // [1] abort flag, [32] grid arrival counter (all zero at launch)
     int frame_end;             // run frames while frame < frame_end (<= max_frames)
+    unsigned producer_sleep_ns; // back-off of the producer lane while the ring is full ($LQT_FK_SLEEP, default 400)
     int mode;                  // 0 = prefill (if pos == 0) + frames; 1 = one talker token from next_in (head on), no frames
     unsigned long long* dbg;   // nullable: phase timeline of CTA dbg_cta, [0] = count
     int dbg_cap, dbg_cta;
@@ -205,7 +207,8 @@ struct FkShared {
     uint32_t sel_prefix; int sel_k;
     int tok; float fsum;
     float ssred[2][FK_CWARPS];        // [phase parity][warp]: partial sums of squares (RMSNorm)
-    alignas(16) float part[FK_CWARPS][8][32];   // matrix-vector per-lane partial sums [warp][slot][lane]
+    alignas(8) uint32_t zero8[2];     // always zero: B-fragment source of the lanes that hold the zero columns (gemv_mma)
+    float part[FK_CWARPS][64];        // matrix-vector partial sums [warp][row of the slice] (K is split over the warps)
     float x1own[FK_X1OWN];            // post-attention stream at the rows of this CTA's down-projection slice (its residual)
     uint64_t land_bar[2];             // multicast landing buffers: complete_tx from all CTAs of the cluster
     uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
@@ -268,14 +271,15 @@ LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, in
     const FkStack& S = is_cp ? p.cp : p.talker;
     const int H = S.H, qkv_dim = (S.heads + 2 * S.kv_heads) * ATT_D, gK = (S.heads / S.kv_heads) * ATT_D;
     FkSlice s{0, 0}; int K = 256, RG = 1, rmax = 0;
+    // the matrix-vector phases deal rows in tiles of FK_TILE_ROWS (the tensor-core fragment height); a gate/up pair never straddles a tile
     auto flat_max = [&](int N, int rg) { return ((N / rg + ncta - 1) / ncta) * rg; };
     switch (kind) {
-        case FKT_INPROJ: s = flat_slice(H, 1, cta, ncta); K = p.talker.H; rmax = flat_max(H, 1); break;
-        case FKT_A: s = flat_slice(qkv_dim, 1, cta, ncta); K = H; rmax = flat_max(qkv_dim, 1); break;
+        case FKT_INPROJ: s = flat_slice(H, FK_TILE_ROWS, cta, ncta); K = p.talker.H; rmax = flat_max(H, FK_TILE_ROWS); break;
+        case FKT_A: s = flat_slice(qkv_dim, FK_TILE_ROWS, cta, ncta); K = H; rmax = flat_max(qkv_dim, FK_TILE_ROWS); break;
         case FKT_C: s = group_slice(H, cta, ncta, S.kv_heads); K = gK; rmax = (H + ncta / S.kv_heads - 1) / (ncta / S.kv_heads); break;
-        case FKT_D: s = flat_slice(2 * S.inter, 2, cta, ncta); K = H; RG = 2; rmax = flat_max(2 * S.inter, 2); break;
-        case FKT_E: s = flat_slice(H, 1, cta, ncta); K = S.inter; rmax = flat_max(H, 1); break;
-        case FKT_HEAD: { const int V = is_cp ? p.cp_vocab : p.vocab; s = flat_slice(V, 1, cta, ncta); K = H; rmax = flat_max(V, 1); break; }
+        case FKT_D: s = flat_slice(2 * S.inter, FK_TILE_ROWS, cta, ncta); K = H; RG = 2; rmax = flat_max(2 * S.inter, FK_TILE_ROWS); break;
+        case FKT_E: s = flat_slice(H, FK_TILE_ROWS, cta, ncta); K = S.inter; rmax = flat_max(H, FK_TILE_ROWS); break;
+        case FKT_HEAD: { const int V = is_cp ? p.cp_vocab : p.vocab; s = flat_slice(V, FK_TILE_ROWS, cta, ncta); K = H; rmax = flat_max(V, FK_TILE_ROWS); break; }
         default: break;
     }
     FkDesc d;
@@ -475,78 +479,122 @@ LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
 // three compares instead of an integer division (~150 cycles, and several per batch)
 LQT_DEVINL int stage_of(int r, int rps) { return (r >= rps ? 1 : 0) + (r >= 2 * rps ? 1 : 0) + (r >= 3 * rps ? 1 : 0); }
 
-// Matrix-vector product of this CTA's weight slice (rows in the ring, row-major bf16) with the plain fp32 vector xp.
-// Slot s of warp w is row s * 8 + w (RG == 1) or row ((s >> 1) * 8 + w) * 2 + (s & 1) (RG == 2: gate/up pairs); a warp owns at
-// most eight slots. The lanes split K (16-byte shared loads, conflict-free), TWO rows at a time with two accumulator pairs
-// each: four independent FFMA2 chains, eight loads in flight, and at most one padding row per warp (the kernel is bound by
-// instruction issue on its 8 consumer warps, so rows are not padded to a wider batch). Per-lane partial sums go to shared
-// memory; one pass at the end reduces all slots of the warp (lane 4s + q sums a quarter of slot s, two shuffles finish).
-// On return lane s (< 8) holds the sum of slot s. RG is a run-time argument: ONE copy of this routine serves every
-// matrix-vector phase, so its code stays warm in the instruction cache across the phases of a layer.
+// ------------------------------------------------------------------------------------------------
+// Tensor-core matrix-vector product (every phase except the grouped O-projection).
+// The kernel is bound by instruction issue on its 8 consumer warps, not by bandwidth: with fp32 FMAs every 16-byte shared load
+// of weights costs ~20 instructions (bf16 -> fp32 unpacking + FFMA2). One mma.sync.m16n8k16 (bf16 x bf16 -> fp32) consumes a
+// 16 x 16 weight block per instruction instead. Exactness is kept by splitting the fp32 input vector into three bf16 planes
+// (x = hi + mid + lo, 8 + 8 + 8 mantissa bits; every product w * plane is exact in fp32) that occupy columns 0..2 of the
+// 16 x 8 B operand; the three result columns are added at the end.
+//  * Weight image (built once by the host, engine.cu fk_build_image_kernel): this CTA's rows in tiles of 8; two tiles form the
+//    16 rows of an A operand. For tile pair p and 16-column block kt the 32 lanes' A fragments (4 registers = 16 bytes each) are
+//    stored contiguously, [p][kt][lane][a0 a1 a2 a3]; an odd last tile stores [kt][lane][a0 a2] (rows 8..15 of the operand are
+//    zero registers). No padding: image bytes = rows * K * 2. One 16-byte shared load per lane per MMA, conflict-free.
+//  * Input vector: B fragments in shared memory, [kt][plane][tg][b0 b1] (96 bytes per kt), written by the staging code.
+//  * Warp w takes the blocks kt = w, w + 8, ... of every tile pair (K split over the warps), two accumulator sets in flight;
+//    its partial sums go to part[w][row], one thread per row adds the eight partials in the epilogue.
+// ------------------------------------------------------------------------------------------------
+LQT_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+LQT_DEVINL uint2 lds64_s(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    return r;
+}
+// fp32 -> three bf16 planes (round-to-nearest each; the remainders are exact)
+LQT_DEVINL void split3(float x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    hi = (uint32_t)__bfloat16_as_ushort(h); mid = (uint32_t)__bfloat16_as_ushort(m); lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+// this thread's four consecutive columns k..k+3 (k % 4 == 0) of the input vector -> B fragments
+LQT_DEVINL void stage_bfrag(uint32_t xf_s, int k, float x0, float x1, float x2, float x3) {
+    uint32_t h[4], m[4], l[4];
+    split3(x0, h[0], m[0], l[0]); split3(x1, h[1], m[1], l[1]); split3(x2, h[2], m[2], l[2]); split3(x3, h[3], m[3], l[3]);
+    const int kt = k >> 4, kk = k & 15;                          // kk in {0, 4, 8, 12}
+    const uint32_t base = xf_s + (uint32_t)kt * 96u + (uint32_t)((kk & 7) >> 1) * 8u + (uint32_t)(kk >> 3) * 4u;   // (tg0, reg)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base), "r"(h[0] | (h[1] << 16)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 8u), "r"(h[2] | (h[3] << 16)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 32u), "r"(m[0] | (m[1] << 16)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 40u), "r"(m[2] | (m[3] << 16)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 64u), "r"(l[0] | (l[1] << 16)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 72u), "r"(l[2] | (l[3] << 16)) : "memory");
+}
+
+// byte offset inside the ring (NST stages, consecutive in shared memory), reduced modulo the ring size
 template <int NST>
-LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int RG) {
-    const int K = d.K, rowbytes = K * 2;
-    const int nch = (K + 1023) >> 10;
-    const int nst = stage_of(d.nrows - 1, d.rps) + 1;
-    const uint32_t ring_s = smem_u32(FK_RING(c)), xp_s = smem_u32(xp);      // shared-space addresses, converted once
-    float* part = &FK_SH(c)->part[c.warp][0][0];
-    unsigned long long xk[16];                    // this lane's 32 input values of the current 1024-column chunk, as f32x2 pairs
-    auto load_chunk = [&](int ch) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = ch * 1024 + i * 256 + c.lane * 8;
-            uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
-            if (k < K) { u0 = lds128_s(xp_s + k * 4); u1 = lds128_s(xp_s + k * 4 + 16); }
-            xk[i * 4 + 0] = pack2(u0.x, u0.y); xk[i * 4 + 1] = pack2(u0.z, u0.w);
-            xk[i * 4 + 2] = pack2(u1.x, u1.y); xk[i * 4 + 3] = pack2(u1.z, u1.w);
-        }
-    };
-    if (nch == 1) load_chunk(0);
-    int cur = 0;                                  // first ring stage of this phase this warp has not released yet
-    int seen = 0;                                 // stages [cur, seen) have been observed full
+LQT_DEVINL uint32_t ring_wrap(uint32_t x) {
+    constexpr uint32_t RING = (uint32_t)NST * FK_STAGE_BYTES;
+    if constexpr ((NST & (NST - 1)) == 0) return x & (RING - 1u);
+    else { while (x >= RING) x -= RING; return x; }
+}
+// the blocks kt = w, w + 8, ... of one tile pair (or of the odd last tile): `iters` (even) blocks, two accumulator sets.
+// lin: ring offset of this lane's fragment of the first block; baddr / binc: this lane's B fragment and its stride
+// (lanes that hold the zero columns of B read one fixed zero word pair, stride 0): no predicates, no bounds checks.
+template <int NST, bool SINGLE>
+LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, uint32_t baddr, uint32_t binc, int iters) {
+    constexpr uint32_t STEP = (SINGLE ? 256u : 512u) * FK_CWARPS;
 #pragma unroll 1
-    for (int sb = 0; sb < 8; sb += 2) {
-        const int ra = (RG == 2) ? ((sb >> 1) * 8 + c.warp) * 2 : sb * 8 + c.warp;
-        if (ra >= d.nrows) break;                 // warp-uniform; rows grow with the slot
-        int rb = (RG == 2) ? ra + 1 : ra + 8;
-        if (rb >= d.nrows) rb = ra;               // padding row: recomputes row a, result never read
-        const int g0 = stage_of(ra, d.rps), g1 = stage_of(rb, d.rps);
-        while (cur < g0) {                        // stages that hold no (further) row of this warp
-            if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
+    for (int it = 0; it < iters; it += 2) {
+        const uint32_t l1 = ring_wrap<NST>(lin + STEP);
+        uint4 a0, a1;
+        if constexpr (SINGLE) {
+            const uint2 t0 = lds64_s(ring_s + lin), t1 = lds64_s(ring_s + l1);
+            a0 = make_uint4(t0.x, 0u, t0.y, 0u); a1 = make_uint4(t1.x, 0u, t1.y, 0u);
+        } else {
+            a0 = lds128_s(ring_s + lin); a1 = lds128_s(ring_s + l1);
+        }
+        const uint2 b0 = lds64_s(baddr), b1 = lds64_s(baddr + binc);
+        mma_bf16_16816(acc[0], a0.x, a0.y, a0.z, a0.w, b0.x, b0.y);
+        mma_bf16_16816(acc[1], a1.x, a1.y, a1.z, a1.w, b1.x, b1.y);
+        lin = ring_wrap<NST>(l1 + STEP);
+        baddr += 2u * binc;
+    }
+}
+
+template <int NST>
+LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d) {
+    const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1;
+    const uint32_t total = (uint32_t)d.nrows * (uint32_t)d.K * 2u;
+    const int nst = (int)((total + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES);
+    const uint32_t ring_s = smem_u32(FK_RING(c));
+    const int g = c.lane >> 2, tg = c.lane & 3;
+    // B fragments: lanes g < 3 hold the three planes; the others (zero columns of B) read a fixed pair of zero words
+    const uint32_t b0addr = (g < 3) ? smem_u32(FK_XP(c)) + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)c.warp * 96u : smem_u32(&FK_SH(c)->zero8[0]);
+    const uint32_t binc = (g < 3) ? 96u * FK_CWARPS : 0u;
+    const uint32_t ring0 = (c.stage_ctr % (unsigned)NST) * FK_STAGE_BYTES;       // ring offset of byte 0 of this slice
+    float* part = &FK_SH(c)->part[c.warp][0];
+    const int iters = nkt / FK_CWARPS;            // blocks per warp per tile pair (even: K % 256 == 0, checked by the host)
+    int cur = 0, seen = 0;                        // ring stages of this phase: [0, cur) released, [cur, seen) observed full
+#pragma unroll 1
+    for (int p = 0; p < npair + (nt & 1); ++p) {
+        const bool single = p == npair;
+        const uint32_t base = (uint32_t)p * (uint32_t)nkt * 512u, end = base + (uint32_t)nkt * (single ? 256u : 512u);
+        const int st_last = (int)((end - 1u) / FK_STAGE_BYTES);
+        while (seen <= st_last) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        if (single) mma_blocks<NST, true>(acc, ring_s, ring_wrap<NST>(ring0 + base + (uint32_t)c.warp * 256u + c.lane * 8u), b0addr, binc, iters);
+        else        mma_blocks<NST, false>(acc, ring_s, ring_wrap<NST>(ring0 + base + (uint32_t)c.warp * 512u + c.lane * 16u), b0addr, binc, iters);
+        // lane (g, tg): acc[.][0..1] = row g, columns 2tg, 2tg + 1; acc[.][2..3] = row g + 8. Columns 0..2 carry the planes.
+        float v0 = (acc[0][0] + acc[1][0]) + (acc[0][1] + acc[1][1]);
+        float v1 = (acc[0][2] + acc[1][2]) + (acc[0][3] + acc[1][3]);
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        if (tg == 0) {
+            part[p * 16 + g] = v0;
+            if (!single) part[p * 16 + 8 + g] = v1;
+        }
+        const int st_done = (int)(end / FK_STAGE_BYTES);         // stages that end at or before the end of this pair
+        while (cur < st_done) {
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + cur) % (unsigned)NST]);
             ++cur;
         }
-        while (seen <= g1) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
-        const uint32_t wa = ring_s + ((c.stage_ctr + g0) % (unsigned)NST) * FK_STAGE_BYTES + (unsigned)(ra - g0 * d.rps) * (unsigned)rowbytes + c.lane * 16;
-        const uint32_t wb = ring_s + ((c.stage_ctr + g1) % (unsigned)NST) * FK_STAGE_BYTES + (unsigned)(rb - g1 * d.rps) * (unsigned)rowbytes + c.lane * 16;
-        unsigned long long a2[2][2] = {{0ull, 0ull}, {0ull, 0ull}};      // [row][accumulator]: (even-column sum, odd-column sum)
-#pragma unroll 1
-        for (int ch = 0; ch < nch; ++ch) {
-            if (nch > 1) load_chunk(ch);
-            uint4 w[2][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool in = ch * 1024 + i * 256 < K;
-                w[0][i] = in ? lds128_s(wa + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
-                w[1][i] = in ? lds128_s(wb + ch * 2048 + i * 512) : make_uint4(0u, 0u, 0u, 0u);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    a2[j][0] = ffma2(bf16x2_to_f32x2(w[j][i].x), xk[i * 4 + 0], a2[j][0]);
-                    a2[j][1] = ffma2(bf16x2_to_f32x2(w[j][i].y), xk[i * 4 + 1], a2[j][1]);
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    a2[j][0] = ffma2(bf16x2_to_f32x2(w[j][i].z), xk[i * 4 + 2], a2[j][0]);
-                    a2[j][1] = ffma2(bf16x2_to_f32x2(w[j][i].w), xk[i * 4 + 3], a2[j][1]);
-                }
-            }
-        }
-        part[sb * 32 + c.lane] = sum2(a2[0][0]) + sum2(a2[0][1]);
-        part[(sb + 1) * 32 + c.lane] = sum2(a2[1][0]) + sum2(a2[1][1]);
     }
     while (cur < nst) {
         if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
@@ -555,15 +603,13 @@ LQT_DEVINL float gemv_rpw(FkCtx& c, const FkDesc& d, const float* xp, const int 
         ++cur;
     }
     c.stage_ctr += nst;
-    __syncwarp();
-    // lane 4s + q: a quarter of slot s (slots this warp did not compute hold stale values; their lanes are never read)
-    const float4 u = *reinterpret_cast<const float4*>(part + c.lane * 8), v = *reinterpret_cast<const float4*>(part + c.lane * 8 + 4);
-    float t = ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    const float mine = __shfl_sync(0xffffffffu, t, (c.lane & 7) * 4);
-    __syncwarp();                                 // everyone has read the partials before the next call overwrites them
-    return mine;
+}
+// sum of the eight warps' partials of row r (after the CTA barrier that follows gemv_mma)
+LQT_DEVINL float part_sum(FkCtx& c, int r) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < FK_CWARPS; ++w) t += FK_SH(c)->part[w][r];
+    return t;
 }
 
 // Row-per-warp product for the grouped O-projection (K = rep*128 <= 512, input row in FK_XS(c)): warp w owns
@@ -1039,13 +1085,21 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; break; }
             continue;
         }
-        // ---- K phases: stage the input vector as plain floats (x * w_norm for the normalised phases) ------------
+        // ---- K phases: stage the input vector as bf16x3 B fragments (x * w_norm for the normalised phases) ------
         float xin[HJ][4];                                      // the raw row (this thread's columns): sum of squares, last_hidden
 #pragma unroll
         for (int j = 0; j < HJ; ++j) { xin[j][0] = 0.f; xin[j][1] = 0.f; xin[j][2] = 0.f; xin[j][3] = 0.f; }
-        const float* xp = FK_XP(c);
+        const uint32_t xf_s = smem_u32(FK_XP(c));
         switch (kind) {
-            case FKT_INPROJ: xp = FK_RES0(c); break;               // plain row in shared memory already, no norm
+            case FKT_INPROJ: {                                     // plain row in shared memory, no norm
+#pragma unroll
+                for (int j = 0; j < HJ; ++j)
+                    if (j * 1024 + tid4 < d.K) {
+                        const float4 v = *reinterpret_cast<const float4*>(FK_RES0(c) + j * 1024 + tid4);
+                        stage_bfrag(xf_s, j * 1024 + tid4, v.x, v.y, v.z, v.w);
+                    }
+                break;
+            }
             case FKT_A: {
                 if (in_res0) {
 #pragma unroll
@@ -1080,7 +1134,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     land_row<3>(c, land, S.act + w0, wn, want, t3);
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
-                        if (j * 1024 + tid4 < wn) *reinterpret_cast<float4*>(FK_XP(c) + w0 + j * 1024 + tid4) = make_float4(t3[j][0], t3[j][1], t3[j][2], t3[j][3]);
+                        if (j * 1024 + tid4 < wn) stage_bfrag(xf_s, w0 + j * 1024 + tid4, t3[j][0], t3[j][1], t3[j][2], t3[j][3]);
                 }
                 break;
             }
@@ -1099,38 +1153,45 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     const float4 w = nwv[j];
                     ss = fmaf(xin[j][0], xin[j][0], ss); ss = fmaf(xin[j][1], xin[j][1], ss);
                     ss = fmaf(xin[j][2], xin[j][2], ss); ss = fmaf(xin[j][3], xin[j][3], ss);
-                    *reinterpret_cast<float4*>(FK_XP(c) + j * 1024 + tid4) = make_float4(xin[j][0] * w.x, xin[j][1] * w.y, xin[j][2] * w.z, xin[j][3] * w.w);
+                    stage_bfrag(xf_s, j * 1024 + tid4, xin[j][0] * w.x, xin[j][1] * w.y, xin[j][2] * w.z, xin[j][3] * w.w);
                 }
             }
             ss_publish(c, ss);
         }
         if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; }
-        if (kind != FKT_INPROJ) csync();                       // the plain input vector (and the sum-of-squares partials) are complete
+        csync();                                               // the input fragments (and the sum-of-squares partials) are complete
         if (FK_SH(c)->aborted) { c.aborted = true; break; }
-        // ---- product + epilogue on the lanes that hold the sums ----------------------------------------------
+        // ---- product (all warps, K split), then the epilogue on warp 0: one lane per row (pair) ----------------------
         {
-            const float rs = nw ? ss_rstd(c, H, p.eps) : 1.f;
-            const int slot = c.lane;
-            const bool lead = c.lane < 8;
-            const float vraw = gemv_rpw<NST>(c, d, xp, kind == FKT_D ? 2 : 1);      // the only call site
+            gemv_mma<NST>(c, d);                                                     // the only call site
             fk_mark(c, 5);
-            if (kind == FKT_D) {
-                const float v = vraw;
-                const float up = __shfl_down_sync(0xffffffffu, v, 1);          // slot s + 1 = the up row of the same pair
-                const int q = (slot >> 1) * 8 + c.warp;
-                if (lead && (slot & 1) == 0 && 2 * q < d.nrows) st_ll(S.act + (d.row0 >> 1) + q, silu_f(v * rs) * (up * rs), c.seq);
-            } else {
-                const float v = vraw * rs;
-                const int r = slot * 8 + c.warp, n = d.row0 + r;
-                if (lead && r < d.nrows) {
-                    if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
-                    else if (kind == FKT_E) st_ll(S.x + n, FK_SH(c)->x1own[r] + v, c.seq);
-                    else if (kind == FKT_INPROJ) st_ll(p.cxin + n, v + __ldg(p.c_inproj_b + n), c.seq);
-                    else {
-                        st_ll((is_cp ? p.clogits_ll : p.logits_ll) + n, v, c.seq);
-                        (is_cp ? p.clogits : p.logits)[n] = v;
+            csync();                                           // every warp's partial sums are in shared memory
+            const bool lh = (kind == FKT_HEAD && !is_cp);
+            float rs = 1.f;
+            if (nw && (c.warp == 0 || lh)) rs = ss_rstd(c, H, p.eps);
+            if (c.warp == 0) {
+                if (kind == FKT_D) {                           // rows 2q (gate), 2q + 1 (up) -> act[q]
+                    const int q = c.lane;
+                    if (2 * q < d.nrows) {
+                        const float gt = part_sum(c, 2 * q) * rs, up = part_sum(c, 2 * q + 1) * rs;
+                        st_ll(S.act + (d.row0 >> 1) + q, silu_f(gt) * up, c.seq);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int r = c.lane; r < d.nrows; r += 32) {
+                        const float v = part_sum(c, r) * rs;
+                        const int n = d.row0 + r;
+                        if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
+                        else if (kind == FKT_E) st_ll(S.x + n, FK_SH(c)->x1own[r] + v, c.seq);
+                        else if (kind == FKT_INPROJ) st_ll(p.cxin + n, v + __ldg(p.c_inproj_b + n), c.seq);
+                        else {
+                            st_ll((is_cp ? p.clogits_ll : p.logits_ll) + n, v, c.seq);
+                            (is_cp ? p.clogits : p.logits)[n] = v;
+                        }
                     }
                 }
+                __syncwarp();
+                if (c.lane == 0) grid_arrive(c);               // the outputs of this CTA are issued
             }
             if (kind == FKT_HEAD && !is_cp) {                  // talker last_hidden = final-norm of the row (:859)
 #pragma unroll
@@ -1143,8 +1204,6 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     }
                 }
             }
-            csync();                                           // every warp has issued its outputs (and finished reading xp)
-            if (c.tid == 0) grid_arrive(c);
         }
         fk_mark(c, 6);
         if (c.aborted) break;
@@ -1513,7 +1572,7 @@ inline FkSmemLayout fk_smem_layout(int nstages, int maxV, int H, int maxK) {
     L.att = off; L.xs = off + attb;
     size_t sc = attb + xsb;
     if ((size_t)maxV * 4 > sc) sc = (size_t)maxV * 4;
-    if ((size_t)maxK * 4 > sc) sc = (size_t)maxK * 4;       // plain input vector of a matrix-vector phase
+    if ((size_t)maxK * 6 > sc) sc = (size_t)maxK * 6;       // input vector of a matrix-vector phase as bf16x3 B fragments (96 bytes per 16 columns)
     off += up(sc);
     L.red = off;
     L.nxt = off; off += up((size_t)H * 4);
@@ -1534,7 +1593,7 @@ frame_kernel(const __grid_constant__ FkParams p) {
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }   // every consumer warp releases a stage
         mbar_init(&sh->land_bar[0], 1); mbar_init(&sh->land_bar[1], 1);
-        sh->stop = 0; sh->consumed = 0; sh->aborted = 0;
+        sh->stop = 0; sh->consumed = 0; sh->aborted = 0; sh->zero8[0] = 0u; sh->zero8[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
@@ -1584,21 +1643,24 @@ frame_kernel(const __grid_constant__ FkParams p) {
                     if (d.nrows <= 0) continue;
                     const uint32_t row_bytes = (uint32_t)d.K * 2u;
                     const char* srcb = reinterpret_cast<const char*>(W + d.img_off);
-                    for (int r0 = 0; r0 < d.nrows && !stopped; r0 += d.rps) {
-                        const int nr = min(d.rps, d.nrows - r0);
+                    // the O-projection slice (row-major) is staged in whole rows, the fragment-ordered images of the
+                    // tensor-core phases as a flat byte stream in full stages
+                    const uint32_t total = (uint32_t)d.nrows * row_bytes;
+                    const uint32_t sbytes = (op.kind == FKT_C) ? (uint32_t)d.rps * row_bytes : (uint32_t)FK_STAGE_BYTES;
+                    for (uint32_t off = 0; off < total && !stopped; off += sbytes) {
                         const unsigned slot = issued % (unsigned)NST, par = ((issued / (unsigned)NST) & 1u) ^ 1u;
                         unsigned long long t0 = 0;
                         while (!mbar_try_wait(&sh->empty[slot], par)) {
                             // The ring is full: the producer is ~10 us ahead of the consumers (profiles/r1_v19_ring_latency.txt), so it
                             // sleeps between polls instead of spinning -- it shares its scheduler with consumer warps 0 and 4, and
                             // warp 0 (grid hand-over, reductions, sampler tail) is the critical path of every phase.
-                            __nanosleep(400);
+                            if (p.producer_sleep_ns) __nanosleep(p.producer_sleep_ns);
                             if (sh->stop) { stopped = true; break; }
                             if (t0 == 0) t0 = clock64();
                             else if (clock64() - t0 > FK_SPIN_LIMIT) { stopped = true; break; }
                         }
                         if (stopped) break;
-                        const uint32_t bytes = (uint32_t)nr * row_bytes;
+                        const uint32_t bytes = min(sbytes, total - off);
 #ifdef FK_FINE_MARKS
                         if (p.dbg && cta == p.dbg_cta) {
                             unsigned long long* pd = p.dbg + p.dbg_cap / 2;
@@ -1606,7 +1668,7 @@ frame_kernel(const __grid_constant__ FkParams p) {
                         }
 #endif
                         mbar_expect_tx(&sh->full[slot], bytes);
-                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + (size_t)r0 * row_bytes, bytes, &sh->full[slot]);
+                        bulk_g2s(fk_smem + (size_t)slot * FK_STAGE_BYTES, srcb + off, bytes, &sh->full[slot]);
                         ++issued;
                     }
                 }
