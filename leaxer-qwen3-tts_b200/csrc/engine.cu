@@ -806,8 +806,7 @@ bool load_vocoder_weights(lqt_engine* h) {
 // persistent frame kernel: one-time weight regrouping, tables, launch
 // ------------------------------------------------------------------------------------------------
 // Per-CTA weight images (see frame_kernel.cuh): CTA c's rows of the matrix.
-//  mode 2 (O-projection, sliced by kv group): row-major [rows][K] bf16.
-//  mode 0 (flat rows) / 1 (gate/up interleaved rows): mma.m16n8k16 A-fragment order (gemv_mma): rows in tiles of 8, two tiles
+//  mode 0 (flat rows) / 1 (gate/up interleaved rows) / 2 (O-projection: rows of a cluster's member index, columns of the CTA's kv group): mma.m16n8k16 A-fragment order (gemv_mma): rows in tiles of 8, two tiles
 //  per 16-row operand; for tile pair p and 16-column block kt the 32 lanes' fragments are contiguous, [p][kt][lane][a0 a1 a2 a3]
 //  (a0/a2: row g of the first tile, columns 2tg.. and 8 + 2tg..; a1/a3: row g of the second tile); an odd last tile stores
 //  [kt][lane][a0 a2]. No padding: image bytes = rows * K * 2.
@@ -820,18 +819,7 @@ struct ImgJob {
 __global__ void fk_build_image_kernel(const ImgJob j) {
     const int c = blockIdx.x, ncta = gridDim.x;
     bf16* dst = j.dst + (size_t)c * j.rmax * j.K;
-    if (j.mode == 2) {
-        const FkSlice sl = group_slice(j.N, c, ncta, j.n_kv);
-        const int kc = j.K >> 3;                                    // 16-byte chunks per row
-        const long long nchunk = (long long)sl.nrows * kc;
-        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < nchunk; i += (long long)gridDim.y * blockDim.x) {
-            const int r = (int)(i / kc), k0 = (int)(i % kc) << 3;
-            const bf16* src = j.src0 + (size_t)(sl.row0 + r) * j.src_stride + (size_t)(c % j.n_kv) * j.K + k0;
-            *reinterpret_cast<uint4*>(dst + (size_t)r * j.K + k0) = *reinterpret_cast<const uint4*>(src);
-        }
-        return;
-    }
-    const FkSlice sl = flat_slice(j.N, FK_TILE_ROWS, c, ncta);
+    const FkSlice sl = (j.mode == 2) ? group_slice(j.N, c, ncta, j.n_kv) : flat_slice(j.N, FK_TILE_ROWS, c, ncta);
     const int nkt = j.K >> 4, nt = sl.nrows >> 3, npair = nt >> 1;
     const long long nword = (long long)sl.nrows * j.K / 2;          // 32-bit words (bf16 pairs)
     const long long pair_words = (long long)npair * nkt * 128;
@@ -849,6 +837,7 @@ __global__ void fk_build_image_kernel(const ImgJob j) {
         }
         const int n = sl.row0 + row;
         const bf16* src = (j.mode == 1) ? ((n & 1) ? j.src1 : j.src0) + (size_t)(n >> 1) * j.src_stride + col
+                        : (j.mode == 2) ? j.src0 + (size_t)n * j.src_stride + (size_t)(c % j.n_kv) * j.K + col
                                         : j.src0 + (size_t)n * j.src_stride + col;
         dw[i] = *reinterpret_cast<const uint32_t*>(src);
     }
@@ -863,7 +852,7 @@ int fk_alloc(lqt_engine* h, T** p, size_t n) {
 }
 
 int fk_rmax(int N, int RG, int mode, int n_kv, int ncta) {        // must match make_desc() in frame_kernel.cuh
-    if (mode == 2) { const int ns = ncta / n_kv; return (N + ns - 1) / ns; }
+    if (mode == 2) { const int ns = ncta / n_kv; return ((N / FK_TILE_ROWS + ns - 1) / ns) * FK_TILE_ROWS; }
     (void)RG;
     return ((N / FK_TILE_ROWS + ncta - 1) / ncta) * FK_TILE_ROWS;           // rows are dealt in tiles of 8
 }

@@ -52,6 +52,7 @@ constexpr int FK_X1OWN = 16;                      // max rows of the down projec
 constexpr int FK_RPP_MAX = 16;                    // O-projection rows reduced per CTA (DSMEM)
 constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
+constexpr int FK_PART_ROWS = 80;                  // max rows of a slice (64 for the flat phases, 72 for the O-projection of 15 clusters)
 constexpr int FK_TILE_ROWS = 8;                   // rows per weight tile of the tensor-core matrix-vector phases
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
 constexpr int FK_RED_STRIDE = 96;                 // warp-partial row sums: [warp][FK_RED_STRIDE]; M = 2 -> second row at +48
@@ -208,7 +209,7 @@ struct FkShared {
     int tok; float fsum;
     float ssred[2][FK_CWARPS];        // [phase parity][warp]: partial sums of squares (RMSNorm)
     alignas(8) uint32_t zero8[2];     // always zero: B-fragment source of the lanes that hold the zero columns (gemv_mma)
-    float part[FK_CWARPS][64];        // matrix-vector partial sums [warp][row of the slice] (K is split over the warps)
+    float part[FK_CWARPS][FK_PART_ROWS];  // matrix-vector partial sums [warp][row of the slice] (K is split over the warps)
     float x1own[FK_X1OWN];            // post-attention stream at the rows of this CTA's down-projection slice (its residual)
     uint64_t land_bar[2];             // multicast landing buffers: complete_tx from all CTAs of the cluster
     uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
@@ -264,8 +265,9 @@ LQT_DEVINL FkSlice flat_slice(int N, int RG, int cta, int ncta) {
 LQT_DEVINL int grp_members(int g, int n_kv, int ncta) { return (ncta - g + n_kv - 1) / n_kv; }
 LQT_DEVINL FkSlice group_slice(int Nout, int cta, int ncta, int n_kv) {
     const int g = cta % n_kv, s = cta / n_kv, ns = grp_members(g, n_kv, ncta);
-    const int r0 = (int)(((unsigned)s * (unsigned)Nout) / (unsigned)ns), r1 = (int)(((unsigned)(s + 1) * (unsigned)Nout) / (unsigned)ns);
-    return FkSlice{r0, r1 - r0};
+    const int T = Nout / FK_TILE_ROWS;           // rows are dealt in tiles of 8 (tensor-core fragment height)
+    const int t0 = (int)(((unsigned)s * (unsigned)T) / (unsigned)ns), t1 = (int)(((unsigned)(s + 1) * (unsigned)T) / (unsigned)ns);
+    return FkSlice{t0 * FK_TILE_ROWS, (t1 - t0) * FK_TILE_ROWS};
 }
 LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, int ncta) {
     const FkStack& S = is_cp ? p.cp : p.talker;
@@ -276,7 +278,7 @@ LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, in
     switch (kind) {
         case FKT_INPROJ: s = flat_slice(H, FK_TILE_ROWS, cta, ncta); K = p.talker.H; rmax = flat_max(H, FK_TILE_ROWS); break;
         case FKT_A: s = flat_slice(qkv_dim, FK_TILE_ROWS, cta, ncta); K = H; rmax = flat_max(qkv_dim, FK_TILE_ROWS); break;
-        case FKT_C: s = group_slice(H, cta, ncta, S.kv_heads); K = gK; rmax = (H + ncta / S.kv_heads - 1) / (ncta / S.kv_heads); break;
+        case FKT_C: s = group_slice(H, cta, ncta, S.kv_heads); K = gK; rmax = ((H / FK_TILE_ROWS + ncta / S.kv_heads - 1) / (ncta / S.kv_heads)) * FK_TILE_ROWS; break;
         case FKT_D: s = flat_slice(2 * S.inter, FK_TILE_ROWS, cta, ncta); K = H; RG = 2; rmax = flat_max(2 * S.inter, FK_TILE_ROWS); break;
         case FKT_E: s = flat_slice(H, FK_TILE_ROWS, cta, ncta); K = S.inter; rmax = flat_max(H, FK_TILE_ROWS); break;
         case FKT_HEAD: { const int V = is_cp ? p.cp_vocab : p.vocab; s = flat_slice(V, FK_TILE_ROWS, cta, ncta); K = H; rmax = flat_max(V, FK_TILE_ROWS); break; }
@@ -527,6 +529,16 @@ LQT_DEVINL void stage_bfrag(uint32_t xf_s, int k, float x0, float x1, float x2, 
 }
 
 // byte offset inside the ring (NST stages, consecutive in shared memory), reduced modulo the ring size
+// one column k of an input vector -> its three bf16 planes in the B-fragment layout
+LQT_DEVINL void stage_bfrag1(uint32_t xf_s, int k, float x) {
+    uint32_t h, m, l;
+    split3(x, h, m, l);
+    const int kt = k >> 4, kk = k & 15;
+    const uint32_t a = xf_s + (uint32_t)kt * 96u + (uint32_t)((kk & 7) >> 1) * 8u + (uint32_t)(kk >> 3) * 4u + (uint32_t)(kk & 1) * 2u;
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)h) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 32u), "h"((unsigned short)m) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 64u), "h"((unsigned short)l) : "memory");
+}
 template <int NST>
 LQT_DEVINL uint32_t ring_wrap(uint32_t x) {
     constexpr uint32_t RING = (uint32_t)NST * FK_STAGE_BYTES;
@@ -558,14 +570,14 @@ LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, ui
 }
 
 template <int NST>
-LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d) {
+LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d, const uint32_t xf_s) {
     const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1;
     const uint32_t total = (uint32_t)d.nrows * (uint32_t)d.K * 2u;
     const int nst = (int)((total + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES);
     const uint32_t ring_s = smem_u32(FK_RING(c));
     const int g = c.lane >> 2, tg = c.lane & 3;
     // B fragments: lanes g < 3 hold the three planes; the others (zero columns of B) read a fixed pair of zero words
-    const uint32_t b0addr = (g < 3) ? smem_u32(FK_XP(c)) + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)c.warp * 96u : smem_u32(&FK_SH(c)->zero8[0]);
+    const uint32_t b0addr = (g < 3) ? xf_s + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)c.warp * 96u : smem_u32(&FK_SH(c)->zero8[0]);
     const uint32_t binc = (g < 3) ? 96u * FK_CWARPS : 0u;
     const uint32_t ring0 = (c.stage_ctr % (unsigned)NST) * FK_STAGE_BYTES;       // ring offset of byte 0 of this slice
     float* part = &FK_SH(c)->part[c.warp][0];
@@ -610,77 +622,6 @@ LQT_DEVINL float part_sum(FkCtx& c, int r) {
 #pragma unroll
     for (int w = 0; w < FK_CWARPS; ++w) t += FK_SH(c)->part[w][r];
     return t;
-}
-
-// Row-per-warp product for the grouped O-projection (K = rep*128 <= 512, input row in FK_XS(c)): warp w owns
-// rows w, w + 8, ... of every stage. The n_kv CTAs that hold the partials of the same rows (one per kv group) sit
-// in the same cluster: partial (row r) goes straight from the reduction into the shared memory of partner
-// r / rpp as a (value, sequence) word (DSMEM store, no barrier); the partner sums them (reduce_partials).
-template <int NST, int NC>
-LQT_DEVINL void gemv_rw_n(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
-    const int K = d.K, rowbytes = K * 2;
-    float x0[NC][8];
-    int coff[NC];
-#pragma unroll
-    for (int cc = 0; cc < NC; ++cc) {
-        const int k = cc * 256 + c.lane * 8;
-        const bool act = k < K;
-        coff[cc] = act ? k * 2 : 0;
-        float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
-        if (act) { u0 = *reinterpret_cast<const float4*>(FK_XS(c) + k); u1 = *reinterpret_cast<const float4*>(FK_XS(c) + k + 4); }
-        x0[cc][0] = u0.x; x0[cc][1] = u0.y; x0[cc][2] = u0.z; x0[cc][3] = u0.w; x0[cc][4] = u1.x; x0[cc][5] = u1.y; x0[cc][6] = u1.z; x0[cc][7] = u1.w;
-    }
-    const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
-    const int nst = (d.nrows + d.rps - 1) / d.rps;
-    int row = 0;
-#pragma unroll 1
-    for (int st = 0; st < nst; ++st) {
-        const unsigned ast = c.stage_ctr + st, slot = ast % (unsigned)NST;
-        wait_full(c, ast, NST);
-        const int nrs = min(d.rps, d.nrows - row);
-        const uint32_t sb = smem_u32(FK_RING(c)) + slot * FK_STAGE_BYTES;
-#pragma unroll 1
-        for (int r0 = 0; r0 < nrs; r0 += 64) {
-            uint4 w[8][NC];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t rb = sb + (unsigned)(min(r0 + c.warp + 8 * i, nrs - 1) * rowbytes);
-#pragma unroll
-                for (int cc = 0; cc < NC; ++cc) w[i][cc] = lds128_s(rb + coff[cc]);
-            }
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                a[i] = 0.f;
-#pragma unroll
-                for (int cc = 0; cc < NC; ++cc) {
-                    a[i] = fmaf(bf16lo(w[i][cc].x), x0[cc][0], a[i]); a[i] = fmaf(bf16hi(w[i][cc].x), x0[cc][1], a[i]);
-                    a[i] = fmaf(bf16lo(w[i][cc].y), x0[cc][2], a[i]); a[i] = fmaf(bf16hi(w[i][cc].y), x0[cc][3], a[i]);
-                    a[i] = fmaf(bf16lo(w[i][cc].z), x0[cc][4], a[i]); a[i] = fmaf(bf16hi(w[i][cc].z), x0[cc][5], a[i]);
-                    a[i] = fmaf(bf16lo(w[i][cc].w), x0[cc][6], a[i]); a[i] = fmaf(bf16hi(w[i][cc].w), x0[cc][7], a[i]);
-                }
-            }
-            const float s = reduce8(a, c.lane);
-            const int r = r0 + c.warp + 8 * (c.lane >> 2);
-            if ((c.lane & 3) == 0 && r < nrs) {
-                const int rr = row + r, tg = rr / rpp;
-#ifdef FK_NO_DSMEM                                // bisecting aid: partials through global memory
-                st_ll((c.p->pa + 8 * FK_NS_MAX * 2 * ATT_PSTRIDE) + (size_t)g * 4096 + d.row0 + rr, s, c.seq);
-                (void)tg; (void)base;
-#else
-                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][rr - tg * rpp], base + (unsigned)tg), s, c.seq);
-#endif
-            }
-        }
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[slot]);
-        row += nrs;
-    }
-    c.stage_ctr += nst;
-}
-template <int NST>
-LQT_DEVINL void gemv_rw(FkCtx& c, const FkDesc& d, int n_kv, int rpp) {
-    if (d.K <= 256) gemv_rw_n<NST, 1>(c, d, n_kv, rpp); else gemv_rw_n<NST, 2>(c, d, n_kv, rpp);
 }
 
 LQT_DEVINL float ss_rstd(FkCtx& c, int K, float eps) {
@@ -856,7 +797,7 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
             }
         }
     }
-    FK_XS(c)[c.tid] = num / den;
+    stage_bfrag1(smem_u32(FK_XS(c)), c.tid, num / den);        // column tid of the O-projection input, as B fragments
     csync();
 }
 
@@ -932,7 +873,7 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, uns
 #pragma unroll
         for (int j = 0; j < FK_CP_POS / 2; ++j) if (j < p0) o = fmaf(row[j], vcol[j], o);
         o = fmaf(row[p0], vn[d_t], o);
-        FK_XS(c)[c.tid] = o;
+        stage_bfrag1(smem_u32(FK_XS(c)), c.tid, o);            // column tid of the O-projection input, as B fragments
     }
     csync();
 }
@@ -1078,8 +1019,16 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             fk_mark(c, 3);
             if (FK_SH(c)->aborted) { c.aborted = true; break; }
             const int rpp = (d.nrows + n_kv - 1) / n_kv;
-            gemv_rw<NST>(c, d, n_kv, rpp);
+            gemv_mma<NST>(c, d, smem_u32(FK_XS(c)));
             fk_mark(c, 5);
+            csync();                                           // every warp's partial sums are in shared memory
+            // The n_kv CTAs that hold the partials of the same rows (one per kv group) sit in the same cluster: the partial of
+            // row r goes straight into the shared memory of partner r / rpp as a (value, sequence) word (DSMEM store, no barrier)
+            if (c.tid < d.nrows) {
+                const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
+                const int tgt = c.tid / rpp;
+                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid), c.seq);
+            }
             reduce_partials(c, d, n_kv, rpp, in_res0 ? FK_RES0(c) : nullptr, FK_LAND(c) + c.land_a * FK_LAND_WORDS, S.x1);
             fk_mark(c, 6);
             if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; break; }
@@ -1163,7 +1112,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         if (FK_SH(c)->aborted) { c.aborted = true; break; }
         // ---- product (all warps, K split), then the epilogue on warp 0: one lane per row (pair) ----------------------
         {
-            gemv_mma<NST>(c, d);                                                     // the only call site
+            gemv_mma<NST>(c, d, xf_s);
             fk_mark(c, 5);
             csync();                                           // every warp's partial sums are in shared memory
             const bool lh = (kind == FKT_HEAD && !is_cp);
@@ -1643,10 +1592,9 @@ frame_kernel(const __grid_constant__ FkParams p) {
                     if (d.nrows <= 0) continue;
                     const uint32_t row_bytes = (uint32_t)d.K * 2u;
                     const char* srcb = reinterpret_cast<const char*>(W + d.img_off);
-                    // the O-projection slice (row-major) is staged in whole rows, the fragment-ordered images of the
-                    // tensor-core phases as a flat byte stream in full stages
+                    // the fragment-ordered image of the slice is staged as a flat byte stream in full stages
                     const uint32_t total = (uint32_t)d.nrows * row_bytes;
-                    const uint32_t sbytes = (op.kind == FKT_C) ? (uint32_t)d.rps * row_bytes : (uint32_t)FK_STAGE_BYTES;
+                    const uint32_t sbytes = (uint32_t)FK_STAGE_BYTES;
                     for (uint32_t off = 0; off < total && !stopped; off += sbytes) {
                         const unsigned slot = issued % (unsigned)NST, par = ((issued / (unsigned)NST) & 1u) ^ 1u;
                         unsigned long long t0 = 0;
