@@ -545,15 +545,15 @@ LQT_DEVINL uint32_t ring_wrap(uint32_t x) {
     if constexpr ((NST & (NST - 1)) == 0) return x & (RING - 1u);
     else { while (x >= RING) x -= RING; return x; }
 }
-// the blocks kt = w, w + 8, ... of one tile pair (or of the odd last tile): `iters` (even) blocks, two accumulator sets.
-// lin: ring offset of this lane's fragment of the first block; baddr / binc: this lane's B fragment and its stride
-// (lanes that hold the zero columns of B read one fixed zero word pair, stride 0): no predicates, no bounds checks.
+// blocks kt = ks, ks + wpp, ... of one tile pair (or of the odd last tile): `iters` (even) blocks, two accumulator sets.
+// lin: ring offset of this lane's fragment of the first block, step: bytes between consecutive blocks of this warp;
+// baddr / binc: this lane's B fragment and its stride (lanes that hold the zero columns of B read one fixed zero word
+// pair, stride 0): no predicates, no bounds checks.
 template <int NST, bool SINGLE>
-LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, uint32_t baddr, uint32_t binc, int iters) {
-    constexpr uint32_t STEP = (SINGLE ? 256u : 512u) * FK_CWARPS;
+LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, uint32_t step, uint32_t baddr, uint32_t binc, int iters) {
 #pragma unroll 1
     for (int it = 0; it < iters; it += 2) {
-        const uint32_t l1 = ring_wrap<NST>(lin + STEP);
+        const uint32_t l1 = ring_wrap<NST>(lin + step);
         uint4 a0, a1;
         if constexpr (SINGLE) {
             const uint2 t0 = lds64_s(ring_s + lin), t1 = lds64_s(ring_s + l1);
@@ -564,34 +564,42 @@ LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, ui
         const uint2 b0 = lds64_s(baddr), b1 = lds64_s(baddr + binc);
         mma_bf16_16816(acc[0], a0.x, a0.y, a0.z, a0.w, b0.x, b0.y);
         mma_bf16_16816(acc[1], a1.x, a1.y, a1.z, a1.w, b1.x, b1.y);
-        lin = ring_wrap<NST>(l1 + STEP);
+        lin = ring_wrap<NST>(l1 + step);
         baddr += 2u * binc;
     }
 }
+// warps per tile pair: the fewer pairs a slice has, the more warps split the K dimension of each (a power of two <= 8)
+LQT_DEVINL int mma_wpp(int nrows) {
+    const int npu = (nrows + 15) >> 4;
+    return npu <= 1 ? 8 : npu <= 2 ? 4 : npu <= 4 ? 2 : 1;
+}
 
+// Every warp takes ONE (tile pair, K slice) unit of the slice (a second one only if there are more than 8 pairs): the
+// per-unit overhead (stage waits, reduction, partial store) is paid once per warp and phase.
 template <int NST>
 LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d, const uint32_t xf_s) {
-    const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1;
+    const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1, npu = npair + (nt & 1);
     const uint32_t total = (uint32_t)d.nrows * (uint32_t)d.K * 2u;
     const int nst = (int)((total + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES);
     const uint32_t ring_s = smem_u32(FK_RING(c));
     const int g = c.lane >> 2, tg = c.lane & 3;
+    const int wpp = mma_wpp(d.nrows), ks = c.warp & (wpp - 1);
     // B fragments: lanes g < 3 hold the three planes; the others (zero columns of B) read a fixed pair of zero words
-    const uint32_t b0addr = (g < 3) ? xf_s + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)c.warp * 96u : smem_u32(&FK_SH(c)->zero8[0]);
-    const uint32_t binc = (g < 3) ? 96u * FK_CWARPS : 0u;
+    const uint32_t b0addr = (g < 3) ? xf_s + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)ks * 96u : smem_u32(&FK_SH(c)->zero8[0]);
+    const uint32_t binc = (g < 3) ? 96u * (uint32_t)wpp : 0u;
     const uint32_t ring0 = (c.stage_ctr % (unsigned)NST) * FK_STAGE_BYTES;       // ring offset of byte 0 of this slice
-    float* part = &FK_SH(c)->part[c.warp][0];
-    const int iters = nkt / FK_CWARPS;            // blocks per warp per tile pair (even: K % 256 == 0, checked by the host)
-    int cur = 0, seen = 0;                        // ring stages of this phase: [0, cur) released, [cur, seen) observed full
+    float* part = &FK_SH(c)->part[ks][0];
+    const int iters = nkt / wpp;                  // blocks per warp and unit (even: K % 256 == 0, checked by the host)
 #pragma unroll 1
-    for (int p = 0; p < npair + (nt & 1); ++p) {
+    for (int p = c.warp / wpp; p < npu; p += FK_CWARPS / wpp) {
         const bool single = p == npair;
-        const uint32_t base = (uint32_t)p * (uint32_t)nkt * 512u, end = base + (uint32_t)nkt * (single ? 256u : 512u);
-        const int st_last = (int)((end - 1u) / FK_STAGE_BYTES);
-        while (seen <= st_last) { wait_full(c, c.stage_ctr + seen, NST); ++seen; }
+        const uint32_t bsz = single ? 256u : 512u;
+        const uint32_t base = (uint32_t)p * (uint32_t)nkt * 512u, end = base + (uint32_t)nkt * bsz;
+        for (int st = (int)(base / FK_STAGE_BYTES); st <= (int)((end - 1u) / FK_STAGE_BYTES); ++st) wait_full(c, c.stage_ctr + st, NST);
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        if (single) mma_blocks<NST, true>(acc, ring_s, ring_wrap<NST>(ring0 + base + (uint32_t)c.warp * 256u + c.lane * 8u), b0addr, binc, iters);
-        else        mma_blocks<NST, false>(acc, ring_s, ring_wrap<NST>(ring0 + base + (uint32_t)c.warp * 512u + c.lane * 16u), b0addr, binc, iters);
+        const uint32_t lin = ring_wrap<NST>(ring0 + base + (uint32_t)ks * bsz + c.lane * (single ? 8u : 16u));
+        if (single) mma_blocks<NST, true>(acc, ring_s, lin, bsz * (uint32_t)wpp, b0addr, binc, iters);
+        else        mma_blocks<NST, false>(acc, ring_s, lin, bsz * (uint32_t)wpp, b0addr, binc, iters);
         // lane (g, tg): acc[.][0..1] = row g, columns 2tg, 2tg + 1; acc[.][2..3] = row g + 8. Columns 0..2 carry the planes.
         float v0 = (acc[0][0] + acc[1][0]) + (acc[0][1] + acc[1][1]);
         float v1 = (acc[0][2] + acc[1][2]) + (acc[0][3] + acc[1][3]);
@@ -601,26 +609,18 @@ LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d, const uint32_t xf_s) {
             part[p * 16 + g] = v0;
             if (!single) part[p * 16 + 8 + g] = v1;
         }
-        const int st_done = (int)(end / FK_STAGE_BYTES);         // stages that end at or before the end of this pair
-        while (cur < st_done) {
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + cur) % (unsigned)NST]);
-            ++cur;
-        }
     }
-    while (cur < nst) {
-        if (seen <= cur) { wait_full(c, c.stage_ctr + cur, NST); seen = cur + 1; }
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + cur) % (unsigned)NST]);
-        ++cur;
-    }
+    // this warp is done with every stage of the slice (those it never read included)
+    __syncwarp();
+    if (c.lane == 0)
+        for (int st = 0; st < nst; ++st) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + st) % (unsigned)NST]);
     c.stage_ctr += nst;
 }
-// sum of the eight warps' partials of row r (after the CTA barrier that follows gemv_mma)
-LQT_DEVINL float part_sum(FkCtx& c, int r) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < FK_CWARPS; ++w) t += FK_SH(c)->part[w][r];
+// sum of the K-slice partials of row r (after the CTA barrier that follows gemv_mma)
+LQT_DEVINL float part_sum(FkCtx& c, int r, int wpp) {
+    float t = FK_SH(c)->part[0][r];
+#pragma unroll 1
+    for (int w = 1; w < wpp; ++w) t += FK_SH(c)->part[w][r];
     return t;
 }
 
@@ -1027,7 +1027,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             if (c.tid < d.nrows) {
                 const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
                 const int tgt = c.tid / rpp;
-                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid), c.seq);
+                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid, mma_wpp(d.nrows)), c.seq);
             }
             reduce_partials(c, d, n_kv, rpp, in_res0 ? FK_RES0(c) : nullptr, FK_LAND(c) + c.land_a * FK_LAND_WORDS, S.x1);
             fk_mark(c, 6);
@@ -1119,16 +1119,17 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             float rs = 1.f;
             if (nw && (c.warp == 0 || lh)) rs = ss_rstd(c, H, p.eps);
             if (c.warp == 0) {
+                const int wpp = mma_wpp(d.nrows);
                 if (kind == FKT_D) {                           // rows 2q (gate), 2q + 1 (up) -> act[q]
                     const int q = c.lane;
                     if (2 * q < d.nrows) {
-                        const float gt = part_sum(c, 2 * q) * rs, up = part_sum(c, 2 * q + 1) * rs;
+                        const float gt = part_sum(c, 2 * q, wpp) * rs, up = part_sum(c, 2 * q + 1, wpp) * rs;
                         st_ll(S.act + (d.row0 >> 1) + q, silu_f(gt) * up, c.seq);
                     }
                 } else {
 #pragma unroll 1
                     for (int r = c.lane; r < d.nrows; r += 32) {
-                        const float v = part_sum(c, r) * rs;
+                        const float v = part_sum(c, r, wpp) * rs;
                         const int n = d.row0 + r;
                         if (kind == FKT_A) st_ll(S.qkv + n, v, c.seq);
                         else if (kind == FKT_E) st_ll(S.x + n, FK_SH(c)->x1own[r] + v, c.seq);
