@@ -1,36 +1,36 @@
 // Persistent frame kernel: loops A and B of the reference (src/tts_onnx.cpp:782-872) as ONE
-// cooperative launch per utterance (or per chunk of frames).
+// cluster launch per utterance (or per chunk of frames).
 //
 // Why one kernel: a frame is 31 dependent network passes (1 talker step + 15 predictor passes, each
-// followed by a draw) = ~460 dependent matrix-vector phases of ~1 us each. As separate launches the
-// HBM pipe drains at every kernel boundary (round-1 v1: 577 launches, 4.2 ms per frame).
-// Here every SM keeps one CTA resident:
+// followed by a draw) = ~475 dependent matrix-vector / attention phases of a few microseconds each. As
+// separate launches the HBM pipe drains at every kernel boundary (round-1 v1: 577 launches, 4.2 ms per
+// frame). Here every SM keeps one CTA resident (15 clusters of 8 CTAs on B200):
 //   * warp 8 (producer) walks the static weight schedule of the whole launch and streams this CTA's
-//     rows of every matrix into a shared-memory ring with 1-D TMA bulk copies
+//     slice of every matrix into a shared-memory ring with 1-D TMA bulk copies
 //     (cp.async.bulk + mbarrier complete_tx), running AHEAD of the math across phase boundaries.
-//     The weights are regrouped once at load time into per-CTA row-major images, so one stage of the
-//     ring = a few complete rows = one contiguous copy;
-//   * warps 0-7 (consumers) run the phases. A matrix-vector product is K-split over the 256 threads:
-//     thread t owns columns 4t..4t+3 of every 1024-column chunk, so its slice of the input vector lives
-//     in REGISTERS (polled straight from L2, no shared-memory staging, no barrier), the weights are read
-//     with conflict-free 8-byte shared loads, eight rows are reduced at a time with a transposing
-//     butterfly (9 shuffles for 8 rows) and the eight warp partials meet in shared memory: ONE CTA
-//     barrier per phase. RMSNorm is folded: the product runs on x*w_norm while the sum of squares
-//     travels with the partials, and 1/rms is applied in the epilogue (exact up to rounding order).
-//     (Round-1 v10 ran this on tcgen05 with M64N8K16 MMAs: K/16 dependent MMAs of ~46 cycles per phase
-//     plus bf16x3 operand staging made a phase 8-10 us; the FMA form is bounded by the shared-memory
-//     read of the weights, ~0.25 us per phase.);
-//   * there is NO grid barrier. Activations travel between CTAs as 8-byte (value, sequence) pairs
-//     written with one store each ("LL" exchange, as in NCCL's low-latency protocol): a reader polls
-//     the data itself until every word carries the sequence number of the phase that produces it.
-//     One L2 write + one L2 read per hop instead of fence + atomic + poll + fence.
-//     Every CTA executes the same numbered phases, so the expected number is always "previous phase";
-//     a CTA can run at most one phase ahead of the slowest one, which makes one buffer per phase
-//     kind race-free;
+//     The weights are regrouped once at load time into per-CTA images in mma A-fragment order, so the
+//     ring is filled by contiguous copies and read with one conflict-free 16-byte load per MMA;
+//   * warps 0-7 (consumers) run the phases. The kernel is bound by instruction issue and dependent
+//     latency on these 8 warps, not by bandwidth, so the matrix-vector products run on the tensor
+//     cores: mma.sync.m16n8k16 (bf16 x bf16 -> fp32) consumes a 16 x 16 weight block per instruction
+//     where the fp32-FMA form needed ~20 instructions per 16-byte load. The fp32 input vector is split
+//     into three bf16 planes (exact: 8 + 8 + 8 mantissa bits) that occupy three columns of the B
+//     operand (gemv_mma). RMSNorm is folded: the product runs on x*w_norm, 1/rms is applied in the
+//     epilogue. (Round-1 v10 ran the products on tcgen05: TMEM allocation, single-thread issue,
+//     commit/mbarrier and tcgen05.ld add several dependent latencies per phase, which is what a batch-1
+//     phase cannot afford; the synchronous warp-level MMA has none of that. tcgen05 returns with the
+//     batched path);
+//   * phases hand over through a grid counter (one arrival per CTA after it has ISSUED its stores, one
+//     polling lane per CTA); activations travel between CTAs as 8-byte (value, sequence) words ("LL"
+//     words, as in NCCL's low-latency protocol) that every reader validates, so no fence is needed; a
+//     vector that every CTA needs is fetched ONCE per cluster with a TMA multicast copy (mc_fetch), and
+//     the O-projection partials of the 8 kv groups are reduced through distributed shared memory;
 //   * the sampler and the embedding glue (src/tts_onnx.cpp:803-842, 854-868, 878-950) run redundantly
 //     in every CTA, so a draw costs no broadcast.
+// Code size matters: the layer loop must stay warm in the instruction cache (one shared routine per kind
+// of work; see tools/fk_codesize.py).
 // Phases per layer: QKV | [talker: split-KV attention] | O-projection by kv-group (the code predictor
-// computes its <=17-position attention inside this phase) | gate/up (SwiGLU) | down.
+// computes its <=16-position attention inside this phase) | gate/up (SwiGLU) | down.
 #pragma once
 #include "attention.cuh"
 #include "common.cuh"
@@ -45,7 +45,7 @@ extern __shared__ __align__(1024) unsigned char fk_smem[];     // the frame kern
 constexpr int FK_CWARPS = 8;
 constexpr int FK_CTHREADS = FK_CWARPS * 32;       // consumer threads
 constexpr int FK_THREADS = FK_CTHREADS + 128;     // + one producer warpgroup (one lane works; a whole warpgroup so that setmaxnreg can hand its registers over)
-constexpr int FK_STAGE_BYTES = 32 * 1024;         // 16 rows of K=1024, 5 rows of K=3072, 64 rows of K=256
+constexpr int FK_STAGE_BYTES = 32 * 1024;         // one ring stage: a slice's fragment-ordered image is streamed as a flat byte stream
 constexpr int FK_CLUSTER = 8;                     // CTAs per thread-block cluster (multicast + DSMEM domain)
 constexpr int FK_LAND_WORDS = 3072;               // landing buffer of a multicast vector fetch (LL words), two of them
 constexpr int FK_X1OWN = 16;                      // max rows of the down projection per CTA
@@ -191,9 +191,10 @@ LQT_DEVINL uint2 ld_ll1(const uint2* p) {
 // ------------------------------------------------------------------------------------------------
 struct FkDesc {                 // this CTA's weight slice of one phase kind
     int row0, nrows, K, RG;
-    int rps;                    // rows per ring stage
+    int nst;                    // ring stages of the slice (flat byte stream, FK_STAGE_BYTES each)
     unsigned img_off;           // element offset of this CTA's image inside the matrix image
-    int pad0_, pad1_;
+    int lw;                     // log2(warps per tile pair) of the tensor-core product (gemv_mma)
+    int rpp;                    // O-projection: rows reduced per cluster partner
 };
 struct FkShared {
     uint64_t full[16];
@@ -286,9 +287,10 @@ LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, in
     }
     FkDesc d;
     d.row0 = s.row0; d.nrows = s.nrows; d.K = K; d.RG = RG;
-    d.rps = max(1, FK_STAGE_BYTES / (K * 2));
+    d.nst = (int)(((unsigned)s.nrows * (unsigned)K * 2u + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES);
     d.img_off = (unsigned)cta * (unsigned)rmax * (unsigned)K;
-    d.pad0_ = 0; d.pad1_ = 0;
+    { const int npu = (s.nrows + 15) >> 4; d.lw = npu <= 1 ? 3 : npu <= 2 ? 2 : npu <= 4 ? 1 : 0; }   // the fewer pairs, the more warps split K
+    d.rpp = (s.nrows + S.kv_heads - 1) / S.kv_heads;
     return d;
 }
 
@@ -408,81 +410,8 @@ LQT_DEVINL void wait_full(FkCtx& c, unsigned st, int nstages) {
     }
 }
 
-// sums of 8 values over the 32 lanes with a transposing butterfly: on return every lane holds the
-// full-warp sum of a[lane >> 2] (9 shuffles instead of 40)
-LQT_DEVINL float reduce8(const float (&a)[8], int lane) {
-    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-    float q[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = b4 ? a[i] : a[i + 4], keep = b4 ? a[i + 4] : a[i];
-        q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    float d[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b3 ? q[i] : q[i + 2], keep = b3 ? q[i + 2] : q[i];
-        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    const float send = b2 ? d[0] : d[1], keep = b2 ? d[1] : d[0];
-    float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    return s;
-}
-
-// Blackwell packed fp32 FMA (FFMA2): two independent fp32 FMAs per instruction on 64-bit register pairs. A u32 holding two
-// bf16 weights unpacks into the pair (w << 16, w & 0xffff0000) = (element 0, element 1); the accumulator pair holds the
-// partial sums of the even and of the odd columns.
-LQT_DEVINL unsigned long long pack2(uint32_t lo, uint32_t hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-    return r;
-}
-LQT_DEVINL unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-LQT_DEVINL unsigned long long bf16x2_to_f32x2(uint32_t u) { return pack2(u << 16, u & 0xffff0000u); }
-LQT_DEVINL float sum2(unsigned long long v) {
-    uint32_t lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-    return __uint_as_float(lo) + __uint_as_float(hi);
-}
-
 // ------------------------------------------------------------------------------------------------
-// Row-per-warp matrix-vector product (all phases except the grouped O-projection, which has its own below).
-// Row group q (RG = 1 row, or RG = 2 for a gate/up pair) belongs to warp q % 8; the 32 lanes split K
-// (lane l owns columns 256*i + 8*l .. +7 of every 1024-column chunk: conflict-free 16-byte shared loads),
-// the input vector is read from its plain copy in shared memory (xp), and up to eight dot products per
-// warp are reduced with warp shuffles. On return lane s (< 8) holds the sum of slot s:
-// slot s = (q / 8) * RG + t  <->  row ((s / RG) * 8 + warp) * RG + t.
-// No cross-warp reduction, no CTA barrier: the epilogue runs on the lanes that hold the sums.
-// ------------------------------------------------------------------------------------------------
-// sums of 4 values over the 32 lanes: on return every lane holds the full-warp sum of a[lane >> 3] (6 shuffles)
-LQT_DEVINL float reduce4(const float (&a)[4], int lane) {
-    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
-    float d[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b4 ? a[i] : a[i + 2], keep = b4 ? a[i + 2] : a[i];
-        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    const float send = b3 ? d[0] : d[1], keep = b3 ? d[1] : d[0];
-    float s = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    return s;
-}
-
-// ring stage of row r of a slice with rps rows per stage, for slices of at most four stages (checked by the host):
-// three compares instead of an integer division (~150 cycles, and several per batch)
-LQT_DEVINL int stage_of(int r, int rps) { return (r >= rps ? 1 : 0) + (r >= 2 * rps ? 1 : 0) + (r >= 3 * rps ? 1 : 0); }
-
-// ------------------------------------------------------------------------------------------------
-// Tensor-core matrix-vector product (every phase except the grouped O-projection).
+// Tensor-core matrix-vector product (every matrix phase, the grouped O-projection included).
 // The kernel is bound by instruction issue on its 8 consumer warps, not by bandwidth: with fp32 FMAs every 16-byte shared load
 // of weights costs ~20 instructions (bf16 -> fp32 unpacking + FFMA2). One mma.sync.m16n8k16 (bf16 x bf16 -> fp32) consumes a
 // 16 x 16 weight block per instruction instead. Exactness is kept by splitting the fp32 input vector into three bf16 planes
@@ -493,8 +422,8 @@ LQT_DEVINL int stage_of(int r, int rps) { return (r >= rps ? 1 : 0) + (r >= 2 * 
 //    stored contiguously, [p][kt][lane][a0 a1 a2 a3]; an odd last tile stores [kt][lane][a0 a2] (rows 8..15 of the operand are
 //    zero registers). No padding: image bytes = rows * K * 2. One 16-byte shared load per lane per MMA, conflict-free.
 //  * Input vector: B fragments in shared memory, [kt][plane][tg][b0 b1] (96 bytes per kt), written by the staging code.
-//  * Warp w takes the blocks kt = w, w + 8, ... of every tile pair (K split over the warps), two accumulator sets in flight;
-//    its partial sums go to part[w][row], one thread per row adds the eight partials in the epilogue.
+//  * Every warp takes ONE (tile pair, K slice) unit: the fewer pairs a slice has, the more warps split the K dimension of each
+//    (FkDesc.lw). Partial sums go to part[K slice][row]; one thread per row adds them in the epilogue.
 // ------------------------------------------------------------------------------------------------
 LQT_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -568,30 +497,24 @@ LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, ui
         baddr += 2u * binc;
     }
 }
-// warps per tile pair: the fewer pairs a slice has, the more warps split the K dimension of each (a power of two <= 8)
-LQT_DEVINL int mma_wpp(int nrows) {
-    const int npu = (nrows + 15) >> 4;
-    return npu <= 1 ? 8 : npu <= 2 ? 4 : npu <= 4 ? 2 : 1;
-}
 
 // Every warp takes ONE (tile pair, K slice) unit of the slice (a second one only if there are more than 8 pairs): the
 // per-unit overhead (stage waits, reduction, partial store) is paid once per warp and phase.
 template <int NST>
 LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d, const uint32_t xf_s) {
     const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1, npu = npair + (nt & 1);
-    const uint32_t total = (uint32_t)d.nrows * (uint32_t)d.K * 2u;
-    const int nst = (int)((total + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES);
+    const int nst = d.nst;
     const uint32_t ring_s = smem_u32(FK_RING(c));
     const int g = c.lane >> 2, tg = c.lane & 3;
-    const int wpp = mma_wpp(d.nrows), ks = c.warp & (wpp - 1);
+    const int wpp = 1 << d.lw, ks = c.warp & (wpp - 1);         // warps per tile pair (a power of two, make_desc)
     // B fragments: lanes g < 3 hold the three planes; the others (zero columns of B) read a fixed pair of zero words
     const uint32_t b0addr = (g < 3) ? xf_s + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)ks * 96u : smem_u32(&FK_SH(c)->zero8[0]);
     const uint32_t binc = (g < 3) ? 96u * (uint32_t)wpp : 0u;
     const uint32_t ring0 = (c.stage_ctr % (unsigned)NST) * FK_STAGE_BYTES;       // ring offset of byte 0 of this slice
     float* part = &FK_SH(c)->part[ks][0];
-    const int iters = nkt / wpp;                  // blocks per warp and unit (even: K % 256 == 0, checked by the host)
+    const int iters = nkt >> d.lw;                  // blocks per warp and unit (even: K % 256 == 0, checked by the host)
 #pragma unroll 1
-    for (int p = c.warp / wpp; p < npu; p += FK_CWARPS / wpp) {
+    for (int p = c.warp >> d.lw; p < npu; p += FK_CWARPS >> d.lw) {
         const bool single = p == npair;
         const uint32_t bsz = single ? 256u : 512u;
         const uint32_t base = (uint32_t)p * (uint32_t)nkt * 512u, end = base + (uint32_t)nkt * bsz;
@@ -1018,7 +941,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             else       talker_attn_combine(c, ps.pos0, want);
             fk_mark(c, 3);
             if (FK_SH(c)->aborted) { c.aborted = true; break; }
-            const int rpp = (d.nrows + n_kv - 1) / n_kv;
+            const int rpp = d.rpp;
             gemv_mma<NST>(c, d, smem_u32(FK_XS(c)));
             fk_mark(c, 5);
             csync();                                           // every warp's partial sums are in shared memory
@@ -1027,7 +950,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             if (c.tid < d.nrows) {
                 const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
                 const int tgt = c.tid / rpp;
-                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid, mma_wpp(d.nrows)), c.seq);
+                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid, 1 << d.lw), c.seq);
             }
             reduce_partials(c, d, n_kv, rpp, in_res0 ? FK_RES0(c) : nullptr, FK_LAND(c) + c.land_a * FK_LAND_WORDS, S.x1);
             fk_mark(c, 6);
@@ -1119,7 +1042,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             float rs = 1.f;
             if (nw && (c.warp == 0 || lh)) rs = ss_rstd(c, H, p.eps);
             if (c.warp == 0) {
-                const int wpp = mma_wpp(d.nrows);
+                const int wpp = 1 << d.lw;
                 if (kind == FKT_D) {                           // rows 2q (gate), 2q + 1 (up) -> act[q]
                     const int q = c.lane;
                     if (2 * q < d.nrows) {
