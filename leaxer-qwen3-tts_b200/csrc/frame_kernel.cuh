@@ -245,11 +245,18 @@ struct FkCtx {
 //  0 phase begin   2 inputs in registers (polling done)   3 inputs complete (attention / staging done; before the GEMV)
 //  4 glue done (sampler phases)   5 weights consumed (all FMAs done)   6 outputs published
 enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_SAMPLE = 7, FKT_INPROJ = 8 };
+// The marks are compiled only into the profiling build (liblqt_b200_prof.so, -DFK_MARKS; tools/fk_timeline.py loads it through
+// $LQT_B200_LIB): even disabled, ~10 mark sites per phase cost ~2 % of the frame in this issue-bound kernel.
+#ifdef FK_MARKS
 LQT_DEVINL void fk_mark(FkCtx& c, int point) {
     if (c.dbg && c.tid == 0 && c.dbg_n < c.dbg_cap)
         c.dbg[c.dbg_n++] = ((unsigned long long)clock64() << 16) | (unsigned)(c.dbg_tag | point);
 }
 LQT_DEVINL void fk_phase(FkCtx& c, int stack, int kind) { c.dbg_tag = (stack << 9) | (kind << 4); }
+#else
+LQT_DEVINL void fk_mark(FkCtx&, int) {}
+LQT_DEVINL void fk_phase(FkCtx&, int, int) {}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // weight slices: which rows of a matrix this CTA owns (identical arithmetic in producer and consumers)

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblqt_b200.so")
+LIB_PATH = os.environ.get("LQT_B200_LIB") or os.path.join(_HERE, "csrc", "liblqt_b200.so")   # $LQT_B200_LIB: the profiling build
 
 LANG_CODEC_ID = {"auto": 0, "en": 2050, "zh": 2051, "ja": 2052, "ko": 2053}   # tts_onnx.h:230-238
 

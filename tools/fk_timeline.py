@@ -12,6 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("LQT_B200_LIB", os.path.join(ROOT, "leaxer-qwen3-tts_b200", "csrc", "liblqt_b200_prof.so"))   # the build with timeline marks
 from __graft_entry__ import load_package  # noqa: E402
 
 load_package()

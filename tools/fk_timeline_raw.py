@@ -1,5 +1,7 @@
 import sys, os
 sys.path.insert(0, '/root/repo')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("LQT_B200_LIB", os.path.join(ROOT, "leaxer-qwen3-tts_b200", "csrc", "liblqt_b200_prof.so"))   # the build with timeline marks
 from __graft_entry__ import load_package
 load_package()
 from leaxer_qwen3_tts_b200 import engine, modelspec as ms
@@ -15,7 +17,7 @@ eng.generate(prompt, trailing, pad, sp)
 clk, tag = eng.timeline_read()
 KINDS = {1: "A", 2: "B", 3: "C", 4: "D", 5: "E", 6: "head", 7: "sample", 8: "inproj"}
 n = len(clk)
-start = n - 400
+start = n - (int(sys.argv[2]) if len(sys.argv) > 2 else 400)
 for i in range(start, start + 150):
     st, kind, pt = (tag[i] >> 9) & 1, (tag[i] >> 4) & 31, tag[i] & 15
     print(f"{'cp' if st else 'tk'} {KINDS.get(kind, kind):6s} pt{pt:2d}  +{int(clk[i]) - int(clk[i-1]):6d} cyc")
