@@ -948,6 +948,7 @@ int fk_init(lqt_engine* h) {
         if (FK_CLUSTER % s.kv_heads || FK_CLUSTER % s.cp_kv_heads) { h->err = "frame kernel: kv heads must divide the cluster size (8)"; return 1; }
         const int rpp_t = (fk_rmax(s.hidden, 1, 2, s.kv_heads, nc) + s.kv_heads - 1) / s.kv_heads, rpp_c = (fk_rmax(s.cp_hidden, 1, 2, s.cp_kv_heads, nc) + s.cp_kv_heads - 1) / s.cp_kv_heads;
         if (std::max(rpp_t, rpp_c) > FK_RPP_MAX) { h->err = "frame kernel: too many O-projection rows per SM"; return 1; }
+        if (std::max(fk_rmax(s.hidden, 1, 2, s.kv_heads, nc), fk_rmax(s.cp_hidden, 1, 2, s.cp_kv_heads, nc)) > FK_PART_ROWS) { h->err = "frame kernel: too many O-projection rows per SM"; return 1; }
         if ((s.heads / s.kv_heads) * ATT_D > FK_XS_STRIDE || (s.cp_heads / s.cp_kv_heads) * ATT_D > FK_XS_STRIDE || s.heads != 2 * s.kv_heads || s.cp_heads != 2 * s.cp_kv_heads) {
             h->err = "frame kernel: needs 2 query heads per kv head"; return 1;
         }

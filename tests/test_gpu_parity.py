@@ -247,6 +247,35 @@ def test_generate_seeded_sampler_token_exact(request, which, frames):
     assert np.array_equal(codes, ref_codes), np.argwhere(codes != ref_codes)[:4]
 
 
+@pytest.mark.parametrize("clusters", [13, 14])
+def test_generate_other_grid_sizes(request, full_dir, monkeypatch, clusters):
+    """The weight slices (whole 8-row tiles per CTA, tile pairs, K split per warp) depend on the number of co-resident
+    clusters: 13 and 14 clusters give other tile counts, single tiles and K splits than the default 15 (fewer than 13
+    clusters exceed the per-CTA row limits and fall back to the graph path). Seeded sampling
+    must stay token-exact against the oracle, and the logits within tolerance."""
+    from leaxer_qwen3_tts_b200 import engine
+    m = request.getfixturevalue("full_oracle")
+    orc = request.getfixturevalue("oracle_mod")
+    monkeypatch.setenv("LQT_FK_CLUSTERS", str(clusters))
+    eng = engine.Engine(full_dir, device=0)
+    try:
+        frames = 3
+        ids = orc.wrap_text_ids([1000, 2000, 3000, 4000, 5000, 6000])
+        sp_o = orc.SamplingParams(temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=frames, seed=1234, utterance_id=3)
+        eng.reset_stats()
+        ref_codes, tr, (codes, tb) = _run_generate(eng, m, orc, ids, "auto", sp_o, eng.sampling(0.8, 50, 0.95, frames, 1234, 3))
+        assert eng.stats().kernel_launches < 40, "the persistent kernel did not run (graph fallback?)"
+        assert np.array_equal(codes, ref_codes), np.argwhere(codes != ref_codes)[:4]
+        V, Vs = m.spec.vocab, m.spec.cp_vocab
+        for f in range(frames):
+            ref0 = np.asarray(tr["talker_logits"][f])
+            fin = np.isfinite(ref0)
+            assert maxabs(tb[f, 0, :V][fin], ref0[fin]) < LOGIT_TOL
+            assert maxabs(tb[f, 1:, :Vs], tr["cp_logits"][f]) < LOGIT_TOL
+    finally:
+        eng.close()
+
+
 def test_teacher_forced_logits(request):
     """feed the oracle's tokens; logits of every one of the 16 draws per frame stay within tolerance
     and the argmax agrees wherever the oracle's top-2 margin exceeds the tolerance"""
