@@ -440,8 +440,14 @@ void launch_conv_gemm(lqt_engine* h, ConvGemmParams p) {
     if (p.bias_mod <= 0) p.bias_mod = p.N;
     if (p.dil <= 0) p.dil = 1;
     if (p.taps <= 0) p.taps = 1;
-    dim3 grid((p.L + CG_BM - 1) / CG_BM, (p.N + CG_BN - 1) / CG_BN);
-    conv_gemm_kernel<<<grid, CG_THREADS, 0, h->stream>>>(p);
+    static const bool no_mma = getenv("LQT_CONV_FP32") != nullptr;             // A/B aid: the CUDA-core kernel
+    if (!no_mma && p.Cin % 16 == 0) {                                       // tensor-core path (bf16x3 split activations, exact products)
+        dim3 grid((p.L + CM_BM - 1) / CM_BM, (p.N + CM_BN - 1) / CM_BN);
+        conv_gemm_mma_kernel<<<grid, CM_THREADS, 0, h->stream>>>(p);
+    } else {
+        dim3 grid((p.L + CG_BM - 1) / CG_BM, (p.N + CG_BN - 1) / CG_BN);
+        conv_gemm_kernel<<<grid, CG_THREADS, 0, h->stream>>>(p);
+    }
     h->stats.kernel_launches++;
 }
 

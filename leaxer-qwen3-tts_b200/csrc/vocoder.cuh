@@ -137,6 +137,133 @@ conv_gemm_kernel(const ConvGemmParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core version of conv_gemm_kernel (same parameters, Cin % 16 == 0): mma.sync.m16n8k16, bf16 weights as the B
+// operand, the fp32 activations as the A operand split into three bf16 planes (x = hi + mid + lo, remainders exact), so
+// every product is exact in fp32 and the result differs from the CUDA-core kernel only by summation order.
+// Block tile 128 positions x 64 outputs x 16 k, 8 warps x (16 x 64): 24 MMAs per warp and k-step, operands staged through
+// padded shared memory (row stride 24 bf16: conflict-free fragment loads), next slab prefetched into registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int CM_BM = 128, CM_BN = 64, CM_BK = 16, CM_LD = 24, CM_THREADS = 256, CM_FLUSH = 2;
+
+__device__ __forceinline__ void cm_split3(float x, unsigned short& h, unsigned short& m, unsigned short& l) {
+    const __nv_bfloat16 bh = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(bh);
+    const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(bm);
+    const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
+    h = __bfloat16_as_ushort(bh); m = __bfloat16_as_ushort(bm); l = __bfloat16_as_ushort(bl);
+}
+
+__global__ void __launch_bounds__(CM_THREADS)
+conv_gemm_mma_kernel(const ConvGemmParams p) {
+    __shared__ __align__(16) unsigned short As[3][CM_BM][CM_LD];
+    __shared__ __align__(16) unsigned short Bs[CM_BN][CM_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int m0 = blockIdx.x * CM_BM, n0 = blockIdx.y * CM_BN;
+    const int K = p.taps * p.Cin;
+
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+
+    const int a_row = tid >> 1, a_k = (tid & 1) * 8;            // 128 rows x 16 k: 8 consecutive k per thread
+    const int b_n = tid >> 1, b_k = (tid & 1) * 8;              // 64 n x 16 k (threads 0..127)
+    float4 a0, a1;
+    uint4 bw;
+    auto load_slab = [&](int k0) {
+        a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0;
+        const int pidx = m0 + a_row, k = k0 + a_k;
+        if (pidx < p.L) {
+            const int tap = k / p.Cin, c = k - tap * p.Cin;       // Cin % 16 == 0: the slab lies inside one tap
+            const int src = pidx + p.shift - (p.tap_rev ? tap : (p.taps - 1 - tap)) * p.dil;
+            if (src >= 0 && src < p.L) {
+                const float4* q = reinterpret_cast<const float4*>(p.x + (size_t)src * p.Cin + c);
+                a0 = q[0]; a1 = q[1];
+            }
+        }
+        bw = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < 128) {
+            const int n = n0 + b_n;
+            if (n < p.N) bw = *reinterpret_cast<const uint4*>(p.W + (size_t)n * K + k0 + b_k);
+        }
+    };
+    auto store_slab = [&]() {
+        const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        unsigned short h[8], m[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cm_split3(v[e], h[e], m[e], l[e]);
+        *reinterpret_cast<uint4*>(&As[0][a_row][a_k]) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+        *reinterpret_cast<uint4*>(&As[1][a_row][a_k]) = make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4] | (m[5] << 16), m[6] | (m[7] << 16));
+        *reinterpret_cast<uint4*>(&As[2][a_row][a_k]) = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+        if (tid < 128) *reinterpret_cast<uint4*>(&Bs[b_n][b_k]) = bw;
+    };
+
+    // The tensor core adds into its accumulator with truncation, a systematic error that grows with the number of chained MMAs
+    // (K up to 5376 here: 3e-4 relative). The MMAs therefore chain over CM_FLUSH k-steps only; the chunk sums are added to the
+    // running result with ordinary round-to-nearest FADDs.
+    float tacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { tacc[j][0] = 0.f; tacc[j][1] = 0.f; tacc[j][2] = 0.f; tacc[j][3] = 0.f; }
+    int since = 0;
+    load_slab(0);
+    for (int k0 = 0; k0 < K; k0 += CM_BK) {
+        store_slab();
+        __syncthreads();
+        if (k0 + CM_BK < K) load_slab(k0 + CM_BK);
+        uint32_t af[3][4];
+        const int r = warp * 16 + g;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            af[pl][0] = *reinterpret_cast<const uint32_t*>(&As[pl][r][tg * 2]);
+            af[pl][1] = *reinterpret_cast<const uint32_t*>(&As[pl][r + 8][tg * 2]);
+            af[pl][2] = *reinterpret_cast<const uint32_t*>(&As[pl][r][tg * 2 + 8]);
+            af[pl][3] = *reinterpret_cast<const uint32_t*>(&As[pl][r + 8][tg * 2 + 8]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Bs[j * 8 + g][tg * 2]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Bs[j * 8 + g][tg * 2 + 8]);
+#pragma unroll
+            for (int pl = 2; pl >= 0; --pl)                       // smallest plane first
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(tacc[j][0]), "+f"(tacc[j][1]), "+f"(tacc[j][2]), "+f"(tacc[j][3])
+                             : "r"(af[pl][0]), "r"(af[pl][1]), "r"(af[pl][2]), "r"(af[pl][3]), "r"(b0), "r"(b1));
+        }
+        if (++since == CM_FLUSH || k0 + CM_BK >= K) {
+            since = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { acc[j][e] += tacc[j][e]; tacc[j][e] = 0.f; }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int m = m0 + warp * 16 + g + hf * 8;
+            if (m >= p.L) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + j * 8 + tg * 2 + e;
+                if (n >= p.N) continue;
+                float v = acc[j][hf * 2 + e];
+                const int bn = n % p.bias_mod;
+                if (p.bias) v += p.bias[bn];
+                if (p.act == 1) v = silu_f(v);
+                else if (p.act == 3) v = gelu_erf_f(v);
+                if (p.scale) v *= p.scale[bn];
+                if (p.residual) v += p.residual[(size_t)m * p.N + n];
+                p.y[(size_t)m * p.N + n] = v;
+            }
+        }
+    }
+}
+
 // ---- RVQ dequantisation: gather-SUM per group (codebook order), output [T][Dc] each -------------
 __global__ void rvq_gather_kernel(const long long* __restrict__ codes, int T, int n_q,
                                   const __nv_bfloat16* __restrict__ cb_sem,   // [1][size][Dc]
