@@ -450,21 +450,30 @@ LQT_DEVINL void split3(float x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
     const __nv_bfloat16 l = __float2bfloat16_rn(r2);
     hi = (uint32_t)__bfloat16_as_ushort(h); mid = (uint32_t)__bfloat16_as_ushort(m); lo = (uint32_t)__bfloat16_as_ushort(l);
 }
+// two fp32 values -> three packed bf16x2 planes (low half = first value): one packed conversion per plane, exact remainders
+LQT_DEVINL void split3x2(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+    const __nv_bfloat162 bh = __floats2bfloat162_rn(x0, x1);
+    h = *reinterpret_cast<const uint32_t*>(&bh);
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+    const __nv_bfloat162 bm = __floats2bfloat162_rn(r0, r1);
+    m = *reinterpret_cast<const uint32_t*>(&bm);
+    const float q0 = r0 - __uint_as_float(m << 16), q1 = r1 - __uint_as_float(m & 0xffff0000u);
+    const __nv_bfloat162 bl = __floats2bfloat162_rn(q0, q1);
+    l = *reinterpret_cast<const uint32_t*>(&bl);
+}
 // this thread's four consecutive columns k..k+3 (k % 4 == 0) of the input vector -> B fragments
 LQT_DEVINL void stage_bfrag(uint32_t xf_s, int k, float x0, float x1, float x2, float x3) {
-    uint32_t h[4], m[4], l[4];
-    split3(x0, h[0], m[0], l[0]); split3(x1, h[1], m[1], l[1]); split3(x2, h[2], m[2], l[2]); split3(x3, h[3], m[3], l[3]);
+    uint32_t h0, m0, l0, h1, m1, l1;
+    split3x2(x0, x1, h0, m0, l0); split3x2(x2, x3, h1, m1, l1);
     const int kt = k >> 4, kk = k & 15;                          // kk in {0, 4, 8, 12}
     const uint32_t base = xf_s + (uint32_t)kt * 96u + (uint32_t)((kk & 7) >> 1) * 8u + (uint32_t)(kk >> 3) * 4u;   // (tg0, reg)
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base), "r"(h[0] | (h[1] << 16)) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 8u), "r"(h[2] | (h[3] << 16)) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 32u), "r"(m[0] | (m[1] << 16)) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 40u), "r"(m[2] | (m[3] << 16)) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 64u), "r"(l[0] | (l[1] << 16)) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 72u), "r"(l[2] | (l[3] << 16)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base), "r"(h0) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 8u), "r"(h1) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 32u), "r"(m0) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 40u), "r"(m1) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 64u), "r"(l0) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 72u), "r"(l1) : "memory");
 }
-
-// byte offset inside the ring (NST stages, consecutive in shared memory), reduced modulo the ring size
 // one column k of an input vector -> its three bf16 planes in the B-fragment layout
 LQT_DEVINL void stage_bfrag1(uint32_t xf_s, int k, float x) {
     uint32_t h, m, l;

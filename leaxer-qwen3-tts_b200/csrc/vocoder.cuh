@@ -146,13 +146,16 @@ conv_gemm_kernel(const ConvGemmParams p) {
 // ------------------------------------------------------------------------------------------------
 constexpr int CM_BM = 128, CM_BN = 64, CM_BK = 16, CM_LD = 24, CM_THREADS = 256, CM_FLUSH = 2;
 
-__device__ __forceinline__ void cm_split3(float x, unsigned short& h, unsigned short& m, unsigned short& l) {
-    const __nv_bfloat16 bh = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(bh);
-    const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(bm);
-    const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
-    h = __bfloat16_as_ushort(bh); m = __bfloat16_as_ushort(bm); l = __bfloat16_as_ushort(bl);
+// two fp32 values -> three packed bf16x2 planes (low half = first value); one packed conversion per plane, exact remainders
+__device__ __forceinline__ void cm_split3x2(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+    const __nv_bfloat162 bh = __floats2bfloat162_rn(x0, x1);
+    h = *reinterpret_cast<const uint32_t*>(&bh);
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+    const __nv_bfloat162 bm = __floats2bfloat162_rn(r0, r1);
+    m = *reinterpret_cast<const uint32_t*>(&bm);
+    const float q0 = r0 - __uint_as_float(m << 16), q1 = r1 - __uint_as_float(m & 0xffff0000u);
+    const __nv_bfloat162 bl = __floats2bfloat162_rn(q0, q1);
+    l = *reinterpret_cast<const uint32_t*>(&bl);
 }
 
 __global__ void __launch_bounds__(CM_THREADS)
@@ -190,13 +193,12 @@ conv_gemm_mma_kernel(const ConvGemmParams p) {
         }
     };
     auto store_slab = [&]() {
-        const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        unsigned short h[8], m[8], l[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) cm_split3(v[e], h[e], m[e], l[e]);
-        *reinterpret_cast<uint4*>(&As[0][a_row][a_k]) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-        *reinterpret_cast<uint4*>(&As[1][a_row][a_k]) = make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4] | (m[5] << 16), m[6] | (m[7] << 16));
-        *reinterpret_cast<uint4*>(&As[2][a_row][a_k]) = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+        uint32_t h[4], m[4], l[4];
+        cm_split3x2(a0.x, a0.y, h[0], m[0], l[0]); cm_split3x2(a0.z, a0.w, h[1], m[1], l[1]);
+        cm_split3x2(a1.x, a1.y, h[2], m[2], l[2]); cm_split3x2(a1.z, a1.w, h[3], m[3], l[3]);
+        *reinterpret_cast<uint4*>(&As[0][a_row][a_k]) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(&As[1][a_row][a_k]) = make_uint4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<uint4*>(&As[2][a_row][a_k]) = make_uint4(l[0], l[1], l[2], l[3]);
         if (tid < 128) *reinterpret_cast<uint4*>(&Bs[b_n][b_k]) = bw;
     };
 
