@@ -51,6 +51,8 @@ constexpr int FK_LAND_WORDS = 3072;               // landing buffer of a multica
 constexpr int FK_X1OWN = 16;                      // max rows of the down projection per CTA
 constexpr int FK_RPP_MAX = 16;                    // O-projection rows reduced per CTA (DSMEM)
 constexpr int FK_NS_MAX = 24;                     // max attention splits per kv group
+constexpr int FK_ATT_MIN_CHUNK = 32;              // positions per split at least (8 warps x 4 positions in flight): short contexts use few
+                                                  // splits, and the combine step reads one L2 round trip per four splits
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_PART_ROWS = 80;                  // max rows of a slice (64 for the flat phases, 72 for the O-projection of 15 clusters)
 constexpr int FK_TILE_ROWS = 8;                   // rows per weight tile of the tensor-core matrix-vector phases
@@ -603,7 +605,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     const FkParams& p = *c.p;
     const FkStack& S = p.talker;
     const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
-    const int n_pos = t + 1, chunk = (n_pos + ns - 1) / ns;
+    const int n_pos = t + 1, chunk = max(FK_ATT_MIN_CHUNK, (n_pos + ns - 1) / ns);
     const int j0 = s * chunk, j1 = min(n_pos, j0 + chunk);
     if (s >= ns || j0 >= j1) return;                           // idle split (short contexts / spare CTAs)
     const int PS = 1 << p.page_shift;
@@ -706,7 +708,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
 LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
     const FkParams& p = *c.p;
     const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
-    const int n_pos = t + 1, chunk = (n_pos + ns - 1) / ns, active = (n_pos + chunk - 1) / chunk;
+    const int n_pos = t + 1, chunk = max(FK_ATT_MIN_CHUNK, (n_pos + ns - 1) / ns), active = (n_pos + chunk - 1) / chunk;
     const int r = c.tid >> 7, d = c.tid & 127;
     float Mx = -INFINITY, num = 0.f, den = 0.f;
     for (int s0 = 0; s0 < active; s0 += 4) {
