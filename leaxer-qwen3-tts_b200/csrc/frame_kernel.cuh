@@ -559,10 +559,10 @@ LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d, const uint32_t xf_s) {
 }
 // sum of the K-slice partials of row r (after the CTA barrier that follows gemv_mma)
 LQT_DEVINL float part_sum(FkCtx& c, int r, int wpp) {
-    float t = FK_SH(c)->part[0][r];
-#pragma unroll 1
-    for (int w = 1; w < wpp; ++w) t += FK_SH(c)->part[w][r];
-    return t;
+    float v[FK_CWARPS];                            // all loads issued before the adds (this runs on the critical warp of every phase)
+#pragma unroll
+    for (int w = 0; w < FK_CWARPS; ++w) v[w] = (w < wpp) ? FK_SH(c)->part[w][r] : 0.f;
+    return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 }
 
 LQT_DEVINL float ss_rstd(FkCtx& c, int K, float eps) {
