@@ -8,6 +8,7 @@
 //   wav PATH              int32 sample rate (or -1) followed by the decoded samples
 //   resample N SRC DST    resample(N synthetic samples)
 //   tok VOCAB MERGES TEXT int32 token ids ("-" for a missing file: tokenizer without vocab/merges)
+//   melwav PATH           the clone front-end of src/tts_onnx.cpp:331-359: read_wav -> resample to 24 kHz -> log-mel [128][frames]
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -44,6 +45,19 @@ int main(int argc, char** argv) {
         mc.sample_rate = 24000; mc.n_fft = 1024; mc.hop_size = 256; mc.win_size = 1024; mc.num_mels = 128; mc.fmin = 0.0f; mc.fmax = 12000.0f;
         MelExtractor mel(mc);
         const std::vector<float> m = mel.extract(synth(std::atoi(argv[2]), static_cast<unsigned>(std::atoi(argv[3]))));
+        put_i(static_cast<int32_t>(mel.num_frames()));
+        put_f(m);
+        return 0;
+    }
+    if (cmd == "melwav" && argc >= 3) {
+        int sr = -1;
+        std::vector<float> a = read_wav(argv[2], sr);
+        if (a.empty()) { put_i(-1); return 0; }
+        if (sr != 24000) a = resample(a, sr, 24000);
+        MelConfig mc;
+        mc.sample_rate = 24000; mc.n_fft = 1024; mc.hop_size = 256; mc.win_size = 1024; mc.num_mels = 128; mc.fmin = 0.0f; mc.fmax = 12000.0f;
+        MelExtractor mel(mc);
+        const std::vector<float> m = mel.extract(a);
         put_i(static_cast<int32_t>(mel.num_frames()));
         put_f(m);
         return 0;

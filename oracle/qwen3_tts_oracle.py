@@ -18,8 +18,13 @@ PARITY PINNING STATUS
     nothing external can pin the numbers. Architecture follows the upstream Qwen3-TTS /
     Qwen3-Omni-talker family (transformers/models/qwen3_omni_moe/modeling_qwen3_omni_moe.py
     :2309-2481, :3283-3366, :3645-3778).
-  * host orchestration + sampler filters: pinned against the reference's own compiled
-    src/tts_onnx.cpp through oracle/ort_shim (see oracle/Makefile, tests/test_ref_host_pin.py).
+  * host orchestration + sampler filters: PINNED against the reference's own src/tts_onnx.cpp,
+    compiled unmodified against a stand-in onnxruntime_cxx_api.h (oracle/ort_shim/) whose
+    Session::Run dispatches to deterministic stub graphs: oracle/Makefile builds
+    oracle/_ref/tts_host_ref, tests/test_ref_host_pin.py runs this file's host logic over the same
+    stubs (oracle/stub_graphs.py) and requires the identical per-call trace (graph order, tensor
+    names, shapes, input digests: prompt rows, masks, KV round trip, trailing schedule, flattened
+    codes), identical tokens with --top-k 1, and bit-identical top-k / softmax / top-p results.
 
 Numerics: fp32 activations, weights are the bf16 values stored in the .lqw files upcast to fp32,
 talker K (post-norm, post-RoPE) and V rounded to bf16 when they enter the KV cache (north_star:
@@ -547,6 +552,15 @@ def synthesize_tokens(m: OracleModel, token_ids, lang: str = "auto", p: Sampling
         return None, codes_np
     audio, n = m.vocoder(codes_np)                                            # :430
     return audio.numpy()[:n].copy(), codes_np
+
+
+def extract_speaker_embedding(m, mel: np.ndarray) -> np.ndarray:
+    """src/tts_onnx.cpp:367-403 (run_speaker_encoder): the log-mel of the reference clip arrives [num_mels, frames]
+    row-major from io::MelExtractor (:331-359) and is transposed to [1, frames, num_mels] for the graph."""
+    mel = np.asarray(mel, dtype=np.float32)
+    assert mel.ndim == 2 and mel.shape[0] == 128                              # :371
+    mel_t = np.ascontiguousarray(mel.T)                                       # :375-380
+    return m.speaker_encoder(torch.from_numpy(mel_t)).numpy().copy()
 
 
 def synthetic_text_ids(n_text: int, seed: int = 1234):
