@@ -176,7 +176,11 @@ def run_reference_arm(a, mdir, token_ids):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": wall / a.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames, "parallelism": "cpu host cores, rank 0 only"},
+            "config": {"workload": WORKLOAD, "frames": frames, "frames_full_workload": a.frames,
+                       "frames_note": "each step is a bounded sample: the FIRST `frames` frames of the same utterance (prompt + prefill + frames + "
+                                      "vocoder), sized so that the run ends within minutes; the b200 arm runs all frames_full_workload frames. "
+                                      "Shorter runs flatter the CPU side (the reference's whole-KV copy per step grows with the position).",
+                       "parallelism": "cpu host cores, rank 0 only"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -184,6 +188,35 @@ def run_reference_arm(a, mdir, token_ids):
                     "(oracle/qwen3_tts_oracle.py) running the reference's schedule"}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def parity_check(eng, a) -> dict:
+    """Outside the timed region: the benchmarked configuration against the committed oracle golden
+    (tests/golden/c2_full_375.npz, written by tests/golden/make_c2_golden.py from oracle/qwen3_tts_oracle.py).
+    (1) teacher-forced over all 375 frames: the engine is fed the oracle's codes and its logits are compared at the stored
+    frames (north_star: <= 2e-2 max-abs); (2) free-running with the benchmark's sampler settings and Philox key (1234, 0):
+    length of the token-exact prefix (a draw within float noise of a CDF boundary ends it; tests/test_gpu_parity.py)."""
+    gpath = os.path.join(ROOT, "tests", "golden", "c2_full_375.npz")
+    if not (a.spec == "0.6b" and a.frames == 375 and os.path.exists(gpath)):
+        return {"parity_checked": False, "why": "no golden for this configuration (only BASELINE configs[1] has one)"}
+    g = np.load(gpath)
+    tol = 2e-2
+    prompt, trailing, pad = eng.build_prompt(g["token_ids"], "en")
+    sp = eng.sampling(0.8, 50, 0.95, 375, seed=4321, utterance_id=9)
+    codes, tb = eng.generate(prompt, trailing, pad, sp, forced_codes=g["codes"], trace=True)
+    worst = 0.0
+    for i, f in enumerate(g["frames"]):
+        ref0, refc = g["talker_logits"][i], g["cp_logits"][i]
+        fin = np.isfinite(ref0)
+        worst = max(worst, float(np.abs(tb[f, 0, :3072][fin] - ref0[fin]).max()), float(np.abs(tb[f, 1:, :2048] - refc).max()))
+    del tb
+    _, free = eng.synthesize_tokens(g["token_ids"], "en", 0.8, 50, 0.95, 375, 1234, 0)
+    diff = np.argwhere(free != g["codes"])
+    prefix = 375 if len(diff) == 0 else int(diff[0][0])
+    ok = bool(np.array_equal(codes, g["codes"]) and worst < tol and prefix >= 8)
+    return {"parity_checked": ok, "golden": "tests/golden/c2_full_375.npz (CPU oracle, 375 frames)",
+            "teacher_forced_frames": 375, "logit_frames_compared": int(len(g["frames"])), "max_abs_logit_err": worst,
+            "logit_tol": tol, "free_running_exact_prefix_frames": prefix}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,6 +230,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spec", default="0.6b", choices=["0.6b", "1.7b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the (untimed) comparison with the committed oracle golden")
     ap.add_argument("--cpu-frames", type=int, default=150, help="frames in the cpu_baseline sample (~10-30 s of CPU work)")
     ap.add_argument("--frame-impl", default="persistent", choices=["persistent", "graph"],
                     help="persistent = one cooperative kernel per utterance (default); graph = round-1 v1 schedule (A/B only)")
@@ -263,6 +297,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = parity_check(eng, a) if rank == 0 and not a.no_parity_check else None
+    if parity is not None:
+        log(f"[bench] parity: {parity}")
     for i in range(a.warmup):
         one_step(-1 - i)
     eng.reset_stats()
@@ -340,7 +377,11 @@ def main():
                    "kv_cache": "paged bf16", "frame_impl": a.frame_impl},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes * a.utterances),
                 "d2h_bytes_per_step": int((a.frames * spf * 4 + a.frames * 16 * 8) * a.utterances),
-                "ms_per_step": wall_max / a.steps * 1e3},
+                "ms_per_step": wall_max / a.steps * 1e3,
+                "first_audio_ms_p50": statistics.median(first_ms) if first_ms else None,
+                "full_utterance_ms_p50": wall_max / a.steps / a.utterances * 1e3},
+        "parity_checked": bool(parity and parity.get("parity_checked")),
+        "parity": parity,
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": roofline,

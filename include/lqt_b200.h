@@ -51,6 +51,9 @@ typedef struct lqt_stats {
     float    last_total_ms;       /* lqt_synthesize_tokens: CUDA-event time prompt build -> last vocoder kernel */
     float    first_audio_ms;      /* lqt_synthesize_tokens: CUDA-event time prompt build -> the first chunk of PCM (2 s) copied into
                                      the caller's buffer (chunked vocoding on a second stream); = last_total_ms when chunking is off */
+    int32_t  frame_impl_active;   /* the frame loop this handle actually runs: LQT_FRAME_PERSISTENT or LQT_FRAME_GRAPH */
+    int32_t  cooperative_launch;  /* 1 = the persistent kernel is launched with the cooperative attribute (co-residency guaranteed);
+                                     0 = refused by the driver/profiler: the second-stream first-audio overlap is then switched off */
 } lqt_stats;
 
 /* Engine options (lqt_create_ex). kv_dtype: LQT_KV_BF16 = paged bf16 talker KV cache (default,
@@ -60,7 +63,10 @@ enum { LQT_KV_BF16 = 0, LQT_KV_F32 = 1 };
 /* frame_impl: LQT_FRAME_PERSISTENT (default) = loops A+B run inside one persistent cooperative kernel
  * whose producer warp streams the weights with TMA bulk copies; LQT_FRAME_GRAPH = the round-1 v1
  * schedule (a CUDA graph of ~577 per-op kernels per frame), kept only for A/B measurements. */
-enum { LQT_FRAME_PERSISTENT = 0, LQT_FRAME_GRAPH = 1 };
+/* LQT_FRAME_AUTO = persistent where the model shape fits the kernel, else the graph (what lqt_create uses; the choice is
+ * reported in lqt_stats.frame_impl_active). An explicit LQT_FRAME_PERSISTENT is strict: lqt_create_ex FAILS with the reason
+ * instead of falling back. */
+enum { LQT_FRAME_PERSISTENT = 0, LQT_FRAME_GRAPH = 1, LQT_FRAME_AUTO = 2 };
 typedef struct lqt_options {
     int32_t kv_dtype;
     int32_t n_slots;      /* KV slots (utterances resident at once); 0 = default (2) */
@@ -73,6 +79,10 @@ typedef struct lqt_options {
 int lqt_create(const char* model_dir, int device_id, lqt_engine** out);
 int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, lqt_engine** out);
 const char* lqt_create_error(void);
+/* Header-only validation of one .lqw weight file (no GPU needed): 0 = well formed; otherwise non-zero and `err` (capacity
+ * err_cap, always NUL-terminated) says why. lqt_create runs the same checks on every file before any device allocation, then
+ * verifies the dtype and shape of every tensor against the model spec. */
+int lqt_check_model_file(const char* path, char* err, int32_t err_cap);
 void lqt_destroy(lqt_engine* h);
 const char* lqt_last_error(lqt_engine* h);
 int lqt_get_info(lqt_engine* h, lqt_info* out);

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "attention.cuh"
@@ -127,6 +128,8 @@ struct lqt_engine {
     cudaEvent_t ev_chunk = nullptr, ev_first = nullptr;
     int first_chunk = 25;                     // frames (2 s of audio); 0 = off; $LQT_FIRST_CHUNK
     float* chunk_audio_dev = nullptr; size_t chunk_audio_cap = 0;
+    float* chunk_audio_out = nullptr; int64_t chunk_audio_out_cap = 0;    // caller's buffer of the running lqt_synthesize_tokens call
+    bool chunk_pending = false;               // stream2 holds work of the current call (synchronised on every exit path)
     // persistent frame kernel (frame_kernel.cuh)
     int frame_impl = 0;                       // 0 = persistent kernel, 1 = v1 graph of kernels
     std::vector<void*> fk_allocs;             // regrouped weights, layer tables, activation buffers
@@ -161,26 +164,42 @@ namespace {
         }                                                                                          \
     } while (0)
 
+// A tensor the kernels will index with dimensions derived from the model spec: it must exist with exactly that dtype and
+// shape, otherwise a smaller vocab / hidden size or a wrong dtype in the file would become an out-of-bounds device read.
 template <typename T>
-const T* need(lqt_engine* h, const LqwFile& f, const std::string& name, bool& ok) {
+const T* need(lqt_engine* h, const LqwFile& f, const std::string& name, bool& ok, std::initializer_list<long long> dims) {
     const DevTensor* t = f.find(name);
-    if (!t) { h->err = "missing tensor " + name; ok = false; return nullptr; }
+    if (!t) { if (ok) h->err = "missing tensor " + name; ok = false; return nullptr; }
+    const int want_dt = std::is_same<T, float>::value ? 1 : 0;
+    bool same = t->dtype == want_dt && t->dims.size() == dims.size();
+    if (same) { size_t i = 0; for (long long d : dims) same = same && t->dims[i++] == d; }
+    if (!same) {
+        if (ok) {
+            std::string got, want;
+            for (auto d : t->dims) got += (got.empty() ? "" : "x") + std::to_string(d);
+            for (auto d : dims) want += (want.empty() ? "" : "x") + std::to_string(d);
+            h->err = "tensor " + name + ": expected " + (want_dt ? "f32 [" : "bf16 [") + want + "], file has " + (t->dtype ? "f32 [" : "bf16 [") + got + "]";
+        }
+        ok = false;
+        return nullptr;
+    }
     return reinterpret_cast<const T*>(t->ptr);
 }
 
-bool load_layers(lqt_engine* h, const LqwFile& f, const std::string& pre, int n, bool qk_norm, bool ls,
-                 std::vector<LayerW>& out) {
+// one decoder layer: hidden H, q width qd, kv width kvd, head dim D, MLP width I
+bool load_layers(lqt_engine* h, const LqwFile& f, const std::string& pre, int n, int H, int qd, int kvd, int D, int I,
+                 bool qk_norm, bool ls, std::vector<LayerW>& out) {
     bool ok = true;
     out.resize(n);
     for (int i = 0; i < n; ++i) {
         const std::string p = pre + "l" + std::to_string(i) + ".";
         LayerW& L = out[i];
-        L.ln1 = need<float>(h, f, p + "ln1", ok);   L.ln2 = need<float>(h, f, p + "ln2", ok);
-        L.wqkv = need<bf16>(h, f, p + "wqkv", ok);  L.wo = need<bf16>(h, f, p + "wo", ok);
-        L.wgate = need<bf16>(h, f, p + "wgate", ok); L.wup = need<bf16>(h, f, p + "wup", ok);
-        L.wdown = need<bf16>(h, f, p + "wdown", ok);
-        if (qk_norm) { L.qnorm = need<float>(h, f, p + "qnorm", ok); L.knorm = need<float>(h, f, p + "knorm", ok); }
-        if (ls) { L.ls1 = need<float>(h, f, p + "ls1", ok); L.ls2 = need<float>(h, f, p + "ls2", ok); }
+        L.ln1 = need<float>(h, f, p + "ln1", ok, {H});   L.ln2 = need<float>(h, f, p + "ln2", ok, {H});
+        L.wqkv = need<bf16>(h, f, p + "wqkv", ok, {qd + 2 * kvd, H});  L.wo = need<bf16>(h, f, p + "wo", ok, {H, qd});
+        L.wgate = need<bf16>(h, f, p + "wgate", ok, {I, H}); L.wup = need<bf16>(h, f, p + "wup", ok, {I, H});
+        L.wdown = need<bf16>(h, f, p + "wdown", ok, {H, I});
+        if (qk_norm) { L.qnorm = need<float>(h, f, p + "qnorm", ok, {D}); L.knorm = need<float>(h, f, p + "knorm", ok, {D}); }
+        if (ls) { L.ls1 = need<float>(h, f, p + "ls1", ok, {H}); L.ls2 = need<float>(h, f, p + "ls2", ok, {H}); }
     }
     return ok;
 }
@@ -486,6 +505,8 @@ int run_text_project(lqt_engine* h, const long long* ids_dev, int S, float* out)
 int build_prompt_device(lqt_engine* h, const int64_t* ids, int n, int lang_id, const float* spk_host,
                         int* P_out, int* trailing_len_out) {
     if (n < 5) { h->err = "token_ids must hold at least 5 ids (role x3, >=1 text, 2 trailer)"; return 1; }
+    // lang_id indexes codec_embed directly (:470-473): 0 = auto, else one of the language rows of the codec vocabulary
+    if (lang_id != 0 && (lang_id < 2048 || lang_id >= h->sp.vocab)) { h->err = "lang_codec_id out of range (0 = auto, else a codec id in [2048, vocab))"; return 1; }
     const int H = h->sp.hidden;
     const int n_text_rest = std::max(0, n - 6);              // ids[4 .. n-3]
     if (n_text_rest + 1 > h->sp.max_pos) { h->err = "text too long"; return 1; }
@@ -537,7 +558,10 @@ int build_prompt_device(lqt_engine* h, const int64_t* ids, int n, int lang_id, c
 }
 
 // tokenizer12hz_decode (src/tts_onnx.cpp:759-776) on device codes [T][16] -> audio_dev [T*spf]
-int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio) {
+int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, cudaStream_t vstream = nullptr) {
+    // every launch below goes to h->stream: a caller that wants another stream (the first-audio chunk) passes it here and the
+    // handle's stream is swapped for the duration of the enqueue only (one host thread per handle, include/lqt_b200.h)
+    struct StreamSwap { lqt_engine* h; cudaStream_t keep; StreamSwap(lqt_engine* e, cudaStream_t v) : h(e), keep(e->stream) { if (v) e->stream = v; } ~StreamSwap() { h->stream = keep; } } swap_(h, vstream);
     const Spec& s = h->sp;
     const int Dc = s.voc_codebook_dim, R = s.voc_rvq_out, Cv = s.voc_hidden, I = s.voc_inter;
     const int vqd = s.voc_heads * s.voc_head_dim;
@@ -715,7 +739,8 @@ int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sa
         // launch is split: prefill + the first chunk of frames, then the rest (the kernel resumes from GenState and the plain
         // logits/last_hidden copies), so that the chunk can be vocoded on a second stream while generation continues.
         CK(cudaEventRecord(h->ev0, h->stream));
-        const int chunk = (chunk_out && h->first_chunk > 0 && h->first_chunk < sp->max_new_tokens) ? h->first_chunk : 0;
+        // without a cooperative launch co-residency of the 120 CTAs is only assumed: never run the chunk vocoder beside them then
+        const int chunk = (chunk_out && h->fk_coop && h->first_chunk > 0 && h->first_chunk < sp->max_new_tokens) ? h->first_chunk : 0;
         if (chunk_out) *chunk_out = 0;
         if (chunk) {
             if (fk_launch(h, slot, 0, h->prompt_dev, P, chunk, trace)) return 1;
@@ -766,45 +791,46 @@ bool load_vocoder_weights(lqt_engine* h) {
     bool ok = true;
     const LqwFile& f = h->f_voc;
     const Spec& s = h->sp;
-    h->rvq_sem_cb = need<bf16>(h, f, "rvq.sem.codebook", ok);  h->rvq_sem_proj = need<bf16>(h, f, "rvq.sem.out_proj", ok);
-    h->rvq_aco_cb = need<bf16>(h, f, "rvq.aco.codebook", ok);  h->rvq_aco_proj = need<bf16>(h, f, "rvq.aco.out_proj", ok);
-    h->pre_conv_w = need<bf16>(h, f, "pre_conv.weight", ok);   h->pre_conv_b = need<float>(h, f, "pre_conv.bias", ok);
-    ok = load_layers(h, f, "pt.", s.voc_layers, false, true, h->vl) && ok;
-    h->v_norm = need<float>(h, f, "pt.norm", ok);
-    h->v_cos = need<float>(h, f, "pt.rope_cos", ok); h->v_sin = need<float>(h, f, "pt.rope_sin", ok);
+    const int Cv = s.voc_hidden, Dc = s.voc_codebook_dim, R = s.voc_rvq_out, vqd = s.voc_heads * s.voc_head_dim;
+    h->rvq_sem_cb = need<bf16>(h, f, "rvq.sem.codebook", ok, {1, s.voc_codebook_size, Dc});  h->rvq_sem_proj = need<bf16>(h, f, "rvq.sem.out_proj", ok, {R, Dc});
+    h->rvq_aco_cb = need<bf16>(h, f, "rvq.aco.codebook", ok, {s.cp_steps, s.voc_codebook_size, Dc});  h->rvq_aco_proj = need<bf16>(h, f, "rvq.aco.out_proj", ok, {R, Dc});
+    h->pre_conv_w = need<bf16>(h, f, "pre_conv.weight", ok, {Cv, 3, R});   h->pre_conv_b = need<float>(h, f, "pre_conv.bias", ok, {Cv});
+    ok = load_layers(h, f, "pt.", s.voc_layers, Cv, vqd, vqd, s.voc_head_dim, s.voc_inter, false, true, h->vl) && ok;
+    h->v_norm = need<float>(h, f, "pt.norm", ok, {Cv});
+    h->v_cos = need<float>(h, f, "pt.rope_cos", ok, {s.voc_max_pos, s.voc_head_dim / 2}); h->v_sin = need<float>(h, f, "pt.rope_sin", ok, {s.voc_max_pos, s.voc_head_dim / 2});
     for (size_t u = 0; u < s.voc_up_ratios.size(); ++u) {
         const std::string p = "up" + std::to_string(u) + ".";
         VocUpW U{};
         U.factor = s.voc_up_ratios[u];
-        U.tconv_w = need<bf16>(h, f, p + "tconv.weight", ok); U.tconv_b = need<float>(h, f, p + "tconv.bias", ok);
-        U.dw_w = need<float>(h, f, p + "dw.weight", ok); U.dw_b = need<float>(h, f, p + "dw.bias", ok);
-        U.ln_w = need<float>(h, f, p + "ln.weight", ok); U.ln_b = need<float>(h, f, p + "ln.bias", ok);
-        U.pw1_w = need<bf16>(h, f, p + "pw1.weight", ok); U.pw1_b = need<float>(h, f, p + "pw1.bias", ok);
-        U.pw2_w = need<bf16>(h, f, p + "pw2.weight", ok); U.pw2_b = need<float>(h, f, p + "pw2.bias", ok);
-        U.gamma = need<float>(h, f, p + "gamma", ok);
+        U.tconv_w = need<bf16>(h, f, p + "tconv.weight", ok, {U.factor, Cv, 1, Cv}); U.tconv_b = need<float>(h, f, p + "tconv.bias", ok, {Cv});
+        U.dw_w = need<float>(h, f, p + "dw.weight", ok, {7, Cv}); U.dw_b = need<float>(h, f, p + "dw.bias", ok, {Cv});
+        U.ln_w = need<float>(h, f, p + "ln.weight", ok, {Cv}); U.ln_b = need<float>(h, f, p + "ln.bias", ok, {Cv});
+        U.pw1_w = need<bf16>(h, f, p + "pw1.weight", ok, {4 * Cv, Cv}); U.pw1_b = need<float>(h, f, p + "pw1.bias", ok, {4 * Cv});
+        U.pw2_w = need<bf16>(h, f, p + "pw2.weight", ok, {Cv, 4 * Cv}); U.pw2_b = need<float>(h, f, p + "pw2.bias", ok, {Cv});
+        U.gamma = need<float>(h, f, p + "gamma", ok, {Cv});
         h->vup.push_back(U);
     }
-    h->dec_in_w = need<bf16>(h, f, "dec.conv_in.weight", ok); h->dec_in_b = need<float>(h, f, "dec.conv_in.bias", ok);
+    h->dec_in_w = need<bf16>(h, f, "dec.conv_in.weight", ok, {s.voc_decoder_dim, 7, Cv}); h->dec_in_b = need<float>(h, f, "dec.conv_in.bias", ok, {s.voc_decoder_dim});
     int cin = s.voc_decoder_dim;
     for (size_t b = 0; b < s.voc_up_rates.size(); ++b) {
         const std::string p = "dec.b" + std::to_string(b) + ".";
         VocBlockW B{};
         B.cin = cin; B.cout = cin / 2; B.stride = s.voc_up_rates[b];
-        B.snake_a = need<float>(h, f, p + "snake.alpha", ok); B.snake_b = need<float>(h, f, p + "snake.beta", ok);
-        B.tconv_w = need<bf16>(h, f, p + "tconv.weight", ok); B.tconv_b = need<float>(h, f, p + "tconv.bias", ok);
+        B.snake_a = need<float>(h, f, p + "snake.alpha", ok, {B.cin}); B.snake_b = need<float>(h, f, p + "snake.beta", ok, {B.cin});
+        B.tconv_w = need<bf16>(h, f, p + "tconv.weight", ok, {B.stride, B.cout, 2, B.cin}); B.tconv_b = need<float>(h, f, p + "tconv.bias", ok, {B.cout});
         for (int r = 0; r < 3; ++r) {
             const std::string q = p + "r" + std::to_string(r) + ".";
             auto& R = B.res[r];
-            R.s1a = need<float>(h, f, q + "snake1.alpha", ok); R.s1b = need<float>(h, f, q + "snake1.beta", ok);
-            R.c1w = need<bf16>(h, f, q + "conv1.weight", ok);  R.c1b = need<float>(h, f, q + "conv1.bias", ok);
-            R.s2a = need<float>(h, f, q + "snake2.alpha", ok); R.s2b = need<float>(h, f, q + "snake2.beta", ok);
-            R.c2w = need<bf16>(h, f, q + "conv2.weight", ok);  R.c2b = need<float>(h, f, q + "conv2.bias", ok);
+            R.s1a = need<float>(h, f, q + "snake1.alpha", ok, {B.cout}); R.s1b = need<float>(h, f, q + "snake1.beta", ok, {B.cout});
+            R.c1w = need<bf16>(h, f, q + "conv1.weight", ok, {B.cout, 7, B.cout});  R.c1b = need<float>(h, f, q + "conv1.bias", ok, {B.cout});
+            R.s2a = need<float>(h, f, q + "snake2.alpha", ok, {B.cout}); R.s2b = need<float>(h, f, q + "snake2.beta", ok, {B.cout});
+            R.c2w = need<bf16>(h, f, q + "conv2.weight", ok, {B.cout, 1, B.cout});  R.c2b = need<float>(h, f, q + "conv2.bias", ok, {B.cout});
         }
         h->vblk.push_back(B);
         cin /= 2;
     }
-    h->out_sa = need<float>(h, f, "dec.snake_out.alpha", ok); h->out_sb = need<float>(h, f, "dec.snake_out.beta", ok);
-    h->out_w = need<float>(h, f, "dec.conv_out.weight", ok);  h->out_b = need<float>(h, f, "dec.conv_out.bias", ok);
+    h->out_sa = need<float>(h, f, "dec.snake_out.alpha", ok, {cin}); h->out_sb = need<float>(h, f, "dec.snake_out.beta", ok, {cin});
+    h->out_w = need<float>(h, f, "dec.conv_out.weight", ok, {1, 7, cin});  h->out_b = need<float>(h, f, "dec.conv_out.bias", ok, {1});
     return ok;
 }
 
@@ -1047,8 +1073,12 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
         at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = h->fk_coop ? 2 : 1;
         cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
-        if (e != cudaSuccess && h->fk_coop) {          // cluster + cooperative rejected: all CTAs are co-resident anyway (grid = occupancy)
+        if (e != cudaSuccess && h->fk_coop) {
+            // cluster + cooperative rejected. The grid equals the occupancy limit, so all CTAs are co-resident as long as nothing
+            // else holds SMs: from here on the chunk vocoder is NOT overlapped on the second stream (fk_coop gates it in
+            // generate_core), and the device-side spin limit stays as the last guard.
             (void)cudaGetLastError();
+            fprintf(stderr, "[lqt] cooperative cluster launch refused (%s): launching without the attribute, first-audio overlap off\n", cudaGetErrorString(e));
             h->fk_coop = false; cfg.numAttrs = 1;
             e = cudaLaunchKernelExC(&cfg, fn, args);
         }
@@ -1130,19 +1160,22 @@ int init_engine(lqt_engine* h, const std::string& dir) {
     if ((s.hidden % 8) || (s.inter % 8) || (s.text_dim % 8)) { h->err = "dims must be multiples of 8"; return 1; }
 
     bool ok = true;
-    h->text_embed = need<bf16>(h, h->f_text, "embed", ok);
-    h->fc1w = need<bf16>(h, h->f_text, "fc1.weight", ok); h->fc1b = need<float>(h, h->f_text, "fc1.bias", ok);
-    h->fc2w = need<bf16>(h, h->f_text, "fc2.weight", ok); h->fc2b = need<float>(h, h->f_text, "fc2.bias", ok);
-    h->codec_embed = need<bf16>(h, h->f_codec, "embed", ok);
-    h->cp_embed = need<bf16>(h, h->f_cpe, "embed", ok);
-    ok = load_layers(h, h->f_talker, "", s.layers, true, false, h->tl) && ok;
-    h->t_norm = need<float>(h, h->f_talker, "norm", ok); h->t_head = need<bf16>(h, h->f_talker, "head", ok);
-    h->t_cos = need<float>(h, h->f_talker, "rope_cos", ok); h->t_sin = need<float>(h, h->f_talker, "rope_sin", ok);
-    ok = load_layers(h, h->f_cp, "", s.cp_layers, true, false, h->cl) && ok;
-    h->c_norm = need<float>(h, h->f_cp, "norm", ok); h->c_heads = need<bf16>(h, h->f_cp, "heads", ok);
-    h->c_cos = need<float>(h, h->f_cp, "rope_cos", ok); h->c_sin = need<float>(h, h->f_cp, "rope_sin", ok);
-    if (s.hidden != s.cp_hidden) {
-        h->c_inproj_w = need<bf16>(h, h->f_cp, "in_proj.weight", ok); h->c_inproj_b = need<float>(h, h->f_cp, "in_proj.bias", ok);
+    {
+        const int H0 = s.hidden, Hc0 = s.cp_hidden, D0 = s.head_dim;
+        h->text_embed = need<bf16>(h, h->f_text, "embed", ok, {s.text_vocab, s.text_dim});
+        h->fc1w = need<bf16>(h, h->f_text, "fc1.weight", ok, {s.text_dim, s.text_dim}); h->fc1b = need<float>(h, h->f_text, "fc1.bias", ok, {s.text_dim});
+        h->fc2w = need<bf16>(h, h->f_text, "fc2.weight", ok, {H0, s.text_dim}); h->fc2b = need<float>(h, h->f_text, "fc2.bias", ok, {H0});
+        h->codec_embed = need<bf16>(h, h->f_codec, "embed", ok, {s.vocab, H0});
+        h->cp_embed = need<bf16>(h, h->f_cpe, "embed", ok, {s.cp_steps, s.cp_vocab, H0});
+        ok = load_layers(h, h->f_talker, "", s.layers, H0, s.heads * D0, s.kv_heads * D0, D0, s.inter, true, false, h->tl) && ok;
+        h->t_norm = need<float>(h, h->f_talker, "norm", ok, {H0}); h->t_head = need<bf16>(h, h->f_talker, "head", ok, {s.vocab, H0});
+        h->t_cos = need<float>(h, h->f_talker, "rope_cos", ok, {s.max_pos, D0 / 2}); h->t_sin = need<float>(h, h->f_talker, "rope_sin", ok, {s.max_pos, D0 / 2});
+        ok = load_layers(h, h->f_cp, "", s.cp_layers, Hc0, s.cp_heads * D0, s.cp_kv_heads * D0, D0, s.cp_inter, true, false, h->cl) && ok;
+        h->c_norm = need<float>(h, h->f_cp, "norm", ok, {Hc0}); h->c_heads = need<bf16>(h, h->f_cp, "heads", ok, {s.cp_steps, s.cp_vocab, Hc0});
+        h->c_cos = need<float>(h, h->f_cp, "rope_cos", ok, {s.cp_max_pos, D0 / 2}); h->c_sin = need<float>(h, h->f_cp, "rope_sin", ok, {s.cp_max_pos, D0 / 2});
+        if (s.hidden != s.cp_hidden) {
+            h->c_inproj_w = need<bf16>(h, h->f_cp, "in_proj.weight", ok, {Hc0, H0}); h->c_inproj_b = need<float>(h, h->f_cp, "in_proj.bias", ok, {Hc0});
+        }
     }
     ok = load_vocoder_weights(h) && ok;
     if (!ok) return 1;
@@ -1189,13 +1222,16 @@ int init_engine(lqt_engine* h, const std::string& dir) {
     CK(cudaEventCreate(&h->ev_chunk)); CK(cudaEventCreate(&h->ev_first));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     if (const char* e = getenv("LQT_FIRST_CHUNK")) h->first_chunk = std::max(0, atoi(e));
-    if (h->frame_impl == 0 && fk_init(h)) {
-        // shapes the persistent kernel does not cover yet (e.g. the 1.7B talker: > 64 rows per CTA): run loops A+B as the
-        // CUDA graph of per-op sm_100a kernels instead (still device-only; there is no CPU path)
+    if (h->frame_impl != LQT_FRAME_GRAPH && fk_init(h)) {
+        // shapes the persistent kernel does not cover (e.g. the 1.7B talker: > 64 rows per CTA). An explicit request for the
+        // persistent kernel fails here, loudly; LQT_FRAME_AUTO runs loops A+B as the CUDA graph of per-op sm_100a kernels instead
+        // (still device-only; there is no CPU path) and says so in lqt_stats.frame_impl_active.
+        if (h->frame_impl == LQT_FRAME_PERSISTENT) { h->err = "persistent frame kernel unavailable for this model: " + h->err; return 1; }
         fprintf(stderr, "[lqt] persistent frame kernel unavailable (%s): using the graph-of-kernels frame loop\n", h->err.c_str());
         h->err.clear();
-        h->frame_impl = 1;
+        h->frame_impl = LQT_FRAME_GRAPH;
     }
+    if (h->frame_impl == LQT_FRAME_AUTO) h->frame_impl = LQT_FRAME_PERSISTENT;
     return 0;
 }
 
@@ -1209,7 +1245,15 @@ extern "C" {
 const char* lqt_create_error(void) { return g_create_error.c_str(); }
 
 int lqt_create(const char* model_dir, int device_id, lqt_engine** out) {
-    return lqt_create_ex(model_dir, device_id, nullptr, out);
+    lqt_options o{};
+    o.kv_dtype = LQT_KV_BF16; o.n_slots = 0; o.frame_impl = LQT_FRAME_AUTO;
+    return lqt_create_ex(model_dir, device_id, &o, out);
+}
+
+int lqt_check_model_file(const char* path, char* err, int32_t err_cap) {
+    const std::string e = path ? check_lqw(path) : std::string("null path");
+    if (err && err_cap > 0) { std::strncpy(err, e.c_str(), (size_t)err_cap - 1); err[err_cap - 1] = 0; }
+    return e.empty() ? 0 : 1;
 }
 
 int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, lqt_engine** out) {
@@ -1233,7 +1277,7 @@ int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, 
         if (opt->kv_dtype != LQT_KV_BF16 && opt->kv_dtype != LQT_KV_F32) { g_create_error = "bad kv_dtype"; delete h; return 1; }
         h->kv_f32 = opt->kv_dtype == LQT_KV_F32;
         if (opt->n_slots > 0) h->n_slots = opt->n_slots;
-        if (opt->frame_impl != LQT_FRAME_PERSISTENT && opt->frame_impl != LQT_FRAME_GRAPH) { g_create_error = "bad frame_impl"; delete h; return 1; }
+        if (opt->frame_impl != LQT_FRAME_PERSISTENT && opt->frame_impl != LQT_FRAME_GRAPH && opt->frame_impl != LQT_FRAME_AUTO) { g_create_error = "bad frame_impl"; delete h; return 1; }
         h->frame_impl = opt->frame_impl;
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1287,7 +1331,13 @@ int lqt_get_info(lqt_engine* h, lqt_info* o) {
     return 0;
 }
 
-int lqt_get_stats(lqt_engine* h, lqt_stats* o) { if (!h || !o) return 1; *o = h->stats; return 0; }
+int lqt_get_stats(lqt_engine* h, lqt_stats* o) {
+    if (!h || !o) return 1;
+    *o = h->stats;
+    o->frame_impl_active = h->frame_impl;
+    o->cooperative_launch = (h->frame_impl == LQT_FRAME_PERSISTENT && h->fk_coop) ? 1 : 0;
+    return 0;
+}
 int lqt_reset_stats(lqt_engine* h) { if (!h) return 1; h->stats = lqt_stats{}; return 0; }
 
 int lqt_text_project(lqt_engine* h, const int64_t* ids, int32_t S, float* out) {
@@ -1439,19 +1489,19 @@ int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float
     CK(cudaMemcpyAsync(in, mel_t, (size_t)frames * M * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     const long long n = (long long)frames * Cs;
     const int eb = (int)std::min<long long>((n + 255) / 256, 4096);
-    { ConvGemmParams p = cg(in, frames, M, need<bf16>(h, f, "in_conv.weight", ok), Cs, b); p.taps = 5; p.shift = 2; p.bias = need<float>(h, f, "in_conv.bias", ok);
+    { ConvGemmParams p = cg(in, frames, M, need<bf16>(h, f, "in_conv.weight", ok, {Cs, 5, M}), Cs, b); p.taps = 5; p.shift = 2; p.bias = need<float>(h, f, "in_conv.bias", ok, {Cs});
       if (!ok) return 1; launch_conv_gemm(h, p); }
     relu_add_kernel<<<eb, 256, 0, h->stream>>>(b, nullptr, a, n); h->stats.kernel_launches++;
     for (int i = 0; i < s.spk_layers; ++i) {
         const std::string q = "l" + std::to_string(i) + ".conv.";
-        ConvGemmParams p = cg(a, frames, Cs, need<bf16>(h, f, q + "weight", ok), Cs, b); p.taps = 3; p.shift = 1; p.bias = need<float>(h, f, q + "bias", ok);
+        ConvGemmParams p = cg(a, frames, Cs, need<bf16>(h, f, q + "weight", ok, {Cs, 3, Cs}), Cs, b); p.taps = 3; p.shift = 1; p.bias = need<float>(h, f, q + "bias", ok, {Cs});
         if (!ok) return 1;
         launch_conv_gemm(h, p);
         relu_add_kernel<<<eb, 256, 0, h->stream>>>(b, a, a, n); h->stats.kernel_launches++;
     }
     stat_pool_kernel<<<(Cs + 127) / 128, 128, 0, h->stream>>>(a, frames, Cs, pool); h->stats.kernel_launches++;
-    GemvParams g = gemv_params(need<bf16>(h, f, "fc.weight", ok), s.hidden, 2 * Cs, pool, o);
-    g.bias = need<float>(h, f, "fc.bias", ok);
+    GemvParams g = gemv_params(need<bf16>(h, f, "fc.weight", ok, {s.hidden, 2 * Cs}), s.hidden, 2 * Cs, pool, o);
+    g.bias = need<float>(h, f, "fc.bias", ok, {s.hidden});
     if (!ok) return 1;
     launch_gemv(h, g, false);
     CK(cudaGetLastError());
@@ -1565,31 +1615,43 @@ int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int
 // First-audio path (the reference vocodes once at the end, src/tts_onnx.cpp:430): every vocoder op is causal
 // (causal convs, causal sliding-window attention, right-trimmed transposed convs), so decoding the first `chunk` frames alone
 // gives exactly the first chunk * 1920 samples of the full decode. Runs on stream2 while the frame kernel generates the rest.
-static float* g_chunk_audio_out = nullptr; static int64_t g_chunk_audio_cap = 0;
 static int first_chunk_hook(lqt_engine* h, int chunk) {
     const size_t n = (size_t)chunk * h->sp.samples_per_frame;
-    if ((int64_t)n > g_chunk_audio_cap) return 0;
+    if (!h->chunk_audio_out || (int64_t)n > h->chunk_audio_out_cap) return 0;
     if (h->chunk_audio_cap < n) {
         if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
         CK(cudaMalloc((void**)&h->chunk_audio_dev, n * sizeof(float)));
         h->chunk_audio_cap = n;
     }
     CK(cudaStreamWaitEvent(h->stream2, h->ev_chunk, 0));
-    cudaStream_t main_stream = h->stream;
-    h->stream = h->stream2;                                   // the vocoder launches on h->stream
-    const int rc = run_vocoder(h, h->codes_dev, chunk, h->chunk_audio_dev);
-    h->stream = main_stream;
-    if (rc) return 1;
-    CK(cudaMemcpyAsync(g_chunk_audio_out, h->chunk_audio_dev, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
+    h->chunk_pending = true;
+    if (run_vocoder(h, h->codes_dev, chunk, h->chunk_audio_dev, h->stream2)) return 1;
+    CK(cudaMemcpyAsync(h->chunk_audio_out, h->chunk_audio_dev, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
     CK(cudaEventRecord(h->ev_first, h->stream2));             // first audio is in the caller's buffer
     return 0;
 }
+
+static int synthesize_tokens_impl(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
+                                  const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
+                                  int64_t* codes_out, int32_t* n_frames);
 
 int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
                           const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
                           int64_t* codes_out, int32_t* n_frames) {
     if (!h || !token_ids || !sp || !n_samples) return 1;
     cudaSetDevice(h->device);
+    h->chunk_audio_out = audio_out; h->chunk_audio_out_cap = audio_capacity; h->chunk_pending = false;
+    const int rc = synthesize_tokens_impl(h, token_ids, n_ids, lang_codec_id, speaker_embed, sp, audio_out, audio_capacity, n_samples, codes_out, n_frames);
+    // whatever happened above, no copy into the caller's buffer may still be in flight when this call returns
+    if (h->chunk_pending) { cudaStreamSynchronize(h->stream2); h->chunk_pending = false; }
+    if (rc) cudaStreamSynchronize(h->stream);
+    h->chunk_audio_out = nullptr; h->chunk_audio_out_cap = 0;
+    return rc;
+}
+
+static int synthesize_tokens_impl(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
+                                  const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
+                                  int64_t* codes_out, int32_t* n_frames) {
     *n_samples = 0;
     if (n_frames) *n_frames = 0;
     int P = 0, TL = 0;
@@ -1597,7 +1659,6 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     if (build_prompt_device(h, token_ids, n_ids, lang_codec_id, speaker_embed, &P, &TL)) return 1;
     int nf = 0, chunk = 0;
     h->stats.first_audio_ms = 0.f;
-    g_chunk_audio_out = audio_out; g_chunk_audio_cap = audio_capacity;
     if (generate_core(h, 0, P, TL, sp, 0, false, &nf, audio_out ? &chunk : nullptr, first_chunk_hook)) return 1;
     if (n_frames) *n_frames = nf;
     h->stats.last_total_ms = 0.f;

@@ -19,7 +19,7 @@ SYMBOLS = [
     "lqt_reset_stats", "lqt_text_project", "lqt_codec_embed", "lqt_code_predictor_embed",
     "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
-    "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange",
+    "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange", "lqt_check_model_file",
 ]
 
 
@@ -43,7 +43,11 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64),
                 ("last_generate_ms", C.c_float), ("last_vocoder_ms", C.c_float),
                 ("last_prefill_ms", C.c_float), ("last_frames", C.c_int32),
-                ("last_total_ms", C.c_float), ("first_audio_ms", C.c_float)]
+                ("last_total_ms", C.c_float), ("first_audio_ms", C.c_float),
+                ("frame_impl_active", C.c_int32), ("cooperative_launch", C.c_int32)]
+
+
+FRAME_IMPL = {"persistent": 0, "graph": 1, "auto": 2}      # include/lqt_b200.h LQT_FRAME_*
 
 
 _lib = None
@@ -90,6 +94,7 @@ def load_library():
     lib.lqt_build_prompt.argtypes = [P, P, I32, I32, P, P, C.POINTER(I32), P, C.POINTER(I32), P]
     lib.lqt_debug_timeline.argtypes = [P, I32, I32, P, I32]
     lib.lqt_debug_exchange.argtypes = [P, I32, P, I32]
+    lib.lqt_check_model_file.argtypes = [C.c_char_p, C.c_char_p, I32]
     _lib = lib
     return lib
 
@@ -119,6 +124,13 @@ class EngineError(RuntimeError):
     pass
 
 
+def check_model_file(path: str) -> str:
+    """Header-only validation of one .lqw file (no GPU): '' = well formed, else the reason."""
+    buf = C.create_string_buffer(512)
+    load_library().lqt_check_model_file(path.encode(), buf, 512)
+    return buf.value.decode()
+
+
 class Engine:
     """One engine = one GPU = one host thread at a time (same contract as the reference)."""
 
@@ -126,7 +138,7 @@ class Engine:
                  frame_impl: str = "persistent"):
         self.lib = load_library()
         h = C.c_void_p()
-        opt = Options({"bf16": 0, "f32": 1}[kv_dtype], n_slots, {"persistent": 0, "graph": 1}[frame_impl])
+        opt = Options({"bf16": 0, "f32": 1}[kv_dtype], n_slots, FRAME_IMPL[frame_impl])
         rc = self.lib.lqt_create_ex(model_dir.encode(), device, C.byref(opt), C.byref(h))
         if rc != 0 or not h:
             raise EngineError(self.lib.lqt_create_error().decode())

@@ -3,7 +3,8 @@
 //   -m/--model DIR  -p/--prompt TEXT  -o/--output PATH  --lang  --ref  --temp  --top-k  --top-p  --max-tokens  -h/--help
 // Unknown flags and flags without a value are ignored, -m and -p are required (exit 1 + usage), the model directory
 // must exist, the output's parent directory is created, synthesis failure / unwritable output -> exit 1.
-// Extension: --seed N (Philox seed; the reference's sampler is not reproducible), also $LEAXER_SEED.
+// Extensions: --seed N (Philox seed; the reference's sampler is not reproducible), also $LEAXER_SEED;
+// --dump-codes PATH (the generated codes, int64 [frames][16] raw, for parity tests).
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
@@ -24,6 +25,7 @@ struct Options {
     const char* output = "output.wav";
     const char* lang = "auto";
     const char* ref = nullptr;
+    const char* dump_codes = nullptr;
     float temperature = 0.8f, top_p = 0.95f;
     int top_k = 50, max_tokens = 2048;
     bool have_seed = false;
@@ -66,6 +68,7 @@ Options parse(int argc, char** argv) {
         else if (a == "--top-k") o.top_k = std::atoi(argv[++i]);
         else if (a == "--top-p") o.top_p = static_cast<float>(std::atof(argv[++i]));
         else if (a == "--max-tokens") o.max_tokens = std::atoi(argv[++i]);
+        else if (a == "--dump-codes") o.dump_codes = argv[++i];
         else if (a == "--seed") { o.seed = static_cast<unsigned>(std::strtoul(argv[++i], nullptr, 10)); o.have_seed = true; }
     }
     return o;
@@ -129,6 +132,13 @@ int main(int argc, char** argv) {
     if (audio.empty()) {
         std::fprintf(stderr, "Error: synthesis failed\n");
         return 1;
+    }
+    if (o.dump_codes) {
+        if (FILE* f = std::fopen(o.dump_codes, "wb")) {
+            const std::vector<int64_t>& c = engine.last_codes();
+            if (!c.empty()) std::fwrite(c.data(), sizeof(int64_t), c.size(), f);
+            std::fclose(f);
+        }
     }
     std::printf("Generated %.2f seconds of audio\n", static_cast<float>(audio.size()) / leaxer_qwen::config::SAMPLE_RATE);
     if (leaxer_qwen::io::write_wav_cli(o.output, audio, leaxer_qwen::config::SAMPLE_RATE) != 0) {

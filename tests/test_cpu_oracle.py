@@ -268,7 +268,7 @@ def test_struct_layouts_match_header():
     import ctypes as C
     from leaxer_qwen3_tts_b200 import engine
     assert C.sizeof(engine.Sampling) == 28 and C.sizeof(engine.Info) == 13 * 4 and C.sizeof(engine.Options) == 12
-    assert C.sizeof(engine.Stats) == 8 + 8 + 4 * 3 + 4 + 4 + 4   # incl. tail padding to 8
+    assert C.sizeof(engine.Stats) == 8 + 8 + 4 * 3 + 4 + 4 + 4 + 4 + 4   # 2 x u64, 3 x f32, i32, 2 x f32, 2 x i32 = 48
 
 
 def test_product_path_fails_loudly_without_gpu(tiny_dir):

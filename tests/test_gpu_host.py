@@ -73,3 +73,39 @@ def test_cli_voice_clone(tiny_engine, tiny_dir, host_env, tmp_path):
     r2 = subprocess.run([host_env["cli"], "-m", tiny_dir, "-p", "hello world", "--lang", "zh", "--ref", str(ref), "--max-tokens", "4",
                          "--seed", "7", "-o", str(wav2)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r2.returncode == 0 and np.array_equal(_read_pcm16(wav2)[1], pcm)
+
+
+@pytest.mark.parametrize("which", ["tiny", "full"])
+def test_clone_chain_matches_oracle(request, which, host_env, tmp_path):
+    """C3 end to end against the oracle: the same synthetic 3 s WAV goes (a) through the CLI
+    (read_wav -> resample -> log-mel -> lqt_speaker_encoder -> prompt row -> frame loop -> vocoder) and (b) through the
+    REFERENCE's own mel (oracle/_ref/io_dump_ref melwav, compiled from /root/reference/src/io) -> oracle.speaker_encoder
+    -> oracle.synthesize_tokens(speaker_embed=...). Codes must be identical, the WAV within PCM16 rounding.
+    Match: src/tts_onnx.cpp:264-403, 442-539."""
+    import ref_host_cases as rc
+    from oracle import qwen3_tts_oracle as orc
+    mdir = request.getfixturevalue(f"{which}_dir")
+    m = request.getfixturevalue(f"{which}_oracle")
+    tokdir = os.path.join(os.path.dirname(mdir), "models", "Qwen3-TTS-12Hz-0.6B-Base")
+    vp, mp = io_cases.write_tokenizer_files(tokdir)
+    text, frames, seed = "hello world speech", 12, 7
+    ref_wav = rc.write_ref_wav(str(tmp_path / "ref3s.wav"))
+    out = subprocess.run([host_env["dump"], "tok", vp, mp, text], check=True, stdout=subprocess.PIPE).stdout
+    ids = orc.wrap_text_ids(np.frombuffer(out, "<i4")[1:].tolist())
+    melbin = rc.IO_REF if os.path.exists(rc.IO_REF) else host_env["dump"]
+    mel = rc.ref_melwav(melbin, ref_wav)
+    assert mel.shape == (128, 278)
+    spk = orc.extract_speaker_embedding(m, mel)
+    sp = orc.SamplingParams(temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=frames, seed=seed, utterance_id=0)
+    ref_audio, ref_codes = orc.synthesize_tokens(m, ids, "zh", sp, speaker_embed=spk)
+    wav, dump = tmp_path / "clone.wav", tmp_path / "codes.i64"
+    r = subprocess.run([host_env["cli"], "-m", mdir, "-p", text, "--lang", "zh", "--ref", ref_wav, "--max-tokens", str(frames),
+                        "--seed", str(seed), "-o", str(wav), "--dump-codes", str(dump)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    codes = np.fromfile(str(dump), np.int64).reshape(-1, 16)
+    assert codes.shape == ref_codes.shape == (frames, 16)
+    assert np.array_equal(codes, ref_codes), np.argwhere(codes != ref_codes)[:4]
+    rate, pcm = _read_pcm16(wav)
+    want = _pcm16(ref_audio)
+    assert rate == 24000 and pcm.shape == want.shape
+    assert np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 2        # rounding of a 1e-5-accurate waveform to int16
