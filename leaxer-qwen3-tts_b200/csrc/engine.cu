@@ -948,7 +948,12 @@ int fk_init(lqt_engine* h) {
         h->fk_so.shared = (unsigned)L.shared; h->fk_so.maxV = maxV;
         h->fk_smem = L.total;
         const void* fn = h->fk_wide ? (const void*)frame_kernel<6, 3> : (const void*)frame_kernel<3, 4>;
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fk_smem));
+        // The attribute belongs to the FUNCTION (process-wide), not to this handle: opt in to the device maximum so that another
+        // engine with a smaller model (smaller carve-up) can never lower it under this one's launches.
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        if ((size_t)optin < h->fk_smem) { h->err = "frame kernel: shared memory carve-up exceeds the device limit"; return 1; }
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(FK_CLUSTER * 64); cfg.blockDim = dim3(FK_THREADS); cfg.dynamicSmemBytes = h->fk_smem; cfg.stream = h->stream;
         cudaLaunchAttribute at[1];

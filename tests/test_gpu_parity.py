@@ -414,7 +414,7 @@ def test_c2_teacher_forced_375_frames(request):
     print(f"\n[c2 teacher-forced] worst |logit error| over {len(g['frames'])} stored frames: {worst:.2e}")
 
 
-@pytest.mark.parametrize("which,key,min_prefix", [("full", "codes", 8), ("full_f32", "codes_f32kv", 64)])
+@pytest.mark.parametrize("which,key,min_prefix", [("full", "codes", 64), ("full_f32", "codes_f32kv", 375)])   # measured on B200: 146 and 375
 def test_c2_free_running_seeded_prefix(request, which, key, min_prefix):
     """free-running C2 with the benchmark's sampler settings and Philox key (1234, 0): token-exact against the oracle for as
     long as no draw sits within float noise of a CDF boundary. The fp32-KV parity mode has no rounding point and must
