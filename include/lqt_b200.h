@@ -146,6 +146,38 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
                           const lqt_sampling* sp, float* audio_out, int64_t audio_capacity,
                           int64_t* n_samples, int64_t* codes_out, int32_t* n_frames);
 
+/* ---- batched path: many utterances per GPU (BASELINE configs[3], [4]) --------------------------- *
+ * The reference synthesises exactly one utterance per call (src/tts_onnx.cpp:405-436, batch dim 1 at :547, 618, 672-674);
+ * a serving host would loop over requests. lqt_synthesize_batch takes the whole list: up to `max_concurrent` utterances
+ * run in lockstep KV slots (continuous batching: a finished utterance's slot and KV pages go to the next request), every
+ * matrix product is one TMA-fed tcgen05 GEMM over all slots, each utterance keeps its own Philox key
+ * (seed, utterance_id) so its codes do not depend on the batch composition. Per request the semantics are those of
+ * lqt_synthesize_tokens. planes: 3 = fp32-exact activations (three bf16 planes, token-exact against the oracle),
+ * 2 = 16-bit mantissa, 1 = plain bf16 activations (logits within the 2e-2 bound). */
+typedef struct lqt_batch_request {
+    const int64_t* token_ids; int32_t n_ids;     /* [IM_START, ASSISTANT, TTS_BOS, text..., TTS_EOS, IM_END] */
+    int32_t  lang_codec_id;                      /* 0 = auto */
+    const float* speaker_embed;                  /* nullable [hidden] */
+    uint32_t utterance_id;                       /* Philox key word 1 */
+    int32_t  max_new_tokens;
+    const int64_t* forced_codes; int32_t n_forced;   /* nullable teacher forcing, [n_forced,16] */
+    float*   audio_out; int64_t audio_capacity; int64_t* n_samples;   /* nullable: skip the vocoder */
+    int64_t* codes_out; int32_t* n_frames;       /* [max_new_tokens,16] */
+    float*   logits_trace;                       /* nullable [max_new_tokens,16,max(vocab,cp_vocab)] */
+} lqt_batch_request;
+typedef struct lqt_batch_options {
+    int32_t max_concurrent;   /* KV slots = utterances in flight; 0 = all requests at once */
+    int32_t planes;           /* 0 = 3 */
+    int32_t poll_frames;      /* frames between completion checks; 0 = 8 */
+} lqt_batch_options;
+int lqt_synthesize_batch(lqt_engine* h, const lqt_batch_request* reqs, int32_t n_reqs, const lqt_sampling* sp,
+                         const lqt_batch_options* opt);
+/* Parity surface of the batched path's GEMM kernel alone (tc_gemm.cuh): out[b][n] = sum_k bf16(W[n][k]) * x[b][k];
+ * W [N,K] and x [B,K] are fp32 host arrays (W is rounded to bf16 on the device, x split into `planes` planes);
+ * splits = 0 picks the split-K factor like the engine does. */
+int lqt_debug_tc_gemm(lqt_engine* h, const float* W, const float* x, int32_t N, int32_t K, int32_t B, int32_t planes,
+                      int32_t splits, float* out);
+
 /* build_prompt_embeddings  :442-539 on the device; outputs to host for parity tests.
  * prompt_out [10,H] capacity, *P rows used; trailing_out [n_ids,H] capacity, *trailing_len. */
 int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids,

@@ -18,7 +18,9 @@
 #include "frame_kernel.cuh"
 #include "gemv.cuh"
 #include "lqw_loader.h"
+#include "batched.cuh"
 #include "sampler.cuh"
+#include "tc_gemm.cuh"
 #include "vocoder.cuh"
 
 using namespace lqt;
@@ -69,8 +71,11 @@ struct VocUpW {
 
 }  // namespace
 
+struct lqt_batch;
+
 struct lqt_engine {
     int device = 0;
+    lqt_batch* batch = nullptr;               // batched path context (batch_engine.inl), created on first use
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     Spec sp{};
@@ -1242,10 +1247,26 @@ int init_engine(lqt_engine* h, const std::string& dir) {
 
 }  // namespace
 
+#include "batch_engine.inl"
+
 // ================================================================================================
 // C-ABI
 // ================================================================================================
 extern "C" {
+
+int lqt_synthesize_batch(lqt_engine* h, const lqt_batch_request* reqs, int32_t n_reqs, const lqt_sampling* sp, const lqt_batch_options* opt) {
+    if (!h || !reqs || n_reqs < 1 || !sp) return 1;
+    cudaSetDevice(h->device);
+    const int rc = synthesize_batch_impl(h, reqs, n_reqs, sp, opt);
+    if (rc) cudaStreamSynchronize(h->stream);
+    return rc;
+}
+
+int lqt_debug_tc_gemm(lqt_engine* h, const float* W, const float* x, int32_t N, int32_t K, int32_t B, int32_t planes, int32_t splits, float* out) {
+    if (!h || !W || !x || !out) return 1;
+    cudaSetDevice(h->device);
+    return debug_tc_gemm_impl(h, W, x, N, K, B, planes, splits, out);
+}
 
 const char* lqt_create_error(void) { return g_create_error.c_str(); }
 
@@ -1301,6 +1322,7 @@ void lqt_destroy(lqt_engine* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    batch_destroy(h->batch); h->batch = nullptr;
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
     for (auto& w : h->ws) if (w.second.first) cudaFree(w.second.first);
     void* bufs[] = {h->x, h->qkv, h->attn, h->act, h->logits, h->last_hidden, h->cx, h->cxin, h->cqkv, h->cattn, h->cact,

@@ -28,6 +28,7 @@ struct SamplingDev {
 
 struct SampleParams {
     const float* logits; int V;
+    int n_splits; long long split_stride;   // batched path: the logits are the sum of n_splits split-K partials (0/1 = plain array)
     int mask_lo, mask_hi, mask_keep;     // logits[i] = -inf for mask_lo <= i < mask_hi, i != mask_keep
     const SamplingDev* sp;
     uint32_t frame_imm;
@@ -86,8 +87,8 @@ LQT_DEVINL int block_excl_scan_flag(int flag, int* warp_tot, int* total) {
 }
 
 // dynamic smem: V * (float x + int idx + float p + float sorted_p + int rank) = 20 V bytes
-__global__ void __launch_bounds__(SMP_THREADS, 1)
-sample_kernel(const SampleParams p) {
+// One draw + glue by one CTA of SMP_THREADS threads (called by sample_kernel and by the batched path's bsample_kernel).
+LQT_DEVINL void sample_block(const SampleParams& p) {
     extern __shared__ unsigned char smp_raw[];
     float* s_x    = reinterpret_cast<float*>(smp_raw);          // (masked, tempered) logits
     int*   s_idx  = reinterpret_cast<int*>(s_x + p.V);          // survivor -> original index
@@ -118,6 +119,7 @@ sample_kernel(const SampleParams p) {
     // ---- load + mask (:803-807) + temperature (:882-884) ---------------------------------------
     for (int i = tid; i < V; i += SMP_THREADS) {
         float v = p.logits[i];
+        for (int q = 1; q < p.n_splits; ++q) v += p.logits[(size_t)q * p.split_stride + i];      // fixed order
         if (i >= p.mask_lo && i < p.mask_hi && i != p.mask_keep) v = -INFINITY;
         if (p.trace) p.trace[((size_t)frame * p.n_codebooks + p.codebook) * p.trace_stride + i] = v;
         if (temper) v = v / sp.temperature;
@@ -294,5 +296,8 @@ sample_kernel(const SampleParams p) {
         p.next_in[h] = acc;
     }
 }
+
+__global__ void __launch_bounds__(SMP_THREADS, 1)
+sample_kernel(const SampleParams p) { sample_block(p); }
 
 }  // namespace lqt

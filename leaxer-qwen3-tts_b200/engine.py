@@ -20,6 +20,7 @@ SYMBOLS = [
     "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
     "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange", "lqt_check_model_file",
+    "lqt_synthesize_batch", "lqt_debug_tc_gemm",
 ]
 
 
@@ -48,6 +49,18 @@ class Stats(C.Structure):
 
 
 FRAME_IMPL = {"persistent": 0, "graph": 1, "auto": 2}      # include/lqt_b200.h LQT_FRAME_*
+
+
+class BatchRequest(C.Structure):
+    _fields_ = [("token_ids", C.c_void_p), ("n_ids", C.c_int32), ("lang_codec_id", C.c_int32),
+                ("speaker_embed", C.c_void_p), ("utterance_id", C.c_uint32), ("max_new_tokens", C.c_int32),
+                ("forced_codes", C.c_void_p), ("n_forced", C.c_int32),
+                ("audio_out", C.c_void_p), ("audio_capacity", C.c_int64), ("n_samples", C.POINTER(C.c_int64)),
+                ("codes_out", C.c_void_p), ("n_frames", C.POINTER(C.c_int32)), ("logits_trace", C.c_void_p)]
+
+
+class BatchOptions(C.Structure):
+    _fields_ = [("max_concurrent", C.c_int32), ("planes", C.c_int32), ("poll_frames", C.c_int32)]
 
 
 _lib = None
@@ -95,6 +108,8 @@ def load_library():
     lib.lqt_debug_timeline.argtypes = [P, I32, I32, P, I32]
     lib.lqt_debug_exchange.argtypes = [P, I32, P, I32]
     lib.lqt_check_model_file.argtypes = [C.c_char_p, C.c_char_p, I32]
+    lib.lqt_synthesize_batch.argtypes = [P, C.POINTER(BatchRequest), I32, C.POINTER(Sampling), C.POINTER(BatchOptions)]
+    lib.lqt_debug_tc_gemm.argtypes = [P, P, P, I32, I32, I32, I32, I32, P]
     _lib = lib
     return lib
 
@@ -310,3 +325,50 @@ class Engine:
         if audio_out is not None or codes_out is not None:
             return audio[: ns.value], codes[: nf.value]
         return audio[: ns.value].copy(), codes[: nf.value].copy()
+
+    # ---- batched path (BASELINE configs[3], [4]) -----------------------------------------------------
+    def synthesize_batch(self, requests, temperature=0.8, top_k=50, top_p=0.95, seed=0, greedy=False,
+                         max_concurrent=0, planes=3, poll_frames=0, vocode=True, trace=False, pinned=None):
+        """requests: list of dicts {token_ids, lang='auto', speaker_embed=None, utterance_id=i, max_new_tokens,
+        forced_codes=None}. -> list of (audio f32 [n] or None, codes i64 [T,16][, trace]) in request order.
+        pinned: optional list of (audio_buffer, codes_buffer) caller-owned host arrays per request."""
+        n = len(requests)
+        arr = (BatchRequest * n)()
+        keep, outs = [], []
+        stride = max(self.info.vocab, self.info.cp_vocab)
+        for i, r in enumerate(requests):
+            ids = _i64(r["token_ids"])
+            mx = int(r["max_new_tokens"])
+            spk = _f32(r["speaker_embed"]) if r.get("speaker_embed") is not None else None
+            fc = _i64(r["forced_codes"]).reshape(-1, 16) if r.get("forced_codes") is not None else None
+            if pinned is not None:
+                audio, codes = pinned[i]
+            else:
+                audio = np.empty(max(mx, 1) * self.info.samples_per_frame, np.float32) if vocode else None
+                codes = np.zeros((max(mx, 1), 16), np.int64)
+            tb = np.zeros((max(mx, 1), 16, stride), np.float32) if trace else None
+            ns, nf = C.c_int64(0), C.c_int32(0)
+            keep.append((ids, spk, fc, audio, codes, tb, ns, nf))
+            a = arr[i]
+            a.token_ids = _ptr(ids); a.n_ids = len(ids); a.lang_codec_id = LANG_CODEC_ID[r.get("lang", "auto")]
+            a.speaker_embed = _ptr(spk); a.utterance_id = int(r.get("utterance_id", i)); a.max_new_tokens = mx
+            a.forced_codes = _ptr(fc); a.n_forced = 0 if fc is None else fc.shape[0]
+            a.audio_out = _ptr(audio) if vocode else None
+            a.audio_capacity = 0 if audio is None else audio.size
+            a.n_samples = C.pointer(ns); a.codes_out = _ptr(codes); a.n_frames = C.pointer(nf)
+            a.logits_trace = _ptr(tb)
+        sp = self.sampling(temperature, top_k, top_p, 0, seed, 0, greedy)
+        opt = BatchOptions(max_concurrent, planes, poll_frames)
+        self._ck(self.lib.lqt_synthesize_batch(self.h, arr, n, C.byref(sp), C.byref(opt)))
+        for ids, spk, fc, audio, codes, tb, ns, nf in keep:
+            a = audio.reshape(-1)[: ns.value] if (audio is not None and vocode) else None
+            c = codes.reshape(-1, 16)[: nf.value]
+            outs.append((a, c, tb) if trace else (a, c))
+        return outs
+
+    def debug_tc_gemm(self, W, x, planes=3, splits=0):
+        """out[b][n] = sum_k bf16(W[n][k]) * x[b][k] through the tcgen05 GEMM of the batched path (parity surface)"""
+        W, x = _f32(W), _f32(x)
+        out = np.empty((x.shape[0], W.shape[0]), np.float32)
+        self._ck(self.lib.lqt_debug_tc_gemm(self.h, _ptr(W), _ptr(x), W.shape[0], W.shape[1], x.shape[0], planes, splits, _ptr(out)))
+        return out
