@@ -231,6 +231,10 @@ def main():
     ap.add_argument("--spec", default="0.6b", choices=["0.6b", "1.7b", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the (untimed) comparison with the committed oracle golden")
+    ap.add_argument("--c4-utterances", type=int, default=256,
+                    help="BASELINE configs[3] leg (after the headline): this many concurrent utterances IN TOTAL, split evenly over the "
+                         "GPUs, through lqt_synthesize_batch (tcgen05 GEMM path); 0 = skip")
+    ap.add_argument("--c4-planes", type=int, default=2, help="bf16 planes per activation in the batched leg (3 = fp32-exact, 2 = 16-bit mantissa)")
     ap.add_argument("--cpu-frames", type=int, default=150, help="frames in the cpu_baseline sample (~10-30 s of CPU work)")
     ap.add_argument("--frame-impl", default="persistent", choices=["persistent", "graph"],
                     help="persistent = one cooperative kernel per utterance (default); graph = round-1 v1 schedule (A/B only)")
@@ -321,6 +325,33 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     st = eng.stats()
 
+    # ---- BASELINE configs[3]: 256 concurrent utterances split over the GPUs, batched tcgen05 path (strong scaling) ----------
+    c4 = None
+    if a.c4_utterances > 0 and a.spec == "0.6b":
+        per = max(1, a.c4_utterances // world)
+        reqs = [{"token_ids": ids_np, "lang": "en", "utterance_id": rank * per + u, "max_new_tokens": a.frames} for u in range(per)]
+        pins = [(torch.empty(a.frames * spf, dtype=torch.float32).pin_memory().numpy(),
+                 torch.empty(a.frames * 16, dtype=torch.int64).pin_memory().numpy()) for _ in range(per)]
+        best = None
+        for rep in range(2):                                      # one warm-up (context + graph creation), one timed
+            fence()
+            t0 = time.perf_counter()
+            outs = eng.synthesize_batch(reqs, 0.8, 50, 0.95, seed=1234, max_concurrent=per, planes=a.c4_planes, pinned=pins)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = (dt, sum(o[1].shape[0] for o in outs), eng.stats().last_frames)
+        c4v = torch.tensor([best[0]], dtype=torch.float64, device=f"cuda:{local}")
+        c4n = torch.tensor([float(best[1])], dtype=torch.float64, device=f"cuda:{local}")
+        if dist:
+            dist.all_reduce(c4v, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c4n, op=dist.ReduceOp.SUM)
+        c4 = {"workload": f"{per * world} concurrent C2-shaped utterances ({per} per GPU), {a.frames} frames each, planes={a.c4_planes} "
+                          "[BASELINE.json configs[3]]", "value": float(c4n.item()) * FRAME_S / float(c4v.item()), "unit": UNIT,
+              "utterances_per_gpu": per, "wall_s": float(c4v.item()), "lockstep_frames_rank0": int(best[2]),
+              "note": "end to end through lqt_synthesize_batch with pinned host buffers (token ids in, PCM + codes out), wall clock, "
+                      "max over ranks; strong scaling: the total is fixed, each GPU takes total / n_gpus utterances"}
+        log(f"[bench] c4: {c4}")
+
     vals = torch.tensor([wall, dev_ms, gen_ms, voc_ms], dtype=torch.float64, device=f"cuda:{local}")
     tot = torch.tensor([float(frames), float(st.kernel_launches)], dtype=torch.float64, device=f"cuda:{local}")
     if dist:
@@ -380,6 +411,7 @@ def main():
                 "ms_per_step": wall_max / a.steps * 1e3,
                 "first_audio_ms_p50": statistics.median(first_ms) if first_ms else None,
                 "full_utterance_ms_p50": wall_max / a.steps / a.utterances * 1e3},
+        "c4_batched": c4,
         "parity_checked": bool(parity and parity.get("parity_checked")),
         "parity": parity,
         "gpu_launches": int(launches_all),

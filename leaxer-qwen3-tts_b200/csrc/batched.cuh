@@ -40,6 +40,22 @@ LQT_DEVINL void bstore_planes4(__nv_bfloat16* X, int K, int planes, int Bt, int 
     }
 }
 
+// sum of the split-K partials of 4 consecutive outputs, in the fixed order 0..S-1 (bit-reproducible). The loads of up to 8
+// splits are issued before the first add: the partials sit in L2 and a dependent chain of S round trips is what this costs
+// otherwise (profiles/r2_batched_launches_*.md: 7.5 us per bprep launch with a rolled loop).
+LQT_DEVINL float4 bsum_splits4(const float* base, int n_splits, long long split_stride, float4 v) {
+    for (int q0 = 0; q0 < n_splits; q0 += 8) {
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            w[u] = (q0 + u < n_splits) ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)(q0 + u) * split_stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (q0 + u < n_splits) { v.x += w[u].x; v.y += w[u].y; v.z += w[u].z; v.w += w[u].w; }
+    }
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 struct BPrepParams {
     const BatchState* st;
@@ -69,10 +85,7 @@ bprep_kernel(const BPrepParams p) {
     float ss = 0.f;
     for (int k = tid * 4; k < H; k += 1024) {
         float4 v = in ? *reinterpret_cast<const float4*>(in + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < p.n_splits; ++q) {                      // fixed order: bit-reproducible
-            const float4 w = *reinterpret_cast<const float4*>(p.part + (size_t)q * p.split_stride + (size_t)b * H + k);
-            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-        }
+        if (p.n_splits) v = bsum_splits4(p.part + (size_t)b * H + k, p.n_splits, p.split_stride, v);
         if (p.bias) { const float4 w = *reinterpret_cast<const float4*>(p.bias + k); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
         *reinterpret_cast<float4*>(bp_row + k) = v;
         if (p.x_out) *reinterpret_cast<float4*>(p.x_out + (size_t)b * H + k) = v;
@@ -112,13 +125,9 @@ bswiglu_kernel(const BSwigluParams p) {
     if (bslot_idle(p.st[b])) return;
     const int I = p.I;
     for (int k = (blockIdx.y * 256 + threadIdx.x) * 4; k < I; k += gridDim.y * 1024) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
-        for (int q = 0; q < p.n_splits; ++q) {
-            const float* row = p.part + (size_t)q * p.split_stride + (size_t)b * 2 * I;
-            const float4 a = *reinterpret_cast<const float4*>(row + k), c = *reinterpret_cast<const float4*>(row + I + k);
-            g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
-            u.x += c.x; u.y += c.y; u.z += c.z; u.w += c.w;
-        }
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 g = bsum_splits4(p.part + (size_t)b * 2 * I + k, p.n_splits, p.split_stride, z);
+        const float4 u = bsum_splits4(p.part + (size_t)b * 2 * I + I + k, p.n_splits, p.split_stride, z);
         bstore_planes4(p.X, I, p.planes, p.Bt, b, k, make_float4(silu_f(g.x) * u.x, silu_f(g.y) * u.y, silu_f(g.z) * u.z, silu_f(g.w) * u.w));
     }
 }
@@ -173,12 +182,7 @@ battn_kernel(const BAttnParams p) {
     const long long head_off = (long long)g * PS * ATT_D;
     const long long v_off = (long long)p.n_kv * PS * ATT_D;
     auto load_qkv = [&](int off) {                                   // sum of the split-K partials, fixed order
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < p.n_splits; ++q) {
-            const float4 w = reinterpret_cast<const float4*>(p.qkv_part + (size_t)q * p.split_stride + (size_t)b * qkv_dim + off)[lane];
-            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-        }
-        return v;
+        return bsum_splits4(p.qkv_part + (size_t)b * qkv_dim + off + lane * 4, p.n_splits, p.split_stride, make_float4(0.f, 0.f, 0.f, 0.f));
     };
     if (warp < REP) {
         float4 v = load_qkv((g * REP + warp) * ATT_D);
@@ -278,6 +282,23 @@ battn_kernel(const BAttnParams p) {
         if (lane == 0) red_l[r][warp] = lsum[r];
     }
     __syncthreads();
+    if (active == 1) {
+        // one split (always the case for the code predictor's <= 17 positions and for short talker contexts): no partial record,
+        // no ticket, no fence -- the CTA holds the whole softmax
+        if (tid < REP * ATT_D / 4) {
+            const int r = tid / (ATT_D / 4), d = (tid % (ATT_D / 4)) * 4;
+            float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+            float den = 0.f;
+#pragma unroll
+            for (int w = 0; w < ATT_WARPS; ++w) {
+                const float4 o = *reinterpret_cast<const float4*>(&o_s[w][r][d]);
+                num.x += o.x; num.y += o.y; num.z += o.z; num.w += o.w;
+                den += red_l[r][w];
+            }
+            bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * REP + r) * ATT_D + d, make_float4(num.x / den, num.y / den, num.z / den, num.w / den));
+        }
+        return;
+    }
     float* partial = p.partial + (size_t)b * p.n_kv * nsplit * REP * ATT_PSTRIDE;
     float* part = partial + ((size_t)(g * nsplit + split) * REP) * ATT_PSTRIDE;
     for (int e = tid; e < REP * ATT_D; e += ATT_THREADS) {

@@ -119,7 +119,15 @@ LQT_DEVINL void sample_block(const SampleParams& p) {
     // ---- load + mask (:803-807) + temperature (:882-884) ---------------------------------------
     for (int i = tid; i < V; i += SMP_THREADS) {
         float v = p.logits[i];
-        for (int q = 1; q < p.n_splits; ++q) v += p.logits[(size_t)q * p.split_stride + i];      // fixed order
+        if (p.n_splits > 1) {                                   // fixed order, loads in flight
+            float w[8];
+            for (int q0 = 1; q0 < p.n_splits; q0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = (q0 + u < p.n_splits) ? __ldcg(p.logits + (size_t)(q0 + u) * p.split_stride + i) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (q0 + u < p.n_splits) v += w[u];
+            }
+        }
         if (i >= p.mask_lo && i < p.mask_hi && i != p.mask_keep) v = -INFINITY;
         if (p.trace) p.trace[((size_t)frame * p.n_codebooks + p.codebook) * p.trace_stride + i] = v;
         if (temper) v = v / sp.temperature;
