@@ -20,6 +20,7 @@
 #include "lqw_loader.h"
 #include "batched.cuh"
 #include "sampler.cuh"
+#include "tc_conv.cuh"
 #include "tc_gemm.cuh"
 #include "vocoder.cuh"
 
@@ -72,10 +73,12 @@ struct VocUpW {
 }  // namespace
 
 struct lqt_batch;
+namespace { struct VocTcModel; }
 
 struct lqt_engine {
     int device = 0;
     lqt_batch* batch = nullptr;               // batched path context (batch_engine.inl), created on first use
+    VocTcModel* voc_tc = nullptr;             // tcgen05 vocoder decoder (voc_tc.inl): padded weights, SnakeBeta constants, plane buffers
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     Spec sp{};
@@ -562,6 +565,9 @@ int build_prompt_device(lqt_engine* h, const int64_t* ids, int n, int lang_id, c
     return 0;
 }
 
+#include "tma_host.inl"
+#include "voc_tc.inl"
+
 // tokenizer12hz_decode (src/tts_onnx.cpp:759-776) on device codes [T][16] -> audio_dev [T*spf]
 int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, cudaStream_t vstream = nullptr) {
     // every launch below goes to h->stream: a caller that wants another stream (the first-audio chunk) passes it here and the
@@ -628,7 +634,9 @@ int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, 
         { ConvGemmParams p = cg(o2, L, Cv, U.pw1_w, 4 * Cv, o3); p.bias = U.pw1_b; p.act = 3; launch_conv_gemm(h, p); }
         { ConvGemmParams p = cg(o3, L, 4 * Cv, U.pw2_w, Cv, cur); p.bias = U.pw2_b; p.scale = U.gamma; p.residual = o1; launch_conv_gemm(h, p); }
     }
-    // decoder
+    // decoder: TMA-fed tcgen05 implicit-GEMM convolutions with fused SnakeBeta (tc_conv.cuh) ...
+    if (h->voc_tc && h->voc_tc->ready) return voc_tc_decoder(h, cur, L, audio);
+    // ... or the round-1 kernels (mma.sync implicit GEMM on fp32 activations + separate SnakeBeta passes; LQT_VOC_TC=0)
     { ConvGemmParams p = cg(cur, L, Cv, h->dec_in_w, s.voc_decoder_dim, o1); p.taps = 7; p.bias = h->dec_in_b; launch_conv_gemm(h, p); }
     float* t = o1;                       // running activation
     float* fa = cur; float* fb = o2;                      // free buffers (o3 unused from here)
@@ -1232,6 +1240,7 @@ int init_engine(lqt_engine* h, const std::string& dir) {
     CK(cudaEventCreate(&h->ev_chunk)); CK(cudaEventCreate(&h->ev_first));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     if (const char* e = getenv("LQT_FIRST_CHUNK")) h->first_chunk = std::max(0, atoi(e));
+    if (voc_tc_init(h)) return 1;
     if (h->frame_impl != LQT_FRAME_GRAPH && fk_init(h)) {
         // shapes the persistent kernel does not cover (e.g. the 1.7B talker: > 64 rows per CTA). An explicit request for the
         // persistent kernel fails here, loudly; LQT_FRAME_AUTO runs loops A+B as the CUDA graph of per-op sm_100a kernels instead
@@ -1323,6 +1332,7 @@ void lqt_destroy(lqt_engine* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     batch_destroy(h->batch); h->batch = nullptr;
+    voc_tc_destroy(h);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
     for (auto& w : h->ws) if (w.second.first) cudaFree(w.second.first);
     void* bufs[] = {h->x, h->qkv, h->attn, h->act, h->logits, h->last_hidden, h->cx, h->cxin, h->cqkv, h->cattn, h->cact,
