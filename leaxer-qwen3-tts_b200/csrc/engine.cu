@@ -463,10 +463,13 @@ float* wsbuf(lqt_engine* h, const std::string& name, size_t n) {
     return e.first;
 }
 
+bool voc_tc_try(lqt_engine* h, const ConvGemmParams& c);
+
 void launch_conv_gemm(lqt_engine* h, ConvGemmParams p) {
     if (p.bias_mod <= 0) p.bias_mod = p.N;
     if (p.dil <= 0) p.dil = 1;
     if (p.taps <= 0) p.taps = 1;
+    if (voc_tc_try(h, p)) return;                 // TMA-fed tcgen05 implicit GEMM (tc_conv.cuh) where the shape allows
     static const bool no_mma = getenv("LQT_CONV_FP32") != nullptr;             // A/B aid: the CUDA-core kernel
     if (!no_mma && p.Cin % 16 == 0) {                                       // tensor-core path (bf16x3 split activations, exact products)
         dim3 grid((p.L + CM_BM - 1) / CM_BM, (p.N + CM_BN - 1) / CM_BN);

@@ -29,6 +29,8 @@ struct TcConvParams {
     int planes, Cp;            // input planes, padded input channels (multiple of 64)
     int stages;
     const float* bias; int bias_mod;        // nullable; index n % bias_mod
+    int act;                                // 0 none, 1 SiLU, 3 GELU(erf), after the bias
+    const float* scale;                     // nullable, index n % bias_mod (LayerScale / ConvNeXt gamma), before the residual
     const float* residual;                  // nullable fp32 [L][N]
     float* y;                               // nullable fp32 [L][N]
     int y_snake;                            // 1: the fp32 output is stored AFTER SnakeBeta (input of conv_out_kernel)
@@ -114,6 +116,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const float* b = p.bias + (n % p.bias_mod);
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) { const float4 w = __ldg(reinterpret_cast<const float4*>(b + j)); v[j] += w.x; v[j + 1] += w.y; v[j + 2] += w.z; v[j + 3] += w.w; }
+            }
+            if (p.act == 3) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = gelu_erf_f(v[j]);
+            } else if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+            }
+            if (p.scale) {
+                const float* sc = p.scale + (n % p.bias_mod);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) { const float4 w = __ldg(reinterpret_cast<const float4*>(sc + j)); v[j] *= w.x; v[j + 1] *= w.y; v[j + 2] *= w.z; v[j + 3] *= w.w; }
             }
             if (p.residual) {
                 const float* r = p.residual + (size_t)l * p.N + n;

@@ -18,6 +18,8 @@ struct VocTcModel {
     VocTcSnake s_out;
     std::vector<void*> allocs;
     bf16 *xa = nullptr, *xb = nullptr; size_t x_cap = 0;        // plane ping-pong buffers
+    bf16* xs = nullptr; size_t xs_cap = 0;                      // planes of an fp32 operand of the front stages (voc_tc_try)
+    std::map<const bf16*, VocTcW> lin;                          // front-stage Linear / conv weights used in place (Cin % 64 == 0)
     float *t0 = nullptr; size_t t_cap = 0;                      // fp32 residual stream / final activation
 };
 
@@ -82,13 +84,14 @@ void voc_tc_destroy(lqt_engine* h) {
     for (void* p : m->allocs) if (p) cudaFree(p);
     if (m->xa) cudaFree(m->xa);
     if (m->xb) cudaFree(m->xb);
+    if (m->xs) cudaFree(m->xs);
     if (m->t0) cudaFree(m->t0);
     delete m;
     h->voc_tc = nullptr;
 }
 
 struct VocTcOut {               // what one convolution's epilogue produces
-    float* y = nullptr; bool y_snake = false; const float* residual = nullptr;
+    float* y = nullptr; bool y_snake = false; const float* residual = nullptr; const float* scale = nullptr; int act = 0;
     bf16* xo = nullptr; int cout = 0, up = 1; const VocTcSnake* sn = nullptr;
 };
 
@@ -98,7 +101,7 @@ int voc_tc_conv(lqt_engine* h, VocTcModel* m, const VocTcW& W, const bf16* x, lo
     TcConvParams p{};
     p.L = (int)L; p.N = W.N; p.BN = W.BN; p.taps = W.taps; p.dil = dil; p.tap_rev = tap_rev ? 1 : 0;
     p.planes = m->planes; p.Cp = W.Cp;
-    p.bias = W.bias; p.bias_mod = W.bias_mod; p.residual = o.residual; p.y = o.y; p.y_snake = o.y_snake ? 1 : 0;
+    p.bias = W.bias; p.bias_mod = W.bias_mod; p.residual = o.residual; p.scale = o.scale; p.act = o.act; p.y = o.y; p.y_snake = o.y_snake ? 1 : 0;
     p.xo = o.xo; p.oplanes = m->planes; p.cout = o.cout ? o.cout : W.N; p.oCp = (p.cout + 63) / 64 * 64; p.up = o.up;
     if (o.sn) { p.sn_ea = o.sn->ea; p.sn_ib = o.sn->ib; }
     const size_t stage = tc_gemm_stage_bytes(W.BN);
@@ -112,6 +115,37 @@ int voc_tc_conv(lqt_engine* h, VocTcModel* m, const VocTcW& W, const bf16* x, lo
     else tc_conv_kernel<256><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
     h->stats.kernel_launches++;
     return 0;
+}
+
+// The GEMM-shaped ops of the stages in FRONT of the decoder (RVQ output projections, pre_conv, the pre-transformer's Linear
+// layers, the upsampling stages' transposed / point-wise convs): same arguments as the round-1 conv_gemm kernels, run on the
+// tcgen05 kernel instead when the shape allows -- the fp32 operand is split into planes by voc_planes_kernel first (these
+// tensors are small: L <= 4 T rows). Returns false if the op has to stay on the old kernel.
+bool voc_tc_try(lqt_engine* h, const ConvGemmParams& c) {
+    VocTcModel* m = h->voc_tc;
+    if (!m || !m->ready || c.shift != 0 || (c.Cin % 64) || (c.N % 16) || c.L < 1 || c.act == 1) return false;
+    auto it = m->lin.find(c.W);
+    if (it == m->lin.end()) {
+        VocTcW w;
+        w.w = const_cast<bf16*>(c.W); w.N = c.N; w.taps = c.taps; w.Cin = c.Cin; w.Cp = c.Cin; w.BN = voc_tc_pick_bn(c.N);
+        if (w.BN > 128 && c.L <= 2048) w.BN = (c.N % 128 == 0) ? 128 : w.BN;        // few rows: more channel tiles = more CTAs
+        if (!w.BN || make_map(h, &w.mw, w.w, c.N, c.taps * c.Cin, w.BN)) { h->err.clear(); return false; }
+        it = m->lin.emplace(c.W, w).first;
+    }
+    VocTcW w = it->second;
+    w.bias = c.bias; w.bias_mod = c.bias_mod > 0 ? c.bias_mod : c.N;
+    const size_t need = (size_t)c.L * m->planes * c.Cin;
+    if (m->xs_cap < need) {
+        if (m->xs) cudaFree(m->xs);
+        m->xs = nullptr; m->xs_cap = 0;
+        if (cudaMalloc((void**)&m->xs, need * sizeof(bf16)) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        m->xs_cap = need;
+    }
+    const long long n4 = (long long)c.L * (c.Cin / 4);
+    voc_planes_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16), 256, 0, h->stream>>>(c.x, m->xs, c.L, c.Cin, m->planes, c.Cin, nullptr, nullptr);
+    h->stats.kernel_launches++;
+    VocTcOut o; o.y = c.y; o.residual = c.residual; o.scale = c.scale; o.act = c.act;
+    return voc_tc_conv(h, m, w, m->xs, c.L, c.dil > 0 ? c.dil : 1, c.tap_rev != 0, o) == 0;
 }
 
 // decoder of tokenizer12hz_decode from the output of the upsampling stages: cur fp32 [L0][Cv] -> audio [L0 * prod(rates)]
