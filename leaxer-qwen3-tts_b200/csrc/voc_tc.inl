@@ -53,7 +53,7 @@ int voc_tc_init(lqt_engine* h) {
     if (h->vblk.size() > 8 || (s.voc_hidden % 64)) return 0;                     // shapes this path does not take: the fp32-staged kernels stay
     int optin = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    CK(cudaFuncSetAttribute(tc_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    CK(cudaFuncSetAttribute(tc_conv_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     CK(cudaFuncSetAttribute(tc_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     CK(cudaFuncSetAttribute(tc_conv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     CK(cudaFuncSetAttribute(tc_conv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -105,14 +105,14 @@ int voc_tc_conv(lqt_engine* h, VocTcModel* m, const VocTcW& W, const bf16* x, lo
     p.xo = o.xo; p.oplanes = m->planes; p.cout = o.cout ? o.cout : W.N; p.oCp = (p.cout + 63) / 64 * 64; p.up = o.up;
     if (o.sn) { p.sn_ea = o.sn->ea; p.sn_ib = o.sn->ib; }
     const size_t stage = tc_gemm_stage_bytes(W.BN);
-    const int niter = W.taps * m->planes * (W.Cp / TG_BK);
-    p.stages = std::max(2, std::min(std::min(niter, 4), (int)((200 * 1024) / stage)));
-    const size_t smem = tc_gemm_smem_bytes(W.BN, p.stages);
-    const dim3 grid((unsigned)((L + TG_BM - 1) / TG_BM), W.N / W.BN);
-    if (W.BN <= 32) tc_conv_kernel<32><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
-    else if (W.BN <= 64) tc_conv_kernel<64><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
-    else if (W.BN <= 128) tc_conv_kernel<128><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
-    else tc_conv_kernel<256><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
+    p.stages = std::max(2, std::min(TG_MAX_STAGES, (int)((190 * 1024) / stage)));                   // persistent CTA: the ring runs on across tiles
+    const size_t smem = 1024 + (size_t)p.stages * stage + sizeof(TcShared) + 16 + 4 * 32 * 36 * sizeof(float);      // + the epilogue's transpose tiles
+    const long long tiles = ((L + TG_BM - 1) / TG_BM) * (long long)(W.N / W.BN);
+    const dim3 grid((unsigned)std::min<long long>(tiles, h->num_sms));                       // persistent: one CTA per SM
+    if (W.BN <= 32) tc_conv_kernel<64><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);              // template = 2 accumulator sets
+    else if (W.BN <= 64) tc_conv_kernel<128><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
+    else if (W.BN <= 128) tc_conv_kernel<256><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
+    else tc_conv_kernel<512><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
     h->stats.kernel_launches++;
     return 0;
 }
