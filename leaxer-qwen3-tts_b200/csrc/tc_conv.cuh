@@ -47,8 +47,12 @@ struct TcShared {
 
 // PERSISTENT: grid = min(tiles, co-resident CTAs); CTA c takes tiles c, c + grid, ... (tile = position block x channel tile).
 // TMEM_COLS = 2 * (power of two >= BN): the two accumulator sets.
+constexpr int TC_EPI_GROUPS = 4;                                  // epilogue warps = 4 TMEM lane quarters x 4 column groups
+constexpr int TC_THREADS = 64 + 128 * TC_EPI_GROUPS;              // + producer warp + MMA warp
+constexpr int TC_STG_PITCH = 36;                                  // transpose tile row pitch (floats)
+
 template <int TMEM_COLS>
-__global__ void __launch_bounds__(TG_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcConvParams p) {
     extern __shared__ __align__(1024) unsigned char tg_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -63,7 +67,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { tg_mbar_init(&sh->full[i], 1); tg_mbar_init(&sh->empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tg_mbar_init(&sh->tmem_full[i], 1); tg_mbar_init(&sh->tmem_empty[i], 4); }   // 4 epilogue warps release a set
+        for (int i = 0; i < 2; ++i) { tg_mbar_init(&sh->tmem_full[i], 1); tg_mbar_init(&sh->tmem_empty[i], 4 * TC_EPI_GROUPS); }   // every epilogue warp releases a set
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -127,9 +131,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // epilogue arithmetic in the transposed domain: lane = channel (bias / scale / SnakeBeta constants are loaded once per
         // chunk), loop over the 32 rows with 128-byte coalesced residual loads and stores. (Thread-per-row stores of 16 bytes
         // at a row stride of N * 4 bytes half-fill every sector: the k = 1 convolutions took as long as the k = 7 ones.)
-        const int q = warp & 3;
-        constexpr int SP = 36;                                       // staging row pitch (floats): 16-byte aligned rows, conflict-free both ways
-        float* stg = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sh) + sizeof(TcShared) + 15) & ~(uintptr_t)15) + q * (32 * SP);
+        // The elementwise tail (SnakeBeta = sinf per element, plane split) is what bounds these layers, not the MMAs: 16 warps
+        // share it -- warp (2 + 4 g + i) owns TMEM lane quarter (warp & 3) and the 32-channel chunks g, g + 4, ...
+        const int q = warp & 3, grp = (warp - 2) >> 2;
+        constexpr int SP = TC_STG_PITCH;                             // 16-byte aligned rows, conflict-free both ways
+        float* stg = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sh) + sizeof(TcShared) + 15) & ~(uintptr_t)15) + (warp - 2) * (32 * SP);
         int nt = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++nt) {
         const int acc = nt & 1;
@@ -141,7 +147,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int nmax = min(p.BN, p.N - n0);
         const int rows = min(32, p.L - lbase);                       // live rows of this warp (<= 0: nothing to store)
         const int r4 = lane >> 3, c4 = (lane & 7) * 4;               // transposed domain: 8 lanes x 4 channels = one row's 32 channels
-        for (int c = 0; c < nmax; c += 32) {
+        for (int c = grp * 32; c < nmax; c += 32 * TC_EPI_GROUPS) {
             const int cw = min(32, nmax - c);                        // 16 or 32 channels in this chunk
             float v[16];
             tg_tmem_ld16(tbase + (uint32_t)c, v);

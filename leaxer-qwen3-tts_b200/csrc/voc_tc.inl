@@ -105,14 +105,15 @@ int voc_tc_conv(lqt_engine* h, VocTcModel* m, const VocTcW& W, const bf16* x, lo
     p.xo = o.xo; p.oplanes = m->planes; p.cout = o.cout ? o.cout : W.N; p.oCp = (p.cout + 63) / 64 * 64; p.up = o.up;
     if (o.sn) { p.sn_ea = o.sn->ea; p.sn_ib = o.sn->ib; }
     const size_t stage = tc_gemm_stage_bytes(W.BN);
-    p.stages = std::max(2, std::min(TG_MAX_STAGES, (int)((190 * 1024) / stage)));                   // persistent CTA: the ring runs on across tiles
-    const size_t smem = 1024 + (size_t)p.stages * stage + sizeof(TcShared) + 16 + 4 * 32 * 36 * sizeof(float);      // + the epilogue's transpose tiles
+    const size_t epi_smem = 16 + (size_t)4 * TC_EPI_GROUPS * 32 * TC_STG_PITCH * sizeof(float);      // the epilogue warps' transpose tiles
+    p.stages = std::max(2, std::min(TG_MAX_STAGES, (int)((224 * 1024 - 2048 - epi_smem) / stage)));   // persistent CTA: the ring runs on across tiles
+    const size_t smem = 1024 + (size_t)p.stages * stage + sizeof(TcShared) + epi_smem;
     const long long tiles = ((L + TG_BM - 1) / TG_BM) * (long long)(W.N / W.BN);
     const dim3 grid((unsigned)std::min<long long>(tiles, h->num_sms));                       // persistent: one CTA per SM
-    if (W.BN <= 32) tc_conv_kernel<64><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);              // template = 2 accumulator sets
-    else if (W.BN <= 64) tc_conv_kernel<128><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
-    else if (W.BN <= 128) tc_conv_kernel<256><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
-    else tc_conv_kernel<512><<<grid, TG_THREADS, smem, h->stream>>>(mx, W.mw, p);
+    if (W.BN <= 32) tc_conv_kernel<64><<<grid, TC_THREADS, smem, h->stream>>>(mx, W.mw, p);              // template = 2 accumulator sets
+    else if (W.BN <= 64) tc_conv_kernel<128><<<grid, TC_THREADS, smem, h->stream>>>(mx, W.mw, p);
+    else if (W.BN <= 128) tc_conv_kernel<256><<<grid, TC_THREADS, smem, h->stream>>>(mx, W.mw, p);
+    else tc_conv_kernel<512><<<grid, TC_THREADS, smem, h->stream>>>(mx, W.mw, p);
     h->stats.kernel_launches++;
     return 0;
 }
