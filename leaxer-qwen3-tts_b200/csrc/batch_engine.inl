@@ -65,9 +65,24 @@ int bgemm_init(lqt_engine* h, lqt_batch* bt, BGemm* g, const bf16* W, const bf16
     return 0;
 }
 
+// every kernel of the frame graph is launched with the programmatic-serialization attribute (PDL, common.cuh): inside the
+// captured graph the edges become programmatic dependencies, so kernel k+1's prologue overlaps kernel k's tail ($LQT_PDL=0: off)
+template <typename... KArgs, typename... Args>
+void pdl_launch(lqt_engine* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    static const bool on = !(getenv("LQT_PDL") && atoi(getenv("LQT_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    h->stats.kernel_launches++;
+}
+
 template <int COLS>
 void tc_launch(lqt_engine* h, const lqt_batch* bt, const BGemm& g, const TcGemmParams& p, dim3 grid, size_t smem) {
-    tc_gemm_kernel<COLS><<<grid, TG_THREADS, smem, h->stream>>>(g.w, g.w2, *g.x, p);
+    pdl_launch(h, tc_gemm_kernel<COLS>, grid, dim3(TG_THREADS), smem, g.w, g.w2, *g.x, p);
 }
 void bgemm_launch(lqt_engine* h, const lqt_batch* bt, const BGemm& g) {
     TcGemmParams p{};
@@ -79,7 +94,6 @@ void bgemm_launch(lqt_engine* h, const lqt_batch* bt, const BGemm& g) {
     else if (bt->BN <= 64) tc_launch<64>(h, bt, g, p, grid, smem);
     else if (bt->BN <= 128) tc_launch<128>(h, bt, g, p, grid, smem);
     else tc_launch<256>(h, bt, g, p, grid, smem);
-    h->stats.kernel_launches++;
 }
 
 void bprep_launch(lqt_engine* h, const lqt_batch* bt, const float* resid, bool select_prompt, const BGemm* from, const float* bias,
@@ -90,8 +104,7 @@ void bprep_launch(lqt_engine* h, const lqt_batch* bt, const float* resid, bool s
     if (from) { p.part = from->part; p.n_splits = from->S; p.split_stride = from->split_stride; }
     p.bias = bias; p.norm_w = norm_w; p.eps = h->sp.rms_eps; p.x_out = x_out; p.hid_out = hid_out;
     p.X = X; p.planes = bt->planes; p.Bt = bt->Bt; p.H = H;
-    bprep_kernel<<<bt->B, 256, (size_t)H * sizeof(float), h->stream>>>(p);
-    h->stats.kernel_launches++;
+    pdl_launch(h, bprep_kernel, dim3(bt->B), dim3(256), (size_t)H * sizeof(float), p);
 }
 
 struct BStackCtx {
@@ -125,16 +138,18 @@ void bstack_run(lqt_engine* h, lqt_batch* bt, const BStackCtx& c, const float* i
                 a.layer_off = (long long)l * 2 * c.kv_heads * KV_PAGE * D;
                 const dim3 grid(c.kv_heads, bt->nsplit_attn, bt->B);
                 const size_t smem = (size_t)2 * ((bt->max_pages + bt->nsplit_attn - 1) / bt->nsplit_attn) * KV_PAGE * sizeof(float);
-                if (h->kv_f32) battn_kernel<float><<<grid, ATT_THREADS, smem, h->stream>>>(a);
-                else battn_kernel<bf16><<<grid, ATT_THREADS, smem, h->stream>>>(a);
+                if (h->kv_f32) pdl_launch(h, battn_kernel<float>, grid, dim3(ATT_THREADS), smem, a);
+                else pdl_launch(h, battn_kernel<bf16>, grid, dim3(ATT_THREADS), smem, a);
             } else {
                 const int PSc = 1 << CP_PAGE_SHIFT;
-                a.kv_pool = bt->cp_kv; a.page_table = bt->cp_page_table; a.pt_stride = 1; a.page_shift = CP_PAGE_SHIFT;
-                a.page_stride = (long long)h->sp.cp_layers * 2 * c.kv_heads * PSc * D;
-                a.layer_off = (long long)l * 2 * c.kv_heads * PSc * D;
-                battn_kernel<float><<<dim3(c.kv_heads, 1, bt->B), ATT_THREADS, (size_t)2 * PSc * sizeof(float), h->stream>>>(a);
+                BCpAttnParams c2{};
+                c2.st = bt->st; c2.qkv_part = L.qkv.part; c2.n_splits = L.qkv.S; c2.split_stride = L.qkv.split_stride;
+                c2.qnorm = L.qnorm; c2.knorm = L.knorm; c2.rope_cos = c.cos; c2.rope_sin = c.sin; c2.pos = fixed_pos;
+                c2.kv = bt->cp_kv; c2.slot_stride = (long long)h->sp.cp_layers * 2 * c.kv_heads * PSc * D;
+                c2.layer_off = (long long)l * 2 * c.kv_heads * PSc * D; c2.PS = PSc; c2.n_kv = c.kv_heads; c2.B = bt->B;
+                c2.X = c.attn; c2.planes = bt->planes; c2.Bt = bt->Bt; c2.eps = h->sp.rms_eps; c2.scale = a.scale;
+                pdl_launch(h, bcp_attn_kernel, dim3((bt->B * c.kv_heads + 7) / 8), dim3(256), 0, c2);
             }
-            h->stats.kernel_launches++;
         }
         bgemm_launch(h, bt, L.o);
         bprep_launch(h, bt, c.xa, false, &L.o, nullptr, L.ln2, c.xb, nullptr, c.xn, c.H);
@@ -143,8 +158,7 @@ void bstack_run(lqt_engine* h, lqt_batch* bt, const BStackCtx& c, const float* i
             BSwigluParams s{};
             s.st = bt->st; s.part = L.gu.part; s.n_splits = L.gu.S; s.split_stride = L.gu.split_stride;
             s.X = c.act; s.planes = bt->planes; s.Bt = bt->Bt; s.I = c.inter;
-            bswiglu_kernel<<<dim3(bt->B, std::max(1, std::min(4, c.inter / 1024))), 256, 0, h->stream>>>(s);
-            h->stats.kernel_launches++;
+            pdl_launch(h, bswiglu_kernel, dim3(bt->B, std::max(1, std::min(4, c.inter / 1024))), dim3(256), 0, s);
         }
         bgemm_launch(h, bt, L.down);
         (void)qd;
@@ -165,8 +179,7 @@ void bsample_launch(lqt_engine* h, lqt_batch* bt, int codebook, const BGemm& log
     } else {
         q.embed_table = h->cp_embed + (size_t)(codebook - 1) * h->sp.cp_vocab * h->sp.hidden;
     }
-    bsample_kernel<<<bt->B, SMP_THREADS, (size_t)logits.N * 20, h->stream>>>(q);
-    h->stats.kernel_launches++;
+    pdl_launch(h, bsample_kernel, dim3(bt->B), dim3(BSMP_THREADS), (size_t)logits.N * 20, q);
 }
 
 // one lockstep frame (src/tts_onnx.cpp:801-846 for every slot): draw code 0 -> 15 x (predictor pass, draw) -> talker step
@@ -193,8 +206,7 @@ void benqueue_frame(lqt_engine* h, lqt_batch* bt) {
     bstack_run(h, bt, tc, bt->next_in, nullptr, nullptr, -1);
     bprep_launch(h, bt, bt->xb_t, false, &bt->tl.back().down, nullptr, h->t_norm, nullptr, bt->last_hidden, bt->xn_t, s.hidden);
     bgemm_launch(h, bt, bt->t_head);
-    badvance_kernel<<<(bt->B + 127) / 128, 128, 0, h->stream>>>(bt->st, bt->B);
-    h->stats.kernel_launches++;
+    pdl_launch(h, badvance_kernel, dim3((bt->B + 127) / 128), dim3(128), 0, bt->st, bt->B);
 }
 
 void batch_destroy(lqt_batch* bt) {

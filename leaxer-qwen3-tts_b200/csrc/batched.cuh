@@ -77,6 +77,8 @@ bprep_kernel(const BPrepParams p) {
     extern __shared__ float bp_row[];            // [H]
     __shared__ float red[8];
     const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const BatchState s = p.st[b];
     if (bslot_idle(s)) return;
     const int H = p.H;
@@ -122,6 +124,8 @@ struct BSwigluParams {
 __global__ void __launch_bounds__(256)
 bswiglu_kernel(const BSwigluParams p) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (bslot_idle(p.st[b])) return;
     const int I = p.I;
     for (int k = (blockIdx.y * 256 + threadIdx.x) * 4; k < I; k += gridDim.y * 1024) {
@@ -162,6 +166,8 @@ battn_kernel(const BAttnParams p) {
     __shared__ __align__(16) float o_s[ATT_WARPS][REP][ATT_D];
     __shared__ int ticket_s;
     const int b = blockIdx.z;
+    pdl_trigger();
+    pdl_wait();
     const BatchState s = p.st[b];
     if (bslot_idle(s)) return;
 
@@ -343,6 +349,83 @@ battn_kernel(const BAttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Code-predictor attention: <= 17 positions, fp32 KV of 32 positions per slot. One WARP per (slot, kv group): q/k RMSNorm +
+// RoPE, KV append, both query heads' softmax and P.V in registers -- no shared memory, no block barrier (battn_kernel spent
+// 25 us per launch at 256 slots on block-level machinery for a 17-position softmax; 80 of these run per frame).
+struct BCpAttnParams {
+    const BatchState* st;
+    const float* qkv_part; int n_splits; long long split_stride;
+    const float* qnorm; const float* knorm; const float* rope_cos; const float* rope_sin;
+    int pos;                   // position of the new token (0..16)
+    float* kv;                 // [B][layers][k|v][n_kv][PS][128] fp32
+    long long slot_stride, layer_off;
+    int PS, n_kv, B;
+    __nv_bfloat16* X; int planes, Bt;
+    float eps, scale;
+};
+__global__ void __launch_bounds__(256)
+bcp_attn_kernel(const BCpAttnParams p) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_trigger();
+    pdl_wait();
+    if (w >= p.B * p.n_kv) return;
+    const int b = w / p.n_kv, g = w - b * p.n_kv;
+    if (bslot_idle(p.st[b])) return;
+    const int q_dim = p.n_kv * 2 * ATT_D, kv_dim = p.n_kv * ATT_D, qkv_dim = q_dim + 2 * kv_dim;
+    const float* cosr = p.rope_cos + (size_t)p.pos * (ATT_D / 2);
+    const float* sinr = p.rope_sin + (size_t)p.pos * (ATT_D / 2);
+    const float* base = p.qkv_part + (size_t)b * qkv_dim + lane * 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 q0 = bsum_splits4(base + (g * 2) * ATT_D, p.n_splits, p.split_stride, z);
+    float4 q1 = bsum_splits4(base + (g * 2 + 1) * ATT_D, p.n_splits, p.split_stride, z);
+    float4 kn = bsum_splits4(base + q_dim + g * ATT_D, p.n_splits, p.split_stride, z);
+    const float4 vn = bsum_splits4(base + q_dim + kv_dim + g * ATT_D, p.n_splits, p.split_stride, z);
+    q0 = head_norm_rope(q0, p.qnorm, p.eps, cosr, sinr, lane);
+    q1 = head_norm_rope(q1, p.qnorm, p.eps, cosr, sinr, lane);
+    kn = head_norm_rope(kn, p.knorm, p.eps, cosr, sinr, lane);
+    float* kc = p.kv + (size_t)b * p.slot_stride + p.layer_off + (size_t)g * p.PS * ATT_D;
+    float* vc = kc + (size_t)p.n_kv * p.PS * ATT_D;
+    reinterpret_cast<float4*>(kc + (size_t)p.pos * ATT_D)[lane] = kn;
+    reinterpret_cast<float4*>(vc + (size_t)p.pos * ATT_D)[lane] = vn;
+    constexpr int MAXP = 17;
+    // every cached row is fetched up front (rows beyond `pos` are in-bounds garbage, masked below): one L2 round trip instead
+    // of one per position
+    float4 kk[MAXP], vv[MAXP];
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+        kk[j] = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + lane);
+        vv[j] = __ldcg(reinterpret_cast<const float4*>(vc + (size_t)j * ATT_D) + lane);
+    }
+    float s0[MAXP], s1[MAXP];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+        s0[j] = -INFINITY; s1[j] = -INFINITY;
+        if (j <= p.pos) {
+            const float4 k4 = (j == p.pos) ? kn : kk[j];
+            s0[j] = warp_sum(k4.x * q0.x + k4.y * q0.y + k4.z * q0.z + k4.w * q0.w) * p.scale;
+            s1[j] = warp_sum(k4.x * q1.x + k4.y * q1.y + k4.z * q1.z + k4.w * q1.w) * p.scale;
+            m0 = fmaxf(m0, s0[j]); m1 = fmaxf(m1, s1[j]);
+        }
+    }
+    float l0 = 0.f, l1 = 0.f;
+    float4 a0 = z, a1 = z;
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+        if (j <= p.pos) {
+            const float4 v4 = (j == p.pos) ? vn : vv[j];
+            const float e0 = expf(s0[j] - m0), e1 = expf(s1[j] - m1);
+            l0 += e0; l1 += e1;
+            a0.x = fmaf(e0, v4.x, a0.x); a0.y = fmaf(e0, v4.y, a0.y); a0.z = fmaf(e0, v4.z, a0.z); a0.w = fmaf(e0, v4.w, a0.w);
+            a1.x = fmaf(e1, v4.x, a1.x); a1.y = fmaf(e1, v4.y, a1.y); a1.z = fmaf(e1, v4.z, a1.z); a1.w = fmaf(e1, v4.w, a1.w);
+        }
+    }
+    bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * 2) * ATT_D + lane * 4, make_float4(a0.x / l0, a0.y / l0, a0.z / l0, a0.w / l0));
+    bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * 2 + 1) * ATT_D + lane * 4, make_float4(a1.x / l1, a1.y / l1, a1.z / l1, a1.w / l1));
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-slot sampler + glue: the batch-1 sampler block (sampler.cuh) with per-slot pointers
 struct BSampleParams {
     BatchState* st; const SamplingDev* sp;        // [B] each (per-slot Philox utterance id)
@@ -357,9 +440,12 @@ struct BSampleParams {
     float* trace; long long trace_bstride; int trace_stride;   // nullable [B][frames][16][trace_stride]
     int eos_id, n_codebooks;
 };
-__global__ void __launch_bounds__(SMP_THREADS, 1)
+constexpr int BSMP_THREADS = 256;
+__global__ void __launch_bounds__(BSMP_THREADS)
 bsample_kernel(const BSampleParams q) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     BatchState* st = q.st + b;
     if (!st->active || bslot_prefilling(*st)) return;              // (done slots leave inside sample_block)
     SampleParams p{};
@@ -373,11 +459,13 @@ bsample_kernel(const BSampleParams q) {
     p.forced = q.forced ? q.forced + (size_t)b * q.codes_stride : nullptr;
     p.trace = q.trace ? q.trace + (size_t)b * q.trace_bstride : nullptr; p.trace_stride = q.trace_stride;
     p.eos_id = q.eos_id; p.n_codebooks = q.n_codebooks;
-    sample_block(p);
+    sample_block<BSMP_THREADS>(p);
 }
 
 __global__ void badvance_kernel(BatchState* st, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (b >= B) return;
     BatchState& s = st[b];
     if (bslot_idle(s)) return;

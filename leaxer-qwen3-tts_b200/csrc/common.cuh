@@ -22,6 +22,14 @@ struct GenState {
     int n_forced;       // teacher forcing: number of forced frames (0 = off)
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream / graph is still running. pdl_trigger() lets the successor's CTAs be scheduled as
+// soon as every CTA of this grid has issued it; pdl_wait() blocks until the predecessor grid has completed and its memory
+// is visible -- everything before it (barrier init, TMEM allocation, descriptor prefetch, index arithmetic) overlaps the
+// predecessor's tail. Both are no-ops in a launch without the attribute.
+LQT_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+LQT_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 LQT_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -117,6 +117,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int kb0 = blockIdx.y * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
     const int niter = kb1 - kb0;                                  // >= 1 by construction of the grid
 
+    pdl_trigger();                                                // the next kernel's prologue may overlap this one
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { tg_mbar_init(&sh->full[i], 1); tg_mbar_init(&sh->empty[i], 1); }
         tg_mbar_init(&sh->tmem_full, 1);
@@ -130,6 +131,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sh->tmem_base;
+    pdl_wait();                                                   // barriers and TMEM are set up; now the predecessor's outputs (X) are needed
 
     if (warp == 0) {
         // ===== TMA producer =====
