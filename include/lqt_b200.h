@@ -118,6 +118,13 @@ int lqt_vocoder_decode(lqt_engine* h, const int64_t* codes, int32_t T, float* au
                        int64_t* length);
 /* speaker_encoder.onnx  :367-403: log-mel f32 [1,frames,128] -> embedding [H] */
 int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float* out);
+/* Clone front end on the device: extract_speaker_embedding's log-mel (src/tts_onnx.cpp:331-359 with
+ * src/io/mel.cpp:132-236: 1024-point Hann STFT, hop 256, no centre padding, 128 HTK-mel triangles, log(e + 1e-10)) as one
+ * kernel. `audio` is 24 kHz mono f32 (host). lqt_log_mel returns the reference layout [128][frames]
+ * (mel_out nullable, capacity 128 * ((n-1024)/256+1)); lqt_speaker_embed_audio chains it with speaker_encoder.onnx's stand-in
+ * (:367-403) without the mel leaving the device. */
+int lqt_log_mel(lqt_engine* h, const float* audio, int64_t n_samples, float* mel_out, int32_t* frames);
+int lqt_speaker_embed_audio(lqt_engine* h, const float* audio, int64_t n_samples, float* out);
 /* sample_token  :878-905 (+ special-token mask :803-807 when mask_codec_specials != 0) on the
  * device sampler, Philox counter (frame, codebook). */
 int lqt_sample(lqt_engine* h, const float* logits, int32_t V, const lqt_sampling* sp,

@@ -44,12 +44,28 @@ int balloc(lqt_engine* h, lqt_batch* bt, T** p, size_t n) {
     return 0;
 }
 
-// K splits of a GEMM with N_total weight rows: enough CTAs (weight tiles x utterance tiles x splits) to cover the SMs
+// K splits of a GEMM with N_total weight rows, from a small cost model (microseconds): waves x (k-blocks per CTA x time per
+// k-block + fixed CTA cost) + the consumers' reduction of the split partials. Few utterances: the machine is empty, split
+// until ~every SM has a CTA. Many utterances (BN = 256): a CTA's ring fills the SM (one CTA per SM), partials are megabytes --
+// 192 CTAs on 148 SMs is two waves for the price of two, so fewer splits win (profiles/r2_batched_launches_b256.md).
 int bgemm_splits(const lqt_engine* h, const lqt_batch* bt, int N_total, int K) {
     const int tiles = (N_total + TG_BM - 1) / TG_BM * bt->n_tiles, nkb = K / TG_BK;
-    const int S = std::max(1, std::min(nkb, (h->num_sms + tiles / 2) / std::max(tiles, 1)));
-    const int per = (nkb + S - 1) / S;
-    return (nkb + per - 1) / per;
+    const double stage_kb = (double)tc_gemm_stage_bytes(bt->BN) / 1024.0;
+    const double t_k = 0.10 + stage_kb / 140.0;                      // one k-block: ~140 KB/us of TMA ingest per SM + issue
+    const double t_fix = 3.0;                                        // prologue (barriers, TMEM) + epilogue + launch slack
+    int best = 1; double best_cost = 1e30;
+    for (int S = 1; S <= nkb; ++S) {
+        const int per = (nkb + S - 1) / S, Se = (nkb + per - 1) / per;
+        if (Se != S) continue;
+        const int st = std::min(bt->stages, per);
+        const size_t smem = tc_gemm_smem_bytes(bt->BN, st);
+        const int occ = std::max(1, std::min(4, (int)((220 * 1024) / smem)));
+        const int waves = (tiles * S + h->num_sms * occ - 1) / (h->num_sms * occ);
+        const double reduce = (double)S * bt->Bpad * N_total * 4.0 / 3.0e6 + 0.15 * S;      // partial bytes at ~3 TB/s (L2) + latency per split
+        const double cost = waves * (per * t_k * (occ > 1 ? 0.75 : 1.0) + t_fix) + reduce;
+        if (cost < best_cost) { best_cost = cost; best = S; }
+    }
+    return best;
 }
 
 // one weight matrix [N][K] (optionally a second one stacked behind it: gate | up) against X operand `x`

@@ -389,13 +389,16 @@ bcp_attn_kernel(const BCpAttnParams p) {
     reinterpret_cast<float4*>(kc + (size_t)p.pos * ATT_D)[lane] = kn;
     reinterpret_cast<float4*>(vc + (size_t)p.pos * ATT_D)[lane] = vn;
     constexpr int MAXP = 17;
-    // every cached row is fetched up front (rows beyond `pos` are in-bounds garbage, masked below): one L2 round trip instead
-    // of one per position
+    // every cached row is requested up front (predicated on j < pos, no dependence between them): one L2 round trip instead of
+    // one per position
     float4 kk[MAXP], vv[MAXP];
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
-        kk[j] = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + lane);
-        vv[j] = __ldcg(reinterpret_cast<const float4*>(vc + (size_t)j * ATT_D) + lane);
+        kk[j] = z; vv[j] = z;
+        if (j < p.pos) {
+            kk[j] = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + lane);
+            vv[j] = __ldcg(reinterpret_cast<const float4*>(vc + (size_t)j * ATT_D) + lane);
+        }
     }
     float s0[MAXP], s1[MAXP];
     float m0 = -INFINITY, m1 = -INFINITY;

@@ -78,6 +78,7 @@ namespace { struct VocTcModel; }
 struct lqt_engine {
     int device = 0;
     lqt_batch* batch = nullptr;               // batched path context (batch_engine.inl), created on first use
+    float *mel_window = nullptr, *mel_tw_re = nullptr, *mel_tw_im = nullptr; int* mel_tri = nullptr;   // log-mel tables (lqt_log_mel)
     VocTcModel* voc_tc = nullptr;             // tcgen05 vocoder decoder (voc_tc.inl): padded weights, SnakeBeta constants, plane buffers
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -1354,6 +1355,7 @@ void lqt_destroy(lqt_engine* h) {
     if (h->ev_first) cudaEventDestroy(h->ev_first);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
+    if (h->mel_window) { cudaFree(h->mel_window); cudaFree(h->mel_tw_re); cudaFree(h->mel_tw_im); cudaFree(h->mel_tri); }
     h->f_text.release(); h->f_codec.release(); h->f_cpe.release(); h->f_talker.release();
     h->f_cp.release(); h->f_voc.release(); h->f_spk.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1512,21 +1514,106 @@ int lqt_vocoder_decode(lqt_engine* h, const int64_t* codes, int32_t T, float* au
     return 0;
 }
 
+// log-mel tables, built like the host extractor's (host/io/mel.cpp == reference src/io/mel.cpp:15-18, 32-80, 132-158):
+// symmetric Hann with the N-1 denominator evaluated in double, HTK mel points on floor((n_fft+1) f / sr) bins, twiddles
+// cos/sin of the f32 angle per stage
+static int mel_tables_init(lqt_engine* h) {
+    if (h->mel_window) return 0;
+    const int win = 1024, nfft = 1024, mels = 128, sr = 24000;
+    const float fmin = 0.0f, fmax = 12000.0f;
+    std::vector<float> w(win), tr, ti;
+    for (int i = 0; i < win; ++i) w[i] = static_cast<float>(0.5f * (1.0f - std::cos(2.0f * M_PI * i / (win - 1))));
+    auto hz_to_mel = [](float hz) { return 2595.0f * std::log10(1.0f + hz / 700.0f); };
+    auto mel_to_hz = [](float mel) { return 700.0f * (std::pow(10.0f, mel / 2595.0f) - 1.0f); };
+    const int bins = nfft / 2 + 1;
+    const float lo = hz_to_mel(fmin), hi = hz_to_mel(fmax);
+    std::vector<int> edge(mels + 2), tri(mels * 3);
+    for (int i = 0; i < mels + 2; ++i) {
+        const float mel = lo + (hi - lo) * i / (mels + 1);
+        edge[i] = std::min((int)std::floor((nfft + 1) * mel_to_hz(mel) / sr), bins - 1);
+    }
+    for (int m = 0; m < mels; ++m) { tri[m * 3] = edge[m]; tri[m * 3 + 1] = edge[m + 1]; tri[m * 3 + 2] = edge[m + 2]; }
+    for (int size = 2; size <= nfft; size *= 2) {
+        const float step = static_cast<float>(-2.0f * M_PI / size);
+        for (int k = 0; k < size / 2; ++k) { const float ang = step * k; tr.push_back(std::cos(ang)); ti.push_back(std::sin(ang)); }
+    }
+    CK(cudaMalloc((void**)&h->mel_window, win * 4)); CK(cudaMalloc((void**)&h->mel_tw_re, tr.size() * 4));
+    CK(cudaMalloc((void**)&h->mel_tw_im, ti.size() * 4)); CK(cudaMalloc((void**)&h->mel_tri, tri.size() * 4));
+    CK(cudaMemcpy(h->mel_window, w.data(), win * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->mel_tw_re, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->mel_tw_im, ti.data(), ti.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->mel_tri, tri.data(), tri.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// audio (host, 24 kHz mono) -> device log-mel [frames][128] in the "spk_in" workspace; *frames_out = frame count
+static int logmel_device(lqt_engine* h, const float* audio, int64_t n, int* frames_out) {
+    if (mel_tables_init(h)) return 1;
+    const int win = 1024, hop = 256, nfft = 1024, mels = 128;
+    const int frames = (n < win) ? 1 : (int)((n - win) / hop + 1);
+    float* a = wsbuf(h, "mel_audio", (size_t)n);
+    float* in = wsbuf(h, "spk_in", (size_t)frames * mels);
+    if (!a || !in) return 1;
+    CK(cudaMemcpyAsync(a, audio, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    MelParams p{};
+    p.audio = a; p.n = n; p.window = h->mel_window; p.tw_re = h->mel_tw_re; p.tw_im = h->mel_tw_im; p.tri = h->mel_tri; p.out = in;
+    p.frames = frames; p.hop = hop; p.win = win; p.n_fft = nfft; p.log2n = 10; p.num_mels = mels;
+    logmel_kernel<<<frames, 256, (size_t)(2 * nfft + nfft / 2 + 1) * sizeof(float), h->stream>>>(p);
+    h->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    *frames_out = frames;
+    return 0;
+}
+
+static int speaker_encoder_device(lqt_engine* h, int frames, float* out);
+
+int lqt_log_mel(lqt_engine* h, const float* audio, int64_t n_samples, float* mel_out, int32_t* frames) {
+    if (!h || !audio || n_samples <= 0 || !frames) return 1;
+    cudaSetDevice(h->device);
+    int nf = 0;
+    if (logmel_device(h, audio, n_samples, &nf)) return 1;
+    *frames = nf;
+    if (mel_out) {                                   // reference layout [num_mels][frames] (MelExtractor::extract)
+        std::vector<float> t((size_t)nf * 128);
+        CK(cudaMemcpyAsync(t.data(), h->ws["spk_in"].first, t.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int f = 0; f < nf; ++f) for (int m = 0; m < 128; ++m) mel_out[(size_t)m * nf + f] = t[(size_t)f * 128 + m];
+    }
+    return 0;
+}
+
+int lqt_speaker_embed_audio(lqt_engine* h, const float* audio, int64_t n_samples, float* out) {
+    if (!h || !audio || !out || n_samples <= 0) return 1;
+    if (!h->has_spk) { h->err = "speaker encoder not available"; return 1; }
+    if (h->sp.spk_mels != 128) { h->err = "speaker encoder expects 128 mel bands"; return 1; }
+    cudaSetDevice(h->device);
+    int nf = 0;
+    if (logmel_device(h, audio, n_samples, &nf)) return 1;
+    return speaker_encoder_device(h, nf, out);
+}
+
 int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float* out) {
     if (!h || !mel_t || !out || frames <= 0) return 1;
     if (!h->has_spk) { h->err = "speaker encoder not available"; return 1; }
     cudaSetDevice(h->device);
+    float* in = wsbuf(h, "spk_in", (size_t)frames * h->sp.spk_mels);
+    if (!in) return 1;
+    CK(cudaMemcpyAsync(in, mel_t, (size_t)frames * h->sp.spk_mels * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    return speaker_encoder_device(h, frames, out);
+}
+
+// the speaker_encoder graph on the device mel [frames][mels] in the "spk_in" workspace
+static int speaker_encoder_device(lqt_engine* h, int frames, float* out) {
     const Spec& s = h->sp;
     const int Cs = s.spk_channels, M = s.spk_mels;
     bool ok = true;
     const LqwFile& f = h->f_spk;
-    float* in = wsbuf(h, "spk_in", (size_t)frames * M);
+    float* in = h->ws["spk_in"].first;
     float* a = wsbuf(h, "spk_a", (size_t)frames * Cs);
     float* b = wsbuf(h, "spk_b", (size_t)frames * Cs);
     float* pool = wsbuf(h, "spk_pool", (size_t)2 * Cs);
     float* o = wsbuf(h, "spk_out", s.hidden);
     if (!in || !a || !b || !pool || !o) return 1;
-    CK(cudaMemcpyAsync(in, mel_t, (size_t)frames * M * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     const long long n = (long long)frames * Cs;
     const int eb = (int)std::min<long long>((n + 255) / 256, 4096);
     { ConvGemmParams p = cg(in, frames, M, need<bf16>(h, f, "in_conv.weight", ok, {Cs, 5, M}), Cs, b); p.taps = 5; p.shift = 2; p.bias = need<float>(h, f, "in_conv.bias", ok, {Cs});
@@ -1660,6 +1747,7 @@ static int first_chunk_hook(lqt_engine* h, int chunk) {
     if (!h->chunk_audio_out || (int64_t)n > h->chunk_audio_out_cap) return 0;
     if (h->chunk_audio_cap < n) {
         if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
+    if (h->mel_window) { cudaFree(h->mel_window); cudaFree(h->mel_tw_re); cudaFree(h->mel_tw_im); cudaFree(h->mel_tri); }
         CK(cudaMalloc((void**)&h->chunk_audio_dev, n * sizeof(float)));
         h->chunk_audio_cap = n;
     }

@@ -399,4 +399,57 @@ __global__ void relu_add_kernel(const float* h, const float* res, float* y, long
         y[i] = (res ? res[i] : 0.f) + fmaxf(h[i], 0.f);
 }
 
+// ---- log-mel front end of the clone path on the device (src/io/mel.cpp:132-236; src/tts_onnx.cpp:331-359) -----------------
+// One CTA per frame: window, 1024-point radix-2 decimation-in-time FFT in shared memory (f32, the twiddle TABLE is the host's:
+// cos/sin of the f32 angle, tabulated per stage exactly as the reference evaluates them), power spectrum, HTK-mel triangles
+// summed in bin order, log(e + 1e-10). Output transposed, [frames][num_mels]: the layout speaker_encoder wants (:374-380).
+struct MelParams {
+    const float* audio; long long n;          // 24 kHz mono
+    const float* window;                      // [win]
+    const float* tw_re; const float* tw_im;   // twiddles of the log2(n_fft) stages, concatenated (n_fft - 1 entries)
+    const int* tri;                           // [num_mels][3]: left, centre, right bin
+    float* out;                               // [frames][num_mels]
+    int frames, hop, win, n_fft, log2n, num_mels;
+};
+__global__ void __launch_bounds__(256)
+logmel_kernel(const MelParams p) {
+    extern __shared__ float mel_smem[];       // re[n_fft] | im[n_fft] | pw[n_fft/2+1]
+    float* re = mel_smem; float* im = re + p.n_fft; float* pw = im + p.n_fft;
+    const int t = blockIdx.x, tid = threadIdx.x, n = p.n_fft;
+    const long long start = (long long)t * p.hop;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const long long idx = start + i;
+        const float v = (i < p.win && idx < p.n) ? p.audio[idx] * p.window[i] : 0.0f;
+        const int j = (int)(__brev((unsigned)i) >> (32 - p.log2n));          // bit-reversal permutation
+        re[j] = v; im[j] = 0.0f;
+    }
+    __syncthreads();
+    int tw0 = 0;
+    for (int size = 2; size <= n; size <<= 1) {
+        const int half = size >> 1;
+        for (int b = tid; b < (n >> 1); b += blockDim.x) {
+            const int k = b & (half - 1), base = (b - k) << 1;
+            const float wr = p.tw_re[tw0 + k], wi = p.tw_im[tw0 + k];
+            const int e = base + k, o = e + half;
+            const float tr = __fsub_rn(__fmul_rn(wr, re[o]), __fmul_rn(wi, im[o]));   // no FMA contraction: the reference's f32 butterflies
+            const float ti = __fadd_rn(__fmul_rn(wr, im[o]), __fmul_rn(wi, re[o]));
+            const float er = re[e], ei = im[e];
+            re[o] = er - tr; im[o] = ei - ti;
+            re[e] = er + tr; im[e] = ei + ti;
+        }
+        tw0 += half;
+        __syncthreads();
+    }
+    const int nb = n / 2 + 1;
+    for (int k = tid; k < nb; k += blockDim.x) pw[k] = __fadd_rn(__fmul_rn(re[k], re[k]), __fmul_rn(im[k], im[k]));
+    __syncthreads();
+    for (int m = tid; m < p.num_mels; m += blockDim.x) {
+        const int l = p.tri[m * 3], c = p.tri[m * 3 + 1], r = p.tri[m * 3 + 2];
+        float e = 0.0f;
+        for (int k = l; k < c && k < nb; ++k) e = __fadd_rn(e, __fmul_rn((float)(k - l) / (float)(c - l), pw[k]));
+        for (int k = c; k < r && k < nb; ++k) e = __fadd_rn(e, __fmul_rn((float)(r - k) / (float)(r - c), pw[k]));
+        p.out[(size_t)t * p.num_mels + m] = logf(e + 1e-10f);
+    }
+}
+
 }  // namespace lqt

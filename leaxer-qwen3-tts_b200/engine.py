@@ -20,7 +20,7 @@ SYMBOLS = [
     "lqt_talker_prefill", "lqt_talker_decode", "lqt_kv_reset", "lqt_kv_len", "lqt_code_predictor",
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
     "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange", "lqt_check_model_file",
-    "lqt_synthesize_batch", "lqt_debug_tc_gemm",
+    "lqt_synthesize_batch", "lqt_debug_tc_gemm", "lqt_log_mel", "lqt_speaker_embed_audio",
 ]
 
 
@@ -110,6 +110,8 @@ def load_library():
     lib.lqt_check_model_file.argtypes = [C.c_char_p, C.c_char_p, I32]
     lib.lqt_synthesize_batch.argtypes = [P, C.POINTER(BatchRequest), I32, C.POINTER(Sampling), C.POINTER(BatchOptions)]
     lib.lqt_debug_tc_gemm.argtypes = [P, P, P, I32, I32, I32, I32, I32, P]
+    lib.lqt_log_mel.argtypes = [P, P, I64, P, C.POINTER(I32)]
+    lib.lqt_speaker_embed_audio.argtypes = [P, P, I64, P]
     _lib = lib
     return lib
 
@@ -245,6 +247,22 @@ class Engine:
         m = _f32(mel_t).reshape(-1, 128)
         out = np.empty(self.H, np.float32)
         self._ck(self.lib.lqt_speaker_encoder(self.h, _ptr(m), m.shape[0], _ptr(out)))
+        return out
+
+    def log_mel(self, audio):
+        """24 kHz mono f32 -> log-mel [128, frames] (reference layout) computed on the device"""
+        a = _f32(audio).reshape(-1)
+        nf = max(1, (a.shape[0] - 1024) // 256 + 1) if a.shape[0] >= 1024 else 1
+        out = np.empty((128, nf), np.float32)
+        n = C.c_int32(0)
+        self._ck(self.lib.lqt_log_mel(self.h, _ptr(a), a.shape[0], _ptr(out), C.byref(n)))
+        assert n.value == nf
+        return out
+
+    def speaker_embed_audio(self, audio):
+        a = _f32(audio).reshape(-1)
+        out = np.empty(self.H, np.float32)
+        self._ck(self.lib.lqt_speaker_embed_audio(self.h, _ptr(a), a.shape[0], _ptr(out)))
         return out
 
     def sample(self, logits, sp: Sampling, frame: int, codebook: int, mask_codec_specials=False) -> int:

@@ -166,7 +166,19 @@ std::vector<float> TTSEngine::extract_speaker_embedding(const std::string& audio
     }
     if (sr != config::SAMPLE_RATE) audio = io::resample(audio, sr, config::SAMPLE_RATE);
 
-    io::MelConfig mc;                      // src/tts_onnx.cpp:347-354
+    lqt_info info{};
+    lqt_get_info(handle_, &info);
+    std::vector<float> out(static_cast<size_t>(info.hidden));
+    if (!std::getenv("LEAXER_HOST_MEL")) {
+        // log-mel (src/tts_onnx.cpp:347-359, mel config 1024/256/1024/128/0/12000) + the [frames][mels] transposition (:374-380) +
+        // the speaker encoder, all on the device: the mel never comes back to the host
+        if (lqt_speaker_embed_audio(handle_, audio.data(), static_cast<int64_t>(audio.size()), out.data()) != 0) {
+            std::cerr << "[TTSEngine] Synthesis error: " << lqt_last_error(handle_) << std::endl;
+            return {};
+        }
+        return out;
+    }
+    io::MelConfig mc;                      // host front end ($LEAXER_HOST_MEL, A/B aid): src/tts_onnx.cpp:347-354
     mc.sample_rate = config::SAMPLE_RATE; mc.n_fft = 1024; mc.hop_size = 256; mc.win_size = 1024;
     mc.num_mels = 128; mc.fmin = 0.0f; mc.fmax = 12000.0f;
     io::MelExtractor mel(mc);
@@ -180,9 +192,6 @@ std::vector<float> TTSEngine::extract_speaker_embedding(const std::string& audio
     std::vector<float> mt(m.size());
     for (size_t f = 0; f < frames; ++f)
         for (size_t b = 0; b < 128; ++b) mt[f * 128 + b] = m[b * frames + f];
-    lqt_info info{};
-    lqt_get_info(handle_, &info);
-    std::vector<float> out(static_cast<size_t>(info.hidden));
     if (lqt_speaker_encoder(handle_, mt.data(), static_cast<int32_t>(frames), out.data()) != 0) {
         std::cerr << "[TTSEngine] Synthesis error: " << lqt_last_error(handle_) << std::endl;
         return {};
