@@ -190,6 +190,62 @@ def run_reference_arm(a, mdir, token_ids):
     return 0
 
 
+def run_c5(a, rank, world, local, token_ids):
+    """BASELINE configs[4]: 1.7B talker (hidden 2048, MLP 6144; the predictor stays 1024 wide behind in_proj), long-form
+    utterances of `--frames` (default 2048 = 163.84 s) frames, 64 utterances in total split over the GPUs, through
+    lqt_synthesize_batch (the persistent batch-1 kernel does not take this shape; lqt_stats.frame_impl_active says so)."""
+    import torch
+    spec = ms.spec_1p7b(0)
+    mdir = ms.default_model_dir(spec)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if local == 0:
+        ms.generate_model_dir(mdir, spec)
+    if dist:
+        dist.barrier()
+    from leaxer_qwen3_tts_b200 import engine
+    eng = engine.Engine(mdir, device=local, frame_impl="auto")
+    frames = a.frames if a.frames != 375 else 2048
+    per = max(1, 64 // world)
+    spf = eng.info.samples_per_frame
+    ids_np = np.asarray(token_ids, np.int64)
+    reqs = [{"token_ids": ids_np, "lang": "en", "utterance_id": rank * per + u, "max_new_tokens": frames} for u in range(per)]
+    pins = [(torch.empty(frames * spf, dtype=torch.float32).pin_memory().numpy(),
+             torch.empty(frames * 16, dtype=torch.int64).pin_memory().numpy()) for _ in range(per)]
+    best = None
+    for rep in range(2):
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        outs = eng.synthesize_batch(reqs, 0.8, 50, 0.95, seed=1234, max_concurrent=per, planes=a.c4_planes, pinned=pins)
+        torch.cuda.synchronize()
+        best = (time.perf_counter() - t0, sum(o[1].shape[0] for o in outs))
+    v = torch.tensor([best[0]], dtype=torch.float64, device=f"cuda:{local}")
+    n = torch.tensor([float(best[1])], dtype=torch.float64, device=f"cuda:{local}")
+    if dist:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        line = {"metric": METRIC, "value": float(n.item()) * FRAME_S / float(v.item()), "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": float(v.item()) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": f"1.7B talker, {per * world} utterances of {frames} frames ({frames * FRAME_S:.2f} s) each, {per} per GPU, "
+                                       f"planes={a.c4_planes} [BASELINE.json configs[4]]", "spec": spec.name, "frames": frames,
+                           "frame_impl_active": int(eng.stats().frame_impl_active), "parallelism": f"dp{world} (request-level, no collective)"},
+                "e2e": {"value": float(n.item()) * FRAME_S / float(v.item()), "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes * per),
+                        "d2h_bytes_per_step": int((frames * spf * 4 + frames * 16 * 8) * per)},
+                "gpu_launches": int(eng.stats().kernel_launches)}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
 def parity_check(eng, a) -> dict:
     """Outside the timed region: the benchmarked configuration against the committed oracle golden
     (tests/golden/c2_full_375.npz, written by tests/golden/make_c2_golden.py from oracle/qwen3_tts_oracle.py).
@@ -234,6 +290,9 @@ def main():
     ap.add_argument("--c4-utterances", type=int, default=256,
                     help="BASELINE configs[3] leg (after the headline): this many concurrent utterances IN TOTAL, split evenly over the "
                          "GPUs, through lqt_synthesize_batch (tcgen05 GEMM path); 0 = skip")
+    ap.add_argument("--c5", action="store_true",
+                    help="BASELINE configs[4] leg instead of the headline: 1.7B talker, 2048 frames (163.84 s) per utterance, 64 utterances "
+                         "split over the GPUs (8 per GPU at 8 GPUs), batched tcgen05 path")
     ap.add_argument("--c4-planes", type=int, default=2, help="bf16 planes per activation in the batched leg (3 = fp32-exact, 2 = 16-bit mantissa)")
     ap.add_argument("--cpu-frames", type=int, default=150, help="frames in the cpu_baseline sample (~10-30 s of CPU work)")
     ap.add_argument("--frame-impl", default="persistent", choices=["persistent", "graph"],
@@ -254,6 +313,8 @@ def main():
         if rank == 0:
             ms.generate_model_dir(mdir, spec)
         return run_reference_arm(a, mdir, token_ids)
+    if a.c5:
+        return run_c5(a, rank, world, local, token_ids)
 
     import torch
     if not torch.cuda.is_available():

@@ -51,7 +51,7 @@ typedef struct lqt_stats {
     float    last_total_ms;       /* lqt_synthesize_tokens: CUDA-event time prompt build -> last vocoder kernel */
     float    first_audio_ms;      /* lqt_synthesize_tokens: CUDA-event time prompt build -> the first chunk of PCM (2 s) copied into
                                      the caller's buffer (chunked vocoding on a second stream); = last_total_ms when chunking is off */
-    int32_t  frame_impl_active;   /* the frame loop this handle actually runs: LQT_FRAME_PERSISTENT or LQT_FRAME_GRAPH */
+    int32_t  frame_impl_active;   /* the frame loop lqt_synthesize_tokens runs on this handle: LQT_FRAME_PERSISTENT, _BATCHED or _GRAPH */
     int32_t  cooperative_launch;  /* 1 = the persistent kernel is launched with the cooperative attribute (co-residency guaranteed);
                                      0 = refused by the driver/profiler: the second-stream first-audio overlap is then switched off */
 } lqt_stats;
@@ -63,10 +63,13 @@ enum { LQT_KV_BF16 = 0, LQT_KV_F32 = 1 };
 /* frame_impl: LQT_FRAME_PERSISTENT (default) = loops A+B run inside one persistent cooperative kernel
  * whose producer warp streams the weights with TMA bulk copies; LQT_FRAME_GRAPH = the round-1 v1
  * schedule (a CUDA graph of ~577 per-op kernels per frame), kept only for A/B measurements. */
-/* LQT_FRAME_AUTO = persistent where the model shape fits the kernel, else the graph (what lqt_create uses; the choice is
- * reported in lqt_stats.frame_impl_active). An explicit LQT_FRAME_PERSISTENT is strict: lqt_create_ex FAILS with the reason
- * instead of falling back. */
-enum { LQT_FRAME_PERSISTENT = 0, LQT_FRAME_GRAPH = 1, LQT_FRAME_AUTO = 2 };
+/* LQT_FRAME_AUTO (what lqt_create uses) = the persistent kernel where the model shape fits it, else LQT_FRAME_BATCHED: the
+ * batched path's CUDA graph of TMA-fed tcgen05 GEMM kernels with a single KV slot (any hidden / MLP width that is a multiple
+ * of 64 / 128, e.g. the 1.7B talker). The choice is reported in lqt_stats.frame_impl_active. An explicit
+ * LQT_FRAME_PERSISTENT is strict: lqt_create_ex FAILS with the reason instead of falling back. LQT_FRAME_GRAPH is the
+ * round-1 graph of per-op GEMV kernels, kept for A/B only; on a LQT_FRAME_BATCHED handle it still backs the per-graph
+ * parity entry points (lqt_talker_prefill/decode, lqt_code_predictor, lqt_generate). */
+enum { LQT_FRAME_PERSISTENT = 0, LQT_FRAME_GRAPH = 1, LQT_FRAME_AUTO = 2, LQT_FRAME_BATCHED = 3 };
 typedef struct lqt_options {
     int32_t kv_dtype;
     int32_t n_slots;      /* KV slots (utterances resident at once); 0 = default (2) */

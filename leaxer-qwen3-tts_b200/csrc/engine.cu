@@ -1245,14 +1245,14 @@ int init_engine(lqt_engine* h, const std::string& dir) {
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     if (const char* e = getenv("LQT_FIRST_CHUNK")) h->first_chunk = std::max(0, atoi(e));
     if (voc_tc_init(h)) return 1;
-    if (h->frame_impl != LQT_FRAME_GRAPH && fk_init(h)) {
+    if (h->frame_impl != LQT_FRAME_GRAPH && h->frame_impl != LQT_FRAME_BATCHED && fk_init(h)) {
         // shapes the persistent kernel does not cover (e.g. the 1.7B talker: > 64 rows per CTA). An explicit request for the
         // persistent kernel fails here, loudly; LQT_FRAME_AUTO runs loops A+B as the CUDA graph of per-op sm_100a kernels instead
         // (still device-only; there is no CPU path) and says so in lqt_stats.frame_impl_active.
         if (h->frame_impl == LQT_FRAME_PERSISTENT) { h->err = "persistent frame kernel unavailable for this model: " + h->err; return 1; }
-        fprintf(stderr, "[lqt] persistent frame kernel unavailable (%s): using the graph-of-kernels frame loop\n", h->err.c_str());
+        fprintf(stderr, "[lqt] persistent frame kernel unavailable (%s): lqt_synthesize_tokens runs the batched tcgen05 path with one slot\n", h->err.c_str());
         h->err.clear();
-        h->frame_impl = LQT_FRAME_GRAPH;
+        h->frame_impl = LQT_FRAME_BATCHED;
     }
     if (h->frame_impl == LQT_FRAME_AUTO) h->frame_impl = LQT_FRAME_PERSISTENT;
     return 0;
@@ -1316,7 +1316,7 @@ int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, 
         if (opt->kv_dtype != LQT_KV_BF16 && opt->kv_dtype != LQT_KV_F32) { g_create_error = "bad kv_dtype"; delete h; return 1; }
         h->kv_f32 = opt->kv_dtype == LQT_KV_F32;
         if (opt->n_slots > 0) h->n_slots = opt->n_slots;
-        if (opt->frame_impl != LQT_FRAME_PERSISTENT && opt->frame_impl != LQT_FRAME_GRAPH && opt->frame_impl != LQT_FRAME_AUTO) { g_create_error = "bad frame_impl"; delete h; return 1; }
+        if (opt->frame_impl < LQT_FRAME_PERSISTENT || opt->frame_impl > LQT_FRAME_BATCHED) { g_create_error = "bad frame_impl"; delete h; return 1; }
         h->frame_impl = opt->frame_impl;
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1781,6 +1781,20 @@ static int synthesize_tokens_impl(lqt_engine* h, const int64_t* token_ids, int32
                                   const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
                                   int64_t* codes_out, int32_t* n_frames) {
     *n_samples = 0;
+    if (h->frame_impl == LQT_FRAME_BATCHED) {            // shapes the persistent kernel does not take (1.7B): one slot of the batched path
+        lqt_batch_request rq{};
+        rq.token_ids = token_ids; rq.n_ids = n_ids; rq.lang_codec_id = lang_codec_id; rq.speaker_embed = speaker_embed;
+        rq.utterance_id = sp->utterance_id; rq.max_new_tokens = sp->max_new_tokens;
+        rq.audio_out = audio_out; rq.audio_capacity = audio_capacity; rq.n_samples = n_samples; rq.codes_out = codes_out;
+        int32_t nf = 0; rq.n_frames = &nf;
+        std::vector<int64_t> codes_tmp;
+        if (!codes_out) { codes_tmp.resize((size_t)std::max(sp->max_new_tokens, 1) * N_CODEBOOKS); rq.codes_out = codes_tmp.data(); }
+        lqt_batch_options bo{}; bo.max_concurrent = 1; bo.planes = 3; bo.poll_frames = 8;
+        if (synthesize_batch_impl(h, &rq, 1, sp, &bo)) return 1;
+        if (n_frames) *n_frames = nf;
+        h->stats.first_audio_ms = h->stats.last_total_ms;
+        return 0;
+    }
     if (n_frames) *n_frames = 0;
     int P = 0, TL = 0;
     CK(cudaEventRecord(h->ev_t0, h->stream));

@@ -48,7 +48,7 @@ class Stats(C.Structure):
                 ("frame_impl_active", C.c_int32), ("cooperative_launch", C.c_int32)]
 
 
-FRAME_IMPL = {"persistent": 0, "graph": 1, "auto": 2}      # include/lqt_b200.h LQT_FRAME_*
+FRAME_IMPL = {"persistent": 0, "graph": 1, "auto": 2, "batched": 3}      # include/lqt_b200.h LQT_FRAME_*
 
 
 class BatchRequest(C.Structure):

@@ -148,3 +148,26 @@ def test_batch_1p7b_shape(request):
             assert rel_l2(audio, ref_audio) < WAVE_REL_L2
     finally:
         eng.close()
+
+
+def test_batch_real_1p7b_dims(request):
+    """BASELINE configs[4] at the REAL 1.7B dimensions (28 talker layers of hidden 2048 / MLP 6144, predictor 5 x 1024 behind
+    in_proj): two utterances, a few frames, token-exact against the oracle; the engine reports that the persistent kernel
+    does not take this shape (frame_impl_active = batched): the tcgen05 path runs it."""
+    from leaxer_qwen3_tts_b200 import engine, modelspec
+    orc = request.getfixturevalue("oracle_mod")
+    spec = modelspec.spec_1p7b(0)
+    d = modelspec.generate_model_dir(modelspec.default_model_dir(spec), spec)
+    # fp32 KV on both sides (the engine's parity mode): with bf16 KV a K/V value on a rounding boundary moves the logits by ~1e-2
+    # and the seeded draw with it (first seen at frame 2 here) -- the same effect the batch-1 path shows after 146 frames
+    m = orc.OracleModel(d, kv_bf16=False)
+    eng = engine.Engine(d, device=0, frame_impl="auto", kv_dtype="f32")
+    try:
+        assert eng.info.hidden == 2048 and eng.stats().frame_impl_active == engine.FRAME_IMPL["batched"]
+        specs = [([9707, 1879, 11], "en", 0, 3, 0), ([21, 22], "ja", 0, 2, 1)]
+        reqs, refs = _requests(orc, m, specs)
+        outs = eng.synthesize_batch(reqs, 0.8, 50, 0.95, seed=1234, planes=3, vocode=False)
+        for (_, codes), (_, ref_codes) in zip(outs, refs):
+            assert np.array_equal(codes, ref_codes), np.argwhere(codes != ref_codes)[:4]
+    finally:
+        eng.close()

@@ -502,7 +502,14 @@ def test_strict_persistent_fails_loudly_and_auto_reports(request):
     with pytest.raises(engine.EngineError, match="persistent frame kernel unavailable"):
         engine.Engine(d, device=0, frame_impl="persistent")
     e = engine.Engine(d, device=0, frame_impl="auto")
-    assert e.stats().frame_impl_active == engine.FRAME_IMPL["graph"]
+    assert e.stats().frame_impl_active == engine.FRAME_IMPL["batched"]
+    # ... and the plain single-utterance call works on such a handle (one slot of the batched tcgen05 path), token-exact
+    orc = request.getfixturevalue("oracle_mod")
+    ids = orc.wrap_text_ids([31, 32, 33])
+    sp = orc.SamplingParams(temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=5, seed=11, utterance_id=2)
+    ref_audio, ref_codes = orc.synthesize_tokens(orc.OracleModel(d), ids, "en", sp)
+    audio, codes = e.synthesize_tokens(ids, "en", 0.8, 50, 0.95, 5, 11, 2)
+    assert np.array_equal(codes, ref_codes) and rel_l2(audio, ref_audio) < WAVE_REL_L2
     e.close()
     assert request.getfixturevalue("tiny_engine").stats().frame_impl_active == engine.FRAME_IMPL["persistent"]
 
