@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--c4-utterances", type=int, default=256,
                     help="BASELINE configs[3] leg (after the headline): this many concurrent utterances IN TOTAL, split evenly over the "
                          "GPUs, through lqt_synthesize_batch (tcgen05 GEMM path); 0 = skip")
+    ap.add_argument("--no-c3", action="store_true", help="skip the voice-clone leg (BASELINE configs[2])")
     ap.add_argument("--c5", action="store_true",
                     help="BASELINE configs[4] leg instead of the headline: 1.7B talker, 2048 frames (163.84 s) per utterance, 64 utterances "
                          "split over the GPUs (8 per GPU at 8 GPUs), batched tcgen05 path")
@@ -413,6 +414,31 @@ def main():
                       "max over ranks; strong scaling: the total is fixed, each GPU takes total / n_gpus utterances"}
         log(f"[bench] c4: {c4}")
 
+    # ---- BASELINE configs[2]: voice clone (3 s synthetic reference clip -> device log-mel -> speaker encoder -> prompt row),
+    # zh/ja/ko prompts, 125 frames, batch 1 (rank 0 only: a latency figure, not a scaling one) ------------------------------
+    c3 = None
+    if rank == 0 and a.spec == "0.6b" and not a.no_c3:
+        t = np.arange(72000) / 24000.0
+        clip = (0.4 * np.sin(2 * np.pi * 220 * t) + 0.25 * np.sin(2 * np.pi * 1330 * t) + 0.1 * np.sin(2 * np.pi * 5100 * t)
+                + 0.02 * np.random.default_rng(3).standard_normal(72000)).astype(np.float32)
+        c3_ids = np.asarray(wrap_text_ids(ms.synthetic_text_ids(30, 77)), np.int64)
+        walls = []
+        for i, lang in enumerate(["zh", "ja", "ko", "zh", "ja", "ko"]):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            spk = eng.speaker_embed_audio(clip)
+            audio, codes = eng.synthesize_tokens(c3_ids, lang, 0.8, 50, 0.95, 125, 1234, 9000 + i, speaker_embed=spk,
+                                                 audio_out=audio_pin, codes_out=codes_pin)
+            torch.cuda.synchronize()
+            if i >= 3:
+                walls.append(time.perf_counter() - t0)
+            assert codes.shape[0] == 125
+        c3 = {"workload": "voice clone: 3 s 24 kHz synthetic reference clip (host f32) -> log-mel + speaker encoder on the device -> "
+                          "125 frames (10 s), zh/ja/ko, batch 1 [BASELINE.json configs[2]]",
+              "value": 125 * FRAME_S / statistics.median(walls), "unit": UNIT, "ms_per_utterance_p50": statistics.median(walls) * 1e3,
+              "h2d_bytes": int(clip.nbytes + c3_ids.nbytes)}
+        log(f"[bench] c3: {c3}")
+
     vals = torch.tensor([wall, dev_ms, gen_ms, voc_ms], dtype=torch.float64, device=f"cuda:{local}")
     tot = torch.tensor([float(frames), float(st.kernel_launches)], dtype=torch.float64, device=f"cuda:{local}")
     if dist:
@@ -472,6 +498,7 @@ def main():
                 "ms_per_step": wall_max / a.steps * 1e3,
                 "first_audio_ms_p50": statistics.median(first_ms) if first_ms else None,
                 "full_utterance_ms_p50": wall_max / a.steps / a.utterances * 1e3},
+        "c3_clone": c3,
         "c4_batched": c4,
         "parity_checked": bool(parity and parity.get("parity_checked")),
         "parity": parity,
