@@ -119,6 +119,13 @@ int lqt_code_predictor(lqt_engine* h, const float* embeds, int32_t L, int64_t ge
  * `audio` must hold T * samples_per_frame floats. */
 int lqt_vocoder_decode(lqt_engine* h, const int64_t* codes, int32_t T, float* audio,
                        int64_t* length);
+/* Streaming form of the same graph (the reference vocodes once at the end, :430): the codes of one utterance are
+ * handed over in chunks of any size, in order; every layer with left context (pre_conv, the 72-position attention window, the
+ * depthwise and k = 7 dilated convolutions, the transposed convolutions) keeps its tail between calls, so the concatenated
+ * chunks are BIT-IDENTICAL to lqt_vocoder_decode of the whole sequence and nothing is decoded twice. reset starts a new
+ * utterance. */
+int lqt_vocoder_stream_reset(lqt_engine* h);
+int lqt_vocoder_stream_chunk(lqt_engine* h, const int64_t* codes, int32_t T, float* audio, int64_t* length);
 /* speaker_encoder.onnx  :367-403: log-mel f32 [1,frames,128] -> embedding [H] */
 int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float* out);
 /* Clone front end on the device: extract_speaker_embedding's log-mel (src/tts_onnx.cpp:331-359 with

@@ -245,6 +245,8 @@ struct WinAttnParams {
     const float* rope_cos; const float* rope_sin;   // [max_pos][32]
     int T, n_heads, window;
     float scale;
+    int pos0;                  // absolute position of row 0 (streaming decode: rows are a chunk of a longer sequence)
+    int hist;                  // rows [-hist, 0) in front of qkv hold the q|k|v of the previous positions (<= window - 1)
 };
 
 __global__ void __launch_bounds__(256)
@@ -263,16 +265,16 @@ window_attn_kernel(const WinAttnParams p) {
         b = x2 * c + x1 * s;
     };
     float q1, q2;
-    rope(p.qkv + (size_t)i * row + h * D, i, q1, q2);
-    const int j0 = max(0, i - p.window + 1);
+    rope(p.qkv + (size_t)i * row + h * D, p.pos0 + i, q1, q2);
+    const int j0 = max(-p.hist, i - p.window + 1);
     float m = -INFINITY, l = 0.f, o1 = 0.f, o2 = 0.f;
     for (int j = j0; j <= i; ++j) {
         float k1, k2;
-        rope(p.qkv + (size_t)j * row + qd + h * D, j, k1, k2);
+        rope(p.qkv + (long long)j * row + qd + h * D, p.pos0 + j, k1, k2);
         const float s = warp_sum(q1 * k1 + q2 * k2) * p.scale;
         const float mn = fmaxf(m, s);
         const float corr = expf(m - mn), pr = expf(s - mn);
-        const float* v = p.qkv + (size_t)j * row + 2 * qd + h * D;
+        const float* v = p.qkv + (long long)j * row + 2 * qd + h * D;
         l = l * corr + pr;
         o1 = o1 * corr + pr * v[lane];
         o2 = o2 * corr + pr * v[lane + 32];

@@ -78,6 +78,8 @@ namespace { struct VocTcModel; }
 struct lqt_engine {
     int device = 0;
     lqt_batch* batch = nullptr;               // batched path context (batch_engine.inl), created on first use
+    // streaming vocoder (lqt_vocoder_stream_*): frames decoded so far + the tail every layer with left context keeps between chunks
+    struct VocStream { int t0 = 0; std::map<std::string, std::pair<void*, size_t>> halo; } voc_stream;
     float *mel_window = nullptr, *mel_tw_re = nullptr, *mel_tw_im = nullptr; int* mel_tri = nullptr;   // log-mel tables (lqt_log_mel)
     VocTcModel* voc_tc = nullptr;             // tcgen05 vocoder decoder (voc_tc.inl): padded weights, SnakeBeta constants, plane buffers
     int num_sms = 148;
@@ -573,14 +575,43 @@ int build_prompt_device(lqt_engine* h, const int64_t* ids, int n, int lang_id, c
 #include "voc_tc.inl"
 
 // tokenizer12hz_decode (src/tts_onnx.cpp:759-776) on device codes [T][16] -> audio_dev [T*spf]
-int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, cudaStream_t vstream = nullptr) {
+// STREAMING (vs != nullptr): codes are frames [vs->t0, vs->t0 + T) of a longer utterance. Every op with left context (pre_conv, the
+// window attention's K/V, the depthwise convs, every k > 1 convolution of the decoder, the final conv) finds the previous chunk's
+// tail in the rows in FRONT of its input (copied in from the per-site state before it runs, saved again afterwards), so a chunk
+// computes exactly what the one-shot decode computes for those frames -- bit for bit (same per-element arithmetic, same K order).
+int voc_halo(lqt_engine* h, lqt_engine::VocStream* vs, const std::string& key, void* row0, size_t row_bytes, int halo_rows, long long n_rows) {
+    if (!vs || halo_rows <= 0) return 0;
+    auto& st = vs->halo[key];
+    const size_t bytes = (size_t)halo_rows * row_bytes;
+    if (st.second != bytes) {
+        if (st.first) cudaFree(st.first);
+        st.first = nullptr; st.second = 0;
+        CK(cudaMalloc(&st.first, bytes));
+        CK(cudaMemsetAsync(st.first, 0, bytes, h->stream));          // before the first frame: zeros = the causal padding
+        st.second = bytes;
+    }
+    char* r0 = reinterpret_cast<char*>(row0);
+    CK(cudaMemcpyAsync(r0 - bytes, st.first, bytes, cudaMemcpyDeviceToDevice, h->stream));                       // previous tail in front of row 0
+    CK(cudaMemcpyAsync(st.first, r0 + (n_rows - halo_rows) * (long long)row_bytes, bytes, cudaMemcpyDeviceToDevice, h->stream));   // new tail
+    return 0;
+}
+void voc_stream_clear(lqt_engine* h) {
+    for (auto& e : h->voc_stream.halo) if (e.second.first) cudaFree(e.second.first);
+    h->voc_stream.halo.clear();
+    h->voc_stream.t0 = 0;
+}
+
+int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, cudaStream_t vstream = nullptr, lqt_engine::VocStream* vs = nullptr) {
     // every launch below goes to h->stream: a caller that wants another stream (the first-audio chunk) passes it here and the
     // handle's stream is swapped for the duration of the enqueue only (one host thread per handle, include/lqt_b200.h)
     struct StreamSwap { lqt_engine* h; cudaStream_t keep; StreamSwap(lqt_engine* e, cudaStream_t v) : h(e), keep(e->stream) { if (v) e->stream = v; } ~StreamSwap() { h->stream = keep; } } swap_(h, vstream);
     const Spec& s = h->sp;
     const int Dc = s.voc_codebook_dim, R = s.voc_rvq_out, Cv = s.voc_hidden, I = s.voc_inter;
     const int vqd = s.voc_heads * s.voc_head_dim;
-    if (T > s.voc_max_pos) { h->err = "vocoder: too many frames"; return 1; }
+    const int t0 = vs ? vs->t0 : 0;
+    if (t0 + T > s.voc_max_pos) { h->err = "vocoder: too many frames"; return 1; }
+    // front margin of every workspace buffer: room for the largest left context (the attention window) of the widest row
+    const size_t margin = (size_t)std::max(s.voc_window, 64) * std::max(std::max(3 * vqd, I), std::max(4 * Cv, s.voc_decoder_dim));
     // largest activation (elements) over all stages
     size_t maxel = (size_t)T * std::max(std::max(3 * vqd, I), std::max(Cv, R));
     {
@@ -590,9 +621,10 @@ int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, 
         int c = s.voc_decoder_dim;
         for (int r : s.voc_up_rates) { L *= r; c /= 2; maxel = std::max(maxel, L * (size_t)c); }
     }
-    float* b0 = wsbuf(h, "v0", maxel); float* b1 = wsbuf(h, "v1", maxel);
-    float* b2 = wsbuf(h, "v2", maxel); float* b3 = wsbuf(h, "v3", maxel);
+    float* b0 = wsbuf(h, "v0", maxel + margin); float* b1 = wsbuf(h, "v1", maxel + margin);
+    float* b2 = wsbuf(h, "v2", maxel + margin); float* b3 = wsbuf(h, "v3", maxel + margin);
     if (!b0 || !b1 || !b2 || !b3) return 1;
+    b0 += margin; b1 += margin; b2 += margin; b3 += margin;
 
     // RVQ gather-sum + 1x1 output projections
     float *sem = b1, *aco = b2;
@@ -603,7 +635,8 @@ int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, 
     { ConvGemmParams p = cg(aco, T, Dc, h->rvq_aco_proj, R, b0); p.residual = b0; launch_conv_gemm(h, p); }
     // pre_conv k3
     float* xa = b3;
-    { ConvGemmParams p = cg(b0, T, R, h->pre_conv_w, Cv, xa); p.taps = 3; p.bias = h->pre_conv_b; launch_conv_gemm(h, p); }
+    if (voc_halo(h, vs, "pre_conv", b0, (size_t)R * 4, 2, T)) return 1;
+    { ConvGemmParams p = cg(b0, T, R, h->pre_conv_w, Cv, xa); p.taps = 3; p.bias = h->pre_conv_b; p.hist = vs ? 2 : 0; launch_conv_gemm(h, p); }
     // pre-transformer (sliding-window attention, LayerScale)
     for (int l = 0; l < s.voc_layers; ++l) {
         const LayerW& L = h->vl[l];
@@ -613,6 +646,8 @@ int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, 
         WinAttnParams w{};
         w.qkv = b1; w.out = b2; w.rope_cos = h->v_cos; w.rope_sin = h->v_sin; w.T = T; w.n_heads = s.voc_heads;
         w.window = s.voc_window; w.scale = 1.0f / sqrtf((float)s.voc_head_dim);
+        w.pos0 = t0; w.hist = std::min(t0, s.voc_window - 1);
+        if (voc_halo(h, vs, "att" + std::to_string(l), b1, (size_t)3 * vqd * 4, s.voc_window - 1, T)) return 1;
         window_attn_kernel<<<(int)(((long long)T * s.voc_heads + 7) / 8), 256, 0, h->stream>>>(w);
         h->stats.kernel_launches++;
         { ConvGemmParams p = cg(b2, T, vqd, L.wo, Cv, xa); p.scale = L.ls1; p.residual = xa; launch_conv_gemm(h, p); }
@@ -633,35 +668,40 @@ int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, 
         const VocUpW& U = h->vup[u];
         { ConvGemmParams p = cg(cur, L, Cv, U.tconv_w, U.factor * Cv, o1); p.bias = U.tconv_b; p.bias_mod = Cv; launch_conv_gemm(h, p); }
         L *= U.factor;
-        dwconv_ln_kernel<<<L, 256, Cv * sizeof(float), h->stream>>>(o1, o2, L, Cv, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f);
+        if (voc_halo(h, vs, "dw" + std::to_string(u), o1, (size_t)Cv * 4, 6, L)) return 1;
+        dwconv_ln_kernel<<<L, 256, Cv * sizeof(float), h->stream>>>(o1, o2, L, Cv, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f, vs ? 6 : 0);
         h->stats.kernel_launches++;
         { ConvGemmParams p = cg(o2, L, Cv, U.pw1_w, 4 * Cv, o3); p.bias = U.pw1_b; p.act = 3; launch_conv_gemm(h, p); }
         { ConvGemmParams p = cg(o3, L, 4 * Cv, U.pw2_w, Cv, cur); p.bias = U.pw2_b; p.scale = U.gamma; p.residual = o1; launch_conv_gemm(h, p); }
     }
     // decoder: TMA-fed tcgen05 implicit-GEMM convolutions with fused SnakeBeta (tc_conv.cuh) ...
-    if (h->voc_tc && h->voc_tc->ready) return voc_tc_decoder(h, cur, L, audio);
+    if (h->voc_tc && h->voc_tc->ready) return voc_tc_decoder(h, cur, L, audio, vs);
     // ... or the round-1 kernels (mma.sync implicit GEMM on fp32 activations + separate SnakeBeta passes; LQT_VOC_TC=0)
-    { ConvGemmParams p = cg(cur, L, Cv, h->dec_in_w, s.voc_decoder_dim, o1); p.taps = 7; p.bias = h->dec_in_b; launch_conv_gemm(h, p); }
+    if (voc_halo(h, vs, "dec_in", cur, (size_t)Cv * 4, 6, L)) return 1;
+    { ConvGemmParams p = cg(cur, L, Cv, h->dec_in_w, s.voc_decoder_dim, o1); p.taps = 7; p.bias = h->dec_in_b; p.hist = vs ? 6 : 0; launch_conv_gemm(h, p); }
     float* t = o1;                       // running activation
     float* fa = cur; float* fb = o2;                      // free buffers (o3 unused from here)
     for (size_t b = 0; b < h->vblk.size(); ++b) {
         const VocBlockW& B = h->vblk[b];
         launch_snake(h, t, fa, (long long)L * B.cin, B.cin, B.snake_a, B.snake_b);
-        { ConvGemmParams p = cg(fa, L, B.cin, B.tconv_w, B.stride * B.cout, fb); p.taps = 2; p.tap_rev = 1; p.bias = B.tconv_b; p.bias_mod = B.cout; launch_conv_gemm(h, p); }
+        if (voc_halo(h, vs, "tconv" + std::to_string(b), fa, (size_t)B.cin * 4, 1, L)) return 1;
+        { ConvGemmParams p = cg(fa, L, B.cin, B.tconv_w, B.stride * B.cout, fb); p.taps = 2; p.tap_rev = 1; p.bias = B.tconv_b; p.bias_mod = B.cout; p.hist = vs ? 1 : 0; launch_conv_gemm(h, p); }
         L *= B.stride;
         std::swap(t, fb);                // t = tconv output; fb = old t (free)
         const int dil[3] = {1, 3, 9};
         for (int r = 0; r < 3; ++r) {
             const auto& Rr = B.res[r];
             launch_snake(h, t, fa, (long long)L * B.cout, B.cout, Rr.s1a, Rr.s1b);
-            { ConvGemmParams p = cg(fa, L, B.cout, Rr.c1w, B.cout, fb); p.taps = 7; p.dil = dil[r]; p.bias = Rr.c1b; launch_conv_gemm(h, p); }
+            if (voc_halo(h, vs, "c1_" + std::to_string(b) + "_" + std::to_string(r), fa, (size_t)B.cout * 4, 6 * dil[r], L)) return 1;
+            { ConvGemmParams p = cg(fa, L, B.cout, Rr.c1w, B.cout, fb); p.taps = 7; p.dil = dil[r]; p.bias = Rr.c1b; p.hist = vs ? 6 * dil[r] : 0; launch_conv_gemm(h, p); }
             launch_snake(h, fb, fa, (long long)L * B.cout, B.cout, Rr.s2a, Rr.s2b);
             { ConvGemmParams p = cg(fa, L, B.cout, Rr.c2w, B.cout, t); p.bias = Rr.c2b; p.residual = t; launch_conv_gemm(h, p); }
         }
     }
     const int Cl = h->vblk.empty() ? s.voc_decoder_dim : h->vblk.back().cout;
     launch_snake(h, t, fa, (long long)L * Cl, Cl, h->out_sa, h->out_sb);
-    conv_out_kernel<<<(L + 7) / 8, 256, 0, h->stream>>>(fa, audio, L, Cl, h->out_w, h->out_b);
+    if (voc_halo(h, vs, "conv_out", fa, (size_t)Cl * 4, 6, L)) return 1;
+    conv_out_kernel<<<(L + 7) / 8, 256, 0, h->stream>>>(fa, audio, L, Cl, h->out_w, h->out_b, vs ? 6 : 0);
     h->stats.kernel_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1337,6 +1377,7 @@ void lqt_destroy(lqt_engine* h) {
     cudaDeviceSynchronize();
     batch_destroy(h->batch); h->batch = nullptr;
     voc_tc_destroy(h);
+    voc_stream_clear(h);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
     for (auto& w : h->ws) if (w.second.first) cudaFree(w.second.first);
     void* bufs[] = {h->x, h->qkv, h->attn, h->act, h->logits, h->last_hidden, h->cx, h->cxin, h->cqkv, h->cattn, h->cact,
@@ -1590,6 +1631,30 @@ int lqt_speaker_embed_audio(lqt_engine* h, const float* audio, int64_t n_samples
     int nf = 0;
     if (logmel_device(h, audio, n_samples, &nf)) return 1;
     return speaker_encoder_device(h, nf, out);
+}
+
+int lqt_vocoder_stream_reset(lqt_engine* h) {
+    if (!h) return 1;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    voc_stream_clear(h);
+    return 0;
+}
+
+int lqt_vocoder_stream_chunk(lqt_engine* h, const int64_t* codes, int32_t T, float* audio, int64_t* length) {
+    if (!h || !codes || !audio || T <= 0) return 1;
+    cudaSetDevice(h->device);
+    for (long long i = 0; i < (long long)T * N_CODEBOOKS; ++i)
+        if (codes[i] < 0 || codes[i] >= h->sp.voc_codebook_size) { h->err = "audio code out of range"; return 1; }
+    if (ensure_audio(h, T)) return 1;
+    CK(cudaMemcpyAsync(h->voc_codes_dev, codes, (size_t)T * N_CODEBOOKS * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (run_vocoder(h, h->voc_codes_dev, T, h->audio_dev, nullptr, &h->voc_stream)) return 1;
+    h->voc_stream.t0 += T;
+    const size_t n = (size_t)T * h->sp.samples_per_frame;
+    CK(cudaMemcpyAsync(audio, h->audio_dev, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (length) *length = (int64_t)n;
+    return 0;
 }
 
 int lqt_speaker_encoder(lqt_engine* h, const float* mel_t, int32_t frames, float* out) {

@@ -27,6 +27,7 @@ struct TcConvParams {
     int BN;                    // channel tile (multiple of 16, <= 256)
     int taps, dil, tap_rev;    // tap t reads x[l - (taps-1-t)*dil] (causal conv) or x[l - t*dil] (tap_rev: transposed conv)
     int planes, Cp;            // input planes, padded input channels (multiple of 64)
+    int x_row0;                // row of the tensor map that is position 0 (streaming decode: the rows before it are the previous chunk's tail)
     int stages;
     const float* bias; int bias_mod;        // nullable; index n % bias_mod
     int act;                                // 0 none, 1 SiLU, 3 GELU(erf), after the bias
@@ -93,7 +94,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             if (i >= p.stages) tg_mbar_wait(&sh->empty[s], (uint32_t)((i / p.stages) - 1) & 1u);
                             unsigned char* a = smem + (size_t)s * stage_bytes;
                             tg_mbar_expect_tx(&sh->full[s], bytes);
-                            tg_tma_2d(a, &map_x, pl * p.Cp + kb * TG_BK, l0 + off, &sh->full[s]);    // rows < 0: zero fill = causal padding
+                            tg_tma_2d(a, &map_x, pl * p.Cp + kb * TG_BK, p.x_row0 + l0 + off, &sh->full[s]);    // rows < 0: zero fill = causal padding
                             tg_tma_2d(a + TG_BM * 128, &map_w, t * p.Cp + kb * TG_BK, n0, &sh->full[s]);
                         }
                 }

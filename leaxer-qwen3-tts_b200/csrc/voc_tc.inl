@@ -3,6 +3,8 @@
 // implicit-GEMM launch per convolution whose epilogue already applies the next SnakeBeta and writes the bf16 planes.
 // (included inside engine.cu's anonymous namespace)
 
+int voc_halo(lqt_engine* h, lqt_engine::VocStream* vs, const std::string& key, void* row0, size_t row_bytes, int halo_rows, long long n_rows);
+
 struct VocTcW {                 // per convolution: zero-padded weights [N][taps][Cp] + bias
     bf16* w = nullptr; const float* bias = nullptr;
     int N = 0, taps = 1, Cin = 0, Cp = 0, bias_mod = 0;
@@ -95,10 +97,12 @@ struct VocTcOut {               // what one convolution's epilogue produces
     bf16* xo = nullptr; int cout = 0, up = 1; const VocTcSnake* sn = nullptr;
 };
 
-int voc_tc_conv(lqt_engine* h, VocTcModel* m, const VocTcW& W, const bf16* x, long long L, int dil, bool tap_rev, const VocTcOut& o) {
+// x: planes of position 0; `halo` rows in front of it hold the previous chunk's tail (streaming decode), else 0
+int voc_tc_conv(lqt_engine* h, VocTcModel* m, const VocTcW& W, const bf16* x, long long L, int dil, bool tap_rev, const VocTcOut& o, int halo = 0) {
     CUtensorMap mx;
-    if (make_map(h, &mx, x, L, m->planes * W.Cp, TG_BM)) return 1;
+    if (make_map(h, &mx, x - (size_t)halo * m->planes * W.Cp, L + halo, m->planes * W.Cp, TG_BM)) return 1;
     TcConvParams p{};
+    p.x_row0 = halo;
     p.L = (int)L; p.N = W.N; p.BN = W.BN; p.taps = W.taps; p.dil = dil; p.tap_rev = tap_rev ? 1 : 0;
     p.planes = m->planes; p.Cp = W.Cp;
     p.bias = W.bias; p.bias_mod = W.bias_mod; p.residual = o.residual; p.scale = o.scale; p.act = o.act; p.y = o.y; p.y_snake = o.y_snake ? 1 : 0;
@@ -135,25 +139,29 @@ bool voc_tc_try(lqt_engine* h, const ConvGemmParams& c) {
     }
     VocTcW w = it->second;
     w.bias = c.bias; w.bias_mod = c.bias_mod > 0 ? c.bias_mod : c.N;
-    const size_t need = (size_t)c.L * m->planes * c.Cin;
+    const int hist = c.hist;                                       // streaming decode: rows in front of x carry the previous chunk's tail
+    const size_t need = (size_t)(c.L + hist) * m->planes * c.Cin;
     if (m->xs_cap < need) {
         if (m->xs) cudaFree(m->xs);
         m->xs = nullptr; m->xs_cap = 0;
         if (cudaMalloc((void**)&m->xs, need * sizeof(bf16)) != cudaSuccess) { (void)cudaGetLastError(); return false; }
         m->xs_cap = need;
     }
-    const long long n4 = (long long)c.L * (c.Cin / 4);
-    voc_planes_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16), 256, 0, h->stream>>>(c.x, m->xs, c.L, c.Cin, m->planes, c.Cin, nullptr, nullptr);
+    const long long n4 = (long long)(c.L + hist) * (c.Cin / 4);
+    voc_planes_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)h->num_sms * 16), 256, 0, h->stream>>>(c.x - (size_t)hist * c.Cin, m->xs, c.L + hist, c.Cin, m->planes, c.Cin, nullptr, nullptr);
     h->stats.kernel_launches++;
     VocTcOut o; o.y = c.y; o.residual = c.residual; o.scale = c.scale; o.act = c.act;
-    return voc_tc_conv(h, m, w, m->xs, c.L, c.dil > 0 ? c.dil : 1, c.tap_rev != 0, o) == 0;
+    return voc_tc_conv(h, m, w, m->xs + (size_t)hist * m->planes * c.Cin, c.L, c.dil > 0 ? c.dil : 1, c.tap_rev != 0, o, hist) == 0;
 }
 
 // decoder of tokenizer12hz_decode from the output of the upsampling stages: cur fp32 [L0][Cv] -> audio [L0 * prod(rates)]
-int voc_tc_decoder(lqt_engine* h, const float* cur, long long L0, float* audio) {
+int voc_tc_decoder(lqt_engine* h, const float* cur, long long L0, float* audio, lqt_engine::VocStream* vs) {
     VocTcModel* m = h->voc_tc;
     const Spec& s = h->sp;
     const int P = m->planes;
+    // front margin of the plane / fp32 buffers: 64 rows (>= the longest left context: k7 at dilation 9 = 54) of the widest row
+    const size_t xmargin = (size_t)64 * P * std::max(s.voc_hidden, (s.voc_decoder_dim + 63) / 64 * 64);
+    const size_t tmargin = (size_t)64 * s.voc_decoder_dim;
     // capacity: largest plane tensor and largest fp32 tensor over the chain
     size_t xmax = (size_t)L0 * P * std::max(s.voc_hidden, (s.voc_decoder_dim + 63) / 64 * 64), tmax = 0;
     {
@@ -164,6 +172,7 @@ int voc_tc_decoder(lqt_engine* h, const float* cur, long long L0, float* audio) 
             tmax = std::max(tmax, (size_t)L * B.cout);
         }
     }
+    xmax += xmargin; tmax += tmargin;
     if (m->x_cap < xmax) {
         if (m->xa) cudaFree(m->xa);
         if (m->xb) cudaFree(m->xb);
@@ -181,7 +190,9 @@ int voc_tc_decoder(lqt_engine* h, const float* cur, long long L0, float* audio) 
     // channel-padding columns (Cin = 96 -> Cp = 128) must read as zeros: the epilogues never write them
     CK(cudaMemsetAsync(m->xa, 0, xmax * sizeof(bf16), h->stream));
     CK(cudaMemsetAsync(m->xb, 0, xmax * sizeof(bf16), h->stream));
-    bf16 *pin = m->xa, *pout = m->xb;
+    bf16 *pin = m->xa + xmargin, *pout = m->xb + xmargin;
+    float* t0buf = m->t0 + tmargin;
+    auto row_bytes = [&](int C) { return (size_t)P * ((C + 63) / 64 * 64) * sizeof(bf16); };
     long long L = L0;
     {
         const long long n4 = L * (s.voc_hidden / 4);
@@ -190,16 +201,18 @@ int voc_tc_decoder(lqt_engine* h, const float* cur, long long L0, float* audio) 
     }
     {   // dec.conv_in (k7) -> planes of snake_b0(.)
         VocTcOut o; o.xo = pout; o.cout = s.voc_decoder_dim; o.sn = h->vblk.empty() ? &m->s_out : &m->blk[0].s_in;
-        if (voc_tc_conv(h, m, m->conv_in, pin, L, 1, false, o)) return 1;
+        if (voc_halo(h, vs, "tc_in", pin, row_bytes(s.voc_hidden), 6, L)) return 1;
+        if (voc_tc_conv(h, m, m->conv_in, pin, L, 1, false, o, vs ? 6 : 0)) return 1;
         std::swap(pin, pout);
     }
-    float* fa = m->t0;
+    float* fa = t0buf;
     for (size_t b = 0; b < h->vblk.size(); ++b) {
         const VocBlockW& B = h->vblk[b];
         auto& K = m->blk[b];
         {   // transposed conv: [L][s*cout] == [L*s][cout]; fp32 residual stream t0 + planes of snake1_r0
-            VocTcOut o; o.y = m->t0; o.xo = pout; o.cout = B.cout; o.up = B.stride; o.sn = &K.s1[0];
-            if (voc_tc_conv(h, m, K.tconv, pin, L, 1, true, o)) return 1;
+            VocTcOut o; o.y = t0buf; o.xo = pout; o.cout = B.cout; o.up = B.stride; o.sn = &K.s1[0];
+            if (voc_halo(h, vs, "tc_t" + std::to_string(b), pin, row_bytes(B.cin), 1, L)) return 1;
+            if (voc_tc_conv(h, m, K.tconv, pin, L, 1, true, o, vs ? 1 : 0)) return 1;
             std::swap(pin, pout);
         }
         L *= B.stride;
@@ -207,21 +220,23 @@ int voc_tc_decoder(lqt_engine* h, const float* cur, long long L0, float* audio) 
         for (int r = 0; r < 3; ++r) {
             {   // conv1 k7 dilated -> planes of snake2(.)
                 VocTcOut o; o.xo = pout; o.cout = B.cout; o.sn = &K.s2[r];
-                if (voc_tc_conv(h, m, K.c1[r], pin, L, dil[r], false, o)) return 1;
+                if (voc_halo(h, vs, "tc_c" + std::to_string(b) + "_" + std::to_string(r), pin, row_bytes(B.cout), 6 * dil[r], L)) return 1;
+                if (voc_tc_conv(h, m, K.c1[r], pin, L, dil[r], false, o, vs ? 6 * dil[r] : 0)) return 1;
                 std::swap(pin, pout);
             }
             {   // conv2 k1 + residual -> t0 (in place) and the planes of the next consumer's SnakeBeta
-                VocTcOut o; o.residual = m->t0; o.cout = B.cout;
+                VocTcOut o; o.residual = t0buf; o.cout = B.cout;
                 const bool last = (r == 2 && b + 1 == h->vblk.size());
-                if (last) { o.y = m->t0; o.y_snake = true; o.sn = &m->s_out; }           // fp32 snake_out(x) for conv_out_kernel
-                else { o.y = m->t0; o.xo = pout; o.sn = (r < 2) ? &K.s1[r + 1] : &m->blk[b + 1].s_in; }
+                if (last) { o.y = t0buf; o.y_snake = true; o.sn = &m->s_out; }           // fp32 snake_out(x) for conv_out_kernel
+                else { o.y = t0buf; o.xo = pout; o.sn = (r < 2) ? &K.s1[r + 1] : &m->blk[b + 1].s_in; }
                 if (voc_tc_conv(h, m, K.c2[r], pin, L, 1, false, o)) return 1;
                 std::swap(pin, pout);
             }
         }
     }
     const int Cl = h->vblk.empty() ? s.voc_decoder_dim : h->vblk.back().cout;
-    conv_out_kernel<<<(unsigned)((L + 7) / 8), 256, 0, h->stream>>>(fa, audio, L, Cl, h->out_w, h->out_b);
+    if (voc_halo(h, vs, "tc_out", fa, (size_t)Cl * 4, 6, L)) return 1;
+    conv_out_kernel<<<(unsigned)((L + 7) / 8), 256, 0, h->stream>>>(fa, audio, L, Cl, h->out_w, h->out_b, vs ? 6 : 0);
     h->stats.kernel_launches++;
     CK(cudaGetLastError());
     return 0;

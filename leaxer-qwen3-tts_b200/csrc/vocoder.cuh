@@ -23,6 +23,7 @@ struct ConvGemmParams {
     int shift;                   // added to the source position (0 = causal; (taps/2)*dil = 'same' padding)
     int bias_mod;
     int act;                     // 0 none, 1 SiLU, 3 GELU(erf)
+    int hist;                    // streaming decode: rows [-hist, 0) in front of x hold the previous chunk's tail (0 = zero padding)
 };
 
 constexpr int CG_BM = 64, CG_BN = 64, CG_BK = 16, CG_THREADS = 256;
@@ -58,7 +59,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
             if (pidx < p.L && k < K) {
                 const int tap = k / p.Cin, c = k - tap * p.Cin;
                 const int src = pidx + p.shift - (p.tap_rev ? tap : (p.taps - 1 - tap)) * p.dil;
-                if (src >= 0 && src < p.L) v = *reinterpret_cast<const float4*>(p.x + (size_t)src * p.Cin + c);
+                if (src >= -p.hist && src < p.L) v = *reinterpret_cast<const float4*>(p.x + (long long)src * p.Cin + c);
             }
             a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
         } else {
@@ -69,7 +70,7 @@ conv_gemm_kernel(const ConvGemmParams p) {
                 if (pidx < p.L && k < K) {
                     const int tap = k / p.Cin, c = k - tap * p.Cin;
                     const int src = pidx + p.shift - (p.tap_rev ? tap : (p.taps - 1 - tap)) * p.dil;
-                    if (src >= 0 && src < p.L) v = p.x[(size_t)src * p.Cin + c];
+                    if (src >= -p.hist && src < p.L) v = p.x[(long long)src * p.Cin + c];
                 }
                 a_reg[e] = v;
             }
@@ -181,8 +182,8 @@ conv_gemm_mma_kernel(const ConvGemmParams p) {
         if (pidx < p.L) {
             const int tap = k / p.Cin, c = k - tap * p.Cin;       // Cin % 16 == 0: the slab lies inside one tap
             const int src = pidx + p.shift - (p.tap_rev ? tap : (p.taps - 1 - tap)) * p.dil;
-            if (src >= 0 && src < p.L) {
-                const float4* q = reinterpret_cast<const float4*>(p.x + (size_t)src * p.Cin + c);
+            if (src >= -p.hist && src < p.L) {
+                const float4* q = reinterpret_cast<const float4*>(p.x + (long long)src * p.Cin + c);
                 a0 = q[0]; a1 = q[1];
             }
         }
@@ -325,9 +326,10 @@ __global__ void silu_mul_kernel(const float* g, const float* u, float* y, long l
 
 // ---- ConvNeXt front: depthwise causal conv k7 (+bias) then LayerNorm over channels ----------------
 // one CTA per position; dynamic smem = C floats
+// hist: rows [-hist, 0) in front of x hold the previous chunk's tail (streaming decode); 0 = causal zero padding
 __global__ void dwconv_ln_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C,
                                  const float* __restrict__ dw_w /*[7][C]*/, const float* __restrict__ dw_b,
-                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps) {
+                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int hist) {
     extern __shared__ float hbuf[];
     __shared__ float red[32];
     __shared__ float stat;
@@ -338,7 +340,7 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, float* __restrict_
 #pragma unroll
         for (int tap = 0; tap < 7; ++tap) {
             const int src = p - (6 - tap);
-            if (src >= 0) a = fmaf(dw_w[tap * C + c], x[(size_t)src * C + c], a);
+            if (src >= -hist) a = fmaf(dw_w[tap * C + c], x[(long long)src * C + c], a);
         }
         hbuf[c] = a;
         s += a;
@@ -365,15 +367,15 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, float* __restrict_
 // ---- final causal conv k7 C->1 (+bias) + clamp[-1,1]; input already SnakeBeta-activated ----------
 // one warp per output sample
 __global__ void conv_out_kernel(const float* __restrict__ x, float* __restrict__ y, long long L, int C,
-                                const float* __restrict__ w /*[7][C]*/, const float* __restrict__ b) {
+                                const float* __restrict__ w /*[7][C]*/, const float* __restrict__ b, int hist) {
     const long long pos = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pos >= L) return;
     float a = 0.f;
     for (int tap = 0; tap < 7; ++tap) {
         const long long src = pos - (6 - tap);
-        if (src < 0) continue;
-        for (int c = lane; c < C; c += 32) a = fmaf(w[tap * C + c], x[(size_t)src * C + c], a);
+        if (src < -hist) continue;
+        for (int c = lane; c < C; c += 32) a = fmaf(w[tap * C + c], x[src * C + c], a);
     }
     a = warp_sum(a);
     if (lane == 0) y[pos] = fminf(1.0f, fmaxf(-1.0f, a + b[0]));

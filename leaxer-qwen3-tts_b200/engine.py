@@ -21,6 +21,7 @@ SYMBOLS = [
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
     "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange", "lqt_check_model_file",
     "lqt_synthesize_batch", "lqt_debug_tc_gemm", "lqt_log_mel", "lqt_speaker_embed_audio",
+    "lqt_vocoder_stream_reset", "lqt_vocoder_stream_chunk",
 ]
 
 
@@ -110,6 +111,8 @@ def load_library():
     lib.lqt_check_model_file.argtypes = [C.c_char_p, C.c_char_p, I32]
     lib.lqt_synthesize_batch.argtypes = [P, C.POINTER(BatchRequest), I32, C.POINTER(Sampling), C.POINTER(BatchOptions)]
     lib.lqt_debug_tc_gemm.argtypes = [P, P, P, I32, I32, I32, I32, I32, P]
+    lib.lqt_vocoder_stream_reset.argtypes = [P]
+    lib.lqt_vocoder_stream_chunk.argtypes = [P, P, I32, P, C.POINTER(I64)]
     lib.lqt_log_mel.argtypes = [P, P, I64, P, C.POINTER(I32)]
     lib.lqt_speaker_embed_audio.argtypes = [P, P, I64, P]
     _lib = lib
@@ -242,6 +245,24 @@ class Engine:
         n = C.c_int64(0)
         self._ck(self.lib.lqt_vocoder_decode(self.h, _ptr(c), c.shape[0], _ptr(audio), C.byref(n)))
         return audio[: n.value]
+
+    def vocoder_stream(self, codes, chunks):
+        """decode `codes` [T,16] in consecutive chunks of the given sizes (streaming vocoder); -> concatenated audio"""
+        c = _i64(codes).reshape(-1, 16)
+        self._ck(self.lib.lqt_vocoder_stream_reset(self.h))
+        out, t = [], 0
+        for n in chunks:
+            n = min(int(n), c.shape[0] - t)
+            if n <= 0:
+                break
+            part = np.ascontiguousarray(c[t:t + n])
+            audio = np.empty(n * self.info.samples_per_frame, np.float32)
+            ln = C.c_int64(0)
+            self._ck(self.lib.lqt_vocoder_stream_chunk(self.h, _ptr(part), n, _ptr(audio), C.byref(ln)))
+            out.append(audio[: ln.value])
+            t += n
+        assert t == c.shape[0], "chunk sizes do not cover the codes"
+        return np.concatenate(out)
 
     def speaker_encoder(self, mel_t):
         m = _f32(mel_t).reshape(-1, 128)

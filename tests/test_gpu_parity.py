@@ -531,3 +531,20 @@ def test_no_cooperative_launch_disables_the_overlap(tiny_dir, monkeypatch):
     assert s1.cooperative_launch == 0 and abs(s1.first_audio_ms - s1.last_total_ms) < 1e-3
     assert np.array_equal(c0, c1) and np.array_equal(a0, a1)
     e1.close()
+
+
+@pytest.mark.parametrize("which,T,chunks", [("tiny", 40, [1, 2, 3, 5, 8, 13, 8]), ("tiny", 30, [30]), ("full", 110, [25, 25, 25, 25, 10]),
+                                              ("full", 90, [7, 1, 40, 2, 40])])
+def test_streaming_vocoder_is_bit_identical(request, which, T, chunks):
+    """the vocoder decodes an utterance in chunks with carried state (conv halos, the 71-position K/V window of the
+    pre-transformer, dilated-conv tails up to 54 rows) -- the concatenation must equal the one-shot decode BIT FOR BIT, for any
+    chunking (single frames, chunks shorter than a layer's left context, chunks longer than the attention window)."""
+    eng, m = pair(request, which)
+    codes = np.random.default_rng(7 * T).integers(0, 2048, size=(T, 16))
+    one_shot = eng.vocoder_decode(codes)
+    streamed = eng.vocoder_stream(codes, chunks)
+    assert streamed.shape == one_shot.shape
+    assert np.array_equal(streamed, one_shot), (int(np.argmax(streamed != one_shot)), float(np.abs(streamed - one_shot).max()))
+    # and a second utterance right after (state reset)
+    codes2 = np.random.default_rng(T).integers(0, 2048, size=(12, 16))
+    assert np.array_equal(eng.vocoder_stream(codes2, [5, 7]), eng.vocoder_decode(codes2))
