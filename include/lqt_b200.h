@@ -195,6 +195,16 @@ int lqt_synthesize_batch(lqt_engine* h, const lqt_batch_request* reqs, int32_t n
 int lqt_debug_tc_gemm(lqt_engine* h, const float* W, const float* x, int32_t N, int32_t K, int32_t B, int32_t planes,
                       int32_t splits, float* out);
 
+/* Streaming form of lqt_synthesize_tokens (the reference returns the whole waveform at the end, :430-436): same
+ * arguments and result, plus a callback that is invoked on the calling thread, in order, for every chunk of PCM (2 s by
+ * default, $LQT_FIRST_CHUNK frames) as soon as it has been vocoded and copied into audio_out -- while the frame kernel is still
+ * generating the rest of the utterance. pcm points into audio_out at first_sample. The chunks are bit-identical to the one-shot
+ * result (streaming vocoder with carried state). */
+typedef void (*lqt_audio_callback)(void* user, const float* pcm, int64_t first_sample, int64_t n_samples);
+int lqt_synthesize_stream(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
+                          const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
+                          int64_t* codes_out, int32_t* n_frames, lqt_audio_callback on_audio, void* user);
+
 /* build_prompt_embeddings  :442-539 on the device; outputs to host for parity tests.
  * prompt_out [10,H] capacity, *P rows used; trailing_out [n_ids,H] capacity, *trailing_len. */
 int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids,

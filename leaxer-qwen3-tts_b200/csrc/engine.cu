@@ -136,7 +136,7 @@ struct lqt_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr;
     // first-audio path: the first `first_chunk` frames are vocoded on a second stream while the frame kernel keeps generating
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_chunk = nullptr, ev_first = nullptr;
+    cudaEvent_t ev_chunk = nullptr, ev_first = nullptr, ev_end = nullptr;
     int first_chunk = 25;                     // frames (2 s of audio); 0 = off; $LQT_FIRST_CHUNK
     float* chunk_audio_dev = nullptr; size_t chunk_audio_cap = 0;
     float* chunk_audio_out = nullptr; int64_t chunk_audio_out_cap = 0;    // caller's buffer of the running lqt_synthesize_tokens call
@@ -152,6 +152,12 @@ struct lqt_engine {
     uint2 *fk_pa = nullptr, *fk_cxin = nullptr, *fk_logits_ll = nullptr, *fk_clogits_ll = nullptr;
     unsigned* fk_ctrl = nullptr;
     unsigned* fk_ctrl_host = nullptr;         // pinned
+    int* fk_progress_host = nullptr;          // pinned: frames completed by the running frame kernel (streaming vocoder)
+    bool fk_progress_on = false;
+    int voc_reserved_frames = 0;              // largest streaming chunk the vocoder workspaces are sized for
+    lqt_audio_callback on_audio = nullptr; void* on_audio_user = nullptr;     // lqt_synthesize_stream: called per finished PCM chunk
+    std::vector<cudaEvent_t> chunk_events;    // one per PCM chunk in flight (created on demand, reused)
+    bool streamed_last = false;               // the last lqt_synthesize_tokens call went through synthesize_streaming
     unsigned long long* fk_dbg = nullptr; int fk_dbg_cap = 0, fk_dbg_cta = 0;
     FkSmemOffsets fk_so{};
     bool fk_wide = false;
@@ -599,6 +605,12 @@ void voc_stream_clear(lqt_engine* h) {
     for (auto& e : h->voc_stream.halo) if (e.second.first) cudaFree(e.second.first);
     h->voc_stream.halo.clear();
     h->voc_stream.t0 = 0;
+}
+// new utterance: zero the carried tails (buffers stay allocated: no cudaMalloc/cudaFree while a frame kernel may be running)
+int voc_stream_reset(lqt_engine* h, cudaStream_t st) {
+    for (auto& e : h->voc_stream.halo) if (e.second.first) CK(cudaMemsetAsync(e.second.first, 0, e.second.second, st));
+    h->voc_stream.t0 = 0;
+    return 0;
 }
 
 int run_vocoder(lqt_engine* h, const long long* codes_dev, int T, float* audio, cudaStream_t vstream = nullptr, lqt_engine::VocStream* vs = nullptr) {
@@ -1093,6 +1105,8 @@ int fk_init(lqt_engine* h) {
     if (fk_alloc(h, &h->fk_cp_kv, (size_t)h->fk_ncta * s.cp_layers * 2 * FK_CP_POS * ATT_D)) return 1;
     if (fk_alloc(h, &h->fk_ctrl, 64)) return 1;      // [1] abort flag, [32] grid arrival counter (own cache line)
     CK(cudaMallocHost((void**)&h->fk_ctrl_host, 64 * sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&h->fk_progress_host, sizeof(int)));
+    *h->fk_progress_host = 0;
     return 0;
 }
 
@@ -1121,6 +1135,7 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.codes_out = h->codes_dev; p.forced = h->forced_dev;
     p.trace = trace ? h->trace_dev : nullptr; p.trace_stride = h->trace_stride;
     p.ctrl = h->fk_ctrl; p.frame_end = frame_end; p.mode = mode;
+    p.progress = h->fk_progress_on ? h->fk_progress_host : nullptr;
     p.dbg = h->fk_dbg; p.dbg_cap = h->fk_dbg_cap; p.dbg_cta = h->fk_dbg_cta;
     CK(cudaMemsetAsync(h->fk_ctrl, 0, 64 * sizeof(unsigned), h->stream));
     CK(cudaMemsetAsync(h->fk_arena, 0, h->fk_arena_words * sizeof(uint2), h->stream));   // sequence numbers restart at 1
@@ -1281,7 +1296,7 @@ int init_engine(lqt_engine* h, const std::string& dir) {
         return 1;
     CK(cudaMallocHost((void**)&h->st_host, sizeof(GenState)));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev_t0));
-    CK(cudaEventCreate(&h->ev_chunk)); CK(cudaEventCreate(&h->ev_first));
+    CK(cudaEventCreate(&h->ev_chunk)); CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_end));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     if (const char* e = getenv("LQT_FIRST_CHUNK")) h->first_chunk = std::max(0, atoi(e));
     if (voc_tc_init(h)) return 1;
@@ -1388,12 +1403,15 @@ void lqt_destroy(lqt_engine* h) {
     for (void* b : bufs) if (b) cudaFree(b);
     for (void* b : h->fk_allocs) if (b) cudaFree(b);
     if (h->fk_ctrl_host) cudaFreeHost(h->fk_ctrl_host);
+    if (h->fk_progress_host) cudaFreeHost(h->fk_progress_host);
     if (h->st_host) cudaFreeHost(h->st_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_chunk) cudaEventDestroy(h->ev_chunk);
     if (h->ev_first) cudaEventDestroy(h->ev_first);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
     if (h->mel_window) { cudaFree(h->mel_window); cudaFree(h->mel_tw_re); cudaFree(h->mel_tw_im); cudaFree(h->mel_tri); }
@@ -1637,8 +1655,7 @@ int lqt_vocoder_stream_reset(lqt_engine* h) {
     if (!h) return 1;
     cudaSetDevice(h->device);
     CK(cudaStreamSynchronize(h->stream));
-    voc_stream_clear(h);
-    return 0;
+    return voc_stream_reset(h, h->stream);
 }
 
 int lqt_vocoder_stream_chunk(lqt_engine* h, const int64_t* codes, int32_t T, float* audio, int64_t* length) {
@@ -1804,34 +1821,29 @@ int lqt_build_prompt(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int
     return 0;
 }
 
-// First-audio path (the reference vocodes once at the end, src/tts_onnx.cpp:430): every vocoder op is causal
-// (causal convs, causal sliding-window attention, right-trimmed transposed convs), so decoding the first `chunk` frames alone
-// gives exactly the first chunk * 1920 samples of the full decode. Runs on stream2 while the frame kernel generates the rest.
-static int first_chunk_hook(lqt_engine* h, int chunk) {
-    const size_t n = (size_t)chunk * h->sp.samples_per_frame;
-    if (!h->chunk_audio_out || (int64_t)n > h->chunk_audio_out_cap) return 0;
-    if (h->chunk_audio_cap < n) {
-        if (h->chunk_audio_dev) cudaFree(h->chunk_audio_dev);
-    if (h->mel_window) { cudaFree(h->mel_window); cudaFree(h->mel_tw_re); cudaFree(h->mel_tw_im); cudaFree(h->mel_tri); }
-        CK(cudaMalloc((void**)&h->chunk_audio_dev, n * sizeof(float)));
-        h->chunk_audio_cap = n;
-    }
-    CK(cudaStreamWaitEvent(h->stream2, h->ev_chunk, 0));
-    h->chunk_pending = true;
-    if (run_vocoder(h, h->codes_dev, chunk, h->chunk_audio_dev, h->stream2)) return 1;
-    CK(cudaMemcpyAsync(h->chunk_audio_out, h->chunk_audio_dev, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
-    CK(cudaEventRecord(h->ev_first, h->stream2));             // first audio is in the caller's buffer
-    return 0;
-}
-
 static int synthesize_tokens_impl(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
                                   const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
                                   int64_t* codes_out, int32_t* n_frames);
+
+int lqt_synthesize_stream(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
+                          const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
+                          int64_t* codes_out, int32_t* n_frames, lqt_audio_callback on_audio, void* user) {
+    if (!h) return 1;
+    h->on_audio = on_audio; h->on_audio_user = user;
+    int64_t ns = 0;
+    const int rc = lqt_synthesize_tokens(h, token_ids, n_ids, lang_codec_id, speaker_embed, sp, audio_out, audio_capacity, &ns, codes_out, n_frames);
+    // paths that do not stream (graph / batched frame loops, chunking off, short utterances): one callback with everything
+    if (rc == 0 && on_audio && ns > 0 && !h->streamed_last) on_audio(user, audio_out, 0, ns);
+    h->on_audio = nullptr; h->on_audio_user = nullptr;
+    if (n_samples) *n_samples = ns;
+    return rc;
+}
 
 int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
                           const lqt_sampling* sp, float* audio_out, int64_t audio_capacity, int64_t* n_samples,
                           int64_t* codes_out, int32_t* n_frames) {
     if (!h || !token_ids || !sp || !n_samples) return 1;
+    h->streamed_last = false;
     cudaSetDevice(h->device);
     h->chunk_audio_out = audio_out; h->chunk_audio_out_cap = audio_capacity; h->chunk_pending = false;
     const int rc = synthesize_tokens_impl(h, token_ids, n_ids, lang_codec_id, speaker_embed, sp, audio_out, audio_capacity, n_samples, codes_out, n_frames);
@@ -1840,6 +1852,112 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
     if (rc) cudaStreamSynchronize(h->stream);
     h->chunk_audio_out = nullptr; h->chunk_audio_out_cap = 0;
     return rc;
+}
+
+// Streaming synthesis on the persistent kernel: ONE frame-kernel launch generates the whole utterance and
+// reports every finished frame through a pinned host word; the host vocodes the finished frames chunk by chunk on the second
+// stream (streaming vocoder with carried state: each chunk is bit-identical to the one-shot decode, nothing is decoded twice)
+// and copies the PCM into the caller's buffer while generation continues on the other SMs. After the last frame only the last
+// chunk is left to decode. chunk = h->first_chunk frames (2 s): the first-audio latency.
+static int synthesize_streaming(lqt_engine* h, int P, int TL, const lqt_sampling* sp, float* audio_out, int64_t audio_capacity,
+                                int64_t* n_samples, int64_t* codes_out, int32_t* n_frames) {
+    const int chunk = h->first_chunk, spf = h->sp.samples_per_frame, max_new = sp->max_new_tokens;
+    if (P < 1 || max_new < 0 || max_new > h->max_frames_cap || P + max_new > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
+    if (audio_capacity < (int64_t)max_new * spf) { h->err = "audio_out too small"; return 1; }
+    if (upload_sampling(h, sp)) return 1;
+    if (ensure_audio(h, max_new)) return 1;
+    if (h->voc_reserved_frames < chunk) {
+        // size every vocoder workspace (and the per-layer state) for a chunk BEFORE the frame kernel starts: allocations while it
+        // runs would serialise behind it. One throw-away chunk of zeros does exactly the allocations the real chunks need.
+        CK(cudaMemsetAsync(h->codes_dev, 0, (size_t)chunk * N_CODEBOOKS * sizeof(long long), h->stream));
+        if (run_vocoder(h, h->codes_dev, chunk, h->audio_dev, nullptr, &h->voc_stream)) return 1;
+        CK(cudaStreamSynchronize(h->stream));
+        h->voc_reserved_frames = chunk;
+    }
+    if (voc_stream_reset(h, h->stream)) return 1;
+    GenState g{};
+    g.trailing_len = TL; g.max_frames = max_new;
+    *h->st_host = g;
+    CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
+    *h->fk_progress_host = 0;
+    h->fk_progress_on = true;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    const int rc = fk_launch(h, 0, 0, h->prompt_dev, P, max_new, false);
+    h->fk_progress_on = false;
+    if (rc) return 1;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev_chunk, h->stream));                  // = "the kernel and the state copy are done"
+    CK(cudaStreamWaitEvent(h->stream2, h->ev0, 0));               // stream2 starts after the state reset above
+    h->chunk_pending = true;
+    int done = 0;                                                 // frames vocoded so far
+    bool first = true, finished = false;
+    volatile int* prog = h->fk_progress_host;
+    struct Pending { int frame0, frames; };
+    std::vector<Pending> pend;                                    // chunks enqueued, in order; [delivered, pend.size()) not yet reported
+    size_t delivered = 0;
+    auto deliver = [&](bool wait) {                               // report the chunks whose PCM has landed in the caller's buffer
+        while (delivered < pend.size()) {
+            if (wait) cudaEventSynchronize(h->chunk_events[delivered]);
+            else if (cudaEventQuery(h->chunk_events[delivered]) != cudaSuccess) break;
+            if (h->on_audio) h->on_audio(h->on_audio_user, audio_out + (size_t)pend[delivered].frame0 * spf,
+                                         (int64_t)pend[delivered].frame0 * spf, (int64_t)pend[delivered].frames * spf);
+            ++delivered;
+        }
+    };
+    auto vocode = [&](int upto) -> int {                          // frames [done, upto) in chunks of at most `chunk`
+        while (done < upto) {
+            const int n = std::min(chunk, upto - done);
+            if (run_vocoder(h, h->codes_dev + (size_t)done * N_CODEBOOKS, n, h->audio_dev + (size_t)done * spf, h->stream2, &h->voc_stream)) return 1;
+            h->voc_stream.t0 += n;
+            CK(cudaMemcpyAsync(audio_out + (size_t)done * spf, h->audio_dev + (size_t)done * spf, (size_t)n * spf * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
+            if (first) { CK(cudaEventRecord(h->ev_first, h->stream2)); first = false; }
+            if (h->chunk_events.size() <= pend.size()) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->chunk_events.push_back(e);
+            }
+            CK(cudaEventRecord(h->chunk_events[pend.size()], h->stream2));
+            pend.push_back(Pending{done, n});
+            done += n;
+        }
+        return 0;
+    };
+    while (!finished) {
+        finished = cudaEventQuery(h->ev_chunk) == cudaSuccess;
+        const int avail = finished ? h->st_host->n_frames : *prog;
+        const int upto = finished ? avail : (avail / chunk) * chunk;          // whole chunks while the kernel runs, the rest at the end
+        if (upto > done) { if (vocode(upto)) return 1; }
+        else if (!finished) { struct timespec ts = {0, 100000}; nanosleep(&ts, nullptr); }
+        deliver(false);
+    }
+    CK(cudaEventRecord(h->ev_end, h->stream2));
+    CK(cudaStreamSynchronize(h->stream2));
+    deliver(true);
+    h->chunk_pending = false;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (fk_check_abort(h)) return 1;
+    const int nf = h->st_host->n_frames;
+    cudaEventElapsedTime(&h->stats.last_generate_ms, h->ev0, h->ev1);
+    h->stats.last_prefill_ms = 0.f;
+    if (nf > 0) {
+        cudaEventElapsedTime(&h->stats.last_total_ms, h->ev_t0, h->ev_end);
+        cudaEventElapsedTime(&h->stats.first_audio_ms, h->ev_t0, h->ev_first);
+        float tail = 0.f;
+        cudaEventElapsedTime(&tail, h->ev1, h->ev_end);           // what is left of the vocoder after the last frame
+        h->stats.last_vocoder_ms = std::max(tail, 0.f);
+    }
+    h->slot_len[0] = h->st_host->pos;
+    h->stats.last_frames = nf;
+    if (n_frames) *n_frames = nf;
+    if (nf > 0 && codes_out) {
+        CK(cudaMemcpyAsync(codes_out, h->codes_dev, (size_t)nf * N_CODEBOOKS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    *n_samples = (int64_t)nf * spf;
+    h->streamed_last = true;
+    return 0;
 }
 
 static int synthesize_tokens_impl(lqt_engine* h, const int64_t* token_ids, int32_t n_ids, int32_t lang_codec_id, const float* speaker_embed,
@@ -1864,9 +1982,11 @@ static int synthesize_tokens_impl(lqt_engine* h, const int64_t* token_ids, int32
     int P = 0, TL = 0;
     CK(cudaEventRecord(h->ev_t0, h->stream));
     if (build_prompt_device(h, token_ids, n_ids, lang_codec_id, speaker_embed, &P, &TL)) return 1;
+    h->stats.first_audio_ms = 0.f; h->stats.last_total_ms = 0.f;
+    if (h->frame_impl == LQT_FRAME_PERSISTENT && audio_out && h->fk_coop && h->first_chunk > 0 && sp->max_new_tokens > h->first_chunk)
+        return synthesize_streaming(h, P, TL, sp, audio_out, audio_capacity, n_samples, codes_out, n_frames);
     int nf = 0, chunk = 0;
-    h->stats.first_audio_ms = 0.f;
-    if (generate_core(h, 0, P, TL, sp, 0, false, &nf, audio_out ? &chunk : nullptr, first_chunk_hook)) return 1;
+    if (generate_core(h, 0, P, TL, sp, 0, false, &nf)) return 1;
     if (n_frames) *n_frames = nf;
     h->stats.last_total_ms = 0.f;
     if (nf == 0) return 0;                                   // empty result, like src/tts_onnx.cpp:418

@@ -103,6 +103,7 @@ struct FkParams {
     const float *trailing, *tts_pad;
     GenState* st; const SamplingDev* sp;
     long long* codes_out; const long long* forced; float* trace; int trace_stride;
+    volatile int* progress;    // nullable, pinned HOST memory: frames completed so far (the host vocodes them while the kernel runs)
     unsigned* ctrl;            // [1] abort flag, [32] grid arrival counter (all zero at launch)
     int frame_end;             // run frames while frame < frame_end (<= max_frames)
     unsigned producer_sleep_ns; // back-off of the producer lane while the ring is full ($LQT_FK_SLEEP, default 400)
@@ -1640,7 +1641,13 @@ frame_kernel(const __grid_constant__ FkParams p) {
             if (p.forced && frame < st0.n_forced) tok = (int)p.forced[(size_t)frame * 16 + cb];
             fk_mark(c, 3);
             if (cb == 0 && tok == 2150) { done = 1; break; }                        // CODEC_EOS (:812)
-            if (cta == 0 && tid == 0) p.codes_out[(size_t)frame * 16 + cb] = tok;   // :818-821
+            if (cta == 0 && tid == 0) {
+                p.codes_out[(size_t)frame * 16 + cb] = tok;                         // :818-821
+                if (cb == p.cp_steps && p.progress) {                               // the frame's 16 codes are stored: tell the host
+                    __threadfence_system();
+                    *p.progress = frame + 1;
+                }
+            }
             // ---- glue: embedding of the drawn code, running 16-way sum, next input rows (in res0) --------
             const bool last_cb = (cb == p.cp_steps);
             const bool use_tr = frame < st0.trailing_len;

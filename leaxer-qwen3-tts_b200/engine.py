@@ -21,7 +21,7 @@ SYMBOLS = [
     "lqt_vocoder_decode", "lqt_speaker_encoder", "lqt_sample", "lqt_generate", "lqt_synthesize_tokens",
     "lqt_build_prompt", "lqt_debug_timeline", "lqt_debug_exchange", "lqt_check_model_file",
     "lqt_synthesize_batch", "lqt_debug_tc_gemm", "lqt_log_mel", "lqt_speaker_embed_audio",
-    "lqt_vocoder_stream_reset", "lqt_vocoder_stream_chunk",
+    "lqt_vocoder_stream_reset", "lqt_vocoder_stream_chunk", "lqt_synthesize_stream",
 ]
 
 
@@ -63,6 +63,8 @@ class BatchRequest(C.Structure):
 class BatchOptions(C.Structure):
     _fields_ = [("max_concurrent", C.c_int32), ("planes", C.c_int32), ("poll_frames", C.c_int32)]
 
+
+AUDIO_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int64)
 
 _lib = None
 
@@ -111,6 +113,7 @@ def load_library():
     lib.lqt_check_model_file.argtypes = [C.c_char_p, C.c_char_p, I32]
     lib.lqt_synthesize_batch.argtypes = [P, C.POINTER(BatchRequest), I32, C.POINTER(Sampling), C.POINTER(BatchOptions)]
     lib.lqt_debug_tc_gemm.argtypes = [P, P, P, I32, I32, I32, I32, I32, P]
+    lib.lqt_synthesize_stream.argtypes = [P, P, I32, I32, P, C.POINTER(Sampling), P, I64, C.POINTER(I64), P, C.POINTER(I32), AUDIO_CB, P]
     lib.lqt_vocoder_stream_reset.argtypes = [P]
     lib.lqt_vocoder_stream_chunk.argtypes = [P, P, I32, P, C.POINTER(I64)]
     lib.lqt_log_mel.argtypes = [P, P, I64, P, C.POINTER(I32)]
@@ -411,3 +414,24 @@ class Engine:
         out = np.empty((x.shape[0], W.shape[0]), np.float32)
         self._ck(self.lib.lqt_debug_tc_gemm(self.h, _ptr(W), _ptr(x), W.shape[0], W.shape[1], x.shape[0], planes, splits, _ptr(out)))
         return out
+
+    def synthesize_stream(self, token_ids, lang="auto", temperature=0.8, top_k=50, top_p=0.95, max_new_tokens=2048, seed=0,
+                          utterance_id=0, on_chunk=None):
+        """lqt_synthesize_stream: on_chunk(first_sample, pcm ndarray copy, seconds since the call started) per PCM chunk, in order,
+        while generation continues. -> (audio, codes)"""
+        import time
+        ids = _i64(token_ids)
+        sp = self.sampling(temperature, top_k, top_p, max_new_tokens, seed, utterance_id, False)
+        cap = max(max_new_tokens, 1) * self.info.samples_per_frame
+        audio = np.empty(cap, np.float32)
+        codes = np.zeros((max(max_new_tokens, 1), 16), np.int64)
+        ns, nf = C.c_int64(0), C.c_int32(0)
+        t0 = time.perf_counter()
+
+        def _cb(user, pcm, first, n):
+            if on_chunk is not None:
+                on_chunk(int(first), np.ctypeslib.as_array(pcm, shape=(int(n),)).copy(), time.perf_counter() - t0)
+        cb = AUDIO_CB(_cb)
+        self._ck(self.lib.lqt_synthesize_stream(self.h, _ptr(ids), len(ids), LANG_CODEC_ID[lang], None, C.byref(sp), _ptr(audio), cap,
+                                                C.byref(ns), _ptr(codes), C.byref(nf), cb, None))
+        return audio[: ns.value].copy(), codes[: nf.value].copy()

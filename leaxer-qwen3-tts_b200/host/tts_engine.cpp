@@ -86,7 +86,7 @@ std::vector<int64_t> TTSEngine::wrap_text(const std::string& text, bool& ok) {
 }
 
 std::vector<float> TTSEngine::run_tokens(const std::vector<int64_t>& ids, Language lang, const SamplingParams& params,
-                                         const float* speaker_embed) {
+                                         const float* speaker_embed, const ChunkCallback* on_chunk) {
     last_codes_.clear();
     if (ids.size() < 5) {       // the reference indexes ids[3] and ids[n-2] unchecked (:493, :516); refuse instead
         std::cerr << "[TTSEngine] Synthesis error: token sequence too short" << std::endl;
@@ -103,10 +103,14 @@ std::vector<float> TTSEngine::run_tokens(const std::vector<int64_t>& ids, Langua
     std::vector<int64_t> codes(cap * 16);
     int64_t n_samples = 0;
     int32_t n_frames = 0;
-    const int rc = lqt_synthesize_tokens(handle_, ids.data(), static_cast<int32_t>(ids.size()),
+    auto trampoline = [](void* user, const float* pcm, int64_t first, int64_t n) {
+        (*static_cast<const ChunkCallback*>(user))(pcm, first, n);
+    };
+    const int rc = lqt_synthesize_stream(handle_, ids.data(), static_cast<int32_t>(ids.size()),
                                          static_cast<int32_t>(language_to_codec_id(lang)), speaker_embed, &sp,
                                          audio.data(), static_cast<int64_t>(audio.size()), &n_samples,
-                                         codes.data(), &n_frames);
+                                         codes.data(), &n_frames, on_chunk ? +trampoline : nullptr,
+                                         const_cast<ChunkCallback*>(on_chunk));
     if (rc != 0) {
         std::cerr << "[TTSEngine] Synthesis error: " << lqt_last_error(handle_) << std::endl;
         return {};
@@ -123,6 +127,15 @@ std::vector<float> TTSEngine::synthesize(const std::string& text, Language lang,
     const std::vector<int64_t> ids = wrap_text(text, ok);
     if (!ok) return {};
     return synthesize_tokens(ids, lang, params);
+}
+
+std::vector<float> TTSEngine::synthesize_stream(const std::string& text, Language lang, const SamplingParams& params,
+                                                const ChunkCallback& on_chunk) {
+    if (!ready_) return {};
+    bool ok = false;
+    const std::vector<int64_t> ids = wrap_text(text, ok);
+    if (!ok) return {};
+    return run_tokens(ids, lang, params, nullptr, &on_chunk);
 }
 
 std::vector<float> TTSEngine::synthesize_tokens(const std::vector<int64_t>& token_ids, Language lang,

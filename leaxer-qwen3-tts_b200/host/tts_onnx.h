@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <memory>
 #include <optional>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -106,6 +107,11 @@ public:
     uint32_t seed() const { return seed_; }
     // frames (each 16 codes, row-major [frame][codebook]) of the last synthesize* call
     const std::vector<int64_t>& last_codes() const { return last_codes_; }
+    // Streaming synthesis: like synthesize(), and on_chunk(pcm, first_sample, n_samples) is called for every 2 s of audio as soon
+    // as it is vocoded, while the rest of the utterance is still being generated (the reference delivers everything at the end)
+    using ChunkCallback = std::function<void(const float* pcm, int64_t first_sample, int64_t n_samples)>;
+    std::vector<float> synthesize_stream(const std::string& text, Language lang, const SamplingParams& params,
+                                         const ChunkCallback& on_chunk);
 
 private:
     lqt_engine* handle_ = nullptr;
@@ -119,7 +125,7 @@ private:
 
     std::vector<int64_t> wrap_text(const std::string& text, bool& ok);
     std::vector<float> run_tokens(const std::vector<int64_t>& ids, Language lang, const SamplingParams& params,
-                                  const float* speaker_embed);
+                                  const float* speaker_embed, const ChunkCallback* on_chunk = nullptr);
 };
 
 inline int64_t language_to_codec_id(Language lang) {

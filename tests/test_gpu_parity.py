@@ -548,3 +548,25 @@ def test_streaming_vocoder_is_bit_identical(request, which, T, chunks):
     # and a second utterance right after (state reset)
     codes2 = np.random.default_rng(T).integers(0, 2048, size=(12, 16))
     assert np.array_equal(eng.vocoder_stream(codes2, [5, 7]), eng.vocoder_decode(codes2))
+
+
+def test_synthesize_stream_delivers_chunks_while_generating(request):
+    """lqt_synthesize_stream on the full model: PCM arrives in 2 s chunks, in order, covering the utterance exactly, equal to the
+    returned buffer and to the non-streaming call; the first chunk arrives long before the call returns (generation of the
+    remaining frames and vocoding of the finished ones overlap)."""
+    import time
+    eng, _ = pair(request, "full")
+    orc = request.getfixturevalue("oracle_mod")
+    ids = orc.wrap_text_ids(orc.synthetic_text_ids(20, 5))
+    frames = 160
+    got = []
+    t0 = time.perf_counter()
+    audio, codes = eng.synthesize_stream(ids, "en", 0.8, 50, 0.95, frames, 1234, 3, on_chunk=lambda first, pcm, t: got.append((first, pcm, t)))
+    total = time.perf_counter() - t0
+    assert codes.shape == (frames, 16) and audio.shape[0] == frames * 1920
+    assert [g[0] for g in got] == sorted(g[0] for g in got) and got[0][0] == 0
+    assert sum(g[1].shape[0] for g in got) == audio.shape[0] and len(got) == (frames + 24) // 25
+    assert np.array_equal(np.concatenate([g[1] for g in got]), audio)
+    assert got[0][2] < 0.5 * total, (got[0][2], total)                  # first 2 s of audio well before the end
+    ref_audio, ref_codes = eng.synthesize_tokens(ids, "en", 0.8, 50, 0.95, frames, 1234, 3)
+    assert np.array_equal(codes, ref_codes) and np.array_equal(audio, ref_audio)
