@@ -363,7 +363,9 @@ struct BCpAttnParams {
     __nv_bfloat16* X; int planes, Bt;
     float eps, scale;
 };
-__global__ void __launch_bounds__(256)
+// (256, 2): <= 128 registers so that two CTAs (16 warps) share an SM -- 256 slots x 8 groups = 2048 warps then fit in one wave;
+// the K rows and the V rows take turns in the same registers.
+__global__ void __launch_bounds__(256, 2)
 bcp_attn_kernel(const BCpAttnParams p) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -377,6 +379,17 @@ bcp_attn_kernel(const BCpAttnParams p) {
     const float* sinr = p.rope_sin + (size_t)p.pos * (ATT_D / 2);
     const float* base = p.qkv_part + (size_t)b * qkv_dim + lane * 4;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* kc = p.kv + (size_t)b * p.slot_stride + p.layer_off + (size_t)g * p.PS * ATT_D;
+    float* vc = kc + (size_t)p.n_kv * p.PS * ATT_D;
+    constexpr int MAXP = 17;
+    // the cached K rows are requested first (predicated on j < pos, independent of everything else): they travel while the
+    // new token's q/k/v are summed, normalised and rotated
+    float4 rows[MAXP];
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+        rows[j] = z;
+        if (j < p.pos) rows[j] = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + lane);
+    }
     float4 q0 = bsum_splits4(base + (g * 2) * ATT_D, p.n_splits, p.split_stride, z);
     float4 q1 = bsum_splits4(base + (g * 2 + 1) * ATT_D, p.n_splits, p.split_stride, z);
     float4 kn = bsum_splits4(base + q_dim + g * ATT_D, p.n_splits, p.split_stride, z);
@@ -384,48 +397,54 @@ bcp_attn_kernel(const BCpAttnParams p) {
     q0 = head_norm_rope(q0, p.qnorm, p.eps, cosr, sinr, lane);
     q1 = head_norm_rope(q1, p.qnorm, p.eps, cosr, sinr, lane);
     kn = head_norm_rope(kn, p.knorm, p.eps, cosr, sinr, lane);
-    float* kc = p.kv + (size_t)b * p.slot_stride + p.layer_off + (size_t)g * p.PS * ATT_D;
-    float* vc = kc + (size_t)p.n_kv * p.PS * ATT_D;
     reinterpret_cast<float4*>(kc + (size_t)p.pos * ATT_D)[lane] = kn;
     reinterpret_cast<float4*>(vc + (size_t)p.pos * ATT_D)[lane] = vn;
-    constexpr int MAXP = 17;
-    // every cached row is requested up front (predicated on j < pos, no dependence between them): one L2 round trip instead of
-    // one per position
-    float4 kk[MAXP], vv[MAXP];
+    // scores of both heads with ONE butterfly per position: the halves of the warp swap one partial sum, then reduce within the
+    // half (lanes 0-15 end up with head 0, lanes 16-31 with head 1)
+    const bool hi = (lane & 16) != 0;
+    float sc[MAXP];
+    float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
-        kk[j] = z; vv[j] = z;
-        if (j < p.pos) {
-            kk[j] = __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + lane);
-            vv[j] = __ldcg(reinterpret_cast<const float4*>(vc + (size_t)j * ATT_D) + lane);
-        }
-    }
-    float s0[MAXP], s1[MAXP];
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXP; ++j) {
-        s0[j] = -INFINITY; s1[j] = -INFINITY;
+        sc[j] = -INFINITY;
         if (j <= p.pos) {
-            const float4 k4 = (j == p.pos) ? kn : kk[j];
-            s0[j] = warp_sum(k4.x * q0.x + k4.y * q0.y + k4.z * q0.z + k4.w * q0.w) * p.scale;
-            s1[j] = warp_sum(k4.x * q1.x + k4.y * q1.y + k4.z * q1.z + k4.w * q1.w) * p.scale;
-            m0 = fmaxf(m0, s0[j]); m1 = fmaxf(m1, s1[j]);
+            const float4 k4 = (j == p.pos) ? kn : rows[j];
+            const float d0 = k4.x * q0.x + k4.y * q0.y + k4.z * q0.z + k4.w * q0.w;
+            const float d1 = k4.x * q1.x + k4.y * q1.y + k4.z * q1.z + k4.w * q1.w;
+            float t = (hi ? d1 : d0) + __shfl_xor_sync(0xffffffffu, hi ? d0 : d1, 16);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            sc[j] = t * p.scale;
+            mx = fmaxf(mx, sc[j]);
         }
     }
-    float l0 = 0.f, l1 = 0.f;
+    // V rows into the same registers
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+        rows[j] = z;
+        if (j < p.pos) rows[j] = __ldcg(reinterpret_cast<const float4*>(vc + (size_t)j * ATT_D) + lane);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+        if (j <= p.pos) { sc[j] = expf(sc[j] - mx); den += sc[j]; }          // this half's head
+    }
     float4 a0 = z, a1 = z;
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
         if (j <= p.pos) {
-            const float4 v4 = (j == p.pos) ? vn : vv[j];
-            const float e0 = expf(s0[j] - m0), e1 = expf(s1[j] - m1);
-            l0 += e0; l1 += e1;
+            const float4 v4 = (j == p.pos) ? vn : rows[j];
+            const float mine = sc[j] / den;                                   // probability of position j for this half's head
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+            const float e0 = hi ? other : mine, e1 = hi ? mine : other;
             a0.x = fmaf(e0, v4.x, a0.x); a0.y = fmaf(e0, v4.y, a0.y); a0.z = fmaf(e0, v4.z, a0.z); a0.w = fmaf(e0, v4.w, a0.w);
             a1.x = fmaf(e1, v4.x, a1.x); a1.y = fmaf(e1, v4.y, a1.y); a1.z = fmaf(e1, v4.z, a1.z); a1.w = fmaf(e1, v4.w, a1.w);
         }
     }
-    bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * 2) * ATT_D + lane * 4, make_float4(a0.x / l0, a0.y / l0, a0.z / l0, a0.w / l0));
-    bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * 2 + 1) * ATT_D + lane * 4, make_float4(a1.x / l1, a1.y / l1, a1.z / l1, a1.w / l1));
+    bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * 2) * ATT_D + lane * 4, a0);
+    bstore_planes4(p.X, q_dim, p.planes, p.Bt, b, (g * 2 + 1) * ATT_D + lane * 4, a1);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -793,7 +793,7 @@ int generate_core_graph(lqt_engine* h, int slot, int P, const lqt_sampling* sp, 
 
 // loops A+B on the device. prompt_dev / trailing_dev / tts_pad_dev / forced_dev already filled.
 int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sampling* sp, int n_forced,
-                  bool trace, int* n_frames_out, int* chunk_out = nullptr, int (*chunk_hook)(lqt_engine*, int) = nullptr) {
+                  bool trace, int* n_frames_out) {
     if (slot < 0 || slot >= h->n_slots) { h->err = "bad slot"; return 1; }
     if (P < 1 || sp->max_new_tokens < 0 || sp->max_new_tokens > h->max_frames_cap ||
         P + sp->max_new_tokens > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
@@ -804,24 +804,19 @@ int generate_core(lqt_engine* h, int slot, int P, int trailing_len, const lqt_sa
     *h->st_host = g;
     CK(cudaMemcpyAsync(h->st, h->st_host, sizeof(GenState), cudaMemcpyHostToDevice, h->stream));
     if (h->frame_impl == 0) {
-        // persistent frame kernel: prefill + all frames in one cluster launch (frame_kernel.cuh). With a first-audio request the
-        // launch is split: prefill + the first chunk of frames, then the rest (the kernel resumes from GenState and the plain
-        // logits/last_hidden copies), so that the chunk can be vocoded on a second stream while generation continues.
+        // persistent frame kernel: prefill + all frames in one cluster launch (frame_kernel.cuh). The kernel can also RESUME an
+        // utterance (from GenState and the plain logits / last_hidden copies of the previous launch): $LQT_FK_SPLIT=n splits the
+        // launch after n frames, which is how the tests exercise that path.
         CK(cudaEventRecord(h->ev0, h->stream));
-        // without a cooperative launch co-residency of the 120 CTAs is only assumed: never run the chunk vocoder beside them then
-        const int chunk = (chunk_out && h->fk_coop && h->first_chunk > 0 && h->first_chunk < sp->max_new_tokens) ? h->first_chunk : 0;
-        if (chunk_out) *chunk_out = 0;
-        if (chunk) {
-            if (fk_launch(h, slot, 0, h->prompt_dev, P, chunk, trace)) return 1;
+        static const int split_env = getenv("LQT_FK_SPLIT") ? atoi(getenv("LQT_FK_SPLIT")) : 0;
+        const int split = (split_env > 0 && split_env < sp->max_new_tokens) ? split_env : 0;
+        if (split) {
+            if (fk_launch(h, slot, 0, h->prompt_dev, P, split, trace)) return 1;
             CK(cudaMemcpyAsync(h->st_host, h->st, sizeof(GenState), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             if (fk_check_abort(h)) return 1;
-            if (!h->st_host->done && h->st_host->n_frames == chunk) {
-                CK(cudaEventRecord(h->ev_chunk, h->stream));
-                *chunk_out = chunk;
-                if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;   // resumes: pos != 0
-                if (chunk_hook && chunk_hook(h, chunk)) return 1;      // enqueues the chunk vocoder + copy on stream2 (after the launch above)
-            }
+            if (!h->st_host->done && h->st_host->n_frames == split)
+                if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;       // resumes: pos != 0
         } else {
             if (fk_launch(h, slot, 0, h->prompt_dev, P, sp->max_new_tokens, trace)) return 1;
         }

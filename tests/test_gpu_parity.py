@@ -570,3 +570,24 @@ def test_synthesize_stream_delivers_chunks_while_generating(request):
     assert got[0][2] < 0.5 * total, (got[0][2], total)                  # first 2 s of audio well before the end
     ref_audio, ref_codes = eng.synthesize_tokens(ids, "en", 0.8, 50, 0.95, frames, 1234, 3)
     assert np.array_equal(codes, ref_codes) and np.array_equal(audio, ref_audio)
+
+
+def test_frame_kernel_resumes_across_launches(tiny_dir, monkeypatch):
+    """the persistent kernel can stop after n frames and resume in a second launch (GenState + plain logits / last_hidden
+    copies): $LQT_FK_SPLIT splits the launch; codes and logits must equal the single-launch run bit for bit"""
+    from leaxer_qwen3_tts_b200 import engine
+    ids = engine.wrap_text_ids([14990, 14615, 88225])
+    e0 = engine.Engine(tiny_dir, device=0)
+    prompt, trailing, pad = e0.build_prompt(ids, "en")
+    c0, t0 = e0.generate(prompt, trailing, pad, e0.sampling(0.8, 50, 0.95, 14, 5, 1), trace=True)
+    e0.close()
+    monkeypatch.setenv("LQT_FK_SPLIT", "5")
+    import subprocess, sys, os, json
+    # the split point is read once per process: run the split variant in a child process
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from __graft_entry__ import load_package; load_package();"
+            "from leaxer_qwen3_tts_b200 import engine; e = engine.Engine(%r, device=0); ids = engine.wrap_text_ids([14990, 14615, 88225]);"
+            "p, t, d = e.build_prompt(ids, 'en'); c, tb = e.generate(p, t, d, e.sampling(0.8, 50, 0.95, 14, 5, 1), trace=True);"
+            "np.savez(%r, c=c, tb=tb); e.close()") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), tiny_dir, "/tmp/lqt_split.npz")
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, LQT_FK_SPLIT="5"))
+    g = np.load("/tmp/lqt_split.npz")
+    assert np.array_equal(g["c"], c0) and np.array_equal(g["tb"], t0)
