@@ -469,7 +469,7 @@ def main():
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_note": "DRAM bytes per utterance (9 prefill rows + 375 frames = two frame_kernel launches: the first 25 frames for first-audio, then the rest), ncu capture of the same command (profiles/r1_v34_launches.md); algorithmic bytes per utterance = total x 375",
+                "traffic_note": "DRAM bytes per utterance (9 prefill rows + 375 frames, one frame_kernel launch), ncu capture of the same command (profiles/r1_v34_launches.md); algorithmic bytes per utterance = total x 375",
                 "kernel": "frame_kernel (persistent cluster kernel: TMA weight stream + tensor-core matrix-vector phases + attention + sampler), per frame",
                 "algorithmic_bytes_per_frame": fb, "us_per_frame": gen_s / frames_r0 * 1e6,
                 "peak_source": peak_src}
@@ -508,7 +508,7 @@ def main():
         "cpu_baseline": cpu,
         "first_audio_ms_p50": statistics.median(first_ms) if first_ms else None,
         "full_utterance_ms_p50": wall_max / a.steps / a.utterances * 1e3,
-        "first_audio_note": "rank 0, CUDA events: request start -> first 25 frames (2 s of PCM) vocoded on a second stream and copied into the "
+        "first_audio_note": "rank 0, CUDA events: request start -> first chunk (4 frames = 320 ms of PCM; later chunks 25 frames) vocoded on a second stream and copied into the "
                             "caller's pinned buffer while the frame kernel generates the rest; the reference has no streaming (first audio = full utterance)",
         "breakdown_ms_per_step": {"frame_loop": gen_ms_max / a.steps, "vocoder": voc_ms_max / a.steps,
                                   "device_total": dev_ms_max / a.steps, "host_wall": wall_max / a.steps * 1e3},

@@ -49,7 +49,7 @@ typedef struct lqt_stats {
     float    last_prefill_ms;
     int32_t  last_frames;
     float    last_total_ms;       /* lqt_synthesize_tokens: CUDA-event time prompt build -> last vocoder kernel */
-    float    first_audio_ms;      /* lqt_synthesize_tokens: CUDA-event time prompt build -> the first chunk of PCM (2 s) copied into
+    float    first_audio_ms;      /* lqt_synthesize_tokens: CUDA-event time prompt build -> the first chunk of PCM (320 ms) copied into
                                      the caller's buffer (chunked vocoding on a second stream); = last_total_ms when chunking is off */
     int32_t  frame_impl_active;   /* the frame loop lqt_synthesize_tokens runs on this handle: LQT_FRAME_PERSISTENT, _BATCHED or _GRAPH */
     int32_t  cooperative_launch;  /* 1 = the persistent kernel is launched with the cooperative attribute (co-residency guaranteed);
@@ -196,8 +196,8 @@ int lqt_debug_tc_gemm(lqt_engine* h, const float* W, const float* x, int32_t N, 
                       int32_t splits, float* out);
 
 /* Streaming form of lqt_synthesize_tokens (the reference returns the whole waveform at the end, :430-436): same
- * arguments and result, plus a callback that is invoked on the calling thread, in order, for every chunk of PCM (2 s by
- * default, $LQT_FIRST_CHUNK frames) as soon as it has been vocoded and copied into audio_out -- while the frame kernel is still
+ * arguments and result, plus a callback that is invoked on the calling thread, in order, for every chunk of PCM (the
+ * first one 4 frames = 320 ms, then 25 frames = 2 s: $LQT_FIRST_CHUNK / $LQT_STREAM_CHUNK) as soon as it has been vocoded and copied into audio_out -- while the frame kernel is still
  * generating the rest of the utterance. pcm points into audio_out at first_sample. The chunks are bit-identical to the one-shot
  * result (streaming vocoder with carried state). */
 typedef void (*lqt_audio_callback)(void* user, const float* pcm, int64_t first_sample, int64_t n_samples);

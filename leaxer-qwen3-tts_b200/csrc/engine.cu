@@ -134,10 +134,12 @@ struct lqt_engine {
     std::map<int, cudaGraphExec_t> graphs;
     int kernels_per_frame = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr;
-    // first-audio path: the first `first_chunk` frames are vocoded on a second stream while the frame kernel keeps generating
+    // streaming path: finished frames are vocoded on a second stream while the frame kernel keeps generating -- a short first
+    // chunk (first-audio latency), then `stream_chunk` frames at a time
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_chunk = nullptr, ev_first = nullptr, ev_end = nullptr;
-    int first_chunk = 25;                     // frames (2 s of audio); 0 = off; $LQT_FIRST_CHUNK
+    int first_chunk = 4;                      // frames of the first chunk (320 ms of audio); 0 = streaming off; $LQT_FIRST_CHUNK
+    int stream_chunk = 25;                    // frames of every later chunk (2 s); $LQT_STREAM_CHUNK
     float* chunk_audio_dev = nullptr; size_t chunk_audio_cap = 0;
     float* chunk_audio_out = nullptr; int64_t chunk_audio_out_cap = 0;    // caller's buffer of the running lqt_synthesize_tokens call
     bool chunk_pending = false;               // stream2 holds work of the current call (synchronised on every exit path)
@@ -1294,6 +1296,8 @@ int init_engine(lqt_engine* h, const std::string& dir) {
     CK(cudaEventCreate(&h->ev_chunk)); CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_end));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     if (const char* e = getenv("LQT_FIRST_CHUNK")) h->first_chunk = std::max(0, atoi(e));
+    if (const char* e = getenv("LQT_STREAM_CHUNK")) h->stream_chunk = std::max(1, atoi(e));
+    h->stream_chunk = std::max(h->stream_chunk, h->first_chunk);
     if (voc_tc_init(h)) return 1;
     if (h->frame_impl != LQT_FRAME_GRAPH && h->frame_impl != LQT_FRAME_BATCHED && fk_init(h)) {
         // shapes the persistent kernel does not cover (e.g. the 1.7B talker: > 64 rows per CTA). An explicit request for the
@@ -1853,14 +1857,14 @@ int lqt_synthesize_tokens(lqt_engine* h, const int64_t* token_ids, int32_t n_ids
 // reports every finished frame through a pinned host word; the host vocodes the finished frames chunk by chunk on the second
 // stream (streaming vocoder with carried state: each chunk is bit-identical to the one-shot decode, nothing is decoded twice)
 // and copies the PCM into the caller's buffer while generation continues on the other SMs. After the last frame only the last
-// chunk is left to decode. chunk = h->first_chunk frames (2 s): the first-audio latency.
+// chunk is left to decode. The first chunk is h->first_chunk frames (the first-audio latency), the others h->stream_chunk.
 static int synthesize_streaming(lqt_engine* h, int P, int TL, const lqt_sampling* sp, float* audio_out, int64_t audio_capacity,
                                 int64_t* n_samples, int64_t* codes_out, int32_t* n_frames) {
-    const int chunk = h->first_chunk, spf = h->sp.samples_per_frame, max_new = sp->max_new_tokens;
+    const int chunk = h->stream_chunk, first_n = h->first_chunk, spf = h->sp.samples_per_frame, max_new = sp->max_new_tokens;
     if (P < 1 || max_new < 0 || max_new > h->max_frames_cap || P + max_new > h->sp.max_pos) { h->err = "P + max_new_tokens exceeds max_pos"; return 1; }
     if (audio_capacity < (int64_t)max_new * spf) { h->err = "audio_out too small"; return 1; }
     if (upload_sampling(h, sp)) return 1;
-    if (ensure_audio(h, max_new)) return 1;
+    if (ensure_audio(h, std::max(max_new, chunk))) return 1;      // the throw-away chunk below writes `chunk` frames of PCM
     if (h->voc_reserved_frames < chunk) {
         // size every vocoder workspace (and the per-layer state) for a chunk BEFORE the frame kernel starts: allocations while it
         // runs would serialise behind it. One throw-away chunk of zeros does exactly the allocations the real chunks need.
@@ -1900,9 +1904,10 @@ static int synthesize_streaming(lqt_engine* h, int P, int TL, const lqt_sampling
             ++delivered;
         }
     };
-    auto vocode = [&](int upto) -> int {                          // frames [done, upto) in chunks of at most `chunk`
+    auto next_size = [&]() { return done == 0 ? first_n : chunk; };
+    auto vocode = [&](int upto) -> int {                          // frames [done, upto): the first chunk, then chunks of at most `chunk`
         while (done < upto) {
-            const int n = std::min(chunk, upto - done);
+            const int n = std::min(next_size(), upto - done);
             if (run_vocoder(h, h->codes_dev + (size_t)done * N_CODEBOOKS, n, h->audio_dev + (size_t)done * spf, h->stream2, &h->voc_stream)) return 1;
             h->voc_stream.t0 += n;
             CK(cudaMemcpyAsync(audio_out + (size_t)done * spf, h->audio_dev + (size_t)done * spf, (size_t)n * spf * sizeof(float), cudaMemcpyDeviceToHost, h->stream2));
@@ -1921,9 +1926,9 @@ static int synthesize_streaming(lqt_engine* h, int P, int TL, const lqt_sampling
     while (!finished) {
         finished = cudaEventQuery(h->ev_chunk) == cudaSuccess;
         const int avail = finished ? h->st_host->n_frames : *prog;
-        const int upto = finished ? avail : (avail / chunk) * chunk;          // whole chunks while the kernel runs, the rest at the end
+        const int upto = finished ? avail : (avail - done >= next_size() ? done + next_size() : done);   // whole chunks while the kernel runs, the rest at the end
         if (upto > done) { if (vocode(upto)) return 1; }
-        else if (!finished) { struct timespec ts = {0, 100000}; nanosleep(&ts, nullptr); }
+        else if (!finished) { struct timespec ts = {0, 50000}; nanosleep(&ts, nullptr); }
         deliver(false);
     }
     CK(cudaEventRecord(h->ev_end, h->stream2));

@@ -362,7 +362,15 @@ def test_first_audio_chunk_is_exact_prefix(tiny_dir, monkeypatch):
     a0, c0 = e0.synthesize_tokens(ids, "en", max_new_tokens=60, seed=5, utterance_id=1)
     s0 = e0.stats()
     assert abs(s0.first_audio_ms - s0.last_total_ms) < 1e-3
+    a0s, c0s = e0.synthesize_tokens(ids, "en", max_new_tokens=12, seed=5, utterance_id=1)
     e0.close()
+    monkeypatch.delenv("LQT_FIRST_CHUNK")                 # defaults: 4 frames first, then 25 -- also for utterances shorter than 25
+    e2 = engine.Engine(tiny_dir, device=0)
+    a2s, c2s = e2.synthesize_tokens(ids, "en", max_new_tokens=12, seed=5, utterance_id=1)
+    assert np.array_equal(c0s, c2s) and np.array_equal(a0s, a2s) and 0 < e2.stats().first_audio_ms < e2.stats().last_total_ms
+    a2l, c2l = e2.synthesize_tokens(ids, "en", max_new_tokens=60, seed=5, utterance_id=1)
+    assert np.array_equal(c0, c2l) and np.array_equal(a0, a2l)
+    e2.close()
     monkeypatch.setenv("LQT_FIRST_CHUNK", "25")
     e1 = engine.Engine(tiny_dir, device=0)
     a1, c1 = e1.synthesize_tokens(ids, "en", max_new_tokens=60, seed=5, utterance_id=1)
@@ -551,7 +559,7 @@ def test_streaming_vocoder_is_bit_identical(request, which, T, chunks):
 
 
 def test_synthesize_stream_delivers_chunks_while_generating(request):
-    """lqt_synthesize_stream on the full model: PCM arrives in 2 s chunks, in order, covering the utterance exactly, equal to the
+    """lqt_synthesize_stream on the full model: PCM arrives in chunks (4 frames first, then 2 s each), in order, covering the utterance exactly, equal to the
     returned buffer and to the non-streaming call; the first chunk arrives long before the call returns (generation of the
     remaining frames and vocoding of the finished ones overlap)."""
     import time
@@ -565,9 +573,9 @@ def test_synthesize_stream_delivers_chunks_while_generating(request):
     total = time.perf_counter() - t0
     assert codes.shape == (frames, 16) and audio.shape[0] == frames * 1920
     assert [g[0] for g in got] == sorted(g[0] for g in got) and got[0][0] == 0
-    assert sum(g[1].shape[0] for g in got) == audio.shape[0] and len(got) == (frames + 24) // 25
+    assert sum(g[1].shape[0] for g in got) == audio.shape[0] and [g[1].shape[0] // 1920 for g in got] == [4] + [25] * 6 + [6]
     assert np.array_equal(np.concatenate([g[1] for g in got]), audio)
-    assert got[0][2] < 0.5 * total, (got[0][2], total)                  # first 2 s of audio well before the end
+    assert got[0][2] < 0.25 * total, (got[0][2], total)                 # first audio long before the end
     ref_audio, ref_codes = eng.synthesize_tokens(ids, "en", 0.8, 50, 0.95, frames, 1234, 3)
     assert np.array_equal(codes, ref_codes) and np.array_equal(audio, ref_audio)
 
