@@ -11,8 +11,10 @@
 // of merges.txt is stored as a rank-0 pair.
 #include "tokenizer.h"
 
+#include <vector>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -37,6 +39,124 @@ struct Symbols {                          // GPT-2 byte encoder with the referen
     }
 };
 const Symbols& symbols() { static const Symbols s; return s; }
+
+// ---- HF mode (tokenizer.h): the published Qwen2 pipeline ---------------------------------------------------------------
+#include "unicode_tables.inc"
+
+void put_utf8(std::string& out, uint32_t cp) {
+    if (cp < 0x80) out.push_back(static_cast<char>(cp));
+    else if (cp < 0x800) { out.push_back(static_cast<char>(0xC0 | (cp >> 6))); out.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
+    else if (cp < 0x10000) { out.push_back(static_cast<char>(0xE0 | (cp >> 12))); out.push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F)));
+                             out.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
+    else { out.push_back(static_cast<char>(0xF0 | (cp >> 18))); out.push_back(static_cast<char>(0x80 | ((cp >> 12) & 0x3F)));
+           out.push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F))); out.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
+}
+
+struct HfSymbols {                        // GPT-2 bytes_to_unicode: printable bytes keep their code point, the rest go to U+0100..
+    std::string of[256];
+    HfSymbols() {
+        int shifted = 0;
+        for (int b = 0; b < 256; ++b) {
+            const bool direct = (b >= 33 && b <= 126) || (b >= 161 && b <= 172) || (b >= 174 && b <= 255);
+            put_utf8(of[b], direct ? static_cast<uint32_t>(b) : static_cast<uint32_t>(0x100 + shifted++));
+        }
+    }
+};
+const HfSymbols& hf_symbols() { static const HfSymbols s; return s; }
+
+template <size_t N>
+bool in_ranges(const uint32_t (&tab)[N][2], uint32_t cp) {
+    size_t lo = 0, hi = N;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (cp < tab[mid][0]) hi = mid;
+        else if (cp > tab[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+inline bool u_letter(uint32_t c) { return in_ranges(kUnicodeLetters, c); }
+inline bool u_number(uint32_t c) { return in_ranges(kUnicodeNumbers, c); }
+inline bool u_space(uint32_t c) {         // Unicode White_Space (what \s means in the pattern)
+    return (c >= 0x9 && c <= 0xD) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 || (c >= 0x2000 && c <= 0x200A) ||
+           c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+inline bool u_newline(uint32_t c) { return c == '\r' || c == '\n'; }
+inline bool u_other(uint32_t c) { return !u_space(c) && !u_letter(c) && !u_number(c); }      // [^\s\p{L}\p{N}]
+
+struct CodePoint { uint32_t cp; uint32_t off; };       // code point and its byte offset in the text
+
+// UTF-8 -> code points; a byte that does not start a valid sequence becomes one "other" code point (U+FFFD) of length 1
+std::vector<CodePoint> decode_utf8(const std::string& s) {
+    std::vector<CodePoint> out;
+    const size_t n = s.size();
+    size_t i = 0;
+    while (i < n) {
+        const unsigned char c = static_cast<unsigned char>(s[i]);
+        uint32_t cp = 0xFFFD; size_t len = 1;
+        auto cont = [&](size_t k) { return i + k < n && (static_cast<unsigned char>(s[i + k]) & 0xC0) == 0x80; };
+        if (c < 0x80) cp = c;
+        else if ((c & 0xE0) == 0xC0 && c >= 0xC2 && cont(1)) { cp = ((c & 0x1Fu) << 6) | (static_cast<unsigned char>(s[i + 1]) & 0x3Fu); len = 2; }
+        else if ((c & 0xF0) == 0xE0 && cont(1) && cont(2)) {
+            cp = ((c & 0x0Fu) << 12) | ((static_cast<unsigned char>(s[i + 1]) & 0x3Fu) << 6) | (static_cast<unsigned char>(s[i + 2]) & 0x3Fu); len = 3;
+            if (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF)) { cp = 0xFFFD; len = 1; }
+        } else if ((c & 0xF8) == 0xF0 && cont(1) && cont(2) && cont(3)) {
+            cp = ((c & 0x07u) << 18) | ((static_cast<unsigned char>(s[i + 1]) & 0x3Fu) << 12) | ((static_cast<unsigned char>(s[i + 2]) & 0x3Fu) << 6) |
+                 (static_cast<unsigned char>(s[i + 3]) & 0x3Fu); len = 4;
+            if (cp < 0x10000 || cp > 0x10FFFF) { cp = 0xFFFD; len = 1; }
+        }
+        out.push_back(CodePoint{cp, static_cast<uint32_t>(i)});
+        i += len;
+    }
+    return out;
+}
+
+// Length (in code points) of the match of the Qwen2 pattern starting exactly at t[i]:
+//   (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n\p{L}\p{N}]?\p{L}+ | \p{N} | ?[^\s\p{L}\p{N}]+[\r\n]* | \s*[\r\n]+ | \s+(?!\S) | \s+
+// (leftmost alternative that matches, greedy quantifiers with backtracking). Every code point starts some alternative.
+size_t hf_match_at(const std::vector<CodePoint>& t, size_t i) {
+    const size_t n = t.size();
+    const uint32_t c = t[i].cp;
+    auto lower = [](uint32_t x) { return (x >= 'A' && x <= 'Z') ? x + 32 : x; };
+    if (c == '\'' && i + 1 < n) {
+        const uint32_t a = lower(t[i + 1].cp), b = (i + 2 < n) ? lower(t[i + 2].cp) : 0;
+        if (a == 's' || a == 't') return 2;
+        if (a == 'r' && b == 'e') return 3;
+        if (a == 'v' && b == 'e') return 3;
+        if (a == 'm') return 2;
+        if (a == 'l' && b == 'l') return 3;
+        if (a == 'd') return 2;
+    }
+    {   // [^\r\n\p{L}\p{N}]?\p{L}+
+        size_t j = i;
+        if (!u_newline(c) && !u_letter(c) && !u_number(c)) j = i + 1;          // the optional prefix (greedy: tried first)
+        size_t k = j;
+        while (k < n && u_letter(t[k].cp)) ++k;
+        if (k > j) return k - i;
+        // (without the prefix the first code point would have to be a letter, which the branch above already covers)
+    }
+    if (u_number(c)) return 1;                                                // \p{N}
+    {   //  ?[^\s\p{L}\p{N}]+[\r\n]*
+        size_t j = i + ((c == ' ') ? 1 : 0);
+        size_t k = j;
+        while (k < n && u_other(t[k].cp)) ++k;
+        if (k > j) { while (k < n && u_newline(t[k].cp)) ++k; return k - i; }
+    }
+    if (u_space(c)) {
+        size_t e = i;
+        while (e < n && u_space(t[e].cp)) ++e;                                // the whitespace run [i, e)
+        size_t last_nl = n;
+        for (size_t k = i; k < e; ++k) if (u_newline(t[k].cp)) last_nl = k;
+        if (last_nl != n) return last_nl + 1 - i;                             // \s*[\r\n]+ : up to the last newline of the run
+        if (e == n) return e - i;                                             // \s+(?!\S) at the end of the text
+        if (e - i >= 2) return e - i - 1;                                     // \s+(?!\S): leaves one space for the next word
+        return e - i;                                                         // \s+
+    }
+    return 1;
+}
+
+TokenizerMode g_mode = (std::getenv("LEAXER_TOKENIZER") && std::string(std::getenv("LEAXER_TOKENIZER")) == "hf") ? TokenizerMode::HF
+                                                                                                              : TokenizerMode::Reference;
 
 inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 inline bool is_alpha(unsigned char c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'); }
@@ -100,7 +220,8 @@ private:
         k.push_back(':'); k += a; k += b;
         return k;
     }
-    void merge_chunk(const std::string& chunk, std::vector<std::string>& out) const;
+    void merge_chunk(const std::string& chunk, std::vector<std::string>& out, const std::string (&sym)[256]) const;
+    void emit(const std::string& chunk, std::vector<std::string>& parts, const std::string (&sym)[256], std::vector<int32_t>& ids) const;
 
     bool vocab_ok_ = false, merges_ok_ = false;
     std::unordered_map<std::string, int32_t> by_text_;
@@ -144,6 +265,7 @@ bool Bpe::read_vocab(const std::string& path) {
         if (buf[p] != '"') { std::fprintf(stderr, "Expected '\"' at position %zu\n", p); return false; }
         ++p;
         std::string key;
+        bool has_surrogate = false;
         while (p < n && buf[p] != '"') {
             char ch = buf[p];
             if (ch != '\\') { key.push_back(ch); ++p; continue; }
@@ -164,6 +286,7 @@ bool Bpe::read_vocab(const std::string& path) {
                 else if (cp < 0x800) { key.push_back(static_cast<char>(0xC0 | (cp >> 6))); key.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }
                 else { key.push_back(static_cast<char>(0xE0 | (cp >> 12))); key.push_back(static_cast<char>(0x80 | ((cp >> 6) & 0x3F)));
                        key.push_back(static_cast<char>(0x80 | (cp & 0x3F))); }          // BMP only, surrogates not joined
+                if (cp >= 0xD800 && cp <= 0xDFFF) has_surrogate = true;
                 p += 4;
             } else key.push_back(ch);                                                    // '\\', '"' and anything else: literal
             ++p;
@@ -179,6 +302,22 @@ bool Bpe::read_vocab(const std::string& path) {
         while (p < n && std::isdigit(static_cast<unsigned char>(buf[p]))) { id = id * 10 + (buf[p] - '0'); ++p; }
         by_text_[key] = id;
         by_id_[id] = key;
+        if (has_surrogate) {
+            // HF mode: the same token with its surrogate pairs joined into 4-byte UTF-8 (an extra key; a reference-mode lookup can never
+            // produce it, because there every byte >= 161 is a raw single byte)
+            std::string joined;
+            for (size_t q = 0; q < key.size();) {
+                const unsigned char b0 = static_cast<unsigned char>(key[q]);
+                if (b0 == 0xED && q + 5 < key.size() && (static_cast<unsigned char>(key[q + 1]) & 0xF0) == 0xA0 &&
+                    static_cast<unsigned char>(key[q + 3]) == 0xED && (static_cast<unsigned char>(key[q + 4]) & 0xF0) == 0xB0) {
+                    const uint32_t hi = 0xD000u | ((static_cast<unsigned char>(key[q + 1]) & 0x3Fu) << 6) | (static_cast<unsigned char>(key[q + 2]) & 0x3Fu);
+                    const uint32_t lo = 0xD000u | ((static_cast<unsigned char>(key[q + 4]) & 0x3Fu) << 6) | (static_cast<unsigned char>(key[q + 5]) & 0x3Fu);
+                    put_utf8(joined, 0x10000u + ((hi - 0xD800u) << 10) + (lo - 0xDC00u));
+                    q += 6;
+                } else { joined.push_back(key[q]); ++q; }
+            }
+            by_text_[joined] = id;
+        }
         if (++count % 10000 == 0) std::fprintf(stderr, "Loaded %d tokens...\n", count);
     }
     std::fprintf(stderr, "Successfully loaded %d tokens\n", count);
@@ -210,9 +349,9 @@ bool Bpe::read_merges(const std::string& path) {
     return n_merges_ > 0;
 }
 
-void Bpe::merge_chunk(const std::string& chunk, std::vector<std::string>& out) const {
+void Bpe::merge_chunk(const std::string& chunk, std::vector<std::string>& out, const std::string (&sym)[256]) const {
     out.clear();
-    for (unsigned char c : chunk) out.push_back(symbols().of[c]);
+    for (unsigned char c : chunk) out.push_back(sym[c]);
     while (out.size() > 1) {
         int best = INT_MAX;
         size_t at = 0;
@@ -226,6 +365,16 @@ void Bpe::merge_chunk(const std::string& chunk, std::vector<std::string>& out) c
     }
 }
 
+void Bpe::emit(const std::string& chunk, std::vector<std::string>& parts, const std::string (&sym)[256], std::vector<int32_t>& ids) const {
+    if (merges_ok_) merge_chunk(chunk, parts, sym);
+    else { parts.clear(); for (char c : chunk) parts.push_back(std::string(1, c)); }
+    for (const std::string& tok : parts) {
+        auto it = by_text_.find(tok);
+        if (it != by_text_.end()) ids.push_back(it->second);
+        else for (unsigned char c : tok) ids.push_back(c);         // unknown symbol: its byte values
+    }
+}
+
 std::vector<int32_t> Bpe::encode(const std::string& text) const {
     std::vector<int32_t> ids;
     if (text.empty()) return ids;
@@ -234,19 +383,24 @@ std::vector<int32_t> Bpe::encode(const std::string& text) const {
         return ids;
     }
     std::vector<std::string> parts;
+    if (g_mode == TokenizerMode::HF) {
+        const std::vector<CodePoint> t = decode_utf8(text);
+        size_t i = 0;
+        while (i < t.size()) {
+            const size_t m = hf_match_at(t, i);
+            const size_t b0 = t[i].off, b1 = (i + m < t.size()) ? t[i + m].off : text.size();
+            emit(text.substr(b0, b1 - b0), parts, hf_symbols().of, ids);
+            i += m;
+        }
+        return ids;
+    }
     size_t i = 0;
     while (i < text.size()) {
         const size_t m = match_at(text, i);
         if (m == 0) { ++i; continue; }                  // matched by no alternative: dropped
         const std::string chunk = text.substr(i, m);
         i += m;
-        if (merges_ok_) merge_chunk(chunk, parts);
-        else { parts.clear(); for (char c : chunk) parts.push_back(std::string(1, c)); }
-        for (const std::string& tok : parts) {
-            auto it = by_text_.find(tok);
-            if (it != by_text_.end()) ids.push_back(it->second);
-            else for (unsigned char c : tok) ids.push_back(c);     // unknown symbol: its byte values
-        }
+        emit(chunk, parts, symbols().of, ids);
     }
     return ids;
 }
@@ -261,6 +415,8 @@ bool is_tokenizer_ready() { return instance().vocab_ok() && instance().merges_ok
 std::vector<int32_t> tokenize(const std::string& text) { return instance().encode(text); }
 std::string token_to_string(int32_t id) { return instance().text_of(id); }
 int32_t string_to_token(const std::string& token) { return instance().id_of(token); }
+void set_tokenizer_mode(TokenizerMode mode) { g_mode = mode; }
+TokenizerMode tokenizer_mode() { return g_mode; }
 
 } // namespace io
 } // namespace leaxer_qwen

@@ -17,6 +17,16 @@ std::vector<int32_t> tokenize(const std::string& text);
 std::string token_to_string(int32_t id);             // "" when unknown
 int32_t string_to_token(const std::string& token);   // -1 when unknown
 
+// Extension, off by default: the reference's pre-tokeniser is ASCII-only and maps bytes 161-172 / 174-255 to raw
+// single bytes, so non-ASCII text (zh/ja/ko) never matches the Qwen vocabulary and degrades to raw byte ids. HF mode is the
+// published Qwen2 tokenizer pipeline instead -- the Unicode pre-tokeniser pattern, the GPT-2 byte -> code-point alphabet,
+// surrogate pairs in vocab.json -- checked against the HuggingFace `tokenizers` library (tests/test_hf_tokenizer.py). Input is
+// expected in NFC (the published pipeline normalises; no normaliser is built in). Specials are still added by id by the engine.
+#define LEAXER_HAS_HF_TOKENIZER 1
+enum class TokenizerMode { Reference, HF };
+void set_tokenizer_mode(TokenizerMode mode);         // process-wide, like the tokenizer itself; also $LEAXER_TOKENIZER=hf
+TokenizerMode tokenizer_mode();
+
 } // namespace io
 } // namespace leaxer_qwen
 

@@ -4,13 +4,15 @@
 // Unknown flags and flags without a value are ignored, -m and -p are required (exit 1 + usage), the model directory
 // must exist, the output's parent directory is created, synthesis failure / unwritable output -> exit 1.
 // Extensions: --seed N (Philox seed; the reference's sampler is not reproducible), also $LEAXER_SEED;
-// --dump-codes PATH (the generated codes, int64 [frames][16] raw, for parity tests).
+// --dump-codes PATH (the generated codes, int64 [frames][16] raw, for parity tests); --tokenizer hf|reference (default reference:
+// the reference's ASCII-only pre-tokeniser; hf = the published Qwen2 pipeline, io/tokenizer.h; also $LEAXER_TOKENIZER=hf).
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
 #include <string>
 #include <vector>
 
+#include "io/tokenizer.h"
 #include "io/wav_reader.h"
 #include "tts_onnx.h"
 
@@ -28,6 +30,7 @@ struct Options {
     const char* dump_codes = nullptr;
     float temperature = 0.8f, top_p = 0.95f;
     int top_k = 50, max_tokens = 2048;
+    const char* tokenizer = nullptr;
     bool have_seed = false;
     unsigned seed = 0;
     bool help = false;
@@ -69,6 +72,7 @@ Options parse(int argc, char** argv) {
         else if (a == "--top-p") o.top_p = static_cast<float>(std::atof(argv[++i]));
         else if (a == "--max-tokens") o.max_tokens = std::atoi(argv[++i]);
         else if (a == "--dump-codes") o.dump_codes = argv[++i];
+        else if (a == "--tokenizer") o.tokenizer = argv[++i];
         else if (a == "--seed") { o.seed = static_cast<unsigned>(std::strtoul(argv[++i], nullptr, 10)); o.have_seed = true; }
     }
     return o;
@@ -105,6 +109,8 @@ int main(int argc, char** argv) {
     const fs::path out(o.output);
     if (out.has_parent_path()) fs::create_directories(out.parent_path());
 
+    if (o.tokenizer) leaxer_qwen::io::set_tokenizer_mode(std::string(o.tokenizer) == "hf" ? leaxer_qwen::io::TokenizerMode::HF
+                                                                                          : leaxer_qwen::io::TokenizerMode::Reference);
     leaxer_qwen::TTSEngine engine(o.model);
     if (!engine.is_ready()) {
         std::fprintf(stderr, "Error: %s\n", engine.get_error().c_str());

@@ -8,6 +8,7 @@
 //   wav PATH              int32 sample rate (or -1) followed by the decoded samples
 //   resample N SRC DST    resample(N synthetic samples)
 //   tok VOCAB MERGES TEXT int32 token ids ("-" for a missing file: tokenizer without vocab/merges)
+//   tokhf VOCAB MERGES FILE   (this repo's build only) HF-faithful tokenizer mode: ids of every line of FILE
 //   melwav PATH           the clone front-end of src/tts_onnx.cpp:331-359: read_wav -> resample to 24 kHz -> log-mel [128][frames]
 #include <cmath>
 #include <cstdint>
@@ -80,5 +81,37 @@ int main(int argc, char** argv) {
         for (int32_t t : tokenize(argv[4])) put_i(t);
         return 0;
     }
+#ifdef LEAXER_HAS_HF_TOKENIZER
+    // tokhf VOCAB MERGES FILE: one text per line of FILE ("\\n" / "\\r" / "\\t" / "\\\\" escapes) through the HF-faithful mode (this repo's
+    // host only); output per line: count, ids
+    if (cmd == "tokhf" && argc >= 5) {
+        set_tokenizer_mode(TokenizerMode::HF);
+        if (!load_vocab(argv[2]) || !load_merges(argv[3])) return 1;
+        FILE* f = std::fopen(argv[4], "rb");
+        if (!f) return 1;
+        std::string all;
+        char buf[4096];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) all.append(buf, got);
+        std::fclose(f);
+        size_t pos = 0;
+        while (pos <= all.size()) {
+            size_t e = all.find('\n', pos);
+            if (e == std::string::npos) { if (pos == all.size()) break; e = all.size(); }
+            std::string text;
+            for (size_t i = pos; i < e; ++i) {
+                if (all[i] == '\\' && i + 1 < e) {
+                    const char c = all[++i];
+                    text.push_back(c == 'n' ? '\n' : c == 'r' ? '\r' : c == 't' ? '\t' : c);
+                } else text.push_back(all[i]);
+            }
+            const std::vector<int32_t> ids = tokenize(text);
+            put_i(static_cast<int32_t>(ids.size()));
+            for (int32_t t : ids) put_i(t);
+            pos = e + 1;
+        }
+        return 0;
+    }
+#endif
     return 2;
 }
