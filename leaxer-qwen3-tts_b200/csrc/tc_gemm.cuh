@@ -131,7 +131,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sh->tmem_base;
-    pdl_wait();                                                   // barriers and TMEM are set up; now the predecessor's outputs (X) are needed
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -141,9 +140,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             const int wrow = second ? row0 - p.n_split2 : row0;
             const int xrow = blockIdx.z * p.BN;
             const uint32_t bytes = (uint32_t)stage_bytes;
-            for (int i = 0; i < niter; ++i) {
+            // The WEIGHTS do not depend on the predecessor kernel: the first ring-full of weight boxes is requested before the
+            // programmatic-dependency wait, so their HBM latency overlaps the predecessor's tail; only the X boxes (L2) follow it
+            const int npre = min(niter, p.stages);
+            for (int i = 0; i < npre; ++i) {
+                tg_mbar_expect_tx(&sh->full[i], bytes);
+                tg_tma_2d(smem + (size_t)i * stage_bytes, mw, (kb0 + i) * TG_BK, wrow, &sh->full[i]);
+            }
+            pdl_wait();                                           // the predecessor's outputs (X) are complete and visible
+            for (int i = 0; i < npre; ++i)
+                tg_tma_2d(smem + (size_t)i * stage_bytes + TG_BM * 128, &map_x, (kb0 + i) * TG_BK, xrow, &sh->full[i]);
+            for (int i = npre; i < niter; ++i) {
                 const int s = i % p.stages;
-                if (i >= p.stages) tg_mbar_wait(&sh->empty[s], (uint32_t)((i / p.stages) - 1) & 1u);
+                tg_mbar_wait(&sh->empty[s], (uint32_t)((i / p.stages) - 1) & 1u);
                 unsigned char* a = smem + (size_t)s * stage_bytes;
                 tg_mbar_expect_tx(&sh->full[s], bytes);
                 tg_tma_2d(a, mw, (kb0 + i) * TG_BK, wrow, &sh->full[s]);
@@ -173,6 +182,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         // ===== epilogue: TMEM lane (warp & 3) * 32 + lane = weight row; columns = plane * Bt + b =====
         tg_mbar_wait(&sh->tmem_full, 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        pdl_wait();                                               // (returns at once: the X boxes were loaded behind the producer's wait)
         const int q = warp & 3;
         const int n = row0 + q * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16);
