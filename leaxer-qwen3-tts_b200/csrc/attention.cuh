@@ -38,6 +38,27 @@ struct AttnParams {
 };
 
 // one warp: RMSNorm (optional) + RoPE on a 128-wide head vector; lane holds dims [4*lane, 4*lane+4)
+// per-head RMSNorm (weights w; skipped when !normed) + rotate-half RoPE with this lane's cos / sin values already in registers
+// (callers on a latency-critical path load them BEFORE they wait for v)
+LQT_DEVINL float4 head_norm_rope_regs(float4 v, bool normed, const float4 w, float eps, const float4 c, const float4 s, int lane) {
+    if (normed) {
+        float ss = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+        const float r = 1.0f / sqrtf(ss / (float)ATT_D + eps);
+        v.x = (v.x * r) * w.x; v.y = (v.y * r) * w.y; v.z = (v.z * r) * w.z; v.w = (v.w * r) * w.w;
+    }
+    float4 o;                                            // rotate-half: partner dims are +-64 -> lane ^ 16
+    o.x = __shfl_xor_sync(0xffffffffu, v.x, 16); o.y = __shfl_xor_sync(0xffffffffu, v.y, 16);
+    o.z = __shfl_xor_sync(0xffffffffu, v.z, 16); o.w = __shfl_xor_sync(0xffffffffu, v.w, 16);
+    float4 r;
+    if (lane < 16) {       // first half:  x1*c - x2*s
+        r.x = v.x * c.x - o.x * s.x; r.y = v.y * c.y - o.y * s.y;
+        r.z = v.z * c.z - o.z * s.z; r.w = v.w * c.w - o.w * s.w;
+    } else {               // second half: x2*c + x1*s
+        r.x = v.x * c.x + o.x * s.x; r.y = v.y * c.y + o.y * s.y;
+        r.z = v.z * c.z + o.z * s.z; r.w = v.w * c.w + o.w * s.w;
+    }
+    return r;
+}
 LQT_DEVINL float4 head_norm_rope(float4 v, const float* norm_w, float eps,
                                  const float* cosr, const float* sinr, int lane) {
     if (norm_w) {

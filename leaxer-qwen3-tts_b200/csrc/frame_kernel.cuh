@@ -199,6 +199,19 @@ struct FkDesc {                 // this CTA's weight slice of one phase kind
     int lw;                     // log2(warps per tile pair) of the tensor-core product (gemv_mma)
     int rpp;                    // O-projection: rows reduced per cluster partner
 };
+// One warp's share of a matrix-vector phase, precomputed at kernel start (per stack, phase kind and consumer warp) so that the
+// product starts with one 16-byte shared load instead of ~100 dependent integer instructions: the (tile pair, K slice) unit of gemv_mma.
+struct alignas(16) FkUnit {
+    uint32_t off;               // byte offset of the unit's first block inside the slice image (before the lane offset)
+    uint16_t step;              // bytes between consecutive blocks of this warp (block size x warps per pair)
+    uint16_t iters;             // blocks of this warp (even)
+    uint8_t st0, st1;           // first / last ring stage of the slice that the unit reads
+    uint8_t flags;              // 1 = this warp has a unit, 2 = the unit is the odd last tile (8 rows)
+    uint8_t ks;                 // K slice index = row of part[][]
+    uint16_t pidx;              // first row of the unit inside the slice
+    uint16_t binc;              // B-fragment stride of this warp (96 bytes x warps per pair)
+};
+enum { FKU_ACTIVE = 1, FKU_SINGLE = 2 };
 struct FkShared {
     uint64_t full[16];
     uint64_t empty[16];
@@ -218,6 +231,7 @@ struct FkShared {
     uint64_t land_bar[2];             // multicast landing buffers: complete_tx from all CTAs of the cluster
     uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
     FkDesc desc[2][10];           // [stack][phase kind]
+    FkUnit unit[2][10][FK_CWARPS];   // [stack][phase kind][consumer warp]
 };
 
 struct FkCtx {
@@ -251,8 +265,13 @@ enum { FKT_A = 1, FKT_B = 2, FKT_C = 3, FKT_D = 4, FKT_E = 5, FKT_HEAD = 6, FKT_
 // The marks are compiled only into the profiling build (liblqt_b200_prof.so, -DFK_MARKS; tools/fk_timeline.py loads it through
 // $LQT_B200_LIB): even disabled, ~10 mark sites per phase cost ~2 % of the frame in this issue-bound kernel.
 #ifdef FK_MARKS
+// thread 0 records into the first half of the buffer, lane 0 of warp FK_MARK_W2 into the second half (same SM clock: the two
+// timelines show where the critical warp 0 lags behind an ordinary consumer warp)
+#ifndef FK_MARK_W2
+#define FK_MARK_W2 5
+#endif
 LQT_DEVINL void fk_mark(FkCtx& c, int point) {
-    if (c.dbg && c.tid == 0 && c.dbg_n < c.dbg_cap)
+    if (c.dbg && c.lane == 0 && (c.warp == 0 || c.warp == FK_MARK_W2) && c.dbg_n < c.dbg_cap)
         c.dbg[c.dbg_n++] = ((unsigned long long)clock64() << 16) | (unsigned)(c.dbg_tag | point);
 }
 LQT_DEVINL void fk_phase(FkCtx& c, int stack, int kind) { c.dbg_tag = (stack << 9) | (kind << 4); }
@@ -302,6 +321,27 @@ LQT_DEVINL FkDesc make_desc(const FkParams& p, bool is_cp, int kind, int cta, in
     { const int npu = (s.nrows + 15) >> 4; d.lw = npu <= 1 ? 3 : npu <= 2 ? 2 : npu <= 4 ? 1 : 0; }   // the fewer pairs, the more warps split K
     d.rpp = (s.nrows + S.kv_heads - 1) / S.kv_heads;
     return d;
+}
+
+LQT_DEVINL FkUnit make_unit(const FkDesc& d, int warp) {
+    FkUnit u{};
+    const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1, npu = npair + (nt & 1);
+    const int wpp = 1 << d.lw, ks = warp & (wpp - 1), p = warp >> d.lw;
+    // npu <= FK_CWARPS >> lw: the host admits at most 64 rows per slice (80 for the O-projection) = 10 tiles = 5 units (fk_init)
+    if (p < npu && nkt > 0) {
+        const bool single = p == npair;
+        const uint32_t bsz = single ? 256u : 512u;
+        const uint32_t base = (uint32_t)p * (uint32_t)nkt * 512u, end = base + (uint32_t)nkt * bsz;
+        u.flags |= FKU_ACTIVE | (single ? FKU_SINGLE : 0);
+        u.off = base + (uint32_t)ks * bsz;
+        u.step = (uint16_t)(bsz * (uint32_t)wpp);
+        u.iters = (uint16_t)(nkt >> d.lw);
+        u.st0 = (uint8_t)(base / FK_STAGE_BYTES); u.st1 = (uint8_t)((end - 1u) / FK_STAGE_BYTES);
+        u.ks = (uint8_t)ks;
+        u.pidx = (uint16_t)(p * 16);
+        u.binc = (uint16_t)(96 * wpp);
+    }
+    return u;
 }
 
 // flat schedule of one token pass: [in_proj] + n_layers x (A qkv, B attention, C o-proj, D gate/up, E down) + [head]
@@ -517,46 +557,48 @@ LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, ui
     }
 }
 
-// Every warp takes ONE (tile pair, K slice) unit of the slice (a second one only if there are more than 8 pairs): the
-// per-unit overhead (stage waits, reduction, partial store) is paid once per warp and phase.
+// Every warp takes ONE (tile pair, K slice) unit of the slice (FkUnit, precomputed): the per-unit overhead (stage waits,
+// reduction, partial store) is paid once per warp and phase. gemv_wait runs early in the phase (while the input vector is still
+// in flight: the weights were requested long before), gemv_mma after the inputs are staged, gemv_release after the CTA barrier
+// that follows the product (one thread hands every stage of the slice back to the producer).
+LQT_DEVINL void gemv_wait(FkCtx& c, const FkUnit& u, int nstages) {
+    if (u.flags & FKU_ACTIVE)
+        for (unsigned st = u.st0; st <= u.st1; ++st) wait_full(c, c.stage_ctr + st, nstages);
+}
 template <int NST>
-LQT_DEVINL void gemv_mma(FkCtx& c, const FkDesc& d, const uint32_t xf_s) {
-    const int nkt = d.K >> 4, nt = d.nrows >> 3, npair = nt >> 1, npu = npair + (nt & 1);
-    const int nst = d.nst;
-    const uint32_t ring_s = smem_u32(FK_RING(c));
-    const int g = c.lane >> 2, tg = c.lane & 3;
-    const int wpp = 1 << d.lw, ks = c.warp & (wpp - 1);         // warps per tile pair (a power of two, make_desc)
-    // B fragments: lanes g < 3 hold the three planes; the others (zero columns of B) read a fixed pair of zero words
-    const uint32_t b0addr = (g < 3) ? xf_s + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)ks * 96u : smem_u32(&FK_SH(c)->zero8[0]);
-    const uint32_t binc = (g < 3) ? 96u * (uint32_t)wpp : 0u;
-    const uint32_t ring0 = (c.stage_ctr % (unsigned)NST) * FK_STAGE_BYTES;       // ring offset of byte 0 of this slice
-    float* part = &FK_SH(c)->part[ks][0];
-    const int iters = nkt >> d.lw;                  // blocks per warp and unit (even: K % 256 == 0, checked by the host)
-#pragma unroll 1
-    for (int p = c.warp >> d.lw; p < npu; p += FK_CWARPS >> d.lw) {
-        const bool single = p == npair;
-        const uint32_t bsz = single ? 256u : 512u;
-        const uint32_t base = (uint32_t)p * (uint32_t)nkt * 512u, end = base + (uint32_t)nkt * bsz;
-        for (int st = (int)(base / FK_STAGE_BYTES); st <= (int)((end - 1u) / FK_STAGE_BYTES); ++st) wait_full(c, c.stage_ctr + st, NST);
+LQT_DEVINL void gemv_mma(FkCtx& c, const FkUnit& u, const uint32_t xf_s) {
+    fk_mark(c, 9);
+    if (u.flags & FKU_ACTIVE) {
+        const uint32_t ring_s = smem_u32(FK_RING(c));
+        const int g = c.lane >> 2, tg = c.lane & 3;
+        // B fragments: lanes g < 3 hold the three planes; the others (zero columns of B) read a fixed pair of zero words
+        const uint32_t b0addr = (g < 3) ? xf_s + (uint32_t)((g * 4 + tg) * 8) + (uint32_t)u.ks * 96u : smem_u32(&FK_SH(c)->zero8[0]);
+        const uint32_t binc = (g < 3) ? (uint32_t)u.binc : 0u;
+        const uint32_t ring0 = (c.stage_ctr % (unsigned)NST) * FK_STAGE_BYTES;       // ring offset of byte 0 of this slice
+        const bool single = (u.flags & FKU_SINGLE) != 0;
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        const uint32_t lin = ring_wrap<NST>(ring0 + base + (uint32_t)ks * bsz + c.lane * (single ? 8u : 16u));
-        if (single) mma_blocks<NST, true>(acc, ring_s, lin, bsz * (uint32_t)wpp, b0addr, binc, iters);
-        else        mma_blocks<NST, false>(acc, ring_s, lin, bsz * (uint32_t)wpp, b0addr, binc, iters);
+        const uint32_t lin = ring_wrap<NST>(ring0 + u.off + c.lane * (single ? 8u : 16u));
+        if (single) mma_blocks<NST, true>(acc, ring_s, lin, (uint32_t)u.step, b0addr, binc, (int)u.iters);
+        else        mma_blocks<NST, false>(acc, ring_s, lin, (uint32_t)u.step, b0addr, binc, (int)u.iters);
+        fk_mark(c, 10);
         // lane (g, tg): acc[.][0..1] = row g, columns 2tg, 2tg + 1; acc[.][2..3] = row g + 8. Columns 0..2 carry the planes.
         float v0 = (acc[0][0] + acc[1][0]) + (acc[0][1] + acc[1][1]);
         float v1 = (acc[0][2] + acc[1][2]) + (acc[0][3] + acc[1][3]);
         v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
         v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
         if (tg == 0) {
-            part[p * 16 + g] = v0;
-            if (!single) part[p * 16 + 8 + g] = v1;
+            float* part = &FK_SH(c)->part[u.ks][u.pidx];
+            part[g] = v0;
+            if (!single) part[8 + g] = v1;
         }
     }
-    // this warp is done with every stage of the slice (those it never read included)
-    __syncwarp();
-    if (c.lane == 0)
-        for (int st = 0; st < nst; ++st) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + st) % (unsigned)NST]);
-    c.stage_ctr += nst;
+    fk_mark(c, 11);
+}
+// after the CTA barrier that follows gemv_mma: every warp is done with every stage of the slice (those it never read included)
+LQT_DEVINL void gemv_release(FkCtx& c, const FkDesc& d, int nstages) {
+    if (c.tid == 32)
+        for (int st = 0; st < d.nst; ++st) mbar_arrive(&FK_SH(c)->empty[(c.stage_ctr + st) % (unsigned)nstages]);
+    c.stage_ctr += d.nst;
 }
 // sum of the K-slice partials of row r (after the CTA barrier that follows gemv_mma)
 LQT_DEVINL float part_sum(FkCtx& c, int r, int wpp) {
@@ -620,16 +662,22 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     float* kn = FK_ATT(c) + FA_KN;
     float* vn = FK_ATT(c) + FA_VN;
     const bool owns_new = (j1 == n_pos);
+    float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;     // loaded before the new row is waited for
+    if (c.warp < 3) {
+        nw4 = __ldg(reinterpret_cast<const float4*>(c.warp == 2 ? L.knorm : L.qnorm) + c.lane);
+        c4 = __ldg(reinterpret_cast<const float4*>(cosr) + (c.lane & 15));
+        s4 = __ldg(reinterpret_cast<const float4*>(sinr) + (c.lane & 15));
+    }
     if (c.warp < 2) {
         float4 v = ll_poll4(c, S.qkv + (size_t)(g * 2 + c.warp) * ATT_D + c.lane * 4, want);
-        v = head_norm_rope(v, L.qnorm, p.eps, cosr, sinr, c.lane);
+        v = head_norm_rope_regs(v, true, nw4, p.eps, c4, s4, c.lane);
         reinterpret_cast<float4*>(q_s + c.warp * ATT_D)[c.lane] = v;
     } else if (owns_new && c.warp < 4) {
         const long long base = (long long)p.page_table[t >> p.page_shift] * p.page_stride + layer_off + head_off +
                                (long long)(t & (PS - 1)) * ATT_D;
         if (c.warp == 2) {
             float4 v = ll_poll4(c, S.qkv + q_dim + (size_t)g * ATT_D + c.lane * 4, want);
-            v = head_norm_rope(v, L.knorm, p.eps, cosr, sinr, c.lane);
+            v = head_norm_rope_regs(v, true, nw4, p.eps, c4, s4, c.lane);
             KvIO<KVT>::store4(pool + base + c.lane * 4, v);
             v.x = KvIO<KVT>::round(v.x); v.y = KvIO<KVT>::round(v.y); v.z = KvIO<KVT>::round(v.z); v.w = KvIO<KVT>::round(v.w);
             reinterpret_cast<float4*>(kn)[c.lane] = v;
@@ -706,8 +754,9 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
 }
 
 // talker: combine the splits of group g -> FK_XS(c)[0][0..rep*128)  (input of the grouped O-projection)
-LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
+LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want, const FkUnit& u, int nstages) {
     const FkParams& p = *c.p;
+    gemv_wait(c, u, nstages);
     const int n_kv = p.talker.kv_heads, g = c.cta % n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
     const int n_pos = t + 1, chunk = max(FK_ATT_MIN_CHUNK, (n_pos + ns - 1) / ns), active = (n_pos + chunk - 1) / chunk;
     const int r = c.tid >> 7, d = c.tid & 127;
@@ -746,7 +795,7 @@ LQT_DEVINL void talker_attn_combine(FkCtx& c, int t, unsigned want) {
 // code predictor: full attention of kv group g for the ONE new position p0 (< FK_CP_POS / 2), result -> FK_XS(c)[0..256).
 // Written for a small instruction footprint (it runs in every predictor layer): one polling / norm / rope path shared by
 // q, k and v, two-value butterfly reductions.
-LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, unsigned want) {
+LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, unsigned want, const FkUnit& u, int nstages) {
     const FkParams& p = *c.p;
     const FkStack& S = p.cp;
     const int n_kv = S.kv_heads, g = c.cta % n_kv;
@@ -769,12 +818,25 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, uns
     if (c.warp < 4) {                                // warps 0, 1: the two q heads of the group; 2: k; 3: v
         const int job = c.warp;
         const int off = (job < 2) ? (g * 2 + job) * ATT_D : (job == 2 ? q_dim : q_dim + kv_dim) + g * ATT_D;
-        float4 v = ll_poll4(c, S.qkv + off + c.lane * 4, want);
-        if (job < 3) v = head_norm_rope(v, job == 2 ? L.knorm : L.qnorm, p.eps, S.cos + (size_t)p0 * (ATT_D / 2), S.sin + (size_t)p0 * (ATT_D / 2), c.lane);
+        // everything that does not depend on the new row is loaded before the row is waited for: norm weights, cos / sin, ring stages
+        float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;
+        if (job < 3) {
+            nw4 = __ldg(reinterpret_cast<const float4*>(job == 2 ? L.knorm : L.qnorm) + c.lane);
+            c4 = __ldg(reinterpret_cast<const float4*>(S.cos + (size_t)p0 * (ATT_D / 2)) + (c.lane & 15));
+            s4 = __ldg(reinterpret_cast<const float4*>(S.sin + (size_t)p0 * (ATT_D / 2)) + (c.lane & 15));
+        }
+        const uint2* src = S.qkv + off + c.lane * 4;
+        const FkRaw4 raw = ll_issue4(src);
+        gemv_wait(c, u, nstages);
+        float4 v = ll_finish4(c, raw, src, want);
+        if (job < 3) v = head_norm_rope_regs(v, true, nw4, p.eps, c4, s4, c.lane);
         float* dst = (job < 2) ? q_s + job * ATT_D : (job == 2 ? kn : vn);
         reinterpret_cast<float4*>(dst)[c.lane] = v;
         if (job >= 2) reinterpret_cast<float4*>((job == 2 ? kc : vc) + (size_t)p0 * ATT_D)[c.lane] = v;   // read back only by this CTA, after CTA barriers
+    } else {
+        gemv_wait(c, u, nstages);
     }
+    fk_mark(c, 13);
     csync();
     const float scale = 1.0f / sqrtf((float)ATT_D);
     // scores: key j against both heads (warp handles j = warp, warp + 8)
@@ -800,6 +862,7 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, uns
         }
     }
     csync();
+    fk_mark(c, 14);
     if (c.warp < 2) {                                // softmax of head `warp` over j <= p0
         float* row = sc + c.warp * FK_CP_POS;
         const float v = (c.lane <= p0) ? row[c.lane] : -INFINITY;
@@ -808,7 +871,9 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, uns
         const float sum = warp_sum(e);
         if (c.lane <= p0) row[c.lane] = e / sum;
     }
+    fk_mark(c, 5);
     csync();
+    fk_mark(c, 15);
     {
         const float* row = sc + r_t * FK_CP_POS;
         float o = 0.f;
@@ -839,7 +904,7 @@ LQT_DEVINL void f4_to(float (&d)[4], const float4& v) { d[0] = v.x; d[1] = v.y; 
 // Readers validate the (value, sequence) words they use; a word whose store had not landed in L2 when the
 // copy read it is re-polled from global memory and patched in place.
 // ------------------------------------------------------------------------------------------------
-LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W) {
+LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W, const FkUnit* u = nullptr, int nstages = 1) {
     const unsigned b = c.land_n & 1u, par = (c.land_n >> 1) & 1u;
     uint2* dst = FK_LAND(c) + b * FK_LAND_WORDS;
     uint64_t* bar = &FK_SH(c)->land_bar[b];
@@ -848,6 +913,7 @@ LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W) {
     csync();
     ++c.land_n;
     (void)par; (void)bar;
+    if (u) gemv_wait(c, *u, nstages);
     return dst;
 #endif
     if (c.tid == 0) {
@@ -856,9 +922,11 @@ LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W) {
         const int share = W / FK_CLUSTER;                                // W % 16 == 0: 16-byte multiples
         bulk_g2s_mc(dst + c.rank * share, src + c.rank * share, (uint32_t)share * 8u, bar, (uint16_t)((1u << FK_CLUSTER) - 1u));
     }
+    if (u) gemv_wait(c, *u, nstages);                 // this warp's ring stages, while the vector is in flight
     if (!mbar_try_wait(bar, par)) {
         if (!wait_full_slow(bar, par, c.p->ctrl)) c.aborted = true;
     }
+    fk_mark(c, 7);
     ++c.land_n;
     return dst;
 }
@@ -936,13 +1004,21 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         fk_mark(c, 0);
         const FkLayer& L = is_cp ? p.c_layers[l] : p.t_layers[l];
         const FkDesc d = FK_SH(c)->desc[tk][kind];
+        const FkUnit u = FK_SH(c)->unit[tk][kind][c.warp];
         // RMSNorm weight of this phase: fetched BEFORE the grid hand-over (independent of the activations)
         const float* nw = (kind == FKT_A) ? L.ln1 : (kind == FKT_D) ? L.ln2 : (kind == FKT_HEAD) ? S.final_norm : nullptr;
         float4 nwv[HJ];
 #pragma unroll
         for (int j = 0; j < HJ; ++j)
             nwv[j] = (nw && j * 1024 + tid4 < H) ? __ldg(reinterpret_cast<const float4*>(nw + j * 1024 + tid4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        grid_wait(c, want);
+        // (Measured and rejected, -DFK_DATAFLOW_QKV: the predictor's phase C and the talker's phase B need only the q/k/v words of
+        // their own kv group, each validated by its sequence tag, so they could skip the grid-wide wait. 2.375 instead of 2.275 ms
+        // per frame: 4 warps x 120 CTAs re-polling the words delays the very stores they wait for.)
+#ifdef FK_DATAFLOW_QKV
+        if (!(kind == FKT_B || (kind == FKT_C && is_cp)))
+#endif
+            grid_wait(c, want);
+        fk_mark(c, 1);
         // the layer input row: res0 (smem) for layer 0 without in_proj, else an LL buffer
         const bool in_res0 = (l == 0 && !inproj);
         const uint2* lin = (l == 0) ? p.cxin : S.x;           // (only read when !in_res0)
@@ -956,14 +1032,15 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             continue;
         }
         if (kind == FKT_C) {
-            if (is_cp) cp_attn_local(c, L, l, ps.pos0, want);
-            else       talker_attn_combine(c, ps.pos0, want);
+            if (is_cp) cp_attn_local(c, L, l, ps.pos0, want, u, NST);
+            else       talker_attn_combine(c, ps.pos0, want, u, NST);
             fk_mark(c, 3);
             if (FK_SH(c)->aborted) { c.aborted = true; break; }
             const int rpp = d.rpp;
-            gemv_mma<NST>(c, d, smem_u32(FK_XS(c)));
-            fk_mark(c, 5);
+            gemv_mma<NST>(c, u, smem_u32(FK_XS(c)));
             csync();                                           // every warp's partial sums are in shared memory
+            fk_mark(c, 12);
+            gemv_release(c, d, NST);
             // The n_kv CTAs that hold the partials of the same rows (one per kv group) sit in the same cluster: the partial of
             // row r goes straight into the shared memory of partner r / rpp as a (value, sequence) word (DSMEM store, no barrier)
             if (c.tid < d.nrows) {
@@ -971,6 +1048,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                 const int tgt = c.tid / rpp;
                 st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid, 1 << d.lw), c.seq);
             }
+            fk_mark(c, 4);
             reduce_partials(c, d, n_kv, rpp, in_res0 ? FK_RES0(c) : nullptr, FK_LAND(c) + c.land_a * FK_LAND_WORDS, S.x1);
             fk_mark(c, 6);
             if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; break; }
@@ -983,6 +1061,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         const uint32_t xf_s = smem_u32(FK_XP(c));
         switch (kind) {
             case FKT_INPROJ: {                                     // plain row in shared memory, no norm
+                gemv_wait(c, u, NST);
 #pragma unroll
                 for (int j = 0; j < HJ; ++j)
                     if (j * 1024 + tid4 < d.K) {
@@ -993,18 +1072,19 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             }
             case FKT_A: {
                 if (in_res0) {
+                    gemv_wait(c, u, NST);
 #pragma unroll
                     for (int j = 0; j < HJ; ++j)
                         if (j * 1024 + tid4 < H) f4_to(xin[j], *reinterpret_cast<const float4*>(FK_RES0(c) + j * 1024 + tid4));
                 } else {
-                    uint2* land = mc_fetch(c, lin, H);
+                    uint2* land = mc_fetch(c, lin, H, &u, NST);
                     land_row<HJ>(c, land, lin, H, want, xin);
                     c.land_a = (c.land_n - 1u) & 1u;
                 }
                 break;
             }
             case FKT_D: {
-                uint2* land = mc_fetch(c, S.x1, H);
+                uint2* land = mc_fetch(c, S.x1, H, &u, NST);
                 land_row<HJ>(c, land, S.x1, H, want, xin);
                 const FkDesc& de = FK_SH(c)->desc[tk][FKT_E];
 #pragma unroll
@@ -1021,7 +1101,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                 for (int w0 = 0; w0 < d.K; w0 += FK_LAND_WORDS) {          // wide models: two landing-buffer loads
                     const int wn = min(FK_LAND_WORDS, d.K - w0);
                     float t3[3][4];
-                    uint2* land = mc_fetch(c, S.act + w0, wn);
+                    uint2* land = mc_fetch(c, S.act + w0, wn, w0 == 0 ? &u : nullptr, NST);
                     land_row<3>(c, land, S.act + w0, wn, want, t3);
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
@@ -1030,7 +1110,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                 break;
             }
             default: {  // FKT_HEAD: final norm + head
-                uint2* land = mc_fetch(c, S.x, H);
+                uint2* land = mc_fetch(c, S.x, H, &u, NST);
                 land_row<HJ>(c, land, S.x, H, want, xin);
                 break;
             }
@@ -1051,12 +1131,14 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         }
         if (c.aborted || FK_SH(c)->aborted) { c.aborted = true; }
         csync();                                               // the input fragments (and the sum-of-squares partials) are complete
+        fk_mark(c, 8);
         if (FK_SH(c)->aborted) { c.aborted = true; break; }
         // ---- product (all warps, K split), then the epilogue on warp 0: one lane per row (pair) ----------------------
         {
-            gemv_mma<NST>(c, d, xf_s);
-            fk_mark(c, 5);
+            gemv_mma<NST>(c, u, xf_s);
             csync();                                           // every warp's partial sums are in shared memory
+            fk_mark(c, 12);
+            gemv_release(c, d, NST);
             const bool lh = (kind == FKT_HEAD && !is_cp);
             float rs = 1.f;
             if (nw && (c.warp == 0 || lh)) rs = ss_rstd(c, H, p.eps);
@@ -1483,12 +1565,16 @@ frame_kernel(const __grid_constant__ FkParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], FK_CWARPS); }   // every consumer warp releases a stage
+        for (int i = 0; i < NST; ++i) { mbar_init(&sh->full[i], 1); mbar_init(&sh->empty[i], 1); }   // one consumer thread releases a stage (gemv_release)
         mbar_init(&sh->land_bar[0], 1); mbar_init(&sh->land_bar[1], 1);
         sh->stop = 0; sh->consumed = 0; sh->aborted = 0; sh->zero8[0] = 0u; sh->zero8[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 20) sh->desc[tid / 10][tid % 10] = make_desc(p, tid >= 10, tid % 10, cta, ncta);
+    if (tid < 160) {
+        const FkDesc dd = make_desc(p, tid >= 80, (tid % 80) >> 3, cta, ncta);
+        if ((tid & 7) == 0) sh->desc[tid / 80][(tid % 80) >> 3] = dd;
+        sh->unit[tid / 80][(tid % 80) >> 3][tid & 7] = make_unit(dd, tid & 7);
+    }
     for (int i = tid; i < FK_NGRP_MAX * FK_RPP_MAX; i += FK_THREADS) (&sh->redc[0][0])[i] = make_uint2(0u, 0u);
     __syncthreads();
     cluster_sync_all();                            // every landing barrier of the cluster is initialised before any multicast can arrive
@@ -1589,7 +1675,10 @@ frame_kernel(const __grid_constant__ FkParams p) {
     c.rank = (unsigned)cta % FK_CLUSTER;
     c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta;
     c.seq = 0; c.stage_ctr = 0; c.aborted = false;
-    c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap - 1; c.dbg_tag = 0;
+    c.dbg = (p.dbg && cta == p.dbg_cta) ? p.dbg + 1 : nullptr; c.dbg_n = 0; c.dbg_cap = p.dbg_cap / 2 - 1; c.dbg_tag = 0;
+#ifdef FK_MARKS
+    if (c.dbg && warp == FK_MARK_W2) c.dbg += p.dbg_cap / 2;
+#endif
     const int H = p.talker.H, H4 = H >> 2;
     int pos = st0.pos, frame = st0.frame, done = st0.done, n_frames = st0.n_frames;
     const SamplingDev sp = *p.sp;
@@ -1695,6 +1784,9 @@ frame_kernel(const __grid_constant__ FkParams p) {
     if (p.mode == 0 && !done && frame >= st0.max_frames) done = 1;
     // ---- exit: publish state, stop the producer -------------------------------------------------------
     csync();
+#ifdef FK_MARKS
+    if (c.dbg && warp == FK_MARK_W2 && lane == 0) c.dbg[-1] = (unsigned long long)c.dbg_n;
+#endif
     if (tid == 0) {
         if (cta == 0) {
             p.st->pos = pos; p.st->frame = frame; p.st->done = done; p.st->n_frames = n_frames;

@@ -323,10 +323,11 @@ class Engine:
             raise EngineError(self.lib.lqt_last_error(self.h).decode())
         self._tl_cap = entries
 
-    def timeline_read(self):
-        """-> (clock uint64 [n], tag int [n]) of the last frame-kernel launch"""
+    def timeline_read(self, half: int = 0):
+        """-> (clock uint64 [n], tag int [n]) of the last frame-kernel launch; half 1 = the second recorder of a profiling build
+        (another consumer warp, or the producer in FK_FINE_MARKS builds)"""
         out = np.zeros(self._tl_cap, np.uint64)
-        n = self.lib.lqt_debug_timeline(self.h, 0, 0, _ptr(out), self._tl_cap)
+        n = self.lib.lqt_debug_timeline(self.h, 0, 1 if half else 0, _ptr(out), self._tl_cap)
         out = out[: max(n, 0)]
         return (out >> np.uint64(16)), (out & np.uint64(0xFFFF)).astype(np.int64)
 

@@ -40,7 +40,9 @@ def main():
     clk, tag = eng.timeline_read()
     print(f"entries {len(clk)}  total {(int(clk[-1]) - int(clk[0])) / a.mhz / 1e3:.2f} ms for prefill + {a.frames} frames "
           f"(generate_ms {eng.stats().last_generate_ms:.2f})")
-    POINTS = {0: "begin", 1: "grid go", 2: "fetched", 3: "inputs staged", 4: "glue", 5: "fma done", 6: "published", 8: "after csync", 9: "x loaded", 10: "batch done", 11: "stages released"}
+    POINTS = {0: "begin", 1: "grid go", 2: "fetched", 3: "inputs staged", 4: "glue/dsmem push", 5: "softmax done", 6: "published", 7: "landed",
+              8: "staged+csync", 9: "stages ready", 10: "mma done", 11: "stages released", 12: "partials csync", 13: "qkv normed", 14: "scores csync",
+              15: "softmax csync"}
     seg = collections.defaultdict(list)
     for i in range(1, len(clk)):
         st, kind, pt = (tag[i] >> 9) & 1, (tag[i] >> 4) & 31, tag[i] & 15
@@ -52,6 +54,23 @@ def main():
         v = np.asarray(seg[k], np.float64)
         print(f"{'cp' if k[0] else 'talker':6s} {KINDS.get(k[1], str(k[1])):10s} {POINTS.get(k[2], str(k[2])):15s} {len(v):7d} {v.mean():9.0f} "
               f"{v.mean() / a.mhz:8.2f} {v.sum() / tot:6.3f}")
+    # the second recorder (lane 0 of another consumer warp): its lag behind thread 0 at the marks both pass, matched by occurrence
+    clk2, tag2 = eng.timeline_read(1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "fk_timeline_raw.npz"), clk=clk, tag=tag, clk2=clk2, tag2=tag2)
+    if len(clk2):
+        occ = collections.defaultdict(list)
+        for i in range(len(clk)):
+            occ[int(tag[i])].append(int(clk[i]))
+        occ2 = collections.defaultdict(list)
+        for i in range(len(clk2)):
+            occ2[int(tag2[i])].append(int(clk2[i]))
+        print(f"second warp: {len(clk2)} entries; mean (t_warp2 - t_warp0) in cycles at common marks")
+        for t in sorted(occ2):
+            if t in occ and len(occ[t]) == len(occ2[t]):
+                dlt = np.asarray(occ2[t], np.float64) - np.asarray(occ[t], np.float64)
+                st, kind, pt = (t >> 9) & 1, (t >> 4) & 31, t & 15
+                print(f"  {'cp' if st else 'talker':6s} {KINDS.get(kind, str(kind)):10s} {POINTS.get(pt, str(pt)):15s} n={len(dlt):5d} mean {dlt.mean():8.0f}  p10 {np.percentile(dlt, 10):8.0f}  p90 {np.percentile(dlt, 90):8.0f}")
     byp = collections.defaultdict(float)
     for k, v in seg.items():
         byp[POINTS.get(k[2], str(k[2]))] += sum(v)
