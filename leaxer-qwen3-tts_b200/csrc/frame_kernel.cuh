@@ -537,6 +537,8 @@ LQT_DEVINL uint32_t ring_wrap(uint32_t x) {
 // lin: ring offset of this lane's fragment of the first block, step: bytes between consecutive blocks of this warp;
 // baddr / binc: this lane's B fragment and its stride (lanes that hold the zero columns of B read one fixed zero word
 // pair, stride 0): no predicates, no bounds checks.
+// (Measured and rejected: a software-pipelined form that requests the fragments of the next two blocks before the MMAs of the current
+// two -- 12 more live registers, a few spills elsewhere in the kernel, 2.17 instead of 2.10 ms per frame.)
 template <int NST, bool SINGLE>
 LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, uint32_t step, uint32_t baddr, uint32_t binc, int iters) {
 #pragma unroll 1
@@ -561,9 +563,12 @@ LQT_DEVINL void mma_blocks(float (&acc)[2][4], uint32_t ring_s, uint32_t lin, ui
 // reduction, partial store) is paid once per warp and phase. gemv_wait runs early in the phase (while the input vector is still
 // in flight: the weights were requested long before), gemv_mma after the inputs are staged, gemv_release after the CTA barrier
 // that follows the product (one thread hands every stage of the slice back to the producer).
+// (Kept inline with a rolled loop: the out-of-line variant had a better instruction-cache hit rate, 87.8 % vs 83.9 %, and was 1.3 % slower.)
 LQT_DEVINL void gemv_wait(FkCtx& c, const FkUnit& u, int nstages) {
-    if (u.flags & FKU_ACTIVE)
+    if (u.flags & FKU_ACTIVE) {
+#pragma unroll 1
         for (unsigned st = u.st0; st <= u.st1; ++st) wait_full(c, c.stage_ctr + st, nstages);
+    }
 }
 template <int NST>
 LQT_DEVINL void gemv_mma(FkCtx& c, const FkUnit& u, const uint32_t xf_s) {
