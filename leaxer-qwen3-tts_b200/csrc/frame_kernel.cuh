@@ -232,6 +232,7 @@ struct FkShared {
     uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
     FkDesc desc[2][10];           // [stack][phase kind]
     FkUnit unit[2][10][FK_CWARPS];   // [stack][phase kind][consumer warp]
+    uint16_t pushmap[2][FK_PART_ROWS];   // O-projection row r of this CTA's slice -> (cluster partner that reduces it << 8) | its slot there
 };
 
 struct FkCtx {
@@ -428,10 +429,15 @@ LQT_DEVINL void grid_arrive(FkCtx& c) {          // one lane, after the CTA's st
 }
 __device__ __noinline__ void grid_wait_slow(const unsigned* ctr, unsigned target, volatile int* aborted, unsigned* ctrl) {
     int spins = 0; unsigned long long t0 = 0;
+    // (Measured and rejected: four polls in flight a quarter of a round trip apart -- 2.15-2.19 instead of 2.10 ms per frame: more
+    // polling delays the arrivals it waits for.)
     unsigned v;
     do {
         if ((++spins & 1023) == 0 && ll_giveup_slow(aborted, ctrl, &t0)) break;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+#ifdef FK_POLL_BACKOFF
+        if ((int)(target - v) > FK_POLL_BACKOFF) __nanosleep(120);      // many CTAs still missing: do not crowd the counter's L2 slice
+#endif
     } while ((int)(v - target) < 0);
 }
 // all consumer threads; returns when every CTA has issued the outputs of phase `n`
@@ -972,6 +978,8 @@ LQT_DEVINL void reduce_partials(FkCtx& c, const FkDesc& d, int n_kv, int rpp, co
     if (c.lane < nmine) {
         const int row = d.row0 + r0 + c.lane;
         float acc = res_plain ? res_plain[row] : __uint_as_float(res_land[row].x);
+        // (sequential on purpose: requesting all eight words before the first is examined samples them all at the earliest moment, and
+        // every word that had not landed yet then takes the slow path -- measured slower for the CTAs that get here first)
 #pragma unroll 1
         for (int gg = 0; gg < n_kv; ++gg) {
 #ifdef FK_NO_DSMEM
@@ -996,9 +1004,9 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
     const int tk = is_cp ? 1 : 0;
     const int H = S.H, n_kv = S.kv_heads;
     const bool inproj = is_cp && p.c_inproj_w != nullptr;
-    const int total = pass_ops(S.n_layers, inproj, ps.head);
     const int tid4 = c.tid * 4;
 
+    const int total = pass_ops(S.n_layers, inproj, ps.head);
     for (int it = 0; it < total && !c.aborted; ++it) {
         const FkOp op = pass_op(it, S.n_layers, inproj);
         const int kind = op.kind, l = op.layer;
@@ -1050,8 +1058,8 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             // row r goes straight into the shared memory of partner r / rpp as a (value, sequence) word (DSMEM store, no barrier)
             if (c.tid < d.nrows) {
                 const unsigned g = c.rank % (unsigned)n_kv, base = c.rank - g;
-                const int tgt = c.tid / rpp;
-                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][c.tid - tgt * rpp], base + (unsigned)tgt), part_sum(c, c.tid, 1 << d.lw), c.seq);
+                const unsigned pm = FK_SH(c)->pushmap[tk][c.tid];          // (partner << 8) | row slot at the partner: tid / rpp, tid % rpp
+                st_ll_dsmem(dsmem_addr(&FK_SH(c)->redc[g][pm & 255u], base + (pm >> 8)), part_sum(c, c.tid, 1 << d.lw), c.seq);
             }
             fk_mark(c, 4);
             reduce_partials(c, d, n_kv, rpp, in_res0 ? FK_RES0(c) : nullptr, FK_LAND(c) + c.land_a * FK_LAND_WORDS, S.x1);
@@ -1148,6 +1156,8 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
             float rs = 1.f;
             if (nw && (c.warp == 0 || lh)) rs = ss_rstd(c, H, p.eps);
             if (c.warp == 0) {
+                // (Measured and rejected: one straight-line epilogue for all kinds with two rows per lane and every load up front --
+                // phase D 0.10 us faster, A and E 0.05-0.11 us slower, 1 % slower overall.)
                 const int wpp = 1 << d.lw;
                 if (kind == FKT_D) {                           // rows 2q (gate), 2q + 1 (up) -> act[q]
                     const int q = c.lane;
@@ -1581,6 +1591,11 @@ frame_kernel(const __grid_constant__ FkParams p) {
         sh->unit[tid / 80][(tid % 80) >> 3][tid & 7] = make_unit(dd, tid & 7);
     }
     for (int i = tid; i < FK_NGRP_MAX * FK_RPP_MAX; i += FK_THREADS) (&sh->redc[0][0])[i] = make_uint2(0u, 0u);
+    __syncthreads();
+    if (tid < 2 * FK_PART_ROWS) {
+        const int st = tid / FK_PART_ROWS, r = tid % FK_PART_ROWS, rpp = max(1, sh->desc[st][FKT_C].rpp);
+        sh->pushmap[st][r] = (uint16_t)(((r / rpp) << 8) | (r % rpp));
+    }
     __syncthreads();
     cluster_sync_all();                            // every landing barrier of the cluster is initialised before any multicast can arrive
 
