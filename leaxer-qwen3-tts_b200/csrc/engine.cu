@@ -1039,6 +1039,7 @@ int fk_init(lqt_engine* h) {
                                    fk_rmax(std::max(s.vocab, s.cp_vocab), 1, 0, s.kv_heads, nc));
         const int worst_c = std::max(fk_rmax(2 * s.cp_inter, 2, 1, s.cp_kv_heads, nc), fk_rmax((s.cp_heads + 2 * s.cp_kv_heads) * ATT_D, 1, 0, s.cp_kv_heads, nc));
         if (worst > 64 || worst_c > 64) { h->err = "frame kernel: too many rows per SM"; return 1; }
+        if (h->max_pages > FK_PT_MAX) { h->err = "frame kernel: max_pos exceeds the page-table copy in shared memory"; return 1; }
         {   // a slice must fit the ring: at most NST stages in flight per phase
             auto nst_of = [&](int rows, int K) { return (int)(((size_t)rows * K * 2 + FK_STAGE_BYTES - 1) / FK_STAGE_BYTES); };
             const int a = nst_of(fk_rmax((s.heads + 2 * s.kv_heads) * ATT_D, 1, 0, s.kv_heads, nc), s.hidden), dd = nst_of(fk_rmax(2 * s.inter, 2, 1, s.kv_heads, nc), s.hidden);
@@ -1119,7 +1120,7 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     p.c_heads = h->fk_c_heads; p.cp_vocab = s.cp_vocab; p.cp_steps = s.cp_steps; p.c_head_stride = h->fk_c_head_stride;
     p.c_inproj_w = h->fk_c_inproj; p.c_inproj_b = h->c_inproj_b; p.cxin = h->fk_cxin;
     p.eps = s.rms_eps;
-    p.kv_pool = h->kv_pool; p.page_table = h->page_tables + (size_t)slot * h->max_pages; p.page_shift = KV_PAGE_SHIFT;
+    p.kv_pool = h->kv_pool; p.page_table = h->page_tables + (size_t)slot * h->max_pages; p.n_pages = h->max_pages; p.page_shift = KV_PAGE_SHIFT;
     p.page_stride = (long long)s.layers * 2 * s.kv_heads * KV_PAGE * ATT_D; p.kv_f32 = h->kv_f32 ? 1 : 0;
     p.pa = h->fk_pa; p.cp_kv = h->fk_cp_kv;
     p.logits_ll = h->fk_logits_ll; p.clogits_ll = h->fk_clogits_ll;

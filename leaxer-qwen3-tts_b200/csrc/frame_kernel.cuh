@@ -56,6 +56,7 @@ constexpr int FK_ATT_MIN_CHUNK = 32;              // positions per split at leas
 constexpr int FK_NGRP_MAX = 8;                    // kv groups
 constexpr int FK_PART_ROWS = 80;                  // max rows of a slice (64 for the flat phases, 72 for the O-projection of 15 clusters)
 constexpr int FK_TILE_ROWS = 8;                   // rows per weight tile of the tensor-core matrix-vector phases
+constexpr int FK_PT_MAX = 128;                    // KV pages per slot at most (8192 positions)
 constexpr int FK_CP_POS = 32;                     // code-predictor KV capacity (positions)
 constexpr int FK_RED_STRIDE = 96;                 // warp-partial row sums: [warp][FK_RED_STRIDE]; M = 2 -> second row at +48
 constexpr int FK_XS_STRIDE = 512;                 // attention output rows (input of the grouped O-projection)
@@ -92,7 +93,7 @@ struct FkParams {
     const bf16_t* c_heads; int cp_vocab, cp_steps; long long c_head_stride;   // image elements per predictor head
     const bf16_t* c_inproj_w; const float* c_inproj_b; uint2* cxin;     // 1.7B: talker width -> predictor width (LL [2][Hc])
     float eps;
-    void* kv_pool; const int* page_table; int page_shift; long long page_stride; int kv_f32;
+    void* kv_pool; const int* page_table; int n_pages; int page_shift; long long page_stride; int kv_f32;   // n_pages <= FK_PT_MAX
     uint2* pa;                 // talker attention partials, LL [n_kv][FK_NS_MAX][2][ATT_PSTRIDE]
     float* cp_kv;              // PER-CTA copies [cta][layer][k|v][FK_CP_POS][128] fp32 of the predictor KV of the CTA's own kv group: every CTA
                                // computes the new k/v row of its group anyway, so it keeps them itself -- no writer fence, no shared lines
@@ -232,6 +233,7 @@ struct FkShared {
     uint2 redc[FK_NGRP_MAX][FK_RPP_MAX];  // O-projection partials of the partner CTAs (DSMEM, (value, sequence) words)         // post-attention residual stream at the rows of this CTA's down-projection slice
     FkDesc desc[2][10];           // [stack][phase kind]
     FkUnit unit[2][10][FK_CWARPS];   // [stack][phase kind][consumer warp]
+    int pt[FK_PT_MAX];                // the slot's page table (static during a launch)
     uint16_t pushmap[2][FK_PART_ROWS];   // O-projection row r of this CTA's slice -> (cluster partner that reduces it << 8) | its slot there
 };
 
@@ -653,38 +655,63 @@ template <> LQT_DEVINL float4 kv_load4_cg<bf16_t>(const bf16_t* p) {
 }
 template <> LQT_DEVINL float4 kv_load4_cg<float>(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// talker: split-KV partial attention of kv group g over this CTA's chunk of positions -> pa (LL)
+// talker: split-KV partial attention of kv group g over this CTA's chunk of positions -> pa (LL).
+// Everything that does not depend on the new row is requested BEFORE the grid hand-over (the function waits for the grid itself): the
+// norm weights, cos / sin, and the first round of cached K/V rows (4 positions per warp = the whole chunk up to 32 positions per CTA),
+// located through the copy of the slot's page table in shared memory. Returns true in the threads that stored the new K/V row: they
+// owe a __threadfence() before the CTA's NEXT arrival (the caller issues it after this phase's arrival, off the critical path; the row
+// is read one frame later at the earliest).
 template <typename KVT>
-LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t, unsigned want) {
+LQT_DEVINL void talker_kv_round(FkCtx& c, const KVT* pool, long long goff, long long v_off, int jb, int j1, int t, float4 (&kk)[4], float4 (&vv)[4]) {
+    const FkParams& p = *c.p;
+    const int PS = 1 << p.page_shift;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = jb + u * FK_CWARPS;
+        if (j < j1 && j != t) {
+            const KVT* kp = pool + (long long)FK_SH(c)->pt[j >> p.page_shift] * p.page_stride + goff + (long long)(j & (PS - 1)) * ATT_D + c.lane * 4;
+            kk[u] = kv_load4_cg<KVT>(kp);
+            vv[u] = kv_load4_cg<KVT>(kp + v_off);
+        }
+    }
+}
+template <typename KVT>
+LQT_DEVINL bool talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t, unsigned want) {
     const FkParams& p = *c.p;
     const FkStack& S = p.talker;
     const int n_kv = S.kv_heads, g = c.cta % n_kv, s = c.cta / n_kv, ns = min(grp_members(g, n_kv, c.ncta), FK_NS_MAX);
     const int n_pos = t + 1, chunk = max(FK_ATT_MIN_CHUNK, (n_pos + ns - 1) / ns);
     const int j0 = s * chunk, j1 = min(n_pos, j0 + chunk);
-    if (s >= ns || j0 >= j1) return;                           // idle split (short contexts / spare CTAs)
+    const bool active = !(s >= ns || j0 >= j1);                // else: idle split (short contexts / spare CTAs)
     const int PS = 1 << p.page_shift;
     const int q_dim = S.heads * ATT_D, kv_dim = n_kv * ATT_D;
-    const float* cosr = S.cos + (size_t)t * (ATT_D / 2);
-    const float* sinr = S.sin + (size_t)t * (ATT_D / 2);
     KVT* pool = reinterpret_cast<KVT*>(p.kv_pool);
     const long long layer_off = (long long)layer * 2 * n_kv * PS * ATT_D;
     const long long head_off = (long long)g * PS * ATT_D, v_off = (long long)n_kv * PS * ATT_D;
+    float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;
+    float4 kk[4], vv[4];
+    if (active) {
+        if (c.warp < 3) {
+            nw4 = __ldg(reinterpret_cast<const float4*>(c.warp == 2 ? L.knorm : L.qnorm) + c.lane);
+            c4 = __ldg(reinterpret_cast<const float4*>(S.cos + (size_t)t * (ATT_D / 2)) + (c.lane & 15));
+            s4 = __ldg(reinterpret_cast<const float4*>(S.sin + (size_t)t * (ATT_D / 2)) + (c.lane & 15));
+        }
+        talker_kv_round<KVT>(c, pool, layer_off + head_off, v_off, j0 + c.warp, j1, t, kk, vv);
+    }
+    grid_wait(c, want);
+    fk_mark(c, 1);
+    if (!active) return false;
     float* q_s = FK_ATT(c) + FA_Q;
     float* kn = FK_ATT(c) + FA_KN;
     float* vn = FK_ATT(c) + FA_VN;
     const bool owns_new = (j1 == n_pos);
-    float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;     // loaded before the new row is waited for
-    if (c.warp < 3) {
-        nw4 = __ldg(reinterpret_cast<const float4*>(c.warp == 2 ? L.knorm : L.qnorm) + c.lane);
-        c4 = __ldg(reinterpret_cast<const float4*>(cosr) + (c.lane & 15));
-        s4 = __ldg(reinterpret_cast<const float4*>(sinr) + (c.lane & 15));
-    }
+    bool fence = false;
     if (c.warp < 2) {
         float4 v = ll_poll4(c, S.qkv + (size_t)(g * 2 + c.warp) * ATT_D + c.lane * 4, want);
         v = head_norm_rope_regs(v, true, nw4, p.eps, c4, s4, c.lane);
         reinterpret_cast<float4*>(q_s + c.warp * ATT_D)[c.lane] = v;
     } else if (owns_new && c.warp < 4) {
-        const long long base = (long long)p.page_table[t >> p.page_shift] * p.page_stride + layer_off + head_off +
+        const long long base = (long long)FK_SH(c)->pt[t >> p.page_shift] * p.page_stride + layer_off + head_off +
                                (long long)(t & (PS - 1)) * ATT_D;
         if (c.warp == 2) {
             float4 v = ll_poll4(c, S.qkv + q_dim + (size_t)g * ATT_D + c.lane * 4, want);
@@ -698,7 +725,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
             v.x = KvIO<KVT>::round(v.x); v.y = KvIO<KVT>::round(v.y); v.z = KvIO<KVT>::round(v.z); v.w = KvIO<KVT>::round(v.w);
             reinterpret_cast<float4*>(vn)[c.lane] = v;
         }
-        __threadfence();        // the cache line must be visible before any later word of this CTA says "done"
+        fence = true;
     }
     csync();
     const float4 q0 = reinterpret_cast<const float4*>(q_s)[c.lane];
@@ -706,8 +733,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     const float scale = 1.0f / sqrtf((float)ATT_D);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    for (int jb = j0 + c.warp; jb < j1; jb += FK_CWARPS * 4) {
-        float4 kk[4], vv[4];
+    for (int jb = j0 + c.warp;;) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = jb + u * FK_CWARPS;
@@ -715,18 +741,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
                 if (j == t) {
                     kk[u] = reinterpret_cast<const float4*>(kn)[c.lane];
                     vv[u] = reinterpret_cast<const float4*>(vn)[c.lane];
-                } else {
-                    const KVT* kp = pool + (long long)p.page_table[j >> p.page_shift] * p.page_stride + layer_off + head_off +
-                                    (long long)(j & (PS - 1)) * ATT_D + c.lane * 4;
-                    kk[u] = kv_load4_cg<KVT>(kp);
-                    vv[u] = kv_load4_cg<KVT>(kp + v_off);
                 }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = jb + u * FK_CWARPS;
-            if (j < j1) {
                 float d0 = kk[u].x * q0.x + kk[u].y * q0.y + kk[u].z * q0.z + kk[u].w * q0.w;
                 float d1 = kk[u].x * q1.x + kk[u].y * q1.y + kk[u].z * q1.z + kk[u].w * q1.w;
                 d0 = warp_sum(d0) * scale; d1 = warp_sum(d1) * scale;
@@ -738,6 +753,9 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
                 m0 = n0; m1 = n1;
             }
         }
+        jb += FK_CWARPS * 4;
+        if (jb >= j1) break;
+        talker_kv_round<KVT>(c, pool, layer_off + head_off, v_off, jb, j1, t, kk, vv);
     }
     float* wm = FK_ATT(c) + FA_WM; float* wl = FK_ATT(c) + FA_WL; float* wo = FK_ATT(c) + FA_WO;
     reinterpret_cast<float4*>(wo + (c.warp * 2 + 0) * ATT_D)[c.lane] = a0;
@@ -762,6 +780,7 @@ LQT_DEVINL void talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
         if (d == 0) { st_ll(part + ATT_D, Mx, c.seq); st_ll(part + ATT_D + 1, den, c.seq); }
     }
     csync();                     // scratch is reused by the next phase
+    return fence;
 }
 
 // talker: combine the splits of group g -> FK_XS(c)[0][0..rep*128)  (input of the grouped O-projection)
@@ -826,16 +845,21 @@ LQT_DEVINL void cp_attn_local(FkCtx& c, const FkLayer& L, int layer, int p0, uns
         const int j = c.warp + u * FK_CWARPS;
         kpre[u] = (j < p0) ? __ldcg(reinterpret_cast<const float4*>(kc + (size_t)j * ATT_D) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // everything that does not depend on the new row is requested before the row -- and, like the cached K/V rows above, before the
+    // grid hand-over, which this function waits for itself: norm weights, cos / sin (then the ring stages while the row is in flight)
+    float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;
+    if (c.warp < 3) {
+        nw4 = __ldg(reinterpret_cast<const float4*>(c.warp == 2 ? L.knorm : L.qnorm) + c.lane);
+        c4 = __ldg(reinterpret_cast<const float4*>(S.cos + (size_t)p0 * (ATT_D / 2)) + (c.lane & 15));
+        s4 = __ldg(reinterpret_cast<const float4*>(S.sin + (size_t)p0 * (ATT_D / 2)) + (c.lane & 15));
+    }
+#ifndef FK_DATAFLOW_QKV
+    grid_wait(c, want);
+#endif
+    fk_mark(c, 1);
     if (c.warp < 4) {                                // warps 0, 1: the two q heads of the group; 2: k; 3: v
         const int job = c.warp;
         const int off = (job < 2) ? (g * 2 + job) * ATT_D : (job == 2 ? q_dim : q_dim + kv_dim) + g * ATT_D;
-        // everything that does not depend on the new row is loaded before the row is waited for: norm weights, cos / sin, ring stages
-        float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;
-        if (job < 3) {
-            nw4 = __ldg(reinterpret_cast<const float4*>(job == 2 ? L.knorm : L.qnorm) + c.lane);
-            c4 = __ldg(reinterpret_cast<const float4*>(S.cos + (size_t)p0 * (ATT_D / 2)) + (c.lane & 15));
-            s4 = __ldg(reinterpret_cast<const float4*>(S.sin + (size_t)p0 * (ATT_D / 2)) + (c.lane & 15));
-        }
         const uint2* src = S.qkv + off + c.lane * 4;
         const FkRaw4 raw = ll_issue4(src);
         gemv_wait(c, u, nstages);
@@ -1027,19 +1051,18 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         // (Measured and rejected, -DFK_DATAFLOW_QKV: the predictor's phase C and the talker's phase B need only the q/k/v words of
         // their own kv group, each validated by its sequence tag, so they could skip the grid-wide wait. 2.375 instead of 2.275 ms
         // per frame: 4 warps x 120 CTAs re-polling the words delays the very stores they wait for.)
-#ifdef FK_DATAFLOW_QKV
-        if (!(kind == FKT_B || (kind == FKT_C && is_cp)))
-#endif
+        if (kind != FKT_B && !(kind == FKT_C && is_cp)) {      // (the attention phases request their cached K/V rows first and then wait themselves)
             grid_wait(c, want);
-        fk_mark(c, 1);
+            fk_mark(c, 1);
+        }
         // the layer input row: res0 (smem) for layer 0 without in_proj, else an LL buffer
         const bool in_res0 = (l == 0 && !inproj);
         const uint2* lin = (l == 0) ? p.cxin : S.x;           // (only read when !in_res0)
         if (kind == FKT_B) {
-            if (p.kv_f32) talker_attn_partial<float>(c, L, l, ps.pos0, want);
-            else          talker_attn_partial<bf16_t>(c, L, l, ps.pos0, want);
+            const bool fence = p.kv_f32 ? talker_attn_partial<float>(c, L, l, ps.pos0, want) : talker_attn_partial<bf16_t>(c, L, l, ps.pos0, want);
             csync();
             if (c.tid == 0) grid_arrive(c);
+            if (fence) __threadfence();                         // the new K/V row, before this CTA's next arrival (see talker_attn_partial)
             fk_mark(c, 3);
             if (FK_SH(c)->aborted) { c.aborted = true; break; }
             continue;
@@ -1591,6 +1614,7 @@ frame_kernel(const __grid_constant__ FkParams p) {
         sh->unit[tid / 80][(tid % 80) >> 3][tid & 7] = make_unit(dd, tid & 7);
     }
     for (int i = tid; i < FK_NGRP_MAX * FK_RPP_MAX; i += FK_THREADS) (&sh->redc[0][0])[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < min(p.n_pages, FK_PT_MAX); i += FK_THREADS) sh->pt[i] = p.page_table[i];
     __syncthreads();
     if (tid < 2 * FK_PART_ROWS) {
         const int st = tid / FK_PART_ROWS, r = tid % FK_PART_ROWS, rpp = max(1, sh->desc[st][FKT_C].rpp);
