@@ -442,13 +442,24 @@ __device__ __noinline__ void grid_wait_slow(const unsigned* ctr, unsigned target
 #endif
     } while ((int)(v - target) < 0);
 }
-// all consumer threads; returns when every CTA has issued the outputs of phase `n`
-LQT_DEVINL void grid_wait(FkCtx& c, unsigned n) {
-    if (c.tid == 0 && n != 0) {
-        const unsigned target = n * (unsigned)c.ncta;
-        unsigned v;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
-        if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &FK_SH(c)->aborted, c.p->ctrl);
+// all consumer threads; returns when every CTA has issued the outputs of phase `n`.
+// The poller is lane 0 of warp 1, not of warp 0: warp 0 runs the epilogue of the previous phase, the other warps get here early, so the
+// poll is already in flight when the last arrival lands and neither the epilogue's tail nor the loop top of warp 0 sits between "every
+// CTA has arrived" and the request for the next input vector. For the same reason the poller issues that request (fetch_src != nullptr:
+// the cluster-multicast copy of mc_fetch) straight after the poll, before the CTA barrier. This is safe: a landing buffer is rewritten
+// two fetches after it was filled, i.e. behind a grid hand-over that every reader of its previous content -- in every CTA of the
+// cluster -- has passed; and the only reader of a landing buffer in an epilogue (the O-projection's residual) reads the OTHER buffer.
+constexpr int FK_POLLER = 32;
+LQT_DEVINL void mc_issue(FkCtx& c, const uint2* src, int W);
+LQT_DEVINL void grid_wait(FkCtx& c, unsigned n, const uint2* fetch_src = nullptr, int fetch_w = 0) {
+    if (c.tid == FK_POLLER) {
+        if (n != 0) {
+            const unsigned target = n * (unsigned)c.ncta;
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
+            if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &FK_SH(c)->aborted, c.p->ctrl);
+        }
+        if (fetch_src) mc_issue(c, fetch_src, fetch_w);
     }
     csync();
 }
@@ -939,7 +950,19 @@ LQT_DEVINL void f4_to(float (&d)[4], const float4& v) { d[0] = v.x; d[1] = v.y; 
 // Readers validate the (value, sequence) words they use; a word whose store had not landed in L2 when the
 // copy read it is re-polled from global memory and patched in place.
 // ------------------------------------------------------------------------------------------------
-LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W, const FkUnit* u = nullptr, int nstages = 1) {
+LQT_DEVINL void mc_issue(FkCtx& c, const uint2* src, int W) {            // one thread (the poller)
+#ifndef FK_NO_MC
+    const unsigned b = c.land_n & 1u;
+    uint2* dst = FK_LAND(c) + b * FK_LAND_WORDS;
+    uint64_t* bar = &FK_SH(c)->land_bar[b];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic writes to the buffer (patches, sampler scratch)
+    mbar_expect_tx(bar, (uint32_t)W * 8u);
+    const int share = W / FK_CLUSTER;                                // W % 16 == 0: 16-byte multiples
+    bulk_g2s_mc(dst + c.rank * share, src + c.rank * share, (uint32_t)share * 8u, bar, (uint16_t)((1u << FK_CLUSTER) - 1u));
+#endif
+}
+// issued = the request was already made by grid_wait
+LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W, bool issued, const FkUnit* u = nullptr, int nstages = 1) {
     const unsigned b = c.land_n & 1u, par = (c.land_n >> 1) & 1u;
     uint2* dst = FK_LAND(c) + b * FK_LAND_WORDS;
     uint64_t* bar = &FK_SH(c)->land_bar[b];
@@ -947,16 +970,11 @@ LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W, const FkUnit* u = 
     for (int w = c.tid * 2; w < W; w += FK_CTHREADS * 2) *reinterpret_cast<uint4*>(dst + w) = ld_ll2(src + w);
     csync();
     ++c.land_n;
-    (void)par; (void)bar;
+    (void)par; (void)bar; (void)issued;
     if (u) gemv_wait(c, *u, nstages);
     return dst;
 #endif
-    if (c.tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic writes to the buffer (patches, sampler scratch)
-        mbar_expect_tx(bar, (uint32_t)W * 8u);
-        const int share = W / FK_CLUSTER;                                // W % 16 == 0: 16-byte multiples
-        bulk_g2s_mc(dst + c.rank * share, src + c.rank * share, (uint32_t)share * 8u, bar, (uint16_t)((1u << FK_CLUSTER) - 1u));
-    }
+    if (!issued && c.tid == FK_POLLER) mc_issue(c, src, W);
     if (u) gemv_wait(c, *u, nstages);                 // this warp's ring stages, while the vector is in flight
     if (!mbar_try_wait(bar, par)) {
         if (!wait_full_slow(bar, par, c.p->ctrl)) c.aborted = true;
@@ -1051,13 +1069,16 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
         // (Measured and rejected, -DFK_DATAFLOW_QKV: the predictor's phase C and the talker's phase B need only the q/k/v words of
         // their own kv group, each validated by its sequence tag, so they could skip the grid-wide wait. 2.375 instead of 2.275 ms
         // per frame: 4 warps x 120 CTAs re-polling the words delays the very stores they wait for.)
-        if (kind != FKT_B && !(kind == FKT_C && is_cp)) {      // (the attention phases request their cached K/V rows first and then wait themselves)
-            grid_wait(c, want);
-            fk_mark(c, 1);
-        }
         // the layer input row: res0 (smem) for layer 0 without in_proj, else an LL buffer
         const bool in_res0 = (l == 0 && !inproj);
         const uint2* lin = (l == 0) ? p.cxin : S.x;           // (only read when !in_res0)
+        // the vector this phase fetches first (requested by the poller as soon as the grid has arrived)
+        const uint2* fsrc = (kind == FKT_A) ? (in_res0 ? nullptr : lin) : (kind == FKT_D) ? S.x1 : (kind == FKT_E) ? S.act : (kind == FKT_HEAD) ? S.x : nullptr;
+        const int fw = (kind == FKT_E) ? min(FK_LAND_WORDS, d.K) : H;
+        if (kind != FKT_B && !(kind == FKT_C && is_cp)) {      // (the attention phases request their cached K/V rows first and then wait themselves)
+            grid_wait(c, want, fsrc, fw);
+            fk_mark(c, 1);
+        }
         if (kind == FKT_B) {
             const bool fence = p.kv_f32 ? talker_attn_partial<float>(c, L, l, ps.pos0, want) : talker_attn_partial<bf16_t>(c, L, l, ps.pos0, want);
             csync();
@@ -1113,14 +1134,14 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                     for (int j = 0; j < HJ; ++j)
                         if (j * 1024 + tid4 < H) f4_to(xin[j], *reinterpret_cast<const float4*>(FK_RES0(c) + j * 1024 + tid4));
                 } else {
-                    uint2* land = mc_fetch(c, lin, H, &u, NST);
+                    uint2* land = mc_fetch(c, lin, H, true, &u, NST);
                     land_row<HJ>(c, land, lin, H, want, xin);
                     c.land_a = (c.land_n - 1u) & 1u;
                 }
                 break;
             }
             case FKT_D: {
-                uint2* land = mc_fetch(c, S.x1, H, &u, NST);
+                uint2* land = mc_fetch(c, S.x1, H, true, &u, NST);
                 land_row<HJ>(c, land, S.x1, H, want, xin);
                 const FkDesc& de = FK_SH(c)->desc[tk][FKT_E];
 #pragma unroll
@@ -1137,7 +1158,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                 for (int w0 = 0; w0 < d.K; w0 += FK_LAND_WORDS) {          // wide models: two landing-buffer loads
                     const int wn = min(FK_LAND_WORDS, d.K - w0);
                     float t3[3][4];
-                    uint2* land = mc_fetch(c, S.act + w0, wn, w0 == 0 ? &u : nullptr, NST);
+                    uint2* land = mc_fetch(c, S.act + w0, wn, w0 == 0, w0 == 0 ? &u : nullptr, NST);
                     land_row<3>(c, land, S.act + w0, wn, want, t3);
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
@@ -1146,7 +1167,7 @@ LQT_DEVINL void consume_token(FkCtx& c, const FkParams& p, const FkPass& ps) {
                 break;
             }
             default: {  // FKT_HEAD: final norm + head
-                uint2* land = mc_fetch(c, S.x, H, &u, NST);
+                uint2* land = mc_fetch(c, S.x, H, true, &u, NST);
                 land_row<HJ>(c, land, S.x, H, want, xin);
                 break;
             }
@@ -1760,13 +1781,13 @@ frame_kernel(const __grid_constant__ FkParams p) {
             const int tk = cb ? 1 : 0;
             fk_phase(c, tk, FKT_SAMPLE);
             fk_mark(c, 0);
-            grid_wait(c, resumed ? 0u : c.seq);                 // the logits of the head phase have been issued everywhere
-            fk_mark(c, 1);
-            float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + cb) * p.trace_stride : nullptr;
             const bool t0 = (cb == 0);                          // one call site: the sampler is instantiated once
             const uint2* lg = t0 ? (resumed ? nullptr : p.logits_ll) : p.clogits_ll;
             const int Vd = t0 ? p.vocab : p.cp_vocab;
-            const uint2* land = lg ? mc_fetch(c, lg, Vd) : nullptr;
+            grid_wait(c, resumed ? 0u : c.seq, lg, Vd);         // the logits of the head phase have been issued everywhere
+            fk_mark(c, 1);
+            float* tr = (p.trace && cta == 0) ? p.trace + ((size_t)frame * 16 + cb) * p.trace_stride : nullptr;
+            const uint2* land = lg ? mc_fetch(c, lg, Vd, true) : nullptr;
             int tok = fk_sample(c, lg, land, t0 ? p.logits : nullptr, c.seq, Vd, t0 ? 2048 : 0, t0 ? p.vocab : 0, t0 ? 2150 : -1,
                                 sp, (uint32_t)frame, cb, tr);
             resumed = false;
