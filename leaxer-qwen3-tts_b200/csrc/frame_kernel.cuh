@@ -1307,6 +1307,7 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
         if (c.lane == 0) sh->sel_k = B;
     }
     csync();
+    fk_mark(c, 10);
     const int B = sh->sel_k;
     if (B < 0) { csync(); return -1; }
     const float lim = (float)(B + 1);
@@ -1320,6 +1321,7 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
         if ((mx - v) * 16.0f < lim) { s.idx[wpos] = (unsigned short)i; s.pr[wpos] = v; ++wpos; }
     }
     csync();
+    fk_mark(c, 11);
     if (c.warp == 0) {
         // One warp, lane l owns candidates l and l + 32 (candidates are in index order). Everything stays in candidate order:
         // a candidate that drops out (below the k-th value, beyond the top-p cut) becomes an exact 0.0f, which is neutral in
@@ -1344,6 +1346,7 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
 #pragma unroll
             for (int q = 0; q < 8; ++q) { gt0 += (xv[q] > x0) ? 1 : 0; gt1 += (xv[q] > x1) ? 1 : 0; }
         }
+        fk_mark(c, 12);
         const bool sv0 = e0 < n_c && gt0 < k, sv1 = e1 < n_c && gt1 < k;      // x >= (k-th largest)  <=>  fewer than k values above it
         const unsigned b0 = __ballot_sync(0xffffffffu, sv0), b1 = __ballot_sync(0xffffffffu, sv1);
         const int ns = __popc(b0) + __popc(b1);
@@ -1356,6 +1359,7 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
             const float4 u = *reinterpret_cast<const float4*>(s.spr + i), w = *reinterpret_cast<const float4*>(s.spr + i + 4);
             sum += u.x; sum += u.y; sum += u.z; sum += u.w; sum += w.x; sum += w.y; sum += w.z; sum += w.w;
         }
+        fk_mark(c, 13);
         pr0 = pr0 / sum; pr1 = pr1 / sum;                                        // (dropped candidates stay 0)
         __syncwarp();
         s.spr[e0] = pr0; s.spr[e1] = pr1;
@@ -1404,6 +1408,7 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
             s.spr[e0] = pr0; s.spr[e1] = pr1;
             __syncwarp();
         }
+        fk_mark(c, 14);
         uint32_t r4[4];
         philox4x32_10(frame, (uint32_t)codebook, 0u, 0u, sp.seed, sp.utt, r4);
         const float u01 = (float)(r4[0] >> 8) * 5.9604644775390625e-08f;
@@ -1424,6 +1429,7 @@ LQT_DEVINL int fk_sample_fast(FkCtx& c, int i0, int i1, float mx, const Sampling
                 }
             }
         }
+        fk_mark(c, 15);
         if (lane == 0) sh->tok = last;
     }
     csync();
@@ -1476,6 +1482,7 @@ LQT_DEVINL int fk_sample(FkCtx& c, const uint2* ll, const uint2* land, const flo
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
+    fk_mark(c, 8);
     if (c.lane == 0) { sh->redf[c.warp][0] = bv; sh->redi[c.warp] = bi; }
     csync();
     {
@@ -1487,6 +1494,7 @@ LQT_DEVINL int fk_sample(FkCtx& c, const uint2* ll, const uint2* land, const flo
     }
     if (sp.greedy) { csync(); return bi; }
     const float mx = bv;
+    fk_mark(c, 9);
     if (sp.top_k > 0 && sp.top_k < V && sp.top_k <= 64) {      // common case: a handful of survivors, finished by one warp
         const int t = fk_sample_fast(c, i0, i1, mx, sp, frame, codebook);
         if (t >= 0) return t;

@@ -43,6 +43,9 @@ def main():
     POINTS = {0: "begin", 1: "grid go", 2: "fetched", 3: "inputs staged", 4: "glue/dsmem push", 5: "softmax done", 6: "published", 7: "landed",
               8: "staged+csync", 9: "stages ready", 10: "mma done", 11: "stages released", 12: "partials csync", 13: "qkv normed", 14: "scores csync",
               15: "softmax csync"}
+    # inside the sampler (phase kind 7) the same ids mark other places
+    SPOINTS = {0: "begin", 1: "grid go", 7: "landed", 8: "logits loaded", 9: "max known", 10: "top-k bin found", 11: "candidates compacted",
+               12: "exact top-k (warp 0)", 13: "softmax sum", 14: "top-p done", 15: "draw done", 3: "token broadcast", 4: "glue"}
     seg = collections.defaultdict(list)
     for i in range(1, len(clk)):
         st, kind, pt = (tag[i] >> 9) & 1, (tag[i] >> 4) & 31, tag[i] & 15
@@ -52,7 +55,7 @@ def main():
     print(f"{'stack':6s} {'phase':10s} {'->point':15s} {'count':>7s} {'mean cyc':>9s} {'mean us':>8s} {'share':>6s}")
     for k in sorted(seg):
         v = np.asarray(seg[k], np.float64)
-        print(f"{'cp' if k[0] else 'talker':6s} {KINDS.get(k[1], str(k[1])):10s} {POINTS.get(k[2], str(k[2])):15s} {len(v):7d} {v.mean():9.0f} "
+        print(f"{'cp' if k[0] else 'talker':6s} {KINDS.get(k[1], str(k[1])):10s} {(SPOINTS if k[1] == 7 else POINTS).get(k[2], str(k[2])):20s} {len(v):7d} {v.mean():9.0f} "
               f"{v.mean() / a.mhz:8.2f} {v.sum() / tot:6.3f}")
     # the second recorder (lane 0 of another consumer warp): its lag behind thread 0 at the marks both pass, matched by occurrence
     clk2, tag2 = eng.timeline_read(1)
