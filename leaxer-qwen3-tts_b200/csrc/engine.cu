@@ -1113,7 +1113,7 @@ int fk_launch(lqt_engine* h, int slot, int mode, const float* prompt, int P, int
     const Spec& s = h->sp;
     FkParams p{};
     p.talker = h->fk_talker; p.cp = h->fk_cp;
-    { static const int sl = getenv("LQT_FK_SLEEP") ? atoi(getenv("LQT_FK_SLEEP")) : 400; p.producer_sleep_ns = (unsigned)(sl < 0 ? 0 : sl); }
+    { static const int sl = getenv("LQT_FK_SLEEP") ? atoi(getenv("LQT_FK_SLEEP")) : 800; p.producer_sleep_ns = (unsigned)(sl < 0 ? 0 : sl); }
     for (size_t l = 0; l < h->fk_tl.size(); ++l) p.t_layers[l] = h->fk_tl[l];
     for (size_t l = 0; l < h->fk_cl.size(); ++l) p.c_layers[l] = h->fk_cl[l];
     p.t_head = h->fk_t_head; p.vocab = s.vocab;

@@ -107,7 +107,7 @@ struct FkParams {
     volatile int* progress;    // nullable, pinned HOST memory: frames completed so far (the host vocodes them while the kernel runs)
     unsigned* ctrl;            // [1] abort flag, [32] grid arrival counter (all zero at launch)
     int frame_end;             // run frames while frame < frame_end (<= max_frames)
-    unsigned producer_sleep_ns; // back-off of the producer lane while the ring is full ($LQT_FK_SLEEP, default 400)
+    unsigned producer_sleep_ns; // back-off of the producer lane while the ring is full ($LQT_FK_SLEEP, default 800: 0-400 ns measured 0.5 % slower, 1600 ns 1.5 % slower)
     int mode;                  // 0 = prefill (if pos == 0) + frames; 1 = one talker token from next_in (head on), no frames
     unsigned long long* dbg;   // nullable: phase timeline of CTA dbg_cta, [0] = count
     int dbg_cap, dbg_cta;
@@ -450,6 +450,9 @@ __device__ __noinline__ void grid_wait_slow(const unsigned* ctr, unsigned target
 // two fetches after it was filled, i.e. behind a grid hand-over that every reader of its previous content -- in every CTA of the
 // cluster -- has passed; and the only reader of a landing buffer in an epilogue (the O-projection's residual) reads the OTHER buffer.
 constexpr int FK_POLLER = 32;
+#ifndef FK_PRODUCER_WARP
+#define FK_PRODUCER_WARP 3                        // which warp of the producer warpgroup streams the weights = the scheduler it shares: 3 (with consumer warps 3 and 7) measured 0.5 % faster than 0 (with warp 0, which runs every epilogue)
+#endif
 LQT_DEVINL void mc_issue(FkCtx& c, const uint2* src, int W);
 LQT_DEVINL void grid_wait(FkCtx& c, unsigned n, const uint2* fetch_src = nullptr, int fetch_w = 0) {
     if (c.tid == FK_POLLER) {
@@ -1663,7 +1666,7 @@ frame_kernel(const __grid_constant__ FkParams p) {
         // ============================ producer warp ============================================
         // Walks the same flat schedule as the consumers, one stage at a time, as far ahead as the
         // ring allows. All state in registers of one lane.
-        if (warp == FK_CWARPS && lane == 0) {
+        if (warp == FK_CWARPS + FK_PRODUCER_WARP && lane == 0) {
             long long n_pass;
             if (p.mode == 1) n_pass = 1;
             else {
