@@ -464,12 +464,12 @@ def main():
     gen_s = gen_ms * 1e-3
     achieved = fb["total"] * frames_r0 / gen_s / 1e9 if gen_s > 0 else 0.0
     traffic = None                      # DRAM bytes of one frame_kernel launch from the committed ncu capture (same workload only)
-    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2s3_traffic.json")
     if a.frames == 375 and a.spec == "0.6b" and a.frame_impl == "persistent" and os.path.exists(tpath):
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_note": "DRAM bytes per utterance (9 prefill rows + 375 frames, one frame_kernel launch), ncu capture of the same command (profiles/r2_summary.md section 0, r2_final_launches.csv.gz); algorithmic bytes per utterance = total x 375",
+                "traffic_note": "DRAM bytes per utterance (9 prefill rows + 375 frames, one frame_kernel launch), ncu capture of the same command (profiles/r2s3_summary.md section 1, r2s3_final_launches.csv.gz); algorithmic bytes per utterance = total x 375",
                 "kernel": "frame_kernel (persistent cluster kernel: TMA weight stream + tensor-core matrix-vector phases + attention + sampler), per frame",
                 "algorithmic_bytes_per_frame": fb, "us_per_frame": gen_s / frames_r0 * 1e6,
                 "peak_source": peak_src}
