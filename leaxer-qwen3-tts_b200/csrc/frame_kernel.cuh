@@ -454,15 +454,36 @@ constexpr int FK_POLLER = 32;
 #define FK_PRODUCER_WARP 3                        // which warp of the producer warpgroup streams the weights = the scheduler it shares: 3 (with consumer warps 3 and 7) measured 0.5 % faster than 0 (with warp 0, which runs every epilogue)
 #endif
 LQT_DEVINL void mc_issue(FkCtx& c, const uint2* src, int W);
+LQT_DEVINL void mc_arm(FkCtx& c, int W);
+LQT_DEVINL void mc_issue_all(FkCtx& c, const uint2* src, int W);
 LQT_DEVINL void grid_wait(FkCtx& c, unsigned n, const uint2* fetch_src = nullptr, int fetch_w = 0) {
     if (c.tid == FK_POLLER) {
-        if (n != 0) {
-            const unsigned target = n * (unsigned)c.ncta;
-            unsigned v;
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
-            if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &FK_SH(c)->aborted, c.p->ctrl);
+#ifndef FK_NO_LEADER_FETCH
+        // One poller per cluster when the phase starts with a fetch (2.033 -> 2.011 ms per frame; several polls in flight by that one poller: 2.03): the landing barrier of a CTA completes when ALL copies into its buffer
+        // have landed, i.e. with eight issuers when the LAST of eight pollers has seen the counter (each samples it once per L2 round trip).
+        // Rank 0 polls and copies the whole vector into all eight CTAs; the others only arm their landing barrier.
+        if (fetch_src) {
+            mc_arm(c, fetch_w);
+            if (c.rank == 0) {
+                if (n != 0) {
+                    const unsigned target = n * (unsigned)c.ncta;
+                    unsigned v;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
+                    if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &FK_SH(c)->aborted, c.p->ctrl);
+                }
+                mc_issue_all(c, fetch_src, fetch_w);
+            }
+        } else
+#endif
+        {
+            if (n != 0) {
+                const unsigned target = n * (unsigned)c.ncta;
+                unsigned v;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.p->ctrl + 32) : "memory");
+                if ((int)(v - target) < 0) grid_wait_slow(c.p->ctrl + 32, target, &FK_SH(c)->aborted, c.p->ctrl);
+            }
+            if (fetch_src) mc_issue(c, fetch_src, fetch_w);
         }
-        if (fetch_src) mc_issue(c, fetch_src, fetch_w);
     }
     csync();
 }
@@ -963,6 +984,15 @@ LQT_DEVINL void mc_issue(FkCtx& c, const uint2* src, int W) {            // one 
     const int share = W / FK_CLUSTER;                                // W % 16 == 0: 16-byte multiples
     bulk_g2s_mc(dst + c.rank * share, src + c.rank * share, (uint32_t)share * 8u, bar, (uint16_t)((1u << FK_CLUSTER) - 1u));
 #endif
+}
+LQT_DEVINL void mc_arm(FkCtx& c, int W) {                                  // one thread: expect W words in the current landing buffer
+    const unsigned b = c.land_n & 1u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&FK_SH(c)->land_bar[b], (uint32_t)W * 8u);
+}
+LQT_DEVINL void mc_issue_all(FkCtx& c, const uint2* src, int W) {          // one thread of ONE CTA of the cluster: the whole vector into all eight
+    const unsigned b = c.land_n & 1u;
+    bulk_g2s_mc(FK_LAND(c) + b * FK_LAND_WORDS, src, (uint32_t)W * 8u, &FK_SH(c)->land_bar[b], (uint16_t)((1u << FK_CLUSTER) - 1u));
 }
 // issued = the request was already made by grid_wait
 LQT_DEVINL uint2* mc_fetch(FkCtx& c, const uint2* src, int W, bool issued, const FkUnit* u = nullptr, int nstages = 1) {
