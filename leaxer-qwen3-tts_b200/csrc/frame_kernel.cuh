@@ -459,7 +459,8 @@ LQT_DEVINL void mc_issue_all(FkCtx& c, const uint2* src, int W);
 LQT_DEVINL void grid_wait(FkCtx& c, unsigned n, const uint2* fetch_src = nullptr, int fetch_w = 0) {
     if (c.tid == FK_POLLER) {
 #ifndef FK_NO_LEADER_FETCH
-        // One poller per cluster when the phase starts with a fetch (2.033 -> 2.011 ms per frame; several polls in flight by that one poller: 2.03): the landing barrier of a CTA completes when ALL copies into its buffer
+        // One poller per cluster when the phase starts with a fetch (2.033 -> 2.011 ms per frame; several polls in flight by that one poller: 2.03;
+        // the same for the phases WITHOUT a fetch, rank 0 releasing its partners through distributed shared memory: 2.005 -> 2.026): the landing barrier of a CTA completes when ALL copies into its buffer
         // have landed, i.e. with eight issuers when the LAST of eight pollers has seen the counter (each samples it once per L2 round trip).
         // Rank 0 polls and copies the whole vector into all eight CTAs; the others only arm their landing barrier.
         if (fetch_src) {
