@@ -102,6 +102,28 @@ def test_talker_long_context_split_kv(request):
     assert worst < LOGIT_TOL_TIGHT, worst
 
 
+@pytest.mark.parametrize("which", ["full_f32", "full"])
+def test_talker_context_beyond_one_kv_round(request, which):
+    """More than 480 positions: every attention split holds more than 32 positions, so a warp runs several rounds of four cached K/V
+    rows (the first round is requested before the grid hand-over, the later ones inside the loop; frame_kernel.cuh
+    talker_attn_partial), the last round is ragged, and 8 KV pages are addressed through the page-table copy in shared memory."""
+    eng, m = pair(request, which)
+    H = m.spec.hidden
+    P = 500
+    x = rnd((P + 3, H), 17)
+    kv = m.new_kv()
+    ref_logits, ref_hid = m.talker_prefill(torch.from_numpy(x[:P]), kv)
+    logits, hid = eng.talker_prefill(x[:P], slot=0)
+    assert eng.kv_len(0) == P
+    assert maxabs(logits, ref_logits[-1].numpy()) < tight(which) and maxabs(hid, ref_hid.numpy()) < tight(which)
+    for i in range(P, P + 3):
+        rl, rh = m.talker_decode(torch.from_numpy(x[i]), kv)
+        lg, hd = eng.talker_decode(x[i], slot=0)
+        e1, e2 = maxabs(lg, rl.numpy()), maxabs(hd, rh.numpy())
+        assert e1 < tight(which) and e2 < tight(which), (i, e1, e2)
+    eng.kv_reset(0)
+
+
 @pytest.mark.parametrize("which", ["tiny", "full"])
 def test_code_predictor(request, which):
     eng, m = pair(request, which)
