@@ -78,7 +78,8 @@ typedef struct lqt_options {
 
 /* src/tts_onnx.cpp:84-130 (TTSEngine ctor) + :134-232 (load_model): loads the 7 required graph
  * files (+ optional speaker_encoder) from model_dir. On failure returns non-zero, *out = NULL and
- * lqt_create_error() describes why (the reference sets error_msg_ and leaves ready_ = false). */
+ * lqt_create_error() describes why (the reference sets error_msg_ and leaves ready_ = false). The message is per calling thread:
+ * engines may be created from several threads (one per device) at once. */
 int lqt_create(const char* model_dir, int device_id, lqt_engine** out);
 int lqt_create_ex(const char* model_dir, int device_id, const lqt_options* opt, lqt_engine** out);
 const char* lqt_create_error(void);

@@ -39,7 +39,7 @@ constexpr int ATT_NSPLIT = 16;
 constexpr int CP_PAGE_SHIFT = 5;                 // predictor: one fp32 page of 32 positions
 constexpr int N_CODEBOOKS = 16;
 
-std::string g_create_error;
+thread_local std::string g_create_error;    // why the last lqt_create on THIS thread failed (no handle exists to hold it)
 
 struct LayerW {
     const float *ln1 = nullptr, *ln2 = nullptr, *qnorm = nullptr, *knorm = nullptr, *ls1 = nullptr, *ls2 = nullptr;
