@@ -450,6 +450,9 @@ __device__ __noinline__ void grid_wait_slow(const unsigned* ctr, unsigned target
 // two fetches after it was filled, i.e. behind a grid hand-over that every reader of its previous content -- in every CTA of the
 // cluster -- has passed; and the only reader of a landing buffer in an epilogue (the O-projection's residual) reads the OTHER buffer.
 constexpr int FK_POLLER = 32;
+#if defined(FK_NO_MC) && !defined(FK_NO_LEADER_FETCH)
+#define FK_NO_LEADER_FETCH                        // the per-CTA copy of the bisecting build needs every CTA to wait for the grid itself
+#endif
 #ifndef FK_PRODUCER_WARP
 #define FK_PRODUCER_WARP 3                        // which warp of the producer warpgroup streams the weights = the scheduler it shares: 3 (with consumer warps 3 and 7) measured 0.5 % faster than 0 (with warp 0, which runs every epilogue)
 #endif
