@@ -686,13 +686,15 @@ constexpr int FA_WL = FA_WM + FK_CWARPS * 2;
 constexpr int FA_WO = FA_WL + FK_CWARPS * 2;         // wo    [8 w][2 r][128]
 constexpr int FA_FLOATS = FA_WO + FK_CWARPS * 2 * ATT_D;
 
-template <typename KVT>
-LQT_DEVINL float4 kv_load4_cg(const KVT* p);
-template <> LQT_DEVINL float4 kv_load4_cg<bf16_t>(const bf16_t* p) {
-    const uint2 u = __ldcg(reinterpret_cast<const uint2*>(p));
-    return make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
-}
-template <> LQT_DEVINL float4 kv_load4_cg<float>(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+// Four consecutive K/V values as loaded (bf16: 8 bytes, unpacked only where they are used -- an unpack right behind the load would make the
+// warp wait for the load, and the loads are issued ahead of the grid hand-over precisely so that nobody waits for them there).
+template <typename KVT> struct FkKvRaw;
+template <> struct FkKvRaw<bf16_t> { uint2 u; };
+template <> struct FkKvRaw<float> { float4 u; };
+LQT_DEVINL void kv_load_raw(FkKvRaw<bf16_t>& r, const bf16_t* p) { r.u = __ldcg(reinterpret_cast<const uint2*>(p)); }
+LQT_DEVINL void kv_load_raw(FkKvRaw<float>& r, const float* p) { r.u = __ldcg(reinterpret_cast<const float4*>(p)); }
+LQT_DEVINL float4 kv_unpack(const FkKvRaw<bf16_t>& r) { return make_float4(bf16lo(r.u.x), bf16hi(r.u.x), bf16lo(r.u.y), bf16hi(r.u.y)); }
+LQT_DEVINL float4 kv_unpack(const FkKvRaw<float>& r) { return r.u; }
 
 // talker: split-KV partial attention of kv group g over this CTA's chunk of positions -> pa (LL).
 // Everything that does not depend on the new row is requested BEFORE the grid hand-over (the function waits for the grid itself): the
@@ -701,7 +703,7 @@ template <> LQT_DEVINL float4 kv_load4_cg<float>(const float* p) { return __ldcg
 // owe a __threadfence() before the CTA's NEXT arrival (the caller issues it after this phase's arrival, off the critical path; the row
 // is read one frame later at the earliest).
 template <typename KVT>
-LQT_DEVINL void talker_kv_round(FkCtx& c, const KVT* pool, long long goff, long long v_off, int jb, int j1, int t, float4 (&kk)[4], float4 (&vv)[4]) {
+LQT_DEVINL void talker_kv_round(FkCtx& c, const KVT* pool, long long goff, long long v_off, int jb, int j1, int t, FkKvRaw<KVT> (&kk)[4], FkKvRaw<KVT> (&vv)[4]) {
     const FkParams& p = *c.p;
     const int PS = 1 << p.page_shift;
 #pragma unroll
@@ -709,8 +711,8 @@ LQT_DEVINL void talker_kv_round(FkCtx& c, const KVT* pool, long long goff, long 
         const int j = jb + u * FK_CWARPS;
         if (j < j1 && j != t) {
             const KVT* kp = pool + (long long)FK_SH(c)->pt[j >> p.page_shift] * p.page_stride + goff + (long long)(j & (PS - 1)) * ATT_D + c.lane * 4;
-            kk[u] = kv_load4_cg<KVT>(kp);
-            vv[u] = kv_load4_cg<KVT>(kp + v_off);
+            kv_load_raw(kk[u], kp);
+            kv_load_raw(vv[u], kp + v_off);
         }
     }
 }
@@ -728,7 +730,7 @@ LQT_DEVINL bool talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     const long long layer_off = (long long)layer * 2 * n_kv * PS * ATT_D;
     const long long head_off = (long long)g * PS * ATT_D, v_off = (long long)n_kv * PS * ATT_D;
     float4 nw4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = nw4, s4 = nw4;
-    float4 kk[4], vv[4];
+    FkKvRaw<KVT> kk[4], vv[4];
     if (active) {
         if (c.warp < 3) {
             nw4 = __ldg(reinterpret_cast<const float4*>(c.warp == 2 ? L.knorm : L.qnorm) + c.lane);
@@ -772,23 +774,25 @@ LQT_DEVINL bool talker_attn_partial(FkCtx& c, const FkLayer& L, int layer, int t
     const float scale = 1.0f / sqrtf((float)ATT_D);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    // The arithmetic of the loop is pinned with explicit intrinsics (which product is rounded and which is fused): the bf16 K/V rounding
+    // amplifies a 1-ulp difference into other tokens within a few frames, so a refactoring must not change what the compiler contracts.
     for (int jb = j0 + c.warp;;) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = jb + u * FK_CWARPS;
             if (j < j1) {
-                if (j == t) {
-                    kk[u] = reinterpret_cast<const float4*>(kn)[c.lane];
-                    vv[u] = reinterpret_cast<const float4*>(vn)[c.lane];
-                }
-                float d0 = kk[u].x * q0.x + kk[u].y * q0.y + kk[u].z * q0.z + kk[u].w * q0.w;
-                float d1 = kk[u].x * q1.x + kk[u].y * q1.y + kk[u].z * q1.z + kk[u].w * q1.w;
-                d0 = warp_sum(d0) * scale; d1 = warp_sum(d1) * scale;
+                const float4 k4 = (j == t) ? reinterpret_cast<const float4*>(kn)[c.lane] : kv_unpack(kk[u]);
+                const float4 v4 = (j == t) ? reinterpret_cast<const float4*>(vn)[c.lane] : kv_unpack(vv[u]);
+                float d0 = __fmaf_rn(k4.w, q0.w, __fmaf_rn(k4.z, q0.z, __fmaf_rn(k4.x, q0.x, __fmul_rn(k4.y, q0.y))));
+                float d1 = __fmaf_rn(k4.w, q1.w, __fmaf_rn(k4.z, q1.z, __fmaf_rn(k4.x, q1.x, __fmul_rn(k4.y, q1.y))));
+                d0 = __fmul_rn(warp_sum(d0), scale); d1 = __fmul_rn(warp_sum(d1), scale);
                 const float n0 = fmaxf(m0, d0), n1 = fmaxf(m1, d1);
                 const float c0 = expf(m0 - n0), c1 = expf(m1 - n1), p0 = expf(d0 - n0), p1 = expf(d1 - n1);
-                l0 = l0 * c0 + p0; l1 = l1 * c1 + p1;
-                a0.x = a0.x * c0 + p0 * vv[u].x; a0.y = a0.y * c0 + p0 * vv[u].y; a0.z = a0.z * c0 + p0 * vv[u].z; a0.w = a0.w * c0 + p0 * vv[u].w;
-                a1.x = a1.x * c1 + p1 * vv[u].x; a1.y = a1.y * c1 + p1 * vv[u].y; a1.z = a1.z * c1 + p1 * vv[u].z; a1.w = a1.w * c1 + p1 * vv[u].w;
+                l0 = __fmaf_rn(l0, c0, p0); l1 = __fmaf_rn(l1, c1, p1);
+                a0.x = __fmaf_rn(a0.x, c0, __fmul_rn(p0, v4.x)); a0.y = __fmaf_rn(a0.y, c0, __fmul_rn(p0, v4.y));
+                a0.z = __fmaf_rn(a0.z, c0, __fmul_rn(p0, v4.z)); a0.w = __fmaf_rn(a0.w, c0, __fmul_rn(p0, v4.w));
+                a1.x = __fmaf_rn(a1.x, c1, __fmul_rn(p1, v4.x)); a1.y = __fmaf_rn(a1.y, c1, __fmul_rn(p1, v4.y));
+                a1.z = __fmaf_rn(a1.z, c1, __fmul_rn(p1, v4.z)); a1.w = __fmaf_rn(a1.w, c1, __fmul_rn(p1, v4.w));
                 m0 = n0; m1 = n1;
             }
         }
