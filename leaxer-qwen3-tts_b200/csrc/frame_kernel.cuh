@@ -489,7 +489,7 @@ LQT_DEVINL void grid_wait(FkCtx& c, unsigned n, const uint2* fetch_src = nullptr
             if (fetch_src) mc_issue(c, fetch_src, fetch_w);
         }
     }
-    fk_mark(c, 14);                                   // (profiling build, second recorder = the poller's warp: poll done, fetch issued)
+    if (c.warp != 0) fk_mark(c, 14);                  // (profiling build with FK_MARK_W2=1, the poller's warp: poll done, fetch issued)
     csync();
 }
 LQT_DEVINL float ll_poll1(FkCtx& c, const uint2* p, unsigned seq) {
