@@ -134,7 +134,9 @@ struct BStackCtx {
 
 // one new position per slot through all layers. `in`: [B][H] input rows (talker: prompt row or next_in per slot state).
 // Leaves the last layer's down-projection partials in layers.back().down; the caller applies the final norm.
-void bstack_run(lqt_engine* h, lqt_batch* bt, const BStackCtx& c, const float* in, const BGemm* in_part, const float* in_bias, int fixed_pos) {
+// kv_only_last: the pass only has to leave its K/V rows behind (predictor position 0: its hidden state is never read, src/tts_onnx.cpp:854-868
+// feeds the head with the LAST row only) -- the last layer stops after the attention kernel, which appends them.
+void bstack_run(lqt_engine* h, lqt_batch* bt, const BStackCtx& c, const float* in, const BGemm* in_part, const float* in_bias, int fixed_pos, bool kv_only_last = false) {
     const int D = ATT_D, qd = c.heads * D;
     const int nl = (int)c.layers->size();
     for (int l = 0; l < nl; ++l) {
@@ -167,6 +169,7 @@ void bstack_run(lqt_engine* h, lqt_batch* bt, const BStackCtx& c, const float* i
                 pdl_launch(h, bcp_attn_kernel, dim3((bt->B * c.kv_heads + 7) / 8), dim3(256), 0, c2);
             }
         }
+        if (kv_only_last && l == nl - 1) break;
         bgemm_launch(h, bt, L.o);
         bprep_launch(h, bt, c.xa, false, &L.o, nullptr, L.ln2, c.xb, nullptr, c.xn, c.H);
         bgemm_launch(h, bt, L.gu);
@@ -208,9 +211,9 @@ void benqueue_frame(lqt_engine* h, lqt_batch* bt) {
         if (h->c_inproj_w) {                                       // 1.7B: talker width -> predictor width
             bprep_launch(h, bt, row, false, nullptr, nullptr, nullptr, nullptr, nullptr, bt->xin_c, s.hidden);
             bgemm_launch(h, bt, bt->c_inproj);
-            bstack_run(h, bt, cc, nullptr, &bt->c_inproj, h->c_inproj_b, pos);
+            bstack_run(h, bt, cc, nullptr, &bt->c_inproj, h->c_inproj_b, pos, pos == 0);
         } else {
-            bstack_run(h, bt, cc, row, nullptr, nullptr, pos);
+            bstack_run(h, bt, cc, row, nullptr, nullptr, pos, pos == 0);
         }
         if (pos >= 1) {
             bprep_launch(h, bt, bt->xb_c, false, &bt->cl.back().down, nullptr, h->c_norm, nullptr, nullptr, bt->xn_c, s.cp_hidden);
