@@ -155,6 +155,109 @@ size_t hf_match_at(const std::vector<CodePoint>& t, size_t i) {
     return 1;
 }
 
+// ---- Unicode normalisation form C (UAX #15): the first stage of the published Qwen2 pipeline ("normalizer": NFC) -------------
+#include "unicode_nfc_tables.inc"
+
+uint32_t nfc_ccc(uint32_t cp) {
+    if (cp < 0x300) return 0;
+    size_t lo = 0, hi = sizeof(kNfcCcc) / sizeof(kNfcCcc[0]);
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (cp < kNfcCcc[mid][0]) hi = mid;
+        else if (cp > kNfcCcc[mid][1]) lo = mid + 1;
+        else return kNfcCcc[mid][2];
+    }
+    return 0;
+}
+// Hangul syllables are (de)composed arithmetically (UAX #15, section 3.12 of the standard)
+constexpr uint32_t kSBase = 0xAC00, kLBase = 0x1100, kVBase = 0x1161, kTBase = 0x11A7, kLCount = 19, kVCount = 21, kTCount = 28,
+                   kNCount = kVCount * kTCount, kSCount = kLCount * kNCount;
+void nfc_decompose(uint32_t cp, std::vector<uint32_t>& out) {       // full canonical decomposition of one code point
+    if (cp < 0xC0) { out.push_back(cp); return; }
+    if (cp >= kSBase && cp < kSBase + kSCount) {
+        const uint32_t s = cp - kSBase, t = s % kTCount;
+        out.push_back(kLBase + s / kNCount);
+        out.push_back(kVBase + (s % kNCount) / kTCount);
+        if (t) out.push_back(kTBase + t);
+        return;
+    }
+    size_t lo = 0, hi = sizeof(kNfcDecomp) / sizeof(kNfcDecomp[0]);
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (kNfcDecomp[mid][0] < cp) lo = mid + 1; else hi = mid;
+    }
+    if (lo < sizeof(kNfcDecomp) / sizeof(kNfcDecomp[0]) && kNfcDecomp[lo][0] == cp) {
+        nfc_decompose(kNfcDecomp[lo][1], out);                      // (the mappings are one step: the first part may decompose further)
+        if (kNfcDecomp[lo][2]) nfc_decompose(kNfcDecomp[lo][2], out);
+        return;
+    }
+    out.push_back(cp);
+}
+uint32_t nfc_compose_pair(uint32_t a, uint32_t b) {                 // primary composite of (a, b), or 0
+    if (a >= kLBase && a < kLBase + kLCount && b >= kVBase && b < kVBase + kVCount)
+        return kSBase + ((a - kLBase) * kVCount + (b - kVBase)) * kTCount;
+    if (a >= kSBase && a < kSBase + kSCount && (a - kSBase) % kTCount == 0 && b > kTBase && b < kTBase + kTCount)
+        return a + (b - kTBase);
+    size_t lo = 0, hi = sizeof(kNfcComp) / sizeof(kNfcComp[0]);
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (kNfcComp[mid][0] < a || (kNfcComp[mid][0] == a && kNfcComp[mid][1] < b)) lo = mid + 1; else hi = mid;
+    }
+    if (lo < sizeof(kNfcComp) / sizeof(kNfcComp[0]) && kNfcComp[lo][0] == a && kNfcComp[lo][1] == b) return kNfcComp[lo][2];
+    return 0;
+}
+// NFC of a run of code points: canonical decomposition, canonical ordering, canonical composition
+std::vector<uint32_t> nfc_run(const std::vector<uint32_t>& in) {
+    std::vector<uint32_t> d;
+    d.reserve(in.size() + 8);
+    for (uint32_t cp : in) nfc_decompose(cp, d);
+    std::vector<uint32_t> cc(d.size());
+    for (size_t i = 0; i < d.size(); ++i) cc[i] = nfc_ccc(d[i]);
+    for (size_t i = 1; i < d.size(); ++i) {                          // stable insertion sort inside every run of non-starters
+        if (cc[i] == 0) continue;
+        size_t j = i;
+        while (j > 0 && cc[j - 1] > cc[j]) { std::swap(cc[j - 1], cc[j]); std::swap(d[j - 1], d[j]); --j; }
+    }
+    std::vector<uint32_t> out;
+    out.reserve(d.size());
+    size_t starter = static_cast<size_t>(-1);
+    uint32_t last_cc = 0;
+    for (size_t i = 0; i < d.size(); ++i) {
+        // d[i] combines with the last starter unless something stands between them whose class is 0 or >= its own ("blocked")
+        if (starter != static_cast<size_t>(-1) && (out.size() - 1 == starter || last_cc < cc[i])) {
+            const uint32_t c = nfc_compose_pair(out[starter], d[i]);
+            if (c) { out[starter] = c; continue; }
+        }
+        if (cc[i] == 0) starter = out.size();
+        last_cc = cc[i];
+        out.push_back(d[i]);
+    }
+    return out;
+}
+// NFC of UTF-8 text. Bytes that are not valid UTF-8 pass through unchanged (and separate the runs); text without any code point
+// >= U+0300 (lead bytes < 0xCC) is already normalised and returned as it is.
+std::string nfc_utf8(const std::string& text) {
+    bool plain = true;
+    for (unsigned char c : text) if (c >= 0xCC) { plain = false; break; }
+    if (plain) return text;
+    const std::vector<CodePoint> t = decode_utf8(text);
+    std::string out;
+    out.reserve(text.size());
+    std::vector<uint32_t> run;
+    auto flush = [&]() {
+        if (run.empty()) return;
+        for (uint32_t cp : nfc_run(run)) put_utf8(out, cp);
+        run.clear();
+    };
+    for (size_t i = 0; i < t.size(); ++i) {
+        const size_t len = ((i + 1 < t.size()) ? t[i + 1].off : text.size()) - t[i].off;
+        if (t[i].cp == 0xFFFD && len == 1) { flush(); out.push_back(text[t[i].off]); }      // an invalid byte (a real U+FFFD is 3 bytes)
+        else run.push_back(t[i].cp);
+    }
+    flush();
+    return out;
+}
+
 TokenizerMode g_mode = (std::getenv("LEAXER_TOKENIZER") && std::string(std::getenv("LEAXER_TOKENIZER")) == "hf") ? TokenizerMode::HF
                                                                                                               : TokenizerMode::Reference;
 
@@ -384,12 +487,13 @@ std::vector<int32_t> Bpe::encode(const std::string& text) const {
     }
     std::vector<std::string> parts;
     if (g_mode == TokenizerMode::HF) {
-        const std::vector<CodePoint> t = decode_utf8(text);
+        const std::string norm = nfc_utf8(text);         // "normalizer": NFC, then the pre-tokeniser pattern, then byte-level BPE
+        const std::vector<CodePoint> t = decode_utf8(norm);
         size_t i = 0;
         while (i < t.size()) {
             const size_t m = hf_match_at(t, i);
-            const size_t b0 = t[i].off, b1 = (i + m < t.size()) ? t[i + m].off : text.size();
-            emit(text.substr(b0, b1 - b0), parts, hf_symbols().of, ids);
+            const size_t b0 = t[i].off, b1 = (i + m < t.size()) ? t[i + m].off : norm.size();
+            emit(norm.substr(b0, b1 - b0), parts, hf_symbols().of, ids);
             i += m;
         }
         return ids;
@@ -415,6 +519,7 @@ bool is_tokenizer_ready() { return instance().vocab_ok() && instance().merges_ok
 std::vector<int32_t> tokenize(const std::string& text) { return instance().encode(text); }
 std::string token_to_string(int32_t id) { return instance().text_of(id); }
 int32_t string_to_token(const std::string& token) { return instance().id_of(token); }
+std::string normalize_nfc(const std::string& text) { return nfc_utf8(text); }
 void set_tokenizer_mode(TokenizerMode mode) { g_mode = mode; }
 TokenizerMode tokenizer_mode() { return g_mode; }
 

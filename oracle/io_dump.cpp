@@ -113,5 +113,38 @@ int main(int argc, char** argv) {
         return 0;
     }
 #endif
+#ifdef LEAXER_HAS_NFC
+    // nfc FILE: every line of FILE (same escapes as tokhf) through normalize_nfc; output: the normalised lines, '\n'-terminated (a '\n'
+    // inside a text is written as the two characters backslash n again)
+    if (cmd == "nfc" && argc >= 3) {
+        FILE* f = std::fopen(argv[2], "rb");
+        if (!f) return 1;
+        std::string all;
+        char buf[4096];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) all.append(buf, got);
+        std::fclose(f);
+        size_t pos = 0;
+        while (pos < all.size()) {
+            size_t e = all.find('\n', pos);
+            if (e == std::string::npos) e = all.size();
+            std::string text;
+            for (size_t i = pos; i < e; ++i) {
+                if (all[i] == '\\' && i + 1 < e) {
+                    const char c = all[++i];
+                    text.push_back(c == 'n' ? '\n' : c == 'r' ? '\r' : c == 't' ? '\t' : c);
+                } else text.push_back(all[i]);
+            }
+            for (char c : normalize_nfc(text)) {
+                if (c == '\n') std::fputs("\\n", stdout);
+                else if (c == '\\') std::fputs("\\\\", stdout);
+                else std::fputc(c, stdout);
+            }
+            std::fputc('\n', stdout);
+            pos = e + 1;
+        }
+        return 0;
+    }
+#endif
     return 2;
 }

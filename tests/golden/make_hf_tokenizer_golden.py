@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """Golden vectors for the HF-faithful tokenizer mode (host/io/tokenizer.cpp), made with the HuggingFace `tokenizers`
 library -- the implementation the published Qwen2/Qwen3 tokenizer.json runs on. No real vocabulary exists offline, so a small
-byte-level BPE is TRAINED here on a multilingual corpus with exactly the published pipeline (Split on the Qwen2 pattern, isolated;
-ByteLevel without prefix space and without its own regex); what is pinned is the pipeline -- pre-tokenisation, byte alphabet, merge
-order -- not the vocabulary. Writes tests/golden/hf_tok/{vocab.json, merges.txt, cases.json}."""
+byte-level BPE is TRAINED here on a multilingual corpus with exactly the published pipeline (NFC normaliser; Split on the Qwen2
+pattern, isolated; ByteLevel without prefix space and without its own regex); what is pinned is the pipeline -- normalisation,
+pre-tokenisation, byte alphabet, merge order -- not the vocabulary. Writes tests/golden/hf_tok/{vocab.json, merges.txt, cases.json}."""
 import json
 import os
 import random
 
-from tokenizers import Regex, Tokenizer, models, pre_tokenizers, trainers
+from tokenizers import Regex, Tokenizer, models, normalizers, pre_tokenizers, trainers
 
 QWEN2_PATTERN = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+")
 
@@ -33,6 +33,10 @@ CASES = [
     "😀😃", "𝒳𝒴𝒵 math", "©®™", "tab\there", "line\nbreak", "crlf\r\nhere", "\n\n\n", "  \n  x", "x \n", "x  ", "x   y", " ", "  ", "\t",
     "a_b_c", "C++", "$100", "50%", "http://example.org/path?q=1", "mixed 中文 and English 123", "!!!\n", "?!\r\n\r\nnext", " !x", "  !x",
     "٣ مرحبا", "नमस्ते १२३", " nbsp　ideographic", " ls", "á combining", "",
+    # not in NFC on input: combining sequences, conjoining jamo, singletons (the Angstrom / Kelvin / Ohm signs), marks out of canonical
+    # order, a composition exclusion (stays decomposed), a compatibility ligature (NFC leaves it alone)
+    "cafe\u0301 nai\u0308ve", "\u1112\u1161\u11ab\u1100\u1173\u11af", "\u212b \u212a \u2126", "q\u0307\u0323 d\u0323\u0307", "\u0915\u093c \u0958",
+    "\ufb01n", "A\u030a\u0301", "\u30ab\u3099\u30cf\u309a", "o\u0302\u0303 \u1ed7", "\u0627\u0653",
 ]
 
 
@@ -40,6 +44,7 @@ def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hf_tok")
     os.makedirs(out, exist_ok=True)
     tok = Tokenizer(models.BPE())
+    tok.normalizer = normalizers.NFC()                    # tokenizer.json of the published checkpoints: "normalizer": {"type": "NFC"}
     tok.pre_tokenizer = pre_tokenizers.Sequence([
         pre_tokenizers.Split(Regex(QWEN2_PATTERN), behavior="isolated", invert=False),
         pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=False)])
