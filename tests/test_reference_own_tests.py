@@ -1,0 +1,44 @@
+"""The reference's OWN test programs (tests/test_wav_reader.cpp, test_mel.cpp, test_onnx.cpp, test_tokenizer.cpp, test_tokenizer_real.cpp;
+wired up in its CMakeLists.txt:117-135) compiled UNMODIFIED against this repo's host tree -- host/tts_onnx.h, host/io/*.h,
+libleaxer_tts_host.so -- instead of the reference's src/: the drop-in claim of INTEGRATION.md section A at the source level. They must build
+and exit 0 exactly as they do in the reference's CI (the tokenizer programs skip their vocabulary-dependent cases when vocab.json /
+merges.txt are absent, test_onnx skips the engine load without a model directory; the constants, WAV reader and mel cases run).
+Needs /root/reference (this container); skipped on boxes without it. No GPU: nothing here calls into the CUDA library."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+HOST = os.path.join(ROOT, "leaxer-qwen3-tts_b200", "host")
+CSRC = os.path.join(ROOT, "leaxer-qwen3-tts_b200", "csrc")
+PROGRAMS = ["test_wav_reader", "test_mel", "test_onnx", "test_tokenizer", "test_tokenizer_real"]
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tests")), reason="reference sources not present on this box")
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    for d in (CSRC, HOST):
+        r = subprocess.run(["make", "-s", "-C", d], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-2000:]
+    return os.path.join(HOST, "libleaxer_tts_host.so")
+
+
+@pytest.mark.parametrize("prog", PROGRAMS)
+def test_reference_test_program_builds_and_passes(host_lib, tmp_path, prog):
+    exe = str(tmp_path / prog)
+    cmd = ["g++", "-std=c++17", "-O1", "-w", "-I" + HOST, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(REF, "tests"),
+           "-o", exe, os.path.join(REF, "tests", prog + ".cpp"), "-L" + HOST, "-lleaxer_tts_host", "-L" + CSRC, "-llqt_b200",
+           "-Wl,-rpath," + HOST, "-Wl,-rpath," + CSRC]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    r = subprocess.run([exe], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    out = r.stdout
+    assert "FAIL" not in out.replace("Failed: 0", ""), out[-3000:]
+    if prog in ("test_wav_reader", "test_mel"):                      # these run completely (no external files)
+        assert "Failed: 0" in out and "Passed: 0" not in out, out[-2000:]
+    if prog == "test_onnx":
+        assert "PASS: Config values correct" in out and "PASS: Language to codec ID mapping" in out, out[-2000:]
