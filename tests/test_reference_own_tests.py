@@ -42,3 +42,32 @@ def test_reference_test_program_builds_and_passes(host_lib, tmp_path, prog):
         assert "Failed: 0" in out and "Passed: 0" not in out, out[-2000:]
     if prog == "test_onnx":
         assert "PASS: Config values correct" in out and "PASS: Language to codec ID mapping" in out, out[-2000:]
+
+
+def test_reference_cli_source_builds_against_the_host_library(host_lib, tmp_path):
+    """src/main_onnx.cpp -- the reference's command-line program -- UNMODIFIED over this repo's tts_onnx.h and libraries: it links, prints its
+    usage, and takes the reference's own error exits (missing arguments, missing model directory, engine not ready: on this GPU-less box
+    TTSEngine reports why instead of throwing, src/tts_onnx.cpp:100-104)."""
+    exe = str(tmp_path / "ref_cli")
+    # compiled through a symlink: `#include "tts_onnx.h"` looks next to the including file first, and next to the original lies the header
+    # this repo's host/tts_onnx.h REPLACES (INTEGRATION.md section A) -- mixing that header with this library is a layout mismatch
+    src = tmp_path / "main_onnx.cpp"
+    os.symlink(os.path.join(REF, "src", "main_onnx.cpp"), src)
+    cmd = ["g++", "-std=c++17", "-O1", "-w", "-I" + HOST, "-I" + os.path.join(ROOT, "include"), "-o", exe, str(src),
+           "-L" + HOST, "-lleaxer_tts_host", "-L" + CSRC, "-llqt_b200", "-Wl,-rpath," + HOST, "-Wl,-rpath," + CSRC]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+    def run(*args):
+        return subprocess.run([exe, *args], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+
+    r = run("--help")
+    assert r.returncode == 0 and "--max-tokens" in r.stdout and "--ref" in r.stdout
+    r = run("-p", "hi")
+    assert r.returncode == 1 and "--model and --prompt are required" in r.stdout
+    r = run("-m", str(tmp_path / "nope"), "-p", "hi")
+    assert r.returncode == 1 and "model directory not found" in r.stdout
+    empty = tmp_path / "empty_model_dir"
+    empty.mkdir()
+    r = run("-m", str(empty), "-p", "hi", "-o", str(tmp_path / "out.wav"))
+    assert r.returncode == 1 and "Error:" in r.stdout and not (tmp_path / "out.wav").exists(), r.stdout[-2000:]
