@@ -136,3 +136,23 @@ def test_device_log_mel_matches_reference(tiny_engine, host_env, tmp_path):
     ref = orc.extract_speaker_embedding(m, gold)
     got = tiny_engine.speaker_embed_audio(audio)
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-4
+
+
+def test_reference_cli_binary_over_this_engine(tiny_dir, host_env, tmp_path):
+    """oracle/_ref/ref_main_b200 is the REFERENCE's command-line program -- src/main_onnx.cpp, unmodified, compiled by oracle/Makefile where
+    it lies -- linked against this repo's tts_onnx.h, libleaxer_tts_host.so and liblqt_b200.so: the drop-in at the source level. For the same
+    arguments and Philox seed ($LEAXER_SEED: the reference's program has no --seed flag) it must write the same WAV, byte for byte, as this
+    repo's own CLI, and print the reference's progress lines (src/main_onnx.cpp:130-190)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_main_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_main_b200 was not built (needs the reference sources at build time)")
+    args = ["-m", tiny_dir, "-p", "hello world speech testing 123", "--lang", "en", "--temp", "0.7", "--top-k", "20", "--top-p", "0.9", "--max-tokens", "6"]
+    a, b = tmp_path / "ref_cli.wav", tmp_path / "own_cli.wav"
+    r1 = subprocess.run([exe] + args + ["-o", str(a)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                        env=dict(os.environ, LEAXER_SEED="4242"))
+    assert r1.returncode == 0, r1.stderr
+    assert "Synthesizing..." in r1.stdout
+    r2 = subprocess.run([host_env["cli"]] + args + ["--seed", "4242", "-o", str(b)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r2.returncode == 0, r2.stderr
+    wa, wb = open(a, "rb").read(), open(b, "rb").read()
+    assert len(wa) == 44 + 6 * 1920 * 2 and wa == wb
