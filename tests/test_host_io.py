@@ -80,3 +80,35 @@ def test_cli_argument_handling(tmp_path):
     r = subprocess.run([cli, "-m", str(tmp_path), "-p", "hi", "-o", str(tmp_path / "sub" / "o.wav")],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Error:" in r.stderr and "Model:" in r.stdout and (tmp_path / "sub").is_dir()
+
+
+def test_file_parsers_survive_fuzzing_under_asan(tmp_path):
+    """host/io/wav_reader.cpp (the --ref clip of the clone path) and the tokenizer's vocab.json / merges.txt loaders compiled with
+    -fsanitize=address,undefined into tests/native/host_io_fuzz.cpp and fed mutated, truncated and shuffled copies of well-formed files:
+    every one is read or rejected; an out-of-bounds access, an overflow or a crash aborts the driver."""
+    import shutil
+    import subprocess
+    import numpy as np
+    import io_cases
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    io_dir = os.path.join(ROOT, "leaxer-qwen3-tts_b200", "host", "io")
+    exe = str(tmp_path / "host_io_fuzz")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I" + io_dir, "-o", exe,
+                        os.path.join(ROOT, "tests", "native", "host_io_fuzz.cpp"), os.path.join(io_dir, "wav_reader.cpp"), os.path.join(io_dir, "tokenizer.cpp")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0 and "sanitize" in r.stdout:
+        pytest.skip("sanitizer runtime not available: " + r.stdout[-200:])
+    assert r.returncode == 0, r.stdout[-2000:]
+    t = np.arange(2400) / 24000.0
+    mono, stereo = str(tmp_path / "mono.wav"), str(tmp_path / "stereo.wav")
+    io_cases._wav(mono, 1, 1, 24000, 16, ((0.4 * np.sin(2 * np.pi * 220 * t)) * 32767).astype("<i2").tobytes())
+    io_cases._wav(stereo, 3, 2, 44100, 32, (0.4 * np.sin(2 * np.pi * 220 * np.arange(4800) / 44100.0)).astype("<f4").tobytes())
+    vp, mp = io_cases.write_tokenizer_files(str(tmp_path / "tok"))
+    for what, src, iters, seed in (("wav", mono, 5000, 1), ("wav", stereo, 5000, 2), ("vocab", vp, 3000, 3), ("merges", mp, 3000, 4)):
+        r = subprocess.run([exe, what, src, str(tmp_path / "scratch.bin"), str(iters), str(seed)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+        last = r.stdout.decode("utf-8", "replace").strip().splitlines()[-1:] or [""]
+        assert r.returncode == 0 and last[0].startswith("ok "), (what, r.returncode, r.stderr.decode("utf-8", "replace")[-3000:])
+        ok, bad = (int(x) for x in last[0].split()[1:3])
+        assert ok + bad == iters and ok > 0 and bad > 0, (what, ok, bad)
